@@ -1,0 +1,353 @@
+"""CPU oracle: PyTorch restatements of the reference's column-emulator models, losses and optimizer steps.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Every class cites the reference file:line it follows
+(paths relative to the reference checkout).  All weights use the *Keras* convention -- Dense kernel stored
+(in, out), Conv1D kernel stored (k, C_in, C_out), channels-last activations -- except ``HSRRef`` which restates a
+PyTorch model and therefore keeps ``torch.nn.Linear``'s (out, in).
+
+PARITY STATUS: MLPRef / EDRef / CNNRef / keras_adam_step / cyclical_lr are UNPINNED (tensorflow is not installable
+here; the reference ships no golden outputs) -- only parameter/FLOP counts are pinned.  HSRRef is PINNED against the
+reference's own hsr.py (tests/golden/hsr_small.npz; tests/test_oracle_pinning.py).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+# --------------------------------------------------------------------------------------------------------------
+# activations (Keras layer semantics)
+# --------------------------------------------------------------------------------------------------------------
+
+def activation(name: str, x: torch.Tensor, alpha: float = 0.15) -> torch.Tensor:
+    """keras.layers.ReLU / ELU(alpha=1) / LeakyReLU(alpha) -- baseline_v1/hpo_baseline_v1.py:82-87,91-96."""
+    if name in ("none", "linear"):
+        return x
+    if name == "relu":
+        return torch.relu(x)
+    if name == "elu":
+        return F.elu(x, alpha=1.0)
+    if name == "leakyrelu":
+        return F.leaky_relu(x, negative_slope=alpha)
+    raise ValueError(f"unknown activation {name!r}")
+
+
+def glorot_uniform(fan_in: int, fan_out: int, shape: Sequence[int], gen: torch.Generator,
+                   dtype=torch.float32) -> torch.Tensor:
+    """Keras default kernel initializer: U(-l, l), l = sqrt(6 / (fan_in + fan_out))."""
+    limit = math.sqrt(6.0 / (fan_in + fan_out))
+    return ((torch.rand(*shape, generator=gen, dtype=torch.float64) * 2.0 - 1.0) * limit).to(dtype)
+
+
+def _bf16_round(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# MLP_v1  (Keras functional model)
+# --------------------------------------------------------------------------------------------------------------
+
+class MLPRef:
+    """Restatement of ``MyHyperModel.build`` -- baseline_models/MLP/training/HPO/baseline_v1/
+    hpo_baseline_v1.py:75-103 (identical graph: step2_retrain/step2_retrain.py:95-126).
+
+        x -> [Dense(units_k) -> act] * n_layers -> Dense(128) -> act -> concat(Dense(120, linear), Dense(8, relu))
+
+    Defaults are the shipped best trial (step1_results.csv lot-147/trial_0027): units [768,640,512,640,640],
+    LeakyReLU(alpha=.15).  ``params`` is the Keras ``model.get_weights()`` list:
+    [W0 (in,out), b0, ..., W_u (h,128), b_u, W_lin (128,120), b_lin, W_relu (128,8), b_relu].
+    """
+
+    def __init__(self, units: Sequence[int] = (768, 640, 512, 640, 640), act: str = "leakyrelu",
+                 alpha: float = 0.15, in_dim: int = 124, out_lin: int = 120, out_relu: int = 8,
+                 seed: int = 0, dtype: torch.dtype = torch.float32):
+        self.units, self.act, self.alpha = list(units), act, alpha
+        self.in_dim, self.out_lin, self.out_relu = in_dim, out_lin, out_relu
+        self.dtype = dtype
+        gen = torch.Generator().manual_seed(seed)
+        dims = [in_dim] + self.units + [out_lin + out_relu]
+        self.params: List[torch.Tensor] = []
+        for k, n in zip(dims[:-1], dims[1:]):
+            self.params += [glorot_uniform(k, n, (k, n), gen, dtype), torch.zeros(n, dtype=dtype)]
+        h = out_lin + out_relu
+        self.params += [glorot_uniform(h, out_lin, (h, out_lin), gen, dtype), torch.zeros(out_lin, dtype=dtype)]
+        self.params += [glorot_uniform(h, out_relu, (h, out_relu), gen, dtype), torch.zeros(out_relu, dtype=dtype)]
+        for p in self.params:
+            p.requires_grad_(True)
+
+    # -- bookkeeping -------------------------------------------------------------------------------------------
+    def num_parameters(self) -> int:
+        return sum(p.numel() for p in self.params)
+
+    def flops_per_sample(self) -> int:
+        """2*MAC + bias adds, the count keras-flops reports (FLOP_calculation.ipynb cells 5-6: 3 503 488)."""
+        return sum(2 * w.shape[0] * w.shape[1] + w.shape[1] for w in self.params[0::2])
+
+    def randomize_biases(self, seed: int = 1, scale: float = 0.05) -> None:
+        """Keras biases start at zero; tests perturb them so that a bias bug cannot hide."""
+        gen = torch.Generator().manual_seed(seed)
+        with torch.no_grad():
+            for b in self.params[1::2]:
+                b.copy_((torch.rand(b.shape, generator=gen, dtype=torch.float64) * 2 - 1).to(self.dtype) * scale)
+
+    # -- graph -------------------------------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, emulate_bf16: bool = False, return_hidden: bool = False):
+        """``emulate_bf16`` rounds the GEMM operands (weights, layer inputs) to bf16 but accumulates in fp32 --
+        the numerics of the tensor-core path -- so that the bf16 CUDA mode can be checked tightly."""
+        rnd = _bf16_round if emulate_bf16 else (lambda t: t)
+        p = self.params
+        n_hidden = len(self.units) + 1                       # hidden layers + the Dense(128) "upper output" layer
+        h = rnd(x.to(self.dtype))
+        hidden = []
+        for i in range(n_hidden):
+            h = rnd(activation(self.act, h @ rnd(p[2 * i]) + p[2 * i + 1], self.alpha))
+            hidden.append(h)
+        w_lin, b_lin, w_relu, b_relu = p[2 * n_hidden: 2 * n_hidden + 4]
+        out = torch.cat([h @ rnd(w_lin) + b_lin, torch.relu(h @ rnd(w_relu) + b_relu)], dim=1)
+        return (out, hidden) if return_hidden else out
+
+    __call__ = forward
+
+
+# --------------------------------------------------------------------------------------------------------------
+# ED  (Keras encoder-decoder MLP)
+# --------------------------------------------------------------------------------------------------------------
+
+def ed_widths(intermediate_dim: int = 463, latent_dim: int = 5, out_dim: int = 128) -> List[int]:
+    """Layer widths of baseline_models/ED/training/ClimSIM_ED_1_3_train.py:56-78.  The script passes floats such
+    as ``intermediate_dim/2`` to ``Dense``; Keras applies ``int()`` (truncation): 231, 115, 57, 28."""
+    d = intermediate_dim
+    enc = [d, d, int(d / 2), int(d / 4), int(d / 8), int(d / 16), latent_dim]
+    dec = [int(d / 16), int(d / 8), int(d / 4), int(d / 2), d, d, out_dim]
+    return enc + dec
+
+
+class EDRef:
+    """ReLU MLP 124->463->463->231->115->57->28->5->28->57->115->231->463->463->128(ELU);
+    ClimSIM_ED_1_3_train.py:56-92.  ``params`` = [W0, b0, W1, b1, ...] Keras order/layout."""
+
+    def __init__(self, in_dim: int = 124, seed: int = 0, dtype: torch.dtype = torch.float32):
+        gen = torch.Generator().manual_seed(seed)
+        dims = [in_dim] + ed_widths()
+        self.dims, self.dtype = dims, dtype
+        self.params: List[torch.Tensor] = []
+        for k, n in zip(dims[:-1], dims[1:]):
+            self.params += [glorot_uniform(k, n, (k, n), gen, dtype), torch.zeros(n, dtype=dtype)]
+        for p in self.params:
+            p.requires_grad_(True)
+
+    def num_parameters(self) -> int:
+        return sum(p.numel() for p in self.params)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        h = x.to(self.dtype)
+        n = len(self.params) // 2
+        for i in range(n):
+            z = h @ self.params[2 * i] + self.params[2 * i + 1]
+            h = F.elu(z, alpha=1.0) if i == n - 1 else torch.relu(z)
+        return h
+
+    __call__ = forward
+
+
+# --------------------------------------------------------------------------------------------------------------
+# CNN  (Keras ResNet-1D)
+# --------------------------------------------------------------------------------------------------------------
+
+def conv1d_same_cl(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """Keras ``Conv1D(padding='same')`` on channels-last input.  x (B, L, Cin); w (k, Cin, Cout); b (Cout).
+    out[b, l, co] = sum_{t, ci} x[b, l + t - (k-1)//2, ci] * w[t, ci, co] + b[co], zero outside [0, L)."""
+    k = w.shape[0]
+    y = F.conv1d(x.transpose(1, 2), w.permute(2, 1, 0), b, padding=(k - 1) // 2)
+    return y.transpose(1, 2)
+
+
+class CNNRef:
+    """Restatement of ``CNNHyperModel.build`` -- baseline_models/CNN/training/hpo_train.py:131-200.
+
+    12 x { Conv1D(406,k=3,same) -> ReLU -> Dropout -> Conv1D(406,k=3,same) -> ReLU -> Dropout -> + Conv1D(406,k=1)(block input) }
+    -> Conv1D(10, k=1, ELU) -> per-level Dense(2, linear) || Dense(8, relu) -> (B, 60, 10).
+    Dropout is evaluated in inference mode (p = 0): TF's dropout RNG cannot be reproduced.
+    ``params`` order = Keras ``get_weights()``: per block [Wc1, bc1, Wc2, bc2, Wres, bres], then [Wout, bout,
+    Wlin, blin, Wrelu, brelu].
+    """
+
+    def __init__(self, depth: int = 12, width: int = 406, kernel: int = 3, in_ch: int = 6, out_ch: int = 10,
+                 out_lin: int = 2, seed: int = 0, dtype: torch.dtype = torch.float32):
+        self.depth, self.width, self.kernel = depth, width, kernel
+        self.in_ch, self.out_ch, self.out_lin, self.dtype = in_ch, out_ch, out_lin, dtype
+        gen = torch.Generator().manual_seed(seed)
+
+        def conv(k, ci, co):
+            return [glorot_uniform(k * ci, k * co, (k, ci, co), gen, dtype), torch.zeros(co, dtype=dtype)]
+
+        def dense(ci, co):
+            return [glorot_uniform(ci, co, (ci, co), gen, dtype), torch.zeros(co, dtype=dtype)]
+
+        self.params: List[torch.Tensor] = []
+        c = in_ch
+        for _ in range(depth):
+            self.params += conv(kernel, c, width) + conv(kernel, width, width) + conv(1, c, width)
+            c = width
+        self.params += conv(1, c, out_ch) + dense(out_ch, out_lin) + dense(out_ch, out_ch - out_lin)
+        for p in self.params:
+            p.requires_grad_(True)
+
+    def num_parameters(self) -> int:
+        return sum(p.numel() for p in self.params)
+
+    def randomize_biases(self, seed: int = 1, scale: float = 0.05) -> None:
+        gen = torch.Generator().manual_seed(seed)
+        with torch.no_grad():
+            for b in self.params[1::2]:
+                b.copy_((torch.rand(b.shape, generator=gen, dtype=torch.float64) * 2 - 1).to(self.dtype) * scale)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        p = self.params
+        h = x.to(self.dtype)
+        prev = h
+        for i in range(self.depth):
+            wc1, bc1, wc2, bc2, wr, br = p[6 * i: 6 * i + 6]
+            h = torch.relu(conv1d_same_cl(h, wc1, bc1))
+            h = torch.relu(conv1d_same_cl(h, wc2, bc2))
+            h = h + conv1d_same_cl(prev, wr, br)
+            prev = h
+        wo, bo, wl, bl, wrl, brl = p[6 * self.depth: 6 * self.depth + 6]
+        h = F.elu(conv1d_same_cl(h, wo, bo), alpha=1.0)
+        return torch.cat([h @ wl + bl, torch.relu(h @ wrl + brl)], dim=-1)
+
+    __call__ = forward
+
+
+# --------------------------------------------------------------------------------------------------------------
+# HSR  (PyTorch model in the reference)
+# --------------------------------------------------------------------------------------------------------------
+
+class HSRMLPRef(torch.nn.Module):
+    """Restatement of ``MLP`` -- baseline_models/HSR/training/hsr.py:14-35:
+    layers x [Linear -> LayerNorm(eps 1e-5) -> Dropout(p) -> ReLU] -> Linear.  Same ``state_dict`` keys as the
+    reference (``linear{i}.0.weight`` ... ``final_linear.weight``) so the shipped ``final_hsr.cp`` loads."""
+
+    def __init__(self, in_dims: int, out_dims: int, hidden_dims: int = 512, layers: int = 1, dropout: float = 0.0):
+        super().__init__()
+        self.n_layers = layers
+        for i in range(layers):
+            self.add_module("linear%d" % i, torch.nn.Sequential(
+                torch.nn.Linear(in_dims if i == 0 else hidden_dims, hidden_dims),
+                torch.nn.LayerNorm(hidden_dims),
+                torch.nn.Dropout(p=dropout)))
+        self.final_linear = torch.nn.Linear(hidden_dims, out_dims)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        for i in range(self.n_layers):
+            x = torch.relu(getattr(self, "linear%d" % i)(x))
+        return self.final_linear(x)
+
+
+class HSRRef(torch.nn.Module):
+    """Restatement of ``HeteroskedasticRegression`` -- hsr.py:38-67 (forward) and :126-138 (loss)."""
+
+    def __init__(self, in_dims: int = 124, out_dims: int = 128, hidden_dims: int = 512, layers: int = 1,
+                 dropout: float = 0.0):
+        super().__init__()
+        self.mean = HSRMLPRef(in_dims, out_dims, hidden_dims, layers, dropout)
+        self.logprec = HSRMLPRef(in_dims, out_dims, hidden_dims, layers, dropout)
+
+    def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self.mean(x), self.logprec(x)
+
+    @staticmethod
+    def loss(mu: torch.Tensor, logprec: torch.Tensor, y: torch.Tensor, mle: bool) -> torch.Tensor:
+        """hsr.py:128-138: MSE for the first third of the epochs, then Gaussian NLL; clipped to +-1e5."""
+        if mle:
+            loss = (torch.exp(logprec) * (y - mu) ** 2 - logprec).mean()
+        else:
+            loss = ((y - mu) ** 2).mean()
+        return torch.clip(loss, min=-1e5, max=1e5)
+
+    @staticmethod
+    def weight_decays(gamma: float = 0.022, rho: Optional[float] = None) -> Tuple[float, float]:
+        """hsr.py:100-107: per-group L2 weight decay (alpha for the mean net, beta for the log-precision net)."""
+        rho = rho if rho is not None else 1 - gamma
+        return (1 - rho) / rho * gamma, (1 - rho) / rho * (1 - gamma)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# losses
+# --------------------------------------------------------------------------------------------------------------
+
+def mse(y_true: torch.Tensor, y_pred: torch.Tensor) -> torch.Tensor:
+    """Keras ``loss='mse'`` (hpo_baseline_v1.py:127-129): mean over the feature axis, then over the batch
+    == global mean of the squared error."""
+    return ((y_pred - y_true) ** 2).mean(dim=-1).mean()
+
+
+def weighted_mse(y_true: torch.Tensor, y_pred: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """mean_ij( w_j * (yhat_ij - y_ij)^2 ); w == 1 reproduces ``mse`` (SURVEY.md section 0 resolution)."""
+    return (w * (y_pred - y_true) ** 2).mean()
+
+
+def mse_adjusted(y_true: torch.Tensor, y_pred: torch.Tensor) -> torch.Tensor:
+    """baseline_models/CNN/training/hpo_train.py:114-116."""
+    se = (y_pred - y_true) ** 2
+    return se[:, :, 0:2].mean() * (120 / 128) + se[:, :, 2:10].mean() * (8 / 128)
+
+
+def mae_adjusted(y_true: torch.Tensor, y_pred: torch.Tensor) -> torch.Tensor:
+    """baseline_models/CNN/training/hpo_train.py:119-121."""
+    ae = (y_pred - y_true).abs()
+    return ae[:, :, 0:2].mean() * (120 / 128) + ae[:, :, 2:10].mean() * (8 / 128)
+
+
+def cnn_loss_weights(levels: int = 60, dtype=torch.float32) -> torch.Tensor:
+    """(60,10) weight w such that sum_{l,c} w[l,c]*e[b,l,c] averaged over b equals ``*_adjusted`` of e:
+    1/128 per profile entry, 1/(128*60) per level-replicated scalar entry."""
+    w = torch.empty(levels, 10, dtype=dtype)
+    w[:, 0:2] = (120 / 128) / (levels * 2)
+    w[:, 2:10] = (8 / 128) / (levels * 8)
+    return w
+
+
+# --------------------------------------------------------------------------------------------------------------
+# optimizers / schedules (Keras + tfa semantics)
+# --------------------------------------------------------------------------------------------------------------
+
+def cyclical_lr(step: int, initial_lr: float = 2.5e-4, max_lr: float = 2.5e-3, step_size: float = 2.0,
+                scale_mode: str = "cycle") -> float:
+    """tfa.optimizers.CyclicalLearningRate as configured at hpo_baseline_v1.py:105-114
+    (scale_fn = 1/2**(x-1), scale_mode='cycle').  Closed form of tensorflow-addons 0.19
+    ``CyclicalLearningRate.__call__``."""
+    cycle = math.floor(1 + step / (2 * step_size))
+    x = abs(step / step_size - 2 * cycle + 1)
+    mode_step = cycle if scale_mode == "cycle" else step
+    return initial_lr + (max_lr - initial_lr) * max(0.0, 1 - x) * (1.0 / (2.0 ** (mode_step - 1)))
+
+
+def keras_adam_step(params: List[torch.Tensor], grads: List[torch.Tensor], m: List[torch.Tensor],
+                    v: List[torch.Tensor], t: int, lr: float, beta1: float = 0.9, beta2: float = 0.999,
+                    eps: float = 1e-7) -> None:
+    """keras.optimizers.Adam (2.11) ``update_step``; defaults as used at hpo_baseline_v1.py:116-117:
+        alpha = lr * sqrt(1 - b2^t) / (1 - b1^t);  m += (g - m)(1 - b1);  v += (g^2 - v)(1 - b2);
+        w -= alpha * m / (sqrt(v) + eps)            (epsilon = 1e-7, *outside* the bias correction)."""
+    alpha = lr * math.sqrt(1 - beta2 ** t) / (1 - beta1 ** t)
+    with torch.no_grad():
+        for p, g, mi, vi in zip(params, grads, m, v):
+            mi.add_((g - mi) * (1 - beta1))
+            vi.add_((g * g - vi) * (1 - beta2))
+            p.sub_(alpha * mi / (vi.sqrt() + eps))
+
+
+def torch_adam_step(params: List[torch.Tensor], grads: List[torch.Tensor], m: List[torch.Tensor],
+                    v: List[torch.Tensor], t: int, lr: float, beta1: float = 0.9, beta2: float = 0.999,
+                    eps: float = 1e-8, weight_decay: float = 0.0) -> None:
+    """torch.optim.Adam (the optimizer the reference's HSR trainer builds, hsr.py:109-112) with L2
+    ``weight_decay`` folded into the gradient; restated so the per-group decay can be checked elementwise."""
+    bc1, bc2 = 1 - beta1 ** t, 1 - beta2 ** t
+    with torch.no_grad():
+        for p, g, mi, vi in zip(params, grads, m, v):
+            g = g + weight_decay * p if weight_decay != 0.0 else g
+            mi.mul_(beta1).add_(g, alpha=1 - beta1)
+            vi.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+            p.sub_((lr / bc1) * mi / (vi.sqrt() / math.sqrt(bc2) + eps))

@@ -1,0 +1,196 @@
+"""Pins the CPU oracle to the reference: golden vectors produced by running the reference's own code
+(tests/golden/make_golden.py) and the known answers the reference holds."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import data_utils_ref as R
+from oracle import models as M
+
+
+@pytest.fixture(scope="module")
+def du(golden_dir):
+    return np.load(os.path.join(golden_dir, "data_utils.npz"))
+
+
+@pytest.fixture(scope="module")
+def hsr(golden_dir):
+    return np.load(os.path.join(golden_dir, "hsr_small.npz"))
+
+
+# ---------------------------------------------------------------- known answers held by the reference
+def test_mlp_v1_param_count_matches_step1_results_csv():
+    # baseline_v1/step1_analysis/step1_results.csv, lot-147 trial_0027: num_parameters = 1753472
+    assert M.MLPRef().num_parameters() == 1_753_472
+
+
+def test_mlp_v1_flops_match_flop_notebook():
+    # step3_prediction/FLOP_calculation.ipynb cells 5-6: 3 503 488 FLOP / sample
+    assert M.MLPRef().flops_per_sample() == 3_503_488
+
+
+def test_cnn_param_count():
+    # block1 505 470 + 11 x 1 155 070 + 4 070 + 110
+    assert M.CNNRef().num_parameters() == 505_470 + 11 * 1_155_070 + 4_070 + 110
+
+
+def test_ed_widths():
+    assert M.ed_widths() == [463, 463, 231, 115, 57, 28, 5, 28, 57, 115, 231, 463, 463, 128]
+
+
+def test_hsr_param_count_matches_shipped_checkpoint(golden_dir):
+    g = np.load(os.path.join(golden_dir, "hsr_final_cp_outputs.npz"))
+    net = M.HSRRef(124, 128, hidden_dims=1024, layers=4)
+    assert sum(p.numel() for p in net.parameters()) == int(g["n_params"]) == 6_832_384
+
+
+def test_cyclical_lr_closed_form():
+    # triangular2-style schedule: starts at INIT_LR, peaks at MAX_LR after step_size, halves each cycle
+    f = lambda s: M.cyclical_lr(s, 2.5e-4, 2.5e-3, step_size=10)
+    assert f(0) == pytest.approx(2.5e-4)
+    assert f(10) == pytest.approx(2.5e-3)
+    assert f(20) == pytest.approx(2.5e-4)
+    assert f(30) == pytest.approx(2.5e-4 + (2.5e-3 - 2.5e-4) / 2)
+    assert f(50) == pytest.approx(2.5e-4 + (2.5e-3 - 2.5e-4) / 4)
+
+
+# ---------------------------------------------------------------- data_utils restatement vs the reference class
+def test_save_norm_vectors(du):
+    assert du["inp_sub"].shape == (124,) and du["inp_div"].shape == (124,) and du["out_scale"].shape == (128,)
+    assert du["inp_div"][60] == 0.0          # the max == min level built into the fixture
+
+
+def test_normalize_nan_inf_rule(du):
+    xn = R.normalize_input(du["x_raw"], du["inp_sub"], du["inp_div"])
+    assert xn.dtype == np.float32
+    np.testing.assert_array_equal(xn, du["x_renorm"])
+    assert np.all(xn[:, 60] == 0)
+
+
+def test_pressure_thickness(du):
+    dp = R.pressure_thickness(du["x_norm"], float(du["ps_mean"]), float(du["ps_max"]), float(du["ps_min"]),
+                              du["hyai"], du["hybi"], 1e5, int(du["ncol"]))
+    np.testing.assert_array_equal(dp, du["dp_val"])
+
+
+def test_output_weighting_and_just_weights(du):
+    dp = du["dp_val"]
+    for key, arr in (("tw_", du["target"]), ("pw_", du["pred"])):
+        got = R.output_weighting(arr, dp, du["out_scale"], du["area_wgt"])
+        for v in R.V1_OUTPUTS:
+            np.testing.assert_array_equal(got[v], du[key + v])
+    w = R.output_weights(dp, du["out_scale"], du["area_wgt"])
+    np.testing.assert_array_equal(w, du["just_weights"])
+
+
+def test_metrics(du):
+    fns = {"MAE": R.calc_mae, "RMSE": R.calc_rmse, "R2": R.calc_r2, "bias": R.calc_bias}
+    for v in R.V1_OUTPUTS:
+        for name, f in fns.items():
+            np.testing.assert_allclose(f(du["pw_" + v], du["tw_" + v]), du[f"{name}_{v}"], rtol=1e-14, atol=0)
+    np.testing.assert_allclose(R.calc_crps(du["crps_samples"], du["tw_ptend_t"]), du["crps"], rtol=1e-13)
+
+
+def test_cnn_reshapes(du):
+    np.testing.assert_array_equal(R.reshape_input_for_cnn(du["x_norm"]), du["cnn_in"])
+    np.testing.assert_array_equal(R.reshape_target_for_cnn(du["target"]), du["cnn_tgt"])
+    np.testing.assert_array_equal(R.reshape_target_from_cnn(du["cnn_pred"]), du["cnn_pred_flat"])
+
+
+# ---------------------------------------------------------------- HSR restatement vs the reference module
+def _load_hsr(hsr, prefix):
+    net = M.HSRRef(124, 128, hidden_dims=32, layers=2)
+    sd = {k[len(prefix):]: torch.from_numpy(hsr[k]) for k in hsr.files if k.startswith(prefix)}
+    missing = net.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return net
+
+
+def test_hsr_forward_losses_grads(hsr):
+    net = _load_hsr(hsr, "init::")
+    x, y = torch.from_numpy(hsr["x0"]), torch.from_numpy(hsr["y0"])
+    mu, lp = net(x)
+    np.testing.assert_allclose(mu.detach().numpy(), hsr["mu"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(lp.detach().numpy(), hsr["logprec"], rtol=1e-6, atol=1e-7)
+    for mode in ("mse", "mle"):
+        net.zero_grad()
+        mu, lp = net(x)
+        loss = M.HSRRef.loss(mu, lp, y, mle=(mode == "mle"))
+        loss.backward()
+        assert loss.item() == pytest.approx(float(hsr[f"loss_{mode}"]), rel=1e-6)
+        for k, p in net.named_parameters():
+            key = f"grad_{mode}::{k}"
+            if key in hsr.files:
+                np.testing.assert_allclose(p.grad.numpy(), hsr[key], rtol=1e-5, atol=1e-8)
+
+
+def test_hsr_training_loop_matches_reference_trainer(hsr):
+    """3 epochs x 2 batches of the reference's own ``trainer`` (MSE phase, then NLL phase; Adam + per-group L2)."""
+    net = _load_hsr(hsr, "init::")
+    alpha, beta = M.HSRRef.weight_decays(gamma=0.022)
+    groups = [(list(net.mean.parameters()), alpha), (list(net.logprec.parameters()), beta)]
+    state = [([torch.zeros_like(p) for p in ps], [torch.zeros_like(p) for p in ps]) for ps, _ in groups]
+    batches = [(torch.from_numpy(hsr[f"x{i}"]), torch.from_numpy(hsr[f"y{i}"])) for i in range(2)]
+    epochs, steps = 3, [0, 0]
+    for epoch in range(epochs):
+        for x, y in batches:
+            for p in net.parameters():
+                p.grad = None
+            mu, lp = net(x)
+            M.HSRRef.loss(mu, lp, y, mle=not (epoch < epochs / 3)).backward()
+            for gi, ((ps, wd), (m, v)) in enumerate(zip(groups, state)):
+                if ps[0].grad is None:      # MSE phase: the log-precision net gets no gradient and torch.optim.Adam
+                    continue                # skips it entirely (its per-parameter step counter does not advance)
+                steps[gi] += 1
+                M.torch_adam_step(ps, [p.grad for p in ps], m, v, steps[gi], lr=1e-3, weight_decay=wd)
+    final = {k[len("final::"):]: hsr[k] for k in hsr.files if k.startswith("final::")}
+    for k, v in net.state_dict().items():
+        np.testing.assert_allclose(v.numpy(), final[k], rtol=2e-5, atol=2e-7, err_msg=k)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/baseline_models/HSR/model/final_hsr.cp"),
+                    reason="reference checkpoint only exists in the build container")
+def test_hsr_shipped_checkpoint_outputs(golden_dir):
+    g = np.load(os.path.join(golden_dir, "hsr_final_cp_outputs.npz"))
+    net = M.HSRRef(124, 128, hidden_dims=1024, layers=4)
+    sd = torch.load("/root/reference/baseline_models/HSR/model/final_hsr.cp", map_location="cpu", weights_only=True)
+    net.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        mu, lp = net(torch.from_numpy(g["x"]))
+    np.testing.assert_allclose(mu.numpy(), g["mu"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(lp.numpy(), g["logprec"], rtol=1e-5, atol=1e-6)
+
+
+# ---------------------------------------------------------------- internal consistency of the unpinned restatements
+def test_keras_adam_first_step_is_sign_step():
+    p = [torch.tensor([1.0, -2.0, 3.0])]
+    g = [torch.tensor([0.5, -0.25, 0.1])]
+    m, v = [torch.zeros(3)], [torch.zeros(3)]
+    M.keras_adam_step(p, g, m, v, t=1, lr=0.1)
+    np.testing.assert_allclose(p[0].numpy(), [0.9, -1.9, 2.9], rtol=1e-4)
+
+
+def test_weighted_mse_reduces_to_keras_mse_and_cnn_weights():
+    g = torch.Generator().manual_seed(0)
+    a, b = torch.randn(5, 128, generator=g), torch.randn(5, 128, generator=g)
+    assert M.weighted_mse(a, b, torch.ones(128)).item() == pytest.approx(M.mse(a, b).item(), rel=1e-6)
+    a, b = torch.randn(4, 60, 10, generator=g), torch.randn(4, 60, 10, generator=g)
+    w = M.cnn_loss_weights()
+    assert (w * (a - b) ** 2).sum(dim=(1, 2)).mean().item() == pytest.approx(M.mse_adjusted(a, b).item(), rel=1e-5)
+    assert (w * (a - b).abs()).sum(dim=(1, 2)).mean().item() == pytest.approx(M.mae_adjusted(a, b).item(), rel=1e-5)
+
+
+def test_conv1d_same_matches_direct_sum():
+    g = torch.Generator().manual_seed(1)
+    x, w, b = torch.randn(2, 7, 3, generator=g), torch.randn(3, 3, 4, generator=g), torch.randn(4, generator=g)
+    y = M.conv1d_same_cl(x, w, b)
+    ref = torch.zeros(2, 7, 4)
+    for l in range(7):
+        for t in range(3):
+            s = l + t - 1
+            if 0 <= s < 7:
+                ref[:, l] += x[:, s] @ w[t]
+    ref += b
+    torch.testing.assert_close(y, ref, rtol=1e-5, atol=1e-6)
