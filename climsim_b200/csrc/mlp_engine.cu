@@ -1,0 +1,935 @@
+// mlp_engine.cu -- the csb_mlp_* C ABI: dense-stack column emulator (MLP_v1 / ED / HSR-style nets) on one B200.
+//
+// Data layout in HBM (all row-major, feature dimension contiguous, every feature dimension padded to a multiple of
+// 64 so that one 128-byte swizzle row == 64 bf16 and TMA boxes never straddle a row pitch):
+//   params / grads / adam m,v : one flat fp32 buffer, per layer  W_l [Kp_l x Np_l] (Keras kernel layout) then b_l [Np_l]
+//                               (then gamma_l, beta_l [Np_l] when LayerNorm) -- padding entries are zero and stay zero.
+//   bf16 mode weight copies   : W16_l [Kp x Np] (operand of the data-gradient GEMM) and Wt16_l [Np x Kp] (operand of
+//                               the forward GEMM), refreshed by the optimizer step.
+//   activations               : xn [cap x Kp_0], act_l [cap x Np_l] (bf16 in CSB_BF16 mode, fp32 in CSB_F32 mode),
+//                               kept for the backward pass; dZ ping-pong [cap x max Np]; pred fp32 [cap x Np_last].
+//   split-K workspace         : per layer  splits_l x (Kp_l*Np_l) fp32 partials of dW_l and S x Np_l partials of db_l,
+//                               reduced in a fixed order (deterministic) into `grads`.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "simt_kernels.cuh"
+#include "tc_gemm.cuh"
+
+namespace csb {
+
+static thread_local char g_err[512] = "";
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// TMA descriptor creation through the driver entry point (no link-time dependency on libcuda)
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// bf16 matrix [rows, ld] with `cols` valid columns; box = box_cols x box_rows; SWIZZLE_128B (box_cols == 64)
+static int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_cols,
+                          uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  CSB_REQUIRE(fn != nullptr, CSB_ECUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CSB_REQUIRE(r == CUDA_SUCCESS, CSB_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (cols %llu rows %llu ld %llu box %ux%u)",
+              (int)r, (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)ld, box_cols, box_rows);
+  return CSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// tensor-core launch helpers
+// ---------------------------------------------------------------------------------------------------------------
+template <int BN, int STAGES, int EPI>
+static int launch_tn(const CUtensorMap& ta, const CUtensorMap& tb, const tc::GemmParams& p, int sm_count, cudaStream_t st) {
+  using L = tc::TnSmem<BN, STAGES>;
+  auto kern = tc::gemm_tn_kernel<BN, STAGES, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CSB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_set = true;
+  }
+  const int tiles = (int)(ceil_div(p.M, tc::BM) * ceil_div(p.N, BN));
+  if (tiles == 0) return CSB_OK;
+  const int grid = std::min(tiles, sm_count);
+  kern<<<grid, tc::NUM_THREADS, L::TOTAL, st>>>(ta, tb, p);
+  CSB_CUDA_CHECK(cudaGetLastError());
+  return CSB_OK;
+}
+
+template <int EPI>
+static int launch_tn_auto(const CUtensorMap& ta, const CUtensorMap& tb, const tc::GemmParams& p, int sm_count, cudaStream_t st) {
+  if (p.N > 128) return launch_tn<256, 4, EPI>(ta, tb, p, sm_count, st);
+  return launch_tn<128, 6, EPI>(ta, tb, p, sm_count, st);
+}
+static inline int tn_block_n(int N) { return N > 128 ? 256 : 128; }
+
+template <int BN, int STAGES>
+static int launch_nt(const CUtensorMap& ta, const CUtensorMap& tb, const tc::NtParams& p, int splits, cudaStream_t st) {
+  using L = tc::NtSmem<BN, STAGES>;
+  auto kern = tc::gemm_nt_kernel<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CSB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)(ceil_div(p.M, tc::BM) * ceil_div(p.N, BN)), (unsigned)splits);
+  kern<<<grid, tc::NUM_THREADS, L::TOTAL, st>>>(ta, tb, p);
+  CSB_CUDA_CHECK(cudaGetLastError());
+  return CSB_OK;
+}
+static int launch_nt_auto(const CUtensorMap& ta, const CUtensorMap& tb, const tc::NtParams& p, int splits, cudaStream_t st) {
+  if (p.N > 128) return launch_nt<256, 4>(ta, tb, p, splits, st);
+  return launch_nt<128, 6>(ta, tb, p, splits, st);
+}
+
+static int grid_for(int64_t work_items, int threads, int sm_count, int per_thread = 1) {
+  int64_t blocks = ceil_div(work_items, (int64_t)threads * per_thread);
+  return (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)sm_count * 8));
+}
+
+}  // namespace csb
+
+using namespace csb;
+
+// ---------------------------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------------------------
+struct LayerInfo {
+  int K, N, Kp, Np;
+  int act;
+  float alpha;
+  int ln;
+  size_t w_off, b_off;         // offsets into the padded flat buffers
+  size_t w_off_user, b_off_user;
+  // split-K workspace
+  size_t ws_w_off, ws_b_off;
+  int max_w_splits, b_splits;
+  int nt_block_n;
+};
+
+struct ActMaps {                 // TMA descriptors that depend on the batch size
+  CUtensorMap a_k128;            // buffer as K-major A operand (box 64 x 128 rows)
+  CUtensorMap mn64;              // buffer as MN-major operand of the weight-gradient GEMM (box 64 x 64 rows)
+};
+
+enum ProfKind { K_BEGIN = 0, K_NORMALIZE, K_GEMM_FWD, K_GEMM_HEAD, K_LOSS, K_GEMM_WGRAD, K_COLSUM, K_GEMM_DGRAD, K_REDUCE, K_OPT,
+                K_REPACK, K_MISC, K_COUNT };
+static const char* kProfNames[K_COUNT] = {"begin", "normalize", "gemm_tn_fwd", "gemm_tn_head", "loss", "gemm_nt_wgrad", "colsum_bias_grad",
+                                          "gemm_tn_dgrad", "reduce_partials", "optimizer", "repack_bf16", "misc"};
+
+struct csb_mlp {
+  csb_mlp_cfg cfg;
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<int> prof_kind;
+  int prof_used = 0;
+  double prof_ms[K_COUNT] = {};
+  int64_t prof_n[K_COUNT] = {};
+  int L = 0;
+  LayerInfo layer[CSB_MAX_LAYERS];
+  int in_dim = 0, in_p = 0, out_dim = 0, out_p = 0, max_np = 0;
+  int64_t cap = 0;
+  size_t P_pad = 0, P_user = 0, ws_elems = 0;
+  int sm_count = 0;
+  bool bf16 = false;
+
+  float *params = nullptr, *grads = nullptr, *m = nullptr, *v = nullptr, *ws = nullptr;
+  __nv_bfloat16* w16[CSB_MAX_LAYERS] = {};
+  __nv_bfloat16* wt16[CSB_MAX_LAYERS] = {};
+  void* xn = nullptr;                       // [cap x in_p]   bf16 or fp32
+  void* act[CSB_MAX_LAYERS] = {};           // [cap x Np_l]   (l < L-1)
+  void* dz[2] = {nullptr, nullptr};         // [cap x max_np]
+  float* pred = nullptr;                    // [cap x out_p]
+  float* dx_tmp = nullptr;                  // [cap x in_p] (lazily allocated)
+  float *d_sub = nullptr, *d_div = nullptr, *d_out_scale = nullptr, *d_inv_out_scale = nullptr, *d_loss_w = nullptr;
+  float *loss_partials = nullptr, *d_loss = nullptr;
+  int n_loss_partials = 0;
+  float *x_stage = nullptr, *y_stage = nullptr;   // device staging for the *_host entry points
+
+  CUtensorMap tm_wt[CSB_MAX_LAYERS];        // Wt16_l as K-major B operand of the forward GEMM
+  CUtensorMap tm_w[CSB_MAX_LAYERS];         // W16_l  as K-major B operand of the data-gradient GEMM
+  int64_t maps_B = -1;
+  ActMaps tm_in[CSB_MAX_LAYERS];            // input of layer l (xn or act[l-1]) with `maps_B` rows
+  ActMaps tm_dz[CSB_MAX_LAYERS];            // dZ_l (ping-pong buffer (L-1-l)&1, ld = Np_l) with `maps_B` rows
+
+  int64_t step = 0, launches = 0;
+  int64_t acts_B = -1;                      // batch of the last forward that kept activations
+  bool acts_normalized = false;
+};
+
+// ---- per-launch device timing (optional): an event is recorded after every kernel launch; the time attributed to a
+// launch is the interval since the previous mark on the same stream (kernel duration + launch gap).
+static void prof_mark(csb_mlp* h, int kind, cudaStream_t st) {
+  if (kind != K_BEGIN) h->launches++;
+  if (!h->prof_on) return;
+  if (h->prof_used == (int)h->prof_ev.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return; }
+    h->prof_ev.push_back(e);
+    h->prof_kind.push_back(kind);
+  }
+  h->prof_kind[h->prof_used] = kind;
+  cudaEventRecord(h->prof_ev[h->prof_used], st);
+  h->prof_used++;
+}
+
+static inline void* layer_in(csb_mlp* h, int l) { return l == 0 ? h->xn : h->act[l - 1]; }
+static inline size_t esize(const csb_mlp* h) { return h->bf16 ? 2 : 4; }
+
+static void free_all(csb_mlp* h) {
+  auto F = [](void* p) { if (p) cudaFree(p); };
+  F(h->params); F(h->grads); F(h->m); F(h->v); F(h->ws);
+  for (int l = 0; l < CSB_MAX_LAYERS; ++l) { F(h->w16[l]); F(h->wt16[l]); F(h->act[l]); }
+  F(h->xn); F(h->dz[0]); F(h->dz[1]); F(h->pred); F(h->dx_tmp);
+  F(h->d_sub); F(h->d_div); F(h->d_out_scale); F(h->d_inv_out_scale); F(h->d_loss_w);
+  F(h->loss_partials); F(h->d_loss); F(h->x_stage); F(h->y_stage);
+}
+
+#define CSB_ALLOC(ptr, bytes)                                                                          \
+  do {                                                                                                 \
+    if (cudaMalloc(reinterpret_cast<void**>(&(ptr)), (bytes)) != cudaSuccess) {                        \
+      set_last_error("cudaMalloc of %zu bytes failed (%s)", (size_t)(bytes), #ptr);                    \
+      cudaGetLastError();                                                                              \
+      return CSB_ENOMEM;                                                                               \
+    }                                                                                                  \
+    if (cudaMemset((ptr), 0, (bytes)) != cudaSuccess) { set_last_error("cudaMemset failed"); return CSB_ECUDA; } \
+  } while (0)
+
+static int repack_weights(csb_mlp* h, cudaStream_t st) {
+  if (!h->bf16) return CSB_OK;
+  simt::RepackTable tab;
+  tab.n = h->L;
+  int max_tiles = 1;
+  for (int l = 0; l < h->L; ++l) {
+    const LayerInfo& li = h->layer[l];
+    tab.l[l] = {h->params + li.w_off, h->w16[l], h->wt16[l], li.Kp, li.Np};
+    max_tiles = std::max(max_tiles, (li.Kp / 32) * (li.Np / 32));
+  }
+  dim3 grid((unsigned)std::min(max_tiles, 4 * h->sm_count), (unsigned)h->L);
+  simt::repack_kernel<<<grid, 256, 0, st>>>(tab);
+  CSB_CUDA_CHECK(cudaGetLastError());
+  prof_mark(h, K_REPACK, st);
+  return CSB_OK;
+}
+
+static int build_weight_maps(csb_mlp* h) {
+  for (int l = 0; l < h->L; ++l) {
+    const LayerInfo& li = h->layer[l];
+    // forward:  D[B, Np] = in[B, Kp] . Wt16[Np, Kp]^T          B-operand rows = Np, contraction = Kp
+    int rc = make_tmap_bf16(&h->tm_wt[l], h->wt16[l], li.Kp, li.Np, li.Kp, 64, (uint32_t)std::min(li.Np, tn_block_n(li.Np)));
+    if (rc) return rc;
+    // dgrad:    D[B, Kp] = dZ[B, Np] . W16[Kp, Np]^T           B-operand rows = Kp, contraction = Np
+    rc = make_tmap_bf16(&h->tm_w[l], h->w16[l], li.Np, li.Kp, li.Np, 64, (uint32_t)std::min(li.Kp, tn_block_n(li.Kp)));
+    if (rc) return rc;
+  }
+  return CSB_OK;
+}
+
+static inline __nv_bfloat16* dz16(csb_mlp* h, int l) { return reinterpret_cast<__nv_bfloat16*>(h->dz[(h->L - 1 - l) & 1]); }
+static inline float* dz32(csb_mlp* h, int l) { return reinterpret_cast<float*>(h->dz[(h->L - 1 - l) & 1]); }
+
+static int build_act_maps(csb_mlp* h, int64_t B) {
+  if (!h->bf16 || h->maps_B == B) return CSB_OK;
+  for (int l = 0; l < h->L; ++l) {
+    const LayerInfo& li = h->layer[l];
+    int rc = make_tmap_bf16(&h->tm_in[l].a_k128, layer_in(h, l), li.Kp, B, li.Kp, 64, 128);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&h->tm_in[l].mn64, layer_in(h, l), li.Kp, B, li.Kp, 64, 64);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&h->tm_dz[l].a_k128, dz16(h, l), li.Np, B, li.Np, 64, 128);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&h->tm_dz[l].mn64, dz16(h, l), li.Np, B, li.Np, 64, 64);
+    if (rc) return rc;
+  }
+  h->maps_B = B;
+  return CSB_OK;
+}
+
+extern "C" {
+
+int csb_version(void) { return CSB_VERSION; }
+
+const char* csb_strerror(int code) {
+  switch (code) {
+    case CSB_OK: return "ok";
+    case CSB_EINVAL: return "invalid argument";
+    case CSB_ENODEV: return "no sm_100 CUDA device";
+    case CSB_ENOMEM: return "device allocation failed";
+    case CSB_ECUDA: return "CUDA call or kernel launch failed";
+    case CSB_ESTATE: return "call order / state violation";
+    case CSB_EUNSUPPORTED: return "unsupported configuration";
+    default: return "unknown error";
+  }
+}
+const char* csb_last_error(void) { return g_err; }
+
+int csb_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* hbm_bytes) {
+  int dev = 0, n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); set_last_error("no CUDA device"); return CSB_ENODEV; }
+  CSB_CUDA_CHECK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CSB_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  if (hbm_bytes) *hbm_bytes = prop.totalGlobalMem;
+  return CSB_OK;
+}
+
+int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
+  CSB_REQUIRE(cfg && out, CSB_EINVAL, "null argument");
+  *out = nullptr;
+  CSB_REQUIRE(cfg->n_layers >= 1 && cfg->n_layers <= CSB_MAX_LAYERS, CSB_EINVAL, "n_layers %d out of range", cfg->n_layers);
+  CSB_REQUIRE(cfg->in_dim >= 1 && cfg->max_batch >= 1, CSB_EINVAL, "in_dim / max_batch must be positive");
+  CSB_REQUIRE(cfg->dtype == CSB_F32 || cfg->dtype == CSB_BF16, CSB_EINVAL, "unknown dtype %d", cfg->dtype);
+  CSB_REQUIRE(cfg->loss == CSB_LOSS_MSE || cfg->loss == CSB_LOSS_MAE, CSB_EINVAL, "unknown loss %d", cfg->loss);
+  int sm = 0, maj = 0, min = 0;
+  int rc = csb_device_info(&sm, &maj, &min, nullptr);
+  if (rc) return rc;
+  CSB_REQUIRE(maj == 10, CSB_ENODEV, "device has compute capability %d.%d; this library is sm_100a only", maj, min);
+  for (int l = 0; l < cfg->n_layers; ++l) {
+    CSB_REQUIRE(cfg->units[l] >= 1, CSB_EINVAL, "units[%d] must be positive", l);
+    CSB_REQUIRE(cfg->act[l] >= CSB_ACT_NONE && cfg->act[l] <= CSB_ACT_LEAKYRELU, CSB_EINVAL, "act[%d] unknown", l);
+    CSB_REQUIRE(cfg->layernorm[l] == 0, CSB_EUNSUPPORTED, "layernorm layers are not implemented yet");
+  }
+
+  csb_mlp* h = new (std::nothrow) csb_mlp();
+  CSB_REQUIRE(h != nullptr, CSB_ENOMEM, "host allocation failed");
+  h->cfg = *cfg;
+  h->L = cfg->n_layers;
+  h->sm_count = sm;
+  h->bf16 = cfg->dtype == CSB_BF16;
+  h->in_dim = cfg->in_dim;
+  h->in_p = (int)round_up(cfg->in_dim, 64);
+  h->cap = round_up(cfg->max_batch, 128);
+  size_t off = 0, off_user = 0, ws_off = 0;
+  int k = cfg->in_dim;
+  for (int l = 0; l < h->L; ++l) {
+    LayerInfo& li = h->layer[l];
+    li.K = k; li.N = cfg->units[l];
+    li.Kp = (int)round_up(li.K, 64); li.Np = (int)round_up(li.N, 64);
+    li.act = cfg->act[l]; li.alpha = cfg->alpha[l]; li.ln = cfg->layernorm[l];
+    li.w_off = off; off += (size_t)li.Kp * li.Np;
+    li.b_off = off; off += (size_t)li.Np;
+    li.w_off_user = off_user; off_user += (size_t)li.K * li.N;
+    li.b_off_user = off_user; off_user += (size_t)li.N;
+    li.nt_block_n = tn_block_n(li.Np);
+    const int tiles = (int)(ceil_div(li.Kp, 128) * ceil_div(li.Np, li.nt_block_n));
+    li.max_w_splits = h->bf16 ? std::max(1, std::min(64, sm / tiles)) : 1;
+    li.b_splits = 32;
+    li.ws_w_off = ws_off; ws_off += (size_t)li.max_w_splits * li.Kp * li.Np;
+    li.ws_b_off = ws_off; ws_off += (size_t)li.b_splits * li.Np;
+    h->max_np = std::max(h->max_np, li.Np);
+    k = li.N;
+  }
+  h->out_dim = k;
+  h->out_p = h->layer[h->L - 1].Np;
+  h->P_pad = off; h->P_user = off_user; h->ws_elems = ws_off;
+  if (h->bf16) {
+    if (h->out_dim % 4 != 0) { delete h; set_last_error("CSB_BF16 mode needs out_dim %% 4 == 0"); return CSB_EUNSUPPORTED; }
+  }
+
+#define CK(x) do { int _rc = (x); if (_rc) { free_all(h); delete h; return _rc; } } while (0)
+#define CKA(ptr, bytes) do { int _rc = [&]() -> int { CSB_ALLOC(ptr, bytes); return CSB_OK; }(); if (_rc) { free_all(h); delete h; return _rc; } } while (0)
+  CKA(h->params, h->P_pad * 4); CKA(h->grads, h->P_pad * 4); CKA(h->m, h->P_pad * 4); CKA(h->v, h->P_pad * 4);
+  CKA(h->ws, h->ws_elems * 4);
+  const size_t es = esize(h);
+  CKA(h->xn, (size_t)h->cap * h->in_p * es);
+  for (int l = 0; l + 1 < h->L; ++l) CKA(h->act[l], (size_t)h->cap * h->layer[l].Np * es);
+  CKA(h->dz[0], (size_t)h->cap * h->max_np * es);
+  CKA(h->dz[1], (size_t)h->cap * h->max_np * es);
+  CKA(h->pred, (size_t)h->cap * h->out_p * 4);
+  CKA(h->d_sub, (size_t)h->in_p * 4); CKA(h->d_div, (size_t)h->in_p * 4);
+  CKA(h->d_out_scale, (size_t)h->out_p * 4); CKA(h->d_inv_out_scale, (size_t)h->out_p * 4); CKA(h->d_loss_w, (size_t)h->out_p * 4);
+  h->n_loss_partials = (int)std::max<int64_t>(h->cap / 128 * 4, 8 * sm);
+  CKA(h->loss_partials, (size_t)h->n_loss_partials * 4);
+  CKA(h->d_loss, 4);
+  if (h->bf16) {
+    for (int l = 0; l < h->L; ++l) {
+      CKA(h->w16[l], (size_t)h->layer[l].Kp * h->layer[l].Np * 2);
+      CKA(h->wt16[l], (size_t)h->layer[l].Kp * h->layer[l].Np * 2);
+    }
+    CK(build_weight_maps(h));
+  }
+  CK(csb_mlp_set_norm(h, nullptr, nullptr, nullptr, nullptr));
+#undef CK
+#undef CKA
+  *out = h;
+  return CSB_OK;
+}
+
+int csb_mlp_destroy(csb_mlp* h) {
+  if (!h) return CSB_OK;
+  cudaDeviceSynchronize();
+  free_all(h);
+  for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+  delete h;
+  return CSB_OK;
+}
+
+size_t csb_mlp_param_count(const csb_mlp* h) { return h ? h->P_user : 0; }
+
+int csb_mlp_profile(csb_mlp* h, int enable) {
+  CSB_REQUIRE(h, CSB_EINVAL, "null handle");
+  CSB_CUDA_CHECK(cudaDeviceSynchronize());
+  h->prof_on = enable != 0;
+  h->prof_used = 0;
+  for (int k = 0; k < K_COUNT; ++k) { h->prof_ms[k] = 0.0; h->prof_n[k] = 0; }
+  return CSB_OK;
+}
+int csb_mlp_profile_read(csb_mlp* h, double* ms_by_kind, int64_t* launches_by_kind, int n_kinds) {
+  CSB_REQUIRE(h && ms_by_kind && launches_by_kind && n_kinds >= K_COUNT, CSB_EINVAL, "need room for %d kinds", (int)K_COUNT);
+  CSB_CUDA_CHECK(cudaDeviceSynchronize());
+  for (int i = 1; i < h->prof_used; ++i) {
+    const int kind = h->prof_kind[i];
+    if (kind == K_BEGIN) continue;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->prof_ev[i - 1], h->prof_ev[i]) != cudaSuccess) { cudaGetLastError(); continue; }
+    h->prof_ms[kind] += ms;
+    h->prof_n[kind] += 1;
+  }
+  h->prof_used = 0;
+  for (int k = 0; k < K_COUNT; ++k) { ms_by_kind[k] = h->prof_ms[k]; launches_by_kind[k] = h->prof_n[k]; }
+  return CSB_OK;
+}
+int csb_profile_kind_count(void) { return K_COUNT; }
+const char* csb_profile_kind_name(int kind) { return (kind >= 0 && kind < K_COUNT) ? kProfNames[kind] : "?"; }
+int64_t csb_mlp_launch_count(const csb_mlp* h) { return h ? h->launches : 0; }
+
+// user (unpadded) blob <-> padded device buffer
+static int upload_padded(csb_mlp* h, const float* user, float* dev) {
+  std::vector<float> pad(h->P_pad, 0.f);
+  for (int l = 0; l < h->L; ++l) {
+    const LayerInfo& li = h->layer[l];
+    for (int r = 0; r < li.K; ++r) memcpy(&pad[li.w_off + (size_t)r * li.Np], user + li.w_off_user + (size_t)r * li.N, (size_t)li.N * 4);
+    memcpy(&pad[li.b_off], user + li.b_off_user, (size_t)li.N * 4);
+  }
+  CSB_CUDA_CHECK(cudaMemcpy(dev, pad.data(), h->P_pad * 4, cudaMemcpyHostToDevice));
+  return CSB_OK;
+}
+static int download_padded(csb_mlp* h, const float* dev, float* user) {
+  std::vector<float> pad(h->P_pad);
+  CSB_CUDA_CHECK(cudaDeviceSynchronize());
+  CSB_CUDA_CHECK(cudaMemcpy(pad.data(), dev, h->P_pad * 4, cudaMemcpyDeviceToHost));
+  for (int l = 0; l < h->L; ++l) {
+    const LayerInfo& li = h->layer[l];
+    for (int r = 0; r < li.K; ++r) memcpy(user + li.w_off_user + (size_t)r * li.N, &pad[li.w_off + (size_t)r * li.Np], (size_t)li.N * 4);
+    memcpy(user + li.b_off_user, &pad[li.b_off], (size_t)li.N * 4);
+  }
+  return CSB_OK;
+}
+
+int csb_mlp_set_params(csb_mlp* h, const float* params_host) {
+  CSB_REQUIRE(h && params_host, CSB_EINVAL, "null argument");
+  CSB_CUDA_CHECK(cudaDeviceSynchronize());
+  int rc = upload_padded(h, params_host, h->params);
+  if (rc) return rc;
+  rc = repack_weights(h, 0);
+  if (rc) return rc;
+  CSB_CUDA_CHECK(cudaDeviceSynchronize());
+  return CSB_OK;
+}
+int csb_mlp_get_params(csb_mlp* h, float* params_host) {
+  CSB_REQUIRE(h && params_host, CSB_EINVAL, "null argument");
+  return download_padded(h, h->params, params_host);
+}
+int csb_mlp_get_grads(csb_mlp* h, float* grads_host) {
+  CSB_REQUIRE(h && grads_host, CSB_EINVAL, "null argument");
+  return download_padded(h, h->grads, grads_host);
+}
+static int pad_copy(csb_mlp* h, float* padded, float* user, int dir, cudaStream_t st) {
+  simt::PadTable tab;
+  tab.n = h->L;
+  int64_t mx = 1;
+  for (int l = 0; l < h->L; ++l) {
+    const LayerInfo& li = h->layer[l];
+    tab.l[l] = {li.K, li.N, li.Np, li.w_off, li.b_off, li.w_off_user, li.b_off_user};
+    mx = std::max<int64_t>(mx, (int64_t)(li.K + 1) * li.N);
+  }
+  dim3 grid((unsigned)std::min<int64_t>(ceil_div(mx, 256), 4 * h->sm_count), (unsigned)h->L);
+  simt::pad_copy_kernel<<<grid, 256, 0, st>>>(padded, user, dir, tab);
+  CSB_CUDA_CHECK(cudaGetLastError());
+  prof_mark(h, K_MISC, st);
+  return CSB_OK;
+}
+int csb_mlp_set_params_device(csb_mlp* h, const float* params_dev, void* stream) {
+  CSB_REQUIRE(h && params_dev, CSB_EINVAL, "null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = pad_copy(h, h->params, const_cast<float*>(params_dev), 0, st);
+  if (rc) return rc;
+  return repack_weights(h, st);
+}
+int csb_mlp_get_params_device(csb_mlp* h, float* params_dev, void* stream) {
+  CSB_REQUIRE(h && params_dev, CSB_EINVAL, "null argument");
+  return pad_copy(h, h->params, params_dev, 1, reinterpret_cast<cudaStream_t>(stream));
+}
+int csb_mlp_get_grads_device(csb_mlp* h, float* grads_dev, void* stream) {
+  CSB_REQUIRE(h && grads_dev, CSB_EINVAL, "null argument");
+  return pad_copy(h, h->grads, grads_dev, 1, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int csb_mlp_get_opt_state(csb_mlp* h, float* m_host, float* v_host, int64_t* step) {
+  CSB_REQUIRE(h, CSB_EINVAL, "null handle");
+  int rc = CSB_OK;
+  if (m_host) rc = download_padded(h, h->m, m_host);
+  if (!rc && v_host) rc = download_padded(h, h->v, v_host);
+  if (step) *step = h->step;
+  return rc;
+}
+int csb_mlp_set_opt_state(csb_mlp* h, const float* m_host, const float* v_host, int64_t step) {
+  CSB_REQUIRE(h, CSB_EINVAL, "null handle");
+  CSB_CUDA_CHECK(cudaDeviceSynchronize());
+  int rc = CSB_OK;
+  if (m_host) rc = upload_padded(h, m_host, h->m);
+  if (!rc && v_host) rc = upload_padded(h, v_host, h->v);
+  h->step = step;
+  return rc;
+}
+
+int csb_mlp_set_norm(csb_mlp* h, const float* inp_sub, const float* inp_div, const float* out_scale, const float* loss_w) {
+  CSB_REQUIRE(h, CSB_EINVAL, "null handle");
+  CSB_CUDA_CHECK(cudaDeviceSynchronize());
+  auto up = [&](float* dev, const float* src, int n, int np, float fill, float padfill) -> int {
+    std::vector<float> t(np, padfill);
+    for (int i = 0; i < n; ++i) t[i] = src ? src[i] : fill;
+    CSB_CUDA_CHECK(cudaMemcpy(dev, t.data(), (size_t)np * 4, cudaMemcpyHostToDevice));
+    return CSB_OK;
+  };
+  int rc;
+  // NULL keeps the previous value, except on the very first call from create (all NULL -> defaults)
+  const bool init = !inp_sub && !inp_div && !out_scale && !loss_w;
+  if (inp_sub || init) { rc = up(h->d_sub, inp_sub, h->in_dim, h->in_p, 0.f, 0.f); if (rc) return rc; }
+  if (inp_div || init) { rc = up(h->d_div, inp_div, h->in_dim, h->in_p, 1.f, 1.f); if (rc) return rc; }
+  if (out_scale || init) {
+    rc = up(h->d_out_scale, out_scale, h->out_dim, h->out_p, 1.f, 1.f); if (rc) return rc;
+    std::vector<float> inv(h->out_p, 1.f);
+    for (int i = 0; i < h->out_dim; ++i) inv[i] = out_scale ? 1.f / out_scale[i] : 1.f;
+    CSB_CUDA_CHECK(cudaMemcpy(h->d_inv_out_scale, inv.data(), (size_t)h->out_p * 4, cudaMemcpyHostToDevice));
+  }
+  if (loss_w || init) { rc = up(h->d_loss_w, loss_w, h->out_dim, h->out_p, 1.f, 0.f); if (rc) return rc; }
+  return CSB_OK;
+}
+
+int csb_mlp_grad_buffer(csb_mlp* h, float** ptr, size_t* n) {
+  CSB_REQUIRE(h && ptr && n, CSB_EINVAL, "null argument");
+  *ptr = h->grads;
+  *n = h->P_pad;
+  return CSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward pieces
+// ---------------------------------------------------------------------------------------------------------------
+static int run_normalize(csb_mlp* h, const float* x, int64_t B, int apply, cudaStream_t st) {
+  const int grid = grid_for(B * h->in_p, 256, h->sm_count);
+  simt::normalize_kernel<<<grid, 256, 0, st>>>(x, h->in_dim, h->d_sub, h->d_div, apply,
+                                               h->bf16 ? nullptr : reinterpret_cast<float*>(h->xn), h->in_p,
+                                               h->bf16 ? reinterpret_cast<__nv_bfloat16*>(h->xn) : nullptr, h->in_p, B,
+                                               h->in_dim, h->in_p);
+  CSB_CUDA_CHECK(cudaGetLastError());
+  prof_mark(h, K_NORMALIZE, st);
+  return CSB_OK;
+}
+
+static int run_hidden_forward(csb_mlp* h, int64_t B, cudaStream_t st) {
+  for (int l = 0; l + 1 < h->L; ++l) {
+    const LayerInfo& li = h->layer[l];
+    if (h->bf16) {
+      tc::GemmParams p = {};
+      p.M = (int)B; p.N = li.Np; p.K = li.Kp; p.act = li.act; p.alpha = li.alpha; p.head_relu_from = -1;
+      p.bias = h->params + li.b_off; p.out = h->act[l]; p.ld_out = li.Np;
+      int rc = launch_tn_auto<tc::EPI_BIAS_ACT>(h->tm_in[l].a_k128, h->tm_wt[l], p, h->sm_count, st);
+      if (rc) return rc;
+    } else {
+      simt::SgemmParams p = {};
+      p.M = (int)B; p.N = li.Np; p.K = li.Kp;
+      p.A = reinterpret_cast<const float*>(layer_in(h, l)); p.lda = li.Kp;
+      p.B = h->params + li.w_off; p.ldb = li.Np;
+      p.C = reinterpret_cast<float*>(h->act[l]); p.ldc = li.Np;
+      p.bias = h->params + li.b_off; p.act = li.act; p.alpha = li.alpha; p.head_relu_from = -1;
+      dim3 grid((unsigned)(li.Np / 64), (unsigned)ceil_div(B, 64));
+      simt::sgemm_kernel<false, false, simt::SEPI_BIAS_ACT><<<grid, 256, 0, st>>>(p);
+      CSB_CUDA_CHECK(cudaGetLastError());
+    }
+    prof_mark(h, K_GEMM_FWD, st);
+  }
+  return CSB_OK;
+}
+
+// output layer.  mode 0: predictions only (pred buffer);  mode 1 (bf16 only): fused loss + dZ
+static int run_head(csb_mlp* h, int64_t B, int fused_loss, const float* y, float grad_scale, cudaStream_t st) {
+  const int l = h->L - 1;
+  const LayerInfo& li = h->layer[l];
+  if (h->bf16) {
+    tc::GemmParams p = {};
+    p.M = (int)B; p.N = li.Np; p.K = li.Kp; p.act = li.act; p.alpha = li.alpha; p.head_relu_from = h->cfg.head_relu_from;
+    p.bias = h->params + li.b_off; p.out_dim = h->out_dim;
+    p.pred = h->pred; p.ld_pred = h->out_p;
+    int rc;
+    if (fused_loss) {
+      p.out = dz16(h, l); p.ld_out = li.Np;
+      p.y = y; p.ld_y = h->out_dim; p.loss_w = h->d_loss_w; p.grad_scale = grad_scale; p.loss_kind = h->cfg.loss;
+      p.loss_partials = h->loss_partials;
+      p.pred = nullptr;
+      rc = launch_tn_auto<tc::EPI_HEAD_LOSS>(h->tm_in[l].a_k128, h->tm_wt[l], p, h->sm_count, st);
+    } else {
+      rc = launch_tn_auto<tc::EPI_HEAD_OUT>(h->tm_in[l].a_k128, h->tm_wt[l], p, h->sm_count, st);
+    }
+    if (rc) return rc;
+  } else {
+    simt::SgemmParams p = {};
+    p.M = (int)B; p.N = li.Np; p.K = li.Kp;
+    p.A = reinterpret_cast<const float*>(layer_in(h, l)); p.lda = li.Kp;
+    p.B = h->params + li.w_off; p.ldb = li.Np;
+    p.C = h->pred; p.ldc = h->out_p;
+    p.bias = h->params + li.b_off; p.act = li.act; p.alpha = li.alpha; p.head_relu_from = h->cfg.head_relu_from;
+    dim3 grid((unsigned)(li.Np / 64), (unsigned)ceil_div(B, 64));
+    simt::sgemm_kernel<false, false, simt::SEPI_BIAS_ACT><<<grid, 256, 0, st>>>(p);
+    CSB_CUDA_CHECK(cudaGetLastError());
+  }
+  prof_mark(h, K_GEMM_HEAD, st);
+  return CSB_OK;
+}
+
+static int check_batch(csb_mlp* h, int64_t B) {
+  CSB_REQUIRE(B >= 0 && B <= h->cfg.max_batch, CSB_ESTATE, "batch %lld exceeds max_batch %lld", (long long)B, (long long)h->cfg.max_batch);
+  return CSB_OK;
+}
+
+int csb_mlp_forward(csb_mlp* h, const float* x, float* y_pred, int64_t B, uint32_t flags, void* stream) {
+  CSB_REQUIRE(h && x && y_pred, CSB_EINVAL, "null argument");
+  int rc = check_batch(h, B);
+  if (rc) return rc;
+  if (B == 0) return CSB_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if ((rc = build_act_maps(h, B))) return rc;
+  prof_mark(h, K_BEGIN, st);
+  if ((rc = run_normalize(h, x, B, (flags & CSB_FWD_NORMALIZE_IN) ? 1 : 0, st))) return rc;
+  if ((rc = run_hidden_forward(h, B, st))) return rc;
+  if ((rc = run_head(h, B, 0, nullptr, 0.f, st))) return rc;
+  const int grid = grid_for(B * h->out_dim, 256, h->sm_count);
+  simt::scale_copy_kernel<<<grid, 256, 0, st>>>(h->pred, h->out_p, (flags & CSB_FWD_DENORM_OUT) ? h->d_inv_out_scale : nullptr,
+                                                y_pred, h->out_dim, B, h->out_dim);
+  CSB_CUDA_CHECK(cudaGetLastError());
+  prof_mark(h, K_MISC, st);
+  h->acts_B = (flags & CSB_FWD_KEEP_ACTIVATIONS) ? B : -1;
+  h->acts_normalized = (flags & CSB_FWD_NORMALIZE_IN) != 0;
+  return CSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// backward chain: given dZ_{L-1} in dz(L-1), produce all parameter gradients (and optionally dx)
+// ---------------------------------------------------------------------------------------------------------------
+static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st) {
+  simt::SegmentTable tab;
+  tab.n = 0;
+  int64_t max_len = 4;
+  for (int l = h->L - 1; l >= 0; --l) {
+    const LayerInfo& li = h->layer[l];
+    // ---- weight gradient dW_l = in_l^T . dZ_l  (contraction over the B rows)
+    int splits = 1;
+    if (h->bf16) {
+      const int num_rb = (int)ceil_div(B, 64);
+      splits = std::max(1, std::min(li.max_w_splits, num_rb));
+      tc::NtParams p;
+      p.M = li.Kp; p.N = li.Np; p.R = (int)B;
+      p.rb_per_split = (int)ceil_div(num_rb, splits);
+      splits = (int)ceil_div(num_rb, p.rb_per_split);
+      p.out = h->ws + li.ws_w_off; p.ld_out = li.Np; p.split_stride = (size_t)li.Kp * li.Np;
+      int rc = launch_nt_auto(h->tm_in[l].mn64, h->tm_dz[l].mn64, p, splits, st);
+      if (rc) return rc;
+    } else {
+      simt::SgemmParams p = {};
+      p.M = li.Kp; p.N = li.Np; p.K = (int)B;
+      p.A = reinterpret_cast<const float*>(layer_in(h, l)); p.lda = li.Kp;
+      p.B = dz32(h, l); p.ldb = li.Np;
+      p.C = h->ws + li.ws_w_off; p.ldc = li.Np;
+      dim3 grid((unsigned)(li.Np / 64), (unsigned)(li.Kp / 64));
+      simt::sgemm_kernel<true, false, simt::SEPI_STORE><<<grid, 256, 0, st>>>(p);
+      CSB_CUDA_CHECK(cudaGetLastError());
+    }
+    prof_mark(h, K_GEMM_WGRAD, st);
+    tab.seg[tab.n++] = {h->ws + li.ws_w_off, (size_t)li.Kp * li.Np, h->grads + li.w_off, (int64_t)li.Kp * li.Np, splits};
+    max_len = std::max<int64_t>(max_len, (int64_t)li.Kp * li.Np);
+    // ---- bias gradient db_l = column sums of dZ_l
+    {
+      const int S = (int)std::max<int64_t>(1, std::min<int64_t>(li.b_splits, ceil_div(B, 256)));
+      dim3 grid((unsigned)(li.Np / 64), (unsigned)S);
+      if (h->bf16) simt::colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(dz16(h, l), li.Np, B, h->ws + li.ws_b_off, (size_t)li.Np);
+      else simt::colsum_kernel<float><<<grid, 256, 0, st>>>(dz32(h, l), li.Np, B, h->ws + li.ws_b_off, (size_t)li.Np);
+      CSB_CUDA_CHECK(cudaGetLastError());
+      prof_mark(h, K_COLSUM, st);
+      tab.seg[tab.n++] = {h->ws + li.ws_b_off, (size_t)li.Np, h->grads + li.b_off, (int64_t)li.Np, S};
+    }
+    // ---- data gradient dZ_{l-1} = (dZ_l . W_l^T) * act'_{l-1}(act_{l-1})
+    if (l > 0) {
+      const LayerInfo& lp = h->layer[l - 1];
+      if (h->bf16) {
+        tc::GemmParams p = {};
+        p.M = (int)B; p.N = li.Kp; p.K = li.Np; p.act = lp.act; p.alpha = lp.alpha; p.head_relu_from = -1;
+        p.out = dz16(h, l - 1); p.ld_out = lp.Np;
+        p.saved = reinterpret_cast<const __nv_bfloat16*>(h->act[l - 1]); p.ld_saved = lp.Np;
+        int rc = launch_tn_auto<tc::EPI_DGRAD>(h->tm_dz[l].a_k128, h->tm_w[l], p, h->sm_count, st);
+        if (rc) return rc;
+      } else {
+        simt::SgemmParams p = {};
+        p.M = (int)B; p.N = li.Kp; p.K = li.Np;
+        p.A = dz32(h, l); p.lda = li.Np;
+        p.B = h->params + li.w_off; p.ldb = li.Np;          // stored [Kp, Np] = [N_out, K_contract] -> TB
+        p.C = dz32(h, l - 1); p.ldc = lp.Np;
+        p.act = lp.act; p.alpha = lp.alpha; p.head_relu_from = -1;
+        p.saved = reinterpret_cast<const float*>(h->act[l - 1]); p.ld_saved = lp.Np;
+        dim3 grid((unsigned)(li.Kp / 64), (unsigned)ceil_div(B, 64));
+        simt::sgemm_kernel<false, true, simt::SEPI_DGRAD><<<grid, 256, 0, st>>>(p);
+        CSB_CUDA_CHECK(cudaGetLastError());
+      }
+      prof_mark(h, K_GEMM_DGRAD, st);
+    } else if (dx != nullptr) {
+      // dL/dxn = dZ_0 . W_0^T  (fp32 result), then / div if the forward normalised
+      if (!h->dx_tmp) { CSB_ALLOC(h->dx_tmp, (size_t)h->cap * h->in_p * 4); }
+      if (h->bf16) {
+        tc::GemmParams p = {};
+        p.M = (int)B; p.N = li.Kp; p.K = li.Np; p.out = h->dx_tmp; p.ld_out = h->in_p;
+        int rc = launch_tn_auto<tc::EPI_F32>(h->tm_dz[0].a_k128, h->tm_w[0], p, h->sm_count, st);
+        if (rc) return rc;
+      } else {
+        simt::SgemmParams p = {};
+        p.M = (int)B; p.N = li.Kp; p.K = li.Np;
+        p.A = dz32(h, 0); p.lda = li.Np; p.B = h->params + li.w_off; p.ldb = li.Np; p.C = h->dx_tmp; p.ldc = h->in_p;
+        dim3 grid((unsigned)(li.Kp / 64), (unsigned)ceil_div(B, 64));
+        simt::sgemm_kernel<false, true, simt::SEPI_STORE><<<grid, 256, 0, st>>>(p);
+        CSB_CUDA_CHECK(cudaGetLastError());
+      }
+      prof_mark(h, K_GEMM_DGRAD, st);
+    }
+  }
+  // ---- deterministic reduction of all split partials into the flat gradient buffer (one launch, blockIdx.y = segment)
+  {
+    dim3 grid((unsigned)std::min<int64_t>(ceil_div(max_len / 4, 256), 2 * h->sm_count), (unsigned)tab.n);
+    simt::reduce_partials_kernel<<<grid, 256, 0, st>>>(tab);
+    CSB_CUDA_CHECK(cudaGetLastError());
+    prof_mark(h, K_REDUCE, st);
+  }
+  return CSB_OK;
+}
+
+int csb_mlp_train_step(csb_mlp* h, const float* x, const float* y, int64_t B, float grad_scale, uint32_t flags,
+                       float* loss_out, void* stream) {
+  CSB_REQUIRE(h && x && y, CSB_EINVAL, "null argument");
+  int rc = check_batch(h, B);
+  if (rc) return rc;
+  CSB_REQUIRE(B > 0, CSB_EINVAL, "empty batch");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (grad_scale <= 0.f) grad_scale = 1.f / ((float)B * (float)h->out_dim);
+  if ((rc = build_act_maps(h, B))) return rc;
+  prof_mark(h, K_BEGIN, st);
+  if ((rc = run_normalize(h, x, B, (flags & CSB_FWD_NORMALIZE_IN) ? 1 : 0, st))) return rc;
+  if ((rc = run_hidden_forward(h, B, st))) return rc;
+  int n_partials;
+  const int l = h->L - 1;
+  if (h->bf16) {
+    if ((rc = run_head(h, B, 1, y, grad_scale, st))) return rc;
+    n_partials = (int)ceil_div(B, 128) * 4;
+  } else {
+    if ((rc = run_head(h, B, 0, nullptr, 0.f, st))) return rc;
+    const int grid = std::min(h->n_loss_partials, grid_for(B * h->out_p, 256, h->sm_count));
+    simt::head_grad_kernel<float><<<grid, 256, 0, st>>>(h->pred, h->out_p, y, h->out_dim, h->d_loss_w, grad_scale, h->cfg.loss, 0,
+                                                        h->layer[l].act, h->layer[l].alpha, h->cfg.head_relu_from, nullptr,
+                                                        dz32(h, l), h->out_p, B, h->out_dim, h->out_p, h->loss_partials);
+    CSB_CUDA_CHECK(cudaGetLastError());
+    prof_mark(h, K_LOSS, st);
+    n_partials = grid;
+  }
+  simt::loss_finalize_kernel<<<1, 256, 0, st>>>(h->loss_partials, n_partials, loss_out ? loss_out : h->d_loss);
+  CSB_CUDA_CHECK(cudaGetLastError());
+  prof_mark(h, K_LOSS, st);
+  if ((rc = run_backward_chain(h, B, nullptr, st))) return rc;
+  h->acts_B = -1;
+  return CSB_OK;
+}
+
+int csb_mlp_backward(csb_mlp* h, const float* dy, float* dx, int64_t B, void* stream) {
+  CSB_REQUIRE(h && dy, CSB_EINVAL, "null argument");
+  CSB_REQUIRE(h->acts_B == B && B > 0, CSB_ESTATE, "csb_mlp_backward needs a preceding forward with CSB_FWD_KEEP_ACTIVATIONS on the same batch");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int l = h->L - 1;
+  const int grid = grid_for(B * h->out_p, 256, h->sm_count);
+  prof_mark(h, K_BEGIN, st);
+  if (h->bf16)
+    simt::head_grad_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(h->pred, h->out_p, dy, h->out_dim, h->d_loss_w, 1.f, 0, 1, h->layer[l].act,
+                                                                 h->layer[l].alpha, h->cfg.head_relu_from, nullptr, dz16(h, l), h->out_p,
+                                                                 B, h->out_dim, h->out_p, nullptr);
+  else
+    simt::head_grad_kernel<float><<<grid, 256, 0, st>>>(h->pred, h->out_p, dy, h->out_dim, h->d_loss_w, 1.f, 0, 1, h->layer[l].act,
+                                                         h->layer[l].alpha, h->cfg.head_relu_from, nullptr, dz32(h, l), h->out_p, B,
+                                                         h->out_dim, h->out_p, nullptr);
+  CSB_CUDA_CHECK(cudaGetLastError());
+  prof_mark(h, K_LOSS, st);
+  int rc = run_backward_chain(h, B, dx, st);
+  if (rc) return rc;
+  if (dx) {
+    // dx_tmp [B, in_p] -> dx [B, in_dim], divided by inp_div when the forward normalised: reuse scale_copy with 1/div
+    // (inp_div entries that are 0 produced xn = 0 in the forward; their gradient is defined as 0)
+    const int g2 = grid_for(B * h->in_dim, 256, h->sm_count);
+    simt::scale_copy_kernel<<<g2, 256, 0, st>>>(h->dx_tmp, h->in_p, nullptr, dx, h->in_dim, B, h->in_dim);
+    CSB_CUDA_CHECK(cudaGetLastError());
+    prof_mark(h, K_MISC, st);
+  }
+  return CSB_OK;
+}
+
+int csb_mlp_apply_opt(csb_mlp* h, int rule, float lr, float beta1, float beta2, float eps, float wd, void* stream) {
+  CSB_REQUIRE(h, CSB_EINVAL, "null handle");
+  CSB_REQUIRE(rule >= CSB_OPT_ADAM_KERAS && rule <= CSB_OPT_SGD, CSB_EINVAL, "unknown optimizer rule %d", rule);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  prof_mark(h, K_BEGIN, st);
+  h->step++;
+  simt::OptParams o;
+  o.rule = rule; o.lr = lr; o.beta1 = beta1; o.beta2 = beta2; o.eps = eps; o.wd = wd;
+  o.bc1 = (float)(1.0 - pow((double)beta1, (double)h->step));
+  o.bc2 = (float)(1.0 - pow((double)beta2, (double)h->step));
+  const int grid = grid_for((int64_t)h->P_pad / 4, 256, h->sm_count);
+  simt::opt_kernel<<<grid, 256, 0, st>>>(h->params, h->grads, h->m, h->v, (int64_t)h->P_pad, o);
+  CSB_CUDA_CHECK(cudaGetLastError());
+  prof_mark(h, K_OPT, st);
+  return repack_weights(h, st);
+}
+
+static int ensure_stage(csb_mlp* h) {
+  if (!h->x_stage) { CSB_ALLOC(h->x_stage, (size_t)h->cap * h->in_dim * 4); }
+  if (!h->y_stage) { CSB_ALLOC(h->y_stage, (size_t)h->cap * h->out_dim * 4); }
+  return CSB_OK;
+}
+
+int csb_mlp_forward_host(csb_mlp* h, const float* x_host, float* y_pred_host, int64_t B, uint32_t flags, void* stream) {
+  CSB_REQUIRE(h && x_host && y_pred_host, CSB_EINVAL, "null argument");
+  int rc = check_batch(h, B);
+  if (rc) return rc;
+  if (B == 0) return CSB_OK;
+  if ((rc = ensure_stage(h))) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CSB_CUDA_CHECK(cudaMemcpyAsync(h->x_stage, x_host, (size_t)B * h->in_dim * 4, cudaMemcpyHostToDevice, st));
+  if ((rc = csb_mlp_forward(h, h->x_stage, h->y_stage, B, flags, stream))) return rc;
+  CSB_CUDA_CHECK(cudaMemcpyAsync(y_pred_host, h->y_stage, (size_t)B * h->out_dim * 4, cudaMemcpyDeviceToHost, st));
+  CSB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return CSB_OK;
+}
+
+int csb_mlp_train_step_host(csb_mlp* h, const float* x_host, const float* y_host, int64_t B, float grad_scale, uint32_t flags,
+                            int rule, float lr, float beta1, float beta2, float eps, float wd, float* loss_host, void* stream) {
+  CSB_REQUIRE(h && x_host && y_host, CSB_EINVAL, "null argument");
+  int rc = check_batch(h, B);
+  if (rc) return rc;
+  if ((rc = ensure_stage(h))) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CSB_CUDA_CHECK(cudaMemcpyAsync(h->x_stage, x_host, (size_t)B * h->in_dim * 4, cudaMemcpyHostToDevice, st));
+  CSB_CUDA_CHECK(cudaMemcpyAsync(h->y_stage, y_host, (size_t)B * h->out_dim * 4, cudaMemcpyHostToDevice, st));
+  if ((rc = csb_mlp_train_step(h, h->x_stage, h->y_stage, B, grad_scale, flags, nullptr, stream))) return rc;
+  if ((rc = csb_mlp_apply_opt(h, rule, lr, beta1, beta2, eps, wd, stream))) return rc;
+  float loss = 0.f;
+  CSB_CUDA_CHECK(cudaMemcpyAsync(&loss, h->d_loss, 4, cudaMemcpyDeviceToHost, st));
+  CSB_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (loss_host) *loss_host = loss;
+  return CSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// data_utils helpers
+// ---------------------------------------------------------------------------------------------------------------
+int csb_normalize(const float* x_raw, const float* sub, const float* div, float* x_out, int64_t N, int32_t F, void* stream) {
+  CSB_REQUIRE(x_raw && sub && div && x_out && N >= 0 && F > 0, CSB_EINVAL, "bad argument");
+  if (N == 0) return CSB_OK;
+  int sm = 148;
+  csb_device_info(&sm, nullptr, nullptr, nullptr);
+  simt::normalize_kernel<<<grid_for(N * F, 256, sm), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x_raw, F, sub, div, 1, x_out, F, nullptr, 0, N, F, F);
+  CSB_CUDA_CHECK(cudaGetLastError());
+  return CSB_OK;
+}
+int csb_reshape_input_for_cnn(const float* x, float* out, int64_t N, void* stream) {
+  CSB_REQUIRE(x && out && N >= 0, CSB_EINVAL, "bad argument");
+  if (N == 0) return CSB_OK;
+  simt::cnn_reshape_in_kernel<<<(unsigned)std::min<int64_t>(ceil_div(N * 360, 256), 148 * 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, out, N, 2, 4, 124);
+  CSB_CUDA_CHECK(cudaGetLastError());
+  return CSB_OK;
+}
+int csb_reshape_target_for_cnn(const float* y, float* out, int64_t N, void* stream) {
+  CSB_REQUIRE(y && out && N >= 0, CSB_EINVAL, "bad argument");
+  if (N == 0) return CSB_OK;
+  simt::cnn_reshape_in_kernel<<<(unsigned)std::min<int64_t>(ceil_div(N * 600, 256), 148 * 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(y, out, N, 2, 8, 128);
+  CSB_CUDA_CHECK(cudaGetLastError());
+  return CSB_OK;
+}
+int csb_reshape_target_from_cnn(const float* p, float* out, int64_t N, void* stream) {
+  CSB_REQUIRE(p && out && N >= 0, CSB_EINVAL, "bad argument");
+  if (N == 0) return CSB_OK;
+  simt::cnn_reshape_out_kernel<<<(unsigned)std::min<int64_t>(ceil_div(N * 128, 256), 148 * 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, out, N);
+  CSB_CUDA_CHECK(cudaGetLastError());
+  return CSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// kernel self-test hooks
+// ---------------------------------------------------------------------------------------------------------------
+int csb_test_gemm_tn(const uint16_t* A, const uint16_t* Bt, float* C, int M, int N, int K, int block_n, void* stream) {
+  CSB_REQUIRE(A && Bt && C, CSB_EINVAL, "null argument");
+  CSB_REQUIRE(N % 64 == 0 && K % 64 == 0 && M > 0, CSB_EINVAL, "N and K must be multiples of 64");
+  CSB_REQUIRE(block_n == 128 || block_n == 256, CSB_EINVAL, "block_n must be 128 or 256");
+  int sm = 0;
+  int rc = csb_device_info(&sm, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  CUtensorMap ta, tb;
+  if ((rc = make_tmap_bf16(&ta, A, K, M, K, 64, 128))) return rc;
+  if ((rc = make_tmap_bf16(&tb, Bt, K, N, K, 64, (uint32_t)std::min(N, block_n)))) return rc;
+  tc::GemmParams p = {};
+  p.M = M; p.N = N; p.K = K; p.out = C; p.ld_out = N;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (block_n == 256) return launch_tn<256, 4, tc::EPI_F32>(ta, tb, p, sm, st);
+  return launch_tn<128, 6, tc::EPI_F32>(ta, tb, p, sm, st);
+}
+
+int csb_test_gemm_nt(const uint16_t* A, const uint16_t* B, float* C, int M, int N, int Kr, int splits, void* stream) {
+  CSB_REQUIRE(A && B && C, CSB_EINVAL, "null argument");
+  CSB_REQUIRE(M % 64 == 0 && N % 64 == 0 && Kr > 0 && splits >= 1, CSB_EINVAL, "M and N must be multiples of 64");
+  CUtensorMap ta, tb;
+  int rc;
+  if ((rc = make_tmap_bf16(&ta, A, M, Kr, M, 64, 64))) return rc;
+  if ((rc = make_tmap_bf16(&tb, B, N, Kr, N, 64, 64))) return rc;
+  const int num_rb = (int)ceil_div(Kr, 64);
+  tc::NtParams p;
+  p.M = M; p.N = N; p.R = Kr;
+  p.rb_per_split = (int)ceil_div(num_rb, splits);
+  p.out = C; p.ld_out = N; p.split_stride = (size_t)M * N;    // caller provides splits * M * N floats
+  return launch_nt_auto(ta, tb, p, splits, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

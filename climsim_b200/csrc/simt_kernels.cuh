@@ -1,0 +1,385 @@
+// simt_kernels.cuh -- fp32 CUDA-core kernels: the CSB_F32 parity mode (every GEMM in FFMA) and the HBM-bound
+// element-wise / reduction kernels shared by both modes (normalise, loss, column sums, partial reduce, optimizer,
+// weight repacking).  All are written for coalesced 128-bit access along the contiguous (feature) dimension.
+#pragma once
+#include "common.cuh"
+
+namespace csb {
+namespace simt {
+
+// ---------------------------------------------------------------------------------------------------------------
+// normalise: xn = (x - sub)/div, inf/nan -> 0   (climsim_utils/data_utils.py:806-809, 894-897)
+// Writes fp32 [N, ld_f32] and/or bf16 [N, ld_bf16]; padding columns [F, ld) are zero-filled.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void normalize_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ sub,
+                                 const float* __restrict__ div, int apply, float* __restrict__ out_f32, int ld_f32,
+                                 __nv_bfloat16* __restrict__ out_bf16, int ld_bf16, int64_t N, int F, int Fp) {
+  const int64_t total = N * Fp;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / Fp;
+    const int c = (int)(i - r * Fp);
+    float v = 0.f;
+    if (c < F) {
+      v = x[r * ld_x + c];
+      if (apply) {
+        v = (v - sub[c]) / div[c];
+        if (isinf(v) || isnan(v)) v = 0.f;
+      }
+    }
+    if (out_f32) out_f32[r * ld_f32 + c] = v;
+    if (out_bf16) out_bf16[r * ld_bf16 + c] = __float2bfloat16_rn(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fp32 GEMM  C[M,N] = epilogue( opA(A) . opB(B) )  -- 64x64 tile, BK 16, 256 threads, 4x4 micro-tile.
+//   TA = false: A stored [M, K] (lda)        TA = true : A stored [K, M] (lda)     (weight gradient: H^T)
+//   TB = false: B stored [K, N] (ldb)        TB = true : B stored [N, K] (ldb)     (data gradient:  W^T)
+// N and the contiguous feature dimensions are multiples of 64 (padded layout); M (and K when it is the batch) may be
+// ragged and is bounds-checked.
+// ---------------------------------------------------------------------------------------------------------------
+enum SEpi : int { SEPI_STORE = 0, SEPI_BIAS_ACT = 1, SEPI_DGRAD = 2 };
+
+struct SgemmParams {
+  int M, N, K;
+  const float* A; int lda;
+  const float* B; int ldb;
+  float* C; int ldc;
+  const float* bias;          // SEPI_BIAS_ACT
+  int act; float alpha; int head_relu_from;
+  const float* saved; int ld_saved;   // SEPI_DGRAD
+};
+
+template <bool TA, bool TB, int EPI>
+__global__ void __launch_bounds__(256) sgemm_kernel(const SgemmParams p) {
+  constexpr int T = 64, BKS = 16;
+  __shared__ float As[BKS][T + 4];
+  __shared__ float Bs[BKS][T + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * T, n0 = blockIdx.x * T;
+  const int tx = tid & 15, ty = tid >> 4;   // micro-tile: rows ty*4.., cols tx*4..
+  float acc[4][4] = {};
+
+  for (int k0 = 0; k0 < p.K; k0 += BKS) {
+    // ---- load A tile -> As[k][m]
+    if constexpr (!TA) {
+      const int r = tid >> 2, kq = (tid & 3) * 4;          // 64 rows x 4 float4
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m0 + r < p.M) {
+        const float* src = p.A + (size_t)(m0 + r) * p.lda + k0 + kq;
+        if (k0 + kq + 3 < p.K) v = *reinterpret_cast<const float4*>(src);
+        else { float t[4] = {0, 0, 0, 0}; for (int i = 0; i < 4; ++i) if (k0 + kq + i < p.K) t[i] = src[i]; v = make_float4(t[0], t[1], t[2], t[3]); }
+      }
+      As[kq + 0][r] = v.x; As[kq + 1][r] = v.y; As[kq + 2][r] = v.z; As[kq + 3][r] = v.w;
+    } else {
+      const int k = tid >> 4, mq = (tid & 15) * 4;         // 16 k-rows x 16 float4
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + k < p.K) {
+        const float* src = p.A + (size_t)(k0 + k) * p.lda + m0 + mq;
+        if (m0 + mq + 3 < p.M) v = *reinterpret_cast<const float4*>(src);
+        else { float t[4] = {0, 0, 0, 0}; for (int i = 0; i < 4; ++i) if (m0 + mq + i < p.M) t[i] = src[i]; v = make_float4(t[0], t[1], t[2], t[3]); }
+      }
+      *reinterpret_cast<float4*>(&As[k][mq]) = v;
+    }
+    // ---- load B tile -> Bs[k][n]
+    if constexpr (!TB) {
+      const int k = tid >> 4, nq = (tid & 15) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + k < p.K) v = *reinterpret_cast<const float4*>(p.B + (size_t)(k0 + k) * p.ldb + n0 + nq);
+      *reinterpret_cast<float4*>(&Bs[k][nq]) = v;
+    } else {
+      const int r = tid >> 2, kq = (tid & 3) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* src = p.B + (size_t)(n0 + r) * p.ldb + k0 + kq;
+      if (k0 + kq + 3 < p.K) v = *reinterpret_cast<const float4*>(src);
+      else { float t[4] = {0, 0, 0, 0}; for (int i = 0; i < 4; ++i) if (k0 + kq + i < p.K) t[i] = src[i]; v = make_float4(t[0], t[1], t[2], t[3]); }
+      Bs[kq + 0][r] = v.x; Bs[kq + 1][r] = v.y; Bs[kq + 2][r] = v.z; Bs[kq + 3][r] = v.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BKS; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = m0 + ty * 4 + i;
+    if (r >= p.M) continue;
+    const int c = n0 + tx * 4;
+    float v[4] = {acc[i][0], acc[i][1], acc[i][2], acc[i][3]};
+    if constexpr (EPI == SEPI_BIAS_ACT) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float z = v[j] + p.bias[c + j];
+        const bool relu_col = p.head_relu_from >= 0 && (c + j) >= p.head_relu_from;
+        v[j] = relu_col ? fmaxf(z, 0.f) : act_fwd(p.act, p.alpha, z);
+      }
+    } else if constexpr (EPI == SEPI_DGRAD) {
+      const float4 a = *reinterpret_cast<const float4*>(p.saved + (size_t)r * p.ld_saved + c);
+      v[0] *= act_bwd_from_out(p.act, p.alpha, a.x);
+      v[1] *= act_bwd_from_out(p.act, p.alpha, a.y);
+      v[2] *= act_bwd_from_out(p.act, p.alpha, a.z);
+      v[3] *= act_bwd_from_out(p.act, p.alpha, a.w);
+    }
+    *reinterpret_cast<float4*>(p.C + (size_t)r * p.ldc + c) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// loss + dL/dz of the head (fp32 mode), and the dy -> dz conversion used by csb_mlp_backward.
+//   mode 0: dz = loss gradient (MSE / MAE, weights w, scale) * head'(p);  accumulates the loss partial
+//   mode 1: dz = dy * head'(p)                                            (external upstream gradient)
+// p is the saved head output [M, ldp]; out dz [M, ldz] (fp32 or bf16); padding columns written as zero.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename TZ>
+__device__ __forceinline__ void store_dz(TZ* dst, float v);
+template <> __device__ __forceinline__ void store_dz<float>(float* dst, float v) { *dst = v; }
+template <> __device__ __forceinline__ void store_dz<__nv_bfloat16>(__nv_bfloat16* dst, float v) { *dst = __float2bfloat16_rn(v); }
+
+template <typename TZ>
+__global__ void __launch_bounds__(256)
+head_grad_kernel(const float* __restrict__ pred, int ldp, const float* __restrict__ y_or_dy, int ldy,
+                 const float* __restrict__ w, float scale, int loss_kind, int mode, int act, float alpha,
+                 int head_relu_from, const float* __restrict__ inv_scale_unused, TZ* __restrict__ dz, int ldz,
+                 int64_t M, int out_dim, int Np, float* __restrict__ loss_partials) {
+  float lacc = 0.f;
+  const int64_t total = M * Np;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / Np;
+    const int c = (int)(i - r * Np);
+    float g = 0.f;
+    if (c < out_dim) {
+      const float pv = pred[r * ldp + c];
+      const bool relu_col = head_relu_from >= 0 && c >= head_relu_from;
+      const float dact = relu_col ? (pv > 0.f ? 1.f : 0.f) : act_bwd_from_out(act, alpha, pv);
+      if (mode == 0) {
+        const float d = pv - y_or_dy[r * ldy + c];
+        if (loss_kind == CSB_LOSS_MSE) { lacc += w[c] * d * d; g = 2.f * w[c] * d * scale * dact; }
+        else { lacc += w[c] * fabsf(d); g = w[c] * scale * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * dact; }
+      } else {
+        g = y_or_dy[r * ldy + c] * dact;
+      }
+    }
+    store_dz<TZ>(dz + r * ldz + c, g);
+  }
+  if (loss_partials != nullptr) {
+    __shared__ float red[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lacc += __shfl_xor_sync(0xffffffffu, lacc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lacc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+      loss_partials[blockIdx.x] = s * scale;
+    }
+  }
+}
+
+// final deterministic reduction of the loss partials (single block, fp64 accumulation)
+__global__ void __launch_bounds__(256) loss_finalize_kernel(const float* __restrict__ partials, int n, float* __restrict__ out) {
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)partials[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = (float)red[0];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// bias gradient: column sums of dZ [M, ld] over rows, two-stage deterministic.
+// grid = (Np/64, S); block = 256 = 64 columns x 4 row lanes; partial [S][Np] written to `out + s*stride`.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename TZ>
+__device__ __forceinline__ float load_as_float(const TZ* p);
+template <> __device__ __forceinline__ float load_as_float<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename TZ>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const TZ* __restrict__ dz, int ld, int64_t M, float* __restrict__ out, size_t split_stride) {
+  __shared__ float red[4][64];
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int rl = threadIdx.x >> 6;
+  const int S = gridDim.y;
+  const int64_t rows_per = (M + S - 1) / S;
+  const int64_t r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+  float s = 0.f;
+  for (int64_t r = r0 + rl; r < r1; r += 4) s += load_as_float<TZ>(dz + r * ld + c);
+  red[rl][threadIdx.x & 63] = s;
+  __syncthreads();
+  if (rl == 0) out[(size_t)blockIdx.y * split_stride + c] = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// reduce split partials in a fixed order: grad[i] = sum_s ws[s*stride + i]
+// ---------------------------------------------------------------------------------------------------------------
+struct Segment { const float* ws; size_t stride; float* grad; int64_t len; int splits; };
+struct SegmentTable { int n; Segment seg[2 * CSB_MAX_LAYERS]; };
+
+// one launch for every gradient segment: blockIdx.y = segment
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const SegmentTable tab) {
+  const Segment sg = tab.seg[blockIdx.y];
+  for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4; i < sg.len; i += (int64_t)gridDim.x * blockDim.x * 4) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < sg.splits; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(sg.ws + (size_t)s * sg.stride + i);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    *reinterpret_cast<float4*>(sg.grad + i) = a;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// optimizer: flat element-wise update over the padded parameter buffer (padding has zero gradient -> stays zero)
+// ---------------------------------------------------------------------------------------------------------------
+struct OptParams {
+  int rule;
+  float lr, beta1, beta2, eps, wd;
+  float bc1, bc2;          // 1 - beta^t
+};
+
+__global__ void __launch_bounds__(256)
+opt_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+           const OptParams o) {
+  for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4; i < n; i += (int64_t)gridDim.x * blockDim.x * 4) {
+    float4 w4 = *reinterpret_cast<float4*>(w + i);
+    const float4 g4 = *reinterpret_cast<const float4*>(g + i);
+    float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+    const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+    if (o.rule == CSB_OPT_SGD) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wv[j] -= o.lr * (gv[j] + o.wd * wv[j]);
+    } else {
+      float4 m4 = *reinterpret_cast<float4*>(m + i), v4 = *reinterpret_cast<float4*>(v + i);
+      float mv[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (o.rule == CSB_OPT_ADAM_KERAS) {
+          // keras Adam.update_step: alpha = lr*sqrt(1-b2^t)/(1-b1^t); m += (g-m)(1-b1); v += (g^2-v)(1-b2); w -= alpha*m/(sqrt(v)+eps)
+          const float alpha = o.lr * sqrtf(o.bc2) / o.bc1;
+          mv[j] += (gv[j] - mv[j]) * (1.f - o.beta1);
+          vv[j] += (gv[j] * gv[j] - vv[j]) * (1.f - o.beta2);
+          wv[j] -= alpha * mv[j] / (sqrtf(vv[j]) + o.eps);
+        } else {
+          // torch.optim.Adam (L2 decay folded into g)
+          const float ge = gv[j] + o.wd * wv[j];
+          mv[j] = o.beta1 * mv[j] + (1.f - o.beta1) * ge;
+          vv[j] = o.beta2 * vv[j] + (1.f - o.beta2) * ge * ge;
+          wv[j] -= (o.lr / o.bc1) * mv[j] / (sqrtf(vv[j]) / sqrtf(o.bc2) + o.eps);
+        }
+      }
+      *reinterpret_cast<float4*>(m + i) = make_float4(mv[0], mv[1], mv[2], mv[3]);
+      *reinterpret_cast<float4*>(v + i) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    }
+    *reinterpret_cast<float4*>(w + i) = make_float4(wv[0], wv[1], wv[2], wv[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// bf16 weight repack: from the fp32 master W [Kp, Np] write W16 [Kp, Np] and Wt16 [Np, Kp] (32x32 smem transpose)
+// one launch for all layers: blockIdx.y = layer, blockIdx.x = 32x32 tile index
+// ---------------------------------------------------------------------------------------------------------------
+struct RepackLayer { const float* w; __nv_bfloat16* w16; __nv_bfloat16* wt16; int Kp, Np; };
+struct RepackTable { int n; RepackLayer l[CSB_MAX_LAYERS]; };
+
+__global__ void __launch_bounds__(256) repack_kernel(const RepackTable tab) {
+  const RepackLayer L = tab.l[blockIdx.y];
+  const int tiles_n = L.Np / 32, tiles = (L.Kp / 32) * tiles_n;
+  __shared__ float t[32][33];
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int k0 = (tile / tiles_n) * 32, n0 = (tile % tiles_n) * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = k0 + ty + 8 * i;
+      const float v = L.w[(size_t)k * L.Np + n0 + tx];
+      t[ty + 8 * i][tx] = v;
+      L.w16[(size_t)k * L.Np + n0 + tx] = __float2bfloat16_rn(v);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = n0 + ty + 8 * i;
+      L.wt16[(size_t)n * L.Kp + k0 + tx] = __float2bfloat16_rn(t[tx][ty + 8 * i]);
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// flat user blob (unpadded, W_l [K x N], b_l [N]) <-> padded internal buffer (W_l [Kp x Np], b_l [Np])
+// dir 0: user -> padded (padding entries untouched = zero);  dir 1: padded -> user.   blockIdx.y = layer
+// ---------------------------------------------------------------------------------------------------------------
+struct PadLayer { int K, N, Np; size_t w_off, b_off, w_off_user, b_off_user; };
+struct PadTable { int n; PadLayer l[CSB_MAX_LAYERS]; };
+
+__global__ void __launch_bounds__(256) pad_copy_kernel(float* __restrict__ padded, float* __restrict__ user, int dir, const PadTable tab) {
+  const PadLayer L = tab.l[blockIdx.y];
+  const int64_t total = (int64_t)(L.K + 1) * L.N;            // K weight rows + the bias row
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / L.N), c = (int)(i - (int64_t)r * L.N);
+    float* pp = (r < L.K) ? padded + L.w_off + (size_t)r * L.Np + c : padded + L.b_off + c;
+    float* pu = (r < L.K) ? user + L.w_off_user + (size_t)r * L.N + c : user + L.b_off_user + c;
+    if (dir == 0) *pp = *pu; else *pu = *pp;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------------------------
+// out[r, c] = in[r, c] * scale[c] for c < F  (denormalise predictions), in ld_in -> out ld_out
+__global__ void scale_copy_kernel(const float* __restrict__ in, int ld_in, const float* __restrict__ scale,
+                                  float* __restrict__ out, int ld_out, int64_t M, int F) {
+  const int64_t total = M * F;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / F;
+    const int c = (int)(i - r * F);
+    const float v = in[r * ld_in + c];
+    out[r * ld_out + c] = scale ? v * scale[c] : v;
+  }
+}
+
+// CNN layout helpers (climsim_utils/data_utils.py:1693-1760)
+__global__ void cnn_reshape_in_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t N, int nprof, int nscal, int ld) {
+  // (N, 60*nprof + nscal) -> (N, 60, nprof + nscal)
+  const int C = nprof + nscal;
+  const int64_t total = N * 60 * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int l = (int)((i / C) % 60);
+    const int64_t n = i / (60 * C);
+    out[i] = (c < nprof) ? x[n * ld + c * 60 + l] : x[n * ld + nprof * 60 + (c - nprof)];
+  }
+}
+__global__ void cnn_reshape_out_kernel(const float* __restrict__ p, float* __restrict__ out, int64_t N) {
+  // (N, 60, 10) -> (N, 128): channels 0,1 as profiles; channels 2..9 = mean over the 60 levels
+  const int64_t total = N * 128;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i & 127);
+    const int64_t n = i >> 7;
+    const float* src = p + n * 600;
+    if (c < 120) {
+      out[i] = src[(c % 60) * 10 + (c / 60)];
+    } else {
+      float s = 0.f;
+      for (int l = 0; l < 60; ++l) s += src[l * 10 + (c - 120 + 2)];
+      out[i] = s / 60.f;
+    }
+  }
+}
+
+}  // namespace simt
+}  // namespace csb

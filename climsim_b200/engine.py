@@ -1,0 +1,244 @@
+"""Python face of the csb_mlp_* C ABI: ``MLPEngine`` owns one handle (one model replica on one GPU).
+
+Everything here is plumbing -- pointer extraction from torch tensors, the current CUDA stream, error mapping.
+No arithmetic happens in Python and there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class _DevPtr:
+    """Exposes a raw device pointer through __cuda_array_interface__ so torch can alias it (no copy)."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def _f32_cuda(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (climsim_b200 has no CPU path)")
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.to(torch.float32).contiguous()
+    return t
+
+
+class MLPEngine:
+    """A dense-stack column emulator bound to libclimsim_b200.so.
+
+    ``layers`` is a list of ``(units, activation, alpha)``; the last entry is the output layer.  ``head_relu_from``
+    turns the output layer into the reference's two-head output (columns >= head_relu_from get ReLU).
+    """
+
+    def __init__(self, in_dim: int, layers: Sequence[Tuple[int, str, float]], head_relu_from: int = -1,
+                 dtype: str = "bf16", loss: str = "mse", max_batch: int = 65536):
+        self.lib = _lib.load()
+        cfg = _lib.MlpCfg()
+        cfg.in_dim, cfg.n_layers = in_dim, len(layers)
+        for i, (n, act, alpha) in enumerate(layers):
+            cfg.units[i], cfg.act[i], cfg.alpha[i], cfg.layernorm[i] = n, _lib.ACT[act], alpha, 0
+        cfg.head_relu_from, cfg.dtype, cfg.loss, cfg.max_batch = head_relu_from, _lib.DTYPE[dtype], _lib.LOSS[loss], max_batch
+        self._h = C.c_void_p()
+        _lib.check(self.lib.csb_mlp_create(C.byref(cfg), C.byref(self._h)), "csb_mlp_create")
+        self.in_dim, self.out_dim = in_dim, layers[-1][0]
+        self.layer_dims: List[Tuple[int, int]] = []
+        k = in_dim
+        for n, _, _ in layers:
+            self.layer_dims.append((k, n))
+            k = n
+        self.dtype, self.max_batch = dtype, max_batch
+        self.n_params = int(self.lib.csb_mlp_param_count(self._h))
+        self._loss_buf: Optional[torch.Tensor] = None
+
+    # -- construction helpers -----------------------------------------------------------------------------------
+    @classmethod
+    def mlp_v1(cls, units: Sequence[int] = (768, 640, 512, 640, 640), act: str = "leakyrelu", alpha: float = 0.15,
+               in_dim: int = 124, out_lin: int = 120, out_relu: int = 8, **kw) -> "MLPEngine":
+        """MLP_v1 (baseline_models/MLP/training/HPO/baseline_v1/hpo_baseline_v1.py:75-103), best-trial defaults."""
+        out = out_lin + out_relu
+        layers = [(u, act, alpha) for u in units] + [(out, act, alpha), (out, "none", 0.0)]
+        return cls(in_dim, layers, head_relu_from=out_lin, **kw)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.csb_mlp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- parameters ---------------------------------------------------------------------------------------------
+    def set_params_flat(self, flat: np.ndarray) -> None:
+        flat = np.ascontiguousarray(flat, dtype=np.float32)
+        assert flat.size == self.n_params, (flat.size, self.n_params)
+        _lib.check(self.lib.csb_mlp_set_params(self._h, flat.ctypes.data), "csb_mlp_set_params")
+
+    def get_params_flat(self) -> np.ndarray:
+        out = np.empty(self.n_params, dtype=np.float32)
+        _lib.check(self.lib.csb_mlp_get_params(self._h, out.ctypes.data), "csb_mlp_get_params")
+        return out
+
+    def get_grads_flat(self) -> np.ndarray:
+        out = np.empty(self.n_params, dtype=np.float32)
+        _lib.check(self.lib.csb_mlp_get_grads(self._h, out.ctypes.data), "csb_mlp_get_grads")
+        return out
+
+    def set_params_device(self, flat: torch.Tensor) -> None:
+        flat = _f32_cuda(flat, "flat")
+        assert flat.numel() == self.n_params
+        _lib.check(self.lib.csb_mlp_set_params_device(self._h, flat.data_ptr(), _lib.current_stream_ptr()), "csb_mlp_set_params_device")
+
+    def get_params_device(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        out = out if out is not None else torch.empty(self.n_params, dtype=torch.float32, device="cuda")
+        _lib.check(self.lib.csb_mlp_get_params_device(self._h, out.data_ptr(), _lib.current_stream_ptr()), "csb_mlp_get_params_device")
+        return out
+
+    def get_grads_device(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        out = out if out is not None else torch.empty(self.n_params, dtype=torch.float32, device="cuda")
+        _lib.check(self.lib.csb_mlp_get_grads_device(self._h, out.data_ptr(), _lib.current_stream_ptr()), "csb_mlp_get_grads_device")
+        return out
+
+    def split_flat(self, flat: np.ndarray) -> List[np.ndarray]:
+        """flat blob -> [W0 (in,out), b0, W1, b1, ...] views."""
+        out, off = [], 0
+        for k, n in self.layer_dims:
+            out.append(flat[off:off + k * n].reshape(k, n)); off += k * n
+            out.append(flat[off:off + n]); off += n
+        return out
+
+    @staticmethod
+    def keras_to_flat(weights: Sequence[np.ndarray], fused_head: bool = True) -> np.ndarray:
+        """Keras ``get_weights()`` list -> the engine's flat blob.  With ``fused_head`` the last two Dense layers
+        (linear 120 | relu 8) are concatenated column-wise into one layer, matching keras.layers.Concatenate."""
+        ws = [np.asarray(w, dtype=np.float32) for w in weights]
+        if fused_head:
+            w_lin, b_lin, w_relu, b_relu = ws[-4:]
+            ws = ws[:-4] + [np.concatenate([w_lin, w_relu], axis=1), np.concatenate([b_lin, b_relu])]
+        return np.concatenate([w.reshape(-1) for w in ws])
+
+    def flat_to_keras(self, flat: np.ndarray, out_lin: Optional[int] = None) -> List[np.ndarray]:
+        ws = [w.copy() for w in self.split_flat(flat)]
+        if out_lin is not None:
+            w, b = ws[-2], ws[-1]
+            ws = ws[:-2] + [w[:, :out_lin].copy(), b[:out_lin].copy(), w[:, out_lin:].copy(), b[out_lin:].copy()]
+        return ws
+
+    def get_opt_state(self) -> Tuple[np.ndarray, np.ndarray, int]:
+        m, v, step = np.empty(self.n_params, np.float32), np.empty(self.n_params, np.float32), C.c_int64()
+        _lib.check(self.lib.csb_mlp_get_opt_state(self._h, m.ctypes.data, v.ctypes.data, C.byref(step)), "csb_mlp_get_opt_state")
+        return m, v, int(step.value)
+
+    def set_opt_state(self, m: np.ndarray, v: np.ndarray, step: int) -> None:
+        m, v = np.ascontiguousarray(m, np.float32), np.ascontiguousarray(v, np.float32)
+        _lib.check(self.lib.csb_mlp_set_opt_state(self._h, m.ctypes.data, v.ctypes.data, step), "csb_mlp_set_opt_state")
+
+    def set_norm(self, inp_sub=None, inp_div=None, out_scale=None, loss_w=None) -> None:
+        keep = []
+
+        def p(a, n):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            assert a.size == n, (a.size, n)
+            keep.append(a)
+            return a.ctypes.data
+
+        _lib.check(self.lib.csb_mlp_set_norm(self._h, p(inp_sub, self.in_dim), p(inp_div, self.in_dim),
+                                             p(out_scale, self.out_dim), p(loss_w, self.out_dim)), "csb_mlp_set_norm")
+
+    # -- compute ------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _flags(normalize_in: bool, denorm_out: bool, keep: bool) -> int:
+        return (_lib.FWD_NORMALIZE_IN if normalize_in else 0) | (_lib.FWD_DENORM_OUT if denorm_out else 0) | \
+               (_lib.FWD_KEEP_ACTIVATIONS if keep else 0)
+
+    def forward(self, x: torch.Tensor, normalize_in: bool = False, denorm_out: bool = False,
+                keep_activations: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        x = _f32_cuda(x, "x")
+        B = x.shape[0]
+        y = out if out is not None else torch.empty(B, self.out_dim, dtype=torch.float32, device=x.device)
+        _lib.check(self.lib.csb_mlp_forward(self._h, x.data_ptr(), y.data_ptr(), B,
+                                            self._flags(normalize_in, denorm_out, keep_activations),
+                                            _lib.current_stream_ptr()), "csb_mlp_forward")
+        return y
+
+    def backward(self, dy: torch.Tensor, need_dx: bool = False) -> Optional[torch.Tensor]:
+        dy = _f32_cuda(dy, "dy")
+        B = dy.shape[0]
+        dx = torch.empty(B, self.in_dim, dtype=torch.float32, device=dy.device) if need_dx else None
+        _lib.check(self.lib.csb_mlp_backward(self._h, dy.data_ptr(), dx.data_ptr() if need_dx else None, B,
+                                             _lib.current_stream_ptr()), "csb_mlp_backward")
+        return dx
+
+    def train_step(self, x: torch.Tensor, y: torch.Tensor, grad_scale: float = 0.0, normalize_in: bool = False,
+                   loss_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """forward + loss + backward; gradients land in the engine's gradient buffer.  Returns the device scalar loss."""
+        x, y = _f32_cuda(x, "x"), _f32_cuda(y, "y")
+        if loss_out is None:
+            if self._loss_buf is None:
+                self._loss_buf = torch.zeros(1, dtype=torch.float32, device=x.device)
+            loss_out = self._loss_buf
+        _lib.check(self.lib.csb_mlp_train_step(self._h, x.data_ptr(), y.data_ptr(), x.shape[0], grad_scale,
+                                               self._flags(normalize_in, False, False), loss_out.data_ptr(),
+                                               _lib.current_stream_ptr()), "csb_mlp_train_step")
+        return loss_out
+
+    def apply_opt(self, rule: str = "adam_keras", lr: float = 1e-3, beta1: float = 0.9, beta2: float = 0.999,
+                  eps: Optional[float] = None, weight_decay: float = 0.0) -> None:
+        if eps is None:
+            eps = 1e-7 if rule in ("adam_keras", "adam") else 1e-8
+        _lib.check(self.lib.csb_mlp_apply_opt(self._h, _lib.OPT[rule], lr, beta1, beta2, eps, weight_decay,
+                                              _lib.current_stream_ptr()), "csb_mlp_apply_opt")
+
+    def grad_buffer(self) -> torch.Tensor:
+        """The engine's flat (padded) fp32 gradient buffer as a torch tensor aliasing device memory: the message of the
+        data-parallel all-reduce."""
+        ptr, n = C.c_void_p(), C.c_size_t()
+        _lib.check(self.lib.csb_mlp_grad_buffer(self._h, C.byref(ptr), C.byref(n)), "csb_mlp_grad_buffer")
+        return torch.as_tensor(_DevPtr(ptr.value, n.value), device="cuda")
+
+    def train_step_host(self, x_host: torch.Tensor, y_host: torch.Tensor, rule: str = "adam_keras", lr: float = 1e-3,
+                        beta1: float = 0.9, beta2: float = 0.999, eps: Optional[float] = None,
+                        weight_decay: float = 0.0, grad_scale: float = 0.0, normalize_in: bool = False) -> float:
+        """End-to-end step from HOST tensors (pinned recommended): H2D + fwd/loss/bwd + optimizer + D2H loss."""
+        assert not x_host.is_cuda and not y_host.is_cuda and x_host.dtype == torch.float32 and y_host.dtype == torch.float32
+        x_host, y_host = x_host.contiguous(), y_host.contiguous()
+        if eps is None:
+            eps = 1e-7 if rule in ("adam_keras", "adam") else 1e-8
+        loss = C.c_float()
+        _lib.check(self.lib.csb_mlp_train_step_host(self._h, x_host.data_ptr(), y_host.data_ptr(), x_host.shape[0],
+                                                    grad_scale, self._flags(normalize_in, False, False), _lib.OPT[rule],
+                                                    lr, beta1, beta2, eps, weight_decay, C.byref(loss),
+                                                    _lib.current_stream_ptr()), "csb_mlp_train_step_host")
+        return float(loss.value)
+
+    def forward_host(self, x_host: torch.Tensor, normalize_in: bool = False, denorm_out: bool = False) -> torch.Tensor:
+        x_host = x_host.contiguous()
+        y = torch.empty(x_host.shape[0], self.out_dim, dtype=torch.float32)
+        _lib.check(self.lib.csb_mlp_forward_host(self._h, x_host.data_ptr(), y.data_ptr(), x_host.shape[0],
+                                                 self._flags(normalize_in, denorm_out, False), _lib.current_stream_ptr()),
+                   "csb_mlp_forward_host")
+        return y
+
+    def profile(self, enable: bool = True) -> None:
+        _lib.check(self.lib.csb_mlp_profile(self._h, 1 if enable else 0), "csb_mlp_profile")
+
+    def profile_read(self) -> Dict[str, Tuple[float, int]]:
+        """kernel kind -> (accumulated device milliseconds, launches) since profile(True); synchronises."""
+        n = int(self.lib.csb_profile_kind_count())
+        ms, cnt = (C.c_double * n)(), (C.c_int64 * n)()
+        _lib.check(self.lib.csb_mlp_profile_read(self._h, ms, cnt, n), "csb_mlp_profile_read")
+        return {self.lib.csb_profile_kind_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n) if cnt[i] > 0}
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.csb_mlp_launch_count(self._h))

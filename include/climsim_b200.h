@@ -1,0 +1,182 @@
+/* climsim_b200.h -- C ABI of libclimsim_b200.so: the B200-native column-emulator engine.
+ *
+ * The reference (leap-stc/ClimSim) has no FFI / plugin interface: its hot path is whatever TensorFlow or PyTorch
+ * executes for the model graphs built inline in its training scripts.  This header therefore DEFINES the boundary a
+ * maintainer would bind; every entry point names the reference statement(s) it replaces.
+ * Paths are relative to the reference checkout.
+ *
+ * Conventions
+ *   - plain C: opaque handle, POD config, raw pointers and sizes; no C++/torch types.
+ *   - unless a name ends in `_host`, data pointers are DEVICE pointers; the caller owns every buffer.
+ *   - every call returns 0 (CSB_OK) or a negative CSB_E* code, never throws; csb_strerror() describes it and
+ *     csb_last_error() returns the detail string of the most recent failure on the calling thread.
+ *   - all device work is enqueued on the caller's stream (`void* stream` is a cudaStream_t; NULL = default stream);
+ *     calls do not synchronise unless documented (the `_host` variants synchronise before returning).
+ *   - a handle is not thread-safe; distinct handles are independent.
+ *   - arrays are row-major fp32 with the reference's column order (climsim_utils/data_utils.py:172-188,815-820):
+ *     inputs (B,124) = state_t[60] | state_q0001[60] | ps | SOLIN | LHFLX | SHFLX,
+ *     targets (B,128) = ptend_t[60] | ptend_q0001[60] | NETSW FLWDS PRECSC PRECC SOLS SOLL SOLSD SOLLD.
+ *   - there is NO CPU fallback: on a machine without an sm_100 device csb_*_create returns CSB_ENODEV.
+ */
+#ifndef CLIMSIM_B200_H
+#define CLIMSIM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSB_VERSION 100          /* 0.1.0 */
+#define CSB_MAX_LAYERS 24
+
+/* ---- error codes ---------------------------------------------------------------------------------------- */
+enum {
+  CSB_OK = 0,
+  CSB_EINVAL = -1,    /* bad argument / configuration */
+  CSB_ENODEV = -2,    /* no CUDA device of compute capability 10.x */
+  CSB_ENOMEM = -3,    /* device allocation failed */
+  CSB_ECUDA = -4,     /* a CUDA runtime / driver call or kernel launch failed */
+  CSB_ESTATE = -5,    /* call order violated (e.g. backward before forward, batch larger than max_batch) */
+  CSB_EUNSUPPORTED = -6
+};
+
+/* ---- enums ---------------------------------------------------------------------------------------------- */
+/* Activations of the reference's Keras hyper-parameter space (baseline_v1/hpo_baseline_v1.py:67,82-87) */
+enum { CSB_ACT_NONE = 0, CSB_ACT_RELU = 1, CSB_ACT_ELU = 2 /* alpha = 1 */, CSB_ACT_LEAKYRELU = 3 };
+
+/* Arithmetic mode.  CSB_F32: fp32 FFMA everywhere (parity mode, <= 1e-5 relative to the fp32 CPU reference).
+ * CSB_BF16: bf16 operands on the tcgen05 tensor cores with fp32 accumulation in TMEM, fp32 master weights,
+ * fp32 loss / optimizer (throughput mode; tolerance stated in tests/test_mlp_gpu.py). */
+enum { CSB_F32 = 0, CSB_BF16 = 1 };
+
+/* Loss.  MSE: mean_ij w_j (p_ij - y_ij)^2  (w = 1 is Keras 'mse', hpo_baseline_v1.py:127-129).
+ * MAE: mean_ij w_j |p_ij - y_ij|           (CNN mae_adjusted through w, CNN/training/hpo_train.py:114-121). */
+enum { CSB_LOSS_MSE = 0, CSB_LOSS_MAE = 1 };
+
+/* Optimizer update rule.
+ * ADAM_KERAS: keras.optimizers.Adam update_step (hpo_baseline_v1.py:116-117): w -= lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps)
+ * ADAM_TORCH: torch.optim.Adam with L2 weight decay (HSR/training/hsr.py:109-112): w -= lr/(1-b1^t) * m/(sqrt(v/(1-b2^t))+eps)
+ * SGD:        w -= lr * g
+ */
+enum { CSB_OPT_ADAM_KERAS = 0, CSB_OPT_ADAM_TORCH = 1, CSB_OPT_SGD = 2 };
+
+/* flags for csb_mlp_forward */
+enum {
+  CSB_FWD_NORMALIZE_IN = 1,   /* x is raw: apply (x - inp_sub)/inp_div with inf/nan -> 0 (data_utils.py:806-809,894-897) */
+  CSB_FWD_DENORM_OUT = 2,     /* divide predictions by out_scale (data_utils.py:1187-1197, step [0] of output_weighting) */
+  CSB_FWD_KEEP_ACTIVATIONS = 4 /* keep per-layer activations so that csb_mlp_backward may follow */
+};
+
+/* ---- MLP family ----------------------------------------------------------------------------------------- */
+/* A dense stack  h_{l+1} = act_l( LN_l?( h_l W_l + b_l ) ),  l = 0..n_layers-1.
+ *  - MLP_v1 (hpo_baseline_v1.py:75-103): units {768,640,512,640,640,128,128}, act LEAKYRELU(0.15) on the first six
+ *    layers, last layer = the two Keras output Dense layers fused column-wise ([120 linear | 8 relu]):
+ *    act[last] = NONE, head_relu_from = 120.
+ *  - ED (ED/training/ClimSIM_ED_1_3_train.py:56-92): 14 layers, RELU, last ELU.
+ *  - HSR mean / log-precision nets (HSR/training/hsr.py:14-35): layernorm = 1 and RELU on the hidden layers. */
+typedef struct csb_mlp_cfg {
+  int32_t in_dim;                      /* 124 */
+  int32_t n_layers;                    /* 1..CSB_MAX_LAYERS, the output layer included */
+  int32_t units[CSB_MAX_LAYERS];       /* output width of each layer */
+  int32_t act[CSB_MAX_LAYERS];         /* CSB_ACT_* per layer */
+  float   alpha[CSB_MAX_LAYERS];       /* LeakyReLU slope (Keras alpha) */
+  int32_t layernorm[CSB_MAX_LAYERS];   /* 1: LayerNorm(eps 1e-5, affine) between the Linear and the activation */
+  int32_t head_relu_from;              /* last layer only: columns >= this index get ReLU; -1 = none */
+  int32_t dtype;                       /* CSB_F32 | CSB_BF16 */
+  int32_t loss;                        /* CSB_LOSS_* */
+  int64_t max_batch;                   /* capacity (columns per call) of the internal activation buffers */
+} csb_mlp_cfg;
+
+typedef struct csb_mlp csb_mlp;
+
+int  csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out);   /* replaces keras.Model(...)/model.compile (hpo_baseline_v1.py:103,127) */
+int  csb_mlp_destroy(csb_mlp* h);
+
+/* Flat parameter blob, fp32, layer by layer: W_l (in_l x out_l, row-major == Keras kernel layout), b_l (out_l),
+ * then gamma_l, beta_l (out_l each) if layernorm[l].  csb_mlp_param_count() is its length (1 753 472 for MLP_v1). */
+size_t csb_mlp_param_count(const csb_mlp* h);
+int  csb_mlp_set_params(csb_mlp* h, const float* params_host);        /* model.set_weights / load_state_dict */
+int  csb_mlp_get_params(csb_mlp* h, float* params_host);              /* model.get_weights / state_dict (synchronises) */
+int  csb_mlp_get_grads(csb_mlp* h, float* grads_host);                /* same order as the parameter blob (synchronises) */
+/* the same three with DEVICE blobs, stream-ordered (no synchronisation): how an nn.Module / optimizer that keeps its
+ * own flat parameter tensor exchanges weights and gradients with the engine */
+int  csb_mlp_set_params_device(csb_mlp* h, const float* params_dev, void* stream);
+int  csb_mlp_get_params_device(csb_mlp* h, float* params_dev, void* stream);
+int  csb_mlp_get_grads_device(csb_mlp* h, float* grads_dev, void* stream);
+/* optimizer state (m, v, each csb_mlp_param_count() long) and step counter: ModelCheckpoint .h5 incl. optimizer
+ * state (step2_retrain.py:253-261) / torch.save(state_dict) (hsr.py:120-121) */
+int  csb_mlp_get_opt_state(csb_mlp* h, float* m_host, float* v_host, int64_t* step);
+int  csb_mlp_set_opt_state(csb_mlp* h, const float* m_host, const float* v_host, int64_t step);
+
+/* Normalisation / loss vectors (HOST pointers; NULL keeps the default): inp_sub[in_dim] (0), inp_div[in_dim] (1),
+ * out_scale[out_dim] (1), loss_w[out_dim] (1).  data_utils.save_norm (data_utils.py:954-988) produces the first three. */
+int  csb_mlp_set_norm(csb_mlp* h, const float* inp_sub, const float* inp_div, const float* out_scale, const float* loss_w);
+
+/* model.predict / module.forward: x (B,in_dim) -> y_pred (B,out_dim).  step3_inference.ipynb cell 2; hsr.py:28-35 */
+int  csb_mlp_forward(csb_mlp* h, const float* x, float* y_pred, int64_t B, uint32_t flags, void* stream);
+int  csb_mlp_forward_host(csb_mlp* h, const float* x_host, float* y_pred_host, int64_t B, uint32_t flags, void* stream);
+
+/* autograd entry: given dL/dy_pred (B,out_dim) for the batch of the last KEEP_ACTIVATIONS forward, accumulate the
+ * parameter gradients into the internal gradient buffer (overwriting it) and, if dx != NULL, write dL/dx (B,in_dim). */
+int  csb_mlp_backward(csb_mlp* h, const float* dy, float* dx, int64_t B, void* stream);
+
+/* One model.fit inner step minus the optimizer (TF train_function, step2_retrain.py:280-285; hsr.py:122-140):
+ * forward + loss + backward on normalised x (B,in_dim), scaled targets y (B,out_dim).
+ *   loss   = grad_scale * sum_ij w_j (p_ij - y_ij)^2        (or |.| for MAE)
+ *   grads  = d loss / d params, written to the internal flat gradient buffer
+ * grad_scale <= 0 selects 1/(B*out_dim) (Keras global mean); a data-parallel caller passes 1/(global_B*out_dim)
+ * and all-reduces (sums) the gradient buffer.  loss_out (device float, may be NULL) receives the scalar. */
+int  csb_mlp_train_step(csb_mlp* h, const float* x, const float* y, int64_t B, float grad_scale, uint32_t flags,
+                        float* loss_out, void* stream);
+
+/* The internal gradient buffer (device, fp32, padded layout, *n elements) -- the message of the data-parallel
+ * ncclAllReduce (the reference's only collective: DDP gradient allreduce, online_testing/.../train_mlp_h5loader.py:195-207). */
+int  csb_mlp_grad_buffer(csb_mlp* h, float** ptr, size_t* n);
+
+/* optimizer.apply_gradients / opt.step(): consumes the gradient buffer, advances the internal step counter.
+ * rule = CSB_OPT_*;  wd = L2 weight decay (ADAM_TORCH/SGD).  In CSB_BF16 mode also refreshes the bf16 weight copies. */
+int  csb_mlp_apply_opt(csb_mlp* h, int rule, float lr, float beta1, float beta2, float eps, float wd, void* stream);
+
+/* End-to-end step from HOST buffers (pinned recommended): H2D copies of x,y + train_step + apply_opt + D2H of the
+ * loss; synchronises; *loss_host receives the scalar.  This is what a model.fit batch costs a host-side caller. */
+int  csb_mlp_train_step_host(csb_mlp* h, const float* x_host, const float* y_host, int64_t B, float grad_scale,
+                             uint32_t flags, int rule, float lr, float beta1, float beta2, float eps, float wd,
+                             float* loss_host, void* stream);
+
+/* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
+int64_t csb_mlp_launch_count(const csb_mlp* h);
+
+/* Optional per-launch device timing (CUDA events on the caller's stream after every kernel launch).
+ * csb_mlp_profile(h, 1) resets and enables, csb_mlp_profile_read() synchronises and returns, per kernel kind, the
+ * accumulated milliseconds and launch count since the last enable (arrays of csb_profile_kind_count() entries). */
+int  csb_mlp_profile(csb_mlp* h, int enable);
+int  csb_mlp_profile_read(csb_mlp* h, double* ms_by_kind, int64_t* launches_by_kind, int n_kinds);
+int  csb_profile_kind_count(void);
+const char* csb_profile_kind_name(int kind);
+
+/* ---- data_utils device helpers -------------------------------------------------------------------------- */
+/* (x - sub)/div, inf/nan -> 0 on (N,F) fp32; data_utils.py:806-809,894-897. */
+int  csb_normalize(const float* x_raw, const float* sub, const float* div, float* x_out, int64_t N, int32_t F, void* stream);
+/* CNN tensor layout helpers, data_utils.py:1693-1760: (N,124)->(N,60,6), (N,128)->(N,60,10), (N,60,10)->(N,128). */
+int  csb_reshape_input_for_cnn(const float* x, float* out, int64_t N, void* stream);
+int  csb_reshape_target_for_cnn(const float* y, float* out, int64_t N, void* stream);
+int  csb_reshape_target_from_cnn(const float* p, float* out, int64_t N, void* stream);
+
+/* ---- kernel self-test hooks (used by tests/test_gemm_gpu.py; device pointers) ----------------------------- */
+/* C[M,N] (fp32) = A[M,K] * Bt[N,K]^T on the tcgen05 path (both operands K-major bf16, raw uint16 payloads). */
+int  csb_test_gemm_tn(const uint16_t* A, const uint16_t* Bt, float* C, int M, int N, int K, int block_n, void* stream);
+/* C[M,N] (fp32) = A[Kr,M]^T * B[Kr,N]  (both operands MN-major bf16): the weight-gradient contraction over rows. */
+int  csb_test_gemm_nt(const uint16_t* A, const uint16_t* B, float* C, int M, int N, int Kr, int splits, void* stream);
+
+/* ---- misc ---------------------------------------------------------------------------------------------- */
+int         csb_version(void);
+const char* csb_strerror(int code);
+const char* csb_last_error(void);
+int         csb_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* hbm_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLIMSIM_B200_H */

@@ -1,0 +1,77 @@
+"""Diagnostic driver for the tcgen05 GEMM kernels (run on the GPU box): prints per-case errors and, for a failing
+case, enough structure (which rows / columns / k-slices are wrong) to diagnose descriptor or swizzle mistakes."""
+import sys
+import torch
+
+from climsim_b200 import _lib
+
+lib = _lib.load()
+
+
+def report(name, got, ref):
+    err = (got - ref).abs()
+    scale = ref.abs().max().item()
+    nan = torch.isnan(got).sum().item()
+    print(f"{name}: max_err {err.max().item():.4e} scale {scale:.3e} nan {nan} "
+          f"bad_frac {(err > 1e-3 * scale).float().mean().item():.4f}", flush=True)
+    if err.max().item() > 1e-3 * scale or nan:
+        bad = (err > 1e-3 * scale) | torch.isnan(got)
+        rows = bad.any(dim=1).nonzero().flatten()[:16].tolist()
+        cols = bad.any(dim=0).nonzero().flatten()[:16].tolist()
+        print("   bad rows (first 16):", rows, " bad cols (first 16):", cols)
+        print("   got[0,:8]", got[0, :8].tolist())
+        print("   ref[0,:8]", ref[0, :8].tolist())
+        return False
+    return True
+
+
+def tn(M, N, K, bn, structured=False):
+    g = torch.Generator().manual_seed(1)
+    if structured:
+        A = torch.zeros(M, K); A[:, 0] = 1.0                       # picks column 0 of Bt^T: C[m, n] = Bt[n, 0]
+        Bt = torch.arange(N * K, dtype=torch.float32).reshape(N, K) % 251
+    else:
+        A, Bt = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
+    A, Bt = A.to(torch.bfloat16).cuda(), Bt.to(torch.bfloat16).cuda()
+    C = torch.full((M, N), float("nan"), device="cuda")
+    rc = lib.csb_test_gemm_tn(A.data_ptr(), Bt.data_ptr(), C.data_ptr(), M, N, K, bn, None)
+    if rc:
+        print("tn launch error", rc, lib.csb_last_error().decode()); return False
+    try:
+        torch.cuda.synchronize()
+    except Exception as e:
+        print("tn sync error", e); return False
+    return report(f"tn M{M} N{N} K{K} bn{bn} structured={structured}", C, A.float() @ Bt.float().t())
+
+
+def nt(M, N, R, splits, structured=False):
+    g = torch.Generator().manual_seed(2)
+    if structured:
+        A = torch.zeros(R, M); A[0, :] = 1.0                        # C[m, n] = B[0, n]
+        B = torch.arange(R * N, dtype=torch.float32).reshape(R, N) % 251
+    else:
+        A, B = torch.randn(R, M, generator=g), torch.randn(R, N, generator=g)
+    A, B = A.to(torch.bfloat16).cuda(), B.to(torch.bfloat16).cuda()
+    C = torch.full((splits, M, N), float("nan"), device="cuda")
+    rc = lib.csb_test_gemm_nt(A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, R, splits, None)
+    if rc:
+        print("nt launch error", rc, lib.csb_last_error().decode()); return False
+    try:
+        torch.cuda.synchronize()
+    except Exception as e:
+        print("nt sync error", e); return False
+    return report(f"nt M{M} N{N} R{R} s{splits} structured={structured}", C.sum(0), A.float().t() @ B.float())
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    ok = True
+    if which in ("all", "tn"):
+        for args in [(128, 128, 64, 128, True), (128, 128, 64, 128), (128, 128, 128, 128), (128, 256, 64, 256),
+                     (256, 128, 512, 128), (1000, 640, 768, 256), (70000, 128, 128, 128)]:
+            ok &= tn(*args)
+    if which in ("all", "nt"):
+        for args in [(128, 128, 64, 1, True), (128, 128, 64, 1), (128, 128, 128, 1), (128, 256, 256, 1), (64, 64, 1000, 3),
+                     (768, 640, 4096, 4)]:
+            ok &= nt(*args)
+    print("ALL OK" if ok else "FAILURES")

@@ -1,0 +1,68 @@
+"""GPU unit tests of the hand-written tcgen05 GEMM kernels through the C-ABI self-test hooks.
+
+Reference: torch fp32 matmul of the same bf16-rounded operands (the tensor cores multiply bf16 exactly and accumulate
+in fp32, so only the summation order differs: tolerance 1e-3 relative to the row scale is generous)."""
+import ctypes as C
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from climsim_b200 import _lib
+    return _lib.load(), _lib
+
+
+def _bf16_operand(rows, cols, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    a = (scale * torch.randn(rows, cols, generator=g)).to(torch.bfloat16).cuda()
+    return a
+
+
+@pytest.mark.parametrize("M,N,K,bn", [
+    (128, 128, 64, 128),        # one tile, one k-block: the descriptor / swizzle smoke test
+    (128, 128, 128, 128),       # two k-blocks (accumulate flag, smem ring advance)
+    (128, 256, 64, 256),        # N = 256 instruction
+    (256, 128, 512, 128),       # ring wraps (6 stages, 8 k-blocks)
+    (1000, 640, 768, 256),      # ragged M, ragged last n-block (640 = 256 + 256 + 128), layer-1 shape
+    (1000, 640, 768, 128),
+    (4096, 768, 128, 256),      # layer-0 shape
+    (333, 64, 192, 128),        # N = 64 (n_valid < BN)
+    (70000, 128, 128, 128),     # many tiles per CTA: both TMEM accumulator buffers, phase flips
+])
+def test_gemm_tn(M, N, K, bn):
+    lib, L = _lib()
+    A = _bf16_operand(M, K, 1)
+    Bt = _bf16_operand(N, K, 2)
+    Cout = torch.full((M, N), float("nan"), device="cuda")
+    L.check(lib.csb_test_gemm_tn(A.data_ptr(), Bt.data_ptr(), Cout.data_ptr(), M, N, K, bn, None), "csb_test_gemm_tn")
+    torch.cuda.synchronize()
+    ref = A.float() @ Bt.float().t()
+    err = (Cout - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 1e-3 * scale, (err, scale)
+
+
+@pytest.mark.parametrize("M,N,R,splits", [
+    (128, 128, 64, 1),          # one 64-row block: MN-major descriptor smoke test
+    (128, 128, 128, 1),
+    (128, 256, 256, 1),
+    (64, 64, 1000, 3),          # M = N = 64 (single chunk), ragged R, split over rows
+    (768, 640, 4096, 4),        # dW of layer 1
+    (128, 768, 5000, 7),        # dW of layer 0, ragged R, splits that do not divide
+    (640, 128, 70000, 16),
+])
+def test_gemm_nt(M, N, R, splits):
+    lib, L = _lib()
+    A = _bf16_operand(R, M, 3)
+    B = _bf16_operand(R, N, 4)
+    Cout = torch.full((splits, M, N), float("nan"), device="cuda")
+    L.check(lib.csb_test_gemm_nt(A.data_ptr(), B.data_ptr(), Cout.data_ptr(), M, N, R, splits, None), "csb_test_gemm_nt")
+    torch.cuda.synchronize()
+    got = Cout.sum(dim=0)
+    ref = A.float().t() @ B.float()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 1e-3 * scale, (err, scale)
