@@ -80,7 +80,9 @@ static int launch_tn(const CUtensorMap& ta, const CUtensorMap& tb, const tc::Gem
   const int tiles = (int)(ceil_div(p.M, tc::BM) * ceil_div(p.N, BN));
   if (tiles == 0) return CSB_OK;
   const int grid = std::min(tiles, sm_count);
-  kern<<<grid, tc::NUM_THREADS, L::TOTAL, st>>>(ta, tb, p);
+  tc::GemmParams q = p;
+  q.b_box_rows = std::min(p.N, BN);      // must equal the box the B tensor map was encoded with
+  kern<<<grid, tc::NUM_THREADS, L::TOTAL, st>>>(ta, tb, q);
   CSB_CUDA_CHECK(cudaGetLastError());
   return CSB_OK;
 }

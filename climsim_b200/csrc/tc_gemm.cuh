@@ -37,6 +37,7 @@ enum Epi : int {
 
 struct GemmParams {
   int M, N, K;                 // problem (N, K multiples of 64; M arbitrary)
+  int b_box_rows;              // rows of the B-operand TMA box (== min(N, BN)): sets the expected transaction bytes
   int act;                     // CSB_ACT_* for EPI_BIAS_ACT / EPI_DGRAD (activation of the layer whose output is stored / was saved)
   float alpha;
   int head_relu_from;          // EPI_HEAD_*: columns >= this get ReLU (-1: none); otherwise `act` applies
@@ -346,7 +347,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int m0 = (tile / num_n_blocks) * BM, n0 = (tile % num_n_blocks) * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1u);
-          mbar_expect_tx(full_bar(s), L::STAGE_BYTES);
+          mbar_expect_tx(full_bar(s), (uint32_t)(L::A_BYTES + p.b_box_rows * BK * 2));
           const uint32_t sa = smem_base + s * L::STAGE_BYTES;
           tma_load_2d(sa, &tmap_a, full_bar(s), kb * BK, m0);
           tma_load_2d(sa + L::A_BYTES, &tmap_b, full_bar(s), kb * BK, n0);

@@ -1,6 +1,10 @@
 """Diagnostic driver for the tcgen05 GEMM kernels (run on the GPU box): prints per-case errors and, for a failing
 case, enough structure (which rows / columns / k-slices are wrong) to diagnose descriptor or swizzle mistakes."""
+import os
+import subprocess
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 from climsim_b200 import _lib
@@ -63,15 +67,25 @@ def nt(M, N, R, splits, structured=False):
     return report(f"nt M{M} N{N} R{R} s{splits} structured={structured}", C.sum(0), A.float().t() @ B.float())
 
 
+TN_CASES = [(128, 128, 64, 128, True), (128, 128, 64, 128), (333, 64, 192, 128), (256, 128, 512, 128),
+            (1000, 640, 768, 256), (70000, 128, 128, 128), (65536, 640, 768, 256)]
+NT_CASES = [(128, 128, 64, 1, True), (128, 128, 64, 1), (128, 128, 128, 1), (128, 256, 256, 1), (64, 64, 1000, 3),
+            (768, 640, 4096, 4), (640, 128, 70000, 16)]
+
 if __name__ == "__main__":
+    # every case in its own process: a trapped kernel poisons the CUDA context
+    if len(sys.argv) >= 3 and sys.argv[1] == "one":
+        kind, args = sys.argv[2], [int(a) for a in sys.argv[3:]]
+        fn = tn if kind == "tn" else nt
+        structured = bool(args[4]) if len(args) > 4 else False
+        sys.exit(0 if fn(*args[:4], structured=structured) else 1)
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     ok = True
-    if which in ("all", "tn"):
-        for args in [(128, 128, 64, 128, True), (128, 128, 64, 128), (128, 128, 128, 128), (128, 256, 64, 256),
-                     (256, 128, 512, 128), (1000, 640, 768, 256), (70000, 128, 128, 128)]:
-            ok &= tn(*args)
-    if which in ("all", "nt"):
-        for args in [(128, 128, 64, 1, True), (128, 128, 64, 1), (128, 128, 128, 1), (128, 256, 256, 1), (64, 64, 1000, 3),
-                     (768, 640, 4096, 4)]:
-            ok &= nt(*args)
+    for kind, cases in (("tn", TN_CASES), ("nt", NT_CASES)):
+        if which not in ("all", kind):
+            continue
+        for c in cases:
+            r = subprocess.run([sys.executable, __file__, "one", kind] + [str(int(a)) for a in c], capture_output=True, text=True, timeout=120)
+            print(r.stdout.strip() or r.stderr.strip()[-500:], flush=True)
+            ok &= r.returncode == 0
     print("ALL OK" if ok else "FAILURES")

@@ -76,7 +76,12 @@ def test_train_step_fp32_parity(units, B):
     g_ref = _flat([p.grad for p in ref.params])
     g_got = eng.get_grads_flat()
     assert _per_tensor(eng, g_got, g_ref, _relmax) <= 1e-5
-    # Keras Adam (epsilon 1e-7) for three steps with the cyclical learning rate of the reference
+    # Keras Adam (epsilon 1e-7), three steps on the reference's cyclical learning rate.  Adam divides by sqrt(v): an
+    # element whose gradient is pure cancellation noise gets an O(lr) update of arbitrary sign in ANY fp32
+    # implementation, so weights are compared with the oracle optimizer fed the engine's gradients (the optimizer
+    # arithmetic in isolation, <= 1e-6), while the gradients themselves are re-checked against the oracle's own
+    # backward pass at every step (<= 1e-5 per tensor).
+    from climsim_b200 import MLPEngine
     m = [torch.zeros_like(p) for p in ref.params]
     v = [torch.zeros_like(p) for p in ref.params]
     for t in range(1, 4):
@@ -86,11 +91,11 @@ def test_train_step_fp32_parity(units, B):
                 p.grad = None
             M.mse(y, ref(x)).backward()
             eng.train_step(x.cuda(), y.cuda())
-        M.keras_adam_step(ref.params, [p.grad for p in ref.params], m, v, t, lr)
+            assert _per_tensor(eng, eng.get_grads_flat(), _flat([p.grad for p in ref.params]), _relmax) <= 1e-5
+        g_eng = [torch.from_numpy(a) for a in eng.flat_to_keras(eng.get_grads_flat(), out_lin=120)]
+        M.keras_adam_step(ref.params, g_eng, m, v, t, lr)
         eng.apply_opt("adam_keras", lr=lr)
-    w_ref = _flat(ref.params)
-    w_got = eng.get_params_flat()
-    assert _per_tensor(eng, w_got, w_ref, _relmax) <= 1e-5
+        assert _per_tensor(eng, eng.get_params_flat(), _flat(ref.params), _relmax) <= 1e-6
 
 
 def test_weighted_loss_and_normalisation_fp32():
