@@ -166,6 +166,8 @@ class MLPEngine:
         x = _f32_cuda(x, "x")
         B = x.shape[0]
         y = out if out is not None else torch.empty(B, self.out_dim, dtype=torch.float32, device=x.device)
+        if B == 0:
+            return y
         _lib.check(self.lib.csb_mlp_forward(self._h, x.data_ptr(), y.data_ptr(), B,
                                             self._flags(normalize_in, denorm_out, keep_activations),
                                             _lib.current_stream_ptr()), "csb_mlp_forward")

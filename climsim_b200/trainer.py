@@ -1,0 +1,83 @@
+"""Training driver on top of ``MLPEngine``: what ``model.fit`` does per batch in the reference
+(baseline_models/MLP/.../step2_retrain.py:280-285; HSR/training/hsr.py:122-140), one process per GPU.
+
+Data parallelism: columns are i.i.d., so each rank takes B/N columns, the flat gradient buffer
+is summed with one NCCL all-reduce over NVLink (the reference's only collective is the DDP gradient all-reduce of its
+online trainer, online_testing/.../train_mlp_h5loader.py:195-207), and every rank applies the same optimizer step.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .engine import MLPEngine
+
+
+def glorot_uniform_flat(layer_dims: Sequence[tuple], seed: int = 0) -> np.ndarray:
+    """Keras default initialisation (glorot_uniform kernels, zero biases) as the engine's flat blob."""
+    rng = np.random.default_rng(seed)
+    parts = []
+    for k, n in layer_dims:
+        lim = math.sqrt(6.0 / (k + n))
+        parts += [rng.uniform(-lim, lim, size=(k, n)).astype(np.float32).reshape(-1), np.zeros(n, np.float32)]
+    return np.concatenate(parts)
+
+
+def cyclical_lr(step: int, initial_lr: float = 2.5e-4, max_lr: float = 2.5e-3, step_size: float = 2.0) -> float:
+    """tfa CyclicalLearningRate(scale_fn=1/2**(x-1), scale_mode='cycle') as configured at hpo_baseline_v1.py:105-114."""
+    cycle = math.floor(1 + step / (2 * step_size))
+    x = abs(step / step_size - 2 * cycle + 1)
+    return initial_lr + (max_lr - initial_lr) * max(0.0, 1 - x) / (2.0 ** (cycle - 1))
+
+
+class Trainer:
+    """``step(x, y)`` = H2D (if host tensors) -> forward + loss + backward -> gradient all-reduce -> optimizer."""
+
+    def __init__(self, engine: MLPEngine, rule: str = "adam_keras", lr: float | Callable[[int], float] = 1e-3,
+                 beta1: float = 0.9, beta2: float = 0.999, eps: Optional[float] = None, weight_decay: float = 0.0,
+                 process_group=None):
+        self.engine, self.rule, self.lr = engine, rule, lr
+        self.beta1, self.beta2, self.eps, self.weight_decay = beta1, beta2, eps, weight_decay
+        self.pg = process_group
+        self.world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(process_group)
+        self.iteration = 0
+        self._grad = engine.grad_buffer() if self.world > 1 else None
+        self._x = self._y = None
+        self._loss = torch.zeros(1, dtype=torch.float32, device="cuda")
+
+    def _lr(self) -> float:
+        return float(self.lr(self.iteration)) if callable(self.lr) else float(self.lr)
+
+    def step(self, x: torch.Tensor, y: torch.Tensor, normalize_in: bool = False, return_loss: bool = True):
+        """x (B_local, in_dim), y (B_local, out_dim): CUDA tensors, or (pinned) host tensors that are copied first.
+        Returns the loss of the GLOBAL batch as a Python float when ``return_loss`` (one D2H read), else the device scalar
+        holding this rank's share."""
+        eng = self.engine
+        B = x.shape[0]
+        lr = self._lr()
+        if self.world == 1 and not x.is_cuda:
+            loss = eng.train_step_host(x, y, rule=self.rule, lr=lr, beta1=self.beta1, beta2=self.beta2, eps=self.eps,
+                                       weight_decay=self.weight_decay, normalize_in=normalize_in)
+            self.iteration += 1
+            return loss
+        if not x.is_cuda:
+            if self._x is None or self._x.shape[0] < B:
+                self._x = torch.empty(B, eng.in_dim, dtype=torch.float32, device="cuda")
+                self._y = torch.empty(B, eng.out_dim, dtype=torch.float32, device="cuda")
+            self._x[:B].copy_(x, non_blocking=True)
+            self._y[:B].copy_(y, non_blocking=True)
+            x, y = self._x[:B], self._y[:B]
+        scale = 1.0 / (B * self.world * eng.out_dim)            # global-mean MSE, as Keras computes on the global batch
+        eng.train_step(x, y, grad_scale=scale, normalize_in=normalize_in, loss_out=self._loss)
+        if self.world > 1:
+            torch.distributed.all_reduce(self._grad, group=self.pg)
+            if return_loss:
+                torch.distributed.all_reduce(self._loss, group=self.pg)
+        eng.apply_opt(self.rule, lr=lr, beta1=self.beta1, beta2=self.beta2, eps=self.eps, weight_decay=self.weight_decay)
+        self.iteration += 1
+        return float(self._loss.item()) if return_loss else self._loss

@@ -110,6 +110,55 @@ class MLPRef:
 
     __call__ = forward
 
+    def manual_train_step(self, x: torch.Tensor, y: torch.Tensor, w: Optional[torch.Tensor] = None,
+                          grad_scale: Optional[float] = None, emulate_bf16: bool = False):
+        """Explicit forward + weighted-MSE + backward (no autograd): returns (loss, grads in ``params`` order).
+
+        With ``emulate_bf16`` every tensor the tensor-core path stores in bf16 is rounded at the same point
+        (normalised input, weights, post-activation outputs, every dZ) while all products accumulate in fp32 --
+        the arithmetic contract of the CSB_BF16 mode (climsim_b200/csrc/mlp_engine.cu), so that its gradients can
+        be checked tightly instead of against a loose fp32 tolerance.  Without it this is plain fp32 backprop and
+        must agree with autograd (tests/test_oracle_pinning.py)."""
+        rnd = _bf16_round if emulate_bf16 else (lambda t: t)
+        with torch.no_grad():
+            p = [t.detach() for t in self.params]
+            n_hidden = len(self.units) + 1
+            B = x.shape[0]
+            out_dim = self.out_lin + self.out_relu
+            scale = grad_scale if grad_scale is not None else 1.0 / (B * out_dim)
+            w = torch.ones(out_dim, dtype=self.dtype) if w is None else w.to(self.dtype)
+            acts = [rnd(x.to(self.dtype))]
+            for i in range(n_hidden):
+                acts.append(rnd(activation(self.act, acts[-1] @ rnd(p[2 * i]) + p[2 * i + 1], self.alpha)))
+            w_head = torch.cat([p[2 * n_hidden], p[2 * n_hidden + 2]], dim=1)
+            b_head = torch.cat([p[2 * n_hidden + 1], p[2 * n_hidden + 3]])
+            z = acts[-1] @ rnd(w_head) + b_head
+            pred = torch.cat([z[:, :self.out_lin], torch.relu(z[:, self.out_lin:])], dim=1)
+            d = pred - y.to(self.dtype)
+            loss = (w * d * d).sum() * scale
+            dact_head = torch.ones_like(pred)
+            dact_head[:, self.out_lin:] = (pred[:, self.out_lin:] > 0).to(self.dtype)
+            dz = rnd(2.0 * w * d * scale * dact_head)
+            grads: List[Optional[torch.Tensor]] = [None] * len(p)
+            g_w_head, g_b_head = acts[-1].t() @ dz, dz.sum(dim=0)
+            grads[2 * n_hidden], grads[2 * n_hidden + 2] = g_w_head[:, :self.out_lin], g_w_head[:, self.out_lin:]
+            grads[2 * n_hidden + 1], grads[2 * n_hidden + 3] = g_b_head[:self.out_lin], g_b_head[self.out_lin:]
+            w_next = rnd(w_head)
+            for i in range(n_hidden - 1, -1, -1):
+                a = acts[i + 1]
+                if self.act == "relu":
+                    da = (a > 0).to(self.dtype)
+                elif self.act == "leakyrelu":
+                    da = torch.where(a > 0, torch.ones_like(a), torch.full_like(a, self.alpha))
+                elif self.act == "elu":
+                    da = torch.where(a > 0, torch.ones_like(a), a + 1.0)
+                else:
+                    da = torch.ones_like(a)
+                dz = rnd((dz @ w_next.t()) * da)
+                grads[2 * i], grads[2 * i + 1] = acts[i].t() @ dz, dz.sum(dim=0)
+                w_next = rnd(p[2 * i])
+        return loss, grads
+
 
 # --------------------------------------------------------------------------------------------------------------
 # ED  (Keras encoder-decoder MLP)

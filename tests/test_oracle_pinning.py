@@ -194,3 +194,19 @@ def test_conv1d_same_matches_direct_sum():
                 ref[:, l] += x[:, s] @ w[t]
     ref += b
     torch.testing.assert_close(y, ref, rtol=1e-5, atol=1e-6)
+
+
+def test_manual_backward_matches_autograd():
+    """The explicit backward used to emulate the bf16 rounding points is, without rounding, plain backprop."""
+    for act in ("leakyrelu", "relu", "elu"):
+        ref = M.MLPRef(units=(96, 64), act=act, seed=2)
+        ref.randomize_biases(3)
+        g = torch.Generator().manual_seed(4)
+        x, y = 0.2 * torch.randn(50, 124, generator=g), 0.1 * torch.randn(50, 128, generator=g)
+        w = torch.linspace(0.5, 2.0, 128)
+        loss = M.weighted_mse(y, ref(x), w)
+        loss.backward()
+        l2, grads = ref.manual_train_step(x, y, w=w)
+        assert l2.item() == pytest.approx(loss.item(), rel=1e-6)
+        for p, gm in zip(ref.params, grads):
+            torch.testing.assert_close(gm, p.grad, rtol=1e-4, atol=1e-9)
