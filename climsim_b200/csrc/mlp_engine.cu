@@ -69,7 +69,8 @@ static int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t cols, uint
 // tensor-core launch helpers
 // ---------------------------------------------------------------------------------------------------------------
 template <int BN, int STAGES, int EPI>
-static int launch_tn(const CUtensorMap& ta, const CUtensorMap& tb, const tc::GemmParams& p, int sm_count, cudaStream_t st) {
+static int launch_tn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tout, const CUtensorMap* tsaved,
+                     const tc::GemmParams& p, int sm_count, cudaStream_t st) {
   using L = tc::TnSmem<BN, STAGES>;
   auto kern = tc::gemm_tn_kernel<BN, STAGES, EPI>;
   static bool attr_set = false;
@@ -82,15 +83,17 @@ static int launch_tn(const CUtensorMap& ta, const CUtensorMap& tb, const tc::Gem
   const int grid = std::min(tiles, sm_count);
   tc::GemmParams q = p;
   q.b_box_rows = std::min(p.N, BN);      // must equal the box the B tensor map was encoded with
-  kern<<<grid, tc::NUM_THREADS, L::TOTAL, st>>>(ta, tb, q);
+  // unused descriptor slots get a valid (never dereferenced) descriptor
+  kern<<<grid, tc::TN_THREADS, L::TOTAL, st>>>(ta, tb, tout ? *tout : ta, tsaved ? *tsaved : ta, q);
   CSB_CUDA_CHECK(cudaGetLastError());
   return CSB_OK;
 }
 
 template <int EPI>
-static int launch_tn_auto(const CUtensorMap& ta, const CUtensorMap& tb, const tc::GemmParams& p, int sm_count, cudaStream_t st) {
-  if (p.N > 128) return launch_tn<256, 4, EPI>(ta, tb, p, sm_count, st);
-  return launch_tn<128, 6, EPI>(ta, tb, p, sm_count, st);
+static int launch_tn_auto(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tout, const CUtensorMap* tsaved,
+                          const tc::GemmParams& p, int sm_count, cudaStream_t st) {
+  if (p.N > 128) return launch_tn<256, 3, EPI>(ta, tb, tout, tsaved, p, sm_count, st);
+  return launch_tn<128, 5, EPI>(ta, tb, tout, tsaved, p, sm_count, st);
 }
 static inline int tn_block_n(int N) { return N > 128 ? 256 : 128; }
 
@@ -347,7 +350,7 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
     li.nt_block_n = tn_block_n(li.Np);
     const int tiles = (int)(ceil_div(li.Kp, 128) * ceil_div(li.Np, li.nt_block_n));
     li.max_w_splits = h->bf16 ? std::max(1, std::min(64, sm / tiles)) : 1;
-    li.b_splits = 32;
+    li.b_splits = h->bf16 ? li.max_w_splits : 32;
     li.ws_w_off = ws_off; ws_off += (size_t)li.max_w_splits * li.Kp * li.Np;
     li.ws_b_off = ws_off; ws_off += (size_t)li.b_splits * li.Np;
     h->max_np = std::max(h->max_np, li.Np);
@@ -372,7 +375,7 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
   CKA(h->pred, (size_t)h->cap * h->out_p * 4);
   CKA(h->d_sub, (size_t)h->in_p * 4); CKA(h->d_div, (size_t)h->in_p * 4);
   CKA(h->d_out_scale, (size_t)h->out_p * 4); CKA(h->d_inv_out_scale, (size_t)h->out_p * 4); CKA(h->d_loss_w, (size_t)h->out_p * 4);
-  h->n_loss_partials = (int)std::max<int64_t>(h->cap / 128 * 4, 8 * sm);
+  h->n_loss_partials = (int)std::max<int64_t>(h->cap / 128 * tc::TN_EPI_WARPS, 8 * sm);
   CKA(h->loss_partials, (size_t)h->n_loss_partials * 4);
   CKA(h->d_loss, 4);
   if (h->bf16) {
@@ -569,7 +572,7 @@ static int run_hidden_forward(csb_mlp* h, int64_t B, cudaStream_t st) {
       tc::GemmParams p = {};
       p.M = (int)B; p.N = li.Np; p.K = li.Kp; p.act = li.act; p.alpha = li.alpha; p.head_relu_from = -1;
       p.bias = h->params + li.b_off; p.out = h->act[l]; p.ld_out = li.Np;
-      int rc = launch_tn_auto<tc::EPI_BIAS_ACT>(h->tm_in[l].a_k128, h->tm_wt[l], p, h->sm_count, st);
+      int rc = launch_tn_auto<tc::EPI_BIAS_ACT>(h->tm_in[l].a_k128, h->tm_wt[l], &h->tm_in[l + 1].a_k128, nullptr, p, h->sm_count, st);
       if (rc) return rc;
     } else {
       simt::SgemmParams p = {};
@@ -602,9 +605,9 @@ static int run_head(csb_mlp* h, int64_t B, int fused_loss, const float* y, float
       p.y = y; p.ld_y = h->out_dim; p.loss_w = h->d_loss_w; p.grad_scale = grad_scale; p.loss_kind = h->cfg.loss;
       p.loss_partials = h->loss_partials;
       p.pred = nullptr;
-      rc = launch_tn_auto<tc::EPI_HEAD_LOSS>(h->tm_in[l].a_k128, h->tm_wt[l], p, h->sm_count, st);
+      rc = launch_tn_auto<tc::EPI_HEAD_LOSS>(h->tm_in[l].a_k128, h->tm_wt[l], &h->tm_dz[l].a_k128, nullptr, p, h->sm_count, st);
     } else {
-      rc = launch_tn_auto<tc::EPI_HEAD_OUT>(h->tm_in[l].a_k128, h->tm_wt[l], p, h->sm_count, st);
+      rc = launch_tn_auto<tc::EPI_HEAD_OUT>(h->tm_in[l].a_k128, h->tm_wt[l], nullptr, nullptr, p, h->sm_count, st);
     }
     if (rc) return rc;
   } else {
@@ -662,11 +665,12 @@ static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st)
     if (h->bf16) {
       const int num_rb = (int)ceil_div(B, 64);
       splits = std::max(1, std::min(li.max_w_splits, num_rb));
-      tc::NtParams p;
+      tc::NtParams p = {};
       p.M = li.Kp; p.N = li.Np; p.R = (int)B;
       p.rb_per_split = (int)ceil_div(num_rb, splits);
       splits = (int)ceil_div(num_rb, p.rb_per_split);
       p.out = h->ws + li.ws_w_off; p.ld_out = li.Np; p.split_stride = (size_t)li.Kp * li.Np;
+      p.colsum_out = h->ws + li.ws_b_off; p.colsum_stride = (size_t)li.Np;      // bias gradient fused into this kernel
       int rc = launch_nt_auto(h->tm_in[l].mn64, h->tm_dz[l].mn64, p, splits, st);
       if (rc) return rc;
     } else {
@@ -682,12 +686,13 @@ static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st)
     prof_mark(h, K_GEMM_WGRAD, st);
     tab.seg[tab.n++] = {h->ws + li.ws_w_off, (size_t)li.Kp * li.Np, h->grads + li.w_off, (int64_t)li.Kp * li.Np, splits};
     max_len = std::max<int64_t>(max_len, (int64_t)li.Kp * li.Np);
-    // ---- bias gradient db_l = column sums of dZ_l
-    {
+    // ---- bias gradient db_l = column sums of dZ_l (CSB_BF16: computed inside the weight-gradient kernel above)
+    if (h->bf16) {
+      tab.seg[tab.n++] = {h->ws + li.ws_b_off, (size_t)li.Np, h->grads + li.b_off, (int64_t)li.Np, splits};
+    } else {
       const int S = (int)std::max<int64_t>(1, std::min<int64_t>(li.b_splits, ceil_div(B, 256)));
       dim3 grid((unsigned)(li.Np / 64), (unsigned)S);
-      if (h->bf16) simt::colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(dz16(h, l), li.Np, B, h->ws + li.ws_b_off, (size_t)li.Np);
-      else simt::colsum_kernel<float><<<grid, 256, 0, st>>>(dz32(h, l), li.Np, B, h->ws + li.ws_b_off, (size_t)li.Np);
+      simt::colsum_kernel<float><<<grid, 256, 0, st>>>(dz32(h, l), li.Np, B, h->ws + li.ws_b_off, (size_t)li.Np);
       CSB_CUDA_CHECK(cudaGetLastError());
       prof_mark(h, K_COLSUM, st);
       tab.seg[tab.n++] = {h->ws + li.ws_b_off, (size_t)li.Np, h->grads + li.b_off, (int64_t)li.Np, S};
@@ -700,7 +705,7 @@ static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st)
         p.M = (int)B; p.N = li.Kp; p.K = li.Np; p.act = lp.act; p.alpha = lp.alpha; p.head_relu_from = -1;
         p.out = dz16(h, l - 1); p.ld_out = lp.Np;
         p.saved = reinterpret_cast<const __nv_bfloat16*>(h->act[l - 1]); p.ld_saved = lp.Np;
-        int rc = launch_tn_auto<tc::EPI_DGRAD>(h->tm_dz[l].a_k128, h->tm_w[l], p, h->sm_count, st);
+        int rc = launch_tn_auto<tc::EPI_DGRAD>(h->tm_dz[l].a_k128, h->tm_w[l], &h->tm_dz[l - 1].a_k128, &h->tm_in[l].a_k128, p, h->sm_count, st);
         if (rc) return rc;
       } else {
         simt::SgemmParams p = {};
@@ -721,7 +726,7 @@ static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st)
       if (h->bf16) {
         tc::GemmParams p = {};
         p.M = (int)B; p.N = li.Kp; p.K = li.Np; p.out = h->dx_tmp; p.ld_out = h->in_p;
-        int rc = launch_tn_auto<tc::EPI_F32>(h->tm_dz[0].a_k128, h->tm_w[0], p, h->sm_count, st);
+        int rc = launch_tn_auto<tc::EPI_F32>(h->tm_dz[0].a_k128, h->tm_w[0], nullptr, nullptr, p, h->sm_count, st);
         if (rc) return rc;
       } else {
         simt::SgemmParams p = {};
@@ -760,7 +765,7 @@ int csb_mlp_train_step(csb_mlp* h, const float* x, const float* y, int64_t B, fl
   const int l = h->L - 1;
   if (h->bf16) {
     if ((rc = run_head(h, B, 1, y, grad_scale, st))) return rc;
-    n_partials = (int)ceil_div(B, 128) * 4;
+    n_partials = (int)ceil_div(B, 128) * tc::TN_EPI_WARPS;
   } else {
     if ((rc = run_head(h, B, 0, nullptr, 0.f, st))) return rc;
     const int grid = std::min(h->n_loss_partials, grid_for(B * h->out_p, 256, h->sm_count));
@@ -915,11 +920,11 @@ int csb_test_gemm_tn(const uint16_t* A, const uint16_t* Bt, float* C, int M, int
   tc::GemmParams p = {};
   p.M = M; p.N = N; p.K = K; p.out = C; p.ld_out = N;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (block_n == 256) return launch_tn<256, 4, tc::EPI_F32>(ta, tb, p, sm, st);
-  return launch_tn<128, 6, tc::EPI_F32>(ta, tb, p, sm, st);
+  if (block_n == 256) return launch_tn<256, 3, tc::EPI_F32>(ta, tb, nullptr, nullptr, p, sm, st);
+  return launch_tn<128, 5, tc::EPI_F32>(ta, tb, nullptr, nullptr, p, sm, st);
 }
 
-int csb_test_gemm_nt(const uint16_t* A, const uint16_t* B, float* C, int M, int N, int Kr, int splits, void* stream) {
+int csb_test_gemm_nt(const uint16_t* A, const uint16_t* B, float* C, float* colsum, int M, int N, int Kr, int splits, void* stream) {
   CSB_REQUIRE(A && B && C, CSB_EINVAL, "null argument");
   CSB_REQUIRE(M % 64 == 0 && N % 64 == 0 && Kr > 0 && splits >= 1, CSB_EINVAL, "M and N must be multiples of 64");
   CUtensorMap ta, tb;
@@ -927,10 +932,11 @@ int csb_test_gemm_nt(const uint16_t* A, const uint16_t* B, float* C, int M, int 
   if ((rc = make_tmap_bf16(&ta, A, M, Kr, M, 64, 64))) return rc;
   if ((rc = make_tmap_bf16(&tb, B, N, Kr, N, 64, 64))) return rc;
   const int num_rb = (int)ceil_div(Kr, 64);
-  tc::NtParams p;
+  tc::NtParams p = {};
   p.M = M; p.N = N; p.R = Kr;
   p.rb_per_split = (int)ceil_div(num_rb, splits);
   p.out = C; p.ld_out = N; p.split_stride = (size_t)M * N;    // caller provides splits * M * N floats
+  p.colsum_out = colsum; p.colsum_stride = (size_t)N;         // optional: splits * N floats
   return launch_nt_auto(ta, tb, p, splits, reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -172,20 +172,8 @@ __device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n, int a_mn_major
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// epilogue helpers: each thread owns one output row (TMEM lane) and 32 consecutive columns
+// epilogue helpers: each thread owns one output row (TMEM lane) and 32 consecutive columns per step
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&v)[32]) {
-  uint4* d = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint4 u;
-    u.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
-    u.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
-    u.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
-    u.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
-    d[q] = u;
-  }
-}
 __device__ __forceinline__ void store_f32x32(float* dst, const float (&v)[32]) {
   float4* d = reinterpret_cast<float4*>(dst);
 #pragma unroll
@@ -199,123 +187,218 @@ __device__ __forceinline__ void load_f32x32(const float* src, float (&v)[32]) {
     v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
   }
 }
-__device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* src, float (&v)[32]) {
-  const uint4* s = reinterpret_cast<const uint4*>(src);
+// activation over a 32-vector with the (warp-uniform) switch hoisted out of the element loop
+__device__ __forceinline__ void act_fwd_vec(int act, float alpha, float (&v)[32]) {
+  switch (act) {
+    case CSB_ACT_RELU:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      break;
+    case CSB_ACT_LEAKYRELU:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : alpha * v[j];
+      break;
+    case CSB_ACT_ELU:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : expm1f(v[j]);
+      break;
+    default: break;
+  }
+}
+// v *= act'(a) with a = saved activation output
+__device__ __forceinline__ void act_bwd_vec(int act, float alpha, float (&v)[32], const float (&a)[32]) {
+  switch (act) {
+    case CSB_ACT_RELU:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = a[j] > 0.f ? v[j] : 0.f;
+      break;
+    case CSB_ACT_LEAKYRELU:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = a[j] > 0.f ? v[j] : alpha * v[j];
+      break;
+    case CSB_ACT_ELU:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = a[j] > 0.f ? v[j] : v[j] * (a[j] + 1.f);
+      break;
+    default: break;
+  }
+}
+
+// The bf16 staging tile in shared memory is laid out exactly as TMA reads/writes it with SWIZZLE_128B and a
+// {64 columns, 128 rows} box: 64-column slabs of 128 rows x 128 B; inside a row the 16-byte pieces are XOR-swizzled
+// with (row & 7).  A quarter-warp (8 consecutive rows, same piece index) therefore touches 8 distinct 16 B bank groups.
+__device__ __forceinline__ uint32_t cst_offset(int row, int col /* multiple of 8, tile-relative */) {
+  return (uint32_t)((col >> 6) * (BM * 128) + row * 128 + ((((col & 63) >> 3) ^ (row & 7)) << 4));
+}
+__device__ __forceinline__ void cst_store32(uint8_t* cst, int row, int col, const float (&v)[32]) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    uint4 t = __ldg(s + q);
+    uint4 u;
+    u.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
+    u.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+    u.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
+    u.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+    *reinterpret_cast<uint4*>(cst + cst_offset(row, col + 8 * q)) = u;
+  }
+}
+__device__ __forceinline__ void cst_load32(const uint8_t* cst, int row, int col, float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint4 t = *reinterpret_cast<const uint4*>(cst + cst_offset(row, col + 8 * q));
     v[8 * q + 0] = bf16_lo(t.x); v[8 * q + 1] = bf16_hi(t.x);
     v[8 * q + 2] = bf16_lo(t.y); v[8 * q + 3] = bf16_hi(t.y);
     v[8 * q + 4] = bf16_lo(t.z); v[8 * q + 5] = bf16_hi(t.z);
     v[8 * q + 6] = bf16_lo(t.w); v[8 * q + 7] = bf16_hi(t.w);
   }
 }
+__device__ __forceinline__ void load_smem_f32x32(const float* s, float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 t = *reinterpret_cast<const float4*>(s + 4 * q);   // same address across the warp: broadcast
+    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+  }
+}
 
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// One 32-column step of the epilogue.  tile_row/tile_col are tile-relative, grow/gcol global.
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int col, const uint32_t (&raw)[32],
-                                               float& loss_acc) {
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint8_t* cst, const float* sbias, int tile_row, int tile_col,
+                                               int grow, int gcol, const uint32_t (&raw)[32], float& loss_acc) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+  const bool row_ok = grow < p.M;
 
   if constexpr (EPI == EPI_F32) {
-    store_f32x32(reinterpret_cast<float*>(p.out) + (size_t)row * p.ld_out + col, v);
+    if (row_ok) store_f32x32(reinterpret_cast<float*>(p.out) + (size_t)grow * p.ld_out + gcol, v);
   } else if constexpr (EPI == EPI_BIAS_ACT) {
     float b[32];
-    load_f32x32(p.bias + col, b);
+    load_smem_f32x32(sbias + tile_col, b);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = act_fwd(p.act, p.alpha, v[j] + b[j]);
-    store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ld_out + col, v);
+    for (int j = 0; j < 32; ++j) v[j] += b[j];
+    act_fwd_vec(p.act, p.alpha, v);
+    cst_store32(cst, tile_row, tile_col, v);
   } else if constexpr (EPI == EPI_DGRAD) {
     float a[32];
-    load_bf16x32(p.saved + (size_t)row * p.ld_saved + col, a);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] *= act_bwd_from_out(p.act, p.alpha, a[j]);
-    store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ld_out + col, v);
-  } else if constexpr (EPI == EPI_HEAD_OUT) {
-    float b[32];
-    load_f32x32(p.bias + col, b);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float z = v[j] + b[j];
-      const bool relu_col = p.head_relu_from >= 0 && (col + j) >= p.head_relu_from;
-      v[j] = relu_col ? fmaxf(z, 0.f) : act_fwd(p.act, p.alpha, z);
-    }
-    if (p.inv_out_scale != nullptr) {
-      load_f32x32(p.inv_out_scale + col, b);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] *= b[j];
-    }
-    if (col + 32 <= p.out_dim) {
-      store_f32x32(p.pred + (size_t)row * p.ld_pred + col, v);
-    } else {
-      for (int j = 0; j < 32; ++j)
-        if (col + j < p.out_dim) p.pred[(size_t)row * p.ld_pred + col + j] = v[j];
-    }
-  } else {  // EPI_HEAD_LOSS
-    float b[32], dz[32];
-    load_f32x32(p.bias + col, b);
-    // p = head activation; g = d p / d z expressed through p
+    cst_load32(cst, tile_row, tile_col, a);        // saved activation tile, TMA-loaded by the producer warp
+    act_bwd_vec(p.act, p.alpha, v, a);
+    cst_store32(cst, tile_row, tile_col, v);       // in place
+  } else {
+    // head: p = (col >= head_relu_from) ? relu(z) : act(z)
+    float b[32], dact[32];
+    load_smem_f32x32(sbias + tile_col, b);
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      float z = v[j] + b[j];
-      const bool relu_col = p.head_relu_from >= 0 && (col + j) >= p.head_relu_from;
-      float pv = relu_col ? fmaxf(z, 0.f) : act_fwd(p.act, p.alpha, z);
-      dz[j] = relu_col ? (pv > 0.f ? 1.f : 0.f) : act_bwd_from_out(p.act, p.alpha, pv);
+      const float z = v[j] + b[j];
+      const bool relu_col = p.head_relu_from >= 0 && (gcol + j) >= p.head_relu_from;
+      const float pv = relu_col ? fmaxf(z, 0.f) : act_fwd(p.act, p.alpha, z);
+      dact[j] = relu_col ? (pv > 0.f ? 1.f : 0.f) : act_bwd_from_out(p.act, p.alpha, pv);
       v[j] = pv;
     }
-    if (p.pred != nullptr && col + 32 <= p.out_dim) store_f32x32(p.pred + (size_t)row * p.ld_pred + col, v);
-    float w[32], yv[32];
-    load_f32x32(p.loss_w + col, w);
-    if (col + 32 <= p.out_dim) {
-      load_f32x32(p.y + (size_t)row * p.ld_y + col, yv);
-    } else {
+    if constexpr (EPI == EPI_HEAD_OUT) {
+      if (p.inv_out_scale != nullptr) {
+        load_f32x32(p.inv_out_scale + gcol, b);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) yv[j] = (col + j < p.out_dim) ? __ldg(p.y + (size_t)row * p.ld_y + col + j) : 0.f;
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float d = v[j] - yv[j];
-      if (p.loss_kind == CSB_LOSS_MSE) {
-        loss_acc += w[j] * d * d;
-        dz[j] *= 2.f * w[j] * d * p.grad_scale;
-      } else {
-        loss_acc += w[j] * fabsf(d);
-        dz[j] *= w[j] * p.grad_scale * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+        for (int j = 0; j < 32; ++j) v[j] *= b[j];
       }
+      if (row_ok) {
+        if (gcol + 32 <= p.out_dim) {
+          store_f32x32(p.pred + (size_t)grow * p.ld_pred + gcol, v);
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (gcol + j < p.out_dim) p.pred[(size_t)grow * p.ld_pred + gcol + j] = v[j];
+        }
+      }
+    } else {  // EPI_HEAD_LOSS
+      float w[32], yv[32];
+      load_f32x32(p.loss_w + gcol, w);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) yv[j] = 0.f;
+      if (row_ok) {
+        if (p.pred != nullptr && gcol + 32 <= p.out_dim) store_f32x32(p.pred + (size_t)grow * p.ld_pred + gcol, v);
+        if (gcol + 32 <= p.out_dim) {
+          load_f32x32(p.y + (size_t)grow * p.ld_y + gcol, yv);
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (gcol + j < p.out_dim) yv[j] = __ldg(p.y + (size_t)grow * p.ld_y + gcol + j);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float d = row_ok ? v[j] - yv[j] : 0.f;
+        if (p.loss_kind == CSB_LOSS_MSE) {
+          loss_acc += w[j] * d * d;
+          dact[j] *= 2.f * w[j] * d * p.grad_scale;
+        } else {
+          loss_acc += w[j] * fabsf(d);
+          dact[j] *= w[j] * p.grad_scale * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+        }
+      }
+      cst_store32(cst, tile_row, tile_col, dact);
     }
-    store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ld_out + col, dz);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// gemm_tn_kernel: persistent, K-major x K-major
+// gemm_tn_kernel: persistent, K-major x K-major.   10 warps: 0-7 epilogue (two per TMEM lane quadrant, each taking
+// half of the tile's columns), 8 = TMA producer, 9 = TMEM owner + MMA issuer.
+// bf16 results are staged in a swizzled smem tile and written with TMA (full 128 B lines); the saved-activation tile
+// of the data-gradient epilogue arrives the same way (TMA load issued by the producer warp behind the k-loop).
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int TN_EPI_WARPS = 8;
+constexpr int TN_EPI_THREADS = TN_EPI_WARPS * 32;
+constexpr int TN_THREADS = TN_EPI_THREADS + 64;
+
 template <int BN, int STAGES>
 struct TnSmem {
   static constexpr int A_BYTES = BM * BK * 2;   // 16 KB
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int CST_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int CST_BYTES = BN * BM * 2;
+  static constexpr int BIAS_OFFSET = CST_OFFSET + CST_BYTES;
+  static constexpr int BAR_OFFSET = BIAS_OFFSET + BN * 4;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // barriers + slack for manual 1024 B alignment
+  static_assert(TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
 };
 
 template <int BN, int STAGES, int EPI>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+__global__ void __launch_bounds__(TN_THREADS, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_saved, const GemmParams p) {
   using L = TnSmem<BN, STAGES>;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static_assert(2 * BN <= 512, "two accumulator buffers must fit the 512 TMEM columns");
+  constexpr bool CST_OUT = (EPI == EPI_BIAS_ACT || EPI == EPI_DGRAD || EPI == EPI_HEAD_LOSS);
+  constexpr bool CST_IN = (EPI == EPI_DGRAD);
+  constexpr bool USE_BIAS = (EPI == EPI_BIAS_ACT || EPI == EPI_HEAD_LOSS || EPI == EPI_HEAD_OUT);
+  constexpr int SLAB_BYTES = BM * 128;   // one 64-column slab of the staging tile
+  constexpr int HALF = BN / 2, NCH = HALF / 32;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B atoms are 1024 B aligned
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  uint8_t* cst = smem_gen + L::CST_OFFSET;
+  float* sbias = reinterpret_cast<float*>(smem_gen + L::BIAS_OFFSET);
   const uint32_t bar_base = smem_base + L::BAR_OFFSET;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + L::BAR_OFFSET + 8 * (2 * STAGES + 4));
+  const uint32_t cst_full = bar_base + 8u * (2 * STAGES + 4);
+  const uint32_t cst_empty = bar_base + 8u * (2 * STAGES + 5);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + L::BAR_OFFSET + 8 * (2 * STAGES + 6));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m_blocks = (p.M + BM - 1) / BM;
@@ -323,14 +406,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int num_tiles = num_m_blocks * num_n_blocks;
   const int num_kb = p.K / BK;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (CST_OUT) tma_prefetch_desc(&tmap_out);
+    if (CST_IN) tma_prefetch_desc(&tmap_saved);
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TN_EPI_WARPS); }
+    mbar_init(cst_full, 1);
+    mbar_init(cst_empty, 1);
     fence_mbar_init();
   }
-  if (warp == 5) {
+  if (warp == 9) {
     tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
     tmem_relinquish();
   }
@@ -339,11 +426,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int s = 0; uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int s = 0; uint32_t ph = 0; int t = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
         const int m0 = (tile / num_n_blocks) * BM, n0 = (tile % num_n_blocks) * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1u);
@@ -353,9 +440,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           tma_load_2d(sa + L::A_BYTES, &tmap_b, full_bar(s), kb * BK, n0);
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
+        if constexpr (CST_IN) {
+          // saved-activation tile of THIS tile, behind its k-loop so that the ring keeps running ahead; the staging
+          // tile is free once the previous tile's TMA store has finished reading it
+          const int slabs = (min(BN, p.N - n0) + 63) / 64;
+          mbar_wait(cst_empty, ((uint32_t)t & 1u) ^ 1u);
+          mbar_expect_tx(cst_full, (uint32_t)(slabs * SLAB_BYTES));
+          for (int sl = 0; sl < slabs; ++sl)
+            tma_load_2d(smem_base + L::CST_OFFSET + sl * SLAB_BYTES, &tmap_saved, cst_full, n0 + 64 * sl, m0);
+        }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       int s = 0; uint32_t ph = 0; int t = 0;
@@ -385,46 +481,71 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else {
-    // ===================== epilogue (warps 0-3 <-> TMEM lanes 32w .. 32w+31) =====================
+    // ===================== epilogue: warp w -> TMEM lanes 32*(w&3).., columns [HALF*(w>>2), HALF*(w>>2)+HALF) ==========
+    const int q = warp & 3, hf = warp >> 2;
+    const int tile_row = q * 32 + lane;
     int t = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
       const int mb = tile / num_n_blocks;
       const int m0 = mb * BM, n0 = (tile % num_n_blocks) * BN;
       const int n_valid = min(BN, p.N - n0);
       const int acc = t & 1;
-      const int row = m0 + warp * 32 + lane;
+      if constexpr (USE_BIAS) {
+        for (int i = threadIdx.x; i < BN; i += TN_EPI_THREADS) sbias[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+      }
       mbar_wait(tfull_bar(acc), (uint32_t)(t >> 1) & 1u);
       tc_fence_after();
+      if constexpr (CST_IN) mbar_wait(cst_full, (uint32_t)t & 1u);
+      named_bar_sync(1, TN_EPI_THREADS);                      // bias staged; every epilogue thread past its waits
       float loss_acc = 0.f;
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN);
-      for (int c = 0; c < n_valid; c += 32) {
-        uint32_t raw[32];
-        tmem_ld_32x32(taddr + (uint32_t)c, raw);
-        tmem_ld_wait();
-        if (row < p.M) epilogue_chunk<EPI>(p, row, n0 + c, raw, loss_acc);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + hf * HALF);
+      uint32_t raw[2][32];
+      if (hf * HALF < n_valid) tmem_ld_32x32(taddr, raw[0]);
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int c = hf * HALF + 32 * i;                     // tile-relative column of this step (warp-uniform)
+        if (c < n_valid) {
+          tmem_ld_wait();
+          if (i + 1 < NCH && c + 32 < n_valid) tmem_ld_32x32(taddr + (uint32_t)(32 * (i + 1)), raw[(i + 1) & 1]);
+          epilogue_chunk<EPI>(p, cst, sbias, tile_row, c, m0 + tile_row, n0 + c, raw[i & 1], loss_acc);
+        }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) mbar_arrive(tempty_bar(acc));            // TMEM buffer free: the MMA of tile t+2 may start
       if constexpr (EPI == EPI_HEAD_LOSS) {
-        // deterministic: one partial per (m-block, warp); requires num_n_blocks == 1 (host asserts)
+        // deterministic: one partial per (m-block, epilogue warp); requires num_n_blocks == 1 (host asserts)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
-        if (lane == 0) p.loss_partials[mb * 4 + warp] = loss_acc * p.grad_scale;
+        if (lane == 0) p.loss_partials[mb * TN_EPI_WARPS + warp] = loss_acc * p.grad_scale;
       }
+      if constexpr (CST_OUT) {
+        fence_proxy_async_smem();                             // generic-proxy smem writes -> visible to the TMA engine
+        named_bar_sync(1, TN_EPI_THREADS);
+        if (threadIdx.x == 0) {
+          const int slabs = (n_valid + 63) / 64;
+          for (int sl = 0; sl < slabs; ++sl) tma_store_2d(&tmap_out, smem_base + L::CST_OFFSET + sl * SLAB_BYTES, n0 + 64 * sl, m0);
+          tma_store_commit();
+          tma_store_wait_read();                              // staging tile read out (global writes may still be in flight)
+          if constexpr (CST_IN) mbar_arrive(cst_empty);
+        }
+      }
+      named_bar_sync(1, TN_EPI_THREADS);                      // staging tile + bias reusable
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// gemm_nt_kernel: D[M,N] = sum_r A[r, m] * B[r, n]; both operands MN-major; split over r (blockIdx.y)
+// gemm_nt_kernel: D[M,N] = sum_r A[r, m] * B[r, n]; both operands MN-major; split over r (blockIdx.y).
+// Weight gradient dW = H^T dZ.  The CTAs of the first m-block additionally reduce the dZ tiles that pass through shared
+// memory over their rows (the otherwise idle epilogue warps do it): that is the bias gradient, at no extra HBM traffic.
 // ---------------------------------------------------------------------------------------------------------------
 struct NtParams {
   int M, N, R;             // M, N feature dims (multiples of 64), R rows to contract
@@ -432,6 +553,8 @@ struct NtParams {
   float* out;              // partials: out + split * split_stride + m * ld_out + n
   int ld_out;
   size_t split_stride;
+  float* colsum_out;       // optional: column sums of B (bias gradient) partials: colsum_out + split * colsum_stride + n
+  size_t colsum_stride;
 };
 
 template <int BN, int STAGES>
@@ -463,15 +586,18 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int num_n_blocks = (p.N + BN - 1) / BN;
   const int m0 = (blockIdx.x / num_n_blocks) * BM, n0 = (blockIdx.x % num_n_blocks) * BN;
   const int m_valid = min(BM, p.M - m0), n_valid = min(BN, p.N - n0);
+  const int a_chunks = (m_valid + 63) / 64, b_chunks = (n_valid + 63) / 64;
   const int num_rb = (p.R + BK - 1) / BK;
   const int rb_begin = blockIdx.y * p.rb_per_split;
   const int rb_end = min(num_rb, rb_begin + p.rb_per_split);
   const int nrb = max(0, rb_end - rb_begin);
+  const bool do_colsum = (p.colsum_out != nullptr) && (m0 == 0);        // CTA-uniform
+  const int colsum_warps = do_colsum ? min(4, b_chunks) : 0;            // warp w sums the columns of chunk w
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1 + colsum_warps); }
     mbar_init(tfull_bar, 1);
     fence_mbar_init();
   }
@@ -487,7 +613,6 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 4) {
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
-      const int a_chunks = (m_valid + 63) / 64, b_chunks = (n_valid + 63) / 64;
       for (int rb = rb_begin; rb < rb_end; ++rb) {
         mbar_wait(empty_bar(s), ph ^ 1u);
         mbar_expect_tx(full_bar(s), (uint32_t)((a_chunks + b_chunks) * CHUNK_BYTES));
@@ -519,6 +644,27 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       umma_commit(tfull_bar);
     }
   } else {
+    // ---- bias gradient: column sums of the dZ tiles streaming through the ring (warps 0..colsum_warps-1)
+    if (warp < colsum_warps) {
+      float s0 = 0.f, s1 = 0.f;                       // columns n0 + 64*warp + 2*lane + {0, 1}
+      int s = 0; uint32_t ph = 0;
+      for (int i = 0; i < nrb; ++i) {
+        mbar_wait(full_bar(s), ph);
+        const uint8_t* chunk = smem_gen + s * L::STAGE_BYTES + L::A_BYTES + warp * CHUNK_BYTES;
+#pragma unroll 8
+        for (int r = 0; r < BK; ++r) {                // rows past R were zero-filled by TMA
+          const uint32_t w = *reinterpret_cast<const uint32_t*>(chunk + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + ((lane & 3) << 2));
+          s0 += bf16_lo(w);
+          s1 += bf16_hi(w);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar(s));     // this warp is done reading the slot
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+      }
+      float* dst = p.colsum_out + (size_t)blockIdx.y * p.colsum_stride + n0 + 64 * warp + 2 * lane;
+      *reinterpret_cast<float2*>(dst) = make_float2(s0, s1);
+    }
+    // ---- weight-gradient tile
     const int row = m0 + warp * 32 + lane;
     float* out = p.out + (size_t)blockIdx.y * p.split_stride + (size_t)row * p.ld_out + n0;
     if (nrb > 0) {

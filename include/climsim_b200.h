@@ -167,8 +167,9 @@ int  csb_reshape_target_from_cnn(const float* p, float* out, int64_t N, void* st
 /* ---- kernel self-test hooks (used by tests/test_gemm_gpu.py; device pointers) ----------------------------- */
 /* C[M,N] (fp32) = A[M,K] * Bt[N,K]^T on the tcgen05 path (both operands K-major bf16, raw uint16 payloads). */
 int  csb_test_gemm_tn(const uint16_t* A, const uint16_t* Bt, float* C, int M, int N, int K, int block_n, void* stream);
-/* C[M,N] (fp32) = A[Kr,M]^T * B[Kr,N]  (both operands MN-major bf16): the weight-gradient contraction over rows. */
-int  csb_test_gemm_nt(const uint16_t* A, const uint16_t* B, float* C, int M, int N, int Kr, int splits, void* stream);
+/* C[s][M,N] (fp32 partials, s < splits) = A[Kr,M]^T * B[Kr,N]  (both operands MN-major bf16): the weight-gradient
+ * contraction over rows; colsum (optional, [splits][N]) receives the per-split column sums of B (bias gradient). */
+int  csb_test_gemm_nt(const uint16_t* A, const uint16_t* B, float* C, float* colsum, int M, int N, int Kr, int splits, void* stream);
 
 /* ---- misc ---------------------------------------------------------------------------------------------- */
 int         csb_version(void);

@@ -57,7 +57,7 @@ def nt(M, N, R, splits, structured=False):
         A, B = torch.randn(R, M, generator=g), torch.randn(R, N, generator=g)
     A, B = A.to(torch.bfloat16).cuda(), B.to(torch.bfloat16).cuda()
     C = torch.full((splits, M, N), float("nan"), device="cuda")
-    rc = lib.csb_test_gemm_nt(A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, R, splits, None)
+    rc = lib.csb_test_gemm_nt(A.data_ptr(), B.data_ptr(), C.data_ptr(), None, M, N, R, splits, None)
     if rc:
         print("nt launch error", rc, lib.csb_last_error().decode()); return False
     try:

@@ -59,10 +59,15 @@ def test_gemm_nt(M, N, R, splits):
     A = _bf16_operand(R, M, 3)
     B = _bf16_operand(R, N, 4)
     Cout = torch.full((splits, M, N), float("nan"), device="cuda")
-    L.check(lib.csb_test_gemm_nt(A.data_ptr(), B.data_ptr(), Cout.data_ptr(), M, N, R, splits, None), "csb_test_gemm_nt")
+    colsum = torch.full((splits, N), float("nan"), device="cuda")
+    L.check(lib.csb_test_gemm_nt(A.data_ptr(), B.data_ptr(), Cout.data_ptr(), colsum.data_ptr(), M, N, R, splits, None), "csb_test_gemm_nt")
     torch.cuda.synchronize()
     got = Cout.sum(dim=0)
     ref = A.float().t() @ B.float()
     err = (got - ref).abs().max().item()
     scale = ref.abs().max().item()
     assert err <= 1e-3 * scale, (err, scale)
+    # fused bias gradient: column sums of B over the contraction rows
+    cs_ref = B.float().sum(dim=0)
+    cs_err = (colsum.sum(dim=0) - cs_ref).abs().max().item()
+    assert cs_err <= 1e-3 * max(cs_ref.abs().max().item(), 1.0), cs_err

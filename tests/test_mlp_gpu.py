@@ -45,6 +45,20 @@ def _batch(B, seed=0):
     return synthetic_batch(B, seed)
 
 
+def _drop_kink_rows(ref, x, y, tol=1e-6):
+    """LeakyReLU'/ReLU' jump at 0: a sample with a pre-activation within rounding distance of 0 can take either branch in
+    two correct fp32 implementations, which changes its whole upstream gradient.  Such samples (typically none or one
+    per batch) are removed from parity batches; everything else is compared at the full 1e-5 tolerance."""
+    with torch.no_grad():
+        out, hidden = ref(x, return_hidden=True)
+        bad = torch.zeros(x.shape[0], dtype=torch.bool)
+        for h in hidden:
+            bad |= (h.abs() < tol).any(dim=1)
+        bad |= (out[:, ref.out_lin:].abs() < tol).any(dim=1) & (out[:, ref.out_lin:] != 0).any(dim=1)
+    keep = ~bad
+    return x[keep].contiguous(), y[keep].contiguous()
+
+
 def _relmax(got, ref):
     got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
     return np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-30)
@@ -87,8 +101,8 @@ def test_train_step_fp32_parity(units, B):
     for t in range(1, 4):
         lr = M.cyclical_lr(t - 1, step_size=2)
         if t > 1:
-            # re-synchronise the (already <= 1e-6 equal) weights bit for bit: a 1e-7 weight difference can flip the
-            # sign of a pre-activation that sits at zero, and LeakyReLU'(0-) != LeakyReLU'(0+) is not a rounding effect
+            # re-synchronise the (already <= 1e-6 equal) weights bit for bit and drop samples sitting on an activation
+            # kink (see _drop_kink_rows): LeakyReLU'(0-) != LeakyReLU'(0+) is not a rounding effect
             eng.set_params_flat(_flat(ref.params))
             for p in ref.params:
                 p.grad = None
