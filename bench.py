@@ -69,9 +69,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin: float = 0.0, t_end: float = float("inf")):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -81,7 +81,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        inside = [ln for ts, ln in self.lines if t_begin <= ts <= t_end + 0.25]
+        window = "timed region"
+        if len(inside) < 2:                       # timed region shorter than two sampling periods: use warm-up + timed
+            inside, window = [ln for _, ln in self.lines], "warm-up + timed region (timed region < 0.4 s)"
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -93,7 +97,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def best_cpu_threads(batch: int, max_threads: int) -> int:
@@ -133,8 +137,8 @@ def cpu_reference_steps(batch: int, steps: int, warmup: int, threads: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=65536, help="columns per GPU per step (weak scaling)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
@@ -187,26 +191,28 @@ def main():
         torch.cuda.synchronize()
 
     # ------------------------------------------------------------------ device-resident timing (the `value`)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for it in range(args.warmup):
         x, y = batches[it % 4]
         trainer.step(x, y, return_loss=False)
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     eng.profile(True)
     launches0 = eng.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_begin = time.time()
     ev0.record()
     for it in range(args.steps):
         x, y = batches[it % 4]
         trainer.step(x, y, return_loss=False)
     ev1.record()
     barrier()
+    t_end = time.time()
     ms_total = ev0.elapsed_time(ev1)
     launches = eng.launch_count - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     prof = eng.profile_read()
     eng.profile(False)
     t = torch.tensor([ms_total], device="cuda")
@@ -216,7 +222,7 @@ def main():
     value = world * B * args.steps / (ms_total * 1e-3)
 
     # ------------------------------------------------------------------ end to end from pinned host buffers
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 50))
     host = [tuple(t_.cpu().pin_memory() for t_ in batches[i]) for i in range(2)]
     for it in range(3):
         trainer.step(*host[it % 2])

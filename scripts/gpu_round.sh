@@ -12,14 +12,14 @@ if [[ "$WHAT" == *tests* ]]; then
   echo "== smoke"; timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "rc=$?"; tail -8 gpurun_out/smoke.log
 fi
 if [[ "$WHAT" == *bench* ]]; then
-  echo "== bench"; timeout 900 python bench.py --steps 30 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "rc=$?"; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
+  echo "== bench"; timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "rc=$?"; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
   echo "== bench reference"; timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "rc=$?"; cat gpurun_out/bench_ref.json
 fi
 if [[ "$WHAT" == *ncu* ]]; then
   echo "== ncu launch list"
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 120 -c 80 --csv --log-file gpurun_out/launches.csv \
-      python bench.py --steps 3 --warmup 3 > gpurun_out/ncu_bench.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/ncu_bench.log
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 60 --csv --log-file gpurun_out/launches.csv \
+      python bench.py --steps 4 --warmup 3 --cpu-sample 256 > gpurun_out/ncu_bench.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/ncu_bench.log
   echo "== ncu full (top kernels)"
-  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:gemm_ -s 30 -c 6 -o gpurun_out/prof_gemm -f \
-      python bench.py --steps 3 --warmup 3 > gpurun_out/ncu_full.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/ncu_full.log
+  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:gemm_ -s 60 -c 20 -o gpurun_out/prof_gemm -f \
+      python bench.py --steps 4 --warmup 3 --cpu-sample 256 > gpurun_out/ncu_full.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/ncu_full.log
 fi

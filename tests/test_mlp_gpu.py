@@ -106,9 +106,12 @@ def test_train_step_fp32_parity(units, B):
             eng.set_params_flat(_flat(ref.params))
             for p in ref.params:
                 p.grad = None
+            x, y = _drop_kink_rows(ref, x, y)
             M.mse(y, ref(x)).backward()
             eng.train_step(x.cuda(), y.cuda())
-            assert _per_tensor(eng, eng.get_grads_flat(), _flat([p.grad for p in ref.params]), _relmax) <= 1e-5
+            errs = [_relmax(g, r) for g, r in zip(eng.split_flat(eng.get_grads_flat()),
+                                                  eng.split_flat(_flat([p.grad for p in ref.params])))]
+            assert max(errs) <= 1e-5, (t, x.shape[0], ["%.1e" % e for e in errs])
         g_eng = [torch.from_numpy(a) for a in eng.flat_to_keras(eng.get_grads_flat(), out_lin=120)]
         M.keras_adam_step(ref.params, g_eng, m, v, t, lr)
         eng.apply_opt("adam_keras", lr=lr)
