@@ -11,6 +11,7 @@
 //   split-K workspace         : per layer  splits_l x (Kp_l*Np_l) fp32 partials of dW_l and S x Np_l partials of db_l,
 //                               reduced in a fixed order (deterministic) into `grads`.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -68,32 +69,51 @@ static int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t cols, uint
 // ---------------------------------------------------------------------------------------------------------------
 // tensor-core launch helpers
 // ---------------------------------------------------------------------------------------------------------------
-template <int BN, int STAGES, int EPI>
+static bool g_use_pairs = true;     // CSB_NO_PAIRS=1 falls back to the single-CTA kernels (debugging aid)
+
+template <int BN, int STAGES, int EPI, int CG>
 static int launch_tn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tout, const CUtensorMap* tsaved,
                      const tc::GemmParams& p, int sm_count, cudaStream_t st) {
-  using L = tc::TnSmem<BN, STAGES>;
-  auto kern = tc::gemm_tn_kernel<BN, STAGES, EPI>;
+  using L = tc::TnSmem<BN, STAGES, CG>;
+  auto kern = tc::gemm_tn_kernel<BN, STAGES, EPI, CG>;
   static bool attr_set = false;
   if (!attr_set) {
     CSB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_set = true;
   }
-  const int tiles = (int)(ceil_div(p.M, tc::BM) * ceil_div(p.N, BN));
+  const int tiles = (int)(ceil_div(ceil_div(p.M, tc::BM), CG) * ceil_div(p.N, BN));   // CG m-blocks per tile
   if (tiles == 0) return CSB_OK;
-  const int grid = std::min(tiles, sm_count);
+  const int grid = std::min(tiles, sm_count / CG) * CG;
   tc::GemmParams q = p;
-  q.b_box_rows = std::min(p.N, BN);      // must equal the box the B tensor map was encoded with
+  q.b_box_rows = std::min(p.N, BN) / CG;     // must equal the box the B tensor map was encoded with
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(tc::TN_THREADS);
+  cfg.dynamicSmemBytes = L::TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (CG > 1) ? 1 : 0;
   // unused descriptor slots get a valid (never dereferenced) descriptor
-  kern<<<grid, tc::TN_THREADS, L::TOTAL, st>>>(ta, tb, tout ? *tout : ta, tsaved ? *tsaved : ta, q);
-  CSB_CUDA_CHECK(cudaGetLastError());
+  CSB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tout ? *tout : ta, tsaved ? *tsaved : ta, q));
   return CSB_OK;
 }
+
+// Tile-shape policy.  N > 128: 256-wide tiles; CTA pairs (cta_group::2, the B tensor map must then have been encoded
+// with a box of min(N,256)/2 rows) whenever the layer is wide enough.
+static inline bool tn_use_pairs(int N) { return g_use_pairs && N > 128; }
+static inline int tn_b_box_rows(int N) { return N > 128 ? (tn_use_pairs(N) ? std::min(N, 256) / 2 : std::min(N, 256)) : std::min(N, 128); }
 
 template <int EPI>
 static int launch_tn_auto(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tout, const CUtensorMap* tsaved,
                           const tc::GemmParams& p, int sm_count, cudaStream_t st) {
-  if (p.N > 128) return launch_tn<256, 3, EPI>(ta, tb, tout, tsaved, p, sm_count, st);
-  return launch_tn<128, 5, EPI>(ta, tb, tout, tsaved, p, sm_count, st);
+  if (p.N > 128) {
+    if (tn_use_pairs(p.N)) return launch_tn<256, 5, EPI, 2>(ta, tb, tout, tsaved, p, sm_count, st);
+    return launch_tn<256, 3, EPI, 1>(ta, tb, tout, tsaved, p, sm_count, st);
+  }
+  return launch_tn<128, 5, EPI, 1>(ta, tb, tout, tsaved, p, sm_count, st);
 }
 static inline int tn_block_n(int N) { return N > 128 ? 256 : 128; }
 
@@ -250,10 +270,10 @@ static int build_weight_maps(csb_mlp* h) {
   for (int l = 0; l < h->L; ++l) {
     const LayerInfo& li = h->layer[l];
     // forward:  D[B, Np] = in[B, Kp] . Wt16[Np, Kp]^T          B-operand rows = Np, contraction = Kp
-    int rc = make_tmap_bf16(&h->tm_wt[l], h->wt16[l], li.Kp, li.Np, li.Kp, 64, (uint32_t)std::min(li.Np, tn_block_n(li.Np)));
+    int rc = make_tmap_bf16(&h->tm_wt[l], h->wt16[l], li.Kp, li.Np, li.Kp, 64, (uint32_t)tn_b_box_rows(li.Np));
     if (rc) return rc;
     // dgrad:    D[B, Kp] = dZ[B, Np] . W16[Kp, Np]^T           B-operand rows = Kp, contraction = Np
-    rc = make_tmap_bf16(&h->tm_w[l], h->w16[l], li.Np, li.Kp, li.Np, 64, (uint32_t)std::min(li.Kp, tn_block_n(li.Kp)));
+    rc = make_tmap_bf16(&h->tm_w[l], h->w16[l], li.Np, li.Kp, li.Np, 64, (uint32_t)tn_b_box_rows(li.Kp));
     if (rc) return rc;
   }
   return CSB_OK;
@@ -327,6 +347,7 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
     CSB_REQUIRE(cfg->layernorm[l] == 0, CSB_EUNSUPPORTED, "layernorm layers are not implemented yet");
   }
 
+  g_use_pairs = getenv("CSB_NO_PAIRS") == nullptr;
   csb_mlp* h = new (std::nothrow) csb_mlp();
   CSB_REQUIRE(h != nullptr, CSB_ENOMEM, "host allocation failed");
   h->cfg = *cfg;
@@ -910,18 +931,21 @@ int csb_reshape_target_from_cnn(const float* p, float* out, int64_t N, void* str
 int csb_test_gemm_tn(const uint16_t* A, const uint16_t* Bt, float* C, int M, int N, int K, int block_n, void* stream) {
   CSB_REQUIRE(A && Bt && C, CSB_EINVAL, "null argument");
   CSB_REQUIRE(N % 64 == 0 && K % 64 == 0 && M > 0, CSB_EINVAL, "N and K must be multiples of 64");
-  CSB_REQUIRE(block_n == 128 || block_n == 256, CSB_EINVAL, "block_n must be 128 or 256");
+  CSB_REQUIRE(block_n == 128 || block_n == 256 || block_n == 512, CSB_EINVAL, "block_n must be 128, 256 (single CTA) or 512 (= 256 on CTA pairs)");
+  const bool pairs = block_n == 512;
+  if (pairs) block_n = 256;
   int sm = 0;
   int rc = csb_device_info(&sm, nullptr, nullptr, nullptr);
   if (rc) return rc;
   CUtensorMap ta, tb;
   if ((rc = make_tmap_bf16(&ta, A, K, M, K, 64, 128))) return rc;
-  if ((rc = make_tmap_bf16(&tb, Bt, K, N, K, 64, (uint32_t)std::min(N, block_n)))) return rc;
+  if ((rc = make_tmap_bf16(&tb, Bt, K, N, K, 64, (uint32_t)(std::min(N, block_n) / (pairs ? 2 : 1))))) return rc;
   tc::GemmParams p = {};
   p.M = M; p.N = N; p.K = K; p.out = C; p.ld_out = N;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (block_n == 256) return launch_tn<256, 3, tc::EPI_F32>(ta, tb, nullptr, nullptr, p, sm, st);
-  return launch_tn<128, 5, tc::EPI_F32>(ta, tb, nullptr, nullptr, p, sm, st);
+  if (pairs) return launch_tn<256, 5, tc::EPI_F32, 2>(ta, tb, nullptr, nullptr, p, sm, st);
+  if (block_n == 256) return launch_tn<256, 3, tc::EPI_F32, 1>(ta, tb, nullptr, nullptr, p, sm, st);
+  return launch_tn<128, 5, tc::EPI_F32, 1>(ta, tb, nullptr, nullptr, p, sm, st);
 }
 
 int csb_test_gemm_nt(const uint16_t* A, const uint16_t* B, float* C, float* colsum, int M, int N, int Kr, int splits, void* stream) {

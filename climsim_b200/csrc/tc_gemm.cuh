@@ -135,6 +135,51 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// ---- cta_group::2 (CTA pair) variants --------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same smem offset in the pair's leader (even) CTA
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+}
+// TMA load issued by either CTA of the pair; the transaction bytes are credited to the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B with M = 256 (128 rows per CTA), B split along N between the two CTAs; leader only
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit: arrive on the mbarrier at this offset in BOTH CTAs of the pair once the issued MMAs have completed
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives lane (base_lane + i), columns [c, c+32)
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -360,10 +405,10 @@ constexpr int TN_EPI_WARPS = 8;
 constexpr int TN_EPI_THREADS = TN_EPI_WARPS * 32;
 constexpr int TN_THREADS = TN_EPI_THREADS + 64;
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CG = 1>
 struct TnSmem {
   static constexpr int A_BYTES = BM * BK * 2;   // 16 KB
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (BN / CG) * BK * 2;   // cta_group::2: each CTA of the pair holds half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int CST_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int CST_BYTES = BN * BM * 2;
@@ -373,11 +418,16 @@ struct TnSmem {
   static_assert(TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
 };
 
-template <int BN, int STAGES, int EPI>
+// CG = 1: one CTA per 128 x BN tile.  CG = 2 (launched as clusters of two): a CTA pair owns a 256 x BN tile with
+// tcgen05 cta_group::2 -- each CTA loads its 128 rows of A and HALF of the B tile, the leader CTA issues the MMAs for
+// both, each CTA runs the epilogue of its own 128 rows.  Halves the B traffic and the B footprint per stage.
+template <int BN, int STAGES, int EPI, int CG>
 __global__ void __launch_bounds__(TN_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_saved, const GemmParams p) {
-  using L = TnSmem<BN, STAGES>;
+  using L = TnSmem<BN, STAGES, CG>;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static_assert(2 * BN <= 512, "two accumulator buffers must fit the 512 TMEM columns");
   constexpr bool CST_OUT = (EPI == EPI_BIAS_ACT || EPI == EPI_DGRAD || EPI == EPI_HEAD_LOSS);
@@ -401,10 +451,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + L::BAR_OFFSET + 8 * (2 * STAGES + 6));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_m_blocks = (p.M + BM - 1) / BM;
+  const int num_m_blocks = ((p.M + BM - 1) / BM + CG - 1) / CG;       // in units of CG m-blocks (pairs when CG == 2)
   const int num_n_blocks = (p.N + BN - 1) / BN;
   const int num_tiles = num_m_blocks * num_n_blocks;
   const int num_kb = p.K / BK;
+  const int first_tile = (int)(blockIdx.x / CG), tile_stride = (int)(gridDim.x / CG);   // both CTAs of a pair walk the same tiles
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -412,17 +463,19 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (CST_OUT) tma_prefetch_desc(&tmap_out);
     if (CST_IN) tma_prefetch_desc(&tmap_saved);
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TN_EPI_WARPS); }
+    // the leader's "accumulator drained" barrier collects the epilogue warps of BOTH CTAs
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TN_EPI_WARPS * CG); }
     mbar_init(cst_full, 1);
     mbar_init(cst_empty, 1);
     fence_mbar_init();
   }
   if (warp == 9) {
-    tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (CG == 2) { tmem_alloc_2sm(smem_u32(tmem_slot), TMEM_COLS); tmem_relinquish_2sm(); }
+    else { tmem_alloc(smem_u32(tmem_slot), TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();       // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -430,14 +483,22 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ===================== TMA producer =====================
     if (lane == 0) {
       int s = 0; uint32_t ph = 0; int t = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
-        const int m0 = (tile / num_n_blocks) * BM, n0 = (tile % num_n_blocks) * BN;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++t) {
+        const int m0 = ((tile / num_n_blocks) * CG + (int)cta_rank) * BM, n0 = (tile % num_n_blocks) * BN;
+        const int nb0 = n0 + (int)cta_rank * (min(BN, p.N - n0) / CG);       // this CTA's share of the B rows
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1u);
-          mbar_expect_tx(full_bar(s), (uint32_t)(L::A_BYTES + p.b_box_rows * BK * 2));
           const uint32_t sa = smem_base + s * L::STAGE_BYTES;
-          tma_load_2d(sa, &tmap_a, full_bar(s), kb * BK, m0);
-          tma_load_2d(sa + L::A_BYTES, &tmap_b, full_bar(s), kb * BK, n0);
+          if constexpr (CG == 2) {
+            // one expect_tx on the leader's barrier covers the four loads of the pair
+            if (is_leader) mbar_expect_tx(full_bar(s), (uint32_t)(2 * (L::A_BYTES + p.b_box_rows * BK * 2)));
+            tma_load_2d_2sm(sa, &tmap_a, full_bar(s), kb * BK, m0);
+            tma_load_2d_2sm(sa + L::A_BYTES, &tmap_b, full_bar(s), kb * BK, nb0);
+          } else {
+            mbar_expect_tx(full_bar(s), (uint32_t)(L::A_BYTES + p.b_box_rows * BK * 2));
+            tma_load_2d(sa, &tmap_a, full_bar(s), kb * BK, m0);
+            tma_load_2d(sa + L::A_BYTES, &tmap_b, full_bar(s), kb * BK, nb0);
+          }
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
         if constexpr (CST_IN) {
@@ -453,12 +514,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else if (warp == 9) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (lane == 0 && is_leader) {
       int s = 0; uint32_t ph = 0; int t = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++t) {
         const int n0 = (tile % num_n_blocks) * BN;
         const int n_valid = min(BN, p.N - n0);
-        const uint32_t idesc = make_idesc_bf16(BM, n_valid, 0, 0);
+        const uint32_t idesc = make_idesc_bf16(BM * CG, n_valid, 0, 0);
         const int acc = t & 1;
         mbar_wait(tempty_bar(acc), ((uint32_t)(t >> 1) & 1u) ^ 1u);
         tc_fence_after();
@@ -472,12 +533,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
-            umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+            if constexpr (CG == 2) umma_f16_2sm(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+            else umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
           }
-          umma_commit(empty_bar(s));            // smem slot reusable once these MMAs have read it
+          // smem slot reusable (in both CTAs of a pair) once these MMAs have read it
+          if constexpr (CG == 2) umma_commit_2sm(empty_bar(s)); else umma_commit(empty_bar(s));
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));            // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs of a pair)
+        if constexpr (CG == 2) umma_commit_2sm(tfull_bar(acc)); else umma_commit(tfull_bar(acc));
       }
     }
   } else {
@@ -485,8 +549,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int q = warp & 3, hf = warp >> 2;
     const int tile_row = q * 32 + lane;
     int t = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
-      const int mb = tile / num_n_blocks;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++t) {
+      const int mb = (tile / num_n_blocks) * CG + (int)cta_rank;
       const int m0 = mb * BM, n0 = (tile % num_n_blocks) * BN;
       const int n_valid = min(BN, p.N - n0);
       const int acc = t & 1;
@@ -512,12 +576,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));            // TMEM buffer free: the MMA of tile t+2 may start
+      if (lane == 0) {                                        // TMEM buffer free: the MMA of tile t+2 may start
+        if constexpr (CG == 2) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc));
+      }
       if constexpr (EPI == EPI_HEAD_LOSS) {
         // deterministic: one partial per (m-block, epilogue warp); requires num_n_blocks == 1 (host asserts)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
-        if (lane == 0) p.loss_partials[mb * TN_EPI_WARPS + warp] = loss_acc * p.grad_scale;
+        if (lane == 0 && m0 < p.M) p.loss_partials[mb * TN_EPI_WARPS + warp] = loss_acc * p.grad_scale;
       }
       if constexpr (CST_OUT) {
         fence_proxy_async_smem();                             // generic-proxy smem writes -> visible to the TMA engine
@@ -536,9 +602,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();       // no CTA leaves (or frees TMEM) while its peer may still signal it
   if (warp == 9) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (CG == 2) tmem_dealloc_2sm(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -646,23 +713,35 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else {
     // ---- bias gradient: column sums of the dZ tiles streaming through the ring (warps 0..colsum_warps-1)
     if (warp < colsum_warps) {
-      float s0 = 0.f, s1 = 0.f;                       // columns n0 + 64*warp + 2*lane + {0, 1}
+      // lane -> logical 16-byte piece (8 columns) lp = lane & 7 of row 4*i + (lane >> 3); a quarter-warp reads one full
+      // 128-byte row (conflict-free); the physical piece position is XOR-swizzled with (row & 7)
+      float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const int lp = lane & 7, rs = lane >> 3;
       int s = 0; uint32_t ph = 0;
       for (int i = 0; i < nrb; ++i) {
         mbar_wait(full_bar(s), ph);
         const uint8_t* chunk = smem_gen + s * L::STAGE_BYTES + L::A_BYTES + warp * CHUNK_BYTES;
-#pragma unroll 8
-        for (int r = 0; r < BK; ++r) {                // rows past R were zero-filled by TMA
-          const uint32_t w = *reinterpret_cast<const uint32_t*>(chunk + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4) + ((lane & 3) << 2));
-          s0 += bf16_lo(w);
-          s1 += bf16_hi(w);
+#pragma unroll
+        for (int it = 0; it < BK / 4; ++it) {         // rows past R were zero-filled by TMA
+          const int r = 4 * it + rs;
+          const uint4 w = *reinterpret_cast<const uint4*>(chunk + r * 128 + ((lp ^ (r & 7)) << 4));
+          acc8[0] += bf16_lo(w.x); acc8[1] += bf16_hi(w.x); acc8[2] += bf16_lo(w.y); acc8[3] += bf16_hi(w.y);
+          acc8[4] += bf16_lo(w.z); acc8[5] += bf16_hi(w.z); acc8[6] += bf16_lo(w.w); acc8[7] += bf16_hi(w.w);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty_bar(s));     // this warp is done reading the slot
         if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
-      float* dst = p.colsum_out + (size_t)blockIdx.y * p.colsum_stride + n0 + 64 * warp + 2 * lane;
-      *reinterpret_cast<float2*>(dst) = make_float2(s0, s1);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {                   // fold the four row-lanes that share a piece
+        acc8[j] += __shfl_xor_sync(0xffffffffu, acc8[j], 8);
+        acc8[j] += __shfl_xor_sync(0xffffffffu, acc8[j], 16);
+      }
+      if (rs == 0) {
+        float* dst = p.colsum_out + (size_t)blockIdx.y * p.colsum_stride + n0 + 64 * warp + 8 * lp;
+        *reinterpret_cast<float4*>(dst) = make_float4(acc8[0], acc8[1], acc8[2], acc8[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(acc8[4], acc8[5], acc8[6], acc8[7]);
+      }
     }
     // ---- weight-gradient tile
     const int row = m0 + warp * 32 + lane;

@@ -67,7 +67,8 @@ def nt(M, N, R, splits, structured=False):
     return report(f"nt M{M} N{N} R{R} s{splits} structured={structured}", C.sum(0), A.float().t() @ B.float())
 
 
-TN_CASES = [(128, 128, 64, 128, True), (128, 128, 64, 128), (333, 64, 192, 128), (256, 128, 512, 128),
+TN_CASES = [(256, 256, 64, 512, True), (256, 256, 64, 512), (256, 256, 512, 512), (1000, 640, 768, 512), (65536, 640, 768, 512),
+            (128, 128, 64, 128, True), (128, 128, 64, 128), (333, 64, 192, 128), (256, 128, 512, 128),
             (1000, 640, 768, 256), (70000, 128, 128, 128), (65536, 640, 768, 256)]
 NT_CASES = [(128, 128, 64, 1, True), (128, 128, 64, 1), (128, 128, 128, 1), (128, 256, 256, 1), (64, 64, 1000, 3),
             (768, 640, 4096, 4), (640, 128, 70000, 16)]

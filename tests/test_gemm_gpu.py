@@ -31,6 +31,11 @@ def _bf16_operand(rows, cols, seed, scale=1.0):
     (4096, 768, 128, 256),      # layer-0 shape
     (333, 64, 192, 128),        # N = 64 (n_valid < BN)
     (70000, 128, 128, 128),     # many tiles per CTA: both TMEM accumulator buffers, phase flips
+    (256, 256, 64, 512),        # bn code 512 = 256-wide tiles on CTA pairs (tcgen05 cta_group::2): smallest case
+    (256, 256, 512, 512),       # pairs: ring wraps
+    (1000, 640, 768, 512),      # pairs: odd number of m-blocks (idle half-pair at the tail), ragged last n-block
+    (65536, 768, 128, 512),     # pairs: layer-0 shape at the benchmark batch
+    (40000, 640, 640, 512),     # pairs: many tiles per pair
 ])
 def test_gemm_tn(M, N, K, bn):
     lib, L = _lib()
