@@ -505,7 +505,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           // saved-activation tile of THIS tile, behind its k-loop so that the ring keeps running ahead; the staging
           // tile is free once the previous tile's TMA store has finished reading it
           const int slabs = (min(BN, p.N - n0) + 63) / 64;
-          mbar_wait(cst_empty, ((uint32_t)t & 1u) ^ 1u);
+          if (t > 0) mbar_wait(cst_empty, (uint32_t)(t - 1) & 1u);    // arrival #k = "the store of tile k has been read out"
           mbar_expect_tx(cst_full, (uint32_t)(slabs * SLAB_BYTES));
           for (int sl = 0; sl < slabs; ++sl)
             tma_load_2d(smem_base + L::CST_OFFSET + sl * SLAB_BYTES, &tmap_saved, cst_full, n0 + 64 * sl, m0);
@@ -554,13 +554,20 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int m0 = mb * BM, n0 = (tile % num_n_blocks) * BN;
       const int n_valid = min(BN, p.N - n0);
       const int acc = t & 1;
+      if constexpr (CST_OUT) {
+        // the previous tile's TMA store was only committed, not waited for: it has had a whole MMA tile of time to drain
+        if (threadIdx.x == 0 && t > 0) {
+          tma_store_wait_read();
+          if constexpr (CST_IN) mbar_arrive(cst_empty);       // producer may now load this tile's saved activations
+        }
+      }
       if constexpr (USE_BIAS) {
         for (int i = threadIdx.x; i < BN; i += TN_EPI_THREADS) sbias[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
       }
       mbar_wait(tfull_bar(acc), (uint32_t)(t >> 1) & 1u);
       tc_fence_after();
       if constexpr (CST_IN) mbar_wait(cst_full, (uint32_t)t & 1u);
-      named_bar_sync(1, TN_EPI_THREADS);                      // bias staged; every epilogue thread past its waits
+      named_bar_sync(1, TN_EPI_THREADS);                      // bias staged; staging tile free; everyone past the waits
       float loss_acc = 0.f;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + hf * HALF);
       uint32_t raw[2][32];
@@ -591,12 +598,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (threadIdx.x == 0) {
           const int slabs = (n_valid + 63) / 64;
           for (int sl = 0; sl < slabs; ++sl) tma_store_2d(&tmap_out, smem_base + L::CST_OFFSET + sl * SLAB_BYTES, n0 + 64 * sl, m0);
-          tma_store_commit();
-          tma_store_wait_read();                              // staging tile read out (global writes may still be in flight)
-          if constexpr (CST_IN) mbar_arrive(cst_empty);
+          tma_store_commit();                                 // waited for at the start of the next tile / before exit
         }
+      } else {
+        named_bar_sync(1, TN_EPI_THREADS);                    // bias buffer reusable
       }
-      named_bar_sync(1, TN_EPI_THREADS);                      // staging tile + bias reusable
+    }
+    if constexpr (CST_OUT) {
+      if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before exit
     }
   }
 

@@ -54,8 +54,10 @@ def _drop_kink_rows(ref, x, y, tol=1e-6):
         bad = torch.zeros(x.shape[0], dtype=torch.bool)
         for h in hidden:
             bad |= (h.abs() < tol).any(dim=1)
-        bad |= (out[:, ref.out_lin:].abs() < tol).any(dim=1) & (out[:, ref.out_lin:] != 0).any(dim=1)
+        head = out[:, ref.out_lin:]
+        bad |= ((head.abs() < tol) & (head != 0)).any(dim=1)       # exact zeros are dead ReLU units, not near-kink ones
     keep = ~bad
+    assert keep.float().mean() > 0.9, 'kink filter removed too many rows'
     return x[keep].contiguous(), y[keep].contiguous()
 
 
