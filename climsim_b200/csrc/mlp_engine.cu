@@ -576,11 +576,17 @@ int csb_mlp_grad_buffer(csb_mlp* h, float** ptr, size_t* n) {
 // forward pieces
 // ---------------------------------------------------------------------------------------------------------------
 static int run_normalize(csb_mlp* h, const float* x, int64_t B, int apply, cudaStream_t st) {
-  const int grid = grid_for(B * h->in_p, 256, h->sm_count);
-  simt::normalize_kernel<<<grid, 256, 0, st>>>(x, h->in_dim, h->d_sub, h->d_div, apply,
-                                               h->bf16 ? nullptr : reinterpret_cast<float*>(h->xn), h->in_p,
-                                               h->bf16 ? reinterpret_cast<__nv_bfloat16*>(h->xn) : nullptr, h->in_p, B,
-                                               h->in_dim, h->in_p);
+  if (h->bf16 && h->in_dim % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const int grid = grid_for(B * (h->in_p / 4), 256, h->sm_count);
+    simt::normalize_bf16_vec4_kernel<<<grid, 256, 0, st>>>(x, h->d_sub, h->d_div, apply, reinterpret_cast<__nv_bfloat16*>(h->xn), B,
+                                                           h->in_dim, h->in_p);
+  } else {
+    const int grid = grid_for(B * h->in_p, 256, h->sm_count);
+    simt::normalize_kernel<<<grid, 256, 0, st>>>(x, h->in_dim, h->d_sub, h->d_div, apply,
+                                                 h->bf16 ? nullptr : reinterpret_cast<float*>(h->xn), h->in_p,
+                                                 h->bf16 ? reinterpret_cast<__nv_bfloat16*>(h->xn) : nullptr, h->in_p, B,
+                                                 h->in_dim, h->in_p);
+  }
   CSB_CUDA_CHECK(cudaGetLastError());
   prof_mark(h, K_NORMALIZE, st);
   return CSB_OK;
@@ -946,6 +952,27 @@ int csb_test_gemm_tn(const uint16_t* A, const uint16_t* Bt, float* C, int M, int
   if (pairs) return launch_tn<256, 5, tc::EPI_F32, 2>(ta, tb, nullptr, nullptr, p, sm, st);
   if (block_n == 256) return launch_tn<256, 3, tc::EPI_F32, 1>(ta, tb, nullptr, nullptr, p, sm, st);
   return launch_tn<128, 5, tc::EPI_F32, 1>(ta, tb, nullptr, nullptr, p, sm, st);
+}
+
+int csb_test_linear_fwd(const uint16_t* A, const uint16_t* Wt, const float* bias, uint16_t* out, int M, int N, int K, int act,
+                        float alpha, int pairs, void* stream) {
+  CSB_REQUIRE(A && Wt && bias && out, CSB_EINVAL, "null argument");
+  CSB_REQUIRE(N % 64 == 0 && K % 64 == 0 && M > 0, CSB_EINVAL, "N and K must be multiples of 64");
+  static int sm = 0;
+  int rc;
+  if (sm == 0 && (rc = csb_device_info(&sm, nullptr, nullptr, nullptr))) return rc;
+  const bool wide = N > 128, use_pairs = wide && pairs != 0;
+  const int bn = wide ? 256 : 128;
+  CUtensorMap ta, tb, tout;
+  if ((rc = make_tmap_bf16(&ta, A, K, M, K, 64, 128))) return rc;
+  if ((rc = make_tmap_bf16(&tb, Wt, K, N, K, 64, (uint32_t)(std::min(N, bn) / (use_pairs ? 2 : 1))))) return rc;
+  if ((rc = make_tmap_bf16(&tout, out, N, M, N, 64, 128))) return rc;
+  tc::GemmParams p = {};
+  p.M = M; p.N = N; p.K = K; p.act = act; p.alpha = alpha; p.head_relu_from = -1; p.bias = bias; p.out = out; p.ld_out = N;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (use_pairs) return launch_tn<256, 5, tc::EPI_BIAS_ACT, 2>(ta, tb, &tout, nullptr, p, sm, st);
+  if (wide) return launch_tn<256, 3, tc::EPI_BIAS_ACT, 1>(ta, tb, &tout, nullptr, p, sm, st);
+  return launch_tn<128, 5, tc::EPI_BIAS_ACT, 1>(ta, tb, &tout, nullptr, p, sm, st);
 }
 
 int csb_test_gemm_nt(const uint16_t* A, const uint16_t* B, float* C, float* colsum, int M, int N, int Kr, int splits, void* stream) {

@@ -365,29 +365,38 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint8_t* cst
             if (gcol + j < p.out_dim) p.pred[(size_t)grow * p.ld_pred + gcol + j] = v[j];
         }
       }
-    } else {  // EPI_HEAD_LOSS
-      float w[32], yv[32];
-      load_f32x32(p.loss_w + gcol, w);
+    } else {  // EPI_HEAD_LOSS: finish 8 columns at a time to keep the live register set small
+      if (row_ok && p.pred != nullptr && gcol + 32 <= p.out_dim) store_f32x32(p.pred + (size_t)grow * p.ld_pred + gcol, v);
+      const float* yrow = p.y + (size_t)grow * p.ld_y + gcol;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) yv[j] = 0.f;
-      if (row_ok) {
-        if (p.pred != nullptr && gcol + 32 <= p.out_dim) store_f32x32(p.pred + (size_t)grow * p.ld_pred + gcol, v);
-        if (gcol + 32 <= p.out_dim) {
-          load_f32x32(p.y + (size_t)grow * p.ld_y + gcol, yv);
-        } else {
-          for (int j = 0; j < 32; ++j)
-            if (gcol + j < p.out_dim) yv[j] = __ldg(p.y + (size_t)grow * p.ld_y + gcol + j);
+      for (int g = 0; g < 4; ++g) {
+        float yv[8], w[8];
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.loss_w + gcol + 8 * g));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.loss_w + gcol + 8 * g + 4));
+        w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w; w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) yv[j] = 0.f;
+        if (row_ok) {
+          if (gcol + 8 * g + 8 <= p.out_dim) {
+            const float4 y0 = __ldg(reinterpret_cast<const float4*>(yrow + 8 * g));
+            const float4 y1 = __ldg(reinterpret_cast<const float4*>(yrow + 8 * g + 4));
+            yv[0] = y0.x; yv[1] = y0.y; yv[2] = y0.z; yv[3] = y0.w; yv[4] = y1.x; yv[5] = y1.y; yv[6] = y1.z; yv[7] = y1.w;
+          } else {
+            for (int j = 0; j < 8; ++j)
+              if (gcol + 8 * g + j < p.out_dim) yv[j] = __ldg(yrow + 8 * g + j);
+          }
         }
-      }
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float d = row_ok ? v[j] - yv[j] : 0.f;
-        if (p.loss_kind == CSB_LOSS_MSE) {
-          loss_acc += w[j] * d * d;
-          dact[j] *= 2.f * w[j] * d * p.grad_scale;
-        } else {
-          loss_acc += w[j] * fabsf(d);
-          dact[j] *= w[j] * p.grad_scale * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+        for (int j = 0; j < 8; ++j) {
+          const int c = 8 * g + j;
+          const float d = row_ok ? v[c] - yv[j] : 0.f;
+          if (p.loss_kind == CSB_LOSS_MSE) {
+            loss_acc += w[j] * d * d;
+            dact[c] *= 2.f * w[j] * d * p.grad_scale;
+          } else {
+            loss_acc += w[j] * fabsf(d);
+            dact[c] *= w[j] * p.grad_scale * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+          }
         }
       }
       cst_store32(cst, tile_row, tile_col, dact);

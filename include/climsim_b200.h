@@ -167,6 +167,10 @@ int  csb_reshape_target_from_cnn(const float* p, float* out, int64_t N, void* st
 /* ---- kernel self-test hooks (used by tests/test_gemm_gpu.py; device pointers) ----------------------------- */
 /* C[M,N] (fp32) = A[M,K] * Bt[N,K]^T on the tcgen05 path (both operands K-major bf16, raw uint16 payloads). */
 int  csb_test_gemm_tn(const uint16_t* A, const uint16_t* Bt, float* C, int M, int N, int K, int block_n, void* stream);
+/* out[M,N] (bf16) = act(A[M,K] * Wt[N,K]^T + bias): one forward layer exactly as the engine runs it (staged TMA-store
+ * epilogue); pairs != 0 selects the cta_group::2 variant.  For kernel micro-benchmarks (scripts/microbench_gemm.py). */
+int  csb_test_linear_fwd(const uint16_t* A, const uint16_t* Wt, const float* bias, uint16_t* out, int M, int N, int K, int act,
+                         float alpha, int pairs, void* stream);
 /* C[s][M,N] (fp32 partials, s < splits) = A[Kr,M]^T * B[Kr,N]  (both operands MN-major bf16): the weight-gradient
  * contraction over rows; colsum (optional, [splits][N]) receives the per-split column sums of B (bias gradient). */
 int  csb_test_gemm_nt(const uint16_t* A, const uint16_t* B, float* C, float* colsum, int M, int N, int Kr, int splits, void* stream);
