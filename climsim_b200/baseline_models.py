@@ -1,0 +1,99 @@
+"""``torch.nn.Module`` faces of the reference's baseline column emulators, backed by the CUDA engine.
+
+The reference builds MLP_v1 / ED as inline Keras graphs (baseline_models/MLP/training/HPO/baseline_v1/
+hpo_baseline_v1.py:75-103, baseline_models/ED/training/ClimSIM_ED_1_3_train.py:56-92) and has no importable model
+class; these modules span the same hyper-parameter space with ``forward(x: (B,124)) -> (B,128)``, keep
+their parameters in ONE flat fp32 ``nn.Parameter`` (Keras ``get_weights()`` order, kernels (in,out)), and run forward and
+backward through ``csb_mlp_forward`` / ``csb_mlp_backward``.  Any torch optimizer and any loss written in torch works on
+top.  The fused path (loss + backward + optimizer inside the engine) is ``climsim_b200.trainer.Trainer``.
+
+There is no CPU path: constructing a module without a B200 raises ``CsbError`` (CSB_ENODEV).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .engine import MLPEngine
+from .trainer import glorot_uniform_flat
+
+
+class _EngineFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, flat, module):
+        eng = module.engine
+        module._sync_params()
+        ctx.module, ctx.need_dx = module, x.requires_grad
+        return eng.forward(x, keep_activations=True)
+
+    @staticmethod
+    def backward(ctx, dy):
+        eng = ctx.module.engine
+        dx = eng.backward(dy.contiguous(), need_dx=ctx.need_dx)
+        return dx, eng.get_grads_device(), None
+
+
+class _EngineModule(torch.nn.Module):
+    def __init__(self, engine: MLPEngine, seed: int = 0):
+        super().__init__()
+        self.engine = engine
+        self.flat = torch.nn.Parameter(torch.from_numpy(glorot_uniform_flat(engine.layer_dims, seed)).cuda())
+        self._uploaded_version = -1
+
+    def _sync_params(self) -> None:
+        if self.flat._version != self._uploaded_version:       # the optimizer updated the parameter in place
+            self.engine.set_params_device(self.flat.detach())
+            self._uploaded_version = self.flat._version
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if torch.is_grad_enabled() and (self.flat.requires_grad or x.requires_grad):
+            return _EngineFunction.apply(x, self.flat, self)
+        self._sync_params()
+        return self.engine.forward(x)
+
+    # -- Keras-style weight access -------------------------------------------------------------------------------
+    def layer_views(self) -> List[torch.Tensor]:
+        """[W0 (in,out), b0, W1, b1, ...] as views of the flat parameter."""
+        out, off = [], 0
+        for k, n in self.engine.layer_dims:
+            out.append(self.flat.detach()[off:off + k * n].view(k, n)); off += k * n
+            out.append(self.flat.detach()[off:off + n]); off += n
+        return out
+
+    def load_flat(self, flat: np.ndarray) -> None:
+        with torch.no_grad():
+            self.flat.copy_(torch.from_numpy(np.ascontiguousarray(flat, dtype=np.float32)))
+
+
+class MLP(_EngineModule):
+    """MLP_v1: ``x -> [Dense(u) -> act]* -> Dense(128) -> act -> concat(Dense(120), relu(Dense(8)))``.
+    Defaults = the shipped best trial (step1_results.csv lot-147 / trial_0027)."""
+
+    def __init__(self, units: Sequence[int] = (768, 640, 512, 640, 640), activation: str = "leakyrelu", alpha: float = 0.15,
+                 in_dim: int = 124, out_lin: int = 120, out_relu: int = 8, dtype: str = "bf16", max_batch: int = 65536,
+                 seed: int = 0):
+        self.out_lin = out_lin
+        super().__init__(MLPEngine.mlp_v1(units=units, act=activation, alpha=alpha, in_dim=in_dim, out_lin=out_lin,
+                                          out_relu=out_relu, dtype=dtype, max_batch=max_batch), seed)
+
+    def load_keras_weights(self, weights: Sequence[np.ndarray]) -> None:
+        """``keras_model.get_weights()`` (the two output Dense layers separate, as Keras stores them)."""
+        self.load_flat(MLPEngine.keras_to_flat(weights, fused_head=True))
+
+    def keras_weights(self) -> List[np.ndarray]:
+        return self.engine.flat_to_keras(self.flat.detach().cpu().numpy(), out_lin=self.out_lin)
+
+
+class ED(_EngineModule):
+    """Encoder-decoder MLP 124->463->463->231->115->57->28->5->28->...->463->128, ReLU, ELU output
+    (baseline_models/ED/training/ClimSIM_ED_1_3_train.py:56-92; Keras truncates the float widths 463/2**k)."""
+
+    def __init__(self, intermediate_dim: int = 463, latent_dim: int = 5, in_dim: int = 124, out_dim: int = 128,
+                 dtype: str = "bf16", max_batch: int = 65536, seed: int = 0):
+        d = intermediate_dim
+        widths = [d, d, int(d / 2), int(d / 4), int(d / 8), int(d / 16), latent_dim,
+                  int(d / 16), int(d / 8), int(d / 4), int(d / 2), d, d, out_dim]
+        layers = [(w, "relu", 0.0) for w in widths[:-1]] + [(out_dim, "elu", 0.0)]
+        super().__init__(MLPEngine(in_dim, layers, head_relu_from=-1, dtype=dtype, max_batch=max_batch), seed)

@@ -46,9 +46,10 @@ class Trainer:
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(process_group)
         self.iteration = 0
+        self.device = getattr(engine, "device", "cuda")
         self._grad = engine.grad_buffer() if self.world > 1 else None
         self._x = self._y = None
-        self._loss = torch.zeros(1, dtype=torch.float32, device="cuda")
+        self._loss = torch.zeros(1, dtype=torch.float32, device=self.device)
 
     def _lr(self) -> float:
         return float(self.lr(self.iteration)) if callable(self.lr) else float(self.lr)
@@ -60,15 +61,16 @@ class Trainer:
         eng = self.engine
         B = x.shape[0]
         lr = self._lr()
-        if self.world == 1 and not x.is_cuda:
+        on_device = x.device.type == torch.device(self.device).type
+        if self.world == 1 and not on_device:
             loss = eng.train_step_host(x, y, rule=self.rule, lr=lr, beta1=self.beta1, beta2=self.beta2, eps=self.eps,
                                        weight_decay=self.weight_decay, normalize_in=normalize_in)
             self.iteration += 1
             return loss
-        if not x.is_cuda:
+        if not on_device:
             if self._x is None or self._x.shape[0] < B:
-                self._x = torch.empty(B, eng.in_dim, dtype=torch.float32, device="cuda")
-                self._y = torch.empty(B, eng.out_dim, dtype=torch.float32, device="cuda")
+                self._x = torch.empty(B, eng.in_dim, dtype=torch.float32, device=self.device)
+                self._y = torch.empty(B, eng.out_dim, dtype=torch.float32, device=self.device)
             self._x[:B].copy_(x, non_blocking=True)
             self._y[:B].copy_(y, non_blocking=True)
             x, y = self._x[:B], self._y[:B]

@@ -1,0 +1,94 @@
+"""Device kernels behind the data_utils mirror and the nn.Module shims, against the reference's golden vectors / the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def g(golden_dir):
+    return np.load(os.path.join(golden_dir, "data_utils.npz"))
+
+
+def test_cnn_reshape_kernels_bit_exact(g):
+    from climsim_b200.data_utils import data_utils
+    x, y, p = (torch.from_numpy(g[k]).cuda() for k in ("x_norm", "target", "cnn_pred"))
+    np.testing.assert_array_equal(data_utils.reshape_input_for_cnn(x).cpu().numpy(), g["cnn_in"])
+    np.testing.assert_array_equal(data_utils.reshape_target_for_cnn(y).cpu().numpy(), g["cnn_tgt"])
+    # mean over 60 levels: the reference reduces a strided fp32 slice with NumPy's pairwise sum; a different summation
+    # order moves the result by at most a few ulp
+    got = data_utils.reshape_target_from_cnn(p).cpu().numpy()
+    np.testing.assert_array_equal(got[:, :120], g["cnn_pred_flat"][:, :120])
+    np.testing.assert_allclose(got[:, 120:], g["cnn_pred_flat"][:, 120:], rtol=2e-6, atol=1e-7)
+
+
+def test_normalize_kernel_matches_reference_rule(g):
+    from climsim_b200 import _lib
+    lib = _lib.load()
+    x_raw = torch.from_numpy(g["x_raw"].astype(np.float32)).cuda()
+    sub = torch.from_numpy(g["inp_sub"].astype(np.float32)).cuda()
+    div = torch.from_numpy(g["inp_div"].astype(np.float32)).cuda()
+    out = torch.empty_like(x_raw)
+    _lib.check(lib.csb_normalize(x_raw.data_ptr(), sub.data_ptr(), div.data_ptr(), out.data_ptr(), x_raw.shape[0], 124, None), "csb_normalize")
+    got = out.cpu().numpy()
+    assert np.all(got[:, 60] == 0)                               # max == min level -> inf/nan -> 0
+    # fp32 arithmetic on fp32 inputs vs the reference's fp64 arithmetic cast to fp32: raw values ~1e5 with spans ~1e4
+    # lose ~3 digits in the subtraction, so compare in units of the input's own fp32 resolution
+    want = g["x_renorm"]
+    scale = np.abs(g["x_raw"]).max(axis=0) / np.where(g["inp_div"] == 0, 1, np.abs(g["inp_div"]))
+    assert np.all(np.abs(got - want) <= 4 * np.finfo(np.float32).eps * (scale + 1))
+
+
+def test_nn_module_autograd_matches_oracle():
+    from climsim_b200.baseline_models import MLP
+    from climsim_b200.synthetic import synthetic_batch
+    from oracle import models as M
+    units, B = (192, 128, 64), 300
+    ref = M.MLPRef(units=units, seed=0)
+    ref.randomize_biases(1)
+    net = MLP(units=units, dtype="fp32", max_batch=512)
+    net.load_keras_weights([p.detach().numpy() for p in ref.params])
+    x, y = synthetic_batch(B, 0)
+    loss_ref = M.mse(y, ref(x))
+    loss_ref.backward()
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    out = net(x.cuda())
+    loss = ((out - y.cuda()) ** 2).mean()          # any torch loss works on top of the engine's forward
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) <= 1e-5 * loss_ref.item()
+    from climsim_b200 import MLPEngine
+    g_ref = MLPEngine.keras_to_flat([p.grad.numpy() for p in ref.params])
+    g_got = net.flat.grad.cpu().numpy()
+    assert np.abs(g_got - g_ref).max() <= 1e-5 * np.abs(g_ref).max()
+    opt.step()                                      # in-place update -> the module re-uploads on the next forward
+    with torch.no_grad():
+        for p in ref.params:
+            p -= 0.1 * p.grad
+        out2 = net(x.cuda()).cpu().numpy()
+    want2 = ref(x).detach().numpy()
+    assert np.abs(out2 - want2).max() <= 1e-5 * np.abs(want2).max()
+    ws = net.keras_weights()
+    assert [w.shape for w in ws][-4:] == [(128, 120), (120,), (128, 8), (8,)]
+
+
+def test_ed_preset_matches_oracle():
+    from climsim_b200.baseline_models import ED
+    from climsim_b200.synthetic import synthetic_batch
+    from oracle import models as M
+    ref = M.EDRef(seed=0)
+    assert ref.num_parameters() == 829_032 + sum(M.ed_widths())    # MACs + biases
+    net = ED(dtype="fp32", max_batch=256)
+    net.load_flat(np.concatenate([p.detach().numpy().reshape(-1) for p in ref.params]))
+    x, _ = synthetic_batch(200, 1)
+    want = ref(x).detach().numpy()
+    with torch.no_grad():
+        got = net(x.cuda()).cpu().numpy()
+    assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+    net16 = ED(dtype="bf16", max_batch=256)
+    net16.load_flat(np.concatenate([p.detach().numpy().reshape(-1) for p in ref.params]))
+    with torch.no_grad():
+        got16 = net16(x.cuda()).cpu().numpy()
+    assert np.abs(got16 - want).max() <= 5e-2 * np.abs(want).max()
