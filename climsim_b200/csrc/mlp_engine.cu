@@ -843,7 +843,7 @@ int csb_mlp_backward(csb_mlp* h, const float* dy, float* dx, int64_t B, void* st
 
 int csb_mlp_apply_opt(csb_mlp* h, int rule, float lr, float beta1, float beta2, float eps, float wd, void* stream) {
   CSB_REQUIRE(h, CSB_EINVAL, "null handle");
-  CSB_REQUIRE(rule >= CSB_OPT_ADAM_KERAS && rule <= CSB_OPT_SGD, CSB_EINVAL, "unknown optimizer rule %d", rule);
+  CSB_REQUIRE(rule >= CSB_OPT_ADAM_KERAS && rule <= CSB_OPT_RMSPROP, CSB_EINVAL, "unknown optimizer rule %d", rule);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   prof_mark(h, K_BEGIN, st);
   h->step++;
@@ -851,6 +851,13 @@ int csb_mlp_apply_opt(csb_mlp* h, int rule, float lr, float beta1, float beta2, 
   o.rule = rule; o.lr = lr; o.beta1 = beta1; o.beta2 = beta2; o.eps = eps; o.wd = wd;
   o.bc1 = (float)(1.0 - pow((double)beta1, (double)h->step));
   o.bc2 = (float)(1.0 - pow((double)beta2, (double)h->step));
+  o.radam_r = -1.f;
+  if (rule == CSB_OPT_RADAM) {
+    const double t = (double)h->step, b2t = pow((double)beta2, t);
+    const double sma_inf = 2.0 / (1.0 - (double)beta2) - 1.0;
+    const double sma_t = sma_inf - 2.0 * t * b2t / (1.0 - b2t);
+    if (sma_t >= 5.0) o.radam_r = (float)sqrt((sma_t - 4.0) / (sma_inf - 4.0) * (sma_t - 2.0) / (sma_inf - 2.0) * sma_inf / sma_t);
+  }
   const int grid = grid_for((int64_t)h->P_pad / 4, 256, h->sm_count);
   simt::opt_kernel<<<grid, 256, 0, st>>>(h->params, h->grads, h->m, h->v, (int64_t)h->P_pad, o);
   CSB_CUDA_CHECK(cudaGetLastError());

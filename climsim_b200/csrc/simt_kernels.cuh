@@ -277,6 +277,7 @@ struct OptParams {
   int rule;
   float lr, beta1, beta2, eps, wd;
   float bc1, bc2;          // 1 - beta^t
+  float radam_r;           // RADAM: rectification factor r_t, or < 0 while sma_t < 5 (un-rectified momentum step)
 };
 
 __global__ void __launch_bounds__(256)
@@ -301,6 +302,17 @@ opt_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict
           mv[j] += (gv[j] - mv[j]) * (1.f - o.beta1);
           vv[j] += (gv[j] * gv[j] - vv[j]) * (1.f - o.beta2);
           wv[j] -= alpha * mv[j] / (sqrtf(vv[j]) + o.eps);
+        } else if (o.rule == CSB_OPT_RADAM) {
+          // tfa RectifiedAdam._resource_apply_dense (no warm-up, no amsgrad)
+          mv[j] = o.beta1 * mv[j] + (1.f - o.beta1) * gv[j];
+          vv[j] = o.beta2 * vv[j] + (1.f - o.beta2) * gv[j] * gv[j];
+          const float mhat = mv[j] / o.bc1;
+          const float step = (o.radam_r >= 0.f) ? o.radam_r * mhat / (sqrtf(vv[j] / o.bc2) + o.eps) : mhat;
+          wv[j] -= o.lr * (step + o.wd * wv[j]);
+        } else if (o.rule == CSB_OPT_RMSPROP) {
+          // keras RMSprop.update_step (rho in beta2; epsilon inside the square root)
+          vv[j] = o.beta2 * vv[j] + (1.f - o.beta2) * gv[j] * gv[j];
+          wv[j] -= o.lr * gv[j] * rsqrtf(vv[j] + o.eps);
         } else {
           // torch.optim.Adam (L2 decay folded into g)
           const float ge = gv[j] + o.wd * wv[j];

@@ -197,7 +197,7 @@ class MLPEngine:
     def apply_opt(self, rule: str = "adam_keras", lr: float = 1e-3, beta1: float = 0.9, beta2: float = 0.999,
                   eps: Optional[float] = None, weight_decay: float = 0.0) -> None:
         if eps is None:
-            eps = 1e-7 if rule in ("adam_keras", "adam") else 1e-8
+            eps = 1e-8 if rule == "adam_torch" else 1e-7          # Keras / tfa default epsilon is 1e-7
         _lib.check(self.lib.csb_mlp_apply_opt(self._h, _lib.OPT[rule], lr, beta1, beta2, eps, weight_decay,
                                               _lib.current_stream_ptr()), "csb_mlp_apply_opt")
 
@@ -215,7 +215,7 @@ class MLPEngine:
         assert not x_host.is_cuda and not y_host.is_cuda and x_host.dtype == torch.float32 and y_host.dtype == torch.float32
         x_host, y_host = x_host.contiguous(), y_host.contiguous()
         if eps is None:
-            eps = 1e-7 if rule in ("adam_keras", "adam") else 1e-8
+            eps = 1e-8 if rule == "adam_torch" else 1e-7          # Keras / tfa default epsilon is 1e-7
         loss = C.c_float()
         _lib.check(self.lib.csb_mlp_train_step_host(self._h, x_host.data_ptr(), y_host.data_ptr(), x_host.shape[0],
                                                     grad_scale, self._flags(normalize_in, False, False), _lib.OPT[rule],

@@ -58,9 +58,12 @@ enum { CSB_LOSS_MSE = 0, CSB_LOSS_MAE = 1 };
 /* Optimizer update rule.
  * ADAM_KERAS: keras.optimizers.Adam update_step (hpo_baseline_v1.py:116-117): w -= lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps)
  * ADAM_TORCH: torch.optim.Adam with L2 weight decay (HSR/training/hsr.py:109-112): w -= lr/(1-b1^t) * m/(sqrt(v/(1-b2^t))+eps)
- * SGD:        w -= lr * g
+ * SGD:        w -= lr * (g + wd*w)
+ * RADAM:      tensorflow_addons.optimizers.RectifiedAdam, no warm-up, sma_threshold 5 (the best MLP_v1 trial's optimizer,
+ *             hpo_baseline_v1.py:118-119):  w -= lr * (sma_t >= 5 ? r_t * mhat/(sqrt(vhat)+eps) : mhat)
+ * RMSPROP:    keras.optimizers.RMSprop (rho = beta2 argument, hpo_baseline_v1.py:120-121): v = rho v + (1-rho) g^2; w -= lr * g * rsqrt(v + eps)
  */
-enum { CSB_OPT_ADAM_KERAS = 0, CSB_OPT_ADAM_TORCH = 1, CSB_OPT_SGD = 2 };
+enum { CSB_OPT_ADAM_KERAS = 0, CSB_OPT_ADAM_TORCH = 1, CSB_OPT_SGD = 2, CSB_OPT_RADAM = 3, CSB_OPT_RMSPROP = 4 };
 
 /* flags for csb_mlp_forward */
 enum {

@@ -400,3 +400,32 @@ def torch_adam_step(params: List[torch.Tensor], grads: List[torch.Tensor], m: Li
             mi.mul_(beta1).add_(g, alpha=1 - beta1)
             vi.mul_(beta2).addcmul_(g, g, value=1 - beta2)
             p.sub_((lr / bc1) * mi / (vi.sqrt() / math.sqrt(bc2) + eps))
+
+
+def radam_step(params: List[torch.Tensor], grads: List[torch.Tensor], m: List[torch.Tensor], v: List[torch.Tensor], t: int,
+               lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-7, sma_threshold: float = 5.0) -> None:
+    """tensorflow_addons.optimizers.RectifiedAdam (0.19) ``_resource_apply_dense`` with its defaults (no warm-up, no
+    weight decay, no amsgrad) -- the optimizer of the shipped best MLP_v1 trial (hpo_baseline_v1.py:118-119).  UNPINNED."""
+    sma_inf = 2.0 / (1.0 - beta2) - 1.0
+    b2t = beta2 ** t
+    sma_t = sma_inf - 2.0 * t * b2t / (1.0 - b2t)
+    with torch.no_grad():
+        for p, g, mi, vi in zip(params, grads, m, v):
+            mi.mul_(beta1).add_(g, alpha=1 - beta1)
+            vi.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+            mhat = mi / (1 - beta1 ** t)
+            if sma_t >= sma_threshold:
+                r = math.sqrt((sma_t - 4) / (sma_inf - 4) * (sma_t - 2) / (sma_inf - 2) * sma_inf / sma_t)
+                p.sub_(lr * r * mhat / ((vi / (1 - b2t)).sqrt() + eps))
+            else:
+                p.sub_(lr * mhat)
+
+
+def keras_rmsprop_step(params: List[torch.Tensor], grads: List[torch.Tensor], v: List[torch.Tensor], lr: float,
+                       rho: float = 0.9, eps: float = 1e-7) -> None:
+    """keras.optimizers.RMSprop (2.11) ``update_step``, momentum 0, not centered (hpo_baseline_v1.py:120-121):
+    v = rho v + (1-rho) g^2;  w -= lr * g * rsqrt(v + eps).  UNPINNED."""
+    with torch.no_grad():
+        for p, g, vi in zip(params, grads, v):
+            vi.mul_(rho).addcmul_(g, g, value=1 - rho)
+            p.sub_(lr * g * torch.rsqrt(vi + eps))

@@ -277,3 +277,34 @@ def test_checkpoint_roundtrip():
         e.train_step(x.cuda(), y.cuda()); e.apply_opt("adam_keras", lr=1e-3)
     np.testing.assert_array_equal(eng.get_params_flat(), eng2.get_params_flat())
     assert step == 2
+
+
+@pytest.mark.parametrize("rule", ["radam", "rmsprop", "sgd", "adam_torch"])
+def test_optimizer_rules_fp32(rule):
+    """Each update rule against its oracle restatement, fed the engine's own gradients (optimizer arithmetic in isolation);
+    8 steps so that RAdam crosses from its un-rectified phase (sma_t < 5 for t <= 5) into the rectified one."""
+    units, B = (128, 64), 256
+    ref, eng = _oracle(units, seed=5), _engine(units, "fp32", max_batch=B)
+    _load(eng, ref)
+    x, y = _batch(B, 7)
+    m = [torch.zeros_like(p) for p in ref.params]
+    v = [torch.zeros_like(p) for p in ref.params]
+    for t in range(1, 9):
+        eng.train_step(x.cuda(), y.cuda())
+        g = [torch.from_numpy(a) for a in eng.flat_to_keras(eng.get_grads_flat(), out_lin=120)]
+        if rule == "radam":
+            M.radam_step(ref.params, g, m, v, t, lr=1e-3)
+            eng.apply_opt("radam", lr=1e-3)
+        elif rule == "rmsprop":
+            M.keras_rmsprop_step(ref.params, g, v, lr=1e-3, rho=0.9)
+            eng.apply_opt("rmsprop", lr=1e-3, beta2=0.9)
+        elif rule == "sgd":
+            with torch.no_grad():
+                for p, gi in zip(ref.params, g):
+                    p -= 1e-2 * gi
+            eng.apply_opt("sgd", lr=1e-2)
+        else:
+            M.torch_adam_step(ref.params, g, m, v, t, lr=1e-3, weight_decay=0.022)
+            eng.apply_opt("adam_torch", lr=1e-3, weight_decay=0.022)
+        assert _per_tensor(eng, eng.get_params_flat(), _flat(ref.params), _relmax) <= 2e-6, (rule, t)
+        eng.set_params_flat(_flat(ref.params))       # keep the two trajectories on identical weights
