@@ -39,7 +39,7 @@ class _EngineModule(torch.nn.Module):
     def __init__(self, engine: MLPEngine, seed: int = 0):
         super().__init__()
         self.engine = engine
-        self.flat = torch.nn.Parameter(torch.from_numpy(glorot_uniform_flat(engine.layer_dims, seed)).cuda())
+        self.flat = torch.nn.Parameter(torch.from_numpy(glorot_uniform_flat(engine.layer_dims, seed, engine.layernorm)).cuda())
         self._uploaded_version = -1
 
     def _sync_params(self) -> None:
@@ -57,9 +57,10 @@ class _EngineModule(torch.nn.Module):
     def layer_views(self) -> List[torch.Tensor]:
         """[W0 (in,out), b0, W1, b1, ...] as views of the flat parameter."""
         out, off = [], 0
-        for k, n in self.engine.layer_dims:
+        for (k, n), ln in zip(self.engine.layer_dims, self.engine.layernorm):
             out.append(self.flat.detach()[off:off + k * n].view(k, n)); off += k * n
-            out.append(self.flat.detach()[off:off + n]); off += n
+            for _ in range(3 if ln else 1):                   # bias (, gamma, beta)
+                out.append(self.flat.detach()[off:off + n]); off += n
         return out
 
     def load_flat(self, flat: np.ndarray) -> None:
@@ -97,3 +98,48 @@ class ED(_EngineModule):
                   int(d / 16), int(d / 8), int(d / 4), int(d / 2), d, d, out_dim]
         layers = [(w, "relu", 0.0) for w in widths[:-1]] + [(out_dim, "elu", 0.0)]
         super().__init__(MLPEngine(in_dim, layers, head_relu_from=-1, dtype=dtype, max_batch=max_batch), seed)
+
+
+class HSRMLP(_EngineModule):
+    """``MLP`` of baseline_models/HSR/training/hsr.py:14-35: layers x [Linear -> LayerNorm -> Dropout(0) -> ReLU] -> Linear."""
+
+    def __init__(self, in_dims: int = 124, out_dims: int = 128, hidden_dims: int = 512, layers: int = 1, dropout: float = 0.0,
+                 dtype: str = "bf16", max_batch: int = 16384, seed: int = 0):
+        assert dropout == 0, "dropout > 0 needs the reference's torch RNG stream; the shipped configuration uses p = 0 (hpo.py:225-238)"
+        spec = [(hidden_dims, "relu", 0.0)] * layers + [(out_dims, "none", 0.0)]
+        self.n_hidden = layers
+        super().__init__(MLPEngine(in_dims, spec, dtype=dtype, max_batch=max_batch, layernorm=[True] * layers + [False]), seed)
+
+    def load_reference_state_dict(self, sd, prefix: str = "") -> None:
+        """Keys of the reference module: ``linear{i}.0.weight`` (out,in), ``linear{i}.0.bias``, ``linear{i}.1.weight`` (gamma),
+        ``linear{i}.1.bias`` (beta), ``final_linear.weight``, ``final_linear.bias``."""
+        parts = []
+        for i in range(self.n_hidden):
+            parts += [sd[f"{prefix}linear{i}.0.weight"].t().reshape(-1), sd[f"{prefix}linear{i}.0.bias"],
+                      sd[f"{prefix}linear{i}.1.weight"], sd[f"{prefix}linear{i}.1.bias"]]
+        parts += [sd[f"{prefix}final_linear.weight"].t().reshape(-1), sd[f"{prefix}final_linear.bias"]]
+        self.load_flat(torch.cat([p.detach().float().cpu().reshape(-1) for p in parts]).numpy())
+
+
+class HSR(torch.nn.Module):
+    """``HeteroskedasticRegression`` (hsr.py:38-81): two LayerNorm MLPs estimating mean and log-precision; ``forward`` returns
+    ``(mean, logprec)``; the losses of hsr.py:126-138 are ordinary torch expressions on top."""
+
+    def __init__(self, in_dims: int = 124, out_dims: int = 128, hidden_dims: int = 512, layers: int = 1, dropout: float = 0.0,
+                 dtype: str = "bf16", max_batch: int = 16384):
+        super().__init__()
+        self.mean = HSRMLP(in_dims, out_dims, hidden_dims, layers, dropout, dtype, max_batch, seed=0)
+        self.logprec = HSRMLP(in_dims, out_dims, hidden_dims, layers, dropout, dtype, max_batch, seed=1)
+
+    def forward(self, x):
+        return self.mean(x), self.logprec(x)
+
+    def sample(self, x, random: bool = True):
+        mu, logprec = self.forward(x)
+        if random:
+            return mu + torch.randn_like(mu) * torch.exp(logprec) ** (-0.5)
+        return mu, torch.exp(logprec) ** (-0.5)
+
+    def load_reference_state_dict(self, sd) -> None:
+        self.mean.load_reference_state_dict(sd, "mean.")
+        self.logprec.load_reference_state_dict(sd, "logprec.")

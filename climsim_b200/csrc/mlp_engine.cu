@@ -153,8 +153,9 @@ struct LayerInfo {
   int act;
   float alpha;
   int ln;
-  size_t w_off, b_off;         // offsets into the padded flat buffers
-  size_t w_off_user, b_off_user;
+  size_t w_off, b_off, g_off;  // offsets into the padded flat buffers (g_off: gamma [Np] then beta [Np], LayerNorm layers)
+  size_t w_off_user, b_off_user, g_off_user;
+  size_t ws_g_off;             // LayerNorm parameter-gradient partials [LN_SPLITS][2][Np]
   // split-K workspace
   size_t ws_w_off, ws_b_off;
   int max_w_splits, b_splits;
@@ -193,6 +194,8 @@ struct csb_mlp {
   void* xn = nullptr;                       // [cap x in_p]   bf16 or fp32
   void* act[CSB_MAX_LAYERS] = {};           // [cap x Np_l]   (l < L-1)
   void* dz[2] = {nullptr, nullptr};         // [cap x max_np]
+  void* zbuf[CSB_MAX_LAYERS] = {};          // LayerNorm layers: pre-norm z [cap x Np_l]
+  float* ln_stats[CSB_MAX_LAYERS] = {};     // LayerNorm layers: (mean, rstd) per row [cap x 2]
   float* pred = nullptr;                    // [cap x out_p]
   float* dx_tmp = nullptr;                  // [cap x in_p] (lazily allocated)
   float *d_sub = nullptr, *d_div = nullptr, *d_out_scale = nullptr, *d_inv_out_scale = nullptr, *d_loss_w = nullptr;
@@ -205,6 +208,7 @@ struct csb_mlp {
   int64_t maps_B = -1;
   ActMaps tm_in[CSB_MAX_LAYERS];            // input of layer l (xn or act[l-1]) with `maps_B` rows
   ActMaps tm_dz[CSB_MAX_LAYERS];            // dZ_l (ping-pong buffer (L-1-l)&1, ld = Np_l) with `maps_B` rows
+  CUtensorMap tm_z[CSB_MAX_LAYERS];         // LayerNorm layers: pre-norm z buffer (TMA-store target of the forward GEMM)
 
   int64_t step = 0, launches = 0;
   int64_t acts_B = -1;                      // batch of the last forward that kept activations
@@ -233,7 +237,7 @@ static inline size_t esize(const csb_mlp* h) { return h->bf16 ? 2 : 4; }
 static void free_all(csb_mlp* h) {
   auto F = [](void* p) { if (p) cudaFree(p); };
   F(h->params); F(h->grads); F(h->m); F(h->v); F(h->ws);
-  for (int l = 0; l < CSB_MAX_LAYERS; ++l) { F(h->w16[l]); F(h->wt16[l]); F(h->act[l]); }
+  for (int l = 0; l < CSB_MAX_LAYERS; ++l) { F(h->w16[l]); F(h->wt16[l]); F(h->act[l]); F(h->zbuf[l]); F(h->ln_stats[l]); }
   F(h->xn); F(h->dz[0]); F(h->dz[1]); F(h->pred); F(h->dx_tmp);
   F(h->d_sub); F(h->d_div); F(h->d_out_scale); F(h->d_inv_out_scale); F(h->d_loss_w);
   F(h->loss_partials); F(h->d_loss); F(h->x_stage); F(h->y_stage);
@@ -294,6 +298,10 @@ static int build_act_maps(csb_mlp* h, int64_t B) {
     if (rc) return rc;
     rc = make_tmap_bf16(&h->tm_dz[l].mn64, dz16(h, l), li.Np, B, li.Np, 64, 64);
     if (rc) return rc;
+    if (li.ln) {
+      rc = make_tmap_bf16(&h->tm_z[l], h->zbuf[l], li.Np, B, li.Np, 64, 128);
+      if (rc) return rc;
+    }
   }
   h->maps_B = B;
   return CSB_OK;
@@ -344,7 +352,7 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
   for (int l = 0; l < cfg->n_layers; ++l) {
     CSB_REQUIRE(cfg->units[l] >= 1, CSB_EINVAL, "units[%d] must be positive", l);
     CSB_REQUIRE(cfg->act[l] >= CSB_ACT_NONE && cfg->act[l] <= CSB_ACT_LEAKYRELU, CSB_EINVAL, "act[%d] unknown", l);
-    CSB_REQUIRE(cfg->layernorm[l] == 0, CSB_EUNSUPPORTED, "layernorm layers are not implemented yet");
+    CSB_REQUIRE(cfg->layernorm[l] == 0 || l + 1 < cfg->n_layers, CSB_EUNSUPPORTED, "layernorm on the output layer is not supported");
   }
 
   g_use_pairs = getenv("CSB_NO_PAIRS") == nullptr;
@@ -366,14 +374,17 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
     li.act = cfg->act[l]; li.alpha = cfg->alpha[l]; li.ln = cfg->layernorm[l];
     li.w_off = off; off += (size_t)li.Kp * li.Np;
     li.b_off = off; off += (size_t)li.Np;
+    li.g_off = off; if (li.ln) off += 2 * (size_t)li.Np;
     li.w_off_user = off_user; off_user += (size_t)li.K * li.N;
     li.b_off_user = off_user; off_user += (size_t)li.N;
+    li.g_off_user = off_user; if (li.ln) off_user += 2 * (size_t)li.N;
     li.nt_block_n = tn_block_n(li.Np);
     const int tiles = (int)(ceil_div(li.Kp, 128) * ceil_div(li.Np, li.nt_block_n));
     li.max_w_splits = h->bf16 ? std::max(1, std::min(64, sm / tiles)) : 1;
     li.b_splits = h->bf16 ? li.max_w_splits : 32;
     li.ws_w_off = ws_off; ws_off += (size_t)li.max_w_splits * li.Kp * li.Np;
     li.ws_b_off = ws_off; ws_off += (size_t)li.b_splits * li.Np;
+    li.ws_g_off = ws_off; if (li.ln) ws_off += (size_t)32 * 2 * li.Np;
     h->max_np = std::max(h->max_np, li.Np);
     k = li.N;
   }
@@ -390,7 +401,13 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
   CKA(h->ws, h->ws_elems * 4);
   const size_t es = esize(h);
   CKA(h->xn, (size_t)h->cap * h->in_p * es);
-  for (int l = 0; l + 1 < h->L; ++l) CKA(h->act[l], (size_t)h->cap * h->layer[l].Np * es);
+  for (int l = 0; l + 1 < h->L; ++l) {
+    CKA(h->act[l], (size_t)h->cap * h->layer[l].Np * es);
+    if (h->layer[l].ln) {
+      CKA(h->zbuf[l], (size_t)h->cap * h->layer[l].Np * es);
+      CKA(h->ln_stats[l], (size_t)h->cap * 2 * 4);
+    }
+  }
   CKA(h->dz[0], (size_t)h->cap * h->max_np * es);
   CKA(h->dz[1], (size_t)h->cap * h->max_np * es);
   CKA(h->pred, (size_t)h->cap * h->out_p * 4);
@@ -458,6 +475,10 @@ static int upload_padded(csb_mlp* h, const float* user, float* dev) {
     const LayerInfo& li = h->layer[l];
     for (int r = 0; r < li.K; ++r) memcpy(&pad[li.w_off + (size_t)r * li.Np], user + li.w_off_user + (size_t)r * li.N, (size_t)li.N * 4);
     memcpy(&pad[li.b_off], user + li.b_off_user, (size_t)li.N * 4);
+    if (li.ln) {
+      memcpy(&pad[li.g_off], user + li.g_off_user, (size_t)li.N * 4);
+      memcpy(&pad[li.g_off + li.Np], user + li.g_off_user + li.N, (size_t)li.N * 4);
+    }
   }
   CSB_CUDA_CHECK(cudaMemcpy(dev, pad.data(), h->P_pad * 4, cudaMemcpyHostToDevice));
   return CSB_OK;
@@ -470,6 +491,10 @@ static int download_padded(csb_mlp* h, const float* dev, float* user) {
     const LayerInfo& li = h->layer[l];
     for (int r = 0; r < li.K; ++r) memcpy(user + li.w_off_user + (size_t)r * li.N, &pad[li.w_off + (size_t)r * li.Np], (size_t)li.N * 4);
     memcpy(user + li.b_off_user, &pad[li.b_off], (size_t)li.N * 4);
+    if (li.ln) {
+      memcpy(user + li.g_off_user, &pad[li.g_off], (size_t)li.N * 4);
+      memcpy(user + li.g_off_user + li.N, &pad[li.g_off + li.Np], (size_t)li.N * 4);
+    }
   }
   return CSB_OK;
 }
@@ -498,8 +523,8 @@ static int pad_copy(csb_mlp* h, float* padded, float* user, int dir, cudaStream_
   int64_t mx = 1;
   for (int l = 0; l < h->L; ++l) {
     const LayerInfo& li = h->layer[l];
-    tab.l[l] = {li.K, li.N, li.Np, li.w_off, li.b_off, li.w_off_user, li.b_off_user};
-    mx = std::max<int64_t>(mx, (int64_t)(li.K + 1) * li.N);
+    tab.l[l] = {li.K, li.N, li.Np, li.ln, li.w_off, li.b_off, li.g_off, li.w_off_user, li.b_off_user, li.g_off_user};
+    mx = std::max<int64_t>(mx, (int64_t)(li.K + 3) * li.N);
   }
   dim3 grid((unsigned)std::min<int64_t>(ceil_div(mx, 256), 4 * h->sm_count), (unsigned)h->L);
   simt::pad_copy_kernel<<<grid, 256, 0, st>>>(padded, user, dir, tab);
@@ -595,24 +620,40 @@ static int run_normalize(csb_mlp* h, const float* x, int64_t B, int apply, cudaS
 static int run_hidden_forward(csb_mlp* h, int64_t B, cudaStream_t st) {
   for (int l = 0; l + 1 < h->L; ++l) {
     const LayerInfo& li = h->layer[l];
+    // LayerNorm layers: the GEMM writes z = hW + b (no activation) to zbuf; ln_fwd_kernel then produces act(LN(z))
+    const int gemm_act = li.ln ? CSB_ACT_NONE : li.act;
     if (h->bf16) {
       tc::GemmParams p = {};
-      p.M = (int)B; p.N = li.Np; p.K = li.Kp; p.act = li.act; p.alpha = li.alpha; p.head_relu_from = -1;
-      p.bias = h->params + li.b_off; p.out = h->act[l]; p.ld_out = li.Np;
-      int rc = launch_tn_auto<tc::EPI_BIAS_ACT>(h->tm_in[l].a_k128, h->tm_wt[l], &h->tm_in[l + 1].a_k128, nullptr, p, h->sm_count, st);
+      p.M = (int)B; p.N = li.Np; p.K = li.Kp; p.act = gemm_act; p.alpha = li.alpha; p.head_relu_from = -1;
+      p.bias = h->params + li.b_off; p.out = li.ln ? h->zbuf[l] : h->act[l]; p.ld_out = li.Np;
+      int rc = launch_tn_auto<tc::EPI_BIAS_ACT>(h->tm_in[l].a_k128, h->tm_wt[l], li.ln ? &h->tm_z[l] : &h->tm_in[l + 1].a_k128, nullptr, p,
+                                                h->sm_count, st);
       if (rc) return rc;
     } else {
       simt::SgemmParams p = {};
       p.M = (int)B; p.N = li.Np; p.K = li.Kp;
       p.A = reinterpret_cast<const float*>(layer_in(h, l)); p.lda = li.Kp;
       p.B = h->params + li.w_off; p.ldb = li.Np;
-      p.C = reinterpret_cast<float*>(h->act[l]); p.ldc = li.Np;
-      p.bias = h->params + li.b_off; p.act = li.act; p.alpha = li.alpha; p.head_relu_from = -1;
+      p.C = reinterpret_cast<float*>(li.ln ? h->zbuf[l] : h->act[l]); p.ldc = li.Np;
+      p.bias = h->params + li.b_off; p.act = gemm_act; p.alpha = li.alpha; p.head_relu_from = -1;
       dim3 grid((unsigned)(li.Np / 64), (unsigned)ceil_div(B, 64));
       simt::sgemm_kernel<false, false, simt::SEPI_BIAS_ACT><<<grid, 256, 0, st>>>(p);
       CSB_CUDA_CHECK(cudaGetLastError());
     }
     prof_mark(h, K_GEMM_FWD, st);
+    if (li.ln) {
+      const int grid = (int)std::min<int64_t>(ceil_div(B, 8), (int64_t)h->sm_count * 8);
+      const float* gamma = h->params + li.g_off;
+      if (h->bf16)
+        simt::ln_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(h->zbuf[l]),
+                                                                 reinterpret_cast<__nv_bfloat16*>(h->act[l]), li.Np, gamma, gamma + li.Np,
+                                                                 h->ln_stats[l], B, li.N, li.Np, li.act, li.alpha, 1e-5f);
+      else
+        simt::ln_fwd_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(h->zbuf[l]), reinterpret_cast<float*>(h->act[l]),
+                                                         li.Np, gamma, gamma + li.Np, h->ln_stats[l], B, li.N, li.Np, li.act, li.alpha, 1e-5f);
+      CSB_CUDA_CHECK(cudaGetLastError());
+      prof_mark(h, K_MISC, st);
+    }
   }
   return CSB_OK;
 }
@@ -687,6 +728,28 @@ static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st)
   int64_t max_len = 4;
   for (int l = h->L - 1; l >= 0; --l) {
     const LayerInfo& li = h->layer[l];
+    if (li.ln) {
+      // the buffer holds du_l = dA_l * act'(a_l): LayerNorm parameter gradients, then du -> dz in place
+      const int S = (int)std::max<int64_t>(1, std::min<int64_t>(32, ceil_div(B, 256)));
+      dim3 gridp((unsigned)(li.Np / 64), (unsigned)S);
+      const int gridb = (int)std::min<int64_t>(ceil_div(B, 8), (int64_t)h->sm_count * 8);
+      const float* gamma = h->params + li.g_off;
+      if (h->bf16) {
+        simt::ln_param_grad_kernel<__nv_bfloat16><<<gridp, 256, 0, st>>>(dz16(h, l), reinterpret_cast<const __nv_bfloat16*>(h->zbuf[l]), li.Np,
+                                                                        h->ln_stats[l], B, h->ws + li.ws_g_off, (size_t)2 * li.Np, li.Np);
+        simt::ln_bwd_kernel<__nv_bfloat16><<<gridb, 256, 0, st>>>(dz16(h, l), reinterpret_cast<const __nv_bfloat16*>(h->zbuf[l]), li.Np, gamma,
+                                                                 h->ln_stats[l], B, li.N);
+      } else {
+        simt::ln_param_grad_kernel<float><<<gridp, 256, 0, st>>>(dz32(h, l), reinterpret_cast<const float*>(h->zbuf[l]), li.Np, h->ln_stats[l], B,
+                                                                h->ws + li.ws_g_off, (size_t)2 * li.Np, li.Np);
+        simt::ln_bwd_kernel<float><<<gridb, 256, 0, st>>>(dz32(h, l), reinterpret_cast<const float*>(h->zbuf[l]), li.Np, gamma, h->ln_stats[l], B, li.N);
+      }
+      CSB_CUDA_CHECK(cudaGetLastError());
+      prof_mark(h, K_MISC, st);
+      prof_mark(h, K_MISC, st);
+      tab.seg[tab.n++] = {h->ws + li.ws_g_off, (size_t)2 * li.Np, h->grads + li.g_off, (int64_t)li.Np, S};
+      tab.seg[tab.n++] = {h->ws + li.ws_g_off + li.Np, (size_t)2 * li.Np, h->grads + li.g_off + li.Np, (int64_t)li.Np, S};
+    }
     // ---- weight gradient dW_l = in_l^T . dZ_l  (contraction over the B rows)
     int splits = 1;
     if (h->bf16) {

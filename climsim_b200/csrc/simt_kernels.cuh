@@ -252,10 +252,105 @@ colsum_kernel(const TZ* __restrict__ dz, int ld, int64_t M, float* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// LayerNorm (eps 1e-5, affine, biased variance -- torch.nn.LayerNorm, baseline_models/HSR/training/hsr.py:23) between
+// a Linear and its activation:  u = (z - mean)/sqrt(var + eps) * gamma + beta,  a = act(u).   One warp per row.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+ln_fwd_kernel(const T* __restrict__ z, T* __restrict__ a, int ld, const float* __restrict__ gamma, const float* __restrict__ beta,
+              float* __restrict__ stats, int64_t M, int N, int Np, int act, float alpha, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); r < M; r += warps) {
+    const T* zr = z + r * ld;
+    float s = 0.f;
+    for (int c = lane; c < N; c += 32) s += to_f32<T>(zr[c]);
+    const float mean = warp_sum(s) / (float)N;
+    float q = 0.f;
+    for (int c = lane; c < N; c += 32) { const float d = to_f32<T>(zr[c]) - mean; q += d * d; }
+    const float rstd = rsqrtf(warp_sum(q) / (float)N + eps);
+    if (lane == 0) { stats[2 * r] = mean; stats[2 * r + 1] = rstd; }
+    T* ar = a + r * ld;
+    for (int c = lane; c < Np; c += 32) {
+      float v = 0.f;
+      if (c < N) v = act_fwd(act, alpha, (to_f32<T>(zr[c]) - mean) * rstd * gamma[c] + beta[c]);
+      ar[c] = from_f32<T>(v);
+    }
+  }
+}
+
+// du -> dz in place:  g = du*gamma;  dz = rstd * (g - mean(g) - xhat * mean(g*xhat))
+template <typename T>
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(T* __restrict__ du_dz, const T* __restrict__ z, int ld, const float* __restrict__ gamma, const float* __restrict__ stats,
+              int64_t M, int N) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); r < M; r += warps) {
+    const float mean = stats[2 * r], rstd = stats[2 * r + 1];
+    T* dr = du_dz + r * ld;
+    const T* zr = z + r * ld;
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < N; c += 32) {
+      const float g = to_f32<T>(dr[c]) * gamma[c];
+      s1 += g;
+      s2 += g * (to_f32<T>(zr[c]) - mean) * rstd;
+    }
+    s1 = warp_sum(s1) / (float)N;
+    s2 = warp_sum(s2) / (float)N;
+    for (int c = lane; c < N; c += 32) {
+      const float xh = (to_f32<T>(zr[c]) - mean) * rstd;
+      dr[c] = from_f32<T>(rstd * (to_f32<T>(dr[c]) * gamma[c] - s1 - xh * s2));
+    }
+  }
+}
+
+// dgamma = sum_rows du*xhat, dbeta = sum_rows du: two-stage column sums; partials [S][2][Np] at out + s*stride
+template <typename T>
+__global__ void __launch_bounds__(256)
+ln_param_grad_kernel(const T* __restrict__ du, const T* __restrict__ z, int ld, const float* __restrict__ stats, int64_t M,
+                     float* __restrict__ out, size_t split_stride, int Np) {
+  __shared__ float red[2][4][64];
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int rl = threadIdx.x >> 6;
+  const int S = gridDim.y;
+  const int64_t rows_per = (M + S - 1) / S;
+  const int64_t r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+  float sg = 0.f, sb = 0.f;
+  for (int64_t r = r0 + rl; r < r1; r += 4) {
+    const float d = to_f32<T>(du[r * ld + c]);
+    sg += d * (to_f32<T>(z[r * ld + c]) - stats[2 * r]) * stats[2 * r + 1];
+    sb += d;
+  }
+  red[0][rl][threadIdx.x & 63] = sg;
+  red[1][rl][threadIdx.x & 63] = sb;
+  __syncthreads();
+  if (rl == 0) {
+    const int t = threadIdx.x;
+    float* o = out + (size_t)blockIdx.y * split_stride;
+    o[c] = red[0][0][t] + red[0][1][t] + red[0][2][t] + red[0][3][t];
+    o[Np + c] = red[1][0][t] + red[1][1][t] + red[1][2][t] + red[1][3][t];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // reduce split partials in a fixed order: grad[i] = sum_s ws[s*stride + i]
 // ---------------------------------------------------------------------------------------------------------------
 struct Segment { const float* ws; size_t stride; float* grad; int64_t len; int splits; };
-struct SegmentTable { int n; Segment seg[2 * CSB_MAX_LAYERS]; };
+struct SegmentTable { int n; Segment seg[4 * CSB_MAX_LAYERS]; };
 
 // one launch for every gradient segment: blockIdx.y = segment
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const SegmentTable tab) {
@@ -363,16 +458,18 @@ __global__ void __launch_bounds__(256) repack_kernel(const RepackTable tab) {
 // flat user blob (unpadded, W_l [K x N], b_l [N]) <-> padded internal buffer (W_l [Kp x Np], b_l [Np])
 // dir 0: user -> padded (padding entries untouched = zero);  dir 1: padded -> user.   blockIdx.y = layer
 // ---------------------------------------------------------------------------------------------------------------
-struct PadLayer { int K, N, Np; size_t w_off, b_off, w_off_user, b_off_user; };
+struct PadLayer { int K, N, Np, ln; size_t w_off, b_off, g_off, w_off_user, b_off_user, g_off_user; };   // gamma at g_off, beta at g_off + Np
 struct PadTable { int n; PadLayer l[CSB_MAX_LAYERS]; };
 
 __global__ void __launch_bounds__(256) pad_copy_kernel(float* __restrict__ padded, float* __restrict__ user, int dir, const PadTable tab) {
   const PadLayer L = tab.l[blockIdx.y];
-  const int64_t total = (int64_t)(L.K + 1) * L.N;            // K weight rows + the bias row
+  const int64_t total = (int64_t)(L.K + 1 + 2 * L.ln) * L.N;  // K weight rows + the bias row (+ gamma, beta rows)
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / L.N), c = (int)(i - (int64_t)r * L.N);
-    float* pp = (r < L.K) ? padded + L.w_off + (size_t)r * L.Np + c : padded + L.b_off + c;
-    float* pu = (r < L.K) ? user + L.w_off_user + (size_t)r * L.N + c : user + L.b_off_user + c;
+    float *pp, *pu;
+    if (r < L.K) { pp = padded + L.w_off + (size_t)r * L.Np + c; pu = user + L.w_off_user + (size_t)r * L.N + c; }
+    else if (r == L.K) { pp = padded + L.b_off + c; pu = user + L.b_off_user + c; }
+    else { pp = padded + L.g_off + (size_t)(r - L.K - 1) * L.Np + c; pu = user + L.g_off_user + (size_t)(r - L.K - 1) * L.N + c; }
     if (dir == 0) *pp = *pu; else *pu = *pp;
   }
 }

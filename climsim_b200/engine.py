@@ -37,12 +37,13 @@ class MLPEngine:
     """
 
     def __init__(self, in_dim: int, layers: Sequence[Tuple[int, str, float]], head_relu_from: int = -1,
-                 dtype: str = "bf16", loss: str = "mse", max_batch: int = 65536):
+                 dtype: str = "bf16", loss: str = "mse", max_batch: int = 65536, layernorm: Optional[Sequence[bool]] = None):
         self.lib = _lib.load()
         cfg = _lib.MlpCfg()
         cfg.in_dim, cfg.n_layers = in_dim, len(layers)
+        self.layernorm = [bool(b) for b in layernorm] if layernorm is not None else [False] * len(layers)
         for i, (n, act, alpha) in enumerate(layers):
-            cfg.units[i], cfg.act[i], cfg.alpha[i], cfg.layernorm[i] = n, _lib.ACT[act], alpha, 0
+            cfg.units[i], cfg.act[i], cfg.alpha[i], cfg.layernorm[i] = n, _lib.ACT[act], alpha, int(self.layernorm[i])
         cfg.head_relu_from, cfg.dtype, cfg.loss, cfg.max_batch = head_relu_from, _lib.DTYPE[dtype], _lib.LOSS[loss], max_batch
         self._h = C.c_void_p()
         _lib.check(self.lib.csb_mlp_create(C.byref(cfg), C.byref(self._h)), "csb_mlp_create")
@@ -110,9 +111,12 @@ class MLPEngine:
     def split_flat(self, flat: np.ndarray) -> List[np.ndarray]:
         """flat blob -> [W0 (in,out), b0, W1, b1, ...] views."""
         out, off = [], 0
-        for k, n in self.layer_dims:
+        for (k, n), ln in zip(self.layer_dims, self.layernorm):
             out.append(flat[off:off + k * n].reshape(k, n)); off += k * n
             out.append(flat[off:off + n]); off += n
+            if ln:                                            # gamma, beta
+                out.append(flat[off:off + n]); off += n
+                out.append(flat[off:off + n]); off += n
         return out
 
     @staticmethod

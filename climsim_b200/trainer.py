@@ -16,13 +16,15 @@ import torch
 from .engine import MLPEngine
 
 
-def glorot_uniform_flat(layer_dims: Sequence[tuple], seed: int = 0) -> np.ndarray:
-    """Keras default initialisation (glorot_uniform kernels, zero biases) as the engine's flat blob."""
+def glorot_uniform_flat(layer_dims: Sequence[tuple], seed: int = 0, layernorm: Optional[Sequence[bool]] = None) -> np.ndarray:
+    """Keras default initialisation (glorot_uniform kernels, zero biases; LayerNorm gamma 1, beta 0) as the engine's flat blob."""
     rng = np.random.default_rng(seed)
     parts = []
-    for k, n in layer_dims:
+    for i, (k, n) in enumerate(layer_dims):
         lim = math.sqrt(6.0 / (k + n))
         parts += [rng.uniform(-lim, lim, size=(k, n)).astype(np.float32).reshape(-1), np.zeros(n, np.float32)]
+        if layernorm is not None and layernorm[i]:
+            parts += [np.ones(n, np.float32), np.zeros(n, np.float32)]
     return np.concatenate(parts)
 
 

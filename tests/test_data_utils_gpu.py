@@ -92,3 +92,41 @@ def test_ed_preset_matches_oracle():
     with torch.no_grad():
         got16 = net16(x.cuda()).cpu().numpy()
     assert np.abs(got16 - want).max() <= 5e-2 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("dtype,tol_out,tol_g", [("fp32", 2e-5, 1e-4), ("bf16", 5e-2, 1e-1)])
+def test_hsr_layernorm_model_against_reference_golden(golden_dir, dtype, tol_out, tol_g):
+    """The LayerNorm MLP pair with the weights, inputs and expected outputs / gradients of the REFERENCE's own
+    HeteroskedasticRegression (tests/golden/hsr_small.npz, produced by running hsr.py): forward, MSE loss and NLL loss."""
+    from climsim_b200.baseline_models import HSR
+    g = np.load(os.path.join(golden_dir, "hsr_small.npz"))
+    sd = {k[len("init::"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("init::")}
+    net = HSR(124, 128, hidden_dims=32, layers=2, dtype=dtype, max_batch=64)
+    net.load_reference_state_dict(sd)
+    x, y = torch.from_numpy(g["x0"]).cuda(), torch.from_numpy(g["y0"]).cuda()
+    mu, lp = net(x)
+    scale = lambda a: np.abs(a).max()
+    assert np.abs(mu.detach().cpu().numpy() - g["mu"]).max() <= tol_out * scale(g["mu"])
+    assert np.abs(lp.detach().cpu().numpy() - g["logprec"]).max() <= tol_out * scale(g["logprec"])
+    for mode in ("mse", "mle"):
+        net.zero_grad()
+        mu, lp = net(x)
+        loss = ((y - mu) ** 2).mean() if mode == "mse" else (torch.exp(lp) * (y - mu) ** 2 - lp).mean()
+        torch.clip(loss, min=-1e5, max=1e5).backward()
+        assert abs(loss.item() - float(g[f"loss_{mode}"])) <= max(tol_out, 1e-5) * abs(float(g[f"loss_{mode}"]))
+        for name, sub in (("mean", net.mean), ("logprec", net.logprec)):
+            if sub.flat.grad is None:
+                continue
+            views, off, got = sub.layer_views(), 0, sub.flat.grad.cpu().numpy()
+            keys = []
+            for i in range(2):
+                keys += [(f"{name}.linear{i}.0.weight", True), (f"{name}.linear{i}.0.bias", False),
+                         (f"{name}.linear{i}.1.weight", False), (f"{name}.linear{i}.1.bias", False)]
+            keys += [(f"{name}.final_linear.weight", True), (f"{name}.final_linear.bias", False)]
+            for (key, transpose), v in zip(keys, views):
+                want = g[f"grad_{mode}::{key}"]
+                want = want.T if transpose else want
+                part = got[off:off + v.numel()].reshape(want.shape)
+                off += v.numel()
+                err = np.linalg.norm(part - want) / max(np.linalg.norm(want), 1e-12)
+                assert err <= tol_g, (mode, key, err)
