@@ -5,6 +5,6 @@ Device side: hand-written sm_100a CUDA in ``csrc/`` behind the C ABI of ``includ
 (``libclimsim_b200.so``).  There is no CPU fallback: importing works anywhere, computing needs a B200.
 """
 from . import _lib  # noqa: F401
-from .engine import MLPEngine  # noqa: F401
+from .engine import CNNEngine, MLPEngine  # noqa: F401
 
 __version__ = "0.1.0"

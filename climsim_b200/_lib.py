@@ -28,6 +28,12 @@ class MlpCfg(C.Structure):
                 ("loss", C.c_int32), ("max_batch", C.c_int64)]
 
 
+class CnnCfg(C.Structure):
+    _fields_ = [("depth", C.c_int32), ("width", C.c_int32), ("kernel", C.c_int32), ("in_ch", C.c_int32), ("out_ch", C.c_int32),
+                ("out_lin", C.c_int32), ("levels", C.c_int32), ("act", C.c_int32), ("pre_out_act", C.c_int32), ("dtype", C.c_int32),
+                ("loss", C.c_int32), ("max_batch", C.c_int64)]
+
+
 class CsbError(RuntimeError):
     def __init__(self, code: int, where: str, detail: str):
         super().__init__(f"{where} failed: {detail} (code {code})")
@@ -66,6 +72,18 @@ SIGNATURES = {
     "csb_mlp_profile_read": (C.c_int, [_VP, _P(C.c_double), _P(C.c_int64), C.c_int]),
     "csb_profile_kind_count": (C.c_int, []),
     "csb_profile_kind_name": (C.c_char_p, [C.c_int]),
+    "csb_cnn_create": (C.c_int, [_P(CnnCfg), _P(_VP)]),
+    "csb_cnn_destroy": (C.c_int, [_VP]),
+    "csb_cnn_param_count": (C.c_size_t, [_VP]),
+    "csb_cnn_set_params": (C.c_int, [_VP, _VP]),
+    "csb_cnn_get_params": (C.c_int, [_VP, _VP]),
+    "csb_cnn_get_grads": (C.c_int, [_VP, _VP]),
+    "csb_cnn_set_loss_weights": (C.c_int, [_VP, _VP]),
+    "csb_cnn_forward": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP]),
+    "csb_cnn_train_step": (C.c_int, [_VP, _VP, _VP, C.c_int64, C.c_float, _VP, _VP]),
+    "csb_cnn_grad_buffer": (C.c_int, [_VP, _P(_VP), _P(C.c_size_t)]),
+    "csb_cnn_apply_opt": (C.c_int, [_VP, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _VP]),
+    "csb_cnn_launch_count": (C.c_int64, [_VP]),
     "csb_normalize": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int64, C.c_int32, _VP]),
     "csb_reshape_input_for_cnn": (C.c_int, [_VP, _VP, C.c_int64, _VP]),
     "csb_reshape_target_for_cnn": (C.c_int, [_VP, _VP, C.c_int64, _VP]),

@@ -1,0 +1,441 @@
+// cnn_engine.cuh -- the csb_cnn_* C ABI: ResNet-1D column emulator of baseline_models/CNN/training/hpo_train.py:131-200
+// (included at the end of mlp_engine.cu: shares its TMA / launch / profiling helpers).
+//
+// Layout: channels-last with one zero halo row above and below every column: sample b owns rows b*62 .. b*62+61 of a
+// [B*62, Cp] bf16 matrix (Cp = channels padded to 64).  Conv1D(k=3,'same') is then ONE GEMM whose contraction runs over
+// (tap, channel): contraction block kb reads the activation rows shifted by (tap - 1) -- the TMA producer of
+// gemm_tn_kernel does the shift, out-of-range rows are zero-filled by TMA, and the epilogue writes zeros into the halo
+// rows so that they keep acting as 'same' padding for the next layer.  1x1 convolutions and the per-level Dense heads
+// are plain GEMMs over the same rows.  Residual `x = relu(conv2) + conv1x1(block input)` = EPI_BIAS_ADD (the relu(conv2)
+// tile arrives by TMA into the staging tile and is added in place).
+//
+// Backward: data gradients are convolutions with the tap-flipped, transposed kernels (wd16 copies); weight gradients
+// are one gemm_nt launch per tap with the activation rows shifted by (tap - 1); bias gradients ride in the tap-0 launch.
+// Only the CSB_BF16 arithmetic mode exists for the CNN so far.
+#pragma once
+
+struct ConvLayerInfo {
+  int taps, Cin, Cout, Cinp, Coutp, act;
+  size_t w_off, b_off, w_off_user, b_off_user;
+  size_t ws_w_off, ws_b_off;
+  int max_splits;
+  __nv_bfloat16 *wt16 = nullptr, *wd16 = nullptr;
+  CUtensorMap tm_wt, tm_wd;
+};
+
+struct BufMaps { CUtensorMap k128, mn64; };
+
+struct csb_cnn {
+  csb_cnn_cfg cfg;
+  int depth = 0, L = 60, P = 62;                 // levels, rows per sample incl. halo
+  int n_layers = 0;                              // 3*depth + 2
+  ConvLayerInfo layer[3 * 16 + 2];
+  int in_ch = 6, in_p = 64, width = 0, width_p = 0, out_ch = 10, out_p = 64, out_lin = 2;
+  int64_t cap = 0;                               // rows capacity = max_batch * P rounded to 128
+  size_t P_pad = 0, P_user = 0, ws_elems = 0;
+  int sm_count = 0;
+  float *params = nullptr, *grads = nullptr, *m = nullptr, *v = nullptr, *ws = nullptr, *zero_bias = nullptr;
+  // activation buffers: x0, per block (h1, h2, out), e;  gradient buffers G0, G1, Z1, Z2, T, dzh (head), dze
+  __nv_bfloat16* x0 = nullptr;
+  __nv_bfloat16* h1[16] = {};
+  __nv_bfloat16* h2[16] = {};
+  __nv_bfloat16* ob[16] = {};
+  __nv_bfloat16 *e = nullptr, *G[2] = {nullptr, nullptr}, *Z1 = nullptr, *Z2 = nullptr, *T = nullptr, *dzh = nullptr, *dze = nullptr;
+  float *d_loss_w = nullptr, *loss_partials = nullptr, *d_loss = nullptr;
+  int n_loss_partials = 0;
+  int64_t maps_B = -1;
+  BufMaps mx0, mh1[16], mh2[16], mob[16], me, mG[2], mZ1, mZ2, mT, mdzh, mdze;
+  int64_t step = 0, launches = 0;
+};
+
+static void cnn_free(csb_cnn* h) {
+  auto F = [](void* p) { if (p) cudaFree(p); };
+  F(h->params); F(h->grads); F(h->m); F(h->v); F(h->ws); F(h->zero_bias);
+  for (int l = 0; l < h->n_layers; ++l) { F(h->layer[l].wt16); F(h->layer[l].wd16); }
+  F(h->x0); F(h->e); F(h->G[0]); F(h->G[1]); F(h->Z1); F(h->Z2); F(h->T); F(h->dzh); F(h->dze);
+  for (int i = 0; i < 16; ++i) { F(h->h1[i]); F(h->h2[i]); F(h->ob[i]); }
+  F(h->d_loss_w); F(h->loss_partials); F(h->d_loss);
+}
+
+static int cnn_repack(csb_cnn* h, cudaStream_t st) {
+  simt::ConvRepackTable tab;
+  tab.n = h->n_layers;
+  int64_t mx = 1;
+  for (int l = 0; l < h->n_layers; ++l) {
+    ConvLayerInfo& li = h->layer[l];
+    tab.l[l] = {h->params + li.w_off, li.wt16, li.wd16, li.taps, li.Cinp, li.Coutp};
+    mx = std::max<int64_t>(mx, (int64_t)li.taps * li.Cinp * li.Coutp);
+  }
+  dim3 grid((unsigned)std::min<int64_t>(ceil_div(mx, 256), 4 * h->sm_count), (unsigned)h->n_layers);
+  simt::conv_repack_kernel<<<grid, 256, 0, st>>>(tab);
+  CSB_CUDA_CHECK(cudaGetLastError());
+  h->launches++;
+  return CSB_OK;
+}
+
+static int cnn_pad_copy(csb_cnn* h, float* padded, float* user, int dir, cudaStream_t st) {
+  simt::ConvPadTable tab;
+  tab.n = h->n_layers;
+  int64_t mx = 1;
+  for (int l = 0; l < h->n_layers; ++l) {
+    const ConvLayerInfo& li = h->layer[l];
+    tab.l[l] = {li.taps, li.Cin, li.Cout, li.Cinp, li.Coutp, li.w_off, li.b_off, li.w_off_user, li.b_off_user};
+    mx = std::max<int64_t>(mx, (int64_t)li.taps * li.Cin * li.Cout + li.Cout);
+  }
+  dim3 grid((unsigned)std::min<int64_t>(ceil_div(mx, 256), 4 * h->sm_count), (unsigned)h->n_layers);
+  simt::conv_pad_copy_kernel<<<grid, 256, 0, st>>>(padded, user, dir, tab);
+  CSB_CUDA_CHECK(cudaGetLastError());
+  h->launches++;
+  return CSB_OK;
+}
+
+static int cnn_buf_maps(BufMaps* m, const void* buf, int Cp, int64_t rows) {
+  int rc = make_tmap_bf16(&m->k128, buf, Cp, rows, Cp, 64, 128);
+  if (rc) return rc;
+  return make_tmap_bf16(&m->mn64, buf, Cp, rows, Cp, 64, 64);
+}
+
+static int cnn_build_maps(csb_cnn* h, int64_t B) {
+  if (h->maps_B == B) return CSB_OK;
+  const int64_t R = B * h->P;
+  int rc;
+  if ((rc = cnn_buf_maps(&h->mx0, h->x0, h->in_p, R))) return rc;
+  for (int i = 0; i < h->depth; ++i) {
+    if ((rc = cnn_buf_maps(&h->mh1[i], h->h1[i], h->width_p, R))) return rc;
+    if ((rc = cnn_buf_maps(&h->mh2[i], h->h2[i], h->width_p, R))) return rc;
+    if ((rc = cnn_buf_maps(&h->mob[i], h->ob[i], h->width_p, R))) return rc;
+  }
+  if ((rc = cnn_buf_maps(&h->me, h->e, h->out_p, R))) return rc;
+  for (int i = 0; i < 2; ++i) if ((rc = cnn_buf_maps(&h->mG[i], h->G[i], h->width_p, R))) return rc;
+  if ((rc = cnn_buf_maps(&h->mZ1, h->Z1, h->width_p, R))) return rc;
+  if ((rc = cnn_buf_maps(&h->mZ2, h->Z2, h->width_p, R))) return rc;
+  if ((rc = cnn_buf_maps(&h->mT, h->T, h->width_p, R))) return rc;
+  if ((rc = cnn_buf_maps(&h->mdzh, h->dzh, h->out_p, R))) return rc;
+  if ((rc = cnn_buf_maps(&h->mdze, h->dze, h->out_p, R))) return rc;
+  h->maps_B = B;
+  return CSB_OK;
+}
+
+// one convolution-as-GEMM launch.  `dgrad` selects the flipped/transposed weights (output width = Cinp).
+template <int EPI>
+static int cnn_gemm(csb_cnn* h, const ConvLayerInfo& li, bool dgrad, const CUtensorMap& a, const CUtensorMap* out, const CUtensorMap* saved,
+                    tc::GemmParams p, int64_t B, cudaStream_t st) {
+  p.M = (int)(B * h->P);
+  p.N = dgrad ? li.Cinp : li.Coutp;
+  p.K = li.taps * (dgrad ? li.Coutp : li.Cinp);
+  p.kb_per_tap = (dgrad ? li.Coutp : li.Cinp) / 64;
+  p.tap_center = (li.taps - 1) / 2;
+  p.halo_period = h->P;
+  int rc = launch_tn_auto<EPI>(a, dgrad ? li.tm_wd : li.tm_wt, out, saved, p, h->sm_count, st);
+  if (rc) return rc;
+  h->launches++;
+  return CSB_OK;
+}
+
+// weight (+ bias) gradient of one conv layer: in [R, Cinp], dz [R, Coutp]
+static int cnn_wgrad(csb_cnn* h, const ConvLayerInfo& li, const BufMaps& in, const BufMaps& dz, int64_t B, simt::SegmentTable& tab,
+                     int64_t& max_len, cudaStream_t st) {
+  const int64_t R = B * h->P;
+  const int num_rb = (int)ceil_div(R, 64);
+  int splits = std::max(1, std::min(li.max_splits, num_rb));
+  const size_t tap_elems = (size_t)li.Cinp * li.Coutp;
+  for (int t = 0; t < li.taps; ++t) {
+    tc::NtParams p = {};
+    p.M = li.Cinp; p.N = li.Coutp; p.R = (int)R;
+    p.rb_per_split = (int)ceil_div(num_rb, splits);
+    const int eff = (int)ceil_div(num_rb, p.rb_per_split);
+    p.out = h->ws + li.ws_w_off + (size_t)t * tap_elems; p.ld_out = li.Coutp; p.split_stride = (size_t)li.taps * tap_elems;
+    p.a_row_offset = t - (li.taps - 1) / 2;
+    if (t == 0) { p.colsum_out = h->ws + li.ws_b_off; p.colsum_stride = (size_t)li.Coutp; }
+    int rc = launch_nt_auto(in.mn64, dz.mn64, p, eff, st);
+    if (rc) return rc;
+    h->launches++;
+    splits = eff;
+  }
+  tab.seg[tab.n++] = {h->ws + li.ws_w_off, (size_t)li.taps * tap_elems, h->grads + li.w_off, (int64_t)(li.taps * tap_elems), splits};
+  tab.seg[tab.n++] = {h->ws + li.ws_b_off, (size_t)li.Coutp, h->grads + li.b_off, (int64_t)li.Coutp, splits};
+  max_len = std::max<int64_t>(max_len, (int64_t)(li.taps * tap_elems));
+  return CSB_OK;
+}
+
+static int cnn_forward_body(csb_cnn* h, const float* x, int64_t B, cudaStream_t st) {
+  const int64_t R = B * h->P;
+  simt::cnn_pack_input_kernel<<<grid_for(R * h->in_p, 256, h->sm_count), 256, 0, st>>>(x, h->x0, B, h->L, h->in_ch, h->in_p);
+  CSB_CUDA_CHECK(cudaGetLastError());
+  h->launches++;
+  const BufMaps* xin = &h->mx0;
+  int rc;
+  for (int i = 0; i < h->depth; ++i) {
+    const ConvLayerInfo &c1 = h->layer[3 * i], &c2 = h->layer[3 * i + 1], &cr = h->layer[3 * i + 2];
+    tc::GemmParams p = {};
+    p.act = c1.act; p.head_relu_from = -1; p.bias = h->params + c1.b_off;
+    if ((rc = cnn_gemm<tc::EPI_BIAS_ACT>(h, c1, false, xin->k128, &h->mh1[i].k128, nullptr, p, B, st))) return rc;
+    p.act = c2.act; p.bias = h->params + c2.b_off;
+    if ((rc = cnn_gemm<tc::EPI_BIAS_ACT>(h, c2, false, h->mh1[i].k128, &h->mh2[i].k128, nullptr, p, B, st))) return rc;
+    p.act = CSB_ACT_NONE; p.bias = h->params + cr.b_off;          // out = conv1x1(x_in) + b + relu(conv2)
+    if ((rc = cnn_gemm<tc::EPI_BIAS_ADD>(h, cr, false, xin->k128, &h->mob[i].k128, &h->mh2[i].k128, p, B, st))) return rc;
+    xin = &h->mob[i];
+  }
+  const ConvLayerInfo& co = h->layer[3 * h->depth];
+  tc::GemmParams p = {};
+  p.act = co.act; p.head_relu_from = -1; p.bias = h->params + co.b_off;
+  return cnn_gemm<tc::EPI_BIAS_ACT>(h, co, false, xin->k128, &h->me.k128, nullptr, p, B, st);
+}
+
+extern "C" {
+
+int csb_cnn_create(const csb_cnn_cfg* cfg, csb_cnn** out) {
+  CSB_REQUIRE(cfg && out, CSB_EINVAL, "null argument");
+  *out = nullptr;
+  CSB_REQUIRE(cfg->depth >= 1 && cfg->depth <= 16, CSB_EINVAL, "depth %d out of range 1..16", cfg->depth);
+  CSB_REQUIRE(cfg->kernel == 3 || cfg->kernel == 1, CSB_EINVAL, "kernel width must be 1 or 3");
+  CSB_REQUIRE(cfg->width >= 1 && cfg->in_ch >= 1 && cfg->out_ch >= 1 && cfg->out_lin >= 0 && cfg->out_lin <= cfg->out_ch, CSB_EINVAL, "bad channel configuration");
+  CSB_REQUIRE(cfg->levels >= 1 && cfg->max_batch >= 1, CSB_EINVAL, "levels / max_batch must be positive");
+  CSB_REQUIRE(cfg->dtype == CSB_BF16, CSB_EUNSUPPORTED, "the CNN engine implements the CSB_BF16 mode only");
+  CSB_REQUIRE(cfg->loss == CSB_LOSS_MSE || cfg->loss == CSB_LOSS_MAE, CSB_EINVAL, "unknown loss %d", cfg->loss);
+  int sm = 0, maj = 0, mnr = 0;
+  int rc = csb_device_info(&sm, &maj, &mnr, nullptr);
+  if (rc) return rc;
+  CSB_REQUIRE(maj == 10, CSB_ENODEV, "device has compute capability %d.%d; this library is sm_100a only", maj, mnr);
+  g_use_pairs = getenv("CSB_NO_PAIRS") == nullptr;
+
+  csb_cnn* h = new (std::nothrow) csb_cnn();
+  CSB_REQUIRE(h != nullptr, CSB_ENOMEM, "host allocation failed");
+  h->cfg = *cfg;
+  h->depth = cfg->depth; h->L = cfg->levels; h->P = cfg->levels + 2;
+  h->in_ch = cfg->in_ch; h->in_p = (int)round_up(cfg->in_ch, 64);
+  h->width = cfg->width; h->width_p = (int)round_up(cfg->width, 64);
+  h->out_ch = cfg->out_ch; h->out_p = (int)round_up(cfg->out_ch, 64); h->out_lin = cfg->out_lin;
+  h->sm_count = sm;
+  h->cap = round_up(cfg->max_batch * h->P, 128);
+  h->n_layers = 3 * h->depth + 2;
+  size_t off = 0, off_user = 0, ws_off = 0;
+  auto add = [&](int idx, int taps, int cin, int cout, int act) {
+    ConvLayerInfo& li = h->layer[idx];
+    li.taps = taps; li.Cin = cin; li.Cout = cout; li.Cinp = (int)round_up(cin, 64); li.Coutp = (int)round_up(cout, 64); li.act = act;
+    li.w_off = off; off += (size_t)taps * li.Cinp * li.Coutp;
+    li.b_off = off; off += (size_t)li.Coutp;
+    li.w_off_user = off_user; off_user += (size_t)taps * cin * cout;
+    li.b_off_user = off_user; off_user += (size_t)cout;
+    const int tiles = (int)(ceil_div(li.Cinp, 128) * ceil_div(li.Coutp, tn_block_n(li.Coutp)));
+    li.max_splits = std::max(1, std::min(64, sm / tiles));
+    li.ws_w_off = ws_off; ws_off += (size_t)li.max_splits * taps * li.Cinp * li.Coutp;
+    li.ws_b_off = ws_off; ws_off += (size_t)li.max_splits * li.Coutp;
+  };
+  int c = cfg->in_ch;
+  for (int i = 0; i < h->depth; ++i) {
+    add(3 * i, cfg->kernel, c, cfg->width, cfg->act);
+    add(3 * i + 1, cfg->kernel, cfg->width, cfg->width, cfg->act);
+    add(3 * i + 2, 1, c, cfg->width, CSB_ACT_NONE);
+    c = cfg->width;
+  }
+  add(3 * h->depth, 1, c, cfg->out_ch, cfg->pre_out_act);
+  add(3 * h->depth + 1, 1, cfg->out_ch, cfg->out_ch, CSB_ACT_NONE);      // Dense(out_lin, linear) || Dense(out_ch - out_lin, relu), fused column-wise
+  h->P_pad = off; h->P_user = off_user; h->ws_elems = ws_off;
+
+#define CKA(ptr, bytes) do { int _rc = [&]() -> int { CSB_ALLOC(ptr, bytes); return CSB_OK; }(); if (_rc) { cnn_free(h); delete h; return _rc; } } while (0)
+  CKA(h->params, h->P_pad * 4); CKA(h->grads, h->P_pad * 4); CKA(h->m, h->P_pad * 4); CKA(h->v, h->P_pad * 4);
+  CKA(h->ws, h->ws_elems * 4);
+  CKA(h->zero_bias, (size_t)std::max(h->width_p, h->out_p) * 4);
+  const size_t wide = (size_t)h->cap * h->width_p * 2, narrow = (size_t)h->cap * h->out_p * 2;
+  CKA(h->x0, (size_t)h->cap * h->in_p * 2);
+  for (int i = 0; i < h->depth; ++i) { CKA(h->h1[i], wide); CKA(h->h2[i], wide); CKA(h->ob[i], wide); }
+  CKA(h->e, narrow); CKA(h->dzh, narrow); CKA(h->dze, narrow);
+  CKA(h->G[0], wide); CKA(h->G[1], wide); CKA(h->Z1, wide); CKA(h->Z2, wide); CKA(h->T, wide);
+  CKA(h->d_loss_w, (size_t)h->out_p * 4);
+  h->n_loss_partials = (int)(h->cap / 128 * tc::TN_EPI_WARPS);
+  CKA(h->loss_partials, (size_t)h->n_loss_partials * 4);
+  CKA(h->d_loss, 4);
+  for (int l = 0; l < h->n_layers; ++l) {
+    ConvLayerInfo& li = h->layer[l];
+    const size_t n = (size_t)li.taps * li.Cinp * li.Coutp;
+    CKA(li.wt16, n * 2); CKA(li.wd16, n * 2);
+  }
+#undef CKA
+  for (int l = 0; l < h->n_layers; ++l) {
+    ConvLayerInfo& li = h->layer[l];
+    rc = make_tmap_bf16(&li.tm_wt, li.wt16, (uint64_t)li.taps * li.Cinp, li.Coutp, (uint64_t)li.taps * li.Cinp, 64, (uint32_t)tn_b_box_rows(li.Coutp));
+    if (!rc) rc = make_tmap_bf16(&li.tm_wd, li.wd16, (uint64_t)li.taps * li.Coutp, li.Cinp, (uint64_t)li.taps * li.Coutp, 64, (uint32_t)tn_b_box_rows(li.Cinp));
+    if (rc) { cnn_free(h); delete h; return rc; }
+  }
+  // default loss weights: the reference's *_adjusted losses (hpo_train.py:114-121): per-sample sum over (level, channel) of
+  // w_c * e with w = (120/128)/(levels*out_lin) on the profile channels and (8/128)/(levels*(out_ch-out_lin)) on the scalars
+  {
+    std::vector<float> w(h->out_p, 0.f);
+    for (int ch = 0; ch < h->out_ch; ++ch)
+      w[ch] = ch < h->out_lin ? (120.f / 128.f) / (float)(h->L * h->out_lin) : (8.f / 128.f) / (float)(h->L * (h->out_ch - h->out_lin));
+    if (cudaMemcpy(h->d_loss_w, w.data(), (size_t)h->out_p * 4, cudaMemcpyHostToDevice) != cudaSuccess) { cnn_free(h); delete h; set_last_error("cudaMemcpy failed"); return CSB_ECUDA; }
+  }
+  *out = h;
+  return CSB_OK;
+}
+
+int csb_cnn_destroy(csb_cnn* h) {
+  if (!h) return CSB_OK;
+  cudaDeviceSynchronize();
+  cnn_free(h);
+  delete h;
+  return CSB_OK;
+}
+
+size_t csb_cnn_param_count(const csb_cnn* h) { return h ? h->P_user : 0; }
+int64_t csb_cnn_launch_count(const csb_cnn* h) { return h ? h->launches : 0; }
+
+int csb_cnn_set_params(csb_cnn* h, const float* params_host) {
+  CSB_REQUIRE(h && params_host, CSB_EINVAL, "null argument");
+  float* tmp = nullptr;
+  CSB_CUDA_CHECK(cudaDeviceSynchronize());
+  CSB_CUDA_CHECK(cudaMalloc(&tmp, h->P_user * 4));
+  cudaError_t e = cudaMemcpy(tmp, params_host, h->P_user * 4, cudaMemcpyHostToDevice);
+  int rc = (e == cudaSuccess) ? cnn_pad_copy(h, h->params, tmp, 0, 0) : CSB_ECUDA;
+  if (!rc) rc = cnn_repack(h, 0);
+  cudaDeviceSynchronize();
+  cudaFree(tmp);
+  return rc;
+}
+static int cnn_download(csb_cnn* h, float* dev_padded, float* host) {
+  float* tmp = nullptr;
+  CSB_CUDA_CHECK(cudaDeviceSynchronize());
+  CSB_CUDA_CHECK(cudaMalloc(&tmp, h->P_user * 4));
+  int rc = cnn_pad_copy(h, dev_padded, tmp, 1, 0);
+  cudaError_t e = cudaMemcpy(host, tmp, h->P_user * 4, cudaMemcpyDeviceToHost);
+  cudaFree(tmp);
+  if (e != cudaSuccess) { set_last_error("cudaMemcpy failed"); return CSB_ECUDA; }
+  return rc;
+}
+int csb_cnn_get_params(csb_cnn* h, float* params_host) {
+  CSB_REQUIRE(h && params_host, CSB_EINVAL, "null argument");
+  return cnn_download(h, h->params, params_host);
+}
+int csb_cnn_get_grads(csb_cnn* h, float* grads_host) {
+  CSB_REQUIRE(h && grads_host, CSB_EINVAL, "null argument");
+  return cnn_download(h, h->grads, grads_host);
+}
+int csb_cnn_grad_buffer(csb_cnn* h, float** ptr, size_t* n) {
+  CSB_REQUIRE(h && ptr && n, CSB_EINVAL, "null argument");
+  *ptr = h->grads; *n = h->P_pad;
+  return CSB_OK;
+}
+int csb_cnn_set_loss_weights(csb_cnn* h, const float* w_host) {
+  CSB_REQUIRE(h && w_host, CSB_EINVAL, "null argument");
+  std::vector<float> w(h->out_p, 0.f);
+  for (int c = 0; c < h->out_ch; ++c) w[c] = w_host[c];
+  CSB_CUDA_CHECK(cudaDeviceSynchronize());
+  CSB_CUDA_CHECK(cudaMemcpy(h->d_loss_w, w.data(), (size_t)h->out_p * 4, cudaMemcpyHostToDevice));
+  return CSB_OK;
+}
+
+int csb_cnn_forward(csb_cnn* h, const float* x, float* y_pred, int64_t B, void* stream) {
+  CSB_REQUIRE(h && x && y_pred, CSB_EINVAL, "null argument");
+  CSB_REQUIRE(B >= 1 && B <= h->cfg.max_batch, CSB_ESTATE, "batch %lld outside 1..max_batch %lld", (long long)B, (long long)h->cfg.max_batch);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc;
+  if ((rc = cnn_build_maps(h, B))) return rc;
+  if ((rc = cnn_forward_body(h, x, B, st))) return rc;
+  const ConvLayerInfo& cd = h->layer[3 * h->depth + 1];
+  tc::GemmParams p = {};
+  p.act = CSB_ACT_NONE; p.head_relu_from = h->out_lin; p.bias = h->params + cd.b_off;
+  p.out_dim = h->out_ch; p.pred = y_pred; p.ld_pred = h->out_ch;
+  return cnn_gemm<tc::EPI_HEAD_OUT>(h, cd, false, h->me.k128, nullptr, nullptr, p, B, st);
+}
+
+int csb_cnn_train_step(csb_cnn* h, const float* x, const float* y, int64_t B, float grad_scale, float* loss_out, void* stream) {
+  CSB_REQUIRE(h && x && y, CSB_EINVAL, "null argument");
+  CSB_REQUIRE(B >= 1 && B <= h->cfg.max_batch, CSB_ESTATE, "batch %lld outside 1..max_batch %lld", (long long)B, (long long)h->cfg.max_batch);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (grad_scale <= 0.f) grad_scale = 1.f / (float)B;       // the *_adjusted losses average over the batch (weights carry the rest)
+  int rc;
+  if ((rc = cnn_build_maps(h, B))) return rc;
+  if ((rc = cnn_forward_body(h, x, B, st))) return rc;
+  const int D = h->depth;
+  const ConvLayerInfo &co = h->layer[3 * D], &cd = h->layer[3 * D + 1];
+  const int64_t R = B * h->P;
+  // ---- head + loss: dzh = dL/dz of the fused Dense heads
+  {
+    tc::GemmParams p = {};
+    p.act = CSB_ACT_NONE; p.head_relu_from = h->out_lin; p.bias = h->params + cd.b_off; p.out_dim = h->out_ch;
+    p.y = y; p.ld_y = h->out_ch; p.loss_w = h->d_loss_w; p.grad_scale = grad_scale; p.loss_kind = h->cfg.loss;
+    p.loss_partials = h->loss_partials;
+    if ((rc = cnn_gemm<tc::EPI_HEAD_LOSS>(h, cd, false, h->me.k128, &h->mdzh.k128, nullptr, p, B, st))) return rc;
+    simt::loss_finalize_kernel<<<1, 256, 0, st>>>(h->loss_partials, (int)ceil_div(R, 128) * tc::TN_EPI_WARPS, loss_out ? loss_out : h->d_loss);
+    CSB_CUDA_CHECK(cudaGetLastError());
+    h->launches++;
+  }
+  simt::SegmentTable tab;
+  tab.n = 0;
+  int64_t max_len = 4;
+  auto flush_reduce = [&]() -> int {
+    if (tab.n == 0) return CSB_OK;
+    dim3 grid((unsigned)std::min<int64_t>(ceil_div(max_len / 4, 256), 2 * h->sm_count), (unsigned)tab.n);
+    simt::reduce_partials_kernel<<<grid, 256, 0, st>>>(tab);
+    CSB_CUDA_CHECK(cudaGetLastError());
+    h->launches++;
+    tab.n = 0; max_len = 4;
+    return CSB_OK;
+  };
+  // ---- Dense heads and the 1x1 output convolution
+  if ((rc = cnn_wgrad(h, cd, h->me, h->mdzh, B, tab, max_len, st))) return rc;
+  {
+    tc::GemmParams p = {};
+    p.act = co.act; p.head_relu_from = -1;                    // dze = (dzh . Wd^T) * elu'(e)
+    if ((rc = cnn_gemm<tc::EPI_DGRAD>(h, cd, true, h->mdzh.k128, &h->mdze.k128, &h->me.k128, p, B, st))) return rc;
+  }
+  const BufMaps* last_out = D > 0 ? &h->mob[D - 1] : &h->mx0;
+  if ((rc = cnn_wgrad(h, co, *last_out, h->mdze, B, tab, max_len, st))) return rc;
+  int g = 0;
+  {
+    tc::GemmParams p = {};
+    p.act = CSB_ACT_NONE; p.head_relu_from = -1; p.bias = h->zero_bias;   // d(block output): no activation after the residual add
+    if ((rc = cnn_gemm<tc::EPI_BIAS_ACT>(h, co, true, h->mdze.k128, &h->mG[g].k128, nullptr, p, B, st))) return rc;
+  }
+  // ---- residual blocks, last to first.  G[g] holds dL/d(block output).
+  for (int i = D - 1; i >= 0; --i) {
+    const ConvLayerInfo &c1 = h->layer[3 * i], &c2 = h->layer[3 * i + 1], &cr = h->layer[3 * i + 2];
+    const BufMaps& xin = i > 0 ? h->mob[i - 1] : h->mx0;
+    // dz2 = d_out * relu'(h2)
+    simt::act_mask_bf16_kernel<<<grid_for(R * h->width_p / 8, 256, h->sm_count), 256, 0, st>>>(h->G[g], h->h2[i], h->Z2, R * h->width_p / 8, c2.act, 0.f);
+    CSB_CUDA_CHECK(cudaGetLastError());
+    h->launches++;
+    if ((rc = cnn_wgrad(h, cr, xin, h->mG[g], B, tab, max_len, st))) return rc;       // residual 1x1: dW = xin^T d_out
+    if ((rc = cnn_wgrad(h, c2, h->mh1[i], h->mZ2, B, tab, max_len, st))) return rc;
+    {
+      tc::GemmParams p = {};
+      p.act = c1.act; p.head_relu_from = -1;                  // dz1 = conv^T(dz2; W2) * relu'(h1)
+      if ((rc = cnn_gemm<tc::EPI_DGRAD>(h, c2, true, h->mZ2.k128, &h->mZ1.k128, &h->mh1[i].k128, p, B, st))) return rc;
+    }
+    if ((rc = cnn_wgrad(h, c1, xin, h->mZ1, B, tab, max_len, st))) return rc;
+    if (i > 0) {
+      tc::GemmParams p = {};
+      p.act = CSB_ACT_NONE; p.head_relu_from = -1; p.bias = h->zero_bias;
+      // d(x_in) = conv^T(dz1; W1) + conv1x1^T(d_out; Wr)
+      if ((rc = cnn_gemm<tc::EPI_BIAS_ACT>(h, c1, true, h->mZ1.k128, &h->mT.k128, nullptr, p, B, st))) return rc;
+      if ((rc = cnn_gemm<tc::EPI_BIAS_ADD>(h, cr, true, h->mG[g].k128, &h->mG[g ^ 1].k128, &h->mT.k128, p, B, st))) return rc;
+      g ^= 1;
+    }
+    if (tab.n + 8 > (int)(sizeof(tab.seg) / sizeof(tab.seg[0]))) { if ((rc = flush_reduce())) return rc; }
+  }
+  return flush_reduce();
+}
+
+int csb_cnn_apply_opt(csb_cnn* h, int rule, float lr, float beta1, float beta2, float eps, float wd, void* stream) {
+  CSB_REQUIRE(h, CSB_EINVAL, "null handle");
+  CSB_REQUIRE(rule >= CSB_OPT_ADAM_KERAS && rule <= CSB_OPT_RMSPROP, CSB_EINVAL, "unknown optimizer rule %d", rule);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  h->step++;
+  simt::OptParams o;
+  o.rule = rule; o.lr = lr; o.beta1 = beta1; o.beta2 = beta2; o.eps = eps; o.wd = wd;
+  o.bc1 = (float)(1.0 - pow((double)beta1, (double)h->step));
+  o.bc2 = (float)(1.0 - pow((double)beta2, (double)h->step));
+  o.radam_r = -1.f;
+  if (rule == CSB_OPT_RADAM) {
+    const double t = (double)h->step, b2t = pow((double)beta2, t);
+    const double sma_inf = 2.0 / (1.0 - (double)beta2) - 1.0, sma_t = sma_inf - 2.0 * t * b2t / (1.0 - b2t);
+    if (sma_t >= 5.0) o.radam_r = (float)sqrt((sma_t - 4.0) / (sma_inf - 4.0) * (sma_t - 2.0) / (sma_inf - 2.0) * sma_inf / sma_t);
+  }
+  simt::opt_kernel<<<grid_for((int64_t)h->P_pad / 4, 256, h->sm_count), 256, 0, st>>>(h->params, h->grads, h->m, h->v, (int64_t)h->P_pad, o);
+  CSB_CUDA_CHECK(cudaGetLastError());
+  h->launches++;
+  return cnn_repack(h, st);
+}
+
+}  // extern "C"

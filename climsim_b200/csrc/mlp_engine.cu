@@ -1062,3 +1062,5 @@ int csb_test_gemm_nt(const uint16_t* A, const uint16_t* B, float* C, float* cols
 }
 
 }  // extern "C"
+
+#include "cnn_engine.cuh"

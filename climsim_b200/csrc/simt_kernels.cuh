@@ -518,5 +518,75 @@ __global__ void cnn_reshape_out_kernel(const float* __restrict__ p, float* __res
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// CNN helpers (channels-last, halo-padded rows: sample b occupies rows b*(L+2) .. b*(L+2)+L+1, first and last are zero)
+// ---------------------------------------------------------------------------------------------------------------
+// x (B, L, C) fp32 -> bf16 [B*(L+2), Cp]
+__global__ void __launch_bounds__(256)
+cnn_pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t B, int L, int C, int Cp) {
+  const int64_t total = B * (L + 2) * Cp;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cp);
+    const int64_t r = i / Cp;
+    const int l = (int)(r % (L + 2)) - 1;
+    const int64_t b = r / (L + 2);
+    float v = 0.f;
+    if (c < C && l >= 0 && l < L) v = x[(b * L + l) * C + c];
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+// dz = g * act'(a) element-wise (bf16, 8 elements per thread)
+__global__ void __launch_bounds__(256)
+act_mask_bf16_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ dz,
+                     int64_t n8, int act, float alpha) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 gv = reinterpret_cast<const uint4*>(g)[i], av = reinterpret_cast<const uint4*>(a)[i];
+    const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w}, aw[4] = {av.x, av.y, av.z, av.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      o[j] = pack_bf16x2(bf16_lo(gw[j]) * act_bwd_from_out(act, alpha, bf16_lo(aw[j])), bf16_hi(gw[j]) * act_bwd_from_out(act, alpha, bf16_hi(aw[j])));
+    reinterpret_cast<uint4*>(dz)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+// conv weight repack from the fp32 master W [taps][Cinp][Coutp]:
+//   wt16 [Coutp][taps*Cinp]            (B operand of the forward GEMM:  k = t*Cinp + ci)
+//   wd16 [Cinp][taps*Coutp], flipped   (B operand of the data-gradient GEMM: k = t'*Coutp + co with t' = taps-1-t)
+struct ConvRepack { const float* w; __nv_bfloat16* wt16; __nv_bfloat16* wd16; int taps, Cinp, Coutp; };
+struct ConvRepackTable { int n; ConvRepack l[48]; };
+__global__ void __launch_bounds__(256) conv_repack_kernel(const ConvRepackTable tab) {
+  const ConvRepack L = tab.l[blockIdx.y];
+  const int64_t total = (int64_t)L.taps * L.Cinp * L.Coutp;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int co = (int)(i % L.Coutp);
+    const int ci = (int)((i / L.Coutp) % L.Cinp);
+    const int t = (int)(i / ((int64_t)L.Coutp * L.Cinp));
+    const __nv_bfloat16 v = __float2bfloat16_rn(L.w[i]);
+    L.wt16[(size_t)co * (L.taps * L.Cinp) + (size_t)t * L.Cinp + ci] = v;
+    L.wd16[(size_t)ci * (L.taps * L.Coutp) + (size_t)(L.taps - 1 - t) * L.Coutp + co] = v;
+  }
+}
+// flat user blob <-> padded conv parameters: W [taps][Cin][Cout] <-> [taps][Cinp][Coutp], b [Cout] <-> [Coutp]
+struct ConvPad { int taps, Cin, Cout, Cinp, Coutp; size_t w_off, b_off, w_off_user, b_off_user; };
+struct ConvPadTable { int n; ConvPad l[48]; };
+__global__ void __launch_bounds__(256) conv_pad_copy_kernel(float* __restrict__ padded, float* __restrict__ user, int dir, const ConvPadTable tab) {
+  const ConvPad L = tab.l[blockIdx.y];
+  const int64_t nw = (int64_t)L.taps * L.Cin * L.Cout, total = nw + L.Cout;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    float *pp, *pu;
+    if (i < nw) {
+      const int co = (int)(i % L.Cout);
+      const int ci = (int)((i / L.Cout) % L.Cin);
+      const int t = (int)(i / ((int64_t)L.Cout * L.Cin));
+      pp = padded + L.w_off + ((size_t)t * L.Cinp + ci) * L.Coutp + co;
+      pu = user + L.w_off_user + i;
+    } else {
+      pp = padded + L.b_off + (i - nw);
+      pu = user + L.b_off_user + (i - nw);
+    }
+    if (dir == 0) *pp = *pu; else *pu = *pp;
+  }
+}
+
 }  // namespace simt
 }  // namespace csb

@@ -32,12 +32,19 @@ enum Epi : int {
   EPI_HEAD_LOSS = 1,  // p = head(acc + bias); loss, dZ(bf16), optional p  forward output layer fused with the loss
   EPI_DGRAD = 2,      // out(bf16) = acc * act'(saved activation)          backward data gradient
   EPI_F32 = 3,        // out(fp32) = acc                                   (self-test, fp32 consumers)
-  EPI_HEAD_OUT = 4    // p = head(acc + bias) -> fp32 (optionally / out_scale)   inference output layer
+  EPI_HEAD_OUT = 4,   // p = head(acc + bias) -> fp32 (optionally / out_scale)   inference output layer
+  EPI_BIAS_ADD = 5    // out(bf16) = acc + bias + saved tile                 residual add / gradient accumulation
 };
 
 struct GemmParams {
   int M, N, K;                 // problem (N, K multiples of 64; M arbitrary)
   int b_box_rows;              // rows of the B-operand TMA box (== min(N, BN)): sets the expected transaction bytes
+  // Conv1D('same') as a row-shifted GEMM over a halo-padded channels-last layout [B*(L+2), C]: contraction block kb
+  // belongs to tap t = kb / kb_per_tap and reads the A rows shifted by (t - tap_center); rows whose index modulo
+  // halo_period is 0 or halo_period-1 are the zero halo rows of each sample and are written as zeros.
+  int kb_per_tap;              // 0: plain GEMM
+  int tap_center;
+  int halo_period;             // 0: no halo rows
   int act;                     // CSB_ACT_* for EPI_BIAS_ACT / EPI_DGRAD (activation of the layer whose output is stored / was saved)
   float alpha;
   int head_relu_from;          // EPI_HEAD_*: columns >= this get ReLU (-1: none); otherwise `act` applies
@@ -323,7 +330,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint8_t* cst
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-  const bool row_ok = grow < p.M;
+  bool row_ok = grow < p.M;
+  int64_t yrow = grow;                               // row of the user's target / prediction arrays (no halo rows there)
+  if (p.halo_period > 0) {
+    const int rr = grow % p.halo_period;
+    if (rr == 0 || rr == p.halo_period - 1) row_ok = false;
+    yrow = (int64_t)(grow / p.halo_period) * (p.halo_period - 2) + rr - 1;
+  }
+  const bool zero_row = p.halo_period > 0 && !row_ok;   // halo rows (and rows past M) of a conv layout are stored as zeros
 
   if constexpr (EPI == EPI_F32) {
     if (row_ok) store_f32x32(reinterpret_cast<float*>(p.out) + (size_t)grow * p.ld_out + gcol, v);
@@ -333,12 +347,27 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint8_t* cst
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] += b[j];
     act_fwd_vec(p.act, p.alpha, v);
+    if (zero_row) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    }
     cst_store32(cst, tile_row, tile_col, v);
   } else if constexpr (EPI == EPI_DGRAD) {
     float a[32];
     cst_load32(cst, tile_row, tile_col, a);        // saved activation tile, TMA-loaded by the producer warp
     act_bwd_vec(p.act, p.alpha, v, a);
+    if (zero_row) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    }
     cst_store32(cst, tile_row, tile_col, v);       // in place
+  } else if constexpr (EPI == EPI_BIAS_ADD) {
+    float a[32], b[32];
+    cst_load32(cst, tile_row, tile_col, a);        // tile to add (residual branch / partial gradient), TMA-loaded
+    load_smem_f32x32(sbias + tile_col, b);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = zero_row ? 0.f : v[j] + b[j] + a[j];
+    cst_store32(cst, tile_row, tile_col, v);
   } else {
     // head: p = (col >= head_relu_from) ? relu(z) : act(z)
     float b[32], dact[32];
@@ -359,15 +388,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint8_t* cst
       }
       if (row_ok) {
         if (gcol + 32 <= p.out_dim) {
-          store_f32x32(p.pred + (size_t)grow * p.ld_pred + gcol, v);
+          store_f32x32(p.pred + (size_t)yrow * p.ld_pred + gcol, v);
         } else {
           for (int j = 0; j < 32; ++j)
-            if (gcol + j < p.out_dim) p.pred[(size_t)grow * p.ld_pred + gcol + j] = v[j];
+            if (gcol + j < p.out_dim) p.pred[(size_t)yrow * p.ld_pred + gcol + j] = v[j];
         }
       }
     } else {  // EPI_HEAD_LOSS: finish 8 columns at a time to keep the live register set small
-      if (row_ok && p.pred != nullptr && gcol + 32 <= p.out_dim) store_f32x32(p.pred + (size_t)grow * p.ld_pred + gcol, v);
-      const float* yrow = p.y + (size_t)grow * p.ld_y + gcol;
+      if (row_ok && p.pred != nullptr && gcol + 32 <= p.out_dim) store_f32x32(p.pred + (size_t)yrow * p.ld_pred + gcol, v);
+      const float* yptr = p.y + (size_t)yrow * p.ld_y + gcol;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         float yv[8], w[8];
@@ -377,13 +406,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint8_t* cst
 #pragma unroll
         for (int j = 0; j < 8; ++j) yv[j] = 0.f;
         if (row_ok) {
-          if (gcol + 8 * g + 8 <= p.out_dim) {
-            const float4 y0 = __ldg(reinterpret_cast<const float4*>(yrow + 8 * g));
-            const float4 y1 = __ldg(reinterpret_cast<const float4*>(yrow + 8 * g + 4));
+          if (gcol + 8 * g + 8 <= p.out_dim && (p.ld_y & 3) == 0) {
+            const float4 y0 = __ldg(reinterpret_cast<const float4*>(yptr + 8 * g));
+            const float4 y1 = __ldg(reinterpret_cast<const float4*>(yptr + 8 * g + 4));
             yv[0] = y0.x; yv[1] = y0.y; yv[2] = y0.z; yv[3] = y0.w; yv[4] = y1.x; yv[5] = y1.y; yv[6] = y1.z; yv[7] = y1.w;
           } else {
             for (int j = 0; j < 8; ++j)
-              if (gcol + 8 * g + j < p.out_dim) yv[j] = __ldg(yrow + 8 * g + j);
+              if (gcol + 8 * g + j < p.out_dim) yv[j] = __ldg(yptr + 8 * g + j);
           }
         }
 #pragma unroll
@@ -398,6 +427,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint8_t* cst
             dact[c] *= w[j] * p.grad_scale * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
           }
         }
+      }
+      if (!row_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dact[j] = 0.f;
       }
       cst_store32(cst, tile_row, tile_col, dact);
     }
@@ -439,9 +472,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const bool is_leader = cta_rank == 0;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static_assert(2 * BN <= 512, "two accumulator buffers must fit the 512 TMEM columns");
-  constexpr bool CST_OUT = (EPI == EPI_BIAS_ACT || EPI == EPI_DGRAD || EPI == EPI_HEAD_LOSS);
-  constexpr bool CST_IN = (EPI == EPI_DGRAD);
-  constexpr bool USE_BIAS = (EPI == EPI_BIAS_ACT || EPI == EPI_HEAD_LOSS || EPI == EPI_HEAD_OUT);
+  constexpr bool CST_OUT = (EPI == EPI_BIAS_ACT || EPI == EPI_DGRAD || EPI == EPI_HEAD_LOSS || EPI == EPI_BIAS_ADD);
+  constexpr bool CST_IN = (EPI == EPI_DGRAD || EPI == EPI_BIAS_ADD);
+  constexpr bool USE_BIAS = (EPI == EPI_BIAS_ACT || EPI == EPI_HEAD_LOSS || EPI == EPI_HEAD_OUT || EPI == EPI_BIAS_ADD);
   constexpr int SLAB_BYTES = BM * 128;   // one 64-column slab of the staging tile
   constexpr int HALF = BN / 2, NCH = HALF / 32;
 
@@ -498,14 +531,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t sa = smem_base + s * L::STAGE_BYTES;
+          const int tap = p.kb_per_tap ? kb / p.kb_per_tap : 0;
+          const int ka = (kb - tap * p.kb_per_tap) * BK;          // column block inside the (un-replicated) A matrix
+          const int tap_shift = p.kb_per_tap ? tap - p.tap_center : 0;   // may be -1 at the top: TMA zero-fills out-of-range rows
           if constexpr (CG == 2) {
             // one expect_tx on the leader's barrier covers the four loads of the pair
             if (is_leader) mbar_expect_tx(full_bar(s), (uint32_t)(2 * (L::A_BYTES + p.b_box_rows * BK * 2)));
-            tma_load_2d_2sm(sa, &tmap_a, full_bar(s), kb * BK, m0);
+            tma_load_2d_2sm(sa, &tmap_a, full_bar(s), ka, m0 + tap_shift);
             tma_load_2d_2sm(sa + L::A_BYTES, &tmap_b, full_bar(s), kb * BK, nb0);
           } else {
             mbar_expect_tx(full_bar(s), (uint32_t)(L::A_BYTES + p.b_box_rows * BK * 2));
-            tma_load_2d(sa, &tmap_a, full_bar(s), kb * BK, m0);
+            tma_load_2d(sa, &tmap_a, full_bar(s), ka, m0 + tap_shift);
             tma_load_2d(sa + L::A_BYTES, &tmap_b, full_bar(s), kb * BK, nb0);
           }
           if (++s == STAGES) { s = 0; ph ^= 1u; }
@@ -640,6 +676,7 @@ struct NtParams {
   size_t split_stride;
   float* colsum_out;       // optional: column sums of B (bias gradient) partials: colsum_out + split * colsum_stride + n
   size_t colsum_stride;
+  int a_row_offset;        // Conv1D weight gradient of tap t: A rows shifted by (t - center); out-of-range rows read as zero
 };
 
 template <int BN, int STAGES>
@@ -702,7 +739,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mbar_wait(empty_bar(s), ph ^ 1u);
         mbar_expect_tx(full_bar(s), (uint32_t)((a_chunks + b_chunks) * CHUNK_BYTES));
         const uint32_t sa = smem_base + s * L::STAGE_BYTES;
-        for (int c = 0; c < a_chunks; ++c) tma_load_2d(sa + c * CHUNK_BYTES, &tmap_a, full_bar(s), m0 + 64 * c, rb * BK);
+        for (int c = 0; c < a_chunks; ++c) tma_load_2d(sa + c * CHUNK_BYTES, &tmap_a, full_bar(s), m0 + 64 * c, rb * BK + p.a_row_offset);
         for (int c = 0; c < b_chunks; ++c) tma_load_2d(sa + L::A_BYTES + c * CHUNK_BYTES, &tmap_b, full_bar(s), n0 + 64 * c, rb * BK);
         if (++s == STAGES) { s = 0; ph ^= 1u; }
       }

@@ -248,3 +248,102 @@ class MLPEngine:
     @property
     def launch_count(self) -> int:
         return int(self.lib.csb_mlp_launch_count(self._h))
+
+
+class CNNEngine:
+    """The ResNet-1D column emulator (baseline_models/CNN/training/hpo_train.py:131-200) bound to the csb_cnn_* C ABI.
+    Tensors are channels-last: x (B, 60, 6), y / predictions (B, 60, 10)."""
+
+    def __init__(self, depth: int = 12, width: int = 406, kernel: int = 3, in_ch: int = 6, out_ch: int = 10, out_lin: int = 2,
+                 levels: int = 60, act: str = "relu", pre_out_act: str = "elu", loss: str = "mae", max_batch: int = 4096):
+        self.lib = _lib.load()
+        cfg = _lib.CnnCfg(depth, width, kernel, in_ch, out_ch, out_lin, levels, _lib.ACT[act], _lib.ACT[pre_out_act],
+                          _lib.DTYPE["bf16"], _lib.LOSS[loss], max_batch)
+        self._h = C.c_void_p()
+        _lib.check(self.lib.csb_cnn_create(C.byref(cfg), C.byref(self._h)), "csb_cnn_create")
+        self.depth, self.width, self.kernel, self.in_ch, self.out_ch, self.out_lin, self.levels = depth, width, kernel, in_ch, out_ch, out_lin, levels
+        self.n_params = int(self.lib.csb_cnn_param_count(self._h))
+        self._loss_buf: Optional[torch.Tensor] = None
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.csb_cnn_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def keras_to_flat(weights: Sequence[np.ndarray]) -> np.ndarray:
+        """Keras ``get_weights()`` -> flat blob (the two Dense heads concatenated column-wise)."""
+        ws = [np.asarray(w, dtype=np.float32) for w in weights]
+        w_lin, b_lin, w_relu, b_relu = ws[-4:]
+        ws = ws[:-4] + [np.concatenate([w_lin, w_relu], axis=1), np.concatenate([b_lin, b_relu])]
+        return np.concatenate([w.reshape(-1) for w in ws])
+
+    def shapes(self) -> List[Tuple[int, ...]]:
+        out, c = [], self.in_ch
+        for _ in range(self.depth):
+            out += [(self.kernel, c, self.width), (self.width,), (self.kernel, self.width, self.width), (self.width,), (1, c, self.width), (self.width,)]
+            c = self.width
+        return out + [(1, c, self.out_ch), (self.out_ch,), (self.out_ch, self.out_ch), (self.out_ch,)]
+
+    def split_flat(self, flat: np.ndarray) -> List[np.ndarray]:
+        out, off = [], 0
+        for shp in self.shapes():
+            n = int(np.prod(shp))
+            out.append(flat[off:off + n].reshape(shp)); off += n
+        return out
+
+    def set_params_flat(self, flat: np.ndarray) -> None:
+        flat = np.ascontiguousarray(flat, dtype=np.float32)
+        assert flat.size == self.n_params, (flat.size, self.n_params)
+        _lib.check(self.lib.csb_cnn_set_params(self._h, flat.ctypes.data), "csb_cnn_set_params")
+
+    def get_params_flat(self) -> np.ndarray:
+        out = np.empty(self.n_params, dtype=np.float32)
+        _lib.check(self.lib.csb_cnn_get_params(self._h, out.ctypes.data), "csb_cnn_get_params")
+        return out
+
+    def get_grads_flat(self) -> np.ndarray:
+        out = np.empty(self.n_params, dtype=np.float32)
+        _lib.check(self.lib.csb_cnn_get_grads(self._h, out.ctypes.data), "csb_cnn_get_grads")
+        return out
+
+    def set_loss_weights(self, w) -> None:
+        w = np.ascontiguousarray(w, dtype=np.float32)
+        assert w.size == self.out_ch
+        _lib.check(self.lib.csb_cnn_set_loss_weights(self._h, w.ctypes.data), "csb_cnn_set_loss_weights")
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        x = _f32_cuda(x, "x")
+        y = torch.empty(x.shape[0], self.levels, self.out_ch, dtype=torch.float32, device=x.device)
+        _lib.check(self.lib.csb_cnn_forward(self._h, x.data_ptr(), y.data_ptr(), x.shape[0], _lib.current_stream_ptr()), "csb_cnn_forward")
+        return y
+
+    def train_step(self, x: torch.Tensor, y: torch.Tensor, grad_scale: float = 0.0) -> torch.Tensor:
+        x, y = _f32_cuda(x, "x"), _f32_cuda(y, "y")
+        if self._loss_buf is None:
+            self._loss_buf = torch.zeros(1, dtype=torch.float32, device=x.device)
+        _lib.check(self.lib.csb_cnn_train_step(self._h, x.data_ptr(), y.data_ptr(), x.shape[0], grad_scale, self._loss_buf.data_ptr(),
+                                               _lib.current_stream_ptr()), "csb_cnn_train_step")
+        return self._loss_buf
+
+    def apply_opt(self, rule: str = "adam_keras", lr: float = 1e-4, beta1: float = 0.9, beta2: float = 0.999, eps: Optional[float] = None,
+                  weight_decay: float = 0.0) -> None:
+        if eps is None:
+            eps = 1e-8 if rule == "adam_torch" else 1e-7
+        _lib.check(self.lib.csb_cnn_apply_opt(self._h, _lib.OPT[rule], lr, beta1, beta2, eps, weight_decay, _lib.current_stream_ptr()),
+                   "csb_cnn_apply_opt")
+
+    def grad_buffer(self) -> torch.Tensor:
+        ptr, n = C.c_void_p(), C.c_size_t()
+        _lib.check(self.lib.csb_cnn_grad_buffer(self._h, C.byref(ptr), C.byref(n)), "csb_cnn_grad_buffer")
+        return torch.as_tensor(_DevPtr(ptr.value, n.value), device="cuda")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.csb_cnn_launch_count(self._h))

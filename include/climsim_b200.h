@@ -159,6 +159,44 @@ int  csb_mlp_profile_read(csb_mlp* h, double* ms_by_kind, int64_t* launches_by_k
 int  csb_profile_kind_count(void);
 const char* csb_profile_kind_name(int kind);
 
+/* ---- CNN family ----------------------------------------------------------------------------------------- */
+/* ResNet-1D of baseline_models/CNN/training/hpo_train.py:131-200: depth x { Conv1D(width,k,'same') -> act -> Conv1D(width,k,
+ * 'same') -> act -> + Conv1D(width,1)(block input) } -> Conv1D(out_ch,1,pre_out_act) -> per-level Dense(out_lin, linear) ||
+ * Dense(out_ch-out_lin, relu).  Tensors are channels-last fp32: x (B,levels,in_ch), y / predictions (B,levels,out_ch)
+ * (what data_utils.reshape_input_for_cnn / reshape_target_for_cnn produce, data_utils.py:1693-1738).  Dropout is inference
+ * mode (p = 0).  Flat parameter blob = Keras get_weights() order: per block Wc1 (k,Cin,Cout), bc1, Wc2, bc2, Wres (1,Cin,Cout),
+ * bres; then Wout (1,width,out_ch), bout, then the two Dense heads fused column-wise: W (out_ch,out_ch) = [W_lin | W_relu], b.
+ * Loss = batch mean of sum_{level,channel} w_c * e (e = squared or absolute error); the default w reproduces the reference's
+ * mse_adjusted / mae_adjusted (hpo_train.py:114-121). */
+typedef struct csb_cnn_cfg {
+  int32_t depth;        /* 12 */
+  int32_t width;        /* 406 */
+  int32_t kernel;       /* 3 */
+  int32_t in_ch;        /* 6 */
+  int32_t out_ch;       /* 10 */
+  int32_t out_lin;      /* 2 */
+  int32_t levels;       /* 60 */
+  int32_t act;          /* CSB_ACT_RELU */
+  int32_t pre_out_act;  /* CSB_ACT_ELU */
+  int32_t dtype;        /* CSB_BF16 (the only mode implemented for the CNN) */
+  int32_t loss;         /* CSB_LOSS_MAE (final reference configuration) | CSB_LOSS_MSE */
+  int64_t max_batch;
+} csb_cnn_cfg;
+typedef struct csb_cnn csb_cnn;
+
+int  csb_cnn_create(const csb_cnn_cfg* cfg, csb_cnn** out);       /* CNNHyperModel.build, hpo_train.py:124-236 */
+int  csb_cnn_destroy(csb_cnn* h);
+size_t csb_cnn_param_count(const csb_cnn* h);                     /* 13 215 420 for the reference configuration */
+int  csb_cnn_set_params(csb_cnn* h, const float* params_host);
+int  csb_cnn_get_params(csb_cnn* h, float* params_host);
+int  csb_cnn_get_grads(csb_cnn* h, float* grads_host);
+int  csb_cnn_set_loss_weights(csb_cnn* h, const float* w_host);   /* out_ch per-channel weights */
+int  csb_cnn_forward(csb_cnn* h, const float* x, float* y_pred, int64_t B, void* stream);                  /* model.predict */
+int  csb_cnn_train_step(csb_cnn* h, const float* x, const float* y, int64_t B, float grad_scale, float* loss_out, void* stream);
+int  csb_cnn_grad_buffer(csb_cnn* h, float** ptr, size_t* n);
+int  csb_cnn_apply_opt(csb_cnn* h, int rule, float lr, float beta1, float beta2, float eps, float wd, void* stream);
+int64_t csb_cnn_launch_count(const csb_cnn* h);
+
 /* ---- data_utils device helpers -------------------------------------------------------------------------- */
 /* (x - sub)/div, inf/nan -> 0 on (N,F) fp32; data_utils.py:806-809,894-897. */
 int  csb_normalize(const float* x_raw, const float* sub, const float* div, float* x_out, int64_t N, int32_t F, void* stream);
