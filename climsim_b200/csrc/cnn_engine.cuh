@@ -153,7 +153,7 @@ static int cnn_wgrad(csb_cnn* h, const ConvLayerInfo& li, const BufMaps& in, con
     splits = eff;
   }
   tab.seg[tab.n++] = {h->ws + li.ws_w_off, (size_t)li.taps * tap_elems, h->grads + li.w_off, (int64_t)(li.taps * tap_elems), splits};
-  tab.seg[tab.n++] = {h->ws + li.ws_b_off, (size_t)li.Coutp, h->grads + li.b_off, (int64_t)li.Coutp, splits};
+  tab.seg[tab.n++] = {h->ws + li.ws_b_off, (size_t)li.Coutp, h->grads + li.b_off, (int64_t)li.Coutp, splits * (int)ceil_div(li.Cinp, 128)};
   max_len = std::max<int64_t>(max_len, (int64_t)(li.taps * tap_elems));
   return CSB_OK;
 }
@@ -220,7 +220,7 @@ int csb_cnn_create(const csb_cnn_cfg* cfg, csb_cnn** out) {
     const int tiles = (int)(ceil_div(li.Cinp, 128) * ceil_div(li.Coutp, tn_block_n(li.Coutp)));
     li.max_splits = std::max(1, std::min(64, sm / tiles));
     li.ws_w_off = ws_off; ws_off += (size_t)li.max_splits * taps * li.Cinp * li.Coutp;
-    li.ws_b_off = ws_off; ws_off += (size_t)li.max_splits * li.Coutp;
+    li.ws_b_off = ws_off; ws_off += (size_t)li.max_splits * ceil_div(li.Cinp, 128) * li.Coutp;
   };
   int c = cfg->in_ch;
   for (int i = 0; i < h->depth; ++i) {

@@ -381,7 +381,7 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
     li.nt_block_n = tn_block_n(li.Np);
     const int tiles = (int)(ceil_div(li.Kp, 128) * ceil_div(li.Np, li.nt_block_n));
     li.max_w_splits = h->bf16 ? std::max(1, std::min(64, sm / tiles)) : 1;
-    li.b_splits = h->bf16 ? li.max_w_splits : 32;
+    li.b_splits = h->bf16 ? li.max_w_splits * (int)ceil_div(li.Kp, 128) : 32;
     li.ws_w_off = ws_off; ws_off += (size_t)li.max_w_splits * li.Kp * li.Np;
     li.ws_b_off = ws_off; ws_off += (size_t)li.b_splits * li.Np;
     li.ws_g_off = ws_off; if (li.ln) ws_off += (size_t)32 * 2 * li.Np;
@@ -778,7 +778,7 @@ static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st)
     max_len = std::max<int64_t>(max_len, (int64_t)li.Kp * li.Np);
     // ---- bias gradient db_l = column sums of dZ_l (CSB_BF16: computed inside the weight-gradient kernel above)
     if (h->bf16) {
-      tab.seg[tab.n++] = {h->ws + li.ws_b_off, (size_t)li.Np, h->grads + li.b_off, (int64_t)li.Np, splits};
+      tab.seg[tab.n++] = {h->ws + li.ws_b_off, (size_t)li.Np, h->grads + li.b_off, (int64_t)li.Np, splits * (int)ceil_div(li.Kp, 128)};
     } else {
       const int S = (int)std::max<int64_t>(1, std::min<int64_t>(li.b_splits, ceil_div(B, 256)));
       dim3 grid((unsigned)(li.Np / 64), (unsigned)S);

@@ -248,7 +248,7 @@ __device__ __forceinline__ void act_fwd_vec(int act, float alpha, float (&v)[32]
       break;
     case CSB_ACT_LEAKYRELU:
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : alpha * v[j];
+      for (int j = 0; j < 32; ++j) v[j] = (alpha >= 0.f && alpha <= 1.f) ? fmaxf(v[j], alpha * v[j]) : (v[j] > 0.f ? v[j] : alpha * v[j]);
       break;
     case CSB_ACT_ELU:
 #pragma unroll
@@ -593,6 +593,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ===================== epilogue: warp w -> TMEM lanes 32*(w&3).., columns [HALF*(w>>2), HALF*(w>>2)+HALF) ==========
     const int q = warp & 3, hf = warp >> 2;
     const int tile_row = q * 32 + lane;
+    float bias_next = 0.f;
     int t = 0;
     for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++t) {
       const int mb = (tile / num_n_blocks) * CG + (int)cta_rank;
@@ -607,12 +608,19 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       }
       if constexpr (USE_BIAS) {
-        for (int i = threadIdx.x; i < BN; i += TN_EPI_THREADS) sbias[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+        static_assert(BN <= TN_EPI_THREADS, "one bias element per epilogue thread");
+        if (t == 0) bias_next = (threadIdx.x < BN && n0 + (int)threadIdx.x < p.N) ? __ldg(p.bias + n0 + threadIdx.x) : 0.f;
+        if (threadIdx.x < BN) sbias[threadIdx.x] = bias_next;         // loaded during the previous tile: no latency here
       }
       mbar_wait(tfull_bar(acc), (uint32_t)(t >> 1) & 1u);
       tc_fence_after();
       if constexpr (CST_IN) mbar_wait(cst_full, (uint32_t)t & 1u);
       named_bar_sync(1, TN_EPI_THREADS);                      // bias staged; staging tile free; everyone past the waits
+      if constexpr (USE_BIAS) {                               // prefetch the next tile's bias element
+        const int tile_next = tile + tile_stride;
+        const int n0_next = (tile_next % num_n_blocks) * BN;
+        bias_next = (tile_next < num_tiles && threadIdx.x < BN && n0_next + (int)threadIdx.x < p.N) ? __ldg(p.bias + n0_next + threadIdx.x) : 0.f;
+      }
       float loss_acc = 0.f;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + hf * HALF);
       uint32_t raw[2][32];
@@ -713,7 +721,10 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int rb_begin = blockIdx.y * p.rb_per_split;
   const int rb_end = min(num_rb, rb_begin + p.rb_per_split);
   const int nrb = max(0, rb_end - rb_begin);
-  const bool do_colsum = (p.colsum_out != nullptr) && (m0 == 0);        // CTA-uniform
+  // bias gradient: every m-block takes the row blocks i with i % num_m_blocks == its index, so no CTA is a straggler;
+  // partial index = split * num_m_blocks + m-block
+  const int num_m_blocks = (p.M + BM - 1) / BM, m_blk = (int)(blockIdx.x / num_n_blocks);
+  const bool do_colsum = p.colsum_out != nullptr;                       // kernel-uniform
   const int colsum_warps = do_colsum ? min(4, b_chunks) : 0;            // warp w sums the columns of chunk w
 
   if (warp == 4 && lane == 0) {
@@ -776,6 +787,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int i = 0; i < nrb; ++i) {
         mbar_wait(full_bar(s), ph);
         const uint8_t* chunk = smem_gen + s * L::STAGE_BYTES + L::A_BYTES + warp * CHUNK_BYTES;
+        if (i % num_m_blocks == m_blk)
 #pragma unroll
         for (int it = 0; it < BK / 4; ++it) {         // rows past R were zero-filled by TMA
           const int r = 4 * it + rs;
@@ -793,7 +805,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         acc8[j] += __shfl_xor_sync(0xffffffffu, acc8[j], 16);
       }
       if (rs == 0) {
-        float* dst = p.colsum_out + (size_t)blockIdx.y * p.colsum_stride + n0 + 64 * warp + 8 * lp;
+        float* dst = p.colsum_out + ((size_t)blockIdx.y * num_m_blocks + m_blk) * p.colsum_stride + n0 + 64 * warp + 8 * lp;
         *reinterpret_cast<float4*>(dst) = make_float4(acc8[0], acc8[1], acc8[2], acc8[3]);
         *reinterpret_cast<float4*>(dst + 4) = make_float4(acc8[4], acc8[5], acc8[6], acc8[7]);
       }

@@ -213,7 +213,7 @@ int  csb_test_gemm_tn(const uint16_t* A, const uint16_t* Bt, float* C, int M, in
 int  csb_test_linear_fwd(const uint16_t* A, const uint16_t* Wt, const float* bias, uint16_t* out, int M, int N, int K, int act,
                          float alpha, int pairs, void* stream);
 /* C[s][M,N] (fp32 partials, s < splits) = A[Kr,M]^T * B[Kr,N]  (both operands MN-major bf16): the weight-gradient
- * contraction over rows; colsum (optional, [splits][N]) receives the per-split column sums of B (bias gradient). */
+ * contraction over rows; colsum (optional, [splits * ceil(M/128)][N]) receives partial column sums of B (bias gradient). */
 int  csb_test_gemm_nt(const uint16_t* A, const uint16_t* B, float* C, float* colsum, int M, int N, int Kr, int splits, void* stream);
 
 /* ---- misc ---------------------------------------------------------------------------------------------- */

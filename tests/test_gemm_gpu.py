@@ -64,7 +64,7 @@ def test_gemm_nt(M, N, R, splits):
     A = _bf16_operand(R, M, 3)
     B = _bf16_operand(R, N, 4)
     Cout = torch.full((splits, M, N), float("nan"), device="cuda")
-    colsum = torch.full((splits, N), float("nan"), device="cuda")
+    colsum = torch.full((splits * ((M + 127) // 128), N), float("nan"), device="cuda")     # one partial per (split, m-block)
     L.check(lib.csb_test_gemm_nt(A.data_ptr(), B.data_ptr(), Cout.data_ptr(), colsum.data_ptr(), M, N, R, splits, None), "csb_test_gemm_nt")
     torch.cuda.synchronize()
     got = Cout.sum(dim=0)
