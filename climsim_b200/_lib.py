@@ -90,6 +90,7 @@ SIGNATURES = {
     "csb_reshape_target_from_cnn": (C.c_int, [_VP, _VP, C.c_int64, _VP]),
     "csb_test_gemm_tn": (C.c_int, [_VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP]),
     "csb_test_linear_fwd": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _VP]),
+    "csb_test_set_debug": (None, [C.c_int]),
     "csb_test_gemm_nt": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP]),
 }
 

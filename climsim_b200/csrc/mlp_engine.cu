@@ -211,6 +211,12 @@ struct csb_mlp {
   CUtensorMap tm_z[CSB_MAX_LAYERS];         // LayerNorm layers: pre-norm z buffer (TMA-store target of the forward GEMM)
 
   int64_t step = 0, launches = 0;
+  struct GraphEntry { const float* x; const float* y; int64_t B; float gs; uint32_t flags; float* loss_out; int64_t maps_B;
+                      cudaGraphExec_t exec; int64_t n_launches; uint64_t use; };
+  std::vector<GraphEntry> graphs;           // cached CUDA graphs of the training step (LRU, 8 entries)
+  uint64_t graph_clock = 0;
+  bool graphs_on = true;
+  cudaStream_t cap_stream = nullptr;
   int64_t acts_B = -1;                      // batch of the last forward that kept activations
   bool acts_normalized = false;
 };
@@ -358,6 +364,7 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
   g_use_pairs = getenv("CSB_NO_PAIRS") == nullptr;
   csb_mlp* h = new (std::nothrow) csb_mlp();
   CSB_REQUIRE(h != nullptr, CSB_ENOMEM, "host allocation failed");
+  h->graphs_on = getenv("CSB_NO_GRAPHS") == nullptr;
   h->cfg = *cfg;
   h->L = cfg->n_layers;
   h->sm_count = sm;
@@ -434,6 +441,8 @@ int csb_mlp_destroy(csb_mlp* h) {
   if (!h) return CSB_OK;
   cudaDeviceSynchronize();
   free_all(h);
+  for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   delete h;
   return CSB_OK;
@@ -839,15 +848,9 @@ static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st)
   return CSB_OK;
 }
 
-int csb_mlp_train_step(csb_mlp* h, const float* x, const float* y, int64_t B, float grad_scale, uint32_t flags,
-                       float* loss_out, void* stream) {
-  CSB_REQUIRE(h && x && y, CSB_EINVAL, "null argument");
-  int rc = check_batch(h, B);
-  if (rc) return rc;
-  CSB_REQUIRE(B > 0, CSB_EINVAL, "empty batch");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (grad_scale <= 0.f) grad_scale = 1.f / ((float)B * (float)h->out_dim);
-  if ((rc = build_act_maps(h, B))) return rc;
+static int train_step_body(csb_mlp* h, const float* x, const float* y, int64_t B, float grad_scale, uint32_t flags, float* loss_out,
+                           cudaStream_t st) {
+  int rc;
   prof_mark(h, K_BEGIN, st);
   if ((rc = run_normalize(h, x, B, (flags & CSB_FWD_NORMALIZE_IN) ? 1 : 0, st))) return rc;
   if ((rc = run_hidden_forward(h, B, st))) return rc;
@@ -866,12 +869,68 @@ int csb_mlp_train_step(csb_mlp* h, const float* x, const float* y, int64_t B, fl
     prof_mark(h, K_LOSS, st);
     n_partials = grid;
   }
-  simt::loss_finalize_kernel<<<1, 256, 0, st>>>(h->loss_partials, n_partials, loss_out ? loss_out : h->d_loss);
+  simt::loss_finalize_kernel<<<1, 256, 0, st>>>(h->loss_partials, n_partials, loss_out);
   CSB_CUDA_CHECK(cudaGetLastError());
   prof_mark(h, K_LOSS, st);
   if ((rc = run_backward_chain(h, B, nullptr, st))) return rc;
   h->acts_B = -1;
   return CSB_OK;
+}
+
+
+// The ~24 launches of a training step are replayed as one CUDA graph once the same (buffers, batch, scale) key has been
+// seen twice: first sight runs eagerly (also warms the one-time kernel attribute setup), second sight captures on an
+// internal stream (the caller's stream may be the legacy default stream, which cannot be captured) and instantiates.
+int csb_mlp_train_step(csb_mlp* h, const float* x, const float* y, int64_t B, float grad_scale, uint32_t flags,
+                       float* loss_out, void* stream) {
+  CSB_REQUIRE(h && x && y, CSB_EINVAL, "null argument");
+  int rc = check_batch(h, B);
+  if (rc) return rc;
+  CSB_REQUIRE(B > 0, CSB_EINVAL, "empty batch");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (grad_scale <= 0.f) grad_scale = 1.f / ((float)B * (float)h->out_dim);
+  if ((rc = build_act_maps(h, B))) return rc;
+  float* lo = loss_out ? loss_out : h->d_loss;
+  if (!h->graphs_on || h->prof_on) return train_step_body(h, x, y, B, grad_scale, flags, lo, st);
+
+  h->graph_clock++;
+  for (auto& g : h->graphs) {
+    if (g.x == x && g.y == y && g.B == B && g.gs == grad_scale && g.flags == flags && g.loss_out == lo && g.maps_B == h->maps_B) {
+      g.use = h->graph_clock;
+      if (g.exec == nullptr) {            // second sight: capture
+        if (h->cap_stream == nullptr) CSB_CUDA_CHECK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+        const int64_t l0 = h->launches;
+        CSB_CUDA_CHECK(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+        rc = train_step_body(h, x, y, B, grad_scale, flags, lo, h->cap_stream);
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
+        g.n_launches = h->launches - l0;
+        h->launches = l0;
+        if (rc || e != cudaSuccess || graph == nullptr) {
+          cudaGetLastError();
+          if (graph) cudaGraphDestroy(graph);
+          h->graphs_on = false;           // capture not possible here: stay on the eager path for good
+          return train_step_body(h, x, y, B, grad_scale, flags, lo, st);
+        }
+        e = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { cudaGetLastError(); g.exec = nullptr; h->graphs_on = false; return train_step_body(h, x, y, B, grad_scale, flags, lo, st); }
+      }
+      CSB_CUDA_CHECK(cudaGraphLaunch(g.exec, st));
+      h->launches += g.n_launches;
+      h->acts_B = -1;
+      return CSB_OK;
+    }
+  }
+  // first sight: remember the key, run eagerly
+  if (h->graphs.size() >= 8) {
+    size_t lru = 0;
+    for (size_t i = 1; i < h->graphs.size(); ++i) if (h->graphs[i].use < h->graphs[lru].use) lru = i;
+    if (h->graphs[lru].exec) cudaGraphExecDestroy(h->graphs[lru].exec);
+    h->graphs.erase(h->graphs.begin() + lru);
+  }
+  h->graphs.push_back({x, y, B, grad_scale, flags, lo, h->maps_B, nullptr, 0, h->graph_clock});
+  return train_step_body(h, x, y, B, grad_scale, flags, lo, st);
 }
 
 int csb_mlp_backward(csb_mlp* h, const float* dy, float* dx, int64_t B, void* stream) {
@@ -1024,6 +1083,9 @@ int csb_test_gemm_tn(const uint16_t* A, const uint16_t* Bt, float* C, int M, int
   return launch_tn<128, 5, tc::EPI_F32, 1>(ta, tb, nullptr, nullptr, p, sm, st);
 }
 
+static int g_test_dbg = 0;
+void csb_test_set_debug(int flags) { g_test_dbg = flags; }
+
 int csb_test_linear_fwd(const uint16_t* A, const uint16_t* Wt, const float* bias, uint16_t* out, int M, int N, int K, int act,
                         float alpha, int pairs, void* stream) {
   CSB_REQUIRE(A && Wt && bias && out, CSB_EINVAL, "null argument");
@@ -1039,6 +1101,7 @@ int csb_test_linear_fwd(const uint16_t* A, const uint16_t* Wt, const float* bias
   if ((rc = make_tmap_bf16(&tout, out, N, M, N, 64, 128))) return rc;
   tc::GemmParams p = {};
   p.M = M; p.N = N; p.K = K; p.act = act; p.alpha = alpha; p.head_relu_from = -1; p.bias = bias; p.out = out; p.ld_out = N;
+  p.dbg = g_test_dbg;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (use_pairs) return launch_tn<256, 5, tc::EPI_BIAS_ACT, 2>(ta, tb, &tout, nullptr, p, sm, st);
   if (wide) return launch_tn<256, 3, tc::EPI_BIAS_ACT, 1>(ta, tb, &tout, nullptr, p, sm, st);

@@ -45,6 +45,8 @@ struct GemmParams {
   int kb_per_tap;              // 0: plain GEMM
   int tap_center;
   int halo_period;             // 0: no halo rows
+  int dbg;                     // micro-benchmark knobs (scripts/microbench_gemm.py): 1 skip bias staging, 2 skip epilogue math + smem
+                               // stores, 4 skip TMA store, 8 skip TMEM loads.  0 in production.
   int act;                     // CSB_ACT_* for EPI_BIAS_ACT / EPI_DGRAD (activation of the layer whose output is stored / was saved)
   float alpha;
   int head_relu_from;          // EPI_HEAD_*: columns >= this get ReLU (-1: none); otherwise `act` applies
@@ -247,8 +249,13 @@ __device__ __forceinline__ void act_fwd_vec(int act, float alpha, float (&v)[32]
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
       break;
     case CSB_ACT_LEAKYRELU:
+      if (alpha >= 0.f && alpha <= 1.f) {               // warp-uniform: leaky(v) == max(v, alpha v) for a slope in [0, 1]
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = (alpha >= 0.f && alpha <= 1.f) ? fmaxf(v[j], alpha * v[j]) : (v[j] > 0.f ? v[j] : alpha * v[j]);
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], alpha * v[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : alpha * v[j];
+      }
       break;
     case CSB_ACT_ELU:
 #pragma unroll
@@ -369,16 +376,22 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint8_t* cst
     for (int j = 0; j < 32; ++j) v[j] = zero_row ? 0.f : v[j] + b[j] + a[j];
     cst_store32(cst, tile_row, tile_col, v);
   } else {
-    // head: p = (col >= head_relu_from) ? relu(z) : act(z)
+    // head: p = (col >= head_relu_from) ? relu(z) : act(z).  The activation switch is hoisted out of the element loops
+    // (act_*_vec): a per-element switch bloats the code past the instruction cache.
     float b[32], dact[32];
     load_smem_f32x32(sbias + tile_col, b);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float z = v[j] + b[j];
-      const bool relu_col = p.head_relu_from >= 0 && (gcol + j) >= p.head_relu_from;
-      const float pv = relu_col ? fmaxf(z, 0.f) : act_fwd(p.act, p.alpha, z);
-      dact[j] = relu_col ? (pv > 0.f ? 1.f : 0.f) : act_bwd_from_out(p.act, p.alpha, pv);
-      v[j] = pv;
+    for (int j = 0; j < 32; ++j) { b[j] += v[j]; v[j] = b[j]; dact[j] = 1.f; }      // b = z
+    act_fwd_vec(p.act, p.alpha, v);                                                   // v = act(z)
+    act_bwd_vec(p.act, p.alpha, dact, v);                                             // dact = act'(z) through act(z)
+    if (p.head_relu_from >= 0 && gcol + 32 > p.head_relu_from) {                      // warp-uniform
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (gcol + j >= p.head_relu_from) {
+          v[j] = fmaxf(b[j], 0.f);
+          dact[j] = b[j] > 0.f ? 1.f : 0.f;
+        }
+      }
     }
     if constexpr (EPI == EPI_HEAD_OUT) {
       if (p.inv_out_scale != nullptr) {
@@ -593,7 +606,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ===================== epilogue: warp w -> TMEM lanes 32*(w&3).., columns [HALF*(w>>2), HALF*(w>>2)+HALF) ==========
     const int q = warp & 3, hf = warp >> 2;
     const int tile_row = q * 32 + lane;
-    float bias_next = 0.f;
     int t = 0;
     for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++t) {
       const int mb = (tile / num_n_blocks) * CG + (int)cta_rank;
@@ -608,30 +620,26 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       }
       if constexpr (USE_BIAS) {
-        static_assert(BN <= TN_EPI_THREADS, "one bias element per epilogue thread");
-        if (t == 0) bias_next = (threadIdx.x < BN && n0 + (int)threadIdx.x < p.N) ? __ldg(p.bias + n0 + threadIdx.x) : 0.f;
-        if (threadIdx.x < BN) sbias[threadIdx.x] = bias_next;         // loaded during the previous tile: no latency here
+        if (!(p.dbg & 1))
+          for (int i = threadIdx.x; i < BN; i += TN_EPI_THREADS) sbias[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
       }
       mbar_wait(tfull_bar(acc), (uint32_t)(t >> 1) & 1u);
       tc_fence_after();
       if constexpr (CST_IN) mbar_wait(cst_full, (uint32_t)t & 1u);
       named_bar_sync(1, TN_EPI_THREADS);                      // bias staged; staging tile free; everyone past the waits
-      if constexpr (USE_BIAS) {                               // prefetch the next tile's bias element
-        const int tile_next = tile + tile_stride;
-        const int n0_next = (tile_next % num_n_blocks) * BN;
-        bias_next = (tile_next < num_tiles && threadIdx.x < BN && n0_next + (int)threadIdx.x < p.N) ? __ldg(p.bias + n0_next + threadIdx.x) : 0.f;
-      }
       float loss_acc = 0.f;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + hf * HALF);
       uint32_t raw[2][32];
-      if (hf * HALF < n_valid) tmem_ld_32x32(taddr, raw[0]);
+      if (hf * HALF < n_valid && !(p.dbg & 8)) tmem_ld_32x32(taddr, raw[0]);
 #pragma unroll
       for (int i = 0; i < NCH; ++i) {
         const int c = hf * HALF + 32 * i;                     // tile-relative column of this step (warp-uniform)
         if (c < n_valid) {
-          tmem_ld_wait();
-          if (i + 1 < NCH && c + 32 < n_valid) tmem_ld_32x32(taddr + (uint32_t)(32 * (i + 1)), raw[(i + 1) & 1]);
-          epilogue_chunk<EPI>(p, cst, sbias, tile_row, c, m0 + tile_row, n0 + c, raw[i & 1], loss_acc);
+          if (!(p.dbg & 8)) {
+            tmem_ld_wait();
+            if (i + 1 < NCH && c + 32 < n_valid) tmem_ld_32x32(taddr + (uint32_t)(32 * (i + 1)), raw[(i + 1) & 1]);
+          }
+          if (!(p.dbg & 2)) epilogue_chunk<EPI>(p, cst, sbias, tile_row, c, m0 + tile_row, n0 + c, raw[i & 1], loss_acc);
         }
       }
       tc_fence_before();
@@ -648,7 +656,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if constexpr (CST_OUT) {
         fence_proxy_async_smem();                             // generic-proxy smem writes -> visible to the TMA engine
         named_bar_sync(1, TN_EPI_THREADS);
-        if (threadIdx.x == 0) {
+        if (threadIdx.x == 0 && !(p.dbg & 4)) {
           const int slabs = (n_valid + 63) / 64;
           for (int sl = 0; sl < slabs; ++sl) tma_store_2d(&tmap_out, smem_base + L::CST_OFFSET + sl * SLAB_BYTES, n0 + 64 * sl, m0);
           tma_store_commit();                                 // waited for at the start of the next tile / before exit
