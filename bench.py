@@ -266,8 +266,13 @@ def main():
         n_dom = kinds[dom]["launches_per_step"]
         achieved = kinds[dom]["tflops"]
         peak = peaks["tf_sustained"]
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath) and B == 65536:
+            traffic = json.load(open(tpath)).get(dom, {}).get("dram_bytes_per_launch")
         roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "peak_source": f"{peaks['src']} bf16_tflops_sustained (kernel timed inside a long step)", "traffic": None,
+                    "peak_source": f"{peaks['src']} bf16_tflops_sustained (kernel timed inside a long step)", "traffic": traffic,
+                    "traffic_note": "bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum from profiles/r01_traffic.json (ncu --set full)",
                     "flops_per_launch": KIND_FLOPS[dom] * B / max(n_dom, 1), "avg_launch_ms": kinds[dom]["ms_per_step"] / max(n_dom, 1),
                     "step_tflops": FLOP_TRAIN * B / (ms_total / args.steps * 1e-3) / 1e12,
                     "step_frac_of_peak": FLOP_TRAIN * B / (ms_total / args.steps * 1e-3) / 1e12 / peak}

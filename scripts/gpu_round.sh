@@ -17,9 +17,9 @@ if [[ "$WHAT" == *bench* ]]; then
 fi
 if [[ "$WHAT" == *ncu* ]]; then
   echo "== ncu launch list"
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 60 --csv --log-file gpurun_out/launches.csv \
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 225 -c 52 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 4 --warmup 3 --cpu-sample 256 > gpurun_out/ncu_bench.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/ncu_bench.log
   echo "== ncu full (top kernels)"
-  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:gemm_ -s 60 -c 20 -o gpurun_out/prof_gemm -f \
+  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:gemm_ -s 180 -c 20 -o gpurun_out/prof_gemm -f \
       python bench.py --steps 4 --warmup 3 --cpu-sample 256 > gpurun_out/ncu_full.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/ncu_full.log
 fi
