@@ -16,7 +16,7 @@ MAX_LAYERS = 24
 OK, EINVAL, ENODEV, ENOMEM, ECUDA, ESTATE, EUNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 ACT = {"none": 0, "linear": 0, "relu": 1, "elu": 2, "leakyrelu": 3}
 DTYPE = {"fp32": 0, "f32": 0, "float32": 0, "bf16": 1, "bfloat16": 1}
-LOSS = {"mse": 0, "mae": 1}
+LOSS = {"mse": 0, "mae": 1, "huber": 2}
 OPT = {"adam_keras": 0, "adam": 0, "adam_torch": 1, "sgd": 2, "radam": 3, "rmsprop": 4}
 FWD_NORMALIZE_IN, FWD_DENORM_OUT, FWD_KEEP_ACTIVATIONS = 1, 2, 4
 
@@ -59,6 +59,7 @@ SIGNATURES = {
     "csb_mlp_get_opt_state": (C.c_int, [_VP, _VP, _VP, _P(C.c_int64)]),
     "csb_mlp_set_opt_state": (C.c_int, [_VP, _VP, _VP, C.c_int64]),
     "csb_mlp_set_norm": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
+    "csb_mlp_set_output_mask": (C.c_int, [_VP, _VP]),
     "csb_mlp_forward": (C.c_int, [_VP, _VP, _VP, C.c_int64, C.c_uint32, _VP]),
     "csb_mlp_forward_host": (C.c_int, [_VP, _VP, _VP, C.c_int64, C.c_uint32, _VP]),
     "csb_mlp_backward": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP]),

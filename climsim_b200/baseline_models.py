@@ -143,3 +143,34 @@ class HSR(torch.nn.Module):
     def load_reference_state_dict(self, sd) -> None:
         self.mean.load_reference_state_dict(sd, "mean.")
         self.logprec.load_reference_state_dict(sd, "logprec.")
+
+
+class OnlineMLP(_EngineModule):
+    """The online-testing MLP (online_testing/baseline_models/MLP_v2rh/training/mlp.py:24-68): ``layers`` x [Linear -> ReLU] ->
+    Linear, optional ``output_prune`` (zero the top ``strato_lev_out`` levels of the q1, q2, q3 and u tendencies), ReLU on the last
+    eight outputs.  Same constructor arguments as the reference class (``dropout`` must be 0)."""
+
+    def __init__(self, in_dims: int = 557, out_dims: int = 368, hidden_dims=(384, 1024, 640), layers: int = 3, dropout: float = 0.0,
+                 output_prune: bool = False, strato_lev_out: int = 15, dtype: str = "bf16", max_batch: int = 16384, seed: int = 0):
+        assert dropout == 0, "dropout > 0 is not reproducible across frameworks; the online configs use 0"
+        if isinstance(hidden_dims, (list, tuple)):
+            assert len(hidden_dims) == layers, "Length of hidden_dims should be equal to layers"
+            hidden = list(hidden_dims)
+        else:
+            hidden = [hidden_dims] * layers
+        spec = [(h, "relu", 0.0) for h in hidden] + [(out_dims, "none", 0.0)]
+        super().__init__(MLPEngine(in_dims, spec, head_relu_from=out_dims - 8, dtype=dtype, max_batch=max_batch), seed)
+        self.output_prune, self.strato_lev_out = output_prune, strato_lev_out
+        if output_prune:
+            mask = np.ones(out_dims, np.float32)
+            for start in (60, 120, 180, 240):
+                mask[start:start + strato_lev_out] = 0
+            self.engine.set_output_mask(mask)
+
+    def load_reference_state_dict(self, sd) -> None:
+        """Keys ``linears.{i}.0.weight`` (out,in) / ``.bias`` and ``final_linear.*`` of the reference module."""
+        parts = []
+        for i in range(len(self.engine.layer_dims) - 1):
+            parts += [sd[f"linears.{i}.0.weight"].t().reshape(-1), sd[f"linears.{i}.0.bias"]]
+        parts += [sd["final_linear.weight"].t().reshape(-1), sd["final_linear.bias"]]
+        self.load_flat(torch.cat([p.detach().float().cpu().reshape(-1) for p in parts]).numpy())

@@ -198,7 +198,8 @@ struct csb_mlp {
   float* ln_stats[CSB_MAX_LAYERS] = {};     // LayerNorm layers: (mean, rstd) per row [cap x 2]
   float* pred = nullptr;                    // [cap x out_p]
   float* dx_tmp = nullptr;                  // [cap x in_p] (lazily allocated)
-  float *d_sub = nullptr, *d_div = nullptr, *d_out_scale = nullptr, *d_inv_out_scale = nullptr, *d_loss_w = nullptr;
+  float *d_sub = nullptr, *d_div = nullptr, *d_out_scale = nullptr, *d_inv_out_scale = nullptr, *d_loss_w = nullptr, *d_out_mask = nullptr;
+  bool has_mask = false;
   float *loss_partials = nullptr, *d_loss = nullptr;
   int n_loss_partials = 0;
   float *x_stage = nullptr, *y_stage = nullptr;   // device staging for the *_host entry points
@@ -245,7 +246,7 @@ static void free_all(csb_mlp* h) {
   F(h->params); F(h->grads); F(h->m); F(h->v); F(h->ws);
   for (int l = 0; l < CSB_MAX_LAYERS; ++l) { F(h->w16[l]); F(h->wt16[l]); F(h->act[l]); F(h->zbuf[l]); F(h->ln_stats[l]); }
   F(h->xn); F(h->dz[0]); F(h->dz[1]); F(h->pred); F(h->dx_tmp);
-  F(h->d_sub); F(h->d_div); F(h->d_out_scale); F(h->d_inv_out_scale); F(h->d_loss_w);
+  F(h->d_sub); F(h->d_div); F(h->d_out_scale); F(h->d_inv_out_scale); F(h->d_loss_w); F(h->d_out_mask);
   F(h->loss_partials); F(h->d_loss); F(h->x_stage); F(h->y_stage);
 }
 
@@ -350,7 +351,7 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
   CSB_REQUIRE(cfg->n_layers >= 1 && cfg->n_layers <= CSB_MAX_LAYERS, CSB_EINVAL, "n_layers %d out of range", cfg->n_layers);
   CSB_REQUIRE(cfg->in_dim >= 1 && cfg->max_batch >= 1, CSB_EINVAL, "in_dim / max_batch must be positive");
   CSB_REQUIRE(cfg->dtype == CSB_F32 || cfg->dtype == CSB_BF16, CSB_EINVAL, "unknown dtype %d", cfg->dtype);
-  CSB_REQUIRE(cfg->loss == CSB_LOSS_MSE || cfg->loss == CSB_LOSS_MAE, CSB_EINVAL, "unknown loss %d", cfg->loss);
+  CSB_REQUIRE(cfg->loss >= CSB_LOSS_MSE && cfg->loss <= CSB_LOSS_HUBER, CSB_EINVAL, "unknown loss %d", cfg->loss);
   int sm = 0, maj = 0, min = 0;
   int rc = csb_device_info(&sm, &maj, &min, nullptr);
   if (rc) return rc;
@@ -420,6 +421,7 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
   CKA(h->pred, (size_t)h->cap * h->out_p * 4);
   CKA(h->d_sub, (size_t)h->in_p * 4); CKA(h->d_div, (size_t)h->in_p * 4);
   CKA(h->d_out_scale, (size_t)h->out_p * 4); CKA(h->d_inv_out_scale, (size_t)h->out_p * 4); CKA(h->d_loss_w, (size_t)h->out_p * 4);
+  CKA(h->d_out_mask, (size_t)h->out_p * 4);
   h->n_loss_partials = (int)std::max<int64_t>(h->cap / 128 * tc::TN_EPI_WARPS, 8 * sm);
   CKA(h->loss_partials, (size_t)h->n_loss_partials * 4);
   CKA(h->d_loss, 4);
@@ -599,6 +601,20 @@ int csb_mlp_set_norm(csb_mlp* h, const float* inp_sub, const float* inp_div, con
   return CSB_OK;
 }
 
+int csb_mlp_set_output_mask(csb_mlp* h, const float* mask_host) {
+  CSB_REQUIRE(h, CSB_EINVAL, "null handle");
+  CSB_CUDA_CHECK(cudaDeviceSynchronize());
+  h->has_mask = mask_host != nullptr;
+  if (mask_host) {
+    std::vector<float> m(h->out_p, 0.f);
+    for (int i = 0; i < h->out_dim; ++i) m[i] = mask_host[i] != 0.f ? 1.f : 0.f;
+    CSB_CUDA_CHECK(cudaMemcpy(h->d_out_mask, m.data(), (size_t)h->out_p * 4, cudaMemcpyHostToDevice));
+  }
+  for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);    // cached graphs captured the old epilogue parameters
+  h->graphs.clear();
+  return CSB_OK;
+}
+
 int csb_mlp_grad_buffer(csb_mlp* h, float** ptr, size_t* n) {
   CSB_REQUIRE(h && ptr && n, CSB_EINVAL, "null argument");
   *ptr = h->grads;
@@ -676,6 +692,7 @@ static int run_head(csb_mlp* h, int64_t B, int fused_loss, const float* y, float
     p.M = (int)B; p.N = li.Np; p.K = li.Kp; p.act = li.act; p.alpha = li.alpha; p.head_relu_from = h->cfg.head_relu_from;
     p.bias = h->params + li.b_off; p.out_dim = h->out_dim;
     p.pred = h->pred; p.ld_pred = h->out_p;
+    p.out_mask = h->has_mask ? h->d_out_mask : nullptr;
     int rc;
     if (fused_loss) {
       p.out = dz16(h, l); p.ld_out = li.Np;
@@ -697,6 +714,10 @@ static int run_head(csb_mlp* h, int64_t B, int fused_loss, const float* y, float
     dim3 grid((unsigned)(li.Np / 64), (unsigned)ceil_div(B, 64));
     simt::sgemm_kernel<false, false, simt::SEPI_BIAS_ACT><<<grid, 256, 0, st>>>(p);
     CSB_CUDA_CHECK(cudaGetLastError());
+    if (h->has_mask) {
+      simt::colmask_kernel<<<grid_for(B * h->out_dim, 256, h->sm_count), 256, 0, st>>>(h->pred, h->out_p, h->d_out_mask, B, h->out_dim);
+      CSB_CUDA_CHECK(cudaGetLastError());
+    }
   }
   prof_mark(h, K_GEMM_HEAD, st);
   return CSB_OK;
@@ -863,7 +884,7 @@ static int train_step_body(csb_mlp* h, const float* x, const float* y, int64_t B
     if ((rc = run_head(h, B, 0, nullptr, 0.f, st))) return rc;
     const int grid = std::min(h->n_loss_partials, grid_for(B * h->out_p, 256, h->sm_count));
     simt::head_grad_kernel<float><<<grid, 256, 0, st>>>(h->pred, h->out_p, y, h->out_dim, h->d_loss_w, grad_scale, h->cfg.loss, 0,
-                                                        h->layer[l].act, h->layer[l].alpha, h->cfg.head_relu_from, nullptr,
+                                                        h->layer[l].act, h->layer[l].alpha, h->cfg.head_relu_from, h->has_mask ? h->d_out_mask : nullptr,
                                                         dz32(h, l), h->out_p, B, h->out_dim, h->out_p, h->loss_partials);
     CSB_CUDA_CHECK(cudaGetLastError());
     prof_mark(h, K_LOSS, st);
@@ -942,11 +963,11 @@ int csb_mlp_backward(csb_mlp* h, const float* dy, float* dx, int64_t B, void* st
   prof_mark(h, K_BEGIN, st);
   if (h->bf16)
     simt::head_grad_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(h->pred, h->out_p, dy, h->out_dim, h->d_loss_w, 1.f, 0, 1, h->layer[l].act,
-                                                                 h->layer[l].alpha, h->cfg.head_relu_from, nullptr, dz16(h, l), h->out_p,
+                                                                 h->layer[l].alpha, h->cfg.head_relu_from, h->has_mask ? h->d_out_mask : nullptr, dz16(h, l), h->out_p,
                                                                  B, h->out_dim, h->out_p, nullptr);
   else
     simt::head_grad_kernel<float><<<grid, 256, 0, st>>>(h->pred, h->out_p, dy, h->out_dim, h->d_loss_w, 1.f, 0, 1, h->layer[l].act,
-                                                         h->layer[l].alpha, h->cfg.head_relu_from, nullptr, dz32(h, l), h->out_p, B,
+                                                         h->layer[l].alpha, h->cfg.head_relu_from, h->has_mask ? h->d_out_mask : nullptr, dz32(h, l), h->out_p, B,
                                                          h->out_dim, h->out_p, nullptr);
   CSB_CUDA_CHECK(cudaGetLastError());
   prof_mark(h, K_LOSS, st);

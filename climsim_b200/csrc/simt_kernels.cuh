@@ -176,7 +176,7 @@ template <typename TZ>
 __global__ void __launch_bounds__(256)
 head_grad_kernel(const float* __restrict__ pred, int ldp, const float* __restrict__ y_or_dy, int ldy,
                  const float* __restrict__ w, float scale, int loss_kind, int mode, int act, float alpha,
-                 int head_relu_from, const float* __restrict__ inv_scale_unused, TZ* __restrict__ dz, int ldz,
+                 int head_relu_from, const float* __restrict__ out_mask, TZ* __restrict__ dz, int ldz,
                  int64_t M, int out_dim, int Np, float* __restrict__ loss_partials) {
   float lacc = 0.f;
   const int64_t total = M * Np;
@@ -185,12 +185,18 @@ head_grad_kernel(const float* __restrict__ pred, int ldp, const float* __restric
     const int c = (int)(i - r * Np);
     float g = 0.f;
     if (c < out_dim) {
-      const float pv = pred[r * ldp + c];
+      const float pv = pred[r * ldp + c];                 // already masked by the forward pass
       const bool relu_col = head_relu_from >= 0 && c >= head_relu_from;
-      const float dact = relu_col ? (pv > 0.f ? 1.f : 0.f) : act_bwd_from_out(act, alpha, pv);
+      float dact = relu_col ? (pv > 0.f ? 1.f : 0.f) : act_bwd_from_out(act, alpha, pv);
+      if (out_mask != nullptr) dact *= out_mask[c];
       if (mode == 0) {
         const float d = pv - y_or_dy[r * ldy + c];
         if (loss_kind == CSB_LOSS_MSE) { lacc += w[c] * d * d; g = 2.f * w[c] * d * scale * dact; }
+        else if (loss_kind == CSB_LOSS_HUBER) {
+          const float ad = fabsf(d);
+          lacc += w[c] * (ad <= 1.f ? 0.5f * d * d : ad - 0.5f);
+          g = w[c] * scale * (ad <= 1.f ? d : (d > 0.f ? 1.f : -1.f)) * dact;
+        }
         else { lacc += w[c] * fabsf(d); g = w[c] * scale * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * dact; }
       } else {
         g = y_or_dy[r * ldy + c] * dact;
@@ -477,6 +483,16 @@ __global__ void __launch_bounds__(256) pad_copy_kernel(float* __restrict__ padde
 // ---------------------------------------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------------------------------------
+// in-place column mask: a[r, c] *= mask[c]
+__global__ void colmask_kernel(float* __restrict__ a, int ld, const float* __restrict__ mask, int64_t M, int F) {
+  const int64_t total = M * F;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / F;
+    const int c = (int)(i - r * F);
+    a[r * ld + c] *= mask[c];
+  }
+}
+
 // out[r, c] = in[r, c] * scale[c] for c < F  (denormalise predictions), in ld_in -> out ld_out
 __global__ void scale_copy_kernel(const float* __restrict__ in, int ld_in, const float* __restrict__ scale,
                                   float* __restrict__ out, int ld_out, int64_t M, int F) {

@@ -65,6 +65,7 @@ struct GemmParams {
   float* pred;                 // optional fp32 predictions [M, ld_pred]
   int ld_pred;
   const float* inv_out_scale;  // optional [N]: pred *= inv_out_scale
+  const float* out_mask;       // optional [N] of 0/1: predictions (and their gradients) of masked columns are zero
   float* loss_partials;        // [num_m_blocks * 4]
 };
 
@@ -393,6 +394,12 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint8_t* cst
         }
       }
     }
+    if (p.out_mask != nullptr) {
+      float mk[32];
+      load_f32x32(p.out_mask + gcol, mk);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { v[j] *= mk[j]; dact[j] *= mk[j]; }
+    }
     if constexpr (EPI == EPI_HEAD_OUT) {
       if (p.inv_out_scale != nullptr) {
         load_f32x32(p.inv_out_scale + gcol, b);
@@ -435,6 +442,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint8_t* cst
           if (p.loss_kind == CSB_LOSS_MSE) {
             loss_acc += w[j] * d * d;
             dact[c] *= 2.f * w[j] * d * p.grad_scale;
+          } else if (p.loss_kind == CSB_LOSS_HUBER) {
+            const float ad = fabsf(d);
+            loss_acc += w[j] * (ad <= 1.f ? 0.5f * d * d : ad - 0.5f);
+            dact[c] *= w[j] * p.grad_scale * (ad <= 1.f ? d : (d > 0.f ? 1.f : -1.f));
           } else {
             loss_acc += w[j] * fabsf(d);
             dact[c] *= w[j] * p.grad_scale * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));

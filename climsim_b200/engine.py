@@ -159,6 +159,15 @@ class MLPEngine:
         _lib.check(self.lib.csb_mlp_set_norm(self._h, p(inp_sub, self.in_dim), p(inp_div, self.in_dim),
                                              p(out_scale, self.out_dim), p(loss_w, self.out_dim)), "csb_mlp_set_norm")
 
+    def set_output_mask(self, mask) -> None:
+        """0/1 mask over the output columns (the online MLP's ``output_prune``); ``None`` removes it."""
+        if mask is None:
+            _lib.check(self.lib.csb_mlp_set_output_mask(self._h, None), "csb_mlp_set_output_mask")
+            return
+        m = np.ascontiguousarray(mask, dtype=np.float32)
+        assert m.size == self.out_dim
+        _lib.check(self.lib.csb_mlp_set_output_mask(self._h, m.ctypes.data), "csb_mlp_set_output_mask")
+
     # -- compute ------------------------------------------------------------------------------------------------
     @staticmethod
     def _flags(normalize_in: bool, denorm_out: bool, keep: bool) -> int:

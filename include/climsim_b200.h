@@ -53,7 +53,8 @@ enum { CSB_F32 = 0, CSB_BF16 = 1 };
 
 /* Loss.  MSE: mean_ij w_j (p_ij - y_ij)^2  (w = 1 is Keras 'mse', hpo_baseline_v1.py:127-129).
  * MAE: mean_ij w_j |p_ij - y_ij|           (CNN mae_adjusted through w, CNN/training/hpo_train.py:114-121). */
-enum { CSB_LOSS_MSE = 0, CSB_LOSS_MAE = 1 };
+/* HUBER: torch.nn.HuberLoss(delta=1) (online_testing/.../train_mlp_h5loader.py:226-232): mean_ij w_j h(p-y), h(d) = d^2/2 if |d| <= 1 else |d| - 1/2 */
+enum { CSB_LOSS_MSE = 0, CSB_LOSS_MAE = 1, CSB_LOSS_HUBER = 2 };
 
 /* Optimizer update rule.
  * ADAM_KERAS: keras.optimizers.Adam update_step (hpo_baseline_v1.py:116-117): w -= lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps)
@@ -116,6 +117,10 @@ int  csb_mlp_set_opt_state(csb_mlp* h, const float* m_host, const float* v_host,
 /* Normalisation / loss vectors (HOST pointers; NULL keeps the default): inp_sub[in_dim] (0), inp_div[in_dim] (1),
  * out_scale[out_dim] (1), loss_w[out_dim] (1).  data_utils.save_norm (data_utils.py:954-988) produces the first three. */
 int  csb_mlp_set_norm(csb_mlp* h, const float* inp_sub, const float* inp_div, const float* out_scale, const float* loss_w);
+
+/* Per-output-column 0/1 mask applied to the predictions (and therefore to their gradients): the online MLP's `output_prune`
+ * zeroing of the stratospheric levels (online_testing/baseline_models/MLP_v2rh/training/mlp.py:56-61).  NULL removes the mask. */
+int  csb_mlp_set_output_mask(csb_mlp* h, const float* mask_host);
 
 /* model.predict / module.forward: x (B,in_dim) -> y_pred (B,out_dim).  step3_inference.ipynb cell 2; hsr.py:28-35 */
 int  csb_mlp_forward(csb_mlp* h, const float* x, float* y_pred, int64_t B, uint32_t flags, void* stream);

@@ -429,3 +429,29 @@ def keras_rmsprop_step(params: List[torch.Tensor], grads: List[torch.Tensor], v:
         for p, g, vi in zip(params, grads, v):
             vi.mul_(rho).addcmul_(g, g, value=1 - rho)
             p.sub_(lr * g * torch.rsqrt(vi + eps))
+
+
+class OnlineMLPRef(torch.nn.Module):
+    """Restatement of the online MLP -- online_testing/baseline_models/MLP_v2rh/training/mlp.py:24-68 -- without the Modulus
+    base class (not installable here): same ``state_dict`` keys (``linears.{i}.0.*``, ``final_linear.*``), same forward incl.
+    ``output_prune`` and the ReLU on the last eight outputs.  UNPINNED (the reference class needs nvidia-modulus to import)."""
+
+    def __init__(self, in_dims, out_dims, hidden_dims, layers, dropout=0.0, output_prune=False, strato_lev_out=15):
+        super().__init__()
+        hidden = list(hidden_dims) if isinstance(hidden_dims, (list, tuple)) else [hidden_dims] * layers
+        assert len(hidden) == layers
+        self.output_prune, self.strato_lev_out = output_prune, strato_lev_out
+        self.linears = torch.nn.ModuleList([torch.nn.Sequential(torch.nn.Linear(in_dims if i == 0 else hidden[i - 1], hidden[i]),
+                                                                torch.nn.Dropout(p=dropout)) for i in range(layers)])
+        self.final_linear = torch.nn.Linear(hidden[-1], out_dims)
+
+    def forward(self, x):
+        for linear in self.linears:
+            x = torch.relu(linear(x))
+        x = self.final_linear(x)
+        if self.output_prune:
+            mask = torch.ones(x.shape[1], dtype=x.dtype)
+            for start in (60, 120, 180, 240):
+                mask[start:start + self.strato_lev_out] = 0
+            x = x * mask
+        return torch.cat([x[:, :-8], torch.relu(x[:, -8:])], dim=1)

@@ -130,3 +130,42 @@ def test_hsr_layernorm_model_against_reference_golden(golden_dir, dtype, tol_out
                 off += v.numel()
                 err = np.linalg.norm(part - want) / max(np.linalg.norm(want), 1e-12)
                 assert err <= tol_g, (mode, key, err)
+
+
+@pytest.mark.parametrize("dtype,tol,tol_g", [("fp32", 2e-5, 1e-4), ("bf16", 3e-2, 1e-1)])
+@pytest.mark.parametrize("loss", ["huber", "mse", "mae"])
+def test_online_mlp_surface(dtype, tol, tol_g, loss):
+    """The online MLP (557 -> [384, 1024, 640] -> 368, output_prune, last-8 ReLU) with Huber / MSE / L1 criteria
+    (train_mlp_h5loader.py:222-232) through the fused train step, against the torch restatement of mlp.py."""
+    from climsim_b200.baseline_models import OnlineMLP
+    from oracle import models as M
+    torch.manual_seed(0)
+    ref = M.OnlineMLPRef(557, 368, [384, 1024, 640], 3, output_prune=True)
+    net = OnlineMLP(557, 368, [384, 1024, 640], 3, output_prune=True, dtype=dtype, max_batch=512)
+    net.load_reference_state_dict(ref.state_dict())
+    g = torch.Generator().manual_seed(1)
+    x, y = 0.5 * torch.randn(300, 557, generator=g), 2.0 * torch.randn(300, 368, generator=g)      # |d| spans both Huber branches
+    want = ref(x)
+    with torch.no_grad():
+        got = net(x.cuda()).cpu()
+    assert (got[:, 60:75] == 0).all() and (got[:, 240:255] == 0).all() and (got[:, -8:] >= 0).all()
+    assert (got - want).abs().max().item() <= tol * want.abs().max().item()
+    crit = {"huber": torch.nn.HuberLoss(), "mse": torch.nn.MSELoss(), "mae": torch.nn.L1Loss()}[loss]
+    l_ref = crit(want, y)
+    l_ref.backward()
+    # fused path: the engine's own loss (criterion selected at creation)
+    from climsim_b200 import MLPEngine
+    eng = MLPEngine(557, [(384, "relu", 0.0), (1024, "relu", 0.0), (640, "relu", 0.0), (368, "none", 0.0)], head_relu_from=360,
+                    dtype=dtype, loss=loss, max_batch=512)
+    eng.set_params_flat(net.flat.detach().cpu().numpy())
+    mask = np.ones(368, np.float32)
+    for s0 in (60, 120, 180, 240):
+        mask[s0:s0 + 15] = 0
+    eng.set_output_mask(mask)
+    l_got = eng.train_step(x.cuda(), y.cuda()).item()
+    assert abs(l_got - l_ref.item()) <= max(tol, 1e-5) * abs(l_ref.item())
+    want_g = torch.cat([torch.cat([l[0].weight.grad.t().reshape(-1), l[0].bias.grad]) for l in ref.linears] +
+                       [ref.final_linear.weight.grad.t().reshape(-1), ref.final_linear.bias.grad]).numpy()
+    got_g = eng.get_grads_flat()
+    tg = tol_g * (2.5 if (loss == "mae" and dtype == "bf16") else 1.0)       # sign(d) flips under bf16 rounding
+    assert np.linalg.norm(got_g - want_g) / np.linalg.norm(want_g) <= tg
