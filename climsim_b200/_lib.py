@@ -89,6 +89,8 @@ SIGNATURES = {
     "csb_reshape_input_for_cnn": (C.c_int, [_VP, _VP, C.c_int64, _VP]),
     "csb_reshape_target_for_cnn": (C.c_int, [_VP, _VP, C.c_int64, _VP]),
     "csb_reshape_target_from_cnn": (C.c_int, [_VP, _VP, C.c_int64, _VP]),
+    "csb_eval_metrics": (C.c_int, [_VP, _VP, _VP, C.c_int64, C.c_int32, _VP, _VP, C.c_double, _VP, _VP, C.c_double, C.c_double, C.c_double,
+                                   C.c_int, _VP, _VP, _VP]),
     "csb_test_gemm_tn": (C.c_int, [_VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP]),
     "csb_test_linear_fwd": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _VP]),
     "csb_test_set_debug": (None, [C.c_int]),

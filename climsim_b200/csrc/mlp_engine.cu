@@ -422,7 +422,7 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
   CKA(h->d_sub, (size_t)h->in_p * 4); CKA(h->d_div, (size_t)h->in_p * 4);
   CKA(h->d_out_scale, (size_t)h->out_p * 4); CKA(h->d_inv_out_scale, (size_t)h->out_p * 4); CKA(h->d_loss_w, (size_t)h->out_p * 4);
   CKA(h->d_out_mask, (size_t)h->out_p * 4);
-  h->n_loss_partials = (int)std::max<int64_t>(h->cap / 128 * tc::TN_EPI_WARPS, 8 * sm);
+  h->n_loss_partials = (int)std::max<int64_t>(h->cap / 128 * ceil_div(h->out_p, tn_block_n(h->out_p)) * tc::TN_EPI_WARPS, 8 * sm);
   CKA(h->loss_partials, (size_t)h->n_loss_partials * 4);
   CKA(h->d_loss, 4);
   if (h->bf16) {
@@ -879,7 +879,7 @@ static int train_step_body(csb_mlp* h, const float* x, const float* y, int64_t B
   const int l = h->L - 1;
   if (h->bf16) {
     if ((rc = run_head(h, B, 1, y, grad_scale, st))) return rc;
-    n_partials = (int)ceil_div(B, 128) * tc::TN_EPI_WARPS;
+    n_partials = (int)(ceil_div(B, 128) * ceil_div(h->out_p, tn_block_n(h->out_p))) * tc::TN_EPI_WARPS;
   } else {
     if ((rc = run_head(h, B, 0, nullptr, 0.f, st))) return rc;
     const int grid = std::min(h->n_loss_partials, grid_for(B * h->out_p, 256, h->sm_count));
@@ -1077,6 +1077,31 @@ int csb_reshape_target_from_cnn(const float* p, float* out, int64_t N, void* str
   CSB_REQUIRE(p && out && N >= 0, CSB_EINVAL, "bad argument");
   if (N == 0) return CSB_OK;
   simt::cnn_reshape_out_kernel<<<(unsigned)std::min<int64_t>(ceil_div(N * 128, 256), 148 * 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, out, N);
+  CSB_CUDA_CHECK(cudaGetLastError());
+  return CSB_OK;
+}
+
+int csb_eval_metrics(const float* pred, const float* target, const float* x_norm, int64_t N, int32_t ncol, const double* hyai,
+                     const double* hybi, double p0, const double* area_wgt, const double* out_scale, double ps_mean, double ps_max,
+                     double ps_min, int normalize, double* out, double* scratch, void* stream) {
+  CSB_REQUIRE(pred && target && x_norm && hyai && hybi && area_wgt && out_scale && out && scratch, CSB_EINVAL, "null argument");
+  CSB_REQUIRE(ncol >= 1 && N >= ncol && N % ncol == 0, CSB_EINVAL, "N (%lld) must be a positive multiple of ncol (%d)", (long long)N, ncol);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  simt::EvalConsts c;
+  for (int i = 0; i < 61; ++i) { c.hyai[i] = hyai[i]; c.hybi[i] = hybi[i]; }
+  c.p0 = p0; c.ps_mean = ps_mean; c.ps_span = ps_max - ps_min; c.grav = 9.80616; c.normalize = normalize;
+  // energy-unit conversion (data_utils.py:480-494) and the small constant vectors live at the tail of the scratch buffer
+  std::vector<double> host((size_t)ncol + 128 + 128);
+  for (int i = 0; i < ncol; ++i) host[i] = area_wgt[i];
+  for (int j = 0; j < 128; ++j) host[ncol + j] = out_scale[j];
+  const double cp = 1.00464e3, lv = 2.501e6, rho_h2o = 1.0e3;
+  for (int j = 0; j < 128; ++j) host[ncol + 128 + j] = j < 60 ? cp : (j < 120 ? lv : ((j == 122 || j == 123) ? lv * rho_h2o : 1.0));
+  double* dconst = scratch + (size_t)4 * 128 * ncol;
+  CSB_CUDA_CHECK(cudaMemcpyAsync(dconst, host.data(), host.size() * 8, cudaMemcpyHostToDevice, st));
+  CSB_CUDA_CHECK(cudaStreamSynchronize(st));       // `host` goes out of scope
+  simt::eval_metrics_kernel<<<ncol, 128, 0, st>>>(pred, target, x_norm, N / ncol, ncol, dconst, dconst + ncol, dconst + ncol + 128, c, scratch);
+  CSB_CUDA_CHECK(cudaGetLastError());
+  simt::eval_gridmean_kernel<<<4, 128, 0, st>>>(scratch, ncol, out);
   CSB_CUDA_CHECK(cudaGetLastError());
   return CSB_OK;
 }

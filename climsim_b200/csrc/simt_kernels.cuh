@@ -604,5 +604,55 @@ __global__ void __launch_bounds__(256) conv_pad_copy_kernel(float* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// fused evaluation: output weighting + per-(column, output) time reductions, then the grid mean (data_utils.py:1112-1362,
+// 1432-1497).  Thread = one (grid column, output index); loops over the T time samples (coalesced over the output index).
+// ---------------------------------------------------------------------------------------------------------------
+struct EvalConsts {
+  double hyai[61], hybi[61];
+  double p0, ps_mean, ps_span, grav;
+  int normalize;
+};
+
+__global__ void __launch_bounds__(128)
+eval_metrics_kernel(const float* __restrict__ pred, const float* __restrict__ target, const float* __restrict__ x_norm, int64_t T, int ncol,
+                    const double* __restrict__ area_wgt, const double* __restrict__ out_scale, const double* __restrict__ conv,
+                    const EvalConsts c, double* __restrict__ scratch) {
+  const int j = threadIdx.x;                         // output index 0..127
+  const int col = blockIdx.x;
+  const double inv_scale = c.normalize ? 1.0 / out_scale[j] : 1.0;      // the reference divides; x * (1/s) differs by <= 1 ulp
+  const double aw = area_wgt[col], cv = conv[j];
+  const int lev = j < 60 ? j : j - 60;
+  const bool prof = j < 120;
+  double s_abs = 0, s_sq = 0, s_p = 0, s_t = 0, s_tt = 0;
+  for (int64_t t = 0; t < T; ++t) {
+    const int64_t r = t * ncol + col;
+    double wgt = aw * cv;
+    if (prof) {
+      double ps = (double)x_norm[r * 124 + 120];
+      if (c.normalize) ps = ps * c.ps_span + c.ps_mean;
+      const double dp = (c.p0 * c.hyai[lev + 1] + c.hybi[lev + 1] * ps) - (c.p0 * c.hyai[lev] + c.hybi[lev] * ps);
+      wgt *= dp / c.grav;
+    }
+    const double pw = (double)pred[r * 128 + j] * inv_scale * wgt;
+    const double tw = (double)target[r * 128 + j] * inv_scale * wgt;
+    const double d = pw - tw;
+    s_abs += fabs(d); s_sq += d * d; s_p += pw; s_t += tw; s_tt += tw * tw;
+  }
+  const double n = (double)T;
+  double* o = scratch + ((size_t)col * 4) * 128 + j;
+  o[0 * 128] = s_abs / n;
+  o[1 * 128] = sqrt(s_sq / n);
+  o[2 * 128] = 1.0 - s_sq / (s_tt - s_t * s_t / n);
+  o[3 * 128] = s_p / n - s_t / n;
+}
+// grid mean in a fixed order: out[m][j] = mean_col scratch[col][m][j]
+__global__ void __launch_bounds__(128) eval_gridmean_kernel(const double* __restrict__ scratch, int ncol, double* __restrict__ out) {
+  const int j = threadIdx.x, m = blockIdx.x;
+  double s = 0;
+  for (int col = 0; col < ncol; ++col) s += scratch[((size_t)col * 4 + m) * 128 + j];
+  out[m * 128 + j] = s / (double)ncol;
+}
+
 }  // namespace simt
 }  // namespace csb

@@ -66,7 +66,7 @@ struct GemmParams {
   int ld_pred;
   const float* inv_out_scale;  // optional [N]: pred *= inv_out_scale
   const float* out_mask;       // optional [N] of 0/1: predictions (and their gradients) of masked columns are zero
-  float* loss_partials;        // [num_m_blocks * 4]
+  float* loss_partials;        // [num_m_blocks * num_n_blocks * TN_EPI_WARPS]
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -659,10 +659,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if constexpr (CG == 2) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc));
       }
       if constexpr (EPI == EPI_HEAD_LOSS) {
-        // deterministic: one partial per (m-block, epilogue warp); requires num_n_blocks == 1 (host asserts)
+        // deterministic: one partial per (m-block, n-block, epilogue warp)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
-        if (lane == 0 && m0 < p.M) p.loss_partials[mb * TN_EPI_WARPS + warp] = loss_acc * p.grad_scale;
+        if (lane == 0 && m0 < p.M) p.loss_partials[(mb * num_n_blocks + (tile % num_n_blocks)) * TN_EPI_WARPS + warp] = loss_acc * p.grad_scale;
       }
       if constexpr (CST_OUT) {
         fence_proxy_async_smem();                             // generic-proxy smem writes -> visible to the TMA engine

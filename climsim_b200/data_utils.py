@@ -248,6 +248,30 @@ class data_utils:
             getattr(self, f"metrics_var_{data_split}")[model_name] = df_var
             getattr(self, f"metrics_idx_{data_split}")[model_name] = df_idx
 
+    def gpu_metrics(self, preds, targets, inputs):
+        """Fused device evaluation (``csb_eval_metrics``): what ``set_pressure_grid`` + ``reweight_target`` + ``reweight_preds`` +
+        ``create_metrics_df`` compute for the metrics MAE / RMSE / R2 / bias, in one pass over CUDA tensors ``preds`` (N,128),
+        ``targets`` (N,128), ``inputs`` (N,124).  Returns a DataFrame indexed by output index (like ``metrics_idx_<split>``)."""
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        assert preds.is_cuda and targets.is_cuda and inputs.is_cuda
+        p, t, x = (a.to(torch.float32).contiguous() for a in (preds, targets, inputs))
+        n = p.shape[0]
+        out = torch.empty(4, 128, dtype=torch.float64, device=p.device)
+        scratch = torch.empty(4 * 128 * self.num_latlon + self.num_latlon + 256, dtype=torch.float64, device=p.device)
+        _, _, out_scale = self.save_norm()
+        hyai, hybi = np.ascontiguousarray(self.hyai), np.ascontiguousarray(self.hybi)
+        aw, osc = np.ascontiguousarray(self.area_wgt), np.ascontiguousarray(out_scale)
+        _lib.check(lib.csb_eval_metrics(p.data_ptr(), t.data_ptr(), x.data_ptr(), n, self.num_latlon, hyai.ctypes.data, hybi.ctypes.data,
+                                        self.p0, aw.ctypes.data, osc.ctypes.data, float(_val(self.input_mean["state_ps"])),
+                                        float(_val(self.input_max["state_ps"])), float(_val(self.input_min["state_ps"])),
+                                        1 if self.normalize else 0, out.data_ptr(), scratch.data_ptr(), _lib.current_stream_ptr()),
+                   "csb_eval_metrics")
+        df = pd.DataFrame(out.cpu().numpy().T, columns=["MAE", "RMSE", "R2", "bias"], index=range(128))
+        df.index.name = "output_idx"
+        return df
+
     # ------------------------------------------------------------------------------------------------ CNN layouts (:1693-1760)
     @staticmethod
     def _cuda_reshape(fn_name, t, out_shape):

@@ -210,6 +210,17 @@ int  csb_reshape_input_for_cnn(const float* x, float* out, int64_t N, void* stre
 int  csb_reshape_target_for_cnn(const float* y, float* out, int64_t N, void* stream);
 int  csb_reshape_target_from_cnn(const float* p, float* out, int64_t N, void* stream);
 
+/* Fused evaluation (V1 variable set): denormalise -> dp/g vertical weighting -> area weighting -> energy units
+ * (data_utils.output_weighting, data_utils.py:1112-1362) and the time-axis metrics MAE / RMSE / R2 / bias followed by the grid
+ * mean (data_utils.calc_*, :1432-1497), in one pass over pred / target (N,128) fp32 with fp64 accumulation.
+ *   x_norm (N,124) is the (normalised) input array the pressure grid is built from (set_pressure_grid, :1037-1086);
+ *   N must be a multiple of ncol (rows are ordered time-major, column fastest, as the reference reshapes them);
+ *   consts (host, fp64): hyai[61], hybi[61], area_wgt[ncol], out_scale[128];  ps_* de-normalise state_ps.
+ * out (device, fp64) [4][128]: rows MAE, RMSE, R2, bias per output index.  scratch (device) needs 4*128*ncol + ncol + 256 doubles. */
+int  csb_eval_metrics(const float* pred, const float* target, const float* x_norm, int64_t N, int32_t ncol, const double* hyai,
+                      const double* hybi, double p0, const double* area_wgt, const double* out_scale, double ps_mean, double ps_max,
+                      double ps_min, int normalize, double* out, double* scratch, void* stream);
+
 /* ---- kernel self-test hooks (used by tests/test_gemm_gpu.py; device pointers) ----------------------------- */
 /* C[M,N] (fp32) = A[M,K] * Bt[N,K]^T on the tcgen05 path (both operands K-major bf16, raw uint16 payloads). */
 int  csb_test_gemm_tn(const uint16_t* A, const uint16_t* Bt, float* C, int M, int N, int K, int block_n, void* stream);

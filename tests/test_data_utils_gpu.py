@@ -169,3 +169,33 @@ def test_online_mlp_surface(dtype, tol, tol_g, loss):
     got_g = eng.get_grads_flat()
     tg = tol_g * (2.5 if (loss == "mae" and dtype == "bf16") else 1.0)       # sign(d) flips under bf16 rounding
     assert np.linalg.norm(got_g - want_g) / np.linalg.norm(want_g) <= tg
+
+
+def test_fused_gpu_metrics_match_reference_golden(golden_dir):
+    """csb_eval_metrics (weighting + MAE/RMSE/R2/bias + grid mean in one pass) against the per-index metrics the REFERENCE's
+    own data_utils produced (tests/golden/data_utils.npz)."""
+    from test_data_utils_cpu import V1_IN, V1_OUT
+    from climsim_b200.data_utils import data_utils
+    g = np.load(os.path.join(golden_dir, "data_utils.npz"))
+    ncol = int(g["ncol"])
+    def split(vec, names, ls):
+        out, off = {}, 0
+        for n, l in zip(names, ls):
+            out[n] = vec[off:off + l] if l > 1 else vec[off]
+            off += l
+        return out
+    mean = split(g["inp_sub"], V1_IN, [60, 60, 1, 1, 1, 1])
+    vmax, vmin = split(g["inp_div"], V1_IN, [60, 60, 1, 1, 1, 1]), split(np.zeros(124), V1_IN, [60, 60, 1, 1, 1, 1])
+    mean["state_ps"], vmax["state_ps"], vmin["state_ps"] = g["ps_mean"], g["ps_max"], g["ps_min"]
+    du = data_utils({"lev": np.arange(60), "ncol": np.arange(ncol), "area": g["area"], "hyai": g["hyai"], "hybi": g["hybi"], "P0": 1e5},
+                    mean, vmax, vmin, split(g["out_scale"], V1_OUT, [60, 60] + [1] * 8))
+    du.set_to_v1_vars()
+    df = du.gpu_metrics(torch.from_numpy(g["pred"]).cuda(), torch.from_numpy(g["target"]).cuda(), torch.from_numpy(g["x_norm"]).cuda())
+    col = 0
+    for v in V1_OUT:
+        n = 60 if v in ("ptend_t", "ptend_q0001") else 1
+        for m in ("MAE", "RMSE", "R2", "bias"):
+            want = np.atleast_1d(g[f"{m}_{v}"])
+            got = df[m].values[col:col + n]
+            np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-12 * max(1.0, np.abs(want).max()), err_msg=f"{m} {v}")
+        col += n
