@@ -16,7 +16,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 import torch
 
-from .engine import MLPEngine
+from .engine import CNNEngine, MLPEngine
 from .trainer import glorot_uniform_flat
 
 
@@ -174,3 +174,24 @@ class OnlineMLP(_EngineModule):
             parts += [sd[f"linears.{i}.0.weight"].t().reshape(-1), sd[f"linears.{i}.0.bias"]]
         parts += [sd["final_linear.weight"].t().reshape(-1), sd["final_linear.bias"]]
         self.load_flat(torch.cat([p.detach().float().cpu().reshape(-1) for p in parts]).numpy())
+
+
+class CNN(torch.nn.Module):
+    """ResNet-1D of baseline_models/CNN/training/hpo_train.py:131-200 (a Keras model in the reference): ``forward(x: (B,60,6))
+    -> (B,60,10)`` for inference; training goes through the fused ``engine.train_step`` / ``engine.apply_opt`` (loss =
+    ``mae_adjusted`` or ``mse_adjusted``), the way ``model.fit`` drives it in the reference (hpo_train.py:355-368)."""
+
+    def __init__(self, depth: int = 12, width: int = 406, kernel: int = 3, loss: str = "mae", dtype: str = "bf16", max_batch: int = 4096):
+        super().__init__()
+        self.engine = CNNEngine(depth=depth, width=width, kernel=kernel, loss=loss, dtype=dtype, max_batch=max_batch)
+
+    def load_keras_weights(self, weights: Sequence[np.ndarray]) -> None:
+        self.engine.set_params_flat(CNNEngine.keras_to_flat(weights))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.engine.forward(x)
+
+    def train_step(self, x: torch.Tensor, y: torch.Tensor, lr: float = 1e-4, rule: str = "adam_keras") -> torch.Tensor:
+        loss = self.engine.train_step(x, y)
+        self.engine.apply_opt(rule, lr=lr)
+        return loss

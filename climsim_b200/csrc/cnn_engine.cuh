@@ -11,7 +11,7 @@
 //
 // Backward: data gradients are convolutions with the tap-flipped, transposed kernels (wd16 copies); weight gradients
 // are one gemm_nt launch per tap with the activation rows shifted by (tap - 1); bias gradients ride in the tap-0 launch.
-// Only the CSB_BF16 arithmetic mode exists for the CNN so far.
+// CSB_F32 parity mode: the same flow on fp32 buffers with sgemm_kernel (tap-aware loaders), no split-K workspace.
 #pragma once
 
 struct ConvLayerInfo {
@@ -24,6 +24,7 @@ struct ConvLayerInfo {
 };
 
 struct BufMaps { CUtensorMap k128, mn64; };
+struct CnnBuf { void* ptr = nullptr; int Cp = 0; BufMaps maps; };      // bf16 (CSB_BF16) or fp32 (CSB_F32) [cap x Cp]
 
 struct csb_cnn {
   csb_cnn_cfg cfg;
@@ -36,15 +37,12 @@ struct csb_cnn {
   int sm_count = 0;
   float *params = nullptr, *grads = nullptr, *m = nullptr, *v = nullptr, *ws = nullptr, *zero_bias = nullptr;
   // activation buffers: x0, per block (h1, h2, out), e;  gradient buffers G0, G1, Z1, Z2, T, dzh (head), dze
-  __nv_bfloat16* x0 = nullptr;
-  __nv_bfloat16* h1[16] = {};
-  __nv_bfloat16* h2[16] = {};
-  __nv_bfloat16* ob[16] = {};
-  __nv_bfloat16 *e = nullptr, *G[2] = {nullptr, nullptr}, *Z1 = nullptr, *Z2 = nullptr, *T = nullptr, *dzh = nullptr, *dze = nullptr;
+  bool bf16 = true;
+  CnnBuf x0, h1[16], h2[16], ob[16], e, G[2], Z1, Z2, T, dzh, dze;
+  float* pred = nullptr;                         // fp32 mode: head output in the halo layout [cap x out_p]
   float *d_loss_w = nullptr, *loss_partials = nullptr, *d_loss = nullptr;
   int n_loss_partials = 0;
   int64_t maps_B = -1;
-  BufMaps mx0, mh1[16], mh2[16], mob[16], me, mG[2], mZ1, mZ2, mT, mdzh, mdze;
   int64_t step = 0, launches = 0;
 };
 
@@ -52,12 +50,13 @@ static void cnn_free(csb_cnn* h) {
   auto F = [](void* p) { if (p) cudaFree(p); };
   F(h->params); F(h->grads); F(h->m); F(h->v); F(h->ws); F(h->zero_bias);
   for (int l = 0; l < h->n_layers; ++l) { F(h->layer[l].wt16); F(h->layer[l].wd16); }
-  F(h->x0); F(h->e); F(h->G[0]); F(h->G[1]); F(h->Z1); F(h->Z2); F(h->T); F(h->dzh); F(h->dze);
-  for (int i = 0; i < 16; ++i) { F(h->h1[i]); F(h->h2[i]); F(h->ob[i]); }
-  F(h->d_loss_w); F(h->loss_partials); F(h->d_loss);
+  F(h->x0.ptr); F(h->e.ptr); F(h->G[0].ptr); F(h->G[1].ptr); F(h->Z1.ptr); F(h->Z2.ptr); F(h->T.ptr); F(h->dzh.ptr); F(h->dze.ptr);
+  for (int i = 0; i < 16; ++i) { F(h->h1[i].ptr); F(h->h2[i].ptr); F(h->ob[i].ptr); }
+  F(h->pred); F(h->d_loss_w); F(h->loss_partials); F(h->d_loss);
 }
 
 static int cnn_repack(csb_cnn* h, cudaStream_t st) {
+  if (!h->bf16) return CSB_OK;
   simt::ConvRepackTable tab;
   tab.n = h->n_layers;
   int64_t mx = 1;
@@ -89,56 +88,96 @@ static int cnn_pad_copy(csb_cnn* h, float* padded, float* user, int dir, cudaStr
   return CSB_OK;
 }
 
-static int cnn_buf_maps(BufMaps* m, const void* buf, int Cp, int64_t rows) {
-  int rc = make_tmap_bf16(&m->k128, buf, Cp, rows, Cp, 64, 128);
+static int cnn_buf_maps(CnnBuf* b, int64_t rows) {
+  int rc = make_tmap_bf16(&b->maps.k128, b->ptr, b->Cp, rows, b->Cp, 64, 128);
   if (rc) return rc;
-  return make_tmap_bf16(&m->mn64, buf, Cp, rows, Cp, 64, 64);
+  return make_tmap_bf16(&b->maps.mn64, b->ptr, b->Cp, rows, b->Cp, 64, 64);
 }
 
 static int cnn_build_maps(csb_cnn* h, int64_t B) {
-  if (h->maps_B == B) return CSB_OK;
+  if (!h->bf16 || h->maps_B == B) return CSB_OK;
   const int64_t R = B * h->P;
   int rc;
-  if ((rc = cnn_buf_maps(&h->mx0, h->x0, h->in_p, R))) return rc;
+  CnnBuf* all[] = {&h->x0, &h->e, &h->G[0], &h->G[1], &h->Z1, &h->Z2, &h->T, &h->dzh, &h->dze};
+  for (CnnBuf* b : all) if ((rc = cnn_buf_maps(b, R))) return rc;
   for (int i = 0; i < h->depth; ++i) {
-    if ((rc = cnn_buf_maps(&h->mh1[i], h->h1[i], h->width_p, R))) return rc;
-    if ((rc = cnn_buf_maps(&h->mh2[i], h->h2[i], h->width_p, R))) return rc;
-    if ((rc = cnn_buf_maps(&h->mob[i], h->ob[i], h->width_p, R))) return rc;
+    if ((rc = cnn_buf_maps(&h->h1[i], R))) return rc;
+    if ((rc = cnn_buf_maps(&h->h2[i], R))) return rc;
+    if ((rc = cnn_buf_maps(&h->ob[i], R))) return rc;
   }
-  if ((rc = cnn_buf_maps(&h->me, h->e, h->out_p, R))) return rc;
-  for (int i = 0; i < 2; ++i) if ((rc = cnn_buf_maps(&h->mG[i], h->G[i], h->width_p, R))) return rc;
-  if ((rc = cnn_buf_maps(&h->mZ1, h->Z1, h->width_p, R))) return rc;
-  if ((rc = cnn_buf_maps(&h->mZ2, h->Z2, h->width_p, R))) return rc;
-  if ((rc = cnn_buf_maps(&h->mT, h->T, h->width_p, R))) return rc;
-  if ((rc = cnn_buf_maps(&h->mdzh, h->dzh, h->out_p, R))) return rc;
-  if ((rc = cnn_buf_maps(&h->mdze, h->dze, h->out_p, R))) return rc;
   h->maps_B = B;
   return CSB_OK;
 }
 
 // one convolution-as-GEMM launch.  `dgrad` selects the flipped/transposed weights (output width = Cinp).
-template <int EPI>
-static int cnn_gemm(csb_cnn* h, const ConvLayerInfo& li, bool dgrad, const CUtensorMap& a, const CUtensorMap* out, const CUtensorMap* saved,
-                    tc::GemmParams p, int64_t B, cudaStream_t st) {
-  p.M = (int)(B * h->P);
-  p.N = dgrad ? li.Cinp : li.Coutp;
-  p.K = li.taps * (dgrad ? li.Coutp : li.Cinp);
-  p.kb_per_tap = (dgrad ? li.Coutp : li.Cinp) / 64;
-  p.tap_center = (li.taps - 1) / 2;
-  p.halo_period = h->P;
-  int rc = launch_tn_auto<EPI>(a, dgrad ? li.tm_wd : li.tm_wt, out, saved, p, h->sm_count, st);
+//   kind 0: out = act(conv + bias)   kind 1: out = conv + bias + saved   kind 2: out = conv * act'(saved)
+static int cnn_conv(csb_cnn* h, const ConvLayerInfo& li, bool dgrad, const CnnBuf& in, CnnBuf& out, int kind, const CnnBuf* saved, int act,
+                    const float* bias, int64_t B, cudaStream_t st) {
+  const int M = (int)(B * h->P), N = dgrad ? li.Cinp : li.Coutp, Kt = dgrad ? li.Coutp : li.Cinp;
+  int rc = CSB_OK;
+  if (h->bf16) {
+    tc::GemmParams p = {};
+    p.M = M; p.N = N; p.K = li.taps * Kt; p.kb_per_tap = Kt / 64; p.tap_center = (li.taps - 1) / 2; p.halo_period = h->P;
+    p.act = act; p.head_relu_from = -1; p.bias = bias;
+    const CUtensorMap& w = dgrad ? li.tm_wd : li.tm_wt;
+    if (kind == 0) rc = launch_tn_auto<tc::EPI_BIAS_ACT>(in.maps.k128, w, &out.maps.k128, nullptr, p, h->sm_count, st);
+    else if (kind == 1) rc = launch_tn_auto<tc::EPI_BIAS_ADD>(in.maps.k128, w, &out.maps.k128, &saved->maps.k128, p, h->sm_count, st);
+    else rc = launch_tn_auto<tc::EPI_DGRAD>(in.maps.k128, w, &out.maps.k128, &saved->maps.k128, p, h->sm_count, st);
+  } else {
+    simt::SgemmParams p = {};
+    p.M = M; p.N = N; p.K = li.taps * Kt;
+    p.A = reinterpret_cast<const float*>(in.ptr); p.lda = in.Cp;
+    p.C = reinterpret_cast<float*>(out.ptr); p.ldc = out.Cp;
+    p.bias = bias; p.act = act; p.head_relu_from = -1; p.halo_period = h->P;
+    p.a_tap_k = Kt; p.tap_center = (li.taps - 1) / 2;
+    if (saved) { p.saved = reinterpret_cast<const float*>(saved->ptr); p.ld_saved = saved->Cp; }
+    dim3 grid((unsigned)(N / 64), (unsigned)ceil_div(M, 64));
+    if (!dgrad) {
+      p.B = h->params + li.w_off; p.ldb = li.Coutp;               // W [taps*Cinp, Coutp]
+      if (kind == 0) simt::sgemm_kernel<false, false, simt::SEPI_BIAS_ACT><<<grid, 256, 0, st>>>(p);
+      else if (kind == 1) simt::sgemm_kernel<false, false, simt::SEPI_BIAS_ADD><<<grid, 256, 0, st>>>(p);
+      else simt::sgemm_kernel<false, false, simt::SEPI_DGRAD><<<grid, 256, 0, st>>>(p);
+    } else {
+      p.B = h->params + li.w_off; p.ldb = li.Coutp;               // W[t][ci][co] read as B'[ci][(taps-1-t', co)]
+      p.b_tap_k = li.Coutp; p.b_tap_rows = li.Cinp; p.taps = li.taps;
+      if (kind == 0) simt::sgemm_kernel<false, true, simt::SEPI_BIAS_ACT><<<grid, 256, 0, st>>>(p);
+      else if (kind == 1) simt::sgemm_kernel<false, true, simt::SEPI_BIAS_ADD><<<grid, 256, 0, st>>>(p);
+      else simt::sgemm_kernel<false, true, simt::SEPI_DGRAD><<<grid, 256, 0, st>>>(p);
+    }
+    if (cudaGetLastError() != cudaSuccess) { set_last_error("sgemm launch failed"); rc = CSB_ECUDA; }
+  }
   if (rc) return rc;
   h->launches++;
   return CSB_OK;
 }
 
 // weight (+ bias) gradient of one conv layer: in [R, Cinp], dz [R, Coutp]
-static int cnn_wgrad(csb_cnn* h, const ConvLayerInfo& li, const BufMaps& in, const BufMaps& dz, int64_t B, simt::SegmentTable& tab,
+static int cnn_wgrad(csb_cnn* h, const ConvLayerInfo& li, const CnnBuf& in, const CnnBuf& dz, int64_t B, simt::SegmentTable& tab,
                      int64_t& max_len, cudaStream_t st) {
   const int64_t R = B * h->P;
+  const size_t tap_elems = (size_t)li.Cinp * li.Coutp;
+  if (!h->bf16) {
+    for (int t = 0; t < li.taps; ++t) {                       // straight into the gradient buffer: no split, no partials
+      simt::SgemmParams p = {};
+      p.M = li.Cinp; p.N = li.Coutp; p.K = (int)R;
+      p.A = reinterpret_cast<const float*>(in.ptr); p.lda = in.Cp; p.a_row_off = t - (li.taps - 1) / 2;
+      p.B = reinterpret_cast<const float*>(dz.ptr); p.ldb = dz.Cp;
+      p.C = h->grads + li.w_off + (size_t)t * tap_elems; p.ldc = li.Coutp;
+      dim3 grid((unsigned)(li.Coutp / 64), (unsigned)(li.Cinp / 64));
+      simt::sgemm_kernel<true, false, simt::SEPI_STORE><<<grid, 256, 0, st>>>(p);
+      CSB_CUDA_CHECK(cudaGetLastError());
+      h->launches++;
+    }
+    const int S = (int)std::max<int64_t>(1, std::min<int64_t>(li.max_splits, ceil_div(R, 256)));
+    dim3 grid((unsigned)(li.Coutp / 64), (unsigned)S);
+    simt::colsum_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(dz.ptr), dz.Cp, R, h->ws + li.ws_b_off, (size_t)li.Coutp);
+    CSB_CUDA_CHECK(cudaGetLastError());
+    h->launches++;
+    tab.seg[tab.n++] = {h->ws + li.ws_b_off, (size_t)li.Coutp, h->grads + li.b_off, (int64_t)li.Coutp, S};
+    return CSB_OK;
+  }
   const int num_rb = (int)ceil_div(R, 64);
   int splits = std::max(1, std::min(li.max_splits, num_rb));
-  const size_t tap_elems = (size_t)li.Cinp * li.Coutp;
   for (int t = 0; t < li.taps; ++t) {
     tc::NtParams p = {};
     p.M = li.Cinp; p.N = li.Coutp; p.R = (int)R;
@@ -147,7 +186,7 @@ static int cnn_wgrad(csb_cnn* h, const ConvLayerInfo& li, const BufMaps& in, con
     p.out = h->ws + li.ws_w_off + (size_t)t * tap_elems; p.ld_out = li.Coutp; p.split_stride = (size_t)li.taps * tap_elems;
     p.a_row_offset = t - (li.taps - 1) / 2;
     if (t == 0) { p.colsum_out = h->ws + li.ws_b_off; p.colsum_stride = (size_t)li.Coutp; }
-    int rc = launch_nt_auto(in.mn64, dz.mn64, p, eff, st);
+    int rc = launch_nt_auto(in.maps.mn64, dz.maps.mn64, p, eff, st);
     if (rc) return rc;
     h->launches++;
     splits = eff;
@@ -160,26 +199,38 @@ static int cnn_wgrad(csb_cnn* h, const ConvLayerInfo& li, const BufMaps& in, con
 
 static int cnn_forward_body(csb_cnn* h, const float* x, int64_t B, cudaStream_t st) {
   const int64_t R = B * h->P;
-  simt::cnn_pack_input_kernel<<<grid_for(R * h->in_p, 256, h->sm_count), 256, 0, st>>>(x, h->x0, B, h->L, h->in_ch, h->in_p);
+  if (h->bf16) simt::cnn_pack_input_kernel<<<grid_for(R * h->in_p, 256, h->sm_count), 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(h->x0.ptr), B, h->L, h->in_ch, h->in_p);
+  else simt::cnn_pack_input_f32_kernel<<<grid_for(R * h->in_p, 256, h->sm_count), 256, 0, st>>>(x, reinterpret_cast<float*>(h->x0.ptr), B, h->L, h->in_ch, h->in_p);
   CSB_CUDA_CHECK(cudaGetLastError());
   h->launches++;
-  const BufMaps* xin = &h->mx0;
+  const CnnBuf* xin = &h->x0;
   int rc;
   for (int i = 0; i < h->depth; ++i) {
     const ConvLayerInfo &c1 = h->layer[3 * i], &c2 = h->layer[3 * i + 1], &cr = h->layer[3 * i + 2];
-    tc::GemmParams p = {};
-    p.act = c1.act; p.head_relu_from = -1; p.bias = h->params + c1.b_off;
-    if ((rc = cnn_gemm<tc::EPI_BIAS_ACT>(h, c1, false, xin->k128, &h->mh1[i].k128, nullptr, p, B, st))) return rc;
-    p.act = c2.act; p.bias = h->params + c2.b_off;
-    if ((rc = cnn_gemm<tc::EPI_BIAS_ACT>(h, c2, false, h->mh1[i].k128, &h->mh2[i].k128, nullptr, p, B, st))) return rc;
-    p.act = CSB_ACT_NONE; p.bias = h->params + cr.b_off;          // out = conv1x1(x_in) + b + relu(conv2)
-    if ((rc = cnn_gemm<tc::EPI_BIAS_ADD>(h, cr, false, xin->k128, &h->mob[i].k128, &h->mh2[i].k128, p, B, st))) return rc;
-    xin = &h->mob[i];
+    if ((rc = cnn_conv(h, c1, false, *xin, h->h1[i], 0, nullptr, c1.act, h->params + c1.b_off, B, st))) return rc;
+    if ((rc = cnn_conv(h, c2, false, h->h1[i], h->h2[i], 0, nullptr, c2.act, h->params + c2.b_off, B, st))) return rc;
+    // out = conv1x1(x_in) + b + relu(conv2)
+    if ((rc = cnn_conv(h, cr, false, *xin, h->ob[i], 1, &h->h2[i], CSB_ACT_NONE, h->params + cr.b_off, B, st))) return rc;
+    xin = &h->ob[i];
   }
   const ConvLayerInfo& co = h->layer[3 * h->depth];
-  tc::GemmParams p = {};
-  p.act = co.act; p.head_relu_from = -1; p.bias = h->params + co.b_off;
-  return cnn_gemm<tc::EPI_BIAS_ACT>(h, co, false, xin->k128, &h->me.k128, nullptr, p, B, st);
+  return cnn_conv(h, co, false, *xin, h->e, 0, nullptr, co.act, h->params + co.b_off, B, st);
+}
+
+// fp32 mode: head GEMM -> pred (halo layout, fp32)
+static int cnn_head_f32(csb_cnn* h, int64_t B, cudaStream_t st) {
+  const ConvLayerInfo& cd = h->layer[3 * h->depth + 1];
+  simt::SgemmParams p = {};
+  p.M = (int)(B * h->P); p.N = cd.Coutp; p.K = cd.Cinp;
+  p.A = reinterpret_cast<const float*>(h->e.ptr); p.lda = h->e.Cp;
+  p.B = h->params + cd.w_off; p.ldb = cd.Coutp;
+  p.C = h->pred; p.ldc = h->out_p;
+  p.bias = h->params + cd.b_off; p.act = CSB_ACT_NONE; p.head_relu_from = h->out_lin; p.halo_period = h->P;
+  dim3 grid((unsigned)(cd.Coutp / 64), (unsigned)ceil_div(p.M, 64));
+  simt::sgemm_kernel<false, false, simt::SEPI_BIAS_ACT><<<grid, 256, 0, st>>>(p);
+  CSB_CUDA_CHECK(cudaGetLastError());
+  h->launches++;
+  return CSB_OK;
 }
 
 extern "C" {
@@ -191,7 +242,7 @@ int csb_cnn_create(const csb_cnn_cfg* cfg, csb_cnn** out) {
   CSB_REQUIRE(cfg->kernel == 3 || cfg->kernel == 1, CSB_EINVAL, "kernel width must be 1 or 3");
   CSB_REQUIRE(cfg->width >= 1 && cfg->in_ch >= 1 && cfg->out_ch >= 1 && cfg->out_lin >= 0 && cfg->out_lin <= cfg->out_ch, CSB_EINVAL, "bad channel configuration");
   CSB_REQUIRE(cfg->levels >= 1 && cfg->max_batch >= 1, CSB_EINVAL, "levels / max_batch must be positive");
-  CSB_REQUIRE(cfg->dtype == CSB_BF16, CSB_EUNSUPPORTED, "the CNN engine implements the CSB_BF16 mode only");
+  CSB_REQUIRE(cfg->dtype == CSB_BF16 || cfg->dtype == CSB_F32, CSB_EINVAL, "unknown dtype %d", cfg->dtype);
   CSB_REQUIRE(cfg->loss == CSB_LOSS_MSE || cfg->loss == CSB_LOSS_MAE, CSB_EINVAL, "unknown loss %d", cfg->loss);
   int sm = 0, maj = 0, mnr = 0;
   int rc = csb_device_info(&sm, &maj, &mnr, nullptr);
@@ -207,6 +258,7 @@ int csb_cnn_create(const csb_cnn_cfg* cfg, csb_cnn** out) {
   h->width = cfg->width; h->width_p = (int)round_up(cfg->width, 64);
   h->out_ch = cfg->out_ch; h->out_p = (int)round_up(cfg->out_ch, 64); h->out_lin = cfg->out_lin;
   h->sm_count = sm;
+  h->bf16 = cfg->dtype == CSB_BF16;
   h->cap = round_up(cfg->max_batch * h->P, 128);
   h->n_layers = 3 * h->depth + 2;
   size_t off = 0, off_user = 0, ws_off = 0;
@@ -218,8 +270,8 @@ int csb_cnn_create(const csb_cnn_cfg* cfg, csb_cnn** out) {
     li.w_off_user = off_user; off_user += (size_t)taps * cin * cout;
     li.b_off_user = off_user; off_user += (size_t)cout;
     const int tiles = (int)(ceil_div(li.Cinp, 128) * ceil_div(li.Coutp, tn_block_n(li.Coutp)));
-    li.max_splits = std::max(1, std::min(64, sm / tiles));
-    li.ws_w_off = ws_off; ws_off += (size_t)li.max_splits * taps * li.Cinp * li.Coutp;
+    li.max_splits = h->bf16 ? std::max(1, std::min(64, sm / tiles)) : 32;
+    li.ws_w_off = ws_off; if (h->bf16) ws_off += (size_t)li.max_splits * taps * li.Cinp * li.Coutp;   // fp32 mode writes dW directly
     li.ws_b_off = ws_off; ws_off += (size_t)li.max_splits * ceil_div(li.Cinp, 128) * li.Coutp;
   };
   int c = cfg->in_ch;
@@ -237,22 +289,26 @@ int csb_cnn_create(const csb_cnn_cfg* cfg, csb_cnn** out) {
   CKA(h->params, h->P_pad * 4); CKA(h->grads, h->P_pad * 4); CKA(h->m, h->P_pad * 4); CKA(h->v, h->P_pad * 4);
   CKA(h->ws, h->ws_elems * 4);
   CKA(h->zero_bias, (size_t)std::max(h->width_p, h->out_p) * 4);
-  const size_t wide = (size_t)h->cap * h->width_p * 2, narrow = (size_t)h->cap * h->out_p * 2;
-  CKA(h->x0, (size_t)h->cap * h->in_p * 2);
-  for (int i = 0; i < h->depth; ++i) { CKA(h->h1[i], wide); CKA(h->h2[i], wide); CKA(h->ob[i], wide); }
-  CKA(h->e, narrow); CKA(h->dzh, narrow); CKA(h->dze, narrow);
-  CKA(h->G[0], wide); CKA(h->G[1], wide); CKA(h->Z1, wide); CKA(h->Z2, wide); CKA(h->T, wide);
+  const size_t es = h->bf16 ? 2 : 4;
+  auto mk = [&](CnnBuf& b, int Cp) -> int { b.Cp = Cp; CSB_ALLOC(b.ptr, (size_t)h->cap * Cp * es); return CSB_OK; };
+#define CKB(buf, Cp) do { int _rc = mk(buf, Cp); if (_rc) { cnn_free(h); delete h; return _rc; } } while (0)
+  CKB(h->x0, h->in_p);
+  for (int i = 0; i < h->depth; ++i) { CKB(h->h1[i], h->width_p); CKB(h->h2[i], h->width_p); CKB(h->ob[i], h->width_p); }
+  CKB(h->e, h->out_p); CKB(h->dzh, h->out_p); CKB(h->dze, h->out_p);
+  CKB(h->G[0], h->width_p); CKB(h->G[1], h->width_p); CKB(h->Z1, h->width_p); CKB(h->Z2, h->width_p); CKB(h->T, h->width_p);
+#undef CKB
+  if (!h->bf16) CKA(h->pred, (size_t)h->cap * h->out_p * 4);
   CKA(h->d_loss_w, (size_t)h->out_p * 4);
-  h->n_loss_partials = (int)(h->cap / 128 * tc::TN_EPI_WARPS);
+  h->n_loss_partials = (int)std::max<int64_t>(h->cap / 128 * tc::TN_EPI_WARPS, 8 * sm);
   CKA(h->loss_partials, (size_t)h->n_loss_partials * 4);
   CKA(h->d_loss, 4);
-  for (int l = 0; l < h->n_layers; ++l) {
+  for (int l = 0; l < h->n_layers && h->bf16; ++l) {
     ConvLayerInfo& li = h->layer[l];
     const size_t n = (size_t)li.taps * li.Cinp * li.Coutp;
     CKA(li.wt16, n * 2); CKA(li.wd16, n * 2);
   }
 #undef CKA
-  for (int l = 0; l < h->n_layers; ++l) {
+  for (int l = 0; l < h->n_layers && h->bf16; ++l) {
     ConvLayerInfo& li = h->layer[l];
     rc = make_tmap_bf16(&li.tm_wt, li.wt16, (uint64_t)li.taps * li.Cinp, li.Coutp, (uint64_t)li.taps * li.Cinp, 64, (uint32_t)tn_b_box_rows(li.Coutp));
     if (!rc) rc = make_tmap_bf16(&li.tm_wd, li.wd16, (uint64_t)li.taps * li.Coutp, li.Cinp, (uint64_t)li.taps * li.Coutp, 64, (uint32_t)tn_b_box_rows(li.Cinp));
@@ -333,10 +389,21 @@ int csb_cnn_forward(csb_cnn* h, const float* x, float* y_pred, int64_t B, void* 
   if ((rc = cnn_build_maps(h, B))) return rc;
   if ((rc = cnn_forward_body(h, x, B, st))) return rc;
   const ConvLayerInfo& cd = h->layer[3 * h->depth + 1];
+  if (!h->bf16) {
+    if ((rc = cnn_head_f32(h, B, st))) return rc;
+    simt::cnn_unpack_output_kernel<<<grid_for(B * h->L * h->out_ch, 256, h->sm_count), 256, 0, st>>>(h->pred, h->out_p, y_pred, B, h->L, h->out_ch);
+    CSB_CUDA_CHECK(cudaGetLastError());
+    h->launches++;
+    return CSB_OK;
+  }
   tc::GemmParams p = {};
+  p.M = (int)(B * h->P); p.N = cd.Coutp; p.K = cd.Cinp; p.halo_period = h->P;
   p.act = CSB_ACT_NONE; p.head_relu_from = h->out_lin; p.bias = h->params + cd.b_off;
   p.out_dim = h->out_ch; p.pred = y_pred; p.ld_pred = h->out_ch;
-  return cnn_gemm<tc::EPI_HEAD_OUT>(h, cd, false, h->me.k128, nullptr, nullptr, p, B, st);
+  rc = launch_tn_auto<tc::EPI_HEAD_OUT>(h->e.maps.k128, cd.tm_wt, nullptr, nullptr, p, h->sm_count, st);
+  if (rc) return rc;
+  h->launches++;
+  return CSB_OK;
 }
 
 int csb_cnn_train_step(csb_cnn* h, const float* x, const float* y, int64_t B, float grad_scale, float* loss_out, void* stream) {
@@ -351,16 +418,27 @@ int csb_cnn_train_step(csb_cnn* h, const float* x, const float* y, int64_t B, fl
   const ConvLayerInfo &co = h->layer[3 * D], &cd = h->layer[3 * D + 1];
   const int64_t R = B * h->P;
   // ---- head + loss: dzh = dL/dz of the fused Dense heads
-  {
+  if (h->bf16) {
     tc::GemmParams p = {};
+    p.M = (int)R; p.N = cd.Coutp; p.K = cd.Cinp; p.halo_period = h->P;
     p.act = CSB_ACT_NONE; p.head_relu_from = h->out_lin; p.bias = h->params + cd.b_off; p.out_dim = h->out_ch;
     p.y = y; p.ld_y = h->out_ch; p.loss_w = h->d_loss_w; p.grad_scale = grad_scale; p.loss_kind = h->cfg.loss;
     p.loss_partials = h->loss_partials;
-    if ((rc = cnn_gemm<tc::EPI_HEAD_LOSS>(h, cd, false, h->me.k128, &h->mdzh.k128, nullptr, p, B, st))) return rc;
+    if ((rc = launch_tn_auto<tc::EPI_HEAD_LOSS>(h->e.maps.k128, cd.tm_wt, &h->dzh.maps.k128, nullptr, p, h->sm_count, st))) return rc;
+    h->launches++;
     simt::loss_finalize_kernel<<<1, 256, 0, st>>>(h->loss_partials, (int)ceil_div(R, 128) * tc::TN_EPI_WARPS, loss_out ? loss_out : h->d_loss);
+  } else {
+    if ((rc = cnn_head_f32(h, B, st))) return rc;
+    const int grid = std::min(h->n_loss_partials, grid_for(R * h->out_p, 256, h->sm_count));
+    simt::head_grad_kernel<float><<<grid, 256, 0, st>>>(h->pred, h->out_p, y, h->out_ch, h->d_loss_w, grad_scale, h->cfg.loss, 0, CSB_ACT_NONE, 0.f,
+                                                        h->out_lin, nullptr, reinterpret_cast<float*>(h->dzh.ptr), h->out_p, R, h->out_ch, h->out_p,
+                                                        h->loss_partials, h->P);
     CSB_CUDA_CHECK(cudaGetLastError());
     h->launches++;
+    simt::loss_finalize_kernel<<<1, 256, 0, st>>>(h->loss_partials, grid, loss_out ? loss_out : h->d_loss);
   }
+  CSB_CUDA_CHECK(cudaGetLastError());
+  h->launches++;
   simt::SegmentTable tab;
   tab.n = 0;
   int64_t max_len = 4;
@@ -373,43 +451,35 @@ int csb_cnn_train_step(csb_cnn* h, const float* x, const float* y, int64_t B, fl
     tab.n = 0; max_len = 4;
     return CSB_OK;
   };
+  auto act_mask = [&](const CnnBuf& g, const CnnBuf& a, CnnBuf& dz, int act) -> int {
+    const int64_t n = R * g.Cp;
+    if (h->bf16) simt::act_mask_bf16_kernel<<<grid_for(n / 8, 256, h->sm_count), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g.ptr), reinterpret_cast<const __nv_bfloat16*>(a.ptr), reinterpret_cast<__nv_bfloat16*>(dz.ptr), n / 8, act, 0.f);
+    else simt::act_mask_f32_kernel<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(reinterpret_cast<const float*>(g.ptr), reinterpret_cast<const float*>(a.ptr), reinterpret_cast<float*>(dz.ptr), n, act, 0.f);
+    CSB_CUDA_CHECK(cudaGetLastError());
+    h->launches++;
+    return CSB_OK;
+  };
   // ---- Dense heads and the 1x1 output convolution
-  if ((rc = cnn_wgrad(h, cd, h->me, h->mdzh, B, tab, max_len, st))) return rc;
-  {
-    tc::GemmParams p = {};
-    p.act = co.act; p.head_relu_from = -1;                    // dze = (dzh . Wd^T) * elu'(e)
-    if ((rc = cnn_gemm<tc::EPI_DGRAD>(h, cd, true, h->mdzh.k128, &h->mdze.k128, &h->me.k128, p, B, st))) return rc;
-  }
-  const BufMaps* last_out = D > 0 ? &h->mob[D - 1] : &h->mx0;
-  if ((rc = cnn_wgrad(h, co, *last_out, h->mdze, B, tab, max_len, st))) return rc;
+  if ((rc = cnn_wgrad(h, cd, h->e, h->dzh, B, tab, max_len, st))) return rc;
+  if ((rc = cnn_conv(h, cd, true, h->dzh, h->dze, 2, &h->e, co.act, nullptr, B, st))) return rc;            // dze = (dzh . Wd^T) * elu'(e)
+  const CnnBuf& last_out = D > 0 ? h->ob[D - 1] : h->x0;
+  if ((rc = cnn_wgrad(h, co, last_out, h->dze, B, tab, max_len, st))) return rc;
   int g = 0;
-  {
-    tc::GemmParams p = {};
-    p.act = CSB_ACT_NONE; p.head_relu_from = -1; p.bias = h->zero_bias;   // d(block output): no activation after the residual add
-    if ((rc = cnn_gemm<tc::EPI_BIAS_ACT>(h, co, true, h->mdze.k128, &h->mG[g].k128, nullptr, p, B, st))) return rc;
-  }
+  // d(block output): no activation after the residual add
+  if ((rc = cnn_conv(h, co, true, h->dze, h->G[g], 0, nullptr, CSB_ACT_NONE, h->zero_bias, B, st))) return rc;
   // ---- residual blocks, last to first.  G[g] holds dL/d(block output).
   for (int i = D - 1; i >= 0; --i) {
     const ConvLayerInfo &c1 = h->layer[3 * i], &c2 = h->layer[3 * i + 1], &cr = h->layer[3 * i + 2];
-    const BufMaps& xin = i > 0 ? h->mob[i - 1] : h->mx0;
-    // dz2 = d_out * relu'(h2)
-    simt::act_mask_bf16_kernel<<<grid_for(R * h->width_p / 8, 256, h->sm_count), 256, 0, st>>>(h->G[g], h->h2[i], h->Z2, R * h->width_p / 8, c2.act, 0.f);
-    CSB_CUDA_CHECK(cudaGetLastError());
-    h->launches++;
-    if ((rc = cnn_wgrad(h, cr, xin, h->mG[g], B, tab, max_len, st))) return rc;       // residual 1x1: dW = xin^T d_out
-    if ((rc = cnn_wgrad(h, c2, h->mh1[i], h->mZ2, B, tab, max_len, st))) return rc;
-    {
-      tc::GemmParams p = {};
-      p.act = c1.act; p.head_relu_from = -1;                  // dz1 = conv^T(dz2; W2) * relu'(h1)
-      if ((rc = cnn_gemm<tc::EPI_DGRAD>(h, c2, true, h->mZ2.k128, &h->mZ1.k128, &h->mh1[i].k128, p, B, st))) return rc;
-    }
-    if ((rc = cnn_wgrad(h, c1, xin, h->mZ1, B, tab, max_len, st))) return rc;
+    const CnnBuf& xin = i > 0 ? h->ob[i - 1] : h->x0;
+    if ((rc = act_mask(h->G[g], h->h2[i], h->Z2, c2.act))) return rc;                                       // dz2 = d_out * relu'(h2)
+    if ((rc = cnn_wgrad(h, cr, xin, h->G[g], B, tab, max_len, st))) return rc;                               // residual 1x1: dW = xin^T d_out
+    if ((rc = cnn_wgrad(h, c2, h->h1[i], h->Z2, B, tab, max_len, st))) return rc;
+    if ((rc = cnn_conv(h, c2, true, h->Z2, h->Z1, 2, &h->h1[i], c1.act, nullptr, B, st))) return rc;       // dz1 = conv^T(dz2; W2) * relu'(h1)
+    if ((rc = cnn_wgrad(h, c1, xin, h->Z1, B, tab, max_len, st))) return rc;
     if (i > 0) {
-      tc::GemmParams p = {};
-      p.act = CSB_ACT_NONE; p.head_relu_from = -1; p.bias = h->zero_bias;
       // d(x_in) = conv^T(dz1; W1) + conv1x1^T(d_out; Wr)
-      if ((rc = cnn_gemm<tc::EPI_BIAS_ACT>(h, c1, true, h->mZ1.k128, &h->mT.k128, nullptr, p, B, st))) return rc;
-      if ((rc = cnn_gemm<tc::EPI_BIAS_ADD>(h, cr, true, h->mG[g].k128, &h->mG[g ^ 1].k128, &h->mT.k128, p, B, st))) return rc;
+      if ((rc = cnn_conv(h, c1, true, h->Z1, h->T, 0, nullptr, CSB_ACT_NONE, h->zero_bias, B, st))) return rc;
+      if ((rc = cnn_conv(h, cr, true, h->G[g], h->G[g ^ 1], 1, &h->T, CSB_ACT_NONE, h->zero_bias, B, st))) return rc;
       g ^= 1;
     }
     if (tab.n + 8 > (int)(sizeof(tab.seg) / sizeof(tab.seg[0]))) { if ((rc = flush_reduce())) return rc; }

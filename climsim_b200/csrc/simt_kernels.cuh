@@ -66,7 +66,7 @@ normalize_bf16_vec4_kernel(const float* __restrict__ x, const float* __restrict_
 // N and the contiguous feature dimensions are multiples of 64 (padded layout); M (and K when it is the batch) may be
 // ragged and is bounds-checked.
 // ---------------------------------------------------------------------------------------------------------------
-enum SEpi : int { SEPI_STORE = 0, SEPI_BIAS_ACT = 1, SEPI_DGRAD = 2 };
+enum SEpi : int { SEPI_STORE = 0, SEPI_BIAS_ACT = 1, SEPI_DGRAD = 2, SEPI_BIAS_ADD = 3 };
 
 struct SgemmParams {
   int M, N, K;
@@ -75,7 +75,14 @@ struct SgemmParams {
   float* C; int ldc;
   const float* bias;          // SEPI_BIAS_ACT
   int act; float alpha; int head_relu_from;
-  const float* saved; int ld_saved;   // SEPI_DGRAD
+  const float* saved; int ld_saved;   // SEPI_DGRAD (act' of the saved activation) / SEPI_BIAS_ADD (tile to add)
+  // Conv1D('same') over the halo-padded channels-last layout (see cnn_engine.cuh):
+  int a_tap_k;       // !TA: contraction index k = t*a_tap_k + c reads A row (m + t - tap_center), column c.   0 = plain GEMM
+  int tap_center;
+  int b_tap_k;       // TB: contraction index k = t*b_tap_k + c reads B[((taps-1-t)*b_tap_rows + n) * ldb + c]  (flipped, transposed taps)
+  int b_tap_rows, taps;
+  int a_row_off;     // TA: A stored [K rows, M]: row k + a_row_off (rows outside [0, K) read as zero)
+  int halo_period;   // rows r with r % halo_period in {0, halo_period-1} are written as zeros
 };
 
 template <bool TA, bool TB, int EPI>
@@ -93,8 +100,10 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmParams p) {
     if constexpr (!TA) {
       const int r = tid >> 2, kq = (tid & 3) * 4;          // 64 rows x 4 float4
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m0 + r < p.M) {
-        const float* src = p.A + (size_t)(m0 + r) * p.lda + k0 + kq;
+      int arow = m0 + r, acol = k0 + kq;
+      if (p.a_tap_k > 0) { const int t = acol / p.a_tap_k; acol -= t * p.a_tap_k; arow += t - p.tap_center; }
+      if (m0 + r < p.M && arow >= 0 && arow < p.M) {
+        const float* src = p.A + (size_t)arow * p.lda + acol;
         if (k0 + kq + 3 < p.K) v = *reinterpret_cast<const float4*>(src);
         else { float t[4] = {0, 0, 0, 0}; for (int i = 0; i < 4; ++i) if (k0 + kq + i < p.K) t[i] = src[i]; v = make_float4(t[0], t[1], t[2], t[3]); }
       }
@@ -102,8 +111,9 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmParams p) {
     } else {
       const int k = tid >> 4, mq = (tid & 15) * 4;         // 16 k-rows x 16 float4
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k0 + k < p.K) {
-        const float* src = p.A + (size_t)(k0 + k) * p.lda + m0 + mq;
+      const int krow = k0 + k + p.a_row_off;
+      if (k0 + k < p.K && krow >= 0 && krow < p.K) {
+        const float* src = p.A + (size_t)krow * p.lda + m0 + mq;
         if (m0 + mq + 3 < p.M) v = *reinterpret_cast<const float4*>(src);
         else { float t[4] = {0, 0, 0, 0}; for (int i = 0; i < 4; ++i) if (m0 + mq + i < p.M) t[i] = src[i]; v = make_float4(t[0], t[1], t[2], t[3]); }
       }
@@ -119,6 +129,10 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmParams p) {
       const int r = tid >> 2, kq = (tid & 3) * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       const float* src = p.B + (size_t)(n0 + r) * p.ldb + k0 + kq;
+      if (p.b_tap_k > 0) {
+        const int t = (k0 + kq) / p.b_tap_k;
+        src = p.B + ((size_t)(p.taps - 1 - t) * p.b_tap_rows + n0 + r) * p.ldb + (k0 + kq - t * p.b_tap_k);
+      }
       if (k0 + kq + 3 < p.K) v = *reinterpret_cast<const float4*>(src);
       else { float t[4] = {0, 0, 0, 0}; for (int i = 0; i < 4; ++i) if (k0 + kq + i < p.K) t[i] = src[i]; v = make_float4(t[0], t[1], t[2], t[3]); }
       Bs[kq + 0][r] = v.x; Bs[kq + 1][r] = v.y; Bs[kq + 2][r] = v.z; Bs[kq + 3][r] = v.w;
@@ -156,6 +170,13 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmParams p) {
       v[1] *= act_bwd_from_out(p.act, p.alpha, a.y);
       v[2] *= act_bwd_from_out(p.act, p.alpha, a.z);
       v[3] *= act_bwd_from_out(p.act, p.alpha, a.w);
+    } else if constexpr (EPI == SEPI_BIAS_ADD) {
+      const float4 a = *reinterpret_cast<const float4*>(p.saved + (size_t)r * p.ld_saved + c);
+      v[0] += p.bias[c] + a.x; v[1] += p.bias[c + 1] + a.y; v[2] += p.bias[c + 2] + a.z; v[3] += p.bias[c + 3] + a.w;
+    }
+    if (p.halo_period > 0) {
+      const int rr = r % p.halo_period;
+      if (rr == 0 || rr == p.halo_period - 1) { v[0] = v[1] = v[2] = v[3] = 0.f; }
     }
     *reinterpret_cast<float4*>(p.C + (size_t)r * p.ldc + c) = make_float4(v[0], v[1], v[2], v[3]);
   }
@@ -177,20 +198,27 @@ __global__ void __launch_bounds__(256)
 head_grad_kernel(const float* __restrict__ pred, int ldp, const float* __restrict__ y_or_dy, int ldy,
                  const float* __restrict__ w, float scale, int loss_kind, int mode, int act, float alpha,
                  int head_relu_from, const float* __restrict__ out_mask, TZ* __restrict__ dz, int ldz,
-                 int64_t M, int out_dim, int Np, float* __restrict__ loss_partials) {
+                 int64_t M, int out_dim, int Np, float* __restrict__ loss_partials, int halo_period = 0) {
   float lacc = 0.f;
   const int64_t total = M * Np;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / Np;
     const int c = (int)(i - r * Np);
     float g = 0.f;
-    if (c < out_dim) {
+    bool interior = true;
+    int64_t yr = r;                                         // row of the (halo-free) target / upstream-gradient array
+    if (halo_period > 0) {
+      const int rr = (int)(r % halo_period);
+      interior = rr != 0 && rr != halo_period - 1;
+      yr = (r / halo_period) * (halo_period - 2) + rr - 1;
+    }
+    if (c < out_dim && interior) {
       const float pv = pred[r * ldp + c];                 // already masked by the forward pass
       const bool relu_col = head_relu_from >= 0 && c >= head_relu_from;
       float dact = relu_col ? (pv > 0.f ? 1.f : 0.f) : act_bwd_from_out(act, alpha, pv);
       if (out_mask != nullptr) dact *= out_mask[c];
       if (mode == 0) {
-        const float d = pv - y_or_dy[r * ldy + c];
+        const float d = pv - y_or_dy[yr * ldy + c];
         if (loss_kind == CSB_LOSS_MSE) { lacc += w[c] * d * d; g = 2.f * w[c] * d * scale * dact; }
         else if (loss_kind == CSB_LOSS_HUBER) {
           const float ad = fabsf(d);
@@ -199,7 +227,7 @@ head_grad_kernel(const float* __restrict__ pred, int ldp, const float* __restric
         }
         else { lacc += w[c] * fabsf(d); g = w[c] * scale * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * dact; }
       } else {
-        g = y_or_dy[r * ldy + c] * dact;
+        g = y_or_dy[yr * ldy + c] * dact;
       }
     }
     store_dz<TZ>(dz + r * ldz + c, g);
@@ -551,6 +579,35 @@ cnn_pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ o
     out[i] = __float2bfloat16_rn(v);
   }
 }
+// fp32 variants for the CSB_F32 parity mode
+__global__ void __launch_bounds__(256)
+cnn_pack_input_f32_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t B, int L, int C, int Cp) {
+  const int64_t total = B * (L + 2) * Cp;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cp);
+    const int64_t r = i / Cp;
+    const int l = (int)(r % (L + 2)) - 1;
+    const int64_t b = r / (L + 2);
+    out[i] = (c < C && l >= 0 && l < L) ? x[(b * L + l) * C + c] : 0.f;
+  }
+}
+__global__ void __launch_bounds__(256)
+act_mask_f32_kernel(const float* __restrict__ g, const float* __restrict__ a, float* __restrict__ dz, int64_t n, int act, float alpha) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dz[i] = g[i] * act_bwd_from_out(act, alpha, a[i]);
+}
+// pred [B*(L+2), ld] (halo layout) -> y (B, L, C)
+__global__ void __launch_bounds__(256)
+cnn_unpack_output_kernel(const float* __restrict__ pred, int ld, float* __restrict__ y, int64_t B, int L, int C) {
+  const int64_t total = B * L * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int l = (int)((i / C) % L);
+    const int64_t b = i / ((int64_t)C * L);
+    y[i] = pred[(b * (L + 2) + l + 1) * ld + c];
+  }
+}
+
 // dz = g * act'(a) element-wise (bf16, 8 elements per thread)
 __global__ void __launch_bounds__(256)
 act_mask_bf16_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ dz,

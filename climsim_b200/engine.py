@@ -264,10 +264,12 @@ class CNNEngine:
     Tensors are channels-last: x (B, 60, 6), y / predictions (B, 60, 10)."""
 
     def __init__(self, depth: int = 12, width: int = 406, kernel: int = 3, in_ch: int = 6, out_ch: int = 10, out_lin: int = 2,
-                 levels: int = 60, act: str = "relu", pre_out_act: str = "elu", loss: str = "mae", max_batch: int = 4096):
+                 levels: int = 60, act: str = "relu", pre_out_act: str = "elu", loss: str = "mae", max_batch: int = 4096,
+                 dtype: str = "bf16"):
         self.lib = _lib.load()
         cfg = _lib.CnnCfg(depth, width, kernel, in_ch, out_ch, out_lin, levels, _lib.ACT[act], _lib.ACT[pre_out_act],
-                          _lib.DTYPE["bf16"], _lib.LOSS[loss], max_batch)
+                          _lib.DTYPE[dtype], _lib.LOSS[loss], max_batch)
+        self.dtype = dtype
         self._h = C.c_void_p()
         _lib.check(self.lib.csb_cnn_create(C.byref(cfg), C.byref(self._h)), "csb_cnn_create")
         self.depth, self.width, self.kernel, self.in_ch, self.out_ch, self.out_lin, self.levels = depth, width, kernel, in_ch, out_ch, out_lin, levels

@@ -1,7 +1,10 @@
 """GPU parity of the CNN engine (ResNet-1D, Conv1D as row-shifted tcgen05 GEMMs over a halo-padded channels-last layout)
 against the CPU oracle ``CNNRef`` (restatement of baseline_models/CNN/training/hpo_train.py:131-200; PARITY UNPINNED: no
-tensorflow here).  Only the CSB_BF16 mode exists for the CNN, so tolerances are the bf16 ones: outputs within 3e-2 of the
-output scale, loss within 2e-2, every gradient tensor within 0.12 relative L2 of the fp32 oracle's autograd."""
+tensorflow here).
+  * CSB_F32 mode: outputs, loss and every gradient tensor within 1e-5 * max|ref| of the fp32 oracle (north_star's bar); MSE loss
+    only for gradients, because d|e|/de jumps at e = 0 exactly like ReLU' (the MAE path is covered by the loss value).
+  * CSB_BF16 mode: outputs within 3e-2 of the output scale, loss within 2e-2, every gradient tensor within 0.12 (MSE) / 0.2 (MAE)
+    relative L2 of the fp32 oracle's autograd."""
 import numpy as np
 import pytest
 import torch
@@ -11,11 +14,11 @@ from oracle import models as M
 pytestmark = pytest.mark.gpu
 
 
-def _setup(depth, width, B, loss="mae", seed=0):
+def _setup(depth, width, B, loss="mae", seed=0, dtype="bf16"):
     from climsim_b200 import CNNEngine
     ref = M.CNNRef(depth=depth, width=width, seed=seed)
     ref.randomize_biases(seed + 1)
-    eng = CNNEngine(depth=depth, width=width, loss=loss, max_batch=max(B, 8))
+    eng = CNNEngine(depth=depth, width=width, loss=loss, max_batch=max(B, 8), dtype=dtype)
     assert eng.n_params == ref.num_parameters()
     eng.set_params_flat(CNNEngine.keras_to_flat([p.detach().numpy() for p in ref.params]))
     g = torch.Generator().manual_seed(seed + 2)
@@ -84,3 +87,22 @@ def test_cnn_training_lowers_loss():
         losses.append(eng.train_step(xs, ys).item())
         eng.apply_opt("adam_keras", lr=2e-3)
     assert losses[-1] < 0.7 * losses[0], (losses[0], losses[-1])
+
+
+@pytest.mark.parametrize("depth,width,B", [(1, 64, 4), (2, 406, 5), (3, 128, 7)])
+def test_cnn_fp32_parity(depth, width, B):
+    ref, eng, x, y = _setup(depth, width, B, "mse", dtype="fp32")
+    want = ref(x)
+    got = eng.forward(x.cuda()).cpu().numpy()
+    assert np.abs(got - want.detach().numpy()).max() <= 1e-5 * want.abs().max().item()
+    loss = M.mse_adjusted(y, want)
+    loss.backward()
+    got_loss = eng.train_step(x.cuda(), y.cuda()).item()
+    assert abs(got_loss - loss.item()) <= 1e-5 * loss.item()
+    for i, (a, b) in enumerate(zip(eng.split_flat(eng.get_grads_flat()), eng.split_flat(_flat([p.grad for p in ref.params])))):
+        sc = np.abs(b).max()
+        if sc > 0:
+            assert np.abs(a - b).max() <= 2e-5 * sc, (i, a.shape, np.abs(a - b).max() / sc)
+    # MAE loss value in fp32
+    ref2, eng2, x2, y2 = _setup(depth, width, B, "mae", dtype="fp32")
+    assert abs(eng2.train_step(x2.cuda(), y2.cuda()).item() - M.mae_adjusted(y2, ref2(x2)).item()) <= 1e-5 * M.mae_adjusted(y2, ref2(x2)).item()
