@@ -194,6 +194,7 @@ struct csb_mlp {
   void* xn = nullptr;                       // [cap x in_p]   bf16 or fp32
   void* act[CSB_MAX_LAYERS] = {};           // [cap x Np_l]   (l < L-1)
   void* dz[2] = {nullptr, nullptr};         // [cap x max_np]
+  uint32_t* amask[CSB_MAX_LAYERS] = {};     // bf16 mode, ReLU / LeakyReLU layers without LayerNorm: sign bits of act_l [cap x Np_l/32]
   void* zbuf[CSB_MAX_LAYERS] = {};          // LayerNorm layers: pre-norm z [cap x Np_l]
   float* ln_stats[CSB_MAX_LAYERS] = {};     // LayerNorm layers: (mean, rstd) per row [cap x 2]
   float* pred = nullptr;                    // [cap x out_p]
@@ -244,7 +245,7 @@ static inline size_t esize(const csb_mlp* h) { return h->bf16 ? 2 : 4; }
 static void free_all(csb_mlp* h) {
   auto F = [](void* p) { if (p) cudaFree(p); };
   F(h->params); F(h->grads); F(h->m); F(h->v); F(h->ws);
-  for (int l = 0; l < CSB_MAX_LAYERS; ++l) { F(h->w16[l]); F(h->wt16[l]); F(h->act[l]); F(h->zbuf[l]); F(h->ln_stats[l]); }
+  for (int l = 0; l < CSB_MAX_LAYERS; ++l) { F(h->w16[l]); F(h->wt16[l]); F(h->act[l]); F(h->zbuf[l]); F(h->ln_stats[l]); F(h->amask[l]); }
   F(h->xn); F(h->dz[0]); F(h->dz[1]); F(h->pred); F(h->dx_tmp);
   F(h->d_sub); F(h->d_div); F(h->d_out_scale); F(h->d_inv_out_scale); F(h->d_loss_w); F(h->d_out_mask);
   F(h->loss_partials); F(h->d_loss); F(h->x_stage); F(h->y_stage);
@@ -411,6 +412,9 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
   CKA(h->xn, (size_t)h->cap * h->in_p * es);
   for (int l = 0; l + 1 < h->L; ++l) {
     CKA(h->act[l], (size_t)h->cap * h->layer[l].Np * es);
+    if (h->bf16 && !h->layer[l].ln && (h->layer[l].act == CSB_ACT_RELU || h->layer[l].act == CSB_ACT_LEAKYRELU) &&
+        getenv("CSB_NO_MASK") == nullptr)
+      CKA(h->amask[l], (size_t)h->cap * (h->layer[l].Np / 32) * 4);
     if (h->layer[l].ln) {
       CKA(h->zbuf[l], (size_t)h->cap * h->layer[l].Np * es);
       CKA(h->ln_stats[l], (size_t)h->cap * 2 * 4);
@@ -651,6 +655,7 @@ static int run_hidden_forward(csb_mlp* h, int64_t B, cudaStream_t st) {
       tc::GemmParams p = {};
       p.M = (int)B; p.N = li.Np; p.K = li.Kp; p.act = gemm_act; p.alpha = li.alpha; p.head_relu_from = -1;
       p.bias = h->params + li.b_off; p.out = li.ln ? h->zbuf[l] : h->act[l]; p.ld_out = li.Np;
+      p.mask_out = h->amask[l]; p.ld_mask = li.Np / 32;
       int rc = launch_tn_auto<tc::EPI_BIAS_ACT>(h->tm_in[l].a_k128, h->tm_wt[l], li.ln ? &h->tm_z[l] : &h->tm_in[l + 1].a_k128, nullptr, p,
                                                 h->sm_count, st);
       if (rc) return rc;
@@ -825,7 +830,13 @@ static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st)
         p.M = (int)B; p.N = li.Kp; p.K = li.Np; p.act = lp.act; p.alpha = lp.alpha; p.head_relu_from = -1;
         p.out = dz16(h, l - 1); p.ld_out = lp.Np;
         p.saved = reinterpret_cast<const __nv_bfloat16*>(h->act[l - 1]); p.ld_saved = lp.Np;
-        int rc = launch_tn_auto<tc::EPI_DGRAD>(h->tm_dz[l].a_k128, h->tm_w[l], &h->tm_dz[l - 1].a_k128, &h->tm_in[l].a_k128, p, h->sm_count, st);
+        int rc;
+        if (h->amask[l - 1] != nullptr) {        // ReLU-family layer: act' from the forward pass's sign bits (no activation re-read)
+          p.mask_in = h->amask[l - 1]; p.ld_mask = lp.Np / 32;
+          rc = launch_tn_auto<tc::EPI_DGRAD_MASK>(h->tm_dz[l].a_k128, h->tm_w[l], &h->tm_dz[l - 1].a_k128, nullptr, p, h->sm_count, st);
+        } else {
+          rc = launch_tn_auto<tc::EPI_DGRAD>(h->tm_dz[l].a_k128, h->tm_w[l], &h->tm_dz[l - 1].a_k128, &h->tm_in[l].a_k128, p, h->sm_count, st);
+        }
         if (rc) return rc;
       } else {
         simt::SgemmParams p = {};

@@ -33,7 +33,9 @@ enum Epi : int {
   EPI_DGRAD = 2,      // out(bf16) = acc * act'(saved activation)          backward data gradient
   EPI_F32 = 3,        // out(fp32) = acc                                   (self-test, fp32 consumers)
   EPI_HEAD_OUT = 4,   // p = head(acc + bias) -> fp32 (optionally / out_scale)   inference output layer
-  EPI_BIAS_ADD = 5    // out(bf16) = acc + bias + saved tile                 residual add / gradient accumulation
+  EPI_BIAS_ADD = 5,   // out(bf16) = acc + bias + saved tile                 residual add / gradient accumulation
+  EPI_DGRAD_MASK = 6  // out(bf16) = acc * act'(sign bit)                    backward data gradient of ReLU / LeakyReLU layers:
+                      //   act' needs only "activation > 0", stored by the forward epilogue as one bit per element
 };
 
 struct GemmParams {
@@ -45,6 +47,9 @@ struct GemmParams {
   int kb_per_tap;              // 0: plain GEMM
   int tap_center;
   int halo_period;             // 0: no halo rows
+  uint32_t* mask_out;          // EPI_BIAS_ACT: optional sign-bit mask [M, ld_mask] (bit j of word w <-> column 32 w + j, set iff out > 0)
+  const uint32_t* mask_in;     // EPI_DGRAD_MASK
+  int ld_mask;                 // words per row
   int dbg;                     // micro-benchmark knobs (scripts/microbench_gemm.py): 1 skip bias staging, 2 skip epilogue math + smem
                                // stores, 4 skip TMA store, 8 skip TMEM loads.  0 in production.
   int act;                     // CSB_ACT_* for EPI_BIAS_ACT / EPI_DGRAD (activation of the layer whose output is stored / was saved)
@@ -301,6 +306,23 @@ __device__ __forceinline__ void cst_store32(uint8_t* cst, int row, int col, cons
     *reinterpret_cast<uint4*>(cst + cst_offset(row, col + 8 * q)) = u;
   }
 }
+// same, and returns bit j = (bf16(v[j]) > 0): the sign-bit mask the data-gradient epilogue consumes instead of the activation
+__device__ __forceinline__ uint32_t cst_store32_mask(uint8_t* cst, int row, int col, const float (&v)[32]) {
+  uint32_t mask = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      w[i] = pack_bf16x2(v[8 * q + 2 * i], v[8 * q + 2 * i + 1]);
+      const uint32_t lo_pos = ((w[i] & 0x7FFFu) != 0u) & ((w[i] & 0x8000u) == 0u);
+      const uint32_t hi_pos = ((w[i] & 0x7FFF0000u) != 0u) & ((w[i] & 0x80000000u) == 0u);
+      mask |= (lo_pos << (8 * q + 2 * i)) | (hi_pos << (8 * q + 2 * i + 1));
+    }
+    *reinterpret_cast<uint4*>(cst + cst_offset(row, col + 8 * q)) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  return mask;
+}
 __device__ __forceinline__ void cst_load32(const uint8_t* cst, int row, int col, float (&v)[32]) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -334,7 +356,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // One 32-column step of the epilogue.  tile_row/tile_col are tile-relative, grow/gcol global.
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint8_t* cst, const float* sbias, int tile_row, int tile_col,
-                                               int grow, int gcol, const uint32_t (&raw)[32], float& loss_acc) {
+                                               int grow, int gcol, const uint32_t (&raw)[32], float& loss_acc, uint32_t mask_word) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
@@ -355,6 +377,21 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint8_t* cst
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] += b[j];
     act_fwd_vec(p.act, p.alpha, v);
+    if (zero_row) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    }
+    if (p.mask_out != nullptr) {
+      const uint32_t m = cst_store32_mask(cst, tile_row, tile_col, v);
+      if (grow < p.M) p.mask_out[(size_t)grow * p.ld_mask + (gcol >> 5)] = m;
+    } else {
+      cst_store32(cst, tile_row, tile_col, v);
+    }
+  } else if constexpr (EPI == EPI_DGRAD_MASK) {
+    // act'(a) through the sign bit: relu -> {1, 0}, leaky relu -> {1, alpha}
+    const float neg = p.act == CSB_ACT_LEAKYRELU ? p.alpha : 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = ((mask_word >> j) & 1u) ? v[j] : neg * v[j];
     if (zero_row) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = 0.f;
@@ -496,7 +533,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const bool is_leader = cta_rank == 0;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static_assert(2 * BN <= 512, "two accumulator buffers must fit the 512 TMEM columns");
-  constexpr bool CST_OUT = (EPI == EPI_BIAS_ACT || EPI == EPI_DGRAD || EPI == EPI_HEAD_LOSS || EPI == EPI_BIAS_ADD);
+  constexpr bool CST_OUT = (EPI == EPI_BIAS_ACT || EPI == EPI_DGRAD || EPI == EPI_HEAD_LOSS || EPI == EPI_BIAS_ADD || EPI == EPI_DGRAD_MASK);
   constexpr bool CST_IN = (EPI == EPI_DGRAD || EPI == EPI_BIAS_ADD);
   constexpr bool USE_BIAS = (EPI == EPI_BIAS_ACT || EPI == EPI_HEAD_LOSS || EPI == EPI_HEAD_OUT || EPI == EPI_BIAS_ADD);
   constexpr int SLAB_BYTES = BM * 128;   // one 64-column slab of the staging tile
@@ -634,6 +671,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (!(p.dbg & 1))
           for (int i = threadIdx.x; i < BN; i += TN_EPI_THREADS) sbias[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
       }
+      uint32_t mask_words[NCH];
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) mask_words[i] = 0u;
+      if constexpr (EPI == EPI_DGRAD_MASK) {                  // independent of the MMA: issued before waiting for the accumulator
+        if (m0 + tile_row < p.M) {
+#pragma unroll
+          for (int i = 0; i < NCH; ++i) {
+            const int c = hf * HALF + 32 * i;
+            if (c < n_valid) mask_words[i] = __ldg(p.mask_in + (size_t)(m0 + tile_row) * p.ld_mask + ((n0 + c) >> 5));
+          }
+        }
+      }
       mbar_wait(tfull_bar(acc), (uint32_t)(t >> 1) & 1u);
       tc_fence_after();
       if constexpr (CST_IN) mbar_wait(cst_full, (uint32_t)t & 1u);
@@ -650,7 +699,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             tmem_ld_wait();
             if (i + 1 < NCH && c + 32 < n_valid) tmem_ld_32x32(taddr + (uint32_t)(32 * (i + 1)), raw[(i + 1) & 1]);
           }
-          if (!(p.dbg & 2)) epilogue_chunk<EPI>(p, cst, sbias, tile_row, c, m0 + tile_row, n0 + c, raw[i & 1], loss_acc);
+          if (!(p.dbg & 2)) epilogue_chunk<EPI>(p, cst, sbias, tile_row, c, m0 + tile_row, n0 + c, raw[i & 1], loss_acc, mask_words[i]);
         }
       }
       tc_fence_before();

@@ -330,3 +330,26 @@ def test_cuda_graph_replay_matches_eager():
     eng.apply_opt("adam_keras", lr=1e-2)
     eng.train_step(xs, ys)
     assert np.abs(eng.get_grads_flat() - g0).max() > 0
+
+
+@pytest.mark.parametrize("act", ["leakyrelu", "relu"])
+def test_sign_mask_dgrad_is_bitwise_equal_to_saved_activation_path(act, monkeypatch):
+    """The data-gradient epilogue takes act' from the sign bits written by the forward epilogue; the older path that re-reads the
+    saved bf16 activations (CSB_NO_MASK=1) must give bit-identical gradients."""
+    from climsim_b200 import MLPEngine
+    units, B = (256, 192, 64), 777
+    ref = M.MLPRef(units=units, act=act, seed=11)
+    ref.randomize_biases(12)
+    x, y = _batch(B, 13)
+    grads = {}
+    for no_mask in ("0", "1"):
+        if no_mask == "1":
+            monkeypatch.setenv("CSB_NO_MASK", "1")
+        else:
+            monkeypatch.delenv("CSB_NO_MASK", raising=False)
+        eng = MLPEngine.mlp_v1(units=units, act=act, dtype="bf16", max_batch=1024)
+        _load(eng, ref)
+        eng.train_step(x.cuda(), y.cuda())
+        grads[no_mask] = eng.get_grads_flat()
+        eng.close()
+    np.testing.assert_array_equal(grads["0"], grads["1"])
