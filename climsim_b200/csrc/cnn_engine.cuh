@@ -120,9 +120,11 @@ static int cnn_conv(csb_cnn* h, const ConvLayerInfo& li, bool dgrad, const CnnBu
     p.M = M; p.N = N; p.K = li.taps * Kt; p.kb_per_tap = Kt / 64; p.tap_center = (li.taps - 1) / 2; p.halo_period = h->P;
     p.act = act; p.head_relu_from = -1; p.bias = bias;
     const CUtensorMap& w = dgrad ? li.tm_wd : li.tm_wt;
-    if (kind == 0) rc = launch_tn_auto<tc::EPI_BIAS_ACT>(in.maps.k128, w, &out.maps.k128, nullptr, p, h->sm_count, st);
-    else if (kind == 1) rc = launch_tn_auto<tc::EPI_BIAS_ADD>(in.maps.k128, w, &out.maps.k128, &saved->maps.k128, p, h->sm_count, st);
-    else rc = launch_tn_auto<tc::EPI_DGRAD>(in.maps.k128, w, &out.maps.k128, &saved->maps.k128, p, h->sm_count, st);
+    p.out = out.ptr; p.ld_out = out.Cp;
+    if (saved) { p.saved = reinterpret_cast<const __nv_bfloat16*>(saved->ptr); p.ld_saved = saved->Cp; }
+    if (kind == 0) rc = launch_tn_auto<tc::EPI_BIAS_ACT>(in.maps.k128, w, p, h->sm_count, st);
+    else if (kind == 1) rc = launch_tn_auto<tc::EPI_BIAS_ADD>(in.maps.k128, w, p, h->sm_count, st);
+    else rc = launch_tn_auto<tc::EPI_DGRAD>(in.maps.k128, w, p, h->sm_count, st);
   } else {
     simt::SgemmParams p = {};
     p.M = M; p.N = N; p.K = li.taps * Kt;
@@ -400,7 +402,7 @@ int csb_cnn_forward(csb_cnn* h, const float* x, float* y_pred, int64_t B, void* 
   p.M = (int)(B * h->P); p.N = cd.Coutp; p.K = cd.Cinp; p.halo_period = h->P;
   p.act = CSB_ACT_NONE; p.head_relu_from = h->out_lin; p.bias = h->params + cd.b_off;
   p.out_dim = h->out_ch; p.pred = y_pred; p.ld_pred = h->out_ch;
-  rc = launch_tn_auto<tc::EPI_HEAD_OUT>(h->e.maps.k128, cd.tm_wt, nullptr, nullptr, p, h->sm_count, st);
+  rc = launch_tn_auto<tc::EPI_HEAD_OUT>(h->e.maps.k128, cd.tm_wt, p, h->sm_count, st);
   if (rc) return rc;
   h->launches++;
   return CSB_OK;
@@ -424,7 +426,8 @@ int csb_cnn_train_step(csb_cnn* h, const float* x, const float* y, int64_t B, fl
     p.act = CSB_ACT_NONE; p.head_relu_from = h->out_lin; p.bias = h->params + cd.b_off; p.out_dim = h->out_ch;
     p.y = y; p.ld_y = h->out_ch; p.loss_w = h->d_loss_w; p.grad_scale = grad_scale; p.loss_kind = h->cfg.loss;
     p.loss_partials = h->loss_partials;
-    if ((rc = launch_tn_auto<tc::EPI_HEAD_LOSS>(h->e.maps.k128, cd.tm_wt, &h->dzh.maps.k128, nullptr, p, h->sm_count, st))) return rc;
+    p.out = h->dzh.ptr; p.ld_out = h->dzh.Cp;
+    if ((rc = launch_tn_auto<tc::EPI_HEAD_LOSS>(h->e.maps.k128, cd.tm_wt, p, h->sm_count, st))) return rc;
     h->launches++;
     simt::loss_finalize_kernel<<<1, 256, 0, st>>>(h->loss_partials, (int)ceil_div(R, 128) * tc::TN_EPI_WARPS, loss_out ? loss_out : h->d_loss);
   } else {

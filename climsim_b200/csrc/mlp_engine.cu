@@ -71,11 +71,11 @@ static int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t cols, uint
 // ---------------------------------------------------------------------------------------------------------------
 static bool g_use_pairs = true;     // CSB_NO_PAIRS=1 falls back to the single-CTA kernels (debugging aid)
 
-template <int BN, int STAGES, int EPI, int CG>
-static int launch_tn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tout, const CUtensorMap* tsaved,
-                     const tc::GemmParams& p, int sm_count, cudaStream_t st) {
+template <int BN, int STAGES, int EPI, int CG, bool ELU = false>
+static int launch_tn(const CUtensorMap& ta, const CUtensorMap& tb, const tc::GemmParams& p, int sm_count, cudaStream_t st) {
   using L = tc::TnSmem<BN, STAGES, CG>;
-  auto kern = tc::gemm_tn_kernel<BN, STAGES, EPI, CG>;
+  auto kern = tc::gemm_tn_kernel<BN, STAGES, EPI, CG, ELU>;
+  CSB_REQUIRE(p.N <= tc::TN_BIAS_SMEM, CSB_EUNSUPPORTED, "layer width %d exceeds %d (bias vector kept in shared memory)", p.N, tc::TN_BIAS_SMEM);
   static bool attr_set = false;
   if (!attr_set) {
     CSB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -96,8 +96,7 @@ static int launch_tn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
   attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (CG > 1) ? 1 : 0;
-  // unused descriptor slots get a valid (never dereferenced) descriptor
-  CSB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tout ? *tout : ta, tsaved ? *tsaved : ta, q));
+  CSB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, q));
   return CSB_OK;
 }
 
@@ -106,14 +105,22 @@ static int launch_tn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
 static inline bool tn_use_pairs(int N) { return g_use_pairs && N > 128; }
 static inline int tn_b_box_rows(int N) { return N > 128 ? (tn_use_pairs(N) ? std::min(N, 256) / 2 : std::min(N, 256)) : std::min(N, 128); }
 
-template <int EPI>
-static int launch_tn_auto(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tout, const CUtensorMap* tsaved,
-                          const tc::GemmParams& p, int sm_count, cudaStream_t st) {
+template <int EPI, bool ELU>
+static int launch_tn_shape(const CUtensorMap& ta, const CUtensorMap& tb, const tc::GemmParams& p, int sm_count, cudaStream_t st) {
   if (p.N > 128) {
-    if (tn_use_pairs(p.N)) return launch_tn<256, 5, EPI, 2>(ta, tb, tout, tsaved, p, sm_count, st);
-    return launch_tn<256, 3, EPI, 1>(ta, tb, tout, tsaved, p, sm_count, st);
+    if (tn_use_pairs(p.N)) return launch_tn<256, 6, EPI, 2, ELU>(ta, tb, p, sm_count, st);
+    return launch_tn<256, 4, EPI, 1, ELU>(ta, tb, p, sm_count, st);
   }
-  return launch_tn<128, 5, EPI, 1>(ta, tb, tout, tsaved, p, sm_count, st);
+  return launch_tn<128, 6, EPI, 1, ELU>(ta, tb, p, sm_count, st);
+}
+template <int EPI>
+static int launch_tn_auto(const CUtensorMap& ta, const CUtensorMap& tb, const tc::GemmParams& p, int sm_count, cudaStream_t st) {
+  // ELU (expm1f in the epilogue) is a separate instantiation of the epilogues that evaluate an activation
+  constexpr bool HAS_ACT = (EPI == tc::EPI_BIAS_ACT || EPI == tc::EPI_HEAD_LOSS || EPI == tc::EPI_HEAD_OUT || EPI == tc::EPI_DGRAD);
+  if constexpr (HAS_ACT) {
+    if (p.act == CSB_ACT_ELU) return launch_tn_shape<EPI, true>(ta, tb, p, sm_count, st);
+  }
+  return launch_tn_shape<EPI, false>(ta, tb, p, sm_count, st);
 }
 static inline int tn_block_n(int N) { return N > 128 ? 256 : 128; }
 
@@ -655,9 +662,8 @@ static int run_hidden_forward(csb_mlp* h, int64_t B, cudaStream_t st) {
       tc::GemmParams p = {};
       p.M = (int)B; p.N = li.Np; p.K = li.Kp; p.act = gemm_act; p.alpha = li.alpha; p.head_relu_from = -1;
       p.bias = h->params + li.b_off; p.out = li.ln ? h->zbuf[l] : h->act[l]; p.ld_out = li.Np;
-      p.mask_out = h->amask[l]; p.ld_mask = li.Np / 32;
-      int rc = launch_tn_auto<tc::EPI_BIAS_ACT>(h->tm_in[l].a_k128, h->tm_wt[l], li.ln ? &h->tm_z[l] : &h->tm_in[l + 1].a_k128, nullptr, p,
-                                                h->sm_count, st);
+      p.mask_out = h->amask[l]; p.ld_mask = (int)h->cap;
+      int rc = launch_tn_auto<tc::EPI_BIAS_ACT>(h->tm_in[l].a_k128, h->tm_wt[l], p, h->sm_count, st);
       if (rc) return rc;
     } else {
       simt::SgemmParams p = {};
@@ -704,9 +710,9 @@ static int run_head(csb_mlp* h, int64_t B, int fused_loss, const float* y, float
       p.y = y; p.ld_y = h->out_dim; p.loss_w = h->d_loss_w; p.grad_scale = grad_scale; p.loss_kind = h->cfg.loss;
       p.loss_partials = h->loss_partials;
       p.pred = nullptr;
-      rc = launch_tn_auto<tc::EPI_HEAD_LOSS>(h->tm_in[l].a_k128, h->tm_wt[l], &h->tm_dz[l].a_k128, nullptr, p, h->sm_count, st);
+      rc = launch_tn_auto<tc::EPI_HEAD_LOSS>(h->tm_in[l].a_k128, h->tm_wt[l], p, h->sm_count, st);
     } else {
-      rc = launch_tn_auto<tc::EPI_HEAD_OUT>(h->tm_in[l].a_k128, h->tm_wt[l], nullptr, nullptr, p, h->sm_count, st);
+      rc = launch_tn_auto<tc::EPI_HEAD_OUT>(h->tm_in[l].a_k128, h->tm_wt[l], p, h->sm_count, st);
     }
     if (rc) return rc;
   } else {
@@ -832,10 +838,10 @@ static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st)
         p.saved = reinterpret_cast<const __nv_bfloat16*>(h->act[l - 1]); p.ld_saved = lp.Np;
         int rc;
         if (h->amask[l - 1] != nullptr) {        // ReLU-family layer: act' from the forward pass's sign bits (no activation re-read)
-          p.mask_in = h->amask[l - 1]; p.ld_mask = lp.Np / 32;
-          rc = launch_tn_auto<tc::EPI_DGRAD_MASK>(h->tm_dz[l].a_k128, h->tm_w[l], &h->tm_dz[l - 1].a_k128, nullptr, p, h->sm_count, st);
+          p.mask_in = h->amask[l - 1]; p.ld_mask = (int)h->cap;
+          rc = launch_tn_auto<tc::EPI_DGRAD_MASK>(h->tm_dz[l].a_k128, h->tm_w[l], p, h->sm_count, st);
         } else {
-          rc = launch_tn_auto<tc::EPI_DGRAD>(h->tm_dz[l].a_k128, h->tm_w[l], &h->tm_dz[l - 1].a_k128, &h->tm_in[l].a_k128, p, h->sm_count, st);
+          rc = launch_tn_auto<tc::EPI_DGRAD>(h->tm_dz[l].a_k128, h->tm_w[l], p, h->sm_count, st);
         }
         if (rc) return rc;
       } else {
@@ -857,7 +863,7 @@ static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st)
       if (h->bf16) {
         tc::GemmParams p = {};
         p.M = (int)B; p.N = li.Kp; p.K = li.Np; p.out = h->dx_tmp; p.ld_out = h->in_p;
-        int rc = launch_tn_auto<tc::EPI_F32>(h->tm_dz[0].a_k128, h->tm_w[0], nullptr, nullptr, p, h->sm_count, st);
+        int rc = launch_tn_auto<tc::EPI_F32>(h->tm_dz[0].a_k128, h->tm_w[0], p, h->sm_count, st);
         if (rc) return rc;
       } else {
         simt::SgemmParams p = {};
@@ -1135,13 +1141,15 @@ int csb_test_gemm_tn(const uint16_t* A, const uint16_t* Bt, float* C, int M, int
   tc::GemmParams p = {};
   p.M = M; p.N = N; p.K = K; p.out = C; p.ld_out = N;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (pairs) return launch_tn<256, 5, tc::EPI_F32, 2>(ta, tb, nullptr, nullptr, p, sm, st);
-  if (block_n == 256) return launch_tn<256, 3, tc::EPI_F32, 1>(ta, tb, nullptr, nullptr, p, sm, st);
-  return launch_tn<128, 5, tc::EPI_F32, 1>(ta, tb, nullptr, nullptr, p, sm, st);
+  if (pairs) return launch_tn<256, 6, tc::EPI_F32, 2>(ta, tb, p, sm, st);
+  if (block_n == 256) return launch_tn<256, 4, tc::EPI_F32, 1>(ta, tb, p, sm, st);
+  return launch_tn<128, 6, tc::EPI_F32, 1>(ta, tb, p, sm, st);
 }
 
 static int g_test_dbg = 0;
+static unsigned long long* g_test_stats = nullptr;
 void csb_test_set_debug(int flags) { g_test_dbg = flags; }
+void csb_test_set_stats(void* dev_u64x4_per_cta) { g_test_stats = reinterpret_cast<unsigned long long*>(dev_u64x4_per_cta); }
 
 int csb_test_linear_fwd(const uint16_t* A, const uint16_t* Wt, const float* bias, uint16_t* out, int M, int N, int K, int act,
                         float alpha, int pairs, void* stream) {
@@ -1152,17 +1160,17 @@ int csb_test_linear_fwd(const uint16_t* A, const uint16_t* Wt, const float* bias
   if (sm == 0 && (rc = csb_device_info(&sm, nullptr, nullptr, nullptr))) return rc;
   const bool wide = N > 128, use_pairs = wide && pairs != 0;
   const int bn = wide ? 256 : 128;
-  CUtensorMap ta, tb, tout;
+  CUtensorMap ta, tb;
   if ((rc = make_tmap_bf16(&ta, A, K, M, K, 64, 128))) return rc;
   if ((rc = make_tmap_bf16(&tb, Wt, K, N, K, 64, (uint32_t)(std::min(N, bn) / (use_pairs ? 2 : 1))))) return rc;
-  if ((rc = make_tmap_bf16(&tout, out, N, M, N, 64, 128))) return rc;
   tc::GemmParams p = {};
   p.M = M; p.N = N; p.K = K; p.act = act; p.alpha = alpha; p.head_relu_from = -1; p.bias = bias; p.out = out; p.ld_out = N;
   p.dbg = g_test_dbg;
+  p.stats = g_test_stats;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (use_pairs) return launch_tn<256, 5, tc::EPI_BIAS_ACT, 2>(ta, tb, &tout, nullptr, p, sm, st);
-  if (wide) return launch_tn<256, 3, tc::EPI_BIAS_ACT, 1>(ta, tb, &tout, nullptr, p, sm, st);
-  return launch_tn<128, 5, tc::EPI_BIAS_ACT, 1>(ta, tb, &tout, nullptr, p, sm, st);
+  if (use_pairs) return launch_tn<256, 6, tc::EPI_BIAS_ACT, 2>(ta, tb, p, sm, st);
+  if (wide) return launch_tn<256, 4, tc::EPI_BIAS_ACT, 1>(ta, tb, p, sm, st);
+  return launch_tn<128, 6, tc::EPI_BIAS_ACT, 1>(ta, tb, p, sm, st);
 }
 
 int csb_test_gemm_nt(const uint16_t* A, const uint16_t* B, float* C, float* colsum, int M, int N, int Kr, int splits, void* stream) {

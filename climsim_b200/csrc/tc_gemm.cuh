@@ -47,11 +47,13 @@ struct GemmParams {
   int kb_per_tap;              // 0: plain GEMM
   int tap_center;
   int halo_period;             // 0: no halo rows
-  uint32_t* mask_out;          // EPI_BIAS_ACT: optional sign-bit mask [M, ld_mask] (bit j of word w <-> column 32 w + j, set iff out > 0)
+  uint32_t* mask_out;          // EPI_BIAS_ACT: optional sign-bit mask (bit j of word w <-> column 32 w + j, set iff out > 0)
   const uint32_t* mask_in;     // EPI_DGRAD_MASK
-  int ld_mask;                 // words per row
+  int ld_mask;                 // chunk-major layout [N/32][ld_mask]: word of (row r, columns 32w..32w+31) at w * ld_mask + r
   int dbg;                     // micro-benchmark knobs (scripts/microbench_gemm.py): 1 skip bias staging, 2 skip epilogue math + smem
-                               // stores, 4 skip TMA store, 8 skip TMEM loads.  0 in production.
+                               // stores, 4 skip TMA store, 8 skip TMEM loads, 16 skip all TMA loads, 32 skip the MMAs, 64 skip the
+                               // B loads, 128 skip the A loads.  0 in production.
+  unsigned long long* stats;   // micro-benchmark: per CTA {clock64 at start, at end, globaltimer ns at start, at end}; NULL in production
   int act;                     // CSB_ACT_* for EPI_BIAS_ACT / EPI_DGRAD (activation of the layer whose output is stored / was saved)
   float alpha;
   int head_relu_from;          // EPI_HEAD_*: columns >= this get ReLU (-1: none); otherwise `act` applies
@@ -247,91 +249,31 @@ __device__ __forceinline__ void load_f32x32(const float* src, float (&v)[32]) {
     v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
   }
 }
-// activation over a 32-vector with the (warp-uniform) switch hoisted out of the element loop
-__device__ __forceinline__ void act_fwd_vec(int act, float alpha, float (&v)[32]) {
-  switch (act) {
-    case CSB_ACT_RELU:
+// ---- register <-> global row pieces.  Each epilogue thread owns one output row; a 32-column step is 64 contiguous bytes of
+// bf16 in that row = two full 32-byte sectors, moved with 256-bit accesses.  (The first version staged the tile in shared
+// memory and wrote it with a TMA store; on B200 the TMA store queues in front of the mainloop's TMA loads and stalls them
+// for the ~2 k cycles the SM needs to push 64 KB to L2 -- see profiles/r01_probe_mainloop.txt.)
+__device__ __forceinline__ void store_bf16x32_global(__nv_bfloat16* dst, const float (&v)[32]) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-      break;
-    case CSB_ACT_LEAKYRELU:
-      if (alpha >= 0.f && alpha <= 1.f) {               // warp-uniform: leaky(v) == max(v, alpha v) for a slope in [0, 1]
+  for (int h = 0; h < 2; ++h) {
+    uint32_t w[8];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], alpha * v[j]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : alpha * v[j];
-      }
-      break;
-    case CSB_ACT_ELU:
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : expm1f(v[j]);
-      break;
-    default: break;
+    for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(v[16 * h + 2 * i], v[16 * h + 2 * i + 1]);
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 16 * h), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+                 "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
   }
 }
-// v *= act'(a) with a = saved activation output
-__device__ __forceinline__ void act_bwd_vec(int act, float alpha, float (&v)[32], const float (&a)[32]) {
-  switch (act) {
-    case CSB_ACT_RELU:
+__device__ __forceinline__ void load_bf16x32_global_raw(const __nv_bfloat16* src, uint32_t (&w)[16]) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = a[j] > 0.f ? v[j] : 0.f;
-      break;
-    case CSB_ACT_LEAKYRELU:
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = a[j] > 0.f ? v[j] : alpha * v[j];
-      break;
-    case CSB_ACT_ELU:
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = a[j] > 0.f ? v[j] : v[j] * (a[j] + 1.f);
-      break;
-    default: break;
-  }
+  for (int h = 0; h < 2; ++h)
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w[8 * h + 0]), "=r"(w[8 * h + 1]), "=r"(w[8 * h + 2]), "=r"(w[8 * h + 3]), "=r"(w[8 * h + 4]), "=r"(w[8 * h + 5]),
+                   "=r"(w[8 * h + 6]), "=r"(w[8 * h + 7])
+                 : "l"(src + 16 * h));
 }
-
-// The bf16 staging tile in shared memory is laid out exactly as TMA reads/writes it with SWIZZLE_128B and a
-// {64 columns, 128 rows} box: 64-column slabs of 128 rows x 128 B; inside a row the 16-byte pieces are XOR-swizzled
-// with (row & 7).  A quarter-warp (8 consecutive rows, same piece index) therefore touches 8 distinct 16 B bank groups.
-__device__ __forceinline__ uint32_t cst_offset(int row, int col /* multiple of 8, tile-relative */) {
-  return (uint32_t)((col >> 6) * (BM * 128) + row * 128 + ((((col & 63) >> 3) ^ (row & 7)) << 4));
-}
-__device__ __forceinline__ void cst_store32(uint8_t* cst, int row, int col, const float (&v)[32]) {
+__device__ __forceinline__ void unpack_bf16x32(const uint32_t (&w)[16], float (&v)[32]) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint4 u;
-    u.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
-    u.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
-    u.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
-    u.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
-    *reinterpret_cast<uint4*>(cst + cst_offset(row, col + 8 * q)) = u;
-  }
-}
-// same, and returns bit j = (bf16(v[j]) > 0): the sign-bit mask the data-gradient epilogue consumes instead of the activation
-__device__ __forceinline__ uint32_t cst_store32_mask(uint8_t* cst, int row, int col, const float (&v)[32]) {
-  uint32_t mask = 0;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint32_t w[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      w[i] = pack_bf16x2(v[8 * q + 2 * i], v[8 * q + 2 * i + 1]);
-      const uint32_t lo_pos = ((w[i] & 0x7FFFu) != 0u) & ((w[i] & 0x8000u) == 0u);
-      const uint32_t hi_pos = ((w[i] & 0x7FFF0000u) != 0u) & ((w[i] & 0x80000000u) == 0u);
-      mask |= (lo_pos << (8 * q + 2 * i)) | (hi_pos << (8 * q + 2 * i + 1));
-    }
-    *reinterpret_cast<uint4*>(cst + cst_offset(row, col + 8 * q)) = make_uint4(w[0], w[1], w[2], w[3]);
-  }
-  return mask;
-}
-__device__ __forceinline__ void cst_load32(const uint8_t* cst, int row, int col, float (&v)[32]) {
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const uint4 t = *reinterpret_cast<const uint4*>(cst + cst_offset(row, col + 8 * q));
-    v[8 * q + 0] = bf16_lo(t.x); v[8 * q + 1] = bf16_hi(t.x);
-    v[8 * q + 2] = bf16_lo(t.y); v[8 * q + 3] = bf16_hi(t.y);
-    v[8 * q + 4] = bf16_lo(t.z); v[8 * q + 5] = bf16_hi(t.z);
-    v[8 * q + 6] = bf16_lo(t.w); v[8 * q + 7] = bf16_hi(t.w);
-  }
+  for (int i = 0; i < 16; ++i) { v[2 * i] = bf16_lo(w[i]); v[2 * i + 1] = bf16_hi(w[i]); }
 }
 __device__ __forceinline__ void load_smem_f32x32(const float* s, float (&v)[32]) {
 #pragma unroll
@@ -341,93 +283,143 @@ __device__ __forceinline__ void load_smem_f32x32(const float* s, float (&v)[32])
   }
 }
 
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1)
-               : "memory");
+constexpr int TN_BIAS_SMEM = 4096;     // widest layer (columns) the kernel accepts: its bias vector lives in shared memory
+
+// cheap activations (ReLU / LeakyReLU / none) over a 32-vector, branch-free inside the element loop; ELU is a separate kernel
+// instantiation (template flag) so that expm1f's code never sits in the instruction stream of the common kernels
+template <bool ELU>
+__device__ __forceinline__ void act_fwd32(int act, float alpha, float (&v)[32]) {
+  if constexpr (ELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : expm1f(v[j]);
+  } else {
+    if (act == CSB_ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    } else if (act == CSB_ACT_LEAKYRELU) {
+      if (alpha >= 0.f && alpha <= 1.f) {               // warp-uniform: leaky(v) == max(v, alpha v) for a slope in [0, 1]
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], alpha * v[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : alpha * v[j];
+      }
+    }
+  }
 }
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+// v *= act'(a) with a = saved activation output
+template <bool ELU>
+__device__ __forceinline__ void act_bwd32(int act, float alpha, float (&v)[32], const float (&a)[32]) {
+  if constexpr (ELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = a[j] > 0.f ? v[j] : v[j] * (a[j] + 1.f);
+  } else {
+    if (act == CSB_ACT_RELU || act == CSB_ACT_LEAKYRELU) {
+      const float neg = act == CSB_ACT_LEAKYRELU ? alpha : 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = a[j] > 0.f ? v[j] : neg * v[j];
+    }
+  }
 }
 
-// One 32-column step of the epilogue.  tile_row/tile_col are tile-relative, grow/gcol global.
-template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint8_t* cst, const float* sbias, int tile_row, int tile_col,
-                                               int grow, int gcol, const uint32_t (&raw)[32], float& loss_acc, uint32_t mask_word) {
+// per-tile facts about the output row a thread owns
+struct RowInfo {
+  int grow;          // global row of the GEMM
+  bool in_range;     // grow < M: the row exists (stores allowed)
+  bool row_ok;       // a real sample row (not a conv halo row, not past M): contributes to the loss
+  bool zero_row;     // conv halo row: stored as zeros
+  int64_t yrow;      // row of the user's target / prediction arrays (no halo rows there)
+};
+__device__ __forceinline__ RowInfo make_row_info(const GemmParams& p, int grow) {
+  RowInfo r;
+  r.grow = grow; r.in_range = grow < p.M; r.row_ok = r.in_range; r.yrow = grow;
+  if (p.halo_period > 0) {
+    const int rr = grow % p.halo_period;
+    if (rr == 0 || rr == p.halo_period - 1) r.row_ok = false;
+    r.yrow = (int64_t)(grow / p.halo_period) * (p.halo_period - 2) + rr - 1;
+  }
+  r.zero_row = p.halo_period > 0 && !r.row_ok;
+  return r;
+}
+
+// One 32-column step of the epilogue.  gcol = global column; sbias = the layer's bias vector in shared memory;
+// `sv` holds the 32 saved bf16 values of EPI_DGRAD / EPI_BIAS_ADD.
+template <int EPI, bool ELU>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float* sbias, const RowInfo& ri, int gcol, const uint32_t (&raw)[32],
+                                               const uint32_t (&sv)[16], float& loss_acc, uint32_t mask_word) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-  bool row_ok = grow < p.M;
-  int64_t yrow = grow;                               // row of the user's target / prediction arrays (no halo rows there)
-  if (p.halo_period > 0) {
-    const int rr = grow % p.halo_period;
-    if (rr == 0 || rr == p.halo_period - 1) row_ok = false;
-    yrow = (int64_t)(grow / p.halo_period) * (p.halo_period - 2) + rr - 1;
+  const bool st_ok = ri.in_range && !(p.dbg & 4);
+  __nv_bfloat16* out16 = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)ri.grow * p.ld_out + gcol;
+  constexpr bool USE_BIAS = (EPI == EPI_BIAS_ACT || EPI == EPI_BIAS_ADD || EPI == EPI_HEAD_LOSS || EPI == EPI_HEAD_OUT);
+  if constexpr (USE_BIAS) {
+    if (!(p.dbg & 1)) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(sbias + gcol + 4 * q);   // same address across the warp: broadcast
+        v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+      }
+    }
   }
-  const bool zero_row = p.halo_period > 0 && !row_ok;   // halo rows (and rows past M) of a conv layout are stored as zeros
 
   if constexpr (EPI == EPI_F32) {
-    if (row_ok) store_f32x32(reinterpret_cast<float*>(p.out) + (size_t)grow * p.ld_out + gcol, v);
+    if (ri.row_ok) store_f32x32(reinterpret_cast<float*>(p.out) + (size_t)ri.grow * p.ld_out + gcol, v);
   } else if constexpr (EPI == EPI_BIAS_ACT) {
-    float b[32];
-    load_smem_f32x32(sbias + tile_col, b);
+    if (p.mask_out != nullptr) {
+      // sign bits of the pre-activation (the activations here preserve the sign; act' of ReLU / LeakyReLU needs nothing else):
+      // one funnel shift per element collects "z < 0" from column 31 down to column 0, so that bit j <-> column j.
+      // Chunk-major layout: the 32 rows of a warp write 32 consecutive words.  (z == +0 counts as positive; TF's ReluGrad
+      // gives 0 there -- a measure-zero difference.)
+      uint32_t m = 0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] += b[j];
-    act_fwd_vec(p.act, p.alpha, v);
-    if (zero_row) {
+      for (int j = 31; j >= 0; --j) m = __funnelshift_l(__float_as_uint(v[j]), m, 1);
+      if (st_ok) p.mask_out[(size_t)(gcol >> 5) * p.ld_mask + ri.grow] = ~m;
+    }
+    act_fwd32<ELU>(p.act, p.alpha, v);
+    if (ri.zero_row) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = 0.f;
     }
-    if (p.mask_out != nullptr) {
-      const uint32_t m = cst_store32_mask(cst, tile_row, tile_col, v);
-      if (grow < p.M) p.mask_out[(size_t)grow * p.ld_mask + (gcol >> 5)] = m;
-    } else {
-      cst_store32(cst, tile_row, tile_col, v);
-    }
+    if (st_ok) store_bf16x32_global(out16, v);
   } else if constexpr (EPI == EPI_DGRAD_MASK) {
     // act'(a) through the sign bit: relu -> {1, 0}, leaky relu -> {1, alpha}
     const float neg = p.act == CSB_ACT_LEAKYRELU ? p.alpha : 0.f;
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = ((mask_word >> j) & 1u) ? v[j] : neg * v[j];
-    if (zero_row) {
+    if (ri.zero_row) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = 0.f;
     }
-    cst_store32(cst, tile_row, tile_col, v);
+    if (st_ok) store_bf16x32_global(out16, v);
   } else if constexpr (EPI == EPI_DGRAD) {
     float a[32];
-    cst_load32(cst, tile_row, tile_col, a);        // saved activation tile, TMA-loaded by the producer warp
-    act_bwd_vec(p.act, p.alpha, v, a);
-    if (zero_row) {
+    unpack_bf16x32(sv, a);                          // saved activation (same rows / columns as the output)
+    act_bwd32<ELU>(p.act, p.alpha, v, a);
+    if (ri.zero_row) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = 0.f;
     }
-    cst_store32(cst, tile_row, tile_col, v);       // in place
+    if (st_ok) store_bf16x32_global(out16, v);
   } else if constexpr (EPI == EPI_BIAS_ADD) {
-    float a[32], b[32];
-    cst_load32(cst, tile_row, tile_col, a);        // tile to add (residual branch / partial gradient), TMA-loaded
-    load_smem_f32x32(sbias + tile_col, b);
+    float a[32];
+    unpack_bf16x32(sv, a);                          // tile to add (residual branch / partial gradient)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = zero_row ? 0.f : v[j] + b[j] + a[j];
-    cst_store32(cst, tile_row, tile_col, v);
+    for (int j = 0; j < 32; ++j) v[j] = ri.zero_row ? 0.f : v[j] + a[j];
+    if (st_ok) store_bf16x32_global(out16, v);
   } else {
-    // head: p = (col >= head_relu_from) ? relu(z) : act(z).  The activation switch is hoisted out of the element loops
-    // (act_*_vec): a per-element switch bloats the code past the instruction cache.
-    float b[32], dact[32];
-    load_smem_f32x32(sbias + tile_col, b);
+    // head: p = (col >= head_relu_from) ? relu(z) : act(z)
+    float z[32], dact[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) { b[j] += v[j]; v[j] = b[j]; dact[j] = 1.f; }      // b = z
-    act_fwd_vec(p.act, p.alpha, v);                                                   // v = act(z)
-    act_bwd_vec(p.act, p.alpha, dact, v);                                             // dact = act'(z) through act(z)
+    for (int j = 0; j < 32; ++j) { z[j] = v[j]; dact[j] = 1.f; }
+    act_fwd32<ELU>(p.act, p.alpha, v);                                                // v = act(z)
+    act_bwd32<ELU>(p.act, p.alpha, dact, v);                                          // dact = act'(z) through act(z)
     if (p.head_relu_from >= 0 && gcol + 32 > p.head_relu_from) {                      // warp-uniform
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         if (gcol + j >= p.head_relu_from) {
-          v[j] = fmaxf(b[j], 0.f);
-          dact[j] = b[j] > 0.f ? 1.f : 0.f;
+          v[j] = fmaxf(z[j], 0.f);
+          dact[j] = z[j] > 0.f ? 1.f : 0.f;
         }
       }
     }
@@ -439,21 +431,21 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint8_t* cst
     }
     if constexpr (EPI == EPI_HEAD_OUT) {
       if (p.inv_out_scale != nullptr) {
-        load_f32x32(p.inv_out_scale + gcol, b);
+        load_f32x32(p.inv_out_scale + gcol, z);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] *= b[j];
+        for (int j = 0; j < 32; ++j) v[j] *= z[j];
       }
-      if (row_ok) {
+      if (ri.row_ok) {
         if (gcol + 32 <= p.out_dim) {
-          store_f32x32(p.pred + (size_t)yrow * p.ld_pred + gcol, v);
+          store_f32x32(p.pred + (size_t)ri.yrow * p.ld_pred + gcol, v);
         } else {
           for (int j = 0; j < 32; ++j)
-            if (gcol + j < p.out_dim) p.pred[(size_t)yrow * p.ld_pred + gcol + j] = v[j];
+            if (gcol + j < p.out_dim) p.pred[(size_t)ri.yrow * p.ld_pred + gcol + j] = v[j];
         }
       }
     } else {  // EPI_HEAD_LOSS: finish 8 columns at a time to keep the live register set small
-      if (row_ok && p.pred != nullptr && gcol + 32 <= p.out_dim) store_f32x32(p.pred + (size_t)yrow * p.ld_pred + gcol, v);
-      const float* yptr = p.y + (size_t)yrow * p.ld_y + gcol;
+      if (ri.row_ok && p.pred != nullptr && gcol + 32 <= p.out_dim) store_f32x32(p.pred + (size_t)ri.yrow * p.ld_pred + gcol, v);
+      const float* yptr = p.y + (size_t)ri.yrow * p.ld_y + gcol;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         float yv[8], w[8];
@@ -462,7 +454,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint8_t* cst
         w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w; w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
 #pragma unroll
         for (int j = 0; j < 8; ++j) yv[j] = 0.f;
-        if (row_ok) {
+        if (ri.row_ok) {
           if (gcol + 8 * g + 8 <= p.out_dim && (p.ld_y & 3) == 0) {
             const float4 y0 = __ldg(reinterpret_cast<const float4*>(yptr + 8 * g));
             const float4 y1 = __ldg(reinterpret_cast<const float4*>(yptr + 8 * g + 4));
@@ -475,7 +467,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint8_t* cst
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int c = 8 * g + j;
-          const float d = row_ok ? v[c] - yv[j] : 0.f;
+          const float d = ri.row_ok ? v[c] - yv[j] : 0.f;
           if (p.loss_kind == CSB_LOSS_MSE) {
             loss_acc += w[j] * d * d;
             dact[c] *= 2.f * w[j] * d * p.grad_scale;
@@ -489,34 +481,35 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint8_t* cst
           }
         }
       }
-      if (!row_ok) {
+      if (!ri.row_ok) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) dact[j] = 0.f;
       }
-      cst_store32(cst, tile_row, tile_col, dact);
+      if (st_ok) store_bf16x32_global(out16, dact);
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// gemm_tn_kernel: persistent, K-major x K-major.   10 warps: 0-7 epilogue (two per TMEM lane quadrant, each taking
-// half of the tile's columns), 8 = TMA producer, 9 = TMEM owner + MMA issuer.
-// bf16 results are staged in a swizzled smem tile and written with TMA (full 128 B lines); the saved-activation tile
-// of the data-gradient epilogue arrives the same way (TMA load issued by the producer warp behind the k-loop).
+// gemm_tn_kernel: persistent, K-major x K-major.   18 warps: 0-15 epilogue (four per TMEM lane quadrant = four per SM
+// sub-partition, each taking a quarter of the tile's columns), 16 = TMA producer, 17 = TMEM owner + MMA issuer.
+// The epilogue warps are independent of each other: each waits for the accumulator, walks its 32-column steps
+// (tcgen05.ld -> registers -> fused math -> 256-bit global stores) and releases the TMEM buffer; no staging tile, no
+// named barriers, so all of the shared memory beyond the bias vector belongs to the operand ring.  Four warps per
+// sub-partition (instead of two with twice the columns) is what hides the tcgen05.ld / store latencies.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int TN_EPI_WARPS = 8;
+constexpr int TN_EPI_WARPS = 16;
 constexpr int TN_EPI_THREADS = TN_EPI_WARPS * 32;
 constexpr int TN_THREADS = TN_EPI_THREADS + 64;
+constexpr int TN_PRODUCER_WARP = TN_EPI_WARPS, TN_MMA_WARP = TN_EPI_WARPS + 1;
 
 template <int BN, int STAGES, int CG = 1>
 struct TnSmem {
   static constexpr int A_BYTES = BM * BK * 2;   // 16 KB
   static constexpr int B_BYTES = (BN / CG) * BK * 2;   // cta_group::2: each CTA of the pair holds half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int CST_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int CST_BYTES = BN * BM * 2;
-  static constexpr int BIAS_OFFSET = CST_OFFSET + CST_BYTES;
-  static constexpr int BAR_OFFSET = BIAS_OFFSET + BN * 4;
+  static constexpr int BIAS_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFFSET = BIAS_OFFSET + TN_BIAS_SMEM * 4;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // barriers + slack for manual 1024 B alignment
   static_assert(TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
 };
@@ -524,34 +517,29 @@ struct TnSmem {
 // CG = 1: one CTA per 128 x BN tile.  CG = 2 (launched as clusters of two): a CTA pair owns a 256 x BN tile with
 // tcgen05 cta_group::2 -- each CTA loads its 128 rows of A and HALF of the B tile, the leader CTA issues the MMAs for
 // both, each CTA runs the epilogue of its own 128 rows.  Halves the B traffic and the B footprint per stage.
-template <int BN, int STAGES, int EPI, int CG>
+template <int BN, int STAGES, int EPI, int CG, bool ELU>
 __global__ void __launch_bounds__(TN_THREADS, 1)
-gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_saved, const GemmParams p) {
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
   using L = TnSmem<BN, STAGES, CG>;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   const bool is_leader = cta_rank == 0;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static_assert(2 * BN <= 512, "two accumulator buffers must fit the 512 TMEM columns");
-  constexpr bool CST_OUT = (EPI == EPI_BIAS_ACT || EPI == EPI_DGRAD || EPI == EPI_HEAD_LOSS || EPI == EPI_BIAS_ADD || EPI == EPI_DGRAD_MASK);
-  constexpr bool CST_IN = (EPI == EPI_DGRAD || EPI == EPI_BIAS_ADD);
+  constexpr bool SAVED_IN = (EPI == EPI_DGRAD || EPI == EPI_BIAS_ADD);
   constexpr bool USE_BIAS = (EPI == EPI_BIAS_ACT || EPI == EPI_HEAD_LOSS || EPI == EPI_HEAD_OUT || EPI == EPI_BIAS_ADD);
-  constexpr int SLAB_BYTES = BM * 128;   // one 64-column slab of the staging tile
-  constexpr int HALF = BN / 2, NCH = HALF / 32;
+  constexpr int QCOLS = BN / 4, NCH = QCOLS / 32;      // columns / 32-column steps per epilogue warp
+  static_assert(NCH >= 1, "BN must be at least 128");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B atoms are 1024 B aligned
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  uint8_t* cst = smem_gen + L::CST_OFFSET;
   float* sbias = reinterpret_cast<float*>(smem_gen + L::BIAS_OFFSET);
   const uint32_t bar_base = smem_base + L::BAR_OFFSET;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-  const uint32_t cst_full = bar_base + 8u * (2 * STAGES + 4);
-  const uint32_t cst_empty = bar_base + 8u * (2 * STAGES + 5);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + L::BAR_OFFSET + 8 * (2 * STAGES + 6));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + L::BAR_OFFSET + 8 * (2 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m_blocks = ((p.M + BM - 1) / BM + CG - 1) / CG;       // in units of CG m-blocks (pairs when CG == 2)
@@ -560,33 +548,36 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int num_kb = p.K / BK;
   const int first_tile = (int)(blockIdx.x / CG), tile_stride = (int)(gridDim.x / CG);   // both CTAs of a pair walk the same tiles
 
-  if (warp == 8 && lane == 0) {
+  if (warp == TN_PRODUCER_WARP && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
-    if (CST_OUT) tma_prefetch_desc(&tmap_out);
-    if (CST_IN) tma_prefetch_desc(&tmap_saved);
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     // the leader's "accumulator drained" barrier collects the epilogue warps of BOTH CTAs
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TN_EPI_WARPS * CG); }
-    mbar_init(cst_full, 1);
-    mbar_init(cst_empty, 1);
     fence_mbar_init();
   }
-  if (warp == 9) {
+  if (warp == TN_MMA_WARP) {
     if constexpr (CG == 2) { tmem_alloc_2sm(smem_u32(tmem_slot), TMEM_COLS); tmem_relinquish_2sm(); }
     else { tmem_alloc(smem_u32(tmem_slot), TMEM_COLS); tmem_relinquish(); }
+  }
+  if constexpr (USE_BIAS) {                          // whole bias vector, zero-extended to the tile grid (host checks N <= TN_BIAS_SMEM)
+    for (int i = threadIdx.x; i < num_n_blocks * BN; i += TN_THREADS) sbias[i] = (i < p.N) ? __ldg(p.bias + i) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
   if constexpr (CG == 2) cluster_sync_all();       // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (p.stats != nullptr && threadIdx.x == 0) {
+    p.stats[4 * blockIdx.x + 0] = (unsigned long long)clock64();
+    p.stats[4 * blockIdx.x + 2] = globaltimer_ns();
+  }
 
-  if (warp == 8) {
+  if (warp == TN_PRODUCER_WARP) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int s = 0; uint32_t ph = 0; int t = 0;
-      for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++t) {
+      int s = 0; uint32_t ph = 0;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
         const int m0 = ((tile / num_n_blocks) * CG + (int)cta_rank) * BM, n0 = (tile % num_n_blocks) * BN;
         const int nb0 = n0 + (int)cta_rank * (min(BN, p.N - n0) / CG);       // this CTA's share of the B rows
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -595,30 +586,23 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const int tap = p.kb_per_tap ? kb / p.kb_per_tap : 0;
           const int ka = (kb - tap * p.kb_per_tap) * BK;          // column block inside the (un-replicated) A matrix
           const int tap_shift = p.kb_per_tap ? tap - p.tap_center : 0;   // may be -1 at the top: TMA zero-fills out-of-range rows
+          const bool ld_a = !(p.dbg & (16 | 128)), ld_b = !(p.dbg & (16 | 64));      // both true in production
+          const uint32_t tx = (ld_a ? (uint32_t)L::A_BYTES : 0u) + (ld_b ? (uint32_t)(p.b_box_rows * BK * 2) : 0u);
           if constexpr (CG == 2) {
             // one expect_tx on the leader's barrier covers the four loads of the pair
-            if (is_leader) mbar_expect_tx(full_bar(s), (uint32_t)(2 * (L::A_BYTES + p.b_box_rows * BK * 2)));
-            tma_load_2d_2sm(sa, &tmap_a, full_bar(s), ka, m0 + tap_shift);
-            tma_load_2d_2sm(sa + L::A_BYTES, &tmap_b, full_bar(s), kb * BK, nb0);
+            if (is_leader) mbar_expect_tx(full_bar(s), 2 * tx);
+            if (ld_a) tma_load_2d_2sm(sa, &tmap_a, full_bar(s), ka, m0 + tap_shift);
+            if (ld_b) tma_load_2d_2sm(sa + L::A_BYTES, &tmap_b, full_bar(s), kb * BK, nb0);
           } else {
-            mbar_expect_tx(full_bar(s), (uint32_t)(L::A_BYTES + p.b_box_rows * BK * 2));
-            tma_load_2d(sa, &tmap_a, full_bar(s), ka, m0 + tap_shift);
-            tma_load_2d(sa + L::A_BYTES, &tmap_b, full_bar(s), kb * BK, nb0);
+            mbar_expect_tx(full_bar(s), tx);
+            if (ld_a) tma_load_2d(sa, &tmap_a, full_bar(s), ka, m0 + tap_shift);
+            if (ld_b) tma_load_2d(sa + L::A_BYTES, &tmap_b, full_bar(s), kb * BK, nb0);
           }
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
-        if constexpr (CST_IN) {
-          // saved-activation tile of THIS tile, behind its k-loop so that the ring keeps running ahead; the staging
-          // tile is free once the previous tile's TMA store has finished reading it
-          const int slabs = (min(BN, p.N - n0) + 63) / 64;
-          if (t > 0) mbar_wait(cst_empty, (uint32_t)(t - 1) & 1u);    // arrival #k = "the store of tile k has been read out"
-          mbar_expect_tx(cst_full, (uint32_t)(slabs * SLAB_BYTES));
-          for (int sl = 0; sl < slabs; ++sl)
-            tma_load_2d(smem_base + L::CST_OFFSET + sl * SLAB_BYTES, &tmap_saved, cst_full, n0 + 64 * sl, m0);
-        }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == TN_MMA_WARP) {
     // ===================== MMA issuer =====================
     if (lane == 0 && is_leader) {
       int s = 0; uint32_t ph = 0; int t = 0;
@@ -638,6 +622,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint64_t db = make_desc_kmajor_sw128(sa + L::A_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
+            if (p.dbg & 32) break;
             // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
             if constexpr (CG == 2) umma_f16_2sm(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
             else umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
@@ -651,8 +636,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else {
-    // ===================== epilogue: warp w -> TMEM lanes 32*(w&3).., columns [HALF*(w>>2), HALF*(w>>2)+HALF) ==========
-    const int q = warp & 3, hf = warp >> 2;
+    // ===================== epilogue: warp w -> TMEM lanes 32*(w&3).., columns [QCOLS*(w>>2), QCOLS*(w>>2)+QCOLS) ==========
+    const int q = warp & 3, cq = warp >> 2;
     const int tile_row = q * 32 + lane;
     int t = 0;
     for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++t) {
@@ -660,46 +645,48 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int m0 = mb * BM, n0 = (tile % num_n_blocks) * BN;
       const int n_valid = min(BN, p.N - n0);
       const int acc = t & 1;
-      if constexpr (CST_OUT) {
-        // the previous tile's TMA store was only committed, not waited for: it has had a whole MMA tile of time to drain
-        if (threadIdx.x == 0 && t > 0) {
-          tma_store_wait_read();
-          if constexpr (CST_IN) mbar_arrive(cst_empty);       // producer may now load this tile's saved activations
-        }
-      }
-      if constexpr (USE_BIAS) {
-        if (!(p.dbg & 1))
-          for (int i = threadIdx.x; i < BN; i += TN_EPI_THREADS) sbias[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
-      }
+      const RowInfo ri = make_row_info(p, m0 + tile_row);
+      const int c0 = cq * QCOLS;                              // tile-relative first column of this warp (warp-uniform)
+      // everything that does not depend on the accumulator is requested before waiting for it
       uint32_t mask_words[NCH];
 #pragma unroll
       for (int i = 0; i < NCH; ++i) mask_words[i] = 0u;
-      if constexpr (EPI == EPI_DGRAD_MASK) {                  // independent of the MMA: issued before waiting for the accumulator
-        if (m0 + tile_row < p.M) {
+      if constexpr (EPI == EPI_DGRAD_MASK) {
+        if (ri.in_range) {
 #pragma unroll
-          for (int i = 0; i < NCH; ++i) {
-            const int c = hf * HALF + 32 * i;
-            if (c < n_valid) mask_words[i] = __ldg(p.mask_in + (size_t)(m0 + tile_row) * p.ld_mask + ((n0 + c) >> 5));
-          }
+          for (int i = 0; i < NCH; ++i)
+            if (c0 + 32 * i < n_valid) mask_words[i] = __ldg(p.mask_in + (size_t)((n0 + c0 + 32 * i) >> 5) * p.ld_mask + ri.grow);
+        }
+      }
+      uint32_t sv[NCH][16];
+#pragma unroll
+      for (int i = 0; i < NCH; ++i)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sv[i][j] = 0u;
+      if constexpr (SAVED_IN) {
+        if (ri.in_range) {
+#pragma unroll
+          for (int i = 0; i < NCH; ++i)
+            if (c0 + 32 * i < n_valid) load_bf16x32_global_raw(p.saved + (size_t)ri.grow * p.ld_saved + n0 + c0 + 32 * i, sv[i]);
         }
       }
       mbar_wait(tfull_bar(acc), (uint32_t)(t >> 1) & 1u);
       tc_fence_after();
-      if constexpr (CST_IN) mbar_wait(cst_full, (uint32_t)t & 1u);
-      named_bar_sync(1, TN_EPI_THREADS);                      // bias staged; staging tile free; everyone past the waits
       float loss_acc = 0.f;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + hf * HALF);
-      uint32_t raw[2][32];
-      if (hf * HALF < n_valid && !(p.dbg & 8)) tmem_ld_32x32(taddr, raw[0]);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0);
 #pragma unroll
       for (int i = 0; i < NCH; ++i) {
-        const int c = hf * HALF + 32 * i;                     // tile-relative column of this step (warp-uniform)
+        const int c = c0 + 32 * i;                            // tile-relative column of this step (warp-uniform)
         if (c < n_valid) {
+          uint32_t raw[32];
           if (!(p.dbg & 8)) {
+            tmem_ld_32x32(taddr + (uint32_t)(32 * i), raw);
             tmem_ld_wait();
-            if (i + 1 < NCH && c + 32 < n_valid) tmem_ld_32x32(taddr + (uint32_t)(32 * (i + 1)), raw[(i + 1) & 1]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) raw[j] = 0u;
           }
-          if (!(p.dbg & 2)) epilogue_chunk<EPI>(p, cst, sbias, tile_row, c, m0 + tile_row, n0 + c, raw[i & 1], loss_acc, mask_words[i]);
+          if (!(p.dbg & 2)) epilogue_chunk<EPI, ELU>(p, sbias, ri, n0 + c, raw, sv[i], loss_acc, mask_words[i]);
         }
       }
       tc_fence_before();
@@ -713,27 +700,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
         if (lane == 0 && m0 < p.M) p.loss_partials[(mb * num_n_blocks + (tile % num_n_blocks)) * TN_EPI_WARPS + warp] = loss_acc * p.grad_scale;
       }
-      if constexpr (CST_OUT) {
-        fence_proxy_async_smem();                             // generic-proxy smem writes -> visible to the TMA engine
-        named_bar_sync(1, TN_EPI_THREADS);
-        if (threadIdx.x == 0 && !(p.dbg & 4)) {
-          const int slabs = (n_valid + 63) / 64;
-          for (int sl = 0; sl < slabs; ++sl) tma_store_2d(&tmap_out, smem_base + L::CST_OFFSET + sl * SLAB_BYTES, n0 + 64 * sl, m0);
-          tma_store_commit();                                 // waited for at the start of the next tile / before exit
-        }
-      } else {
-        named_bar_sync(1, TN_EPI_THREADS);                    // bias buffer reusable
-      }
-    }
-    if constexpr (CST_OUT) {
-      if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before exit
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (p.stats != nullptr && threadIdx.x == 0) {
+    p.stats[4 * blockIdx.x + 1] = (unsigned long long)clock64();
+    p.stats[4 * blockIdx.x + 3] = globaltimer_ns();
+  }
   if constexpr (CG == 2) cluster_sync_all();       // no CTA leaves (or frees TMEM) while its peer may still signal it
-  if (warp == 9) {
+  if (warp == TN_MMA_WARP) {
     tc_fence_after();
     if constexpr (CG == 2) tmem_dealloc_2sm(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
