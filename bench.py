@@ -236,16 +236,19 @@ def main():
 
     # ------------------------------------------------------------------ end to end from pinned host buffers
     e2e_steps = max(3, min(args.steps, 50))
-    host = [tuple(t_.cpu().pin_memory() for t_ in batches[i]) for i in range(2)]
-    for it in range(3):
-        trainer.step(*host[it % 2])
+    # every step copies its own x,y from pinned host memory and reads its own loss back; the engine's two staging slots
+    # let the copy of step i+1 overlap the compute of step i (sync=False), as an input pipeline with prefetch does
+    host = [tuple(t_.cpu().pin_memory() for t_ in batches[i]) for i in range(4)]
+    for it in range(4):
+        trainer.step(*host[it % 4], sync=False)
     barrier()
     t0 = time.perf_counter()
     ev0.record()
     for it in range(e2e_steps):
-        loss = trainer.step(*host[it % 2])
+        loss_slot = trainer.step(*host[it % 4], sync=False)
     ev1.record()
     barrier()
+    loss = float(loss_slot.item())
     e2e_ms = max(ev0.elapsed_time(ev1), 0.0)
     wall_ms = 1e3 * (time.perf_counter() - t0)
     t = torch.tensor([e2e_ms], device="cuda")
@@ -289,7 +292,9 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "columns/s", "h2d_bytes_per_step": world * B * (IN_DIM + OUT_DIM) * 4,
                         "d2h_bytes_per_step": world * 4, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                         "wall_ms_per_step": wall_ms / e2e_steps, "last_loss": loss,
-                        "api": "climsim_b200.Trainer.step(x_pinned, y_pinned) -> csb_mlp_train_step_host (N=1)"},
+                        "api": "climsim_b200.Trainer.step(x_pinned, y_pinned, sync=False) -> csb_mlp_train_step_host_async (N=1) / "
+                               "csb_mlp_stage_host_batch + train_step + all-reduce + apply_opt (N>1); per step: H2D of x,y into one of two "
+                               "staging slots on the copy stream (overlaps the previous step's compute), D2H of the loss into a pinned slot"},
                 "gpu_launches": launches, "roofline": roofline, "kernels": kinds,
                 "kernels_note": f"per-kind times from a second pass of {prof_steps} steps with per-launch CUDA events (eager launches, "
                                 f"{prof_ms_total / prof_steps:.4f} ms/step); the timed region replays the step as a CUDA graph",

@@ -68,6 +68,10 @@ SIGNATURES = {
     "csb_mlp_apply_opt": (C.c_int, [_VP, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _VP]),
     "csb_mlp_train_step_host": (C.c_int, [_VP, _VP, _VP, C.c_int64, C.c_float, C.c_uint32, C.c_int, C.c_float,
                                           C.c_float, C.c_float, C.c_float, C.c_float, _P(C.c_float), _VP]),
+    "csb_mlp_stage_host_batch": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP, _P(_VP), _P(_VP)]),
+    "csb_mlp_release_staged": (C.c_int, [_VP, _VP]),
+    "csb_mlp_train_step_host_async": (C.c_int, [_VP, _VP, _VP, C.c_int64, C.c_float, C.c_uint32, C.c_int, C.c_float,
+                                                C.c_float, C.c_float, C.c_float, C.c_float, _VP, _VP]),
     "csb_mlp_launch_count": (C.c_int64, [_VP]),
     "csb_mlp_profile": (C.c_int, [_VP, C.c_int]),
     "csb_mlp_profile_read": (C.c_int, [_VP, _P(C.c_double), _P(C.c_int64), C.c_int]),

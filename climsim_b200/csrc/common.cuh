@@ -53,6 +53,14 @@ __device__ __forceinline__ float act_bwd_from_out(int act, float alpha, float a)
   }
 }
 
+// ---- programmatic dependent launch ------------------------------------------------------------------------------
+// Every kernel of the training step is launched with cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs may
+// start (barrier setup, TMEM allocation, descriptor prefetch) while the previous kernel drains, and pdl_wait() blocks
+// until that kernel has completed and its memory is visible.  pdl_wait() precedes the first global-memory access of
+// every such kernel, which also makes completion transitive along the stream.  Both are no-ops in a normal launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);   // .x = lo (low 16 bits), .y = hi
   return *reinterpret_cast<uint32_t*>(&v);

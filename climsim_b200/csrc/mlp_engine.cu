@@ -70,6 +70,19 @@ static int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t cols, uint
 // tensor-core launch helpers
 // ---------------------------------------------------------------------------------------------------------------
 static bool g_use_pairs = true;     // CSB_NO_PAIRS=1 falls back to the single-CTA kernels (debugging aid)
+static bool g_use_pdl = true;       // CSB_NO_PDL=1 launches every kernel fully serialised (debugging aid)
+
+// launch with (optionally) programmatic stream serialisation: see pdl_wait() in common.cuh
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = g_use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 template <int BN, int STAGES, int EPI, int CG, bool ELU = false>
 static int launch_tn(const CUtensorMap& ta, const CUtensorMap& tb, const tc::GemmParams& p, int sm_count, cudaStream_t st) {
@@ -91,11 +104,20 @@ static int launch_tn(const CUtensorMap& ta, const CUtensorMap& tb, const tc::Gem
   cfg.blockDim = dim3(tc::TN_THREADS);
   cfg.dynamicSmemBytes = L::TOTAL;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CG > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CG; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (g_use_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = (CG > 1) ? 1 : 0;
+  cfg.numAttrs = na;
   CSB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, q));
   return CSB_OK;
 }
@@ -134,8 +156,7 @@ static int launch_nt(const CUtensorMap& ta, const CUtensorMap& tb, const tc::NtP
     attr_set = true;
   }
   dim3 grid((unsigned)(ceil_div(p.M, tc::BM) * ceil_div(p.N, BN)), (unsigned)splits);
-  kern<<<grid, tc::NUM_THREADS, L::TOTAL, st>>>(ta, tb, p);
-  CSB_CUDA_CHECK(cudaGetLastError());
+  CSB_CUDA_CHECK(launch_pdl(kern, grid, dim3(tc::NUM_THREADS), L::TOTAL, st, ta, tb, p));
   return CSB_OK;
 }
 static int launch_nt_auto(const CUtensorMap& ta, const CUtensorMap& tb, const tc::NtParams& p, int splits, cudaStream_t st) {
@@ -210,7 +231,13 @@ struct csb_mlp {
   bool has_mask = false;
   float *loss_partials = nullptr, *d_loss = nullptr;
   int n_loss_partials = 0;
-  float *x_stage = nullptr, *y_stage = nullptr;   // device staging for the *_host entry points
+  // device staging for the *_host entry points: two slots, filled on an internal copy stream so that the H2D copy of
+  // batch i+1 overlaps the compute of batch i (csb_mlp_stage_host_batch / csb_mlp_train_step_host_async)
+  float *x_stage[2] = {nullptr, nullptr}, *y_stage[2] = {nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_released[2] = {nullptr, nullptr};
+  bool released_valid[2] = {false, false};
+  int stage_next = 0, staged_cur = -1;
 
   CUtensorMap tm_wt[CSB_MAX_LAYERS];        // Wt16_l as K-major B operand of the forward GEMM
   CUtensorMap tm_w[CSB_MAX_LAYERS];         // W16_l  as K-major B operand of the data-gradient GEMM
@@ -255,7 +282,13 @@ static void free_all(csb_mlp* h) {
   for (int l = 0; l < CSB_MAX_LAYERS; ++l) { F(h->w16[l]); F(h->wt16[l]); F(h->act[l]); F(h->zbuf[l]); F(h->ln_stats[l]); F(h->amask[l]); }
   F(h->xn); F(h->dz[0]); F(h->dz[1]); F(h->pred); F(h->dx_tmp);
   F(h->d_sub); F(h->d_div); F(h->d_out_scale); F(h->d_inv_out_scale); F(h->d_loss_w); F(h->d_out_mask);
-  F(h->loss_partials); F(h->d_loss); F(h->x_stage); F(h->y_stage);
+  F(h->loss_partials); F(h->d_loss);
+  for (int i = 0; i < 2; ++i) {
+    F(h->x_stage[i]); F(h->y_stage[i]);
+    if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+    if (h->ev_released[i]) cudaEventDestroy(h->ev_released[i]);
+  }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
 }
 
 #define CSB_ALLOC(ptr, bytes)                                                                          \
@@ -279,8 +312,7 @@ static int repack_weights(csb_mlp* h, cudaStream_t st) {
     max_tiles = std::max(max_tiles, (li.Kp / 32) * (li.Np / 32));
   }
   dim3 grid((unsigned)std::min(max_tiles, 4 * h->sm_count), (unsigned)h->L);
-  simt::repack_kernel<<<grid, 256, 0, st>>>(tab);
-  CSB_CUDA_CHECK(cudaGetLastError());
+  CSB_CUDA_CHECK(launch_pdl(simt::repack_kernel, grid, dim3(256), 0, st, tab));
   prof_mark(h, K_REPACK, st);
   return CSB_OK;
 }
@@ -371,6 +403,7 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
   }
 
   g_use_pairs = getenv("CSB_NO_PAIRS") == nullptr;
+  g_use_pdl = getenv("CSB_NO_PDL") == nullptr;
   csb_mlp* h = new (std::nothrow) csb_mlp();
   CSB_REQUIRE(h != nullptr, CSB_ENOMEM, "host allocation failed");
   h->graphs_on = getenv("CSB_NO_GRAPHS") == nullptr;
@@ -639,8 +672,8 @@ int csb_mlp_grad_buffer(csb_mlp* h, float** ptr, size_t* n) {
 static int run_normalize(csb_mlp* h, const float* x, int64_t B, int apply, cudaStream_t st) {
   if (h->bf16 && h->in_dim % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
     const int grid = grid_for(B * (h->in_p / 4), 256, h->sm_count);
-    simt::normalize_bf16_vec4_kernel<<<grid, 256, 0, st>>>(x, h->d_sub, h->d_div, apply, reinterpret_cast<__nv_bfloat16*>(h->xn), B,
-                                                           h->in_dim, h->in_p);
+    CSB_CUDA_CHECK(launch_pdl(simt::normalize_bf16_vec4_kernel, dim3(grid), dim3(256), 0, st, x, h->d_sub, h->d_div, apply,
+                              reinterpret_cast<__nv_bfloat16*>(h->xn), B, h->in_dim, h->in_p));
   } else {
     const int grid = grid_for(B * h->in_p, 256, h->sm_count);
     simt::normalize_kernel<<<grid, 256, 0, st>>>(x, h->in_dim, h->d_sub, h->d_div, apply,
@@ -763,9 +796,10 @@ int csb_mlp_forward(csb_mlp* h, const float* x, float* y_pred, int64_t B, uint32
 // ---------------------------------------------------------------------------------------------------------------
 // backward chain: given dZ_{L-1} in dz(L-1), produce all parameter gradients (and optionally dx)
 // ---------------------------------------------------------------------------------------------------------------
-static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st) {
+static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st, int n_loss_partials = 0, float* loss_out = nullptr) {
   simt::SegmentTable tab;
   tab.n = 0;
+  tab.loss_partials = h->loss_partials; tab.n_loss = n_loss_partials; tab.loss_out = loss_out;
   int64_t max_len = 4;
   for (int l = h->L - 1; l >= 0; --l) {
     const LayerInfo& li = h->layer[l];
@@ -878,9 +912,8 @@ static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st)
   }
   // ---- deterministic reduction of all split partials into the flat gradient buffer (one launch, blockIdx.y = segment)
   {
-    dim3 grid((unsigned)std::min<int64_t>(ceil_div(max_len / 4, 256), 2 * h->sm_count), (unsigned)tab.n);
-    simt::reduce_partials_kernel<<<grid, 256, 0, st>>>(tab);
-    CSB_CUDA_CHECK(cudaGetLastError());
+    dim3 grid((unsigned)std::min<int64_t>(ceil_div(max_len / 4, 256), 2 * h->sm_count), (unsigned)(tab.n + (loss_out ? 1 : 0)));
+    CSB_CUDA_CHECK(launch_pdl(simt::reduce_partials_kernel, grid, dim3(256), 0, st, tab));
     prof_mark(h, K_REDUCE, st);
   }
   return CSB_OK;
@@ -907,10 +940,8 @@ static int train_step_body(csb_mlp* h, const float* x, const float* y, int64_t B
     prof_mark(h, K_LOSS, st);
     n_partials = grid;
   }
-  simt::loss_finalize_kernel<<<1, 256, 0, st>>>(h->loss_partials, n_partials, loss_out);
-  CSB_CUDA_CHECK(cudaGetLastError());
-  prof_mark(h, K_LOSS, st);
-  if ((rc = run_backward_chain(h, B, nullptr, st))) return rc;
+  // the scalar loss is summed inside the gradient-reduction launch at the end of the backward pass
+  if ((rc = run_backward_chain(h, B, nullptr, st, n_partials, loss_out))) return rc;
   h->acts_B = -1;
   return CSB_OK;
 }
@@ -1019,15 +1050,51 @@ int csb_mlp_apply_opt(csb_mlp* h, int rule, float lr, float beta1, float beta2, 
     if (sma_t >= 5.0) o.radam_r = (float)sqrt((sma_t - 4.0) / (sma_inf - 4.0) * (sma_t - 2.0) / (sma_inf - 2.0) * sma_inf / sma_t);
   }
   const int grid = grid_for((int64_t)h->P_pad / 4, 256, h->sm_count);
-  simt::opt_kernel<<<grid, 256, 0, st>>>(h->params, h->grads, h->m, h->v, (int64_t)h->P_pad, o);
-  CSB_CUDA_CHECK(cudaGetLastError());
+  CSB_CUDA_CHECK(launch_pdl(simt::opt_kernel, dim3(grid), dim3(256), 0, st, h->params, h->grads, h->m, h->v, (int64_t)h->P_pad, o));
   prof_mark(h, K_OPT, st);
   return repack_weights(h, st);
 }
 
 static int ensure_stage(csb_mlp* h) {
-  if (!h->x_stage) { CSB_ALLOC(h->x_stage, (size_t)h->cap * h->in_dim * 4); }
-  if (!h->y_stage) { CSB_ALLOC(h->y_stage, (size_t)h->cap * h->out_dim * 4); }
+  for (int i = 0; i < 2; ++i) {
+    if (!h->x_stage[i]) { CSB_ALLOC(h->x_stage[i], (size_t)h->cap * h->in_dim * 4); }
+    if (!h->y_stage[i]) { CSB_ALLOC(h->y_stage[i], (size_t)h->cap * h->out_dim * 4); }
+    if (!h->ev_copied[i]) CSB_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
+    if (!h->ev_released[i]) CSB_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_released[i], cudaEventDisableTiming));
+  }
+  // non-blocking: must not synchronise implicitly with the legacy default stream the caller may be computing on
+  if (!h->copy_stream) CSB_CUDA_CHECK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  return CSB_OK;
+}
+
+int csb_mlp_stage_host_batch(csb_mlp* h, const float* x_host, const float* y_host, int64_t B, void* stream, float** x_dev, float** y_dev) {
+  CSB_REQUIRE(h && x_host && x_dev, CSB_EINVAL, "null argument");
+  CSB_REQUIRE((y_host == nullptr) == (y_dev == nullptr), CSB_EINVAL, "y_host and y_dev go together");
+  int rc = check_batch(h, B);
+  if (rc) return rc;
+  if ((rc = ensure_stage(h))) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int slot = h->stage_next;
+  h->stage_next ^= 1;
+  // the slot was last read by the step staged two calls ago: wait (on the host) until that step has released it.  This also
+  // bounds how far the host runs ahead of the device (one step) and therefore how long a caller must keep its host buffers.
+  if (h->released_valid[slot]) CSB_CUDA_CHECK(cudaEventSynchronize(h->ev_released[slot]));
+  CSB_CUDA_CHECK(cudaMemcpyAsync(h->x_stage[slot], x_host, (size_t)B * h->in_dim * 4, cudaMemcpyHostToDevice, h->copy_stream));
+  if (y_host) CSB_CUDA_CHECK(cudaMemcpyAsync(h->y_stage[slot], y_host, (size_t)B * h->out_dim * 4, cudaMemcpyHostToDevice, h->copy_stream));
+  CSB_CUDA_CHECK(cudaEventRecord(h->ev_copied[slot], h->copy_stream));
+  CSB_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_copied[slot], 0));
+  h->staged_cur = slot;
+  h->released_valid[slot] = false;
+  *x_dev = h->x_stage[slot];
+  if (y_dev) *y_dev = h->y_stage[slot];
+  return CSB_OK;
+}
+
+int csb_mlp_release_staged(csb_mlp* h, void* stream) {
+  CSB_REQUIRE(h, CSB_EINVAL, "null handle");
+  CSB_REQUIRE(h->staged_cur >= 0, CSB_ESTATE, "no staged batch");
+  CSB_CUDA_CHECK(cudaEventRecord(h->ev_released[h->staged_cur], reinterpret_cast<cudaStream_t>(stream)));
+  h->released_valid[h->staged_cur] = true;
   return CSB_OK;
 }
 
@@ -1036,29 +1103,37 @@ int csb_mlp_forward_host(csb_mlp* h, const float* x_host, float* y_pred_host, in
   int rc = check_batch(h, B);
   if (rc) return rc;
   if (B == 0) return CSB_OK;
-  if ((rc = ensure_stage(h))) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  CSB_CUDA_CHECK(cudaMemcpyAsync(h->x_stage, x_host, (size_t)B * h->in_dim * 4, cudaMemcpyHostToDevice, st));
-  if ((rc = csb_mlp_forward(h, h->x_stage, h->y_stage, B, flags, stream))) return rc;
-  CSB_CUDA_CHECK(cudaMemcpyAsync(y_pred_host, h->y_stage, (size_t)B * h->out_dim * 4, cudaMemcpyDeviceToHost, st));
+  float* xd = nullptr;
+  if ((rc = csb_mlp_stage_host_batch(h, x_host, nullptr, B, stream, &xd, nullptr))) return rc;
+  float* yd = h->y_stage[h->staged_cur];               // the slot's target buffer doubles as the prediction staging
+  if ((rc = csb_mlp_forward(h, xd, yd, B, flags, stream))) return rc;
+  CSB_CUDA_CHECK(cudaMemcpyAsync(y_pred_host, yd, (size_t)B * h->out_dim * 4, cudaMemcpyDeviceToHost, st));
+  if ((rc = csb_mlp_release_staged(h, stream))) return rc;
   CSB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return CSB_OK;
+}
+
+int csb_mlp_train_step_host_async(csb_mlp* h, const float* x_host, const float* y_host, int64_t B, float grad_scale, uint32_t flags,
+                                  int rule, float lr, float beta1, float beta2, float eps, float wd, float* loss_host, void* stream) {
+  CSB_REQUIRE(h && x_host && y_host, CSB_EINVAL, "null argument");
+  int rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float *xd = nullptr, *yd = nullptr;
+  if ((rc = csb_mlp_stage_host_batch(h, x_host, y_host, B, stream, &xd, &yd))) return rc;
+  if ((rc = csb_mlp_train_step(h, xd, yd, B, grad_scale, flags, nullptr, stream))) return rc;
+  if ((rc = csb_mlp_release_staged(h, stream))) return rc;
+  if ((rc = csb_mlp_apply_opt(h, rule, lr, beta1, beta2, eps, wd, stream))) return rc;
+  if (loss_host) CSB_CUDA_CHECK(cudaMemcpyAsync(loss_host, h->d_loss, 4, cudaMemcpyDeviceToHost, st));
   return CSB_OK;
 }
 
 int csb_mlp_train_step_host(csb_mlp* h, const float* x_host, const float* y_host, int64_t B, float grad_scale, uint32_t flags,
                             int rule, float lr, float beta1, float beta2, float eps, float wd, float* loss_host, void* stream) {
-  CSB_REQUIRE(h && x_host && y_host, CSB_EINVAL, "null argument");
-  int rc = check_batch(h, B);
+  float loss = 0.f;      // pageable: the 4-byte D2H is staged by the driver and complete after the synchronise below
+  int rc = csb_mlp_train_step_host_async(h, x_host, y_host, B, grad_scale, flags, rule, lr, beta1, beta2, eps, wd, &loss, stream);
   if (rc) return rc;
-  if ((rc = ensure_stage(h))) return rc;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  CSB_CUDA_CHECK(cudaMemcpyAsync(h->x_stage, x_host, (size_t)B * h->in_dim * 4, cudaMemcpyHostToDevice, st));
-  CSB_CUDA_CHECK(cudaMemcpyAsync(h->y_stage, y_host, (size_t)B * h->out_dim * 4, cudaMemcpyHostToDevice, st));
-  if ((rc = csb_mlp_train_step(h, h->x_stage, h->y_stage, B, grad_scale, flags, nullptr, stream))) return rc;
-  if ((rc = csb_mlp_apply_opt(h, rule, lr, beta1, beta2, eps, wd, stream))) return rc;
-  float loss = 0.f;
-  CSB_CUDA_CHECK(cudaMemcpyAsync(&loss, h->d_loss, 4, cudaMemcpyDeviceToHost, st));
-  CSB_CUDA_CHECK(cudaStreamSynchronize(st));
+  CSB_CUDA_CHECK(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
   if (loss_host) *loss_host = loss;
   return CSB_OK;
 }

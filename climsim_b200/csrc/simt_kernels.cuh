@@ -37,6 +37,8 @@ normalize_bf16_vec4_kernel(const float* __restrict__ x, const float* __restrict_
                            __nv_bfloat16* __restrict__ out, int64_t N, int F, int Fp) {
   const int q = Fp >> 2, qv = F >> 2;                    // float4 slots per padded row / valid slots
   const int64_t total = N * q;
+  pdl_launch_dependents();
+  pdl_wait();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / q;
     const int c4 = (int)(i - r * q);
@@ -247,17 +249,9 @@ head_grad_kernel(const float* __restrict__ pred, int ldp, const float* __restric
 }
 
 // final deterministic reduction of the loss partials (single block, fp64 accumulation)
+__device__ __forceinline__ void block_sum_loss(const float* __restrict__ partials, int n, float* __restrict__ out);
 __global__ void __launch_bounds__(256) loss_finalize_kernel(const float* __restrict__ partials, int n, float* __restrict__ out) {
-  __shared__ double red[256];
-  double s = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)partials[i];
-  red[threadIdx.x] = s;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *out = (float)red[0];
+  block_sum_loss(partials, n, out);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -384,10 +378,38 @@ ln_param_grad_kernel(const T* __restrict__ du, const T* __restrict__ z, int ld, 
 // reduce split partials in a fixed order: grad[i] = sum_s ws[s*stride + i]
 // ---------------------------------------------------------------------------------------------------------------
 struct Segment { const float* ws; size_t stride; float* grad; int64_t len; int splits; };
-struct SegmentTable { int n; Segment seg[4 * CSB_MAX_LAYERS]; };
+struct SegmentTable {
+  int n; Segment seg[4 * CSB_MAX_LAYERS];
+  // optional: the scalar loss rides in the same launch (row blockIdx.y == n, one block), off the backward pass's critical path
+  const float* loss_partials; int n_loss; float* loss_out;
+};
+
+// fixed-order fp64 sum of the loss partials by one block (deterministic)
+__device__ __forceinline__ void block_sum_loss(const float* __restrict__ partials, int n, float* __restrict__ out) {
+  __shared__ double red[256];
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int i = threadIdx.x;
+  for (; i + 3 * 256 < n; i += 4 * 256) {          // four independent loads in flight per thread
+    s0 += (double)partials[i]; s1 += (double)partials[i + 256]; s2 += (double)partials[i + 512]; s3 += (double)partials[i + 768];
+  }
+  for (; i < n; i += 256) s0 += (double)partials[i];
+  red[threadIdx.x] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = (float)red[0];
+}
 
 // one launch for every gradient segment: blockIdx.y = segment
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const SegmentTable tab) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if ((int)blockIdx.y == tab.n) {
+    if (blockIdx.x == 0) block_sum_loss(tab.loss_partials, tab.n_loss, tab.loss_out);
+    return;
+  }
   const Segment sg = tab.seg[blockIdx.y];
   for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4; i < sg.len; i += (int64_t)gridDim.x * blockDim.x * 4) {
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -412,6 +434,8 @@ struct OptParams {
 __global__ void __launch_bounds__(256)
 opt_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
            const OptParams o) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4; i < n; i += (int64_t)gridDim.x * blockDim.x * 4) {
     float4 w4 = *reinterpret_cast<float4*>(w + i);
     const float4 g4 = *reinterpret_cast<const float4*>(g + i);
@@ -468,6 +492,8 @@ __global__ void __launch_bounds__(256) repack_kernel(const RepackTable tab) {
   const RepackLayer L = tab.l[blockIdx.y];
   const int tiles_n = L.Np / 32, tiles = (L.Kp / 32) * tiles_n;
   __shared__ float t[32][33];
+  pdl_launch_dependents();
+  pdl_wait();
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int k0 = (tile / tiles_n) * 32, n0 = (tile % tiles_n) * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8

@@ -560,6 +560,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if constexpr (CG == 2) { tmem_alloc_2sm(smem_u32(tmem_slot), TMEM_COLS); tmem_relinquish_2sm(); }
     else { tmem_alloc(smem_u32(tmem_slot), TMEM_COLS); tmem_relinquish(); }
   }
+  pdl_launch_dependents();                           // the next kernel may begin its own prologue as SMs free up
+  pdl_wait();                                        // everything below reads memory the previous kernel may have written
   if constexpr (USE_BIAS) {                          // whole bias vector, zero-extended to the tile grid (host checks N <= TN_BIAS_SMEM)
     for (int i = threadIdx.x; i < num_n_blocks * BN; i += TN_THREADS) sbias[i] = (i < p.N) ? __ldg(p.bias + i) : 0.f;
   }
@@ -783,6 +785,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
     tmem_relinquish();
   }
+  pdl_launch_dependents();
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();

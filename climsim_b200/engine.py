@@ -236,6 +236,37 @@ class MLPEngine:
                                                     _lib.current_stream_ptr()), "csb_mlp_train_step_host")
         return float(loss.value)
 
+    def train_step_host_async(self, x_host: torch.Tensor, y_host: torch.Tensor, loss_slot: torch.Tensor, rule: str = "adam_keras",
+                              lr: float = 1e-3, beta1: float = 0.9, beta2: float = 0.999, eps: Optional[float] = None,
+                              weight_decay: float = 0.0, grad_scale: float = 0.0, normalize_in: bool = False) -> None:
+        """``train_step_host`` without the final synchronisation: the H2D copies go to one of two staging slots on the engine's
+        copy stream (overlapping the previous step's compute) and the loss lands in ``loss_slot`` (a pinned CPU float32
+        tensor) once the current stream has passed this step.  Host buffers may be reused after two further calls."""
+        assert not x_host.is_cuda and not y_host.is_cuda and x_host.dtype == torch.float32 and y_host.dtype == torch.float32
+        assert x_host.is_contiguous() and y_host.is_contiguous() and loss_slot.is_pinned()
+        if eps is None:
+            eps = 1e-8 if rule == "adam_torch" else 1e-7
+        _lib.check(self.lib.csb_mlp_train_step_host_async(self._h, x_host.data_ptr(), y_host.data_ptr(), x_host.shape[0],
+                                                          grad_scale, self._flags(normalize_in, False, False), _lib.OPT[rule],
+                                                          lr, beta1, beta2, eps, weight_decay, loss_slot.data_ptr(),
+                                                          _lib.current_stream_ptr()), "csb_mlp_train_step_host_async")
+
+    def stage_host_batch(self, x_host: torch.Tensor, y_host: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Enqueue the H2D copies of a host batch into one of the engine's two staging slots (internal copy stream; the
+        current stream waits for them) and return CUDA tensors aliasing the slot.  Pair with ``release_staged()``."""
+        assert not x_host.is_cuda and not y_host.is_cuda and x_host.dtype == torch.float32 and y_host.dtype == torch.float32
+        assert x_host.is_contiguous() and y_host.is_contiguous()
+        B = x_host.shape[0]
+        xd, yd = C.c_void_p(), C.c_void_p()
+        _lib.check(self.lib.csb_mlp_stage_host_batch(self._h, x_host.data_ptr(), y_host.data_ptr(), B, _lib.current_stream_ptr(),
+                                                     C.byref(xd), C.byref(yd)), "csb_mlp_stage_host_batch")
+        x = torch.as_tensor(_DevPtr(xd.value, B * self.in_dim), device="cuda").view(B, self.in_dim)
+        y = torch.as_tensor(_DevPtr(yd.value, B * self.out_dim), device="cuda").view(B, self.out_dim)
+        return x, y
+
+    def release_staged(self) -> None:
+        _lib.check(self.lib.csb_mlp_release_staged(self._h, _lib.current_stream_ptr()), "csb_mlp_release_staged")
+
     def forward_host(self, x_host: torch.Tensor, normalize_in: bool = False, denorm_out: bool = False) -> torch.Tensor:
         x_host = x_host.contiguous()
         y = torch.empty(x_host.shape[0], self.out_dim, dtype=torch.float32)

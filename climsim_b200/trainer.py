@@ -36,7 +36,11 @@ def cyclical_lr(step: int, initial_lr: float = 2.5e-4, max_lr: float = 2.5e-3, s
 
 
 class Trainer:
-    """``step(x, y)`` = H2D (if host tensors) -> forward + loss + backward -> gradient all-reduce -> optimizer."""
+    """``step(x, y)`` = H2D (if host tensors) -> forward + loss + backward -> gradient all-reduce -> optimizer.
+
+    Host batches are fed through the engine's two staging slots on its copy stream, so with ``sync=False`` the H2D copy of
+    batch i+1 overlaps the compute of batch i (the role of ``tf.data`` prefetch / ``DataLoader(pin_memory=True)`` in the
+    reference's drivers); every step still performs its own H2D copy and the D2H read of its loss."""
 
     def __init__(self, engine: MLPEngine, rule: str = "adam_keras", lr: float | Callable[[int], float] = 1e-3,
                  beta1: float = 0.9, beta2: float = 0.999, eps: Optional[float] = None, weight_decay: float = 0.0,
@@ -52,36 +56,58 @@ class Trainer:
         self._grad = engine.grad_buffer() if self.world > 1 else None
         self._x = self._y = None
         self._loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._loss_host = None            # pinned ring of loss slots for the asynchronous host-fed path
 
     def _lr(self) -> float:
         return float(self.lr(self.iteration)) if callable(self.lr) else float(self.lr)
 
-    def step(self, x: torch.Tensor, y: torch.Tensor, normalize_in: bool = False, return_loss: bool = True):
-        """x (B_local, in_dim), y (B_local, out_dim): CUDA tensors, or (pinned) host tensors that are copied first.
-        Returns the loss of the GLOBAL batch as a Python float when ``return_loss`` (one D2H read), else the device scalar
-        holding this rank's share."""
+    def _loss_slot(self) -> torch.Tensor:
+        if self._loss_host is None:
+            self._loss_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+        return self._loss_host[self.iteration % 4:self.iteration % 4 + 1]
+
+    def synchronize(self) -> None:
+        """Wait for every step enqueued so far (the loss slots returned by ``step(..., sync=False)`` are valid afterwards)."""
+        torch.cuda.current_stream().synchronize()
+
+    def step(self, x: torch.Tensor, y: torch.Tensor, normalize_in: bool = False, return_loss: bool = True, sync: bool = True):
+        """x (B_local, in_dim), y (B_local, out_dim): CUDA tensors, or (pinned, contiguous) host tensors that are copied first.
+
+        Device tensors: returns the loss of the GLOBAL batch as a Python float when ``return_loss`` (one D2H read), else the
+        device scalar holding this rank's share.
+        Host tensors: the loss is always read back (4-byte D2H into a pinned slot).  ``sync=True`` waits and returns a float;
+        ``sync=False`` returns the pinned one-element tensor, valid after ``synchronize()`` (or once two further steps have
+        been issued) -- x and y must stay untouched for the same span."""
         eng = self.engine
         B = x.shape[0]
         lr = self._lr()
         on_device = x.device.type == torch.device(self.device).type
-        if self.world == 1 and not on_device:
-            loss = eng.train_step_host(x, y, rule=self.rule, lr=lr, beta1=self.beta1, beta2=self.beta2, eps=self.eps,
-                                       weight_decay=self.weight_decay, normalize_in=normalize_in)
-            self.iteration += 1
-            return loss
+        slot = None
         if not on_device:
-            if self._x is None or self._x.shape[0] < B:
-                self._x = torch.empty(B, eng.in_dim, dtype=torch.float32, device=self.device)
-                self._y = torch.empty(B, eng.out_dim, dtype=torch.float32, device=self.device)
-            self._x[:B].copy_(x, non_blocking=True)
-            self._y[:B].copy_(y, non_blocking=True)
-            x, y = self._x[:B], self._y[:B]
+            slot = self._loss_slot()
+            if self.world == 1:
+                eng.train_step_host_async(x, y, slot, rule=self.rule, lr=lr, beta1=self.beta1, beta2=self.beta2, eps=self.eps,
+                                          weight_decay=self.weight_decay, normalize_in=normalize_in)
+                self.iteration += 1
+                if not sync:
+                    return slot
+                self.synchronize()
+                return float(slot.item())
+            x, y = eng.stage_host_batch(x, y)
         scale = 1.0 / (B * self.world * eng.out_dim)            # global-mean MSE, as Keras computes on the global batch
         eng.train_step(x, y, grad_scale=scale, normalize_in=normalize_in, loss_out=self._loss)
+        if slot is not None:
+            eng.release_staged()
         if self.world > 1:
             torch.distributed.all_reduce(self._grad, group=self.pg)
-            if return_loss:
+            if return_loss or slot is not None:
                 torch.distributed.all_reduce(self._loss, group=self.pg)
         eng.apply_opt(self.rule, lr=lr, beta1=self.beta1, beta2=self.beta2, eps=self.eps, weight_decay=self.weight_decay)
         self.iteration += 1
+        if slot is not None:
+            slot.copy_(self._loss, non_blocking=True)
+            if not sync:
+                return slot
+            self.synchronize()
+            return float(slot.item())
         return float(self._loss.item()) if return_loss else self._loss

@@ -153,6 +153,22 @@ int  csb_mlp_train_step_host(csb_mlp* h, const float* x_host, const float* y_hos
                              uint32_t flags, int rule, float lr, float beta1, float beta2, float eps, float wd,
                              float* loss_host, void* stream);
 
+/* Pipelined host feed -- the engine-side counterpart of the reference's input prefetch (tf.data .prefetch at
+ * baseline_models/MLP/.../step2_retrain.py:266-276; DataLoader(pin_memory) + non-blocking copies in
+ * online_testing/.../train_mlp_h5loader.py:126-150).
+ * csb_mlp_stage_host_batch: enqueue the H2D copies of (x_host, y_host) into one of two internal staging slots on an internal
+ *   copy stream and make `stream` wait for them; *x_dev / *y_dev receive the slot's device pointers (y_host and y_dev may both
+ *   be NULL).  Blocks the host only while the slot is still being read by the step staged two calls earlier, so the copy of
+ *   batch i+1 overlaps the compute of batch i and a caller may reuse its host buffers after two further calls.
+ * csb_mlp_release_staged: call once the work reading the staged batch has been enqueued on `stream`.
+ * csb_mlp_train_step_host_async: csb_mlp_train_step_host without the final synchronisation; *loss_host (pinned memory) is
+ *   written by a D2H copy enqueued on `stream` and is valid once the stream has passed it. */
+int  csb_mlp_stage_host_batch(csb_mlp* h, const float* x_host, const float* y_host, int64_t B, void* stream, float** x_dev, float** y_dev);
+int  csb_mlp_release_staged(csb_mlp* h, void* stream);
+int  csb_mlp_train_step_host_async(csb_mlp* h, const float* x_host, const float* y_host, int64_t B, float grad_scale,
+                                   uint32_t flags, int rule, float lr, float beta1, float beta2, float eps, float wd,
+                                   float* loss_host, void* stream);
+
 /* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
 int64_t csb_mlp_launch_count(const csb_mlp* h);
 

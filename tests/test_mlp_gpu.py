@@ -353,3 +353,33 @@ def test_sign_mask_dgrad_is_bitwise_equal_to_saved_activation_path(act, monkeypa
         grads[no_mask] = eng.get_grads_flat()
         eng.close()
     np.testing.assert_array_equal(grads["0"], grads["1"])
+
+
+def test_pipelined_host_feed_matches_synchronous_steps():
+    """Trainer.step(host tensors, sync=False): H2D copies ride the engine's copy stream into two staging slots and the loss
+    comes back through a pinned slot.  Same batches, same order => the same loss trajectory and weights, bit for bit, as
+    the synchronous entry point; every staged batch is really the one that was passed (distinct batches per step)."""
+    from climsim_b200.trainer import Trainer
+    units, B, steps = SMALL_UNITS, 384, 6
+    ref = _oracle(units)
+    host = [tuple(t.pin_memory() for t in _batch(B, 100 + i)) for i in range(steps)]
+    out = {}
+    for mode in ("sync", "async"):
+        eng = _engine(units, "bf16", max_batch=B)
+        _load(eng, ref)
+        tr = Trainer(eng, rule="adam_keras", lr=1e-3)
+        if mode == "sync":
+            losses = [tr.step(x, y) for x, y in host]
+        else:
+            slots = [tr.step(x, y, sync=False) for x, y in host[:3]]
+            tr.synchronize()
+            losses = [float(s.item()) for s in slots]
+            for x, y in host[3:]:                       # the 4-slot ring is reused: read each loss before its slot comes round again
+                s = tr.step(x, y, sync=False)
+                tr.synchronize()
+                losses.append(float(s.item()))
+        out[mode] = (losses, eng.get_params_flat())
+        eng.close()
+    assert out["sync"][0] == out["async"][0]
+    np.testing.assert_array_equal(out["sync"][1], out["async"][1])
+    assert len(set(out["sync"][0])) == steps            # distinct batches gave distinct losses
