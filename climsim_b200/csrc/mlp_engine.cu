@@ -84,11 +84,12 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
-template <int BN, int STAGES, int EPI, int CG, bool ELU = false>
+template <int BN, int STAGES, int EPI, int CG, int VAR = 0>
 static int launch_tn(const CUtensorMap& ta, const CUtensorMap& tb, const tc::GemmParams& p, int sm_count, cudaStream_t st) {
   using L = tc::TnSmem<BN, STAGES, CG>;
-  auto kern = tc::gemm_tn_kernel<BN, STAGES, EPI, CG, ELU>;
-  CSB_REQUIRE(p.N <= tc::TN_BIAS_SMEM, CSB_EUNSUPPORTED, "layer width %d exceeds %d (bias vector kept in shared memory)", p.N, tc::TN_BIAS_SMEM);
+  auto kern = tc::gemm_tn_kernel<BN, STAGES, EPI, CG, VAR>;
+  CSB_REQUIRE((EPI == tc::EPI_HEAD_LOSS ? 2 : 1) * (int)round_up(p.N, BN) <= tc::TN_BIAS_SMEM, CSB_EUNSUPPORTED,
+              "layer width %d too large for the %d-float bias / loss-weight area in shared memory", p.N, tc::TN_BIAS_SMEM);
   static bool attr_set = false;
   if (!attr_set) {
     CSB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -127,22 +128,27 @@ static int launch_tn(const CUtensorMap& ta, const CUtensorMap& tb, const tc::Gem
 static inline bool tn_use_pairs(int N) { return g_use_pairs && N > 128; }
 static inline int tn_b_box_rows(int N) { return N > 128 ? (tn_use_pairs(N) ? std::min(N, 256) / 2 : std::min(N, 256)) : std::min(N, 128); }
 
-template <int EPI, bool ELU>
+template <int EPI, int VAR>
 static int launch_tn_shape(const CUtensorMap& ta, const CUtensorMap& tb, const tc::GemmParams& p, int sm_count, cudaStream_t st) {
   if (p.N > 128) {
-    if (tn_use_pairs(p.N)) return launch_tn<256, 6, EPI, 2, ELU>(ta, tb, p, sm_count, st);
-    return launch_tn<256, 4, EPI, 1, ELU>(ta, tb, p, sm_count, st);
+    if (tn_use_pairs(p.N)) return launch_tn<256, 6, EPI, 2, VAR>(ta, tb, p, sm_count, st);
+    return launch_tn<256, 4, EPI, 1, VAR>(ta, tb, p, sm_count, st);
   }
-  return launch_tn<128, 6, EPI, 1, ELU>(ta, tb, p, sm_count, st);
+  return launch_tn<128, 6, EPI, 1, VAR>(ta, tb, p, sm_count, st);
 }
 template <int EPI>
 static int launch_tn_auto(const CUtensorMap& ta, const CUtensorMap& tb, const tc::GemmParams& p, int sm_count, cudaStream_t st) {
   // ELU (expm1f in the epilogue) is a separate instantiation of the epilogues that evaluate an activation
   constexpr bool HAS_ACT = (EPI == tc::EPI_BIAS_ACT || EPI == tc::EPI_HEAD_LOSS || EPI == tc::EPI_HEAD_OUT || EPI == tc::EPI_DGRAD);
-  if constexpr (HAS_ACT) {
-    if (p.act == CSB_ACT_ELU) return launch_tn_shape<EPI, true>(ta, tb, p, sm_count, st);
+  if constexpr (EPI == tc::EPI_HEAD_LOSS) {
+    // the lean loss loop covers MSE without an output mask on a non-ELU head; everything else takes the general variant
+    if (p.act == CSB_ACT_ELU || p.loss_kind != CSB_LOSS_MSE || p.out_mask != nullptr)
+      return p.act == CSB_ACT_ELU ? launch_tn_shape<EPI, tc::VAR_ELU | tc::VAR_GENERAL_LOSS>(ta, tb, p, sm_count, st)
+                                  : launch_tn_shape<EPI, tc::VAR_GENERAL_LOSS>(ta, tb, p, sm_count, st);
+  } else if constexpr (HAS_ACT) {
+    if (p.act == CSB_ACT_ELU) return launch_tn_shape<EPI, tc::VAR_ELU>(ta, tb, p, sm_count, st);
   }
-  return launch_tn_shape<EPI, false>(ta, tb, p, sm_count, st);
+  return launch_tn_shape<EPI, 0>(ta, tb, p, sm_count, st);
 }
 static inline int tn_block_n(int N) { return N > 128 ? 256 : 128; }
 
@@ -253,6 +259,11 @@ struct csb_mlp {
   uint64_t graph_clock = 0;
   bool graphs_on = true;
   cudaStream_t cap_stream = nullptr;
+  // CSB_TRAIN_FUSED_OPT: the split partials of the last training step are still unreduced; csb_mlp_apply_opt consumes them
+  bool pending = false;
+  int64_t pending_B = 0;
+  int pending_n_loss = 0;
+  float* pending_loss_out = nullptr;
   int64_t acts_B = -1;                      // batch of the last forward that kept activations
   bool acts_normalized = false;
 };
@@ -355,6 +366,8 @@ static int build_act_maps(csb_mlp* h, int64_t B) {
 }
 
 extern "C" {
+
+static int flush_pending(csb_mlp* h, cudaStream_t st);   // reduces gradient partials left behind by CSB_TRAIN_FUSED_OPT
 
 int csb_version(void) { return CSB_VERSION; }
 
@@ -570,6 +583,9 @@ int csb_mlp_get_params(csb_mlp* h, float* params_host) {
 }
 int csb_mlp_get_grads(csb_mlp* h, float* grads_host) {
   CSB_REQUIRE(h && grads_host, CSB_EINVAL, "null argument");
+  CSB_CUDA_CHECK(cudaDeviceSynchronize());
+  int rc = flush_pending(h, 0);
+  if (rc) return rc;
   return download_padded(h, h->grads, grads_host);
 }
 static int pad_copy(csb_mlp* h, float* padded, float* user, int dir, cudaStream_t st) {
@@ -600,6 +616,8 @@ int csb_mlp_get_params_device(csb_mlp* h, float* params_dev, void* stream) {
 }
 int csb_mlp_get_grads_device(csb_mlp* h, float* grads_dev, void* stream) {
   CSB_REQUIRE(h && grads_dev, CSB_EINVAL, "null argument");
+  int rc = flush_pending(h, reinterpret_cast<cudaStream_t>(stream));
+  if (rc) return rc;
   return pad_copy(h, h->grads, grads_dev, 1, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -796,7 +814,45 @@ int csb_mlp_forward(csb_mlp* h, const float* x, float* y_pred, int64_t B, uint32
 // ---------------------------------------------------------------------------------------------------------------
 // backward chain: given dZ_{L-1} in dz(L-1), produce all parameter gradients (and optionally dx)
 // ---------------------------------------------------------------------------------------------------------------
-static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st, int n_loss_partials = 0, float* loss_out = nullptr) {
+// split-K geometry of the weight-gradient GEMM of layer l at batch B (CSB_BF16)
+static inline int wgrad_splits(const csb_mlp* h, int l, int64_t B, int* rb_per_split) {
+  const LayerInfo& li = h->layer[l];
+  const int num_rb = (int)ceil_div(B, 64);
+  int splits = std::max(1, std::min(li.max_w_splits, num_rb));
+  const int rps = (int)ceil_div(num_rb, splits);
+  if (rb_per_split) *rb_per_split = rps;
+  return (int)ceil_div(num_rb, rps);
+}
+static inline bool fused_opt_supported(const csb_mlp* h) {
+  static const bool off = getenv("CSB_NO_FUSED_OPT") != nullptr;     // debugging aid: always take the three-launch path
+  if (!h->bf16 || off) return false;
+  for (int l = 0; l < h->L; ++l) if (h->layer[l].ln) return false;
+  return true;
+}
+
+// reduce the pending split partials into the gradient buffer (and finish the pending loss) with the plain reduction kernel
+static int flush_pending(csb_mlp* h, cudaStream_t st) {
+  if (!h->pending) return CSB_OK;
+  simt::SegmentTable tab;
+  tab.n = 0;
+  tab.loss_partials = h->loss_partials; tab.n_loss = h->pending_n_loss; tab.loss_out = h->pending_loss_out;
+  int64_t max_len = 4;
+  for (int l = h->L - 1; l >= 0; --l) {
+    const LayerInfo& li = h->layer[l];
+    const int splits = wgrad_splits(h, l, h->pending_B, nullptr);
+    tab.seg[tab.n++] = {h->ws + li.ws_w_off, (size_t)li.Kp * li.Np, h->grads + li.w_off, (int64_t)li.Kp * li.Np, splits};
+    tab.seg[tab.n++] = {h->ws + li.ws_b_off, (size_t)li.Np, h->grads + li.b_off, (int64_t)li.Np, splits * (int)ceil_div(li.Kp, 128)};
+    max_len = std::max<int64_t>(max_len, (int64_t)li.Kp * li.Np);
+  }
+  dim3 grid((unsigned)std::min<int64_t>(ceil_div(max_len / 4, 256), 2 * h->sm_count), (unsigned)(tab.n + (tab.loss_out ? 1 : 0)));
+  CSB_CUDA_CHECK(launch_pdl(simt::reduce_partials_kernel, grid, dim3(256), 0, st, tab));
+  prof_mark(h, K_REDUCE, st);
+  h->pending = false;
+  return CSB_OK;
+}
+
+static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st, int n_loss_partials = 0, float* loss_out = nullptr,
+                              bool defer_reduce = false) {
   simt::SegmentTable tab;
   tab.n = 0;
   tab.loss_partials = h->loss_partials; tab.n_loss = n_loss_partials; tab.loss_out = loss_out;
@@ -828,12 +884,9 @@ static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st,
     // ---- weight gradient dW_l = in_l^T . dZ_l  (contraction over the B rows)
     int splits = 1;
     if (h->bf16) {
-      const int num_rb = (int)ceil_div(B, 64);
-      splits = std::max(1, std::min(li.max_w_splits, num_rb));
       tc::NtParams p = {};
       p.M = li.Kp; p.N = li.Np; p.R = (int)B;
-      p.rb_per_split = (int)ceil_div(num_rb, splits);
-      splits = (int)ceil_div(num_rb, p.rb_per_split);
+      splits = wgrad_splits(h, l, B, &p.rb_per_split);
       p.out = h->ws + li.ws_w_off; p.ld_out = li.Np; p.split_stride = (size_t)li.Kp * li.Np;
       p.colsum_out = h->ws + li.ws_b_off; p.colsum_stride = (size_t)li.Np;      // bias gradient fused into this kernel
       int rc = launch_nt_auto(h->tm_in[l].mn64, h->tm_dz[l].mn64, p, splits, st);
@@ -910,8 +963,11 @@ static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st,
       prof_mark(h, K_GEMM_DGRAD, st);
     }
   }
-  // ---- deterministic reduction of all split partials into the flat gradient buffer (one launch, blockIdx.y = segment)
-  {
+  // ---- deterministic reduction of all split partials into the flat gradient buffer (one launch, blockIdx.y = segment);
+  // with CSB_TRAIN_FUSED_OPT it is left to csb_mlp_apply_opt, which fuses it with the update
+  if (defer_reduce) {
+    h->pending = true; h->pending_B = B; h->pending_n_loss = n_loss_partials; h->pending_loss_out = loss_out;
+  } else {
     dim3 grid((unsigned)std::min<int64_t>(ceil_div(max_len / 4, 256), 2 * h->sm_count), (unsigned)(tab.n + (loss_out ? 1 : 0)));
     CSB_CUDA_CHECK(launch_pdl(simt::reduce_partials_kernel, grid, dim3(256), 0, st, tab));
     prof_mark(h, K_REDUCE, st);
@@ -941,7 +997,8 @@ static int train_step_body(csb_mlp* h, const float* x, const float* y, int64_t B
     n_partials = grid;
   }
   // the scalar loss is summed inside the gradient-reduction launch at the end of the backward pass
-  if ((rc = run_backward_chain(h, B, nullptr, st, n_partials, loss_out))) return rc;
+  const bool defer = (flags & CSB_TRAIN_FUSED_OPT) != 0 && fused_opt_supported(h);
+  if ((rc = run_backward_chain(h, B, nullptr, st, n_partials, loss_out, defer))) return rc;
   h->acts_B = -1;
   return CSB_OK;
 }
@@ -959,6 +1016,7 @@ int csb_mlp_train_step(csb_mlp* h, const float* x, const float* y, int64_t B, fl
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (grad_scale <= 0.f) grad_scale = 1.f / ((float)B * (float)h->out_dim);
   if ((rc = build_act_maps(h, B))) return rc;
+  if ((rc = flush_pending(h, st))) return rc;          // a deferred reduction nobody consumed (no csb_mlp_apply_opt in between)
   float* lo = loss_out ? loss_out : h->d_loss;
   if (!h->graphs_on || h->prof_on) return train_step_body(h, x, y, B, grad_scale, flags, lo, st);
 
@@ -988,6 +1046,10 @@ int csb_mlp_train_step(csb_mlp* h, const float* x, const float* y, int64_t B, fl
       CSB_CUDA_CHECK(cudaGraphLaunch(g.exec, st));
       h->launches += g.n_launches;
       h->acts_B = -1;
+      if ((flags & CSB_TRAIN_FUSED_OPT) != 0 && fused_opt_supported(h)) {      // what run_backward_chain records when it runs eagerly
+        h->pending = true; h->pending_B = B; h->pending_n_loss = (int)(ceil_div(B, 128) * ceil_div(h->out_p, tn_block_n(h->out_p))) * tc::TN_EPI_WARPS;
+        h->pending_loss_out = lo;
+      }
       return CSB_OK;
     }
   }
@@ -1006,6 +1068,7 @@ int csb_mlp_backward(csb_mlp* h, const float* dy, float* dx, int64_t B, void* st
   CSB_REQUIRE(h && dy, CSB_EINVAL, "null argument");
   CSB_REQUIRE(h->acts_B == B && B > 0, CSB_ESTATE, "csb_mlp_backward needs a preceding forward with CSB_FWD_KEEP_ACTIVATIONS on the same batch");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  { int rc0 = flush_pending(h, st); if (rc0) return rc0; }
   const int l = h->L - 1;
   const int grid = grid_for(B * h->out_p, 256, h->sm_count);
   prof_mark(h, K_BEGIN, st);
@@ -1048,6 +1111,26 @@ int csb_mlp_apply_opt(csb_mlp* h, int rule, float lr, float beta1, float beta2, 
     const double sma_inf = 2.0 / (1.0 - (double)beta2) - 1.0;
     const double sma_t = sma_inf - 2.0 * t * b2t / (1.0 - b2t);
     if (sma_t >= 5.0) o.radam_r = (float)sqrt((sma_t - 4.0) / (sma_inf - 4.0) * (sma_t - 2.0) / (sma_inf - 2.0) * sma_inf / sma_t);
+  }
+  if (h->pending) {
+    // split partials -> gradient -> update -> bf16 copies in one launch (bit-identical to the three-launch path)
+    simt::FusedOptTable tab;
+    tab.n = h->L;
+    tab.params = h->params; tab.grads = h->grads; tab.m = h->m; tab.v = h->v;
+    tab.loss_partials = h->loss_partials; tab.n_loss = h->pending_n_loss; tab.loss_out = h->pending_loss_out;
+    int max_items = 1;
+    for (int l = 0; l < h->L; ++l) {
+      const LayerInfo& li = h->layer[l];
+      const int splits = wgrad_splits(h, l, h->pending_B, nullptr);
+      tab.l[l] = {li.Kp, li.Np, li.w_off, li.b_off, h->w16[l], h->wt16[l], h->ws + li.ws_w_off, splits,
+                  h->ws + li.ws_b_off, splits * (int)ceil_div(li.Kp, 128)};
+      max_items = std::max(max_items, (li.Kp / 32) * (li.Np / 64) + (int)ceil_div(li.Np / 4, 256));
+    }
+    dim3 grid((unsigned)max_items, (unsigned)(h->L + 1));
+    CSB_CUDA_CHECK(launch_pdl(simt::opt_fused_kernel, grid, dim3(256), 0, st, tab, o));
+    prof_mark(h, K_OPT, st);
+    h->pending = false;
+    return CSB_OK;
   }
   const int grid = grid_for((int64_t)h->P_pad / 4, 256, h->sm_count);
   CSB_CUDA_CHECK(launch_pdl(simt::opt_kernel, dim3(grid), dim3(256), 0, st, h->params, h->grads, h->m, h->v, (int64_t)h->P_pad, o));
@@ -1121,7 +1204,7 @@ int csb_mlp_train_step_host_async(csb_mlp* h, const float* x_host, const float* 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float *xd = nullptr, *yd = nullptr;
   if ((rc = csb_mlp_stage_host_batch(h, x_host, y_host, B, stream, &xd, &yd))) return rc;
-  if ((rc = csb_mlp_train_step(h, xd, yd, B, grad_scale, flags, nullptr, stream))) return rc;
+  if ((rc = csb_mlp_train_step(h, xd, yd, B, grad_scale, flags | CSB_TRAIN_FUSED_OPT, nullptr, stream))) return rc;
   if ((rc = csb_mlp_release_staged(h, stream))) return rc;
   if ((rc = csb_mlp_apply_opt(h, rule, lr, beta1, beta2, eps, wd, stream))) return rc;
   if (loss_host) CSB_CUDA_CHECK(cudaMemcpyAsync(loss_host, h->d_loss, 4, cudaMemcpyDeviceToHost, st));

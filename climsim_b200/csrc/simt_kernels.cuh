@@ -378,6 +378,25 @@ ln_param_grad_kernel(const T* __restrict__ du, const T* __restrict__ z, int ld, 
 // reduce split partials in a fixed order: grad[i] = sum_s ws[s*stride + i]
 // ---------------------------------------------------------------------------------------------------------------
 struct Segment { const float* ws; size_t stride; float* grad; int64_t len; int splits; };
+
+// sum_s p[s * stride] over four consecutive floats, splits taken in order 0, 1, 2, ... (the fixed order every gradient in the
+// engine is reduced in); loads are issued four splits at a time so that several are in flight per thread
+__device__ __forceinline__ float4 sum_partials4(const float* __restrict__ p, size_t stride, int splits) {
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  int s = 0;
+  for (; s + 4 <= splits; s += 4) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldcs(reinterpret_cast<const float4*>(p + (size_t)(s + u) * stride));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
+  }
+  for (; s < splits; ++s) {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(p + (size_t)s * stride));
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  return a;
+}
 struct SegmentTable {
   int n; Segment seg[4 * CSB_MAX_LAYERS];
   // optional: the scalar loss rides in the same launch (row blockIdx.y == n, one block), off the backward pass's critical path
@@ -412,12 +431,7 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const SegmentTable
   }
   const Segment sg = tab.seg[blockIdx.y];
   for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4; i < sg.len; i += (int64_t)gridDim.x * blockDim.x * 4) {
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s = 0; s < sg.splits; ++s) {
-      const float4 v = *reinterpret_cast<const float4*>(sg.ws + (size_t)s * sg.stride + i);
-      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-    }
-    *reinterpret_cast<float4*>(sg.grad + i) = a;
+    *reinterpret_cast<float4*>(sg.grad + i) = sum_partials4(sg.ws + i, sg.stride, sg.splits);
   }
 }
 
@@ -431,53 +445,141 @@ struct OptParams {
   float radam_r;           // RADAM: rectification factor r_t, or < 0 while sma_t < 5 (un-rectified momentum step)
 };
 
+// one parameter element; the arithmetic of each rule is written exactly once and shared by the flat and the fused kernels.
+// Every operation is an explicit round-to-nearest intrinsic so that the compiler cannot contract multiply-adds differently in
+// the two kernels (their results are compared bit for bit).
+__device__ __forceinline__ void opt_update(const OptParams& o, float& w, const float g, float& m, float& v) {
+  const float one_m_b1 = __fsub_rn(1.f, o.beta1), one_m_b2 = __fsub_rn(1.f, o.beta2);
+  if (o.rule == CSB_OPT_SGD) {
+    w = __fsub_rn(w, __fmul_rn(o.lr, __fmaf_rn(o.wd, w, g)));
+  } else if (o.rule == CSB_OPT_ADAM_KERAS) {
+    // keras Adam.update_step: alpha = lr*sqrt(1-b2^t)/(1-b1^t); m += (g-m)(1-b1); v += (g^2-v)(1-b2); w -= alpha*m/(sqrt(v)+eps)
+    const float alpha = __fdiv_rn(__fmul_rn(o.lr, __fsqrt_rn(o.bc2)), o.bc1);
+    m = __fmaf_rn(__fsub_rn(g, m), one_m_b1, m);
+    v = __fmaf_rn(__fmaf_rn(g, g, -v), one_m_b2, v);
+    w = __fsub_rn(w, __fdiv_rn(__fmul_rn(alpha, m), __fadd_rn(__fsqrt_rn(v), o.eps)));
+  } else if (o.rule == CSB_OPT_RADAM) {
+    // tfa RectifiedAdam._resource_apply_dense (no warm-up, no amsgrad)
+    m = __fmaf_rn(o.beta1, m, __fmul_rn(one_m_b1, g));
+    v = __fmaf_rn(o.beta2, v, __fmul_rn(__fmul_rn(one_m_b2, g), g));
+    const float mhat = __fdiv_rn(m, o.bc1);
+    const float step = (o.radam_r >= 0.f) ? __fdiv_rn(__fmul_rn(o.radam_r, mhat), __fadd_rn(__fsqrt_rn(__fdiv_rn(v, o.bc2)), o.eps)) : mhat;
+    w = __fsub_rn(w, __fmul_rn(o.lr, __fmaf_rn(o.wd, w, step)));
+  } else if (o.rule == CSB_OPT_RMSPROP) {
+    // keras RMSprop.update_step (rho in beta2; epsilon inside the square root)
+    v = __fmaf_rn(o.beta2, v, __fmul_rn(__fmul_rn(one_m_b2, g), g));
+    w = __fsub_rn(w, __fdiv_rn(__fmul_rn(o.lr, g), __fsqrt_rn(__fadd_rn(v, o.eps))));
+  } else {
+    // torch.optim.Adam (L2 decay folded into g)
+    const float ge = __fmaf_rn(o.wd, w, g);
+    m = __fmaf_rn(o.beta1, m, __fmul_rn(one_m_b1, ge));
+    v = __fmaf_rn(o.beta2, v, __fmul_rn(__fmul_rn(one_m_b2, ge), ge));
+    w = __fsub_rn(w, __fdiv_rn(__fmul_rn(__fdiv_rn(o.lr, o.bc1), m), __fadd_rn(__fdiv_rn(__fsqrt_rn(v), __fsqrt_rn(o.bc2)), o.eps)));
+  }
+}
+
 __global__ void __launch_bounds__(256)
 opt_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
            const OptParams o) {
   pdl_launch_dependents();
   pdl_wait();
   for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4; i < n; i += (int64_t)gridDim.x * blockDim.x * 4) {
-    float4 w4 = *reinterpret_cast<float4*>(w + i);
-    const float4 g4 = *reinterpret_cast<const float4*>(g + i);
-    float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+    const float4 w4 = *reinterpret_cast<float4*>(w + i), g4 = *reinterpret_cast<const float4*>(g + i);
+    const float4 m4 = *reinterpret_cast<float4*>(m + i), v4 = *reinterpret_cast<float4*>(v + i);
+    float wv[4] = {w4.x, w4.y, w4.z, w4.w}, mv[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
     const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
-    if (o.rule == CSB_OPT_SGD) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) wv[j] -= o.lr * (gv[j] + o.wd * wv[j]);
-    } else {
-      float4 m4 = *reinterpret_cast<float4*>(m + i), v4 = *reinterpret_cast<float4*>(v + i);
-      float mv[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (o.rule == CSB_OPT_ADAM_KERAS) {
-          // keras Adam.update_step: alpha = lr*sqrt(1-b2^t)/(1-b1^t); m += (g-m)(1-b1); v += (g^2-v)(1-b2); w -= alpha*m/(sqrt(v)+eps)
-          const float alpha = o.lr * sqrtf(o.bc2) / o.bc1;
-          mv[j] += (gv[j] - mv[j]) * (1.f - o.beta1);
-          vv[j] += (gv[j] * gv[j] - vv[j]) * (1.f - o.beta2);
-          wv[j] -= alpha * mv[j] / (sqrtf(vv[j]) + o.eps);
-        } else if (o.rule == CSB_OPT_RADAM) {
-          // tfa RectifiedAdam._resource_apply_dense (no warm-up, no amsgrad)
-          mv[j] = o.beta1 * mv[j] + (1.f - o.beta1) * gv[j];
-          vv[j] = o.beta2 * vv[j] + (1.f - o.beta2) * gv[j] * gv[j];
-          const float mhat = mv[j] / o.bc1;
-          const float step = (o.radam_r >= 0.f) ? o.radam_r * mhat / (sqrtf(vv[j] / o.bc2) + o.eps) : mhat;
-          wv[j] -= o.lr * (step + o.wd * wv[j]);
-        } else if (o.rule == CSB_OPT_RMSPROP) {
-          // keras RMSprop.update_step (rho in beta2; epsilon inside the square root)
-          vv[j] = o.beta2 * vv[j] + (1.f - o.beta2) * gv[j] * gv[j];
-          wv[j] -= o.lr * gv[j] * rsqrtf(vv[j] + o.eps);
-        } else {
-          // torch.optim.Adam (L2 decay folded into g)
-          const float ge = gv[j] + o.wd * wv[j];
-          mv[j] = o.beta1 * mv[j] + (1.f - o.beta1) * ge;
-          vv[j] = o.beta2 * vv[j] + (1.f - o.beta2) * ge * ge;
-          wv[j] -= (o.lr / o.bc1) * mv[j] / (sqrtf(vv[j]) / sqrtf(o.bc2) + o.eps);
-        }
-      }
+    for (int j = 0; j < 4; ++j) opt_update(o, wv[j], gv[j], mv[j], vv[j]);
+    if (o.rule != CSB_OPT_SGD) {
       *reinterpret_cast<float4*>(m + i) = make_float4(mv[0], mv[1], mv[2], mv[3]);
       *reinterpret_cast<float4*>(v + i) = make_float4(vv[0], vv[1], vv[2], vv[3]);
     }
     *reinterpret_cast<float4*>(w + i) = make_float4(wv[0], wv[1], wv[2], wv[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fused "reduce split partials -> optimizer rule -> bf16 weight copies" (CSB_TRAIN_FUSED_OPT): one launch replaces
+// reduce_partials_kernel + opt_kernel + repack_kernel.  blockIdx.y = layer (row n: the scalar loss), blockIdx.x walks the
+// 32 x 32 tiles of W_l [Kp, Np] and then 256-wide pieces of b_l.  The partials are summed in the same fixed order as
+// reduce_partials_kernel does, so gradients (also written to the gradient buffer) and weights are bit-identical.
+// ---------------------------------------------------------------------------------------------------------------
+struct FusedOptLayer {
+  int Kp, Np;
+  size_t w_off, b_off;                  // offsets into params / grads / m / v
+  __nv_bfloat16 *w16, *wt16;
+  const float* ws_w; int w_splits;      // partials of dW: ws_w + s * Kp * Np
+  const float* ws_b; int b_splits;      // partials of db: ws_b + s * Np
+};
+struct FusedOptTable {
+  int n; FusedOptLayer l[CSB_MAX_LAYERS];
+  float *params, *grads, *m, *v;
+  const float* loss_partials; int n_loss; float* loss_out;
+};
+
+__global__ void __launch_bounds__(256) opt_fused_kernel(const FusedOptTable tab, const OptParams o) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if ((int)blockIdx.y == tab.n) {
+    if (blockIdx.x == 0 && tab.loss_out != nullptr) block_sum_loss(tab.loss_partials, tab.n_loss, tab.loss_out);
+    return;
+  }
+  const FusedOptLayer L = tab.l[blockIdx.y];
+  // W_l in tiles of 32 (k) x 64 (n): thread -> 4 consecutive n (one float4) of rows ty and ty + 16
+  const int tiles_n = L.Np / 64, tiles = (L.Kp / 32) * tiles_n, vec_items = (L.Np / 4 + 255) / 256;
+  const size_t wsz = (size_t)L.Kp * L.Np;
+  __shared__ float t[32][65];
+  for (int item = blockIdx.x; item < tiles + vec_items; item += gridDim.x) {
+    if (item < tiles) {
+      const int k0 = (item / tiles_n) * 32, n0 = (item % tiles_n) * 64;
+      const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int k = ty + 16 * i;
+        const size_t idx = (size_t)(k0 + k) * L.Np + n0 + 4 * tx, e = L.w_off + idx;
+        const float4 g4 = sum_partials4(L.ws_w + idx, wsz, L.w_splits);
+        const float4 w4 = *reinterpret_cast<const float4*>(tab.params + e), m4 = *reinterpret_cast<const float4*>(tab.m + e),
+                     v4 = *reinterpret_cast<const float4*>(tab.v + e);
+        float w[4] = {w4.x, w4.y, w4.z, w4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
+        const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { opt_update(o, w[j], g[j], m[j], v[j]); t[k][4 * tx + j] = w[j]; }
+        *reinterpret_cast<float4*>(tab.grads + e) = g4;
+        *reinterpret_cast<float4*>(tab.params + e) = make_float4(w[0], w[1], w[2], w[3]);
+        if (o.rule != CSB_OPT_SGD) {
+          *reinterpret_cast<float4*>(tab.m + e) = make_float4(m[0], m[1], m[2], m[3]);
+          *reinterpret_cast<float4*>(tab.v + e) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+        *reinterpret_cast<uint2*>(L.w16 + idx) = make_uint2(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]));
+      }
+      __syncthreads();
+      {  // transposed copy: 64 n-rows x 32 k; thread -> 8 consecutive k of one n (one 16-byte store)
+        const int n = threadIdx.x >> 2, kq = (threadIdx.x & 3) * 8;
+        uint4 u;
+        u.x = pack_bf16x2(t[kq + 0][n], t[kq + 1][n]); u.y = pack_bf16x2(t[kq + 2][n], t[kq + 3][n]);
+        u.z = pack_bf16x2(t[kq + 4][n], t[kq + 5][n]); u.w = pack_bf16x2(t[kq + 6][n], t[kq + 7][n]);
+        *reinterpret_cast<uint4*>(L.wt16 + (size_t)(n0 + n) * L.Kp + k0 + kq) = u;
+      }
+      __syncthreads();
+    } else {
+      const int c = ((item - tiles) * 256 + threadIdx.x) * 4;
+      if (c < L.Np) {
+        const size_t e = L.b_off + c;
+        const float4 g4 = sum_partials4(L.ws_b + c, (size_t)L.Np, L.b_splits);
+        const float4 w4 = *reinterpret_cast<const float4*>(tab.params + e), m4 = *reinterpret_cast<const float4*>(tab.m + e),
+                     v4 = *reinterpret_cast<const float4*>(tab.v + e);
+        float w[4] = {w4.x, w4.y, w4.z, w4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
+        const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) opt_update(o, w[j], g[j], m[j], v[j]);
+        *reinterpret_cast<float4*>(tab.grads + e) = g4;
+        *reinterpret_cast<float4*>(tab.params + e) = make_float4(w[0], w[1], w[2], w[3]);
+        if (o.rule != CSB_OPT_SGD) {
+          *reinterpret_cast<float4*>(tab.m + e) = make_float4(m[0], m[1], m[2], m[3]);
+          *reinterpret_cast<float4*>(tab.v + e) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
+    }
   }
 }
 

@@ -69,7 +69,7 @@ struct GemmParams {
   const float* loss_w;         // [N] (zero in padding)
   float grad_scale;            // multiplies loss and dL/dp
   int loss_kind;               // CSB_LOSS_*
-  float* pred;                 // optional fp32 predictions [M, ld_pred]
+  float* pred;                 // EPI_HEAD_OUT: fp32 predictions [M, ld_pred]
   int ld_pred;
   const float* inv_out_scale;  // optional [N]: pred *= inv_out_scale
   const float* out_mask;       // optional [N] of 0/1: predictions (and their gradients) of masked columns are zero
@@ -271,6 +271,15 @@ __device__ __forceinline__ void load_bf16x32_global_raw(const __nv_bfloat16* src
                    "=r"(w[8 * h + 6]), "=r"(w[8 * h + 7])
                  : "l"(src + 16 * h));
 }
+// 32 consecutive fp32 (128 B, 32 B aligned) of one row: four 256-bit loads (full sectors, no reliance on L1)
+__device__ __forceinline__ void load_f32x32_global_v8(const float* src, float (&v)[32]) {
+#pragma unroll
+  for (int h = 0; h < 4; ++h)
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[8 * h + 0]), "=f"(v[8 * h + 1]), "=f"(v[8 * h + 2]), "=f"(v[8 * h + 3]), "=f"(v[8 * h + 4]), "=f"(v[8 * h + 5]),
+                   "=f"(v[8 * h + 6]), "=f"(v[8 * h + 7])
+                 : "l"(src + 8 * h));
+}
 __device__ __forceinline__ void unpack_bf16x32(const uint32_t (&w)[16], float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) { v[2 * i] = bf16_lo(w[i]); v[2 * i + 1] = bf16_hi(w[i]); }
@@ -344,9 +353,10 @@ __device__ __forceinline__ RowInfo make_row_info(const GemmParams& p, int grow) 
 
 // One 32-column step of the epilogue.  gcol = global column; sbias = the layer's bias vector in shared memory;
 // `sv` holds the 32 saved bf16 values of EPI_DGRAD / EPI_BIAS_ADD.
-template <int EPI, bool ELU>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float* sbias, const RowInfo& ri, int gcol, const uint32_t (&raw)[32],
-                                               const uint32_t (&sv)[16], float& loss_acc, uint32_t mask_word) {
+template <int EPI, bool ELU, bool GENERAL_LOSS>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float* sbias, const float* sloss_w, const RowInfo& ri, int gcol,
+                                               const uint32_t (&raw)[32], const uint32_t (&sv)[16], const float (&yv)[32], float& loss_acc,
+                                               uint32_t mask_word) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
@@ -386,7 +396,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
     // act'(a) through the sign bit: relu -> {1, 0}, leaky relu -> {1, alpha}
     const float neg = p.act == CSB_ACT_LEAKYRELU ? p.alpha : 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = ((mask_word >> j) & 1u) ? v[j] : neg * v[j];
+    for (int j = 0; j < 32; ++j)
+      if (!(mask_word & (1u << j))) v[j] *= neg;               // one predicate-setting LOP3 + one predicated FMUL per element
     if (ri.zero_row) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = 0.f;
@@ -408,32 +419,38 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
     for (int j = 0; j < 32; ++j) v[j] = ri.zero_row ? 0.f : v[j] + a[j];
     if (st_ok) store_bf16x32_global(out16, v);
   } else {
-    // head: p = (col >= head_relu_from) ? relu(z) : act(z)
-    float z[32], dact[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) { z[j] = v[j]; dact[j] = 1.f; }
-    act_fwd32<ELU>(p.act, p.alpha, v);                                                // v = act(z)
-    act_bwd32<ELU>(p.act, p.alpha, dact, v);                                          // dact = act'(z) through act(z)
-    if (p.head_relu_from >= 0 && gcol + 32 > p.head_relu_from) {                      // warp-uniform
+    // head: p = (col >= head_relu_from) ? relu(z) : act(z); everything is computed element by element in place (v: z -> p -> dL/dz)
+    // so that the live set stays at the accumulator chunk + the prefetched targets (a spill here exposes the target loads' latency)
+    const float slope = p.act == CSB_ACT_RELU ? 0.f : (p.act == CSB_ACT_LEAKYRELU ? p.alpha : 1.f);   // relu / leaky / identity as one formula
+    const bool relu_cols = p.head_relu_from >= 0 && gcol + 32 > p.head_relu_from;                      // warp-uniform
+    auto head_elem = [&](int j, float z, float& pj, float& da) {
+      if constexpr (ELU) {
+        pj = z > 0.f ? z : expm1f(z);
+        da = z > 0.f ? 1.f : pj + 1.f;
+      } else {
+        pj = z > 0.f ? z : slope * z;
+        da = z > 0.f ? 1.f : slope;
+      }
+      if (relu_cols && gcol + j >= p.head_relu_from) { pj = fmaxf(z, 0.f); da = z > 0.f ? 1.f : 0.f; }
+    };
+    if constexpr (EPI == EPI_HEAD_OUT) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        if (gcol + j >= p.head_relu_from) {
-          v[j] = fmaxf(z[j], 0.f);
-          dact[j] = z[j] > 0.f ? 1.f : 0.f;
-        }
+        float pj, da;
+        head_elem(j, v[j], pj, da);
+        v[j] = pj;
       }
-    }
-    if (p.out_mask != nullptr) {
-      float mk[32];
-      load_f32x32(p.out_mask + gcol, mk);
+      if (p.out_mask != nullptr) {
+        float mk[32];
+        load_f32x32(p.out_mask + gcol, mk);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) { v[j] *= mk[j]; dact[j] *= mk[j]; }
-    }
-    if constexpr (EPI == EPI_HEAD_OUT) {
+        for (int j = 0; j < 32; ++j) v[j] *= mk[j];
+      }
       if (p.inv_out_scale != nullptr) {
-        load_f32x32(p.inv_out_scale + gcol, z);
+        float sc[32];
+        load_f32x32(p.inv_out_scale + gcol, sc);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] *= z[j];
+        for (int j = 0; j < 32; ++j) v[j] *= sc[j];
       }
       if (ri.row_ok) {
         if (gcol + 32 <= p.out_dim) {
@@ -443,49 +460,65 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
             if (gcol + j < p.out_dim) p.pred[(size_t)ri.yrow * p.ld_pred + gcol + j] = v[j];
         }
       }
-    } else {  // EPI_HEAD_LOSS: finish 8 columns at a time to keep the live register set small
-      if (ri.row_ok && p.pred != nullptr && gcol + 32 <= p.out_dim) store_f32x32(p.pred + (size_t)ri.yrow * p.ld_pred + gcol, v);
-      const float* yptr = p.y + (size_t)ri.yrow * p.ld_y + gcol;
+    } else {  // EPI_HEAD_LOSS: targets were requested before the accumulator wait (yv), loss weights sit in shared memory
+      // the common configuration -- identity (or ReLU / LeakyReLU) head, MSE, no output mask -- gets a loop of ~6 instructions
+      // per element; the general loop below costs ~30 and made this kernel ALU-bound (128 x 128 outputs per 2 k-blocks of MMA)
+      if constexpr (!ELU && !GENERAL_LOSS) {      // host guarantees: MSE, no output mask
+        const float two_gs = 2.f * p.grad_scale;
+        if (!ri.row_ok) {
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        float yv[8], w[8];
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.loss_w + gcol + 8 * g));
-        const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.loss_w + gcol + 8 * g + 4));
-        w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w; w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) yv[j] = 0.f;
-        if (ri.row_ok) {
-          if (gcol + 8 * g + 8 <= p.out_dim && (p.ld_y & 3) == 0) {
-            const float4 y0 = __ldg(reinterpret_cast<const float4*>(yptr + 8 * g));
-            const float4 y1 = __ldg(reinterpret_cast<const float4*>(yptr + 8 * g + 4));
-            yv[0] = y0.x; yv[1] = y0.y; yv[2] = y0.z; yv[3] = y0.w; yv[4] = y1.x; yv[5] = y1.y; yv[6] = y1.z; yv[7] = y1.w;
-          } else {
-            for (int j = 0; j < 8; ++j)
-              if (gcol + 8 * g + j < p.out_dim) yv[j] = __ldg(yptr + 8 * g + j);
+          for (int g = 0; g < 8; ++g) {
+            const float4 w4 = *reinterpret_cast<const float4*>(sloss_w + gcol + 4 * g);
+            const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int c = 4 * g + j;
+              const float z = v[c];
+              const float sc = (relu_cols && gcol + c >= p.head_relu_from) ? 0.f : slope;      // warp-uniform per column
+              const float sl = z > 0.f ? 1.f : sc;
+              const float wd = w[j] * (sl * z - yv[c]);        // w (p - y)
+              loss_acc = fmaf(wd, sl * z - yv[c], loss_acc);
+              v[c] = sl * (two_gs * wd);
+            }
           }
         }
+      } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int c = 8 * g + j;
-          const float d = ri.row_ok ? v[c] - yv[j] : 0.f;
+      for (int g = 0; g < 8; ++g) {
+        const float4 w4 = *reinterpret_cast<const float4*>(sloss_w + gcol + 4 * g);      // broadcast; zero in padding columns (general path)
+        const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+        float mk[4] = {1.f, 1.f, 1.f, 1.f};
+        if (p.out_mask != nullptr) {
+          const float4 m4 = __ldg(reinterpret_cast<const float4*>(p.out_mask + gcol + 4 * g));
+          mk[0] = m4.x; mk[1] = m4.y; mk[2] = m4.z; mk[3] = m4.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = 4 * g + j;
+          float pj, da;
+          head_elem(c, v[c], pj, da);
+          pj *= mk[j]; da *= mk[j];
+          const float d = ri.row_ok ? pj - yv[c] : 0.f;
+          float dl;                                              // dL/dp
           if (p.loss_kind == CSB_LOSS_MSE) {
             loss_acc += w[j] * d * d;
-            dact[c] *= 2.f * w[j] * d * p.grad_scale;
+            dl = 2.f * w[j] * d * p.grad_scale;
           } else if (p.loss_kind == CSB_LOSS_HUBER) {
             const float ad = fabsf(d);
             loss_acc += w[j] * (ad <= 1.f ? 0.5f * d * d : ad - 0.5f);
-            dact[c] *= w[j] * p.grad_scale * (ad <= 1.f ? d : (d > 0.f ? 1.f : -1.f));
+            dl = w[j] * p.grad_scale * (ad <= 1.f ? d : (d > 0.f ? 1.f : -1.f));
           } else {
             loss_acc += w[j] * fabsf(d);
-            dact[c] *= w[j] * p.grad_scale * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+            dl = w[j] * p.grad_scale * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
           }
+          v[c] = ri.row_ok ? da * dl : 0.f;
         }
       }
-      if (!ri.row_ok) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) dact[j] = 0.f;
       }
-      if (st_ok) store_bf16x32_global(out16, dact);
+      if (st_ok) store_bf16x32_global(out16, v);
     }
   }
 }
@@ -517,10 +550,14 @@ struct TnSmem {
 // CG = 1: one CTA per 128 x BN tile.  CG = 2 (launched as clusters of two): a CTA pair owns a 256 x BN tile with
 // tcgen05 cta_group::2 -- each CTA loads its 128 rows of A and HALF of the B tile, the leader CTA issues the MMAs for
 // both, each CTA runs the epilogue of its own 128 rows.  Halves the B traffic and the B footprint per stage.
-template <int BN, int STAGES, int EPI, int CG, bool ELU>
+// VAR: bit 0 = ELU activation (expm1f in the epilogue), bit 1 = general loss path of EPI_HEAD_LOSS (MAE / Huber / output mask);
+// both keep rarely used code out of the instruction stream (and the register budget) of the common kernels
+constexpr int VAR_ELU = 1, VAR_GENERAL_LOSS = 2;
+template <int BN, int STAGES, int EPI, int CG, int VAR>
 __global__ void __launch_bounds__(TN_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
   using L = TnSmem<BN, STAGES, CG>;
+  constexpr bool ELU = (VAR & VAR_ELU) != 0, GENERAL_LOSS = (VAR & VAR_GENERAL_LOSS) != 0;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   const bool is_leader = cta_rank == 0;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
@@ -562,8 +599,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   pdl_launch_dependents();                           // the next kernel may begin its own prologue as SMs free up
   pdl_wait();                                        // everything below reads memory the previous kernel may have written
+  const float* sloss_w = sbias + num_n_blocks * BN;   // EPI_HEAD_LOSS: loss weights behind the bias vector (host checks 2 N <= TN_BIAS_SMEM)
   if constexpr (USE_BIAS) {                          // whole bias vector, zero-extended to the tile grid (host checks N <= TN_BIAS_SMEM)
-    for (int i = threadIdx.x; i < num_n_blocks * BN; i += TN_THREADS) sbias[i] = (i < p.N) ? __ldg(p.bias + i) : 0.f;
+    for (int i = threadIdx.x; i < num_n_blocks * BN; i += TN_THREADS) {
+      sbias[i] = (i < p.N) ? __ldg(p.bias + i) : 0.f;
+      if constexpr (EPI == EPI_HEAD_LOSS) sbias[num_n_blocks * BN + i] = (i < p.N) ? __ldg(p.loss_w + i) : 0.f;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -672,6 +713,25 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (c0 + 32 * i < n_valid) load_bf16x32_global_raw(p.saved + (size_t)ri.grow * p.ld_saved + n0 + c0 + 32 * i, sv[i]);
         }
       }
+      // EPI_HEAD_LOSS: the 32 targets of the first step, requested before the accumulator wait (later steps: before their tcgen05.ld)
+      float yv[32];
+      auto load_targets = [&](int c) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) yv[j] = 0.f;
+        if constexpr (EPI == EPI_HEAD_LOSS) {
+          if (ri.row_ok && c < n_valid) {
+            const int gc = n0 + c;
+            const float* yptr = p.y + (size_t)ri.yrow * p.ld_y + gc;
+            if (gc + 32 <= p.out_dim && (p.ld_y & 7) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 31) == 0) {
+              load_f32x32_global_v8(yptr, yv);
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (gc + j < p.out_dim) yv[j] = __ldg(yptr + j);
+            }
+          }
+        }
+      };
+      load_targets(c0);
       mbar_wait(tfull_bar(acc), (uint32_t)(t >> 1) & 1u);
       tc_fence_after();
       float loss_acc = 0.f;
@@ -680,6 +740,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int i = 0; i < NCH; ++i) {
         const int c = c0 + 32 * i;                            // tile-relative column of this step (warp-uniform)
         if (c < n_valid) {
+          if (i > 0) load_targets(c);
           uint32_t raw[32];
           if (!(p.dbg & 8)) {
             tmem_ld_32x32(taddr + (uint32_t)(32 * i), raw);
@@ -688,7 +749,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; ++j) raw[j] = 0u;
           }
-          if (!(p.dbg & 2)) epilogue_chunk<EPI, ELU>(p, sbias, ri, n0 + c, raw, sv[i], loss_acc, mask_words[i]);
+          if (!(p.dbg & 2)) epilogue_chunk<EPI, ELU, GENERAL_LOSS>(p, sbias, sloss_w, ri, n0 + c, raw, sv[i], yv, loss_acc, mask_words[i]);
         }
       }
       tc_fence_before();

@@ -195,16 +195,18 @@ class MLPEngine:
         return dx
 
     def train_step(self, x: torch.Tensor, y: torch.Tensor, grad_scale: float = 0.0, normalize_in: bool = False,
-                   loss_out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """forward + loss + backward; gradients land in the engine's gradient buffer.  Returns the device scalar loss."""
+                   loss_out: Optional[torch.Tensor] = None, fused_opt: bool = False) -> torch.Tensor:
+        """forward + loss + backward; gradients land in the engine's gradient buffer.  Returns the device scalar loss.
+        ``fused_opt``: ``apply_opt`` follows directly (no all-reduce in between), so the split-partial reduction and the loss
+        sum ride in the optimizer launch (CSB_TRAIN_FUSED_OPT); the loss scalar is then valid after ``apply_opt``."""
         x, y = _f32_cuda(x, "x"), _f32_cuda(y, "y")
         if loss_out is None:
             if self._loss_buf is None:
                 self._loss_buf = torch.zeros(1, dtype=torch.float32, device=x.device)
             loss_out = self._loss_buf
         _lib.check(self.lib.csb_mlp_train_step(self._h, x.data_ptr(), y.data_ptr(), x.shape[0], grad_scale,
-                                               self._flags(normalize_in, False, False), loss_out.data_ptr(),
-                                               _lib.current_stream_ptr()), "csb_mlp_train_step")
+                                               self._flags(normalize_in, False, False) | (_lib.TRAIN_FUSED_OPT if fused_opt else 0),
+                                               loss_out.data_ptr(), _lib.current_stream_ptr()), "csb_mlp_train_step")
         return loss_out
 
     def apply_opt(self, rule: str = "adam_keras", lr: float = 1e-3, beta1: float = 0.9, beta2: float = 0.999,

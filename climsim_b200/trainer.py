@@ -95,7 +95,7 @@ class Trainer:
                 return float(slot.item())
             x, y = eng.stage_host_batch(x, y)
         scale = 1.0 / (B * self.world * eng.out_dim)            # global-mean MSE, as Keras computes on the global batch
-        eng.train_step(x, y, grad_scale=scale, normalize_in=normalize_in, loss_out=self._loss)
+        eng.train_step(x, y, grad_scale=scale, normalize_in=normalize_in, loss_out=self._loss, fused_opt=self.world == 1)
         if slot is not None:
             eng.release_staged()
         if self.world > 1:

@@ -70,7 +70,13 @@ enum { CSB_OPT_ADAM_KERAS = 0, CSB_OPT_ADAM_TORCH = 1, CSB_OPT_SGD = 2, CSB_OPT_
 enum {
   CSB_FWD_NORMALIZE_IN = 1,   /* x is raw: apply (x - inp_sub)/inp_div with inf/nan -> 0 (data_utils.py:806-809,894-897) */
   CSB_FWD_DENORM_OUT = 2,     /* divide predictions by out_scale (data_utils.py:1187-1197, step [0] of output_weighting) */
-  CSB_FWD_KEEP_ACTIVATIONS = 4 /* keep per-layer activations so that csb_mlp_backward may follow */
+  CSB_FWD_KEEP_ACTIVATIONS = 4, /* keep per-layer activations so that csb_mlp_backward may follow */
+  /* csb_mlp_train_step only: the caller will call csb_mlp_apply_opt next and does not need the gradient buffer before that.
+   * The reduction of the split-K gradient partials (and the loss sum) is then fused into the optimizer launch, which also
+   * refreshes the bf16 weight copies and still fills the gradient buffer.  Results are bit-identical to the unfused path.
+   * Not for data-parallel callers (they all-reduce the gradient buffer between the two calls).  If something else reads the
+   * gradients first (csb_mlp_get_grads*, another train step) the engine reduces them on demand. */
+  CSB_TRAIN_FUSED_OPT = 8
 };
 
 /* ---- MLP family ----------------------------------------------------------------------------------------- */

@@ -35,7 +35,8 @@ class OracleEngine:
     def grad_buffer(self):
         return self._grad
 
-    def train_step(self, x, y, grad_scale=0.0, normalize_in=False, loss_out=None):
+    def train_step(self, x, y, grad_scale=0.0, normalize_in=False, loss_out=None, fused_opt=False):
+        assert not (fused_opt and dist.is_initialized() and dist.get_world_size() > 1)   # DP callers need the gradient buffer
         for p in self.ref.params:
             p.grad = None
         scale = grad_scale if grad_scale > 0 else 1.0 / (x.shape[0] * 128)

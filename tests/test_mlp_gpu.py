@@ -383,3 +383,34 @@ def test_pipelined_host_feed_matches_synchronous_steps():
     assert out["sync"][0] == out["async"][0]
     np.testing.assert_array_equal(out["sync"][1], out["async"][1])
     assert len(set(out["sync"][0])) == steps            # distinct batches gave distinct losses
+
+
+@pytest.mark.parametrize("rule", ["adam_keras", "radam", "sgd"])
+def test_fused_optimizer_launch_is_bitwise_equal_to_the_three_launch_path(rule):
+    """CSB_TRAIN_FUSED_OPT: partial reduction + update + bf16 repack in one launch.  Same gradients, loss, weights and
+    optimizer state as reduce_partials -> opt -> repack, bit for bit, over several steps (the bf16 copies feed the next step);
+    reading the gradients while the reduction is still pending reduces them on demand."""
+    units, B = (256, 192, 64), 1000
+    ref = M.MLPRef(units=units, seed=21)
+    ref.randomize_biases(22)
+    x, y = _batch(B, 23)
+    xs, ys = x.cuda(), y.cuda()
+    out = {}
+    for fused in (False, True):
+        from climsim_b200 import MLPEngine
+        eng = MLPEngine.mlp_v1(units=units, dtype="bf16", max_batch=1024)
+        _load(eng, ref)
+        losses = []
+        for it in range(5):
+            loss = eng.train_step(xs, ys, fused_opt=fused)
+            if it == 3:
+                g_mid = eng.get_grads_flat()              # fused: forces the on-demand reduction; apply_opt then takes the plain path
+            eng.apply_opt(rule, lr=1e-3)
+            losses.append(float(loss.item()))
+        m, v, step = eng.get_opt_state()
+        out[fused] = (losses, g_mid, eng.get_grads_flat(), eng.get_params_flat(), m, v, step)
+        eng.close()
+    assert out[False][0] == out[True][0]
+    for a, b in zip(out[False][1:6], out[True][1:6]):
+        np.testing.assert_array_equal(a, b)
+    assert out[False][6] == out[True][6] == 5
