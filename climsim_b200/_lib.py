@@ -100,6 +100,7 @@ SIGNATURES = {
     "csb_test_set_debug": (None, [C.c_int]),
     "csb_test_set_stats": (None, [_VP]),
     "csb_test_gemm_nt": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP]),
+    "csb_test_gemm_nt_cg": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), _VP]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -97,7 +97,8 @@ static int launch_tn(const CUtensorMap& ta, const CUtensorMap& tb, const tc::Gem
   }
   const int tiles = (int)(ceil_div(ceil_div(p.M, tc::BM), CG) * ceil_div(p.N, BN));   // CG m-blocks per tile
   if (tiles == 0) return CSB_OK;
-  const int grid = std::min(tiles, sm_count / CG) * CG;
+  int grid = std::min(tiles, sm_count / CG) * CG;
+  if (p.dbg >> 16) grid = std::min(grid, (p.dbg >> 16) * CG);      // micro-benchmark: run on a few SMs only (no power capping)
   tc::GemmParams q = p;
   q.b_box_rows = std::min(p.N, BN) / CG;     // must equal the box the B tensor map was encoded with
   cudaLaunchConfig_t cfg = {};
@@ -152,22 +153,52 @@ static int launch_tn_auto(const CUtensorMap& ta, const CUtensorMap& tb, const tc
 }
 static inline int tn_block_n(int N) { return N > 128 ? 256 : 128; }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CG>
 static int launch_nt(const CUtensorMap& ta, const CUtensorMap& tb, const tc::NtParams& p, int splits, cudaStream_t st) {
-  using L = tc::NtSmem<BN, STAGES>;
-  auto kern = tc::gemm_nt_kernel<BN, STAGES>;
+  using L = tc::NtSmem<BN, STAGES, CG>;
+  auto kern = tc::gemm_nt_kernel<BN, STAGES, CG>;
   static bool attr_set = false;
   if (!attr_set) {
     CSB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_set = true;
   }
-  dim3 grid((unsigned)(ceil_div(p.M, tc::BM) * ceil_div(p.N, BN)), (unsigned)splits);
-  CSB_CUDA_CHECK(launch_pdl(kern, grid, dim3(tc::NUM_THREADS), L::TOTAL, st, ta, tb, p));
+  CSB_REQUIRE(CG == 1 || p.N % 128 == 0, CSB_EUNSUPPORTED, "CTA-pair weight-gradient tiles need N %% 128 == 0 (N = %d)", p.N);
+  const unsigned tiles = (unsigned)(ceil_div(ceil_div(p.M, tc::BM), CG) * ceil_div(p.N, BN));     // CG m-blocks per tile
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(tiles * CG, (unsigned)splits);
+  cfg.blockDim = dim3(tc::NUM_THREADS);
+  cfg.dynamicSmemBytes = L::TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CG > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CG; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (g_use_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  CSB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
   return CSB_OK;
 }
-static int launch_nt_auto(const CUtensorMap& ta, const CUtensorMap& tb, const tc::NtParams& p, int splits, cudaStream_t st) {
-  if (p.N > 128) return launch_nt<256, 4>(ta, tb, p, splits, st);
-  return launch_nt<128, 6>(ta, tb, p, splits, st);
+// Weight-gradient tile policy: CTA pairs (256 x BN tiles, cg == 2) whenever the layer has at least two 128-row m-blocks and
+// its width splits into two 64-column-chunk-aligned halves; an odd m-block count leaves half of the last pair's rows empty
+// (zero-filled by TMA, never stored), which still beats single CTAs that cannot take their operands in fast enough.
+static bool g_use_nt_pairs = true;  // CSB_NO_NT_PAIRS=1: single-CTA weight-gradient tiles (debugging aid)
+static inline int nt_cta_group(int M, int N) { return (g_use_nt_pairs && N % 128 == 0 && M > 128) ? 2 : 1; }
+static inline int nt_m_tiles(int M, int cg) { return (int)ceil_div(ceil_div(M, 128), cg); }
+static int launch_nt_auto(const CUtensorMap& ta, const CUtensorMap& tb, const tc::NtParams& p, int splits, cudaStream_t st, int cg = 1) {
+  if (cg == 2) {
+    if (p.N > 128) return launch_nt<256, 6, 2>(ta, tb, p, splits, st);
+    return launch_nt<128, 8, 2>(ta, tb, p, splits, st);
+  }
+  if (p.N > 128) return launch_nt<256, 4, 1>(ta, tb, p, splits, st);
+  return launch_nt<128, 6, 1>(ta, tb, p, splits, st);
 }
 
 static int grid_for(int64_t work_items, int threads, int sm_count, int per_thread = 1) {
@@ -194,6 +225,7 @@ struct LayerInfo {
   size_t ws_w_off, ws_b_off;
   int max_w_splits, b_splits;
   int nt_block_n;
+  int nt_cg;                   // CTAs per weight-gradient tile (2: cta_group::2 pairs)
 };
 
 struct ActMaps {                 // TMA descriptors that depend on the batch size
@@ -416,6 +448,7 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
   }
 
   g_use_pairs = getenv("CSB_NO_PAIRS") == nullptr;
+  g_use_nt_pairs = getenv("CSB_NO_NT_PAIRS") == nullptr;
   g_use_pdl = getenv("CSB_NO_PDL") == nullptr;
   csb_mlp* h = new (std::nothrow) csb_mlp();
   CSB_REQUIRE(h != nullptr, CSB_ENOMEM, "host allocation failed");
@@ -441,9 +474,10 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
     li.b_off_user = off_user; off_user += (size_t)li.N;
     li.g_off_user = off_user; if (li.ln) off_user += 2 * (size_t)li.N;
     li.nt_block_n = tn_block_n(li.Np);
-    const int tiles = (int)(ceil_div(li.Kp, 128) * ceil_div(li.Np, li.nt_block_n));
-    li.max_w_splits = h->bf16 ? std::max(1, std::min(64, sm / tiles)) : 1;
-    li.b_splits = h->bf16 ? li.max_w_splits * (int)ceil_div(li.Kp, 128) : 32;
+    li.nt_cg = h->bf16 ? nt_cta_group(li.Kp, li.Np) : 1;
+    const int tiles = nt_m_tiles(li.Kp, li.nt_cg) * (int)ceil_div(li.Np, li.nt_block_n);
+    li.max_w_splits = h->bf16 ? std::max(1, std::min(64, (sm / li.nt_cg) / tiles)) : 1;
+    li.b_splits = h->bf16 ? li.max_w_splits * nt_m_tiles(li.Kp, li.nt_cg) : 32;
     li.ws_w_off = ws_off; ws_off += (size_t)li.max_w_splits * li.Kp * li.Np;
     li.ws_b_off = ws_off; ws_off += (size_t)li.b_splits * li.Np;
     li.ws_g_off = ws_off; if (li.ln) ws_off += (size_t)32 * 2 * li.Np;
@@ -841,7 +875,7 @@ static int flush_pending(csb_mlp* h, cudaStream_t st) {
     const LayerInfo& li = h->layer[l];
     const int splits = wgrad_splits(h, l, h->pending_B, nullptr);
     tab.seg[tab.n++] = {h->ws + li.ws_w_off, (size_t)li.Kp * li.Np, h->grads + li.w_off, (int64_t)li.Kp * li.Np, splits};
-    tab.seg[tab.n++] = {h->ws + li.ws_b_off, (size_t)li.Np, h->grads + li.b_off, (int64_t)li.Np, splits * (int)ceil_div(li.Kp, 128)};
+    tab.seg[tab.n++] = {h->ws + li.ws_b_off, (size_t)li.Np, h->grads + li.b_off, (int64_t)li.Np, splits * nt_m_tiles(li.Kp, li.nt_cg)};
     max_len = std::max<int64_t>(max_len, (int64_t)li.Kp * li.Np);
   }
   dim3 grid((unsigned)std::min<int64_t>(ceil_div(max_len / 4, 256), 2 * h->sm_count), (unsigned)(tab.n + (tab.loss_out ? 1 : 0)));
@@ -889,7 +923,7 @@ static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st,
       splits = wgrad_splits(h, l, B, &p.rb_per_split);
       p.out = h->ws + li.ws_w_off; p.ld_out = li.Np; p.split_stride = (size_t)li.Kp * li.Np;
       p.colsum_out = h->ws + li.ws_b_off; p.colsum_stride = (size_t)li.Np;      // bias gradient fused into this kernel
-      int rc = launch_nt_auto(h->tm_in[l].mn64, h->tm_dz[l].mn64, p, splits, st);
+      int rc = launch_nt_auto(h->tm_in[l].mn64, h->tm_dz[l].mn64, p, splits, st, li.nt_cg);
       if (rc) return rc;
     } else {
       simt::SgemmParams p = {};
@@ -906,7 +940,7 @@ static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st,
     max_len = std::max<int64_t>(max_len, (int64_t)li.Kp * li.Np);
     // ---- bias gradient db_l = column sums of dZ_l (CSB_BF16: computed inside the weight-gradient kernel above)
     if (h->bf16) {
-      tab.seg[tab.n++] = {h->ws + li.ws_b_off, (size_t)li.Np, h->grads + li.b_off, (int64_t)li.Np, splits * (int)ceil_div(li.Kp, 128)};
+      tab.seg[tab.n++] = {h->ws + li.ws_b_off, (size_t)li.Np, h->grads + li.b_off, (int64_t)li.Np, splits * nt_m_tiles(li.Kp, li.nt_cg)};
     } else {
       const int S = (int)std::max<int64_t>(1, std::min<int64_t>(li.b_splits, ceil_div(B, 256)));
       dim3 grid((unsigned)(li.Np / 64), (unsigned)S);
@@ -1123,7 +1157,7 @@ int csb_mlp_apply_opt(csb_mlp* h, int rule, float lr, float beta1, float beta2, 
       const LayerInfo& li = h->layer[l];
       const int splits = wgrad_splits(h, l, h->pending_B, nullptr);
       tab.l[l] = {li.Kp, li.Np, li.w_off, li.b_off, h->w16[l], h->wt16[l], h->ws + li.ws_w_off, splits,
-                  h->ws + li.ws_b_off, splits * (int)ceil_div(li.Kp, 128)};
+                  h->ws + li.ws_b_off, splits * nt_m_tiles(li.Kp, li.nt_cg)};
       max_items = std::max(max_items, (li.Kp / 32) * (li.Np / 64) + (int)ceil_div(li.Np / 4, 256));
     }
     dim3 grid((unsigned)max_items, (unsigned)(h->L + 1));
@@ -1345,6 +1379,28 @@ int csb_test_gemm_nt(const uint16_t* A, const uint16_t* B, float* C, float* cols
   p.out = C; p.ld_out = N; p.split_stride = (size_t)M * N;    // caller provides splits * M * N floats
   p.colsum_out = colsum; p.colsum_stride = (size_t)N;         // optional: splits * N floats
   return launch_nt_auto(ta, tb, p, splits, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// the same with an explicit tile policy: cg = 1 single CTAs, 2 CTA pairs, 0 what the engine would pick.  *m_tiles_out receives the
+// number of bias-gradient partial rows per split (colsum must hold splits * m_tiles * N floats; ceil(M / 128) rows always suffice).
+int csb_test_gemm_nt_cg(const uint16_t* A, const uint16_t* B, float* C, float* colsum, int M, int N, int Kr, int splits, int cg,
+                        int* m_tiles_out, void* stream) {
+  CSB_REQUIRE(A && B && C, CSB_EINVAL, "null argument");
+  CSB_REQUIRE(M % 64 == 0 && N % 64 == 0 && Kr > 0 && splits >= 1, CSB_EINVAL, "M and N must be multiples of 64");
+  CSB_REQUIRE(cg >= 0 && cg <= 2, CSB_EINVAL, "cg must be 0, 1 or 2");
+  if (cg == 0) cg = nt_cta_group(M, N);
+  CUtensorMap ta, tb;
+  int rc;
+  if ((rc = make_tmap_bf16(&ta, A, M, Kr, M, 64, 64))) return rc;
+  if ((rc = make_tmap_bf16(&tb, B, N, Kr, N, 64, 64))) return rc;
+  const int num_rb = (int)ceil_div(Kr, 64);
+  tc::NtParams p = {};
+  p.M = M; p.N = N; p.R = Kr;
+  p.rb_per_split = (int)ceil_div(num_rb, splits);
+  p.out = C; p.ld_out = N; p.split_stride = (size_t)M * N;
+  p.colsum_out = colsum; p.colsum_stride = (size_t)N;
+  if (m_tiles_out) *m_tiles_out = nt_m_tiles(M, cg);
+  return launch_nt_auto(ta, tb, p, splits, reinterpret_cast<cudaStream_t>(stream), cg);
 }
 
 }  // extern "C"

@@ -164,6 +164,9 @@ __device__ __forceinline__ void cluster_sync_all() {
 // shared::cluster address of the same smem offset in the pair's leader (even) CTA
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  // default semantics on purpose: `.release.cluster` makes ptxas put MEMBAR.ALL.GPU in front of every arrive (and an
+  // `.acquire.cluster` wait adds CCTL.IVALL), which halves the kernel.  What the arrive orders here is shared memory written by
+  // TMA / read by tcgen05 (async proxy, observed through the mbarrier chain) and TMEM, neither of which those fences serve.
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
 }
 // TMA load issued by either CTA of the pair; the transaction bytes are credited to the LEADER's mbarrier
@@ -391,6 +394,21 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = 0.f;
     }
+    if (p.dbg & 256) {
+      // bandwidth experiment only (results are permuted): the same bytes, but every store instruction of the warp covers 8 rows x
+      // 128 contiguous bytes instead of 32 rows x 32 bytes
+      const int lane = threadIdx.x & 31, i = (gcol >> 5) & 1;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)(ri.grow - lane + 8 * (2 * i + h) + (lane >> 2)) * p.ld_out +
+                           (gcol - 32 * i) + (lane & 3) * 16;
+        uint32_t w[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) w[k] = pack_bf16x2(v[16 * h + 2 * k], v[16 * h + 2 * k + 1]);
+        if (st_ok) asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(d), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+                                "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+      }
+    } else
     if (st_ok) store_bf16x32_global(out16, v);
   } else if constexpr (EPI == EPI_DGRAD_MASK) {
     // act'(a) through the sign bit: relu -> {1, 0}, leaky relu -> {1, alpha}
@@ -524,7 +542,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// gemm_tn_kernel: persistent, K-major x K-major.   18 warps: 0-15 epilogue (four per TMEM lane quadrant = four per SM
+// gemm_tn_kernel: persistent, K-major x K-major.   18 warps: 0 = TMEM owner + MMA issuer, 1 = TMA producer, 2-17 epilogue (four per TMEM lane quadrant = four per SM
 // sub-partition, each taking a quarter of the tile's columns), 16 = TMA producer, 17 = TMEM owner + MMA issuer.
 // The epilogue warps are independent of each other: each waits for the accumulator, walks its 32-column steps
 // (tcgen05.ld -> registers -> fused math -> 256-bit global stores) and releases the TMEM buffer; no staging tile, no
@@ -534,7 +552,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
 constexpr int TN_EPI_WARPS = 16;
 constexpr int TN_EPI_THREADS = TN_EPI_WARPS * 32;
 constexpr int TN_THREADS = TN_EPI_THREADS + 64;
-constexpr int TN_PRODUCER_WARP = TN_EPI_WARPS, TN_MMA_WARP = TN_EPI_WARPS + 1;
+// The MMA issuer and the TMA producer are the two LOWEST-numbered warps: the warp scheduler favours older (lower-numbered) warps
+// among the ready ones, and the single thread that feeds the tensor pipe must never queue behind the epilogue warps' long
+// ALU bursts (as warp 17 it did: the epilogue's issue cycles showed up one-for-one in the tile time).
+constexpr int TN_MMA_WARP = 0, TN_PRODUCER_WARP = 1, TN_FIRST_EPI_WARP = 2;
 
 template <int BN, int STAGES, int CG = 1>
 struct TnSmem {
@@ -611,9 +632,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if constexpr (CG == 2) cluster_sync_all();       // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (p.stats != nullptr && threadIdx.x == 0) {
-    p.stats[4 * blockIdx.x + 0] = (unsigned long long)clock64();
-    p.stats[4 * blockIdx.x + 2] = globaltimer_ns();
+  if (p.stats != nullptr && threadIdx.x == 32) {
+    p.stats[8 * blockIdx.x + 0] = (unsigned long long)clock64();
+    p.stats[8 * blockIdx.x + 2] = globaltimer_ns();
   }
 
   if (warp == TN_PRODUCER_WARP) {
@@ -649,16 +670,21 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ===================== MMA issuer =====================
     if (lane == 0 && is_leader) {
       int s = 0; uint32_t ph = 0; int t = 0;
+      long long st_tempty = 0, st_full = 0;          // micro-benchmark: cycles the issuer waited for a free accumulator / for operands
       for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++t) {
         const int n0 = (tile % num_n_blocks) * BN;
         const int n_valid = min(BN, p.N - n0);
         const uint32_t idesc = make_idesc_bf16(BM * CG, n_valid, 0, 0);
         const int acc = t & 1;
+        long long c0 = p.stats ? clock64() : 0;
         mbar_wait(tempty_bar(acc), ((uint32_t)(t >> 1) & 1u) ^ 1u);
+        if (p.stats) st_tempty += clock64() - c0;
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < num_kb; ++kb) {
+          c0 = p.stats ? clock64() : 0;
           mbar_wait(full_bar(s), ph);
+          if (p.stats) st_full += clock64() - c0;
           tc_fence_after();
           const uint32_t sa = smem_base + s * L::STAGE_BYTES;
           const uint64_t da = make_desc_kmajor_sw128(sa);
@@ -677,12 +703,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // accumulator complete -> epilogue (of both CTAs of a pair)
         if constexpr (CG == 2) umma_commit_2sm(tfull_bar(acc)); else umma_commit(tfull_bar(acc));
       }
+      if (p.stats) { p.stats[8 * blockIdx.x + 4] = (unsigned long long)st_tempty; p.stats[8 * blockIdx.x + 5] = (unsigned long long)st_full; }
     }
   } else {
     // ===================== epilogue: warp w -> TMEM lanes 32*(w&3).., columns [QCOLS*(w>>2), QCOLS*(w>>2)+QCOLS) ==========
-    const int q = warp & 3, cq = warp >> 2;
+    const int ew = warp - TN_FIRST_EPI_WARP;                 // 0..15
+    const int q = warp & 3, cq = ew >> 2;                    // TMEM lane quadrant = hardware warp id % 4; column quarter
     const int tile_row = q * 32 + lane;
     int t = 0;
+    long long st_epi_wait = 0, st_epi_busy = 0;      // micro-benchmark (epilogue warp 0): cycles waiting for an accumulator / working on it
     for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++t) {
       const int mb = (tile / num_n_blocks) * CG + (int)cta_rank;
       const int m0 = mb * BM, n0 = (tile % num_n_blocks) * BN;
@@ -732,7 +761,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       };
       load_targets(c0);
+      long long ck0 = p.stats ? clock64() : 0;
       mbar_wait(tfull_bar(acc), (uint32_t)(t >> 1) & 1u);
+      long long ck1 = p.stats ? clock64() : 0;
       tc_fence_after();
       float loss_acc = 0.f;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0);
@@ -757,20 +788,22 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (lane == 0) {                                        // TMEM buffer free: the MMA of tile t+2 may start
         if constexpr (CG == 2) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc));
       }
+      if (p.stats && ew == 0 && lane == 0) { st_epi_wait += ck1 - ck0; st_epi_busy += clock64() - ck1; }
       if constexpr (EPI == EPI_HEAD_LOSS) {
         // deterministic: one partial per (m-block, n-block, epilogue warp)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
-        if (lane == 0 && m0 < p.M) p.loss_partials[(mb * num_n_blocks + (tile % num_n_blocks)) * TN_EPI_WARPS + warp] = loss_acc * p.grad_scale;
+        if (lane == 0 && m0 < p.M) p.loss_partials[(mb * num_n_blocks + (tile % num_n_blocks)) * TN_EPI_WARPS + ew] = loss_acc * p.grad_scale;
       }
     }
+    if (p.stats && ew == 0 && lane == 0) { p.stats[8 * blockIdx.x + 6] = (unsigned long long)st_epi_wait; p.stats[8 * blockIdx.x + 7] = (unsigned long long)st_epi_busy; }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (p.stats != nullptr && threadIdx.x == 0) {
-    p.stats[4 * blockIdx.x + 1] = (unsigned long long)clock64();
-    p.stats[4 * blockIdx.x + 3] = globaltimer_ns();
+  if (p.stats != nullptr && threadIdx.x == 32) {
+    p.stats[8 * blockIdx.x + 1] = (unsigned long long)clock64();
+    p.stats[8 * blockIdx.x + 3] = globaltimer_ns();
   }
   if constexpr (CG == 2) cluster_sync_all();       // no CTA leaves (or frees TMEM) while its peer may still signal it
   if (warp == TN_MMA_WARP) {
@@ -795,21 +828,30 @@ struct NtParams {
   int a_row_offset;        // Conv1D weight gradient of tap t: A rows shifted by (t - center); out-of-range rows read as zero
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CG = 1>
 struct NtSmem {
-  static constexpr int A_BYTES = BK * BM * 2;   // 64 contraction rows x 128 m (2 chunks of [64 rows x 128 B])
-  static constexpr int B_BYTES = BK * BN * 2;   // BN/64 chunks
+  static constexpr int A_BYTES = BK * BM * 2;          // 64 contraction rows x 128 m (2 chunks of [64 rows x 128 B])
+  static constexpr int B_BYTES = BK * (BN / CG) * 2;   // BN/64 chunks; a CTA pair holds half of the columns each
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+  static_assert(TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
 };
 
-template <int BN, int STAGES>
+// CG = 1: one 128 x BN tile per CTA.
+// CG = 2 (clusters of two): a CTA pair owns a 256 x BN tile with tcgen05 cta_group::2 -- CTA r loads its 128 rows of the
+// m-range and HALF of the dZ columns, the leader issues the MMAs for both.  Per SM that is 32 KB of operands per 64-row block
+// and 512 MMA cycles (64 B/cycle) instead of 48 KB (96 B/cycle), which is more than an SM can take in from L2 (~69 B/cycle
+// measured, profiles/r01_probe_mainloop.txt).  Each CTA fills its own shared memory through its own `full` barrier (its
+// bias-gradient warps read the dZ chunks from there); a relay lane in the peer forwards "my stage is full" to the leader.
+template <int BN, int STAGES, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const NtParams p) {
-  using L = NtSmem<BN, STAGES>;
+  using L = NtSmem<BN, STAGES, CG>;
   constexpr uint32_t TMEM_COLS = (BN <= 32) ? 32 : (BN <= 64) ? 64 : (BN <= 128) ? 128 : (BN <= 256) ? 256 : 512;
   constexpr int CHUNK_BYTES = BK * 128;   // one [64 rows x 64 elements] box = 8 KB
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -817,39 +859,50 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t bar_base = smem_base + L::BAR_OFFSET;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  const uint32_t tfull_bar = bar_base + 8u * (2 * STAGES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + L::BAR_OFFSET + 8 * (2 * STAGES + 1));
+  auto peer_full_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };     // leader only: the peer's stage s is full
+  const uint32_t tfull_bar = bar_base + 8u * (3 * STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + L::BAR_OFFSET + 8 * (3 * STAGES + 1));
+  static_assert(8 * (3 * STAGES + 2) <= 256, "barrier area");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_n_blocks = (p.N + BN - 1) / BN;
-  const int m0 = (blockIdx.x / num_n_blocks) * BM, n0 = (blockIdx.x % num_n_blocks) * BN;
-  const int m_valid = min(BM, p.M - m0), n_valid = min(BN, p.N - n0);
-  const int a_chunks = (m_valid + 63) / 64, b_chunks = (n_valid + 63) / 64;
+  const int tile = (int)(blockIdx.x / CG);                               // both CTAs of a pair share the tile
+  const int m_tile = tile / num_n_blocks;
+  const int m0 = (m_tile * CG + (int)cta_rank) * BM, n0 = (tile % num_n_blocks) * BN;
+  const int n_valid = min(BN, p.N - n0);
+  const int nb0 = n0 + (int)cta_rank * (n_valid / CG);                   // first dZ column this CTA loads
+  // CG == 2 always loads both 64-wide m chunks (columns past M are zero-filled by TMA) so that the transaction size is uniform
+  const int a_chunks = (CG == 2) ? 2 : (min(BM, p.M - m0) + 63) / 64, b_chunks = (n_valid / CG + 63) / 64;
   const int num_rb = (p.R + BK - 1) / BK;
   const int rb_begin = blockIdx.y * p.rb_per_split;
   const int rb_end = min(num_rb, rb_begin + p.rb_per_split);
   const int nrb = max(0, rb_end - rb_begin);
-  // bias gradient: every m-block takes the row blocks i with i % num_m_blocks == its index, so no CTA is a straggler;
-  // partial index = split * num_m_blocks + m-block
-  const int num_m_blocks = (p.M + BM - 1) / BM, m_blk = (int)(blockIdx.x / num_n_blocks);
+  // bias gradient: every m-tile takes the row blocks i with i % num_m_tiles == its index, so no CTA is a straggler;
+  // partial index = split * num_m_tiles + m-tile
+  const int num_m_tiles = ((p.M + BM - 1) / BM + CG - 1) / CG;
   const bool do_colsum = p.colsum_out != nullptr;                       // kernel-uniform
-  const int colsum_warps = do_colsum ? min(4, b_chunks) : 0;            // warp w sums the columns of chunk w
+  const int colsum_warps = do_colsum ? min(4, b_chunks) : 0;            // warp w sums the columns of this CTA's chunk w
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1 + colsum_warps); }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1 + colsum_warps);
+      mbar_init(peer_full_bar(s), 1);
+    }
     mbar_init(tfull_bar, 1);
     fence_mbar_init();
   }
   if (warp == 5) {
-    tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (CG == 2) { tmem_alloc_2sm(smem_u32(tmem_slot), TMEM_COLS); tmem_relinquish_2sm(); }
+    else { tmem_alloc(smem_u32(tmem_slot), TMEM_COLS); tmem_relinquish(); }
   }
   pdl_launch_dependents();
   pdl_wait();
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -861,30 +914,41 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mbar_expect_tx(full_bar(s), (uint32_t)((a_chunks + b_chunks) * CHUNK_BYTES));
         const uint32_t sa = smem_base + s * L::STAGE_BYTES;
         for (int c = 0; c < a_chunks; ++c) tma_load_2d(sa + c * CHUNK_BYTES, &tmap_a, full_bar(s), m0 + 64 * c, rb * BK + p.a_row_offset);
-        for (int c = 0; c < b_chunks; ++c) tma_load_2d(sa + L::A_BYTES + c * CHUNK_BYTES, &tmap_b, full_bar(s), n0 + 64 * c, rb * BK);
+        for (int c = 0; c < b_chunks; ++c) tma_load_2d(sa + L::A_BYTES + c * CHUNK_BYTES, &tmap_b, full_bar(s), nb0 + 64 * c, rb * BK);
         if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 5) {
     if (lane == 0 && nrb > 0) {
       int s = 0; uint32_t ph = 0;
-      // M is always issued as 128: rows >= m_valid read stale smem (never stored by the epilogue)
-      const uint32_t idesc = make_idesc_bf16(BM, n_valid, 1, 1);
-      for (int i = 0; i < nrb; ++i) {
-        mbar_wait(full_bar(s), ph);
-        tc_fence_after();
-        const uint32_t sa = smem_base + s * L::STAGE_BYTES;
+      if (is_leader) {
+        // M is always issued in full: rows >= M read zero-filled / stale smem and are never stored by the epilogue
+        const uint32_t idesc = make_idesc_bf16(BM * CG, n_valid, 1, 1);
+        for (int i = 0; i < nrb; ++i) {
+          mbar_wait(full_bar(s), ph);
+          if constexpr (CG == 2) mbar_wait(peer_full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * L::STAGE_BYTES;
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // 16 contraction rows = 2 groups of 8 rows x 128 B = 2048 B further into every chunk
-          const uint64_t da = make_desc_mnmajor_sw128(sa + k * 2048, CHUNK_BYTES);
-          const uint64_t db = make_desc_mnmajor_sw128(sa + L::A_BYTES + k * 2048, CHUNK_BYTES);
-          umma_f16(tmem_base, da, db, idesc, (uint32_t)((i | k) != 0));
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // 16 contraction rows = 2 groups of 8 rows x 128 B = 2048 B further into every chunk
+            const uint64_t da = make_desc_mnmajor_sw128(sa + k * 2048, CHUNK_BYTES);
+            const uint64_t db = make_desc_mnmajor_sw128(sa + L::A_BYTES + k * 2048, CHUNK_BYTES);
+            if constexpr (CG == 2) umma_f16_2sm(tmem_base, da, db, idesc, (uint32_t)((i | k) != 0));
+            else umma_f16(tmem_base, da, db, idesc, (uint32_t)((i | k) != 0));
+          }
+          if constexpr (CG == 2) umma_commit_2sm(empty_bar(s)); else umma_commit(empty_bar(s));
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
-        umma_commit(empty_bar(s));
-        if (++s == STAGES) { s = 0; ph ^= 1u; }
+        if constexpr (CG == 2) umma_commit_2sm(tfull_bar); else umma_commit(tfull_bar);
+      } else {
+        // peer of a pair: relay "stage s of my shared memory is full" to the leader's MMA issuer
+        for (int i = 0; i < nrb; ++i) {
+          mbar_wait(full_bar(s), ph);
+          mbar_arrive_leader(peer_full_bar(s));
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
       }
-      umma_commit(tfull_bar);
     }
   } else {
     // ---- bias gradient: column sums of the dZ tiles streaming through the ring (warps 0..colsum_warps-1)
@@ -897,7 +961,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int i = 0; i < nrb; ++i) {
         mbar_wait(full_bar(s), ph);
         const uint8_t* chunk = smem_gen + s * L::STAGE_BYTES + L::A_BYTES + warp * CHUNK_BYTES;
-        if (i % num_m_blocks == m_blk)
+        if (i % num_m_tiles == m_tile)
 #pragma unroll
         for (int it = 0; it < BK / 4; ++it) {         // rows past R were zero-filled by TMA
           const int r = 4 * it + rs;
@@ -915,7 +979,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         acc8[j] += __shfl_xor_sync(0xffffffffu, acc8[j], 16);
       }
       if (rs == 0) {
-        float* dst = p.colsum_out + ((size_t)blockIdx.y * num_m_blocks + m_blk) * p.colsum_stride + n0 + 64 * warp + 8 * lp;
+        float* dst = p.colsum_out + ((size_t)blockIdx.y * num_m_tiles + m_tile) * p.colsum_stride + nb0 + 64 * warp + 8 * lp;
         *reinterpret_cast<float4*>(dst) = make_float4(acc8[0], acc8[1], acc8[2], acc8[3]);
         *reinterpret_cast<float4*>(dst + 4) = make_float4(acc8[4], acc8[5], acc8[6], acc8[7]);
       }
@@ -945,9 +1009,10 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();       // no CTA leaves (or frees TMEM) while its peer may still signal it
   if (warp == 5) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (CG == 2) tmem_dealloc_2sm(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 

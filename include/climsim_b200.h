@@ -251,10 +251,16 @@ int  csb_test_gemm_tn(const uint16_t* A, const uint16_t* Bt, float* C, int M, in
 int  csb_test_linear_fwd(const uint16_t* A, const uint16_t* Wt, const float* bias, uint16_t* out, int M, int N, int K, int act,
                          float alpha, int pairs, void* stream);
 void csb_test_set_debug(int flags);   /* epilogue ablation knobs for the micro-benchmark (0 = normal operation) */
-void csb_test_set_stats(void* dev_u64x4_per_cta);   /* micro-benchmark: per-CTA {clock64 start, end, globaltimer start, end} of csb_test_linear_fwd; NULL = off */
+void csb_test_set_stats(void* dev_u64x8_per_cta);   /* micro-benchmark: per-CTA {clock64 start, end, globaltimer start, end, MMA issuer cycles waiting for a
+                                                      * free accumulator, ... for operands, epilogue warp 0 cycles waiting for an accumulator, ... working} of
+                                                      * csb_test_linear_fwd; NULL = off */
 /* C[s][M,N] (fp32 partials, s < splits) = A[Kr,M]^T * B[Kr,N]  (both operands MN-major bf16): the weight-gradient
  * contraction over rows; colsum (optional, [splits * ceil(M/128)][N]) receives partial column sums of B (bias gradient). */
 int  csb_test_gemm_nt(const uint16_t* A, const uint16_t* B, float* C, float* colsum, int M, int N, int Kr, int splits, void* stream);
+/* the same with an explicit tile policy: cg = 1 single CTAs, 2 CTA pairs (cta_group::2, needs N % 128 == 0), 0 = the engine's choice;
+ * *m_tiles_out = bias-gradient partial rows written per split */
+int  csb_test_gemm_nt_cg(const uint16_t* A, const uint16_t* B, float* C, float* colsum, int M, int N, int Kr, int splits, int cg,
+                         int* m_tiles_out, void* stream);
 
 /* ---- misc ---------------------------------------------------------------------------------------------- */
 int         csb_version(void);

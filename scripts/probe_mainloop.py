@@ -8,27 +8,32 @@ from climsim_b200 import _lib
 from microbench_gemm import time_it
 lib = _lib.load()
 M = 65536
-stats = torch.zeros(148 * 4, dtype=torch.int64, device="cuda")
+stats = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
 lib.csb_test_set_stats(stats.data_ptr())
 CASES = [(0, "full"), (4, "no stores"), (2, "no math, no stores"), (1, "no bias"), (15, "epilogue off"), (15 + 16, "epi off, no loads"),
-         (15 + 32, "epi off, no MMA (ingest only)"), (16, "full epilogue, no loads"), (32, "full epilogue, no MMA"), (16 + 32, "epilogue only")]
-for (N, K) in ((768, 768), (640, 640), (768, 128), (128, 640)):
+         (15 + 32, "epi off, no MMA (ingest only)"), (16, "full epilogue, no loads"), (32, "full epilogue, no MMA"), (16 + 32, "epilogue only"),
+         (256, "full, coalesced (permuted) stores")]
+GRID = int(sys.argv[1]) if len(sys.argv) > 1 else 0      # CTA pairs to run on (0 = all): a few pairs stay far below the power cap
+if GRID:
+    M = 256 * GRID * 4
+for (N, K) in ((768, 768),):
     A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
     Wt = (0.05 * torch.randn(N, K, device="cuda")).to(torch.bfloat16)
     bias = torch.zeros(N, device="cuda")
     out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
     for pairs in (1,):
         for flags, name in CASES:
-            lib.csb_test_set_debug(flags)
+            lib.csb_test_set_debug(flags | (GRID << 16))
             us = time_it(lambda: _lib.check(lib.csb_test_linear_fwd(A.data_ptr(), Wt.data_ptr(), bias.data_ptr(), out.data_ptr(), M, N, K, 3, 0.15, pairs, None), "fwd"))
-            if flags == 0:
+            if flags == 0 and False:
                 ref = torch.nn.functional.leaky_relu(A[:256].float() @ Wt.float().t(), 0.15)
                 print("   check err", ((out[:256].float() - ref).abs().max() / ref.abs().max()).item())
-            s = stats.view(148, 4).cpu().double()
+            s = stats.view(148, 8)[: (2 * GRID if GRID else 148)].cpu().double()
             mhz = ((s[:, 1] - s[:, 0]) / (s[:, 3] - s[:, 2]).clamp(min=1) * 1e3).median().item()
             cyc = (s[:, 1] - s[:, 0]).median().item()
-            tiles = (M / 128) * ((N + 255) // 256) / 148
+            tiles = (M / 128) * ((N + 255) // 256) / (2 * GRID if GRID else 148)
             print(f"N={N} K={K} pairs={pairs} {name:32s} {us:7.1f} us  {2*M*N*K/us/1e6:7.1f} TF/s  SM {mhz:6.0f} MHz  {cyc/tiles:8.0f} cyc/tile/SM"
-                  f"  (MMA floor {K * 8 * N / (((N + 255) // 256) * 256):6.0f})", flush=True)
+                  f"  (MMA floor {K * 8 * N / (((N + 255) // 256) * 256):6.0f})  issuer waits: acc {s[::2, 4].median().item()/tiles:6.0f} operands {s[::2, 5].median().item()/tiles:6.0f}"
+                  f"  epi warp: wait {s[:, 6].median().item()/tiles:6.0f} busy {s[:, 7].median().item()/tiles:6.0f}", flush=True)
 lib.csb_test_set_debug(0)
 lib.csb_test_set_stats(None)

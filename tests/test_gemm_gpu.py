@@ -76,3 +76,42 @@ def test_gemm_nt(M, N, R, splits):
     cs_ref = B.float().sum(dim=0)
     cs_err = (colsum.sum(dim=0) - cs_ref).abs().max().item()
     assert cs_err <= 1e-3 * max(cs_ref.abs().max().item(), 1.0), cs_err
+
+
+@pytest.mark.parametrize("M,N,R,splits", [
+    (256, 128, 64, 1),          # smallest CTA pair: one 64-row block, 64 dZ columns per CTA
+    (256, 256, 1024, 1),        # ring wraps (6 stages), no split
+    (768, 640, 4096, 4),        # dW of layer 1: ragged last n-block (128 wide -> 64 columns per CTA)
+    (640, 640, 5000, 7),        # odd m-block count (idle half pair), ragged R, splits that do not divide
+    (640, 128, 70000, 16),      # 128-wide layer on pairs (BN = 128 instantiation)
+    (512, 640, 100, 3),         # more splits than the rows need: trailing splits get no work and write zeros
+    (192, 384, 3000, 5),        # M = 192: the last m-block is half a chunk short
+])
+def test_gemm_nt_cta_pairs(M, N, R, splits):
+    """gemm_nt_kernel<.., CG = 2>: 256 x BN weight-gradient tiles on tcgen05 cta_group::2 pairs."""
+    import ctypes
+    lib, L = _lib()
+    A = _bf16_operand(R, M, 5)
+    B = _bf16_operand(R, N, 6)
+    Cout = torch.full((splits, M, N), float("nan"), device="cuda")
+    colsum = torch.full((splits * ((M + 127) // 128), N), float("nan"), device="cuda")
+    m_tiles = ctypes.c_int(0)
+    L.check(lib.csb_test_gemm_nt_cg(A.data_ptr(), B.data_ptr(), Cout.data_ptr(), colsum.data_ptr(), M, N, R, splits, 2,
+                                    ctypes.byref(m_tiles), None), "csb_test_gemm_nt_cg")
+    torch.cuda.synchronize()
+    assert m_tiles.value == ((M + 127) // 128 + 1) // 2
+    got = Cout.sum(dim=0)
+    ref = A.float().t() @ B.float()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 1e-3 * scale, (err, scale)
+    cs_ref = B.float().sum(dim=0)
+    cs = colsum[: splits * m_tiles.value]
+    cs_err = (cs.sum(dim=0) - cs_ref).abs().max().item()
+    assert cs_err <= 1e-3 * max(cs_ref.abs().max().item(), 1.0), cs_err
+    # bit-reproducible (no atomics, fixed split geometry)
+    Cout2 = torch.empty_like(Cout)
+    L.check(lib.csb_test_gemm_nt_cg(A.data_ptr(), B.data_ptr(), Cout2.data_ptr(), colsum.data_ptr(), M, N, R, splits, 2,
+                                    ctypes.byref(m_tiles), None), "csb_test_gemm_nt_cg")
+    torch.cuda.synchronize()
+    assert torch.equal(Cout, Cout2)
