@@ -190,7 +190,7 @@ static int launch_nt(const CUtensorMap& ta, const CUtensorMap& tb, const tc::NtP
 // its width splits into two 64-column-chunk-aligned halves; an odd m-block count leaves half of the last pair's rows empty
 // (zero-filled by TMA, never stored), which still beats single CTAs that cannot take their operands in fast enough.
 static bool g_use_nt_pairs = true;  // CSB_NO_NT_PAIRS=1: single-CTA weight-gradient tiles (debugging aid)
-static inline int nt_cta_group(int M, int N) { return (g_use_nt_pairs && N % 128 == 0 && M > 128) ? 2 : 1; }
+static inline int nt_cta_group(int M, int N) { return (g_use_nt_pairs && N % 128 == 0 && N > 128 && M > 128) ? 2 : 1; }   // 128-wide layers: measured no gain
 static inline int nt_m_tiles(int M, int cg) { return (int)ceil_div(ceil_div(M, 128), cg); }
 static int launch_nt_auto(const CUtensorMap& ta, const CUtensorMap& tb, const tc::NtParams& p, int splits, cudaStream_t st, int cg = 1) {
   if (cg == 2) {
@@ -476,7 +476,7 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
     li.nt_block_n = tn_block_n(li.Np);
     li.nt_cg = h->bf16 ? nt_cta_group(li.Kp, li.Np) : 1;
     const int tiles = nt_m_tiles(li.Kp, li.nt_cg) * (int)ceil_div(li.Np, li.nt_block_n);
-    li.max_w_splits = h->bf16 ? std::max(1, std::min(64, (sm / li.nt_cg) / tiles)) : 1;
+    li.max_w_splits = h->bf16 ? std::max(1, (sm / li.nt_cg) / tiles) : 1;     // one wave of CTAs
     li.b_splits = h->bf16 ? li.max_w_splits * nt_m_tiles(li.Kp, li.nt_cg) : 32;
     li.ws_w_off = ws_off; ws_off += (size_t)li.max_w_splits * li.Kp * li.Np;
     li.ws_b_off = ws_off; ws_off += (size_t)li.b_splits * li.Np;
@@ -722,8 +722,8 @@ int csb_mlp_grad_buffer(csb_mlp* h, float** ptr, size_t* n) {
 // forward pieces
 // ---------------------------------------------------------------------------------------------------------------
 static int run_normalize(csb_mlp* h, const float* x, int64_t B, int apply, cudaStream_t st) {
-  if (h->bf16 && h->in_dim % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
-    const int grid = grid_for(B * (h->in_p / 4), 256, h->sm_count);
+  if (h->bf16 && h->in_dim % 4 == 0 && 256 % (h->in_p / 4) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const int grid = grid_for(B * (h->in_p / 4), 256, h->sm_count, 4);
     CSB_CUDA_CHECK(launch_pdl(simt::normalize_bf16_vec4_kernel, dim3(grid), dim3(256), 0, st, x, h->d_sub, h->d_div, apply,
                               reinterpret_cast<__nv_bfloat16*>(h->xn), B, h->in_dim, h->in_p));
   } else {

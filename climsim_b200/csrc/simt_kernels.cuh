@@ -31,33 +31,43 @@ __global__ void normalize_kernel(const float* __restrict__ x, int ld_x, const fl
   }
 }
 
-// Vectorised variant for F % 4 == 0 and bf16 output: one thread per 4 columns (128-bit load, 64-bit store).
+// Vectorised variant for F % 4 == 0 and bf16 output: one thread per 4 columns (128-bit load, 64-bit store).  A thread keeps its
+// column slot for the whole launch (the block is q = Fp / 4 slots wide, 256 / q rows tall; host guarantees 256 % q == 0), so the
+// normalisation constants are loaded once and no index division runs per element; four rows are in flight per thread.
+__device__ __forceinline__ float norm_elem(float x, float s, float d) {
+  const float v = __fdiv_rn(__fsub_rn(x, s), d);
+  return (isinf(v) || isnan(v)) ? 0.f : v;                 // (max == min) columns: inf / nan -> 0 as the reference does
+}
 __global__ void __launch_bounds__(256)
 normalize_bf16_vec4_kernel(const float* __restrict__ x, const float* __restrict__ sub, const float* __restrict__ div, int apply,
                            __nv_bfloat16* __restrict__ out, int64_t N, int F, int Fp) {
   const int q = Fp >> 2, qv = F >> 2;                    // float4 slots per padded row / valid slots
-  const int64_t total = N * q;
+  const int c4 = (int)threadIdx.x % q, rows_per_block = 256 / q;
+  const bool valid = c4 < qv;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), d = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (valid && apply) { s = __ldg(reinterpret_cast<const float4*>(sub) + c4); d = __ldg(reinterpret_cast<const float4*>(div) + c4); }
   pdl_launch_dependents();
   pdl_wait();
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / q;
-    const int c4 = (int)(i - r * q);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c4 < qv) {
-      v = __ldg(reinterpret_cast<const float4*>(x + r * F) + c4);
-      if (apply) {
-        const float4 s = __ldg(reinterpret_cast<const float4*>(sub) + c4), d = __ldg(reinterpret_cast<const float4*>(div) + c4);
-        v.x = (v.x - s.x) / d.x; v.y = (v.y - s.y) / d.y; v.z = (v.z - s.z) / d.z; v.w = (v.w - s.w) / d.w;
-        if (isinf(v.x) || isnan(v.x)) v.x = 0.f;
-        if (isinf(v.y) || isnan(v.y)) v.y = 0.f;
-        if (isinf(v.z) || isnan(v.z)) v.z = 0.f;
-        if (isinf(v.w) || isnan(v.w)) v.w = 0.f;
-      }
+  const int64_t step = (int64_t)gridDim.x * rows_per_block;
+  for (int64_t r0 = (int64_t)blockIdx.x * rows_per_block + (int)threadIdx.x / q; r0 < N; r0 += 4 * step) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t r = r0 + u * step;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid && r < N) v[u] = __ldcs(reinterpret_cast<const float4*>(x + r * F) + c4);       // streamed once
     }
-    uint2 o;
-    o.x = pack_bf16x2(v.x, v.y);
-    o.y = pack_bf16x2(v.z, v.w);
-    *reinterpret_cast<uint2*>(out + r * Fp + 4 * c4) = o;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t r = r0 + u * step;
+      if (r >= N) break;
+      float4 w = v[u];
+      if (apply && valid) { w.x = norm_elem(w.x, s.x, d.x); w.y = norm_elem(w.y, s.y, d.y); w.z = norm_elem(w.z, s.z, d.z); w.w = norm_elem(w.w, s.w, d.w); }
+      uint2 o;
+      o.x = pack_bf16x2(w.x, w.y);
+      o.y = pack_bf16x2(w.z, w.w);
+      *reinterpret_cast<uint2*>(out + r * Fp + 4 * c4) = o;
+    }
   }
 }
 

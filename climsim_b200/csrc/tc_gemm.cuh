@@ -126,6 +126,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
       : "memory");
 }
 
+// bulk (TMA, non-tensor) copy shared -> global of `bytes` (multiple of 16; both addresses 16-byte aligned), tracked by bulk groups
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, uint32_t ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// generic-proxy writes to shared memory (st.shared) -> visible to the async proxy (TMA) of this thread's later bulk copies
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
 }
@@ -990,18 +999,29 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (nrb > 0) {
       mbar_wait(tfull_bar, 0);
       tc_fence_after();
+      // Every MMA has completed, so the operand ring is free: each thread parks its output row (n_valid fp32) there and hands
+      // it to the bulk-copy engine as ONE contiguous shared -> global copy.  (Storing straight from registers makes every
+      // store instruction touch 32 different lines, ~16 B/clk per SM: 4 us for the 128 KB tile of a CTA, with nothing to
+      // overlap it in this one-tile-per-CTA kernel.)  Row pitch n_valid * 4 + 16 B keeps the 16-byte shared stores conflict-free.
+      // (the other epilogue warps may still be column-summing the last ring slot: all four pass this barrier before any writes)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+      const uint32_t pitch = (uint32_t)n_valid * 4u + 16u;
+      const uint32_t srow = smem_base + (uint32_t)(warp * 32 + lane) * pitch;
+      static_assert(BM * (BN * 4 + 16) <= L::BAR_OFFSET, "output staging tile must fit the operand ring");
       for (int c = 0; c < n_valid; c += 32) {
         uint32_t raw[32];
         tmem_ld_32x32(taddr + (uint32_t)c, raw);
         tmem_ld_wait();
-        if (row < p.M) {
-          float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-          store_f32x32(out + c, v);
-        }
+        for (int q4 = 0; q4 < 8; ++q4)
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(srow + (uint32_t)(c + 4 * q4) * 4u), "r"(raw[4 * q4]), "r"(raw[4 * q4 + 1]),
+                       "r"(raw[4 * q4 + 2]), "r"(raw[4 * q4 + 3]) : "memory");
       }
+      fence_proxy_async_smem();
+      if (row < p.M) bulk_store_s2g(out, srow, (uint32_t)n_valid * 4u);
+      bulk_commit();
+      bulk_wait_read_all();                         // shared memory must stay intact until the copy engine has read it
     } else if (row < p.M) {
       for (int c = 0; c < n_valid; c += 4) *reinterpret_cast<float4*>(out + c) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
