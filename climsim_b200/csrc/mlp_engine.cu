@@ -86,7 +86,9 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 
 template <int BN, int STAGES, int EPI, int CG, int VAR = 0>
 static int launch_tn(const CUtensorMap& ta, const CUtensorMap& tb, const tc::GemmParams& p, int sm_count, cudaStream_t st) {
-  using L = tc::TnSmem<BN, STAGES, CG>;
+  constexpr bool BF16_OUT = (EPI == tc::EPI_BIAS_ACT || EPI == tc::EPI_HEAD_LOSS || EPI == tc::EPI_DGRAD || EPI == tc::EPI_DGRAD_MASK ||
+                             EPI == tc::EPI_BIAS_ADD);
+  using L = tc::TnSmem<BN, STAGES, CG, (VAR & tc::VAR_STAGED) != 0 && BF16_OUT>;
   auto kern = tc::gemm_tn_kernel<BN, STAGES, EPI, CG, VAR>;
   CSB_REQUIRE((EPI == tc::EPI_HEAD_LOSS ? 2 : 1) * (int)round_up(p.N, BN) <= tc::TN_BIAS_SMEM, CSB_EUNSUPPORTED,
               "layer width %d too large for the %d-float bias / loss-weight area in shared memory", p.N, tc::TN_BIAS_SMEM);
@@ -129,8 +131,23 @@ static int launch_tn(const CUtensorMap& ta, const CUtensorMap& tb, const tc::Gem
 static inline bool tn_use_pairs(int N) { return g_use_pairs && N > 128; }
 static inline int tn_b_box_rows(int N) { return N > 128 ? (tn_use_pairs(N) ? std::min(N, 256) / 2 : std::min(N, 256)) : std::min(N, 128); }
 
+static bool g_use_staged = true;    // CSB_NO_STAGED_EPI=1: register -> global stores in every launch (debugging aid)
 template <int EPI, int VAR>
 static int launch_tn_shape(const CUtensorMap& ta, const CUtensorMap& tb, const tc::GemmParams& p, int sm_count, cudaStream_t st) {
+  constexpr bool BF16_OUT = (EPI == tc::EPI_BIAS_ACT || EPI == tc::EPI_HEAD_LOSS || EPI == tc::EPI_DGRAD || EPI == tc::EPI_DGRAD_MASK ||
+                             EPI == tc::EPI_BIAS_ADD);
+  if constexpr (BF16_OUT) {
+    // Short contractions (K <= 256: at most four k-blocks per tile) are bound by the epilogue's stores, not by the mainloop:
+    // they trade operand-ring stages for an output staging tile and coalesced stores.
+    if (g_use_staged && p.K <= 256 && p.kb_per_tap == 0) {
+      constexpr int V = VAR | tc::VAR_STAGED;
+      if (p.N > 128) {
+        if (tn_use_pairs(p.N)) return launch_tn<256, 4, EPI, 2, V>(ta, tb, p, sm_count, st);
+        return launch_tn<256, 2, EPI, 1, V>(ta, tb, p, sm_count, st);
+      }
+      return launch_tn<128, 4, EPI, 1, V>(ta, tb, p, sm_count, st);
+    }
+  }
   if (p.N > 128) {
     if (tn_use_pairs(p.N)) return launch_tn<256, 6, EPI, 2, VAR>(ta, tb, p, sm_count, st);
     return launch_tn<256, 4, EPI, 1, VAR>(ta, tb, p, sm_count, st);
@@ -449,6 +466,7 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
 
   g_use_pairs = getenv("CSB_NO_PAIRS") == nullptr;
   g_use_nt_pairs = getenv("CSB_NO_NT_PAIRS") == nullptr;
+  g_use_staged = getenv("CSB_NO_STAGED_EPI") == nullptr;
   g_use_pdl = getenv("CSB_NO_PDL") == nullptr;
   csb_mlp* h = new (std::nothrow) csb_mlp();
   CSB_REQUIRE(h != nullptr, CSB_ENOMEM, "host allocation failed");
@@ -476,7 +494,8 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
     li.nt_block_n = tn_block_n(li.Np);
     li.nt_cg = h->bf16 ? nt_cta_group(li.Kp, li.Np) : 1;
     const int tiles = nt_m_tiles(li.Kp, li.nt_cg) * (int)ceil_div(li.Np, li.nt_block_n);
-    li.max_w_splits = h->bf16 ? std::max(1, (sm / li.nt_cg) / tiles) : 1;     // one wave of CTAs
+    // one wave of CTAs, but at most 64 partials: the reduction walks a tile's partials serially
+    li.max_w_splits = h->bf16 ? std::max(1, std::min(64, (sm / li.nt_cg) / tiles)) : 1;
     li.b_splits = h->bf16 ? li.max_w_splits * nt_m_tiles(li.Kp, li.nt_cg) : 32;
     li.ws_w_off = ws_off; ws_off += (size_t)li.max_w_splits * li.Kp * li.Np;
     li.ws_b_off = ws_off; ws_off += (size_t)li.b_splits * li.Np;

@@ -390,10 +390,17 @@ ln_param_grad_kernel(const T* __restrict__ du, const T* __restrict__ z, int ld, 
 struct Segment { const float* ws; size_t stride; float* grad; int64_t len; int splits; };
 
 // sum_s p[s * stride] over four consecutive floats, splits taken in order 0, 1, 2, ... (the fixed order every gradient in the
-// engine is reduced in); loads are issued four splits at a time so that several are in flight per thread
+// engine is reduced in); loads are issued eight (then four) splits at a time so that several are in flight per thread
 __device__ __forceinline__ float4 sum_partials4(const float* __restrict__ p, size_t stride, int splits) {
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
   int s = 0;
+  for (; s + 8 <= splits; s += 8) {               // (the additions stay in split order: only the loads are batched)
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldcs(reinterpret_cast<const float4*>(p + (size_t)(s + u) * stride));
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
+  }
   for (; s + 4 <= splits; s += 4) {
     float4 v[4];
 #pragma unroll

@@ -275,6 +275,14 @@ __device__ __forceinline__ void store_bf16x32_global(__nv_bfloat16* dst, const f
                  "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
   }
 }
+// 32 bf16 (64 B) into shared memory at a 16-byte aligned address
+__device__ __forceinline__ void stage_bf16x32(uint32_t saddr, const float (&v)[32]) {
+#pragma unroll
+  for (int h = 0; h < 4; ++h)
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr + 16u * h), "r"(pack_bf16x2(v[8 * h], v[8 * h + 1])),
+                 "r"(pack_bf16x2(v[8 * h + 2], v[8 * h + 3])), "r"(pack_bf16x2(v[8 * h + 4], v[8 * h + 5])),
+                 "r"(pack_bf16x2(v[8 * h + 6], v[8 * h + 7])) : "memory");
+}
 __device__ __forceinline__ void load_bf16x32_global_raw(const __nv_bfloat16* src, uint32_t (&w)[16]) {
 #pragma unroll
   for (int h = 0; h < 2; ++h)
@@ -365,10 +373,12 @@ __device__ __forceinline__ RowInfo make_row_info(const GemmParams& p, int grow) 
 
 // One 32-column step of the epilogue.  gcol = global column; sbias = the layer's bias vector in shared memory;
 // `sv` holds the 32 saved bf16 values of EPI_DGRAD / EPI_BIAS_ADD.
-template <int EPI, bool ELU, bool GENERAL_LOSS>
+// STAGED: the 32 bf16 results go to this thread's row of the warp's staging tile in shared memory (`stage_addr`); the warp writes the
+// tile to global memory afterwards with fully coalesced stores (see the kernel).
+template <int EPI, bool ELU, bool GENERAL_LOSS, bool STAGED>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float* sbias, const float* sloss_w, const RowInfo& ri, int gcol,
                                                const uint32_t (&raw)[32], const uint32_t (&sv)[16], const float (&yv)[32], float& loss_acc,
-                                               uint32_t mask_word) {
+                                               uint32_t mask_word, uint32_t stage_addr) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
@@ -403,22 +413,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = 0.f;
     }
-    if (p.dbg & 256) {
-      // bandwidth experiment only (results are permuted): the same bytes, but every store instruction of the warp covers 8 rows x
-      // 128 contiguous bytes instead of 32 rows x 32 bytes
-      const int lane = threadIdx.x & 31, i = (gcol >> 5) & 1;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)(ri.grow - lane + 8 * (2 * i + h) + (lane >> 2)) * p.ld_out +
-                           (gcol - 32 * i) + (lane & 3) * 16;
-        uint32_t w[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) w[k] = pack_bf16x2(v[16 * h + 2 * k], v[16 * h + 2 * k + 1]);
-        if (st_ok) asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(d), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
-                                "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
-      }
-    } else
-    if (st_ok) store_bf16x32_global(out16, v);
+    if constexpr (STAGED) stage_bf16x32(stage_addr, v); else if (st_ok) store_bf16x32_global(out16, v);
   } else if constexpr (EPI == EPI_DGRAD_MASK) {
     // act'(a) through the sign bit: relu -> {1, 0}, leaky relu -> {1, alpha}
     const float neg = p.act == CSB_ACT_LEAKYRELU ? p.alpha : 0.f;
@@ -429,7 +424,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = 0.f;
     }
-    if (st_ok) store_bf16x32_global(out16, v);
+    if constexpr (STAGED) stage_bf16x32(stage_addr, v); else if (st_ok) store_bf16x32_global(out16, v);
   } else if constexpr (EPI == EPI_DGRAD) {
     float a[32];
     unpack_bf16x32(sv, a);                          // saved activation (same rows / columns as the output)
@@ -438,13 +433,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = 0.f;
     }
-    if (st_ok) store_bf16x32_global(out16, v);
+    if constexpr (STAGED) stage_bf16x32(stage_addr, v); else if (st_ok) store_bf16x32_global(out16, v);
   } else if constexpr (EPI == EPI_BIAS_ADD) {
     float a[32];
     unpack_bf16x32(sv, a);                          // tile to add (residual branch / partial gradient)
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = ri.zero_row ? 0.f : v[j] + a[j];
-    if (st_ok) store_bf16x32_global(out16, v);
+    if constexpr (STAGED) stage_bf16x32(stage_addr, v); else if (st_ok) store_bf16x32_global(out16, v);
   } else {
     // head: p = (col >= head_relu_from) ? relu(z) : act(z); everything is computed element by element in place (v: z -> p -> dL/dz)
     // so that the live set stays at the accumulator chunk + the prefetched targets (a spill here exposes the target loads' latency)
@@ -545,7 +540,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
         }
       }
       }
-      if (st_ok) store_bf16x32_global(out16, v);
+      if constexpr (STAGED) stage_bf16x32(stage_addr, v); else if (st_ok) store_bf16x32_global(out16, v);
     }
   }
 }
@@ -566,13 +561,18 @@ constexpr int TN_THREADS = TN_EPI_THREADS + 64;
 // ALU bursts (as warp 17 it did: the epilogue's issue cycles showed up one-for-one in the tile time).
 constexpr int TN_MMA_WARP = 0, TN_PRODUCER_WARP = 1, TN_FIRST_EPI_WARP = 2;
 
-template <int BN, int STAGES, int CG = 1>
+template <int BN, int STAGES, int CG = 1, bool STAGED = false>
 struct TnSmem {
   static constexpr int A_BYTES = BM * BK * 2;   // 16 KB
   static constexpr int B_BYTES = (BN / CG) * BK * 2;   // cta_group::2: each CTA of the pair holds half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BIAS_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFFSET = BIAS_OFFSET + TN_BIAS_SMEM * 4;
+  // STAGED: one output staging tile per epilogue warp, 32 rows x (BN / 4 bf16 + 16 B): the odd multiple of 16 B keeps the
+  // row-per-lane 16-byte writes and the row-contiguous reads both free of bank conflicts
+  static constexpr int OUT_PITCH = (BN / 4) * 2 + 16;
+  static constexpr int OUT_WARP_BYTES = 32 * OUT_PITCH;
+  static constexpr int OUT_OFFSET = BIAS_OFFSET + TN_BIAS_SMEM * 4;
+  static constexpr int BAR_OFFSET = OUT_OFFSET + (STAGED ? TN_EPI_WARPS * OUT_WARP_BYTES : 0);
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // barriers + slack for manual 1024 B alignment
   static_assert(TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
 };
@@ -582,12 +582,16 @@ struct TnSmem {
 // both, each CTA runs the epilogue of its own 128 rows.  Halves the B traffic and the B footprint per stage.
 // VAR: bit 0 = ELU activation (expm1f in the epilogue), bit 1 = general loss path of EPI_HEAD_LOSS (MAE / Huber / output mask);
 // both keep rarely used code out of the instruction stream (and the register budget) of the common kernels
-constexpr int VAR_ELU = 1, VAR_GENERAL_LOSS = 2;
+// bit 2 = results staged in shared memory and written with coalesced stores (the launches whose time is the epilogue: K <= 256)
+constexpr int VAR_ELU = 1, VAR_GENERAL_LOSS = 2, VAR_STAGED = 4;
 template <int BN, int STAGES, int EPI, int CG, int VAR>
 __global__ void __launch_bounds__(TN_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
-  using L = TnSmem<BN, STAGES, CG>;
   constexpr bool ELU = (VAR & VAR_ELU) != 0, GENERAL_LOSS = (VAR & VAR_GENERAL_LOSS) != 0;
+  constexpr bool BF16_OUT = (EPI == EPI_BIAS_ACT || EPI == EPI_HEAD_LOSS || EPI == EPI_DGRAD || EPI == EPI_DGRAD_MASK || EPI == EPI_BIAS_ADD);
+  constexpr bool STAGED = (VAR & VAR_STAGED) != 0 && BF16_OUT;
+  constexpr bool STATS = (EPI == EPI_BIAS_ACT && VAR == 0);    // only the kernel the micro-benchmark drives carries the cycle counters
+  using L = TnSmem<BN, STAGES, CG, STAGED>;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   const bool is_leader = cta_rank == 0;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
@@ -641,7 +645,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if constexpr (CG == 2) cluster_sync_all();       // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (p.stats != nullptr && threadIdx.x == 32) {
+  if (STATS && p.stats != nullptr && threadIdx.x == 32) {
     p.stats[8 * blockIdx.x + 0] = (unsigned long long)clock64();
     p.stats[8 * blockIdx.x + 2] = globaltimer_ns();
   }
@@ -685,15 +689,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int n_valid = min(BN, p.N - n0);
         const uint32_t idesc = make_idesc_bf16(BM * CG, n_valid, 0, 0);
         const int acc = t & 1;
-        long long c0 = p.stats ? clock64() : 0;
+        long long c0 = (STATS && p.stats) ? clock64() : 0;
         mbar_wait(tempty_bar(acc), ((uint32_t)(t >> 1) & 1u) ^ 1u);
-        if (p.stats) st_tempty += clock64() - c0;
+        if (STATS && p.stats) st_tempty += clock64() - c0;
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < num_kb; ++kb) {
-          c0 = p.stats ? clock64() : 0;
+          c0 = (STATS && p.stats) ? clock64() : 0;
           mbar_wait(full_bar(s), ph);
-          if (p.stats) st_full += clock64() - c0;
+          if (STATS && p.stats) st_full += clock64() - c0;
           tc_fence_after();
           const uint32_t sa = smem_base + s * L::STAGE_BYTES;
           const uint64_t da = make_desc_kmajor_sw128(sa);
@@ -712,13 +716,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // accumulator complete -> epilogue (of both CTAs of a pair)
         if constexpr (CG == 2) umma_commit_2sm(tfull_bar(acc)); else umma_commit(tfull_bar(acc));
       }
-      if (p.stats) { p.stats[8 * blockIdx.x + 4] = (unsigned long long)st_tempty; p.stats[8 * blockIdx.x + 5] = (unsigned long long)st_full; }
+      if (STATS && p.stats) { p.stats[8 * blockIdx.x + 4] = (unsigned long long)st_tempty; p.stats[8 * blockIdx.x + 5] = (unsigned long long)st_full; }
     }
   } else {
     // ===================== epilogue: warp w -> TMEM lanes 32*(w&3).., columns [QCOLS*(w>>2), QCOLS*(w>>2)+QCOLS) ==========
     const int ew = warp - TN_FIRST_EPI_WARP;                 // 0..15
     const int q = warp & 3, cq = ew >> 2;                    // TMEM lane quadrant = hardware warp id % 4; column quarter
     const int tile_row = q * 32 + lane;
+    const uint32_t stage_warp = smem_base + (uint32_t)(L::OUT_OFFSET + ew * L::OUT_WARP_BYTES);     // STAGED only
     int t = 0;
     long long st_epi_wait = 0, st_epi_busy = 0;      // micro-benchmark (epilogue warp 0): cycles waiting for an accumulator / working on it
     for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++t) {
@@ -770,9 +775,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       };
       load_targets(c0);
-      long long ck0 = p.stats ? clock64() : 0;
+      long long ck0 = (STATS && p.stats) ? clock64() : 0;
       mbar_wait(tfull_bar(acc), (uint32_t)(t >> 1) & 1u);
-      long long ck1 = p.stats ? clock64() : 0;
+      long long ck1 = (STATS && p.stats) ? clock64() : 0;
       tc_fence_after();
       float loss_acc = 0.f;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0);
@@ -789,7 +794,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; ++j) raw[j] = 0u;
           }
-          if (!(p.dbg & 2)) epilogue_chunk<EPI, ELU, GENERAL_LOSS>(p, sbias, sloss_w, ri, n0 + c, raw, sv[i], yv, loss_acc, mask_words[i]);
+          if (!(p.dbg & 2))
+            epilogue_chunk<EPI, ELU, GENERAL_LOSS, STAGED>(p, sbias, sloss_w, ri, n0 + c, raw, sv[i], yv, loss_acc, mask_words[i],
+                                                           stage_warp + (uint32_t)(lane * L::OUT_PITCH + 64 * i));
         }
       }
       tc_fence_before();
@@ -797,7 +804,26 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (lane == 0) {                                        // TMEM buffer free: the MMA of tile t+2 may start
         if constexpr (CG == 2) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc));
       }
-      if (p.stats && ew == 0 && lane == 0) { st_epi_wait += ck1 - ck0; st_epi_busy += clock64() - ck1; }
+      if constexpr (STAGED) {
+        // the warp's 32 x QCOLS bf16 tile, shared -> global: each instruction moves 16 B per lane, a row's lanes adjacent, so
+        // a store instruction covers 4 (QCOLS = 64) or 8 (QCOLS = 32) whole row segments instead of 32 separate 32-byte pieces
+        if (c0 < n_valid && !(p.dbg & (2 | 4))) {
+          constexpr int CPR = QCOLS * 2 / 16, RPI = 32 / CPR;     // 16-byte chunks per row, rows per instruction
+          const int rr = lane / CPR, ch = lane % CPR;
+          __nv_bfloat16* gbase = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)(m0 + q * 32) * p.ld_out + n0 + c0 + 8 * ch;
+#pragma unroll
+          for (int j = 0; j < 32 / RPI; ++j) {
+            const int r = j * RPI + rr;
+            uint32_t w0, w1, w2, w3;
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                         : "r"(stage_warp + (uint32_t)(r * L::OUT_PITCH + 16 * ch)) : "memory");
+            if (m0 + q * 32 + r < p.M)
+              asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(gbase + (size_t)r * p.ld_out), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+          }
+        }
+        __syncwarp();                                         // the tile is read before the next tile's rows overwrite it
+      }
+      if (STATS && p.stats && ew == 0 && lane == 0) { st_epi_wait += ck1 - ck0; st_epi_busy += clock64() - ck1; }
       if constexpr (EPI == EPI_HEAD_LOSS) {
         // deterministic: one partial per (m-block, n-block, epilogue warp)
 #pragma unroll
@@ -805,12 +831,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (lane == 0 && m0 < p.M) p.loss_partials[(mb * num_n_blocks + (tile % num_n_blocks)) * TN_EPI_WARPS + ew] = loss_acc * p.grad_scale;
       }
     }
-    if (p.stats && ew == 0 && lane == 0) { p.stats[8 * blockIdx.x + 6] = (unsigned long long)st_epi_wait; p.stats[8 * blockIdx.x + 7] = (unsigned long long)st_epi_busy; }
+    if (STATS && p.stats && ew == 0 && lane == 0) { p.stats[8 * blockIdx.x + 6] = (unsigned long long)st_epi_wait; p.stats[8 * blockIdx.x + 7] = (unsigned long long)st_epi_busy; }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (p.stats != nullptr && threadIdx.x == 32) {
+  if (STATS && p.stats != nullptr && threadIdx.x == 32) {
     p.stats[8 * blockIdx.x + 1] = (unsigned long long)clock64();
     p.stats[8 * blockIdx.x + 3] = globaltimer_ns();
   }
