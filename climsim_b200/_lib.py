@@ -10,7 +10,7 @@ import os
 from typing import Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libclimsim_b200.so")
+LIB_PATH = os.environ.get("CSB_LIB_PATH") or os.path.join(HERE, "libclimsim_b200.so")    # override: A/B runs of two builds
 MAX_LAYERS = 24
 
 OK, EINVAL, ENODEV, ENOMEM, ECUDA, ESTATE, EUNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
@@ -116,6 +116,8 @@ def load() -> C.CDLL:
                           "climsim_b200 has no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
+        if name.startswith("csb_test_") and os.environ.get("CSB_LIB_PATH") and not hasattr(lib, name):
+            continue                     # an older build loaded for an A/B run may lack newer self-test hooks
         fn = getattr(lib, name)          # AttributeError here == header/library mismatch
         fn.restype, fn.argtypes = res, args
     _lib = lib

@@ -1379,6 +1379,7 @@ int csb_test_linear_fwd(const uint16_t* A, const uint16_t* Wt, const float* bias
   p.dbg = g_test_dbg;
   p.stats = g_test_stats;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (use_pairs && p.stats != nullptr) return launch_tn<256, 6, tc::EPI_BIAS_ACT, 2, tc::VAR_STATS>(ta, tb, p, sm, st);   // probe_mainloop.py
   if (use_pairs) return launch_tn<256, 6, tc::EPI_BIAS_ACT, 2>(ta, tb, p, sm, st);
   if (wide) return launch_tn<256, 4, tc::EPI_BIAS_ACT, 1>(ta, tb, p, sm, st);
   return launch_tn<128, 6, tc::EPI_BIAS_ACT, 1>(ta, tb, p, sm, st);

@@ -583,14 +583,15 @@ struct TnSmem {
 // VAR: bit 0 = ELU activation (expm1f in the epilogue), bit 1 = general loss path of EPI_HEAD_LOSS (MAE / Huber / output mask);
 // both keep rarely used code out of the instruction stream (and the register budget) of the common kernels
 // bit 2 = results staged in shared memory and written with coalesced stores (the launches whose time is the epilogue: K <= 256)
-constexpr int VAR_ELU = 1, VAR_GENERAL_LOSS = 2, VAR_STAGED = 4;
+// bit 3 = in-kernel cycle counters for the micro-benchmark (p.stats); production instantiations carry none of that code
+constexpr int VAR_ELU = 1, VAR_GENERAL_LOSS = 2, VAR_STAGED = 4, VAR_STATS = 8;
 template <int BN, int STAGES, int EPI, int CG, int VAR>
 __global__ void __launch_bounds__(TN_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
   constexpr bool ELU = (VAR & VAR_ELU) != 0, GENERAL_LOSS = (VAR & VAR_GENERAL_LOSS) != 0;
   constexpr bool BF16_OUT = (EPI == EPI_BIAS_ACT || EPI == EPI_HEAD_LOSS || EPI == EPI_DGRAD || EPI == EPI_DGRAD_MASK || EPI == EPI_BIAS_ADD);
   constexpr bool STAGED = (VAR & VAR_STAGED) != 0 && BF16_OUT;
-  constexpr bool STATS = (EPI == EPI_BIAS_ACT && VAR == 0);    // only the kernel the micro-benchmark drives carries the cycle counters
+  constexpr bool STATS = (VAR & VAR_STATS) != 0;
   using L = TnSmem<BN, STAGES, CG, STAGED>;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   const bool is_leader = cta_rank == 0;
