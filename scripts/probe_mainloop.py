@@ -1,6 +1,7 @@
 """Mainloop probe (GPU box): forward-layer kernel with parts of the pipeline switched off (csb_test_set_debug) and the SM
 clock measured inside the kernel (clock64 / globaltimer per CTA), to tell ingest-bound from MMA-bound from epilogue-bound.
-flags: 1 bias, 2 math+sts, 4 TMA store, 8 LDTM, 16 no TMA loads, 32 no MMAs, 64 no B loads, 128 no A loads."""
+flags: 1 bias, 2 math + stores, 4 stores, 8 TMEM loads, 16 no TMA loads, 32 no MMAs, 64 no B loads, 128 no A loads.
+    python scripts/probe_mainloop.py [pairs]     pairs > 0: run on that many CTA pairs only (stays below the power cap)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -11,8 +12,7 @@ M = 65536
 stats = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
 lib.csb_test_set_stats(stats.data_ptr())
 CASES = [(0, "full"), (4, "no stores"), (2, "no math, no stores"), (1, "no bias"), (15, "epilogue off"), (15 + 16, "epi off, no loads"),
-         (15 + 32, "epi off, no MMA (ingest only)"), (16, "full epilogue, no loads"), (32, "full epilogue, no MMA"), (16 + 32, "epilogue only"),
-         (256, "full, coalesced (permuted) stores")]
+         (15 + 32, "epi off, no MMA (ingest only)"), (16, "full epilogue, no loads"), (32, "full epilogue, no MMA"), (16 + 32, "epilogue only")]
 GRID = int(sys.argv[1]) if len(sys.argv) > 1 else 0      # CTA pairs to run on (0 = all): a few pairs stay far below the power cap
 if GRID:
     M = 256 * GRID * 4
