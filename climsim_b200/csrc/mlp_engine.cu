@@ -1419,6 +1419,11 @@ int csb_test_linear_fwd(const uint16_t* A, const uint16_t* Wt, const float* bias
   p.dbg = g_test_dbg;
   p.stats = g_test_stats;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (pairs == 2) {                       // the engine's own policy (tile shape, CTA pairs, staged epilogue for short contractions)
+    CUtensorMap tb2;
+    if ((rc = make_tmap_bf16(&tb2, Wt, K, N, K, 64, (uint32_t)tn_b_box_rows(N)))) return rc;
+    return act == CSB_ACT_ELU ? launch_tn_shape<tc::EPI_BIAS_ACT, tc::VAR_ELU>(ta, tb2, p, sm, st) : launch_tn_shape<tc::EPI_BIAS_ACT, 0>(ta, tb2, p, sm, st);
+  }
   if (use_pairs && p.stats != nullptr) return launch_tn<256, 6, tc::EPI_BIAS_ACT, 2, tc::VAR_STATS>(ta, tb, p, sm, st);   // probe_mainloop.py
   if (use_pairs) return launch_tn<256, 6, tc::EPI_BIAS_ACT, 2>(ta, tb, p, sm, st);
   if (wide) return launch_tn<256, 4, tc::EPI_BIAS_ACT, 1>(ta, tb, p, sm, st);

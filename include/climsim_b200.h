@@ -246,8 +246,9 @@ int  csb_eval_metrics(const float* pred, const float* target, const float* x_nor
 /* ---- kernel self-test hooks (used by tests/test_gemm_gpu.py; device pointers) ----------------------------- */
 /* C[M,N] (fp32) = A[M,K] * Bt[N,K]^T on the tcgen05 path (both operands K-major bf16, raw uint16 payloads). */
 int  csb_test_gemm_tn(const uint16_t* A, const uint16_t* Bt, float* C, int M, int N, int K, int block_n, void* stream);
-/* out[M,N] (bf16) = act(A[M,K] * Wt[N,K]^T + bias): one forward layer exactly as the engine runs it (staged TMA-store
- * epilogue); pairs != 0 selects the cta_group::2 variant.  For kernel micro-benchmarks (scripts/microbench_gemm.py). */
+/* out[M,N] (bf16) = act(A[M,K] * Wt[N,K]^T + bias): one forward layer as the engine runs it.  pairs = 0: single-CTA tiles,
+ * 1: cta_group::2 pairs (layers wider than 128), 2: the engine's own launch policy (pairs + the staged coalesced-store epilogue
+ * for K <= 256).  For kernel micro-benchmarks (scripts/microbench_gemm.py) and tests/test_gemm_gpu.py. */
 int  csb_test_linear_fwd(const uint16_t* A, const uint16_t* Wt, const float* bias, uint16_t* out, int M, int N, int K, int act,
                          float alpha, int pairs, void* stream);
 void csb_test_set_debug(int flags);   /* epilogue ablation knobs for the micro-benchmark (0 = normal operation) */

@@ -115,3 +115,28 @@ def test_gemm_nt_cta_pairs(M, N, R, splits):
                                     ctypes.byref(m_tiles), None), "csb_test_gemm_nt_cg")
     torch.cuda.synchronize()
     assert torch.equal(Cout, Cout2)
+
+
+@pytest.mark.parametrize("M,N,K,act", [
+    (4096, 768, 128, 3),        # layer-0 shape: staged epilogue on CTA pairs (K <= 256), LeakyReLU
+    (1000, 640, 128, 1),        # ragged M, ragged last n-block (128 of 256 columns), ReLU
+    (333, 128, 128, 0),         # 128-wide tiles (32 columns per epilogue warp), no activation
+    (70000, 128, 256, 3),       # many tiles per CTA: the staging tile is reused across tiles
+    (513, 192, 64, 2),          # ELU instantiation, N not a multiple of 128
+    (2048, 640, 768, 3),        # long contraction: register -> global epilogue (not staged), for comparison
+])
+def test_linear_fwd_engine_policy(M, N, K, act):
+    """One forward layer through the engine's launch policy (csb_test_linear_fwd, pairs = 2) against torch fp32 on the same bf16
+    operands: covers the staged (shared memory -> coalesced stores) epilogue of the short-contraction launches."""
+    lib, L = _lib()
+    A = _bf16_operand(M, K, 7)
+    Wt = (_bf16_operand(N, K, 8).float() * 0.1).to(torch.bfloat16)
+    bias = torch.linspace(-0.5, 0.5, N, device="cuda")
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    L.check(lib.csb_test_linear_fwd(A.data_ptr(), Wt.data_ptr(), bias.data_ptr(), out.data_ptr(), M, N, K, act, 0.15, 2, None), "csb_test_linear_fwd")
+    torch.cuda.synchronize()
+    z = A.float() @ Wt.float().t() + bias
+    ref = {0: z, 1: torch.relu(z), 2: torch.nn.functional.elu(z), 3: torch.nn.functional.leaky_relu(z, 0.15)}[act]
+    assert not torch.isnan(out.float()).any()
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 1e-2 * ref.abs().max().item(), err          # one bf16 rounding of the result
