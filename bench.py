@@ -173,6 +173,8 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a GPU for --impl ours (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: anything NCCL wants to say (its version banner under NCCL_DEBUG=VERSION) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from climsim_b200 import MLPEngine
