@@ -59,6 +59,7 @@ SIGNATURES = {
     "csb_mlp_get_opt_state": (C.c_int, [_VP, _VP, _VP, _P(C.c_int64)]),
     "csb_mlp_set_opt_state": (C.c_int, [_VP, _VP, _VP, C.c_int64]),
     "csb_mlp_set_norm": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
+    "csb_mlp_set_input_transform": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
     "csb_mlp_set_output_mask": (C.c_int, [_VP, _VP]),
     "csb_mlp_forward": (C.c_int, [_VP, _VP, _VP, C.c_int64, C.c_uint32, _VP]),
     "csb_mlp_forward_host": (C.c_int, [_VP, _VP, _VP, C.c_int64, C.c_uint32, _VP]),

@@ -47,7 +47,18 @@ class _EngineModule(torch.nn.Module):
             self.engine.set_params_device(self.flat.detach())
             self._uploaded_version = self.flat._version
 
+    def _apply_own_config(self) -> None:
+        """Engine state this module relies on (output mask, no input transform); re-applied after a wrapper borrowed the engine."""
+        self.engine.set_input_transform()
+        self.engine.set_output_mask(None)
+
+    def _claim_engine(self) -> None:
+        if getattr(self.engine, "config_owner", None) is not None:
+            self._apply_own_config()
+            self.engine.config_owner = None
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        self._claim_engine()
         if torch.is_grad_enabled() and (self.flat.requires_grad or x.requires_grad):
             return _EngineFunction.apply(x, self.flat, self)
         self._sync_params()
@@ -161,11 +172,19 @@ class OnlineMLP(_EngineModule):
         spec = [(h, "relu", 0.0) for h in hidden] + [(out_dims, "none", 0.0)]
         super().__init__(MLPEngine(in_dims, spec, head_relu_from=out_dims - 8, dtype=dtype, max_batch=max_batch), seed)
         self.output_prune, self.strato_lev_out = output_prune, strato_lev_out
-        if output_prune:
-            mask = np.ones(out_dims, np.float32)
-            for start in (60, 120, 180, 240):
-                mask[start:start + strato_lev_out] = 0
-            self.engine.set_output_mask(mask)
+        self._apply_own_config()
+
+    def _own_mask(self) -> Optional[np.ndarray]:
+        if not self.output_prune:
+            return None
+        mask = np.ones(self.engine.out_dim, np.float32)
+        for start in (60, 120, 180, 240):
+            mask[start:start + self.strato_lev_out] = 0
+        return mask
+
+    def _apply_own_config(self) -> None:
+        self.engine.set_input_transform()
+        self.engine.set_output_mask(self._own_mask())
 
     def load_reference_state_dict(self, sd) -> None:
         """Keys ``linears.{i}.0.weight`` (out,in) / ``.bias`` and ``final_linear.*`` of the reference module."""
@@ -174,6 +193,49 @@ class OnlineMLP(_EngineModule):
             parts += [sd[f"linears.{i}.0.weight"].t().reshape(-1), sd[f"linears.{i}.0.bias"]]
         parts += [sd["final_linear.weight"].t().reshape(-1), sd["final_linear.bias"]]
         self.load_flat(torch.cat([p.detach().float().cpu().reshape(-1) for p in parts]).numpy())
+
+
+class OnlineInferenceWrapper(torch.nn.Module):
+    """``NewModel`` of online_testing/model_postprocessing/v2_nn_wrapper.ipynb (cell 5), the module exported for the E3SM coupling:
+    raw, un-normalised ``(B, 557)`` in, physical-unit ``(B, 368)`` tendencies out.  ``preprocessing`` (``1 - exp(-lambda q)`` for
+    cloud liquid / ice, normalisation, nan / inf -> 0, pruning of the top ``prune_qn_levels`` cloud levels, clipping of relative
+    humidity to [0, 1.2]), the network and ``postprocessing`` (zeroing of the stratospheric tendencies, division by ``out_scale``)
+    run as ONE engine call: the prologue kernel, the GEMM chain, and the output layer's epilogue carrying mask and scale.
+
+    Same constructor arguments as the reference class; the pruning ranges it hard-codes are keyword arguments with its values."""
+
+    def __init__(self, original_model: "OnlineMLP", input_sub, input_div, out_scale, lbd_qc, lbd_qi, prune_qn_levels: int = 15,
+                 rh_clip=(0.0, 1.2), out_prune=((60, 75), (120, 148), (180, 195), (240, 255), (300, 315))):
+        super().__init__()
+        self.original_model = original_model
+        eng = original_model.engine
+        n_in, n_out = eng.in_dim, eng.out_dim
+        lam = np.zeros(n_in, np.float32)
+        lam[120:180] = np.asarray(lbd_qc, np.float32).reshape(-1)
+        lam[180:240] = np.asarray(lbd_qi, np.float32).reshape(-1)
+        keep = np.ones(n_in, np.float32)
+        keep[120:120 + prune_qn_levels] = 0
+        keep[180:180 + prune_qn_levels] = 0
+        lo, hi = np.full(n_in, -np.inf, np.float32), np.full(n_in, np.inf, np.float32)
+        lo[60:120], hi[60:120] = rh_clip
+        own = original_model._own_mask()                      # the network's own output_prune (mlp.py:56-61)
+        mask = own.copy() if own is not None else np.ones(n_out, np.float32)
+        for a, b in out_prune:
+            mask[a:b] = 0
+        self._cfg = dict(sub=np.asarray(input_sub, np.float32), div=np.asarray(input_div, np.float32),
+                         scale=np.asarray(out_scale, np.float32), lam=lam, keep=keep, lo=lo, hi=hi, mask=mask)
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        m, c = self.original_model, self._cfg
+        eng = m.engine
+        m._sync_params()
+        if getattr(eng, "config_owner", None) is not self:    # configure the engine once; the wrapped module re-claims it on its next call
+            eng.set_norm(inp_sub=c["sub"], inp_div=c["div"], out_scale=c["scale"])
+            eng.set_input_transform(c["lam"], c["keep"], c["lo"], c["hi"])
+            eng.set_output_mask(c["mask"])
+            eng.config_owner = self
+        return eng.forward(x, normalize_in=True, denorm_out=True)
 
 
 class CNN(torch.nn.Module):

@@ -284,6 +284,7 @@ struct csb_mlp {
   float* dx_tmp = nullptr;                  // [cap x in_p] (lazily allocated)
   float *d_sub = nullptr, *d_div = nullptr, *d_out_scale = nullptr, *d_inv_out_scale = nullptr, *d_loss_w = nullptr, *d_out_mask = nullptr;
   bool has_mask = false;
+  float* d_xform = nullptr;                 // csb_mlp_set_input_transform: [4][in_p] lambda, keep, clip_lo, clip_hi (NULL: plain normalisation)
   float *loss_partials = nullptr, *d_loss = nullptr;
   int n_loss_partials = 0;
   // device staging for the *_host entry points: two slots, filled on an internal copy stream so that the H2D copy of
@@ -348,7 +349,7 @@ static void free_all(csb_mlp* h) {
   for (int l = 0; l < CSB_MAX_LAYERS; ++l) { F(h->w16[l]); F(h->wt16[l]); F(h->act[l]); F(h->zbuf[l]); F(h->ln_stats[l]); F(h->amask[l]); }
   F(h->xn); F(h->dz[0]); F(h->dz[1]); F(h->pred); F(h->dx_tmp);
   F(h->d_sub); F(h->d_div); F(h->d_out_scale); F(h->d_inv_out_scale); F(h->d_loss_w); F(h->d_out_mask);
-  F(h->loss_partials); F(h->d_loss);
+  F(h->loss_partials); F(h->d_loss); F(h->d_xform);
   for (int i = 0; i < 2; ++i) {
     F(h->x_stage[i]); F(h->y_stage[i]);
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
@@ -737,6 +738,30 @@ int csb_mlp_set_norm(csb_mlp* h, const float* inp_sub, const float* inp_div, con
   return CSB_OK;
 }
 
+int csb_mlp_set_input_transform(csb_mlp* h, const float* exp_lambda, const float* keep, const float* clip_lo, const float* clip_hi) {
+  CSB_REQUIRE(h, CSB_EINVAL, "null handle");
+  CSB_CUDA_CHECK(cudaDeviceSynchronize());
+  for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);    // cached graphs captured the old prologue
+  h->graphs.clear();
+  if (!exp_lambda && !keep && !clip_lo && !clip_hi) {
+    if (h->d_xform) { cudaFree(h->d_xform); h->d_xform = nullptr; }
+    return CSB_OK;
+  }
+  const int np = h->in_p;
+  std::vector<float> t((size_t)4 * np);
+  for (int c = 0; c < np; ++c) {
+    const bool v = c < h->in_dim;
+    t[c] = (v && exp_lambda) ? exp_lambda[c] : 0.f;
+    t[np + c] = v ? ((keep == nullptr || keep[c] != 0.f) ? 1.f : 0.f) : 0.f;
+    t[2 * np + c] = (v && clip_lo) ? clip_lo[c] : -INFINITY;
+    t[3 * np + c] = (v && clip_hi) ? clip_hi[c] : INFINITY;
+    CSB_REQUIRE(!(t[2 * np + c] > t[3 * np + c]), CSB_EINVAL, "clip_lo[%d] > clip_hi[%d]", c, c);
+  }
+  if (!h->d_xform) { CSB_ALLOC(h->d_xform, (size_t)4 * np * 4); }
+  CSB_CUDA_CHECK(cudaMemcpy(h->d_xform, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
+  return CSB_OK;
+}
+
 int csb_mlp_set_output_mask(csb_mlp* h, const float* mask_host) {
   CSB_REQUIRE(h, CSB_EINVAL, "null handle");
   CSB_CUDA_CHECK(cudaDeviceSynchronize());
@@ -762,6 +787,15 @@ int csb_mlp_grad_buffer(csb_mlp* h, float** ptr, size_t* n) {
 // forward pieces
 // ---------------------------------------------------------------------------------------------------------------
 static int run_normalize(csb_mlp* h, const float* x, int64_t B, int apply, cudaStream_t st) {
+  if (apply && h->d_xform != nullptr) {       // generalised prologue (exp transforms, pruned columns, clipping) of the online models
+    dim3 grid((unsigned)std::min<int64_t>(ceil_div(B, 2), (int64_t)h->sm_count * 8), (unsigned)ceil_div(h->in_p, 128));
+    simt::prepare_input_kernel<<<grid, 256, 0, st>>>(x, h->in_dim, h->d_sub, h->d_div, h->d_xform,
+                                                     h->bf16 ? nullptr : reinterpret_cast<float*>(h->xn),
+                                                     h->bf16 ? reinterpret_cast<__nv_bfloat16*>(h->xn) : nullptr, h->in_p, B, h->in_dim, h->in_p);
+    CSB_CUDA_CHECK(cudaGetLastError());
+    prof_mark(h, K_NORMALIZE, st);
+    return CSB_OK;
+  }
   if (h->bf16 && h->in_dim % 4 == 0 && 256 % (h->in_p / 4) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
     const int grid = grid_for(B * (h->in_p / 4), 256, h->sm_count, 4);
     CSB_CUDA_CHECK(launch_pdl(simt::normalize_bf16_vec4_kernel, dim3(grid), dim3(256), 0, st, x, h->d_sub, h->d_div, apply,
@@ -1160,6 +1194,8 @@ int csb_mlp_train_step(csb_mlp* h, const float* x, const float* y, int64_t B, fl
 int csb_mlp_backward(csb_mlp* h, const float* dy, float* dx, int64_t B, void* stream) {
   CSB_REQUIRE(h && dy, CSB_EINVAL, "null argument");
   CSB_REQUIRE(h->acts_B == B && B > 0, CSB_ESTATE, "csb_mlp_backward needs a preceding forward with CSB_FWD_KEEP_ACTIVATIONS on the same batch");
+  CSB_REQUIRE(!(dx != nullptr && h->acts_normalized && h->d_xform != nullptr), CSB_EUNSUPPORTED,
+              "dL/dx through the input transform of csb_mlp_set_input_transform is not available");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   { int rc0 = flush_pending(h, st); if (rc0) return rc0; }
   const int l = h->L - 1;

@@ -31,6 +31,34 @@ __global__ void normalize_kernel(const float* __restrict__ x, int ld_x, const fl
   }
 }
 
+// Generalised input prologue of the online models (online_testing/model_postprocessing/v2_nn_wrapper.ipynb cell 5 `preprocessing`,
+// online_testing/baseline_models/MLP_v2rh/training/climsim_datapip_h5.py:132-168), in the reference's order:
+//   x' = 1 - exp(-lambda_c x) where lambda_c != 0  ->  (x' - sub_c) / div_c  ->  nan, inf -> 0  ->  0 where keep_c == 0  ->  clamp to [lo_c, hi_c]
+// xform = [4][Fp] floats: lambda, keep, lo, hi.  One thread per column (its constants live in registers), blockIdx.y = 128-column
+// chunk, two rows per block pass; reads and writes are coalesced along the row.
+__global__ void __launch_bounds__(256)
+prepare_input_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ sub, const float* __restrict__ div,
+                     const float* __restrict__ xform, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, int ld_out,
+                     int64_t N, int F, int Fp) {
+  const int c = blockIdx.y * 128 + (threadIdx.x & 127);
+  if (c >= Fp) return;
+  const bool valid = c < F;
+  const float lam = valid ? xform[c] : 0.f, keep = valid ? xform[Fp + c] : 0.f, lo = xform[2 * Fp + c], hi = xform[3 * Fp + c];
+  const float s = valid ? sub[c] : 0.f, d = valid ? div[c] : 1.f;
+  for (int64_t r = (int64_t)blockIdx.x * 2 + (threadIdx.x >> 7); r < N; r += (int64_t)gridDim.x * 2) {
+    float v = 0.f;
+    if (valid && keep != 0.f) {
+      v = __ldcs(x + r * ld_x + c);
+      if (lam != 0.f) v = __fsub_rn(1.f, expf(-__fmul_rn(v, lam)));
+      v = __fdiv_rn(__fsub_rn(v, s), d);
+      if (isinf(v) || isnan(v)) v = 0.f;
+      v = fminf(fmaxf(v, lo), hi);
+    }
+    if (out_f32) out_f32[r * ld_out + c] = v;
+    if (out_bf16) out_bf16[r * ld_out + c] = __float2bfloat16_rn(v);
+  }
+}
+
 // Vectorised variant for F % 4 == 0 and bf16 output: one thread per 4 columns (128-bit load, 64-bit store).  A thread keeps its
 // column slot for the whole launch (the block is q = Fp / 4 slots wide, 256 / q rows tall; host guarantees 256 % q == 0), so the
 // normalisation constants are loaded once and no index division runs per element; four rows are in flight per thread.

@@ -159,6 +159,21 @@ class MLPEngine:
         _lib.check(self.lib.csb_mlp_set_norm(self._h, p(inp_sub, self.in_dim), p(inp_div, self.in_dim),
                                              p(out_scale, self.out_dim), p(loss_w, self.out_dim)), "csb_mlp_set_norm")
 
+    def set_input_transform(self, exp_lambda=None, keep=None, clip_lo=None, clip_hi=None) -> None:
+        """Generalised input prologue of the online models (``1 - exp(-lambda x)`` columns, pruned columns, clipping), applied by
+        every ``normalize_in=True`` call -- see ``csb_mlp_set_input_transform``.  All ``None`` restores the plain normalisation."""
+        hold = []
+
+        def p(a):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            assert a.size == self.in_dim, (a.size, self.in_dim)
+            hold.append(a)
+            return a.ctypes.data
+
+        _lib.check(self.lib.csb_mlp_set_input_transform(self._h, p(exp_lambda), p(keep), p(clip_lo), p(clip_hi)), "csb_mlp_set_input_transform")
+
     def set_output_mask(self, mask) -> None:
         """0/1 mask over the output columns (the online MLP's ``output_prune``); ``None`` removes it."""
         if mask is None:

@@ -124,6 +124,15 @@ int  csb_mlp_set_opt_state(csb_mlp* h, const float* m_host, const float* v_host,
  * out_scale[out_dim] (1), loss_w[out_dim] (1).  data_utils.save_norm (data_utils.py:954-988) produces the first three. */
 int  csb_mlp_set_norm(csb_mlp* h, const float* inp_sub, const float* inp_div, const float* out_scale, const float* loss_w);
 
+/* Generalised input prologue of the online models, applied by every call that passes CSB_FWD_NORMALIZE_IN, in the reference's
+ * order (online_testing/model_postprocessing/v2_nn_wrapper.ipynb cell 5 `preprocessing`;
+ * online_testing/baseline_models/MLP_v2rh/training/climsim_datapip_h5.py:132-168):
+ *   x' = 1 - exp(-exp_lambda[j] * x) where exp_lambda[j] != 0 (cloud liquid / ice);  (x' - inp_sub[j]) / inp_div[j];  nan, inf -> 0;
+ *   column j zeroed where keep[j] == 0 (pruned stratospheric inputs);  clamped to [clip_lo[j], clip_hi[j]] (relative humidity).
+ * Host arrays of in_dim floats; NULL = no transform / keep everything / no bound.  All NULL restores the plain normalisation.
+ * csb_mlp_backward cannot return dL/dx through a transform (CSB_EUNSUPPORTED). */
+int  csb_mlp_set_input_transform(csb_mlp* h, const float* exp_lambda, const float* keep, const float* clip_lo, const float* clip_hi);
+
 /* Per-output-column 0/1 mask applied to the predictions (and therefore to their gradients): the online MLP's `output_prune`
  * zeroing of the stratospheric levels (online_testing/baseline_models/MLP_v2rh/training/mlp.py:56-61).  NULL removes the mask. */
 int  csb_mlp_set_output_mask(csb_mlp* h, const float* mask_host);

@@ -12,6 +12,8 @@ reference's own hsr.py (tests/golden/hsr_small.npz; tests/test_oracle_pinning.py
 from __future__ import annotations
 
 import math
+
+import numpy as np
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -434,7 +436,8 @@ def keras_rmsprop_step(params: List[torch.Tensor], grads: List[torch.Tensor], v:
 class OnlineMLPRef(torch.nn.Module):
     """Restatement of the online MLP -- online_testing/baseline_models/MLP_v2rh/training/mlp.py:24-68 -- without the Modulus
     base class (not installable here): same ``state_dict`` keys (``linears.{i}.0.*``, ``final_linear.*``), same forward incl.
-    ``output_prune`` and the ReLU on the last eight outputs.  UNPINNED (the reference class needs nvidia-modulus to import)."""
+    ``output_prune`` and the ReLU on the last eight outputs.  PINNED: tests/golden/online_mlp.npz holds outputs of the reference
+    class itself (imported with a stand-in for the modulus base classes, tests/golden/make_golden.py::make_online)."""
 
     def __init__(self, in_dims, out_dims, hidden_dims, layers, dropout=0.0, output_prune=False, strato_lev_out=15):
         super().__init__()
@@ -455,3 +458,40 @@ class OnlineMLPRef(torch.nn.Module):
                 mask[start:start + self.strato_lev_out] = 0
             x = x * mask
         return torch.cat([x[:, :-8], torch.relu(x[:, -8:])], dim=1)
+
+
+class OnlineWrapperRef(torch.nn.Module):
+    """Restatement of ``NewModel`` -- online_testing/model_postprocessing/v2_nn_wrapper.ipynb, cell 5 -- the module exported for the
+    E3SM coupling: raw (B, 557) inputs -> physical-unit (B, 368) tendencies.  Same constructor arguments; the pruning ranges the
+    notebook hard-codes are the defaults here.  PINNED by tests/golden/online_mlp.npz (outputs of the notebook's own class).
+    The same pre-processing is what the training pipeline applies per sample
+    (online_testing/baseline_models/MLP_v2rh/training/climsim_datapip_h5.py:132-168)."""
+
+    def __init__(self, original_model, input_sub, input_div, out_scale, lbd_qc, lbd_qi, prune_qn_levels=15, rh_clip=(0.0, 1.2),
+                 out_prune=((60, 75), (120, 148), (180, 195), (240, 255), (300, 315))):
+        super().__init__()
+        self.original_model = original_model
+        f32 = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32)
+        self.input_sub, self.input_div, self.out_scale = f32(input_sub), f32(input_div), f32(out_scale)
+        self.lbd_qc, self.lbd_qi = f32(lbd_qc), f32(lbd_qi)
+        self.prune_qn_levels, self.rh_clip, self.out_prune = prune_qn_levels, rh_clip, out_prune
+
+    def preprocessing(self, x):
+        x = x.clone()
+        x[:, 120:180] = 1 - torch.exp(-x[:, 120:180] * self.lbd_qc)
+        x[:, 180:240] = 1 - torch.exp(-x[:, 180:240] * self.lbd_qi)
+        x = (x - self.input_sub) / self.input_div
+        x = torch.where(torch.isnan(x) | torch.isinf(x), torch.zeros((), dtype=x.dtype), x)
+        x[:, 120:120 + self.prune_qn_levels] = 0
+        x[:, 180:180 + self.prune_qn_levels] = 0
+        x[:, 60:120] = torch.clamp(x[:, 60:120], self.rh_clip[0], self.rh_clip[1])
+        return x
+
+    def postprocessing(self, y):
+        y = y.clone()
+        for a, b in self.out_prune:
+            y[:, a:b] = 0
+        return y / self.out_scale
+
+    def forward(self, x):
+        return self.postprocessing(self.original_model(self.preprocessing(x)))

@@ -3,7 +3,7 @@
 
     python tests/golden/make_golden.py            # needs /root/reference (read-only); writes *.npz next to itself
 
-Two fixtures are produced (both small enough to commit):
+The fixtures produced (all small enough to commit):
 
 * ``data_utils.npz`` -- outputs of the reference class ``climsim_utils.data_utils.data_utils`` (imported from
   /root/reference with the absent third-party modules xarray / matplotlib / tensorflow / netCDF4 / h5py replaced by
@@ -14,6 +14,9 @@ Two fixtures are produced (both small enough to commit):
 * ``hsr_small.npz`` -- the reference's ``baseline_models/HSR/training/hsr.py``: ``HeteroskedasticRegression``
   (hidden 32, 2 layers) forward, both losses, gradients, and the end state of its own ``trainer`` loop (3 epochs x 2
   batches: MSE phase then NLL phase, Adam with the per-group weight decay).
+
+* ``online_mlp.npz`` -- the reference's online MLP (``mlp.py``) and its E3SM inference wrapper (``v2_nn_wrapper.ipynb`` cell 5),
+  see ``make_online``.
 
 The GPU box has no /root/reference: tests only read the committed .npz files.
 """
@@ -195,6 +198,70 @@ def make_hsr():
     print("wrote hsr_final_cp_outputs.npz")
 
 
+def make_online():
+    """``online_mlp.npz``: the reference's online MLP (online_testing/baseline_models/MLP_v2rh/training/mlp.py, imported with a
+    stand-in for the absent nvidia-modulus base classes, which add nothing to the arithmetic) and its E3SM inference wrapper
+    ``NewModel`` (online_testing/model_postprocessing/v2_nn_wrapper.ipynb, cell 5, executed verbatim from the notebook) on a
+    seeded raw batch: network outputs, wrapper pre-processing, wrapper outputs."""
+    import dataclasses
+    import json
+    import torch
+
+    modulus = types.ModuleType("modulus")
+    modulus.__spec__ = importlib.machinery.ModuleSpec("modulus", None)
+
+    class _Module(torch.nn.Module):
+        def __init__(self, meta=None):
+            super().__init__()
+
+    @dataclasses.dataclass
+    class _Meta:
+        name: str = "model"
+
+    modulus.Module, modulus.ModelMetaData = _Module, _Meta
+    sys.modules["modulus"] = modulus
+    sys.path.insert(0, os.path.join(REF, "online_testing", "baseline_models", "MLP_v2rh", "training"))
+    import mlp as ref_mlp
+
+    nb = json.load(open(os.path.join(REF, "online_testing", "model_postprocessing", "v2_nn_wrapper.ipynb")))
+    src = "".join(nb["cells"][5]["source"])
+    assert "class NewModel" in src
+    ns = {"torch": torch, "nn": torch.nn, "np": np}
+    exec(src, ns)
+    NewModel = ns["NewModel"]
+
+    torch.manual_seed(11)
+    hidden = [48, 64, 40]
+    net = ref_mlp.MLP(557, 368, hidden, 3, dropout=0.0, output_prune=True, strato_lev_out=15).eval()
+    rng = np.random.default_rng(21)
+    B = 24
+    x_raw = rng.normal(0.0, 1.0, size=(B, 557)).astype(np.float32)
+    x_raw[:, 60:120] = rng.uniform(-0.2, 1.6, size=(B, 60))                   # relative humidity incl. values outside [0, 1.2]
+    x_raw[:, 120:240] = np.abs(rng.normal(0.0, 3e-5, size=(B, 120)))           # cloud liquid / ice mixing ratios
+    input_sub = rng.normal(0.0, 0.3, size=557).astype(np.float32)
+    input_div = rng.uniform(0.5, 2.0, size=557).astype(np.float32)
+    input_div[[7, 300]] = 0.0                                                  # max == min columns -> inf / nan -> 0
+    input_sub[7] = x_raw[0, 7]                                                 # 0 / 0 -> nan in row 0
+    out_scale = np.exp(rng.uniform(0.0, np.log(1e4), size=368)).astype(np.float32)
+    lbd_qc = np.exp(rng.uniform(np.log(1e4), np.log(1e6), size=60)).astype(np.float32)
+    lbd_qi = np.exp(rng.uniform(np.log(1e4), np.log(1e6), size=60)).astype(np.float32)
+    wrapper = NewModel(net, input_sub, input_div, out_scale, lbd_qc, lbd_qi).eval()
+    with torch.no_grad():
+        xt = torch.from_numpy(x_raw)
+        pre = wrapper.preprocessing(xt.clone())
+        y_net = net(pre.clone())
+        y_wrapped = wrapper(xt.clone())
+        y_plain = net(torch.from_numpy(x_raw[:, :].copy()) * 0.1)              # the bare network on already-normalised inputs
+    out = {"x_raw": x_raw, "input_sub": input_sub, "input_div": input_div, "out_scale": out_scale, "lbd_qc": lbd_qc, "lbd_qi": lbd_qi,
+           "pre": pre.numpy(), "y_net": y_net.numpy(), "y_wrapped": y_wrapped.numpy(), "y_plain": y_plain.numpy(),
+           "hidden": np.asarray(hidden, np.int64)}
+    for k, v in net.state_dict().items():
+        out["sd." + k] = v.numpy()
+    np.savez_compressed(os.path.join(HERE, "online_mlp.npz"), **out)
+    print("wrote online_mlp.npz with", len(out), "arrays; state_dict keys:", list(net.state_dict().keys()))
+
+
 if __name__ == "__main__":
     make_data_utils()
     make_hsr()
+    make_online()

@@ -171,6 +171,64 @@ def test_online_mlp_surface(dtype, tol, tol_g, loss):
     assert np.linalg.norm(got_g - want_g) / np.linalg.norm(want_g) <= tg
 
 
+@pytest.mark.parametrize("dtype,tol", [("fp32", 1e-5), ("bf16", 3e-2)])
+def test_online_inference_wrapper_matches_reference_golden(golden_dir, dtype, tol):
+    """OnlineInferenceWrapper (prologue kernel with the exp transforms / pruning / clipping -> GEMM chain -> output epilogue with mask
+    and 1/out_scale, one engine call) against the outputs of the REFERENCE's `NewModel` (v2_nn_wrapper.ipynb cell 5) wrapped around
+    the reference's own `mlp.MLP` (tests/golden/online_mlp.npz)."""
+    from climsim_b200.baseline_models import OnlineInferenceWrapper, OnlineMLP
+    g = np.load(os.path.join(golden_dir, "online_mlp.npz"))
+    hidden = [int(h) for h in g["hidden"]]
+    net = OnlineMLP(557, 368, hidden, 3, output_prune=True, strato_lev_out=15, dtype=dtype, max_batch=256)
+    net.load_reference_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")})
+    wrap = OnlineInferenceWrapper(net, g["input_sub"], g["input_div"], g["out_scale"], g["lbd_qc"], g["lbd_qi"])
+    x = torch.from_numpy(g["x_raw"]).cuda()
+    x_before = x.clone()
+    got = wrap(x).cpu().numpy()
+    assert torch.equal(x, x_before)                              # unlike the reference module, the caller's buffer is left alone
+    # compare in scaled space (the physical outputs span eight decades through 1 / out_scale)
+    got_s, want_s = got * g["out_scale"], g["y_wrapped"] * g["out_scale"]
+    assert np.abs(got_s - want_s).max() <= tol * np.abs(want_s).max()
+    for a, b in ((60, 75), (120, 148), (180, 195), (240, 255), (300, 315)):
+        assert (got[:, a:b] == 0).all()
+    assert (got[:, -8:] >= 0).all() and np.isfinite(got).all()
+    # the wrapped module gets its own configuration back: bare network on normalised inputs == the reference network
+    with torch.no_grad():
+        y_plain = net((torch.from_numpy(g["x_raw"]) * 0.1).cuda()).cpu().numpy()
+    assert np.abs(y_plain - g["y_plain"]).max() <= tol * np.abs(g["y_plain"]).max()
+    # and the wrapper can be used again afterwards
+    got2 = wrap(x).cpu().numpy()
+    np.testing.assert_array_equal(got, got2)
+
+
+def test_input_transform_prologue_bit_exact(golden_dir):
+    """The prologue kernel alone (fp32 engine, identity 557 -> 557 'network' is not available, so the first layer's input buffer is
+    read back through a one-layer engine with an identity weight): pre-processed inputs equal the reference's bit for bit except for
+    the exp() columns (libdevice expf against the host libm, <= 2 ulp of 1 - exp(.) before normalisation)."""
+    from climsim_b200 import MLPEngine
+    g = np.load(os.path.join(golden_dir, "online_mlp.npz"))
+    eng = MLPEngine(557, [(557, "none", 0.0)], head_relu_from=-1, dtype="fp32", max_batch=64)
+    flat = np.concatenate([np.eye(557, dtype=np.float32).reshape(-1), np.zeros(557, np.float32)])
+    eng.set_params_flat(flat)
+    lam = np.zeros(557, np.float32); lam[120:180] = g["lbd_qc"]; lam[180:240] = g["lbd_qi"]
+    keep = np.ones(557, np.float32); keep[120:135] = 0; keep[180:195] = 0
+    lo, hi = np.full(557, -np.inf, np.float32), np.full(557, np.inf, np.float32)
+    lo[60:120], hi[60:120] = 0.0, 1.2
+    eng.set_norm(inp_sub=g["input_sub"], inp_div=g["input_div"])
+    eng.set_input_transform(lam, keep, lo, hi)
+    got = eng.forward(torch.from_numpy(g["x_raw"]).cuda(), normalize_in=True).cpu().numpy()
+    want = g["pre"]
+    plain = np.ones(557, bool); plain[120:240] = False
+    np.testing.assert_array_equal(got[:, plain], want[:, plain])
+    np.testing.assert_allclose(got[:, ~plain], want[:, ~plain], rtol=0, atol=4e-7 / np.abs(g["input_div"][~plain]).min())
+    eng.set_input_transform()                                     # back to the plain normalisation
+    got0 = eng.forward(torch.from_numpy(g["x_raw"]).cuda(), normalize_in=True).cpu().numpy()
+    with np.errstate(divide="ignore", invalid="ignore"):
+        z = (g["x_raw"] - g["input_sub"]) / g["input_div"]
+    z[~np.isfinite(z)] = 0
+    np.testing.assert_array_equal(got0, z.astype(np.float32))
+
+
 def test_fused_gpu_metrics_match_reference_golden(golden_dir):
     """csb_eval_metrics (weighting + MAE/RMSE/R2/bias + grid mean in one pass) against the per-index metrics the REFERENCE's
     own data_utils produced (tests/golden/data_utils.npz)."""

@@ -163,6 +163,39 @@ def test_hsr_shipped_checkpoint_outputs(golden_dir):
     np.testing.assert_allclose(lp.numpy(), g["logprec"], rtol=1e-5, atol=1e-6)
 
 
+def _online_ref(g):
+    net = M.OnlineMLPRef(557, 368, [int(h) for h in g["hidden"]], 3, dropout=0.0, output_prune=True, strato_lev_out=15)
+    net.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}, strict=True)
+    return net.eval()
+
+
+def test_online_mlp_matches_reference_class(golden_dir):
+    """oracle OnlineMLPRef == the reference's own mlp.MLP (output_prune, last-eight ReLU) on the golden batch."""
+    g = np.load(os.path.join(golden_dir, "online_mlp.npz"))
+    net = _online_ref(g)
+    with torch.no_grad():
+        y_plain = net(torch.from_numpy(g["x_raw"]) * 0.1)
+        y_net = net(torch.from_numpy(g["pre"]))
+    np.testing.assert_allclose(y_plain.numpy(), g["y_plain"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(y_net.numpy(), g["y_net"], rtol=1e-6, atol=1e-6)
+    assert (y_net.numpy()[:, 60:75] == 0).all() and (y_net.numpy()[:, -8:] >= 0).all()
+
+
+def test_online_inference_wrapper_matches_notebook_class(golden_dir):
+    """oracle OnlineWrapperRef == `NewModel` of v2_nn_wrapper.ipynb cell 5 (executed from the notebook by make_golden.py):
+    exp transforms, normalisation with 0-width columns, nan / inf -> 0, pruning, RH clipping, output pruning, / out_scale."""
+    g = np.load(os.path.join(golden_dir, "online_mlp.npz"))
+    w = M.OnlineWrapperRef(_online_ref(g), g["input_sub"], g["input_div"], g["out_scale"], g["lbd_qc"], g["lbd_qi"])
+    x = torch.from_numpy(g["x_raw"])
+    with torch.no_grad():
+        pre = w.preprocessing(x)
+        y = w(x)
+    np.testing.assert_array_equal(pre.numpy(), g["pre"])                      # element-wise fp32 arithmetic: bit-exact
+    np.testing.assert_allclose(y.numpy(), g["y_wrapped"], rtol=1e-6, atol=1e-9)
+    assert np.isfinite(g["pre"]).all() and (g["pre"][:, [7, 300]] == 0).all()   # the max == min columns came out as 0
+    assert g["pre"][:, 60:120].min() >= 0 and g["pre"][:, 60:120].max() <= np.float32(1.2)
+
+
 # ---------------------------------------------------------------- internal consistency of the unpinned restatements
 def test_keras_adam_first_step_is_sign_step():
     p = [torch.tensor([1.0, -2.0, 3.0])]
