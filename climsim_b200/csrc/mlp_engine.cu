@@ -521,7 +521,7 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
     li.b_splits = h->bf16 ? li.max_w_splits * nt_m_tiles(li.Kp, li.nt_cg) : 32;
     li.ws_w_off = ws_off; ws_off += (size_t)li.max_w_splits * li.Kp * li.Np;
     li.ws_b_off = ws_off; ws_off += (size_t)li.b_splits * li.Np;
-    li.ws_g_off = ws_off; if (li.ln) ws_off += (size_t)32 * 2 * li.Np;
+    li.ws_g_off = ws_off; if (li.ln) ws_off += (size_t)std::max(32, 2 * sm) * 2 * li.Np;      // one partial pair per block of ln_bwd_bf16_kernel
     h->max_np = std::max(h->max_np, li.Np);
     k = li.N;
   }
@@ -839,7 +839,10 @@ static int run_hidden_forward(csb_mlp* h, int64_t B, cudaStream_t st) {
     if (li.ln) {
       const int grid = (int)std::min<int64_t>(ceil_div(B, 8), (int64_t)h->sm_count * 8);
       const float* gamma = h->params + li.g_off;
-      if (h->bf16)
+      if (h->bf16 && li.Np <= 256 * simt::LN_MAXP)
+        simt::ln_fwd_bf16_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(h->zbuf[l]), reinterpret_cast<__nv_bfloat16*>(h->act[l]),
+                                                       li.Np, gamma, gamma + li.Np, h->ln_stats[l], B, li.N, li.Np, li.act, li.alpha, 1e-5f);
+      else if (h->bf16)
         simt::ln_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(h->zbuf[l]),
                                                                  reinterpret_cast<__nv_bfloat16*>(h->act[l]), li.Np, gamma, gamma + li.Np,
                                                                  h->ln_stats[l], B, li.N, li.Np, li.act, li.alpha, 1e-5f);
@@ -970,11 +973,22 @@ static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st,
     const LayerInfo& li = h->layer[l];
     if (li.ln) {
       // the buffer holds du_l = dA_l * act'(a_l): LayerNorm parameter gradients, then du -> dz in place
-      const int S = (int)std::max<int64_t>(1, std::min<int64_t>(32, ceil_div(B, 256)));
+      int S = (int)std::max<int64_t>(1, std::min<int64_t>(32, ceil_div(B, 256)));
       dim3 gridp((unsigned)(li.Np / 64), (unsigned)S);
       const int gridb = (int)std::min<int64_t>(ceil_div(B, 8), (int64_t)h->sm_count * 8);
       const float* gamma = h->params + li.g_off;
-      if (h->bf16) {
+      if (h->bf16 && li.Np <= 256 * simt::LN_MAXP) {
+        // one fused kernel: du -> dz and the (dgamma, dbeta) partials of each block
+        S = (int)std::max<int64_t>(1, std::min<int64_t>(2 * h->sm_count, ceil_div(B, 8)));
+        const size_t smem = (size_t)8 * li.Np * 4;
+        static bool attr_set = false;
+        if (!attr_set) {
+          CSB_CUDA_CHECK(cudaFuncSetAttribute(simt::ln_bwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 256 * simt::LN_MAXP * 4));
+          attr_set = true;
+        }
+        simt::ln_bwd_bf16_kernel<<<S, 256, smem, st>>>(dz16(h, l), reinterpret_cast<const __nv_bfloat16*>(h->zbuf[l]), li.Np, gamma, h->ln_stats[l],
+                                                       B, li.N, li.Np, h->ws + li.ws_g_off);
+      } else if (h->bf16) {
         simt::ln_param_grad_kernel<__nv_bfloat16><<<gridp, 256, 0, st>>>(dz16(h, l), reinterpret_cast<const __nv_bfloat16*>(h->zbuf[l]), li.Np,
                                                                         h->ln_stats[l], B, h->ws + li.ws_g_off, (size_t)2 * li.Np, li.Np);
         simt::ln_bwd_kernel<__nv_bfloat16><<<gridb, 256, 0, st>>>(dz16(h, l), reinterpret_cast<const __nv_bfloat16*>(h->zbuf[l]), li.Np, gamma,

@@ -384,6 +384,144 @@ ln_bwd_kernel(T* __restrict__ du_dz, const T* __restrict__ z, int ld, const floa
   }
 }
 
+// ---- bf16 LayerNorm, rows of at most 256 * MAXP columns: a warp owns a row and keeps it in registers (lane -> eight consecutive
+// columns per 256-column pass, 128-bit loads and stores), so z is read once; the backward kernel fuses the parameter gradients
+// (per-lane column sums carried across the warp's rows, reduced over the block's warps through shared memory in a fixed order)
+// with du -> dz.  Statistics run over the N valid columns; padding columns [N, Np) are written as zeros.
+constexpr int LN_MAXP = 4;       // up to 1024 columns (the HSR networks: 1024)
+
+__device__ __forceinline__ void ln_load8(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 w = *reinterpret_cast<const uint4*>(p);
+  v[0] = bf16_lo(w.x); v[1] = bf16_hi(w.x); v[2] = bf16_lo(w.y); v[3] = bf16_hi(w.y);
+  v[4] = bf16_lo(w.z); v[5] = bf16_hi(w.z); v[6] = bf16_lo(w.w); v[7] = bf16_hi(w.w);
+}
+__device__ __forceinline__ void ln_store8(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 w;
+  w.x = pack_bf16x2(v[0], v[1]); w.y = pack_bf16x2(v[2], v[3]); w.z = pack_bf16x2(v[4], v[5]); w.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = w;
+}
+__device__ __forceinline__ void ln_load8f(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+__global__ void __launch_bounds__(256)
+ln_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ z, __nv_bfloat16* __restrict__ a, int ld, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, float* __restrict__ stats, int64_t M, int N, int Np, int act, float alpha, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float inv_n = 1.f / (float)N;
+  for (int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5); r < M; r += warps) {
+    float v[LN_MAXP][8];
+    float s = 0.f;
+#pragma unroll
+    for (int p = 0; p < LN_MAXP; ++p) {
+      const int c = p * 256 + lane * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[p][j] = 0.f;
+      if (c < Np) ln_load8(z + r * ld + c, v[p]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += (c + j < N) ? v[p][j] : 0.f;
+    }
+    const float mean = warp_sum(s) * inv_n;
+    float q = 0.f;
+#pragma unroll
+    for (int p = 0; p < LN_MAXP; ++p) {
+      const int c = p * 256 + lane * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[p][j] - mean; q += (c + j < N) ? d * d : 0.f; }
+    }
+    const float rstd = rsqrtf(warp_sum(q) * inv_n + eps);
+    if (lane == 0) { stats[2 * r] = mean; stats[2 * r + 1] = rstd; }
+#pragma unroll
+    for (int p = 0; p < LN_MAXP; ++p) {
+      const int c = p * 256 + lane * 8;
+      if (c < Np) {
+        float g[8], b[8], o[8];
+        ln_load8f(gamma + c, g);
+        ln_load8f(beta + c, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (c + j < N) ? act_fwd(act, alpha, (v[p][j] - mean) * rstd * g[j] + b[j]) : 0.f;
+        ln_store8(a + r * ld + c, o);
+      }
+    }
+  }
+}
+
+// du -> dz in place (g = du * gamma; dz = rstd * (g - mean(g) - xhat * mean(g * xhat))) fused with the parameter gradients
+// dgamma = sum_rows du * xhat, dbeta = sum_rows du: one partial pair per block at partials + blockIdx.x * 2 * Np
+__global__ void __launch_bounds__(256)
+ln_bwd_bf16_kernel(__nv_bfloat16* __restrict__ du_dz, const __nv_bfloat16* __restrict__ z, int ld, const float* __restrict__ gamma,
+                   const float* __restrict__ stats, int64_t M, int N, int Np, float* __restrict__ partials) {
+  extern __shared__ float red[];                     // [8 warps][Np]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t warps = (int64_t)gridDim.x * 8;
+  const float inv_n = 1.f / (float)N;
+  float ag[LN_MAXP][8], ab[LN_MAXP][8], gm[LN_MAXP][8];
+#pragma unroll
+  for (int p = 0; p < LN_MAXP; ++p) {
+    const int c = p * 256 + lane * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ag[p][j] = 0.f; ab[p][j] = 0.f; gm[p][j] = 0.f; }
+    if (c < Np) ln_load8f(gamma + c, gm[p]);
+  }
+  for (int64_t r = blockIdx.x * (int64_t)8 + warp; r < M; r += warps) {
+    const float mean = stats[2 * r], rstd = stats[2 * r + 1];
+    float du[LN_MAXP][8], xh[LN_MAXP][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int p = 0; p < LN_MAXP; ++p) {
+      const int c = p * 256 + lane * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { du[p][j] = 0.f; xh[p][j] = 0.f; }
+      if (c < Np) { ln_load8(du_dz + r * ld + c, du[p]); ln_load8(z + r * ld + c, xh[p]); }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool ok = c + j < N;
+        xh[p][j] = ok ? (xh[p][j] - mean) * rstd : 0.f;
+        du[p][j] = ok ? du[p][j] : 0.f;
+        const float g = du[p][j] * gm[p][j];
+        s1 += g;
+        s2 += g * xh[p][j];
+        ag[p][j] += du[p][j] * xh[p][j];
+        ab[p][j] += du[p][j];
+      }
+    }
+    s1 = warp_sum(s1) * inv_n;
+    s2 = warp_sum(s2) * inv_n;
+#pragma unroll
+    for (int p = 0; p < LN_MAXP; ++p) {
+      const int c = p * 256 + lane * 8;
+      if (c < Np) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (c + j < N) ? rstd * (du[p][j] * gm[p][j] - s1 - xh[p][j] * s2) : 0.f;
+        ln_store8(du_dz + r * ld + c, o);
+      }
+    }
+  }
+  // block reduction over the eight warps, warp 0 first (fixed order), once for dgamma and once for dbeta
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < LN_MAXP; ++p) {
+      const int c = p * 256 + lane * 8;
+      if (c < Np) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[warp * Np + c + j] = which == 0 ? ag[p][j] : ab[p][j];
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < Np; c += 256) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[w * Np + c];
+      partials[(size_t)blockIdx.x * 2 * Np + which * Np + c] = t;
+    }
+  }
+}
+
 // dgamma = sum_rows du*xhat, dbeta = sum_rows du: two-stage column sums; partials [S][2][Np] at out + s*stride
 template <typename T>
 __global__ void __launch_bounds__(256)

@@ -132,6 +132,42 @@ def test_hsr_layernorm_model_against_reference_golden(golden_dir, dtype, tol_out
                 assert err <= tol_g, (mode, key, err)
 
 
+@pytest.mark.parametrize("hidden,layers,B", [(1024, 2, 333), (200, 1, 1000), (512, 3, 129)])
+def test_layernorm_mlp_bf16_wide_rows(hidden, layers, B):
+    """bf16 LayerNorm kernels (a row per warp held in registers, fused du -> dz + parameter gradients) at the widths the small golden
+    model does not reach: 1024 (four 256-column passes, the shipped HSR width), 200 (statistics over N = 200 of 256 padded columns),
+    512; forward and every gradient tensor against the fp32 torch restatement of hsr.MLP."""
+    from climsim_b200.baseline_models import HSRMLP
+    from oracle import models as M
+    torch.manual_seed(3)
+    ref = M.HSRMLPRef(124, 128, hidden, layers)
+    with torch.no_grad():
+        for i in range(layers):                                   # non-trivial gamma / beta
+            ln = getattr(ref, f"linear{i}")[1]
+            ln.weight.uniform_(0.5, 1.5); ln.bias.uniform_(-0.3, 0.3)
+    net = HSRMLP(124, 128, hidden_dims=hidden, layers=layers, dtype="bf16", max_batch=1024)
+    net.load_reference_state_dict(ref.state_dict())
+    g = torch.Generator().manual_seed(4)
+    x, y = 0.5 * torch.randn(B, 124, generator=g), 0.3 * torch.randn(B, 128, generator=g)
+    want = ref(x)
+    ((want - y) ** 2).mean().backward()
+    got = net(x.cuda())
+    ((got - y.cuda()) ** 2).mean().backward()
+    assert (got.detach().cpu() - want.detach()).abs().max().item() <= 5e-2 * want.abs().max().item()
+    want_g = []
+    for i in range(layers):
+        seq = getattr(ref, f"linear{i}")
+        want_g += [seq[0].weight.grad.t().reshape(-1), seq[0].bias.grad, seq[1].weight.grad, seq[1].bias.grad]
+    want_g += [ref.final_linear.weight.grad.t().reshape(-1), ref.final_linear.bias.grad]
+    off, got_g = 0, net.flat.grad.cpu()
+    for i, w in enumerate(want_g):
+        part = got_g[off:off + w.numel()]
+        off += w.numel()
+        err = (part - w).norm().item() / max(w.norm().item(), 1e-12)
+        assert err <= 1e-1, (i, err)
+    assert off == got_g.numel()
+
+
 @pytest.mark.parametrize("dtype,tol,tol_g", [("fp32", 2e-5, 1e-4), ("bf16", 3e-2, 1e-1)])
 @pytest.mark.parametrize("loss", ["huber", "mse", "mae"])
 def test_online_mlp_surface(dtype, tol, tol_g, loss):
