@@ -1452,6 +1452,43 @@ static unsigned long long* g_test_stats = nullptr;
 void csb_test_set_debug(int flags) { g_test_dbg = flags; }
 void csb_test_set_stats(void* dev_u64x4_per_cta) { g_test_stats = reinterpret_cast<unsigned long long*>(dev_u64x4_per_cta); }
 
+static int* g_gather_bad = nullptr;                       // device flag: a gather saw an index outside [0, src_rows)
+
+int csb_gather_rows(const float* src, const int64_t* idx, float* dst, int64_t n_rows, int row_len, int64_t src_rows, void* stream) {
+  CSB_REQUIRE(src && idx && dst, CSB_EINVAL, "null argument");
+  CSB_REQUIRE(n_rows >= 0 && row_len > 0 && src_rows > 0, CSB_EINVAL, "bad shape (n_rows %lld, row_len %d, src_rows %lld)", (long long)n_rows,
+              row_len, (long long)src_rows);
+  if (n_rows == 0) return CSB_OK;
+  static int sm = 0;
+  int rc;
+  if (sm == 0 && (rc = csb_device_info(&sm, nullptr, nullptr, nullptr))) return rc;
+  if (g_gather_bad == nullptr) {
+    CSB_ALLOC(g_gather_bad, sizeof(int));
+    CSB_CUDA_CHECK(cudaMemset(g_gather_bad, 0, sizeof(int)));
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool vec = row_len % 4 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+  const dim3 block(32, 8), grid((unsigned)std::min<int64_t>(ceil_div(n_rows, 8), (int64_t)sm * 16));
+  if (vec) simt::gather_rows_kernel<true><<<grid, block, 0, st>>>(src, idx, dst, n_rows, row_len, src_rows, g_gather_bad);
+  else simt::gather_rows_kernel<false><<<grid, block, 0, st>>>(src, idx, dst, n_rows, row_len, src_rows, g_gather_bad);
+  CSB_CUDA_CHECK(cudaGetLastError());
+  return CSB_OK;
+}
+
+int csb_gather_rows_check(void* stream) {
+  if (g_gather_bad == nullptr) return CSB_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int bad = 0;
+  CSB_CUDA_CHECK(cudaMemcpyAsync(&bad, g_gather_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CSB_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (bad) {
+    CSB_CUDA_CHECK(cudaMemsetAsync(g_gather_bad, 0, sizeof(int), st));
+    set_last_error("csb_gather_rows: an index outside [0, src_rows) was skipped (its destination row is unwritten)");
+    return CSB_EINVAL;
+  }
+  return CSB_OK;
+}
+
 int csb_test_linear_fwd(const uint16_t* A, const uint16_t* Wt, const float* bias, uint16_t* out, int M, int N, int K, int act,
                         float alpha, int pairs, void* stream) {
   CSB_REQUIRE(A && Wt && bias && out, CSB_EINVAL, "null argument");

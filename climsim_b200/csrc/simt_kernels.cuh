@@ -31,6 +31,29 @@ __global__ void normalize_kernel(const float* __restrict__ x, int ld_x, const fl
   }
 }
 
+// Row gather dst[i, :] = src[idx[i], :]: the shuffle stage of the input pipeline on the device (the reference shuffles samples on the
+// host: tf.data `unbatch().shuffle(11520).batch(B)`, hpo_baseline_v1.py:140-143; DistributedSampler(shuffle=True),
+// train_mlp_h5loader.py:126-134).  blockDim = (32, 8): a warp per row; VEC: rows are multiples of four floats and 16-byte aligned.
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx, float* __restrict__ dst, int64_t n_rows, int row_len,
+                   int64_t src_rows, int* __restrict__ bad) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; i < n_rows; i += (int64_t)gridDim.x * blockDim.y) {
+    const int64_t r = idx[i];
+    if (r < 0 || r >= src_rows) {                      // never dereference an index outside the source; reported to the caller
+      if (threadIdx.x == 0) atomicExch(bad, 1);
+      continue;
+    }
+    if constexpr (VEC) {
+      const float4* s = reinterpret_cast<const float4*>(src + r * row_len);
+      float4* d = reinterpret_cast<float4*>(dst + i * row_len);
+      for (int c = threadIdx.x; c < row_len / 4; c += 32) d[c] = __ldcs(s + c);
+    } else {
+      for (int c = threadIdx.x; c < row_len; c += 32) dst[i * row_len + c] = __ldcs(src + r * row_len + c);
+    }
+  }
+}
+
 // Generalised input prologue of the online models (online_testing/model_postprocessing/v2_nn_wrapper.ipynb cell 5 `preprocessing`,
 // online_testing/baseline_models/MLP_v2rh/training/climsim_datapip_h5.py:132-168), in the reference's order:
 //   x' = 1 - exp(-lambda_c x) where lambda_c != 0  ->  (x' - sub_c) / div_c  ->  nan, inf -> 0  ->  0 where keep_c == 0  ->  clamp to [lo_c, hi_c]

@@ -252,6 +252,15 @@ int  csb_eval_metrics(const float* pred, const float* target, const float* x_nor
                       const double* hybi, double p0, const double* area_wgt, const double* out_scale, double ps_mean, double ps_max,
                       double ps_min, int normalize, double* out, double* scratch, void* stream);
 
+/* ---- input pipeline ------------------------------------------------------------------------------------------------------------- */
+/* dst[i, :] = src[idx[i], :] for i < n_rows (fp32 rows of row_len floats, device pointers, idx int64 on the device): the sample
+ * shuffle of the reference's input pipelines -- tf.data `unbatch().shuffle(384*30).batch(B)` (hpo_baseline_v1.py:140-143,
+ * step2_retrain.py:266-271) and DistributedSampler(shuffle=True) (online_testing/.../train_mlp_h5loader.py:126-134) -- done on the
+ * device over a window of columns already resident in HBM.  Never synchronises; an index outside [0, src_rows) is skipped and
+ * reported by the next csb_gather_rows_check (CSB_EINVAL), which synchronises the stream. */
+int  csb_gather_rows(const float* src, const int64_t* idx, float* dst, int64_t n_rows, int row_len, int64_t src_rows, void* stream);
+int  csb_gather_rows_check(void* stream);
+
 /* ---- kernel self-test hooks (used by tests/test_gemm_gpu.py; device pointers) ----------------------------- */
 /* C[M,N] (fp32) = A[M,K] * Bt[N,K]^T on the tcgen05 path (both operands K-major bf16, raw uint16 payloads). */
 int  csb_test_gemm_tn(const uint16_t* A, const uint16_t* Bt, float* C, int M, int N, int K, int block_n, void* stream);
