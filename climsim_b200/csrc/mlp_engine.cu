@@ -1275,6 +1275,24 @@ int csb_mlp_apply_opt(csb_mlp* h, int rule, float lr, float beta1, float beta2, 
     h->pending = false;
     return CSB_OK;
   }
+  if (fused_opt_supported(h)) {
+    // gradients already reduced (data-parallel path: partial reduction -> all-reduce -> here): the same fused kernel with the
+    // gradient buffer itself as the single "partial" updates the weights and writes the bf16 copies in one launch
+    simt::FusedOptTable tab;
+    tab.n = h->L;
+    tab.params = h->params; tab.grads = h->grads; tab.m = h->m; tab.v = h->v;
+    tab.loss_partials = nullptr; tab.n_loss = 0; tab.loss_out = nullptr;
+    int max_items = 1;
+    for (int l = 0; l < h->L; ++l) {
+      const LayerInfo& li = h->layer[l];
+      tab.l[l] = {li.Kp, li.Np, li.w_off, li.b_off, h->w16[l], h->wt16[l], h->grads + li.w_off, 1, h->grads + li.b_off, 1};
+      max_items = std::max(max_items, (li.Kp / 32) * (li.Np / 64) + (int)ceil_div(li.Np / 4, 256));
+    }
+    dim3 grid((unsigned)max_items, (unsigned)(h->L + 1));
+    CSB_CUDA_CHECK(launch_pdl(simt::opt_fused_kernel, grid, dim3(256), 0, st, tab, o));
+    prof_mark(h, K_OPT, st);
+    return CSB_OK;
+  }
   const int grid = grid_for((int64_t)h->P_pad / 4, 256, h->sm_count);
   CSB_CUDA_CHECK(launch_pdl(simt::opt_kernel, dim3(grid), dim3(256), 0, st, h->params, h->grads, h->m, h->v, (int64_t)h->P_pad, o));
   prof_mark(h, K_OPT, st);
