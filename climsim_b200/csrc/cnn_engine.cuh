@@ -109,6 +109,15 @@ static int cnn_build_maps(csb_cnn* h, int64_t B) {
   return CSB_OK;
 }
 
+// Output width the tensor cores compute for a layer of `c` real channels stored with pitch `cp` (a multiple of 64): the last n-block
+// stops at the next multiple of 32 (406 -> 416 instead of 448: 7 % fewer MMA columns).  The columns in between are never written
+// and stay what the allocation made them, zero, which is what the next layer's contraction over the full pitch needs.  Only when the
+// trimmed width still fills a 256-wide first block, so that the B tensor-map box (encoded for the padded width) is unchanged.
+static inline int cnn_mma_width(int c, int cp) {
+  const int w = (int)round_up(c, 32);
+  return (cp > 256 && w >= 256 && w < cp) ? w : cp;
+}
+
 // one convolution-as-GEMM launch.  `dgrad` selects the flipped/transposed weights (output width = Cinp).
 //   kind 0: out = act(conv + bias)   kind 1: out = conv + bias + saved   kind 2: out = conv * act'(saved)
 static int cnn_conv(csb_cnn* h, const ConvLayerInfo& li, bool dgrad, const CnnBuf& in, CnnBuf& out, int kind, const CnnBuf* saved, int act,
@@ -117,7 +126,8 @@ static int cnn_conv(csb_cnn* h, const ConvLayerInfo& li, bool dgrad, const CnnBu
   int rc = CSB_OK;
   if (h->bf16) {
     tc::GemmParams p = {};
-    p.M = M; p.N = N; p.K = li.taps * Kt; p.kb_per_tap = Kt / 64; p.tap_center = (li.taps - 1) / 2; p.halo_period = h->P;
+    p.M = M; p.N = cnn_mma_width(dgrad ? li.Cin : li.Cout, N); p.K = li.taps * Kt; p.kb_per_tap = Kt / 64; p.tap_center = (li.taps - 1) / 2;
+    p.halo_period = h->P;
     p.act = act; p.head_relu_from = -1; p.bias = bias;
     const CUtensorMap& w = dgrad ? li.tm_wd : li.tm_wt;
     p.out = out.ptr; p.ld_out = out.Cp;
@@ -182,7 +192,7 @@ static int cnn_wgrad(csb_cnn* h, const ConvLayerInfo& li, const CnnBuf& in, cons
   int splits = std::max(1, std::min(li.max_splits, num_rb));
   for (int t = 0; t < li.taps; ++t) {
     tc::NtParams p = {};
-    p.M = li.Cinp; p.N = li.Coutp; p.R = (int)R;
+    p.M = li.Cinp; p.N = cnn_mma_width(li.Cout, li.Coutp); p.R = (int)R;
     p.rb_per_split = (int)ceil_div(num_rb, splits);
     const int eff = (int)ceil_div(num_rb, p.rb_per_split);
     p.out = h->ws + li.ws_w_off + (size_t)t * tap_elems; p.ld_out = li.Coutp; p.split_stride = (size_t)li.taps * tap_elems;
