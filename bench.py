@@ -145,6 +145,15 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=4096, help="columns per CPU-baseline step")
     args = ap.parse_args()
     assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+    # stdout must carry exactly ONE line, the JSON: libraries (NCCL prints its version banner with printf) get stderr as their
+    # file descriptor 1 for the whole run, and emit() writes the line to the real stdout at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: dict) -> None:
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -167,14 +176,12 @@ def main():
                 "cpu_baseline": {"value": cps, "unit": "columns/s", "cores": threads, "kind": "port",
                                  "sample": f"{args.steps} steps of {args.cpu_sample} columns (PyTorch-CPU fp32 oracle of the Keras MLP_v1 train step)"},
                 "e2e": {"value": cps, "unit": "columns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
 
     assert torch.cuda.is_available(), "bench.py needs a GPU for --impl ours (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # stdout carries exactly one JSON line: anything NCCL wants to say (its version banner under NCCL_DEBUG=VERSION) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from climsim_b200 import MLPEngine
@@ -301,7 +308,7 @@ def main():
                 "kernels_note": f"per-kind times from a second pass of {prof_steps} steps with per-launch CUDA events (eager launches, "
                                 f"{prof_ms_total / prof_steps:.4f} ms/step); the timed region replays the step as a CUDA graph",
                 "cpu_baseline": cpu_baseline}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
 
