@@ -100,6 +100,7 @@ SIGNATURES = {
     "csb_test_linear_fwd": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _VP]),
     "csb_test_set_debug": (None, [C.c_int]),
     "csb_test_set_stats": (None, [_VP]),
+    "csb_eval_crps": (C.c_int, [_VP, _VP, C.c_int, C.c_int64, C.c_int, C.c_int, _VP, _VP, _VP]),
     "csb_gather_rows": (C.c_int, [_VP, _VP, _VP, C.c_int64, C.c_int, C.c_int64, _VP]),
     "csb_gather_rows_check": (C.c_int, [_VP]),
     "csb_test_gemm_nt": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP]),

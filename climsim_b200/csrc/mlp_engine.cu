@@ -1470,6 +1470,21 @@ static unsigned long long* g_test_stats = nullptr;
 void csb_test_set_debug(int flags) { g_test_dbg = flags; }
 void csb_test_set_stats(void* dev_u64x4_per_cta) { g_test_stats = reinterpret_cast<unsigned long long*>(dev_u64x4_per_cta); }
 
+int csb_eval_crps(const void* samples, const void* target, int is_f64, int64_t n_tc, int L, int S, double* out, double* scratch, void* stream) {
+  CSB_REQUIRE(samples && target && out && scratch, CSB_EINVAL, "null argument");
+  CSB_REQUIRE(n_tc > 0 && L > 0 && S >= 2 && S <= 32, CSB_EINVAL, "need n_tc > 0, L > 0 and 2 <= S <= 32 ensemble members (got %lld, %d, %d)",
+              (long long)n_tc, L, S);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int NB = (int)std::max<int64_t>(1, std::min<int64_t>(CSB_CRPS_BLOCKS, ceil_div(n_tc, 8)));
+  dim3 grid((unsigned)L, (unsigned)NB);
+  if (is_f64) simt::crps_kernel<double><<<grid, 256, 0, st>>>(reinterpret_cast<const double*>(samples), reinterpret_cast<const double*>(target), n_tc, L, S, scratch);
+  else simt::crps_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(samples), reinterpret_cast<const float*>(target), n_tc, L, S, scratch);
+  CSB_CUDA_CHECK(cudaGetLastError());
+  simt::crps_finalize_kernel<<<(unsigned)ceil_div(L, 64), 64, 0, st>>>(scratch, NB, n_tc, L, out);
+  CSB_CUDA_CHECK(cudaGetLastError());
+  return CSB_OK;
+}
+
 static int* g_gather_bad = nullptr;                       // device flag: a gather saw an index outside [0, src_rows)
 
 int csb_gather_rows(const float* src, const int64_t* idx, float* dst, int64_t n_rows, int row_len, int64_t src_rows, void* stream) {

@@ -31,6 +31,57 @@ __global__ void normalize_kernel(const float* __restrict__ x, int ld_x, const fl
   }
 }
 
+// CRPS by the sorted-sample identity (climsim_utils/data_utils.py:1499-1524), averaged over time and grid:
+//   out[l] = mean over (t, c) of [ mean_s |p_s - y|  -  sum_i (p_(i+1) - p_(i)) * (i + 1)(S - 1 - i) / (S (S - 1)) ]
+// samples [n_tc, L, S] (S <= 32 ensemble members, contiguous), target [n_tc, L].  A warp owns one (t, c, l) element: lane s holds
+// member s, the 32 lanes are sorted with a bitonic network of shuffles, the spread is one neighbour difference per lane.
+// grid = (L, NB): block b of level l takes elements b*8 + warp, stepping NB*8; fp64 accumulation, fixed-order block reduction into
+// partials[l * NB + b]; crps_finalize_kernel sums the NB partials of a level in order.
+template <typename T>
+__global__ void __launch_bounds__(256)
+crps_kernel(const T* __restrict__ samples, const T* __restrict__ target, int64_t n_tc, int L, int S, double* __restrict__ partials) {
+  __shared__ double red[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, l = blockIdx.x, NB = gridDim.y;
+  const double norm = 1.0 / ((double)S * (double)(S - 1));
+  double acc = 0.0;
+  for (int64_t tc = (int64_t)blockIdx.y * 8 + warp; tc < n_tc; tc += (int64_t)NB * 8) {
+    const bool has = lane < S;
+    double v = has ? (double)samples[(tc * L + l) * S + lane] : INFINITY;      // +inf pads sort to the end
+    const double y = (double)target[tc * L + l];
+    double a = has ? fabs(v - y) : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        const double other = __shfl_xor_sync(0xffffffffu, v, j);
+        const bool up = (lane & k) == 0, lower = (lane & j) == 0;
+        v = (lower == up) ? fmin(v, other) : fmax(v, other);
+      }
+    }
+    const double next = __shfl_down_sync(0xffffffffu, v, 1);
+    double d = (lane < S - 1) ? (next - v) * (double)((lane + 1) * (S - 1 - lane)) : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    acc += a / (double)S - d * norm;
+  }
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    partials[(size_t)l * NB + blockIdx.y] = t;
+  }
+}
+__global__ void crps_finalize_kernel(const double* __restrict__ partials, int NB, int64_t n_tc, int L, double* __restrict__ out) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= L) return;
+  double t = 0.0;
+  for (int b = 0; b < NB; ++b) t += partials[(size_t)l * NB + b];
+  out[l] = t / (double)n_tc;
+}
+
 // Row gather dst[i, :] = src[idx[i], :]: the shuffle stage of the input pipeline on the device (the reference shuffles samples on the
 // host: tf.data `unbatch().shuffle(11520).batch(B)`, hpo_baseline_v1.py:140-143; DistributedSampler(shuffle=True),
 // train_mlp_h5loader.py:126-134).  blockDim = (32, 8): a warp per row; VEC: rows are multiples of four floats and 16-byte aligned.

@@ -213,6 +213,8 @@ class data_utils:
         assert samplepreds.shape[1] == self.num_latlon
         assert len(samplepreds.shape) == len(target.shape) + 1
         assert len(samplepreds.shape) == 3 or len(samplepreds.shape) == 4
+        if torch is not None and isinstance(samplepreds, torch.Tensor) and samplepreds.is_cuda:
+            return self._gpu_crps(samplepreds, target, avg_grid)
         n = samplepreds.shape[-1]
         mae = np.mean(np.abs(samplepreds - target[..., np.newaxis]), axis=(0, -1))
         s = np.sort(samplepreds, axis=-1)
@@ -221,6 +223,25 @@ class data_utils:
         spread = (diff * count).sum(axis=-1).mean(axis=0)
         m = mae - spread / (n * (n - 1))
         return m.mean(axis=0) if avg_grid else m
+
+    @staticmethod
+    def _gpu_crps(samplepreds, target, avg_grid):
+        """``csb_eval_crps``: CUDA tensors (T, ncol, [L,] S) / (T, ncol[, L]), fp32 or fp64; returns a CUDA fp64 tensor of length L (or 1)."""
+        from . import _lib
+        lib = _lib.load()
+        if not avg_grid:
+            raise NotImplementedError("the device CRPS returns the grid average (avg_grid=True); pass NumPy arrays for the per-column field")
+        f64 = samplepreds.dtype == torch.float64
+        dt = torch.float64 if f64 else torch.float32
+        s, t = samplepreds.to(dt).contiguous(), target.to(samplepreds.device, dt).contiguous()
+        S = int(s.shape[-1])
+        L = int(s.shape[2]) if s.dim() == 4 else 1
+        n_tc = int(s.shape[0] * s.shape[1])
+        out = torch.empty(L, dtype=torch.float64, device=s.device)
+        scratch = torch.empty(L * 64, dtype=torch.float64, device=s.device)
+        _lib.check(lib.csb_eval_crps(s.data_ptr(), t.data_ptr(), 1 if f64 else 0, n_tc, L, S, out.data_ptr(), scratch.data_ptr(),
+                                     _lib.current_stream_ptr()), "csb_eval_crps")
+        return out if s.dim() == 4 else out[0]
 
     def create_metrics_df(self, data_split):
         """:1526-1621 -- per-variable and per-output-index metric tables for every model in ``model_names``."""

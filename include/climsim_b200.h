@@ -252,6 +252,13 @@ int  csb_eval_metrics(const float* pred, const float* target, const float* x_nor
                       const double* hybi, double p0, const double* area_wgt, const double* out_scale, double ps_mean, double ps_max,
                       double ps_min, int normalize, double* out, double* scratch, void* stream);
 
+/* CRPS of an ensemble by the sorted-sample identity, averaged over time and grid (data_utils.calc_CRPS, data_utils.py:1499-1524):
+ * samples [n_tc, L, S] and target [n_tc, L] on the device (fp32, or fp64 with is_f64 != 0; n_tc = time x grid, L = 60 levels or 1,
+ * 2 <= S <= 32 members contiguous); out (device, fp64) [L]; scratch (device) needs L * CSB_CRPS_BLOCKS doubles.
+ * fp64 arithmetic, fixed summation order (deterministic). */
+#define CSB_CRPS_BLOCKS 64
+int  csb_eval_crps(const void* samples, const void* target, int is_f64, int64_t n_tc, int L, int S, double* out, double* scratch, void* stream);
+
 /* ---- input pipeline ------------------------------------------------------------------------------------------------------------- */
 /* dst[i, :] = src[idx[i], :] for i < n_rows (fp32 rows of row_len floats, device pointers, idx int64 on the device): the sample
  * shuffle of the reference's input pipelines -- tf.data `unbatch().shuffle(384*30).batch(B)` (hpo_baseline_v1.py:140-143,

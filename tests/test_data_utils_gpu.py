@@ -293,3 +293,28 @@ def test_fused_gpu_metrics_match_reference_golden(golden_dir):
             got = df[m].values[col:col + n]
             np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-12 * max(1.0, np.abs(want).max()), err_msg=f"{m} {v}")
         col += n
+
+
+def test_gpu_crps_matches_reference_golden(golden_dir):
+    """csb_eval_crps (a warp per (time, column, level) element, bitonic sort of the ensemble in registers) against the CRPS the
+    REFERENCE's data_utils.calc_CRPS produced (tests/golden/data_utils.npz), and against the oracle on a 32-member ensemble."""
+    from climsim_b200.data_utils import data_utils
+    from oracle import data_utils_ref as R
+    g = np.load(os.path.join(golden_dir, "data_utils.npz"))
+    du = data_utils.__new__(data_utils)
+    du.num_latlon = int(g["ncol"])
+    got = du.calc_CRPS(torch.from_numpy(g["crps_samples"]).cuda(), torch.from_numpy(g["tw_ptend_t"]).cuda()).cpu().numpy()
+    np.testing.assert_allclose(got, g["crps"], rtol=1e-12, atol=1e-300)
+    rng = np.random.default_rng(3)
+    T, ncol = 37, int(g["ncol"])
+    for shape_l in ((60,), ()):                                       # profile variable / scalar variable
+        samples = rng.normal(size=(T, ncol) + shape_l + (32,))
+        samples[0, 0] = samples[0, 0, ..., :1]                         # ties: an ensemble of identical members has zero spread
+        target = rng.normal(size=(T, ncol) + shape_l)
+        want = R.calc_crps(samples, target)
+        got64 = du.calc_CRPS(torch.from_numpy(samples).cuda(), torch.from_numpy(target).cuda()).cpu().numpy()
+        np.testing.assert_allclose(got64, want, rtol=1e-12)
+        got32 = du.calc_CRPS(torch.from_numpy(samples).float().cuda(), torch.from_numpy(target).float().cuda()).cpu().numpy()
+        np.testing.assert_allclose(got32, want, rtol=2e-6)
+    with pytest.raises(NotImplementedError):
+        du.calc_CRPS(torch.from_numpy(g["crps_samples"]).cuda(), torch.from_numpy(g["tw_ptend_t"]).cuda(), avg_grid=False)
