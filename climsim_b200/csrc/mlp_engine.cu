@@ -132,10 +132,26 @@ static inline bool tn_use_pairs(int N) { return g_use_pairs && N > 128; }
 static inline int tn_b_box_rows(int N) { return N > 128 ? (tn_use_pairs(N) ? std::min(N, 256) / 2 : std::min(N, 256)) : std::min(N, 128); }
 
 static bool g_use_staged = true;    // CSB_NO_STAGED_EPI=1: register -> global stores in every launch (debugging aid)
+// Small batches: when the 256 x 256 pair tiles of a wide layer would occupy at most half of the SMs (e.g. the reference's own batch
+// size 3072: 36 pairs), the layer runs on 128 x 128 single-CTA tiles instead -- four times as many CTAs, each a quarter of the
+// mainloop.  `tb_small` is the B tensor map encoded with the 128-row box those tiles need (nullptr: policy off).
+static inline bool tn_small_tiles(int M, int N, int sm_count, const CUtensorMap* tb_small) {
+  static const bool off = getenv("CSB_NO_SMALL_TILES") != nullptr;          // debugging aid: always the 256-wide pair tiles
+  if (off || tb_small == nullptr || N <= 128 || !tn_use_pairs(N)) return false;
+  const int64_t pairs = ceil_div(ceil_div(M, 128), 2) * ceil_div(N, 256);
+  return 4 * pairs <= sm_count;
+}
 template <int EPI, int VAR>
-static int launch_tn_shape(const CUtensorMap& ta, const CUtensorMap& tb, const tc::GemmParams& p, int sm_count, cudaStream_t st) {
+static int launch_tn_shape(const CUtensorMap& ta, const CUtensorMap& tb, const tc::GemmParams& p, int sm_count, cudaStream_t st,
+                           const CUtensorMap* tb_small = nullptr) {
   constexpr bool BF16_OUT = (EPI == tc::EPI_BIAS_ACT || EPI == tc::EPI_HEAD_LOSS || EPI == tc::EPI_DGRAD || EPI == tc::EPI_DGRAD_MASK ||
                              EPI == tc::EPI_BIAS_ADD);
+  if (tn_small_tiles(p.M, p.N, sm_count, tb_small)) {
+    if constexpr (BF16_OUT) {
+      if (g_use_staged && p.K <= 256 && p.kb_per_tap == 0) return launch_tn<128, 4, EPI, 1, VAR | tc::VAR_STAGED>(ta, *tb_small, p, sm_count, st);
+    }
+    return launch_tn<128, 6, EPI, 1, VAR>(ta, *tb_small, p, sm_count, st);
+  }
   if constexpr (BF16_OUT) {
     // Short contractions (K <= 256: at most four k-blocks per tile) are bound by the epilogue's stores, not by the mainloop:
     // they trade operand-ring stages for an output staging tile and coalesced stores.
@@ -155,18 +171,19 @@ static int launch_tn_shape(const CUtensorMap& ta, const CUtensorMap& tb, const t
   return launch_tn<128, 6, EPI, 1, VAR>(ta, tb, p, sm_count, st);
 }
 template <int EPI>
-static int launch_tn_auto(const CUtensorMap& ta, const CUtensorMap& tb, const tc::GemmParams& p, int sm_count, cudaStream_t st) {
+static int launch_tn_auto(const CUtensorMap& ta, const CUtensorMap& tb, const tc::GemmParams& p, int sm_count, cudaStream_t st,
+                          const CUtensorMap* tb_small = nullptr) {
   // ELU (expm1f in the epilogue) is a separate instantiation of the epilogues that evaluate an activation
   constexpr bool HAS_ACT = (EPI == tc::EPI_BIAS_ACT || EPI == tc::EPI_HEAD_LOSS || EPI == tc::EPI_HEAD_OUT || EPI == tc::EPI_DGRAD);
   if constexpr (EPI == tc::EPI_HEAD_LOSS) {
     // the lean loss loop covers MSE without an output mask on a non-ELU head; everything else takes the general variant
     if (p.act == CSB_ACT_ELU || p.loss_kind != CSB_LOSS_MSE || p.out_mask != nullptr)
-      return p.act == CSB_ACT_ELU ? launch_tn_shape<EPI, tc::VAR_ELU | tc::VAR_GENERAL_LOSS>(ta, tb, p, sm_count, st)
-                                  : launch_tn_shape<EPI, tc::VAR_GENERAL_LOSS>(ta, tb, p, sm_count, st);
+      return p.act == CSB_ACT_ELU ? launch_tn_shape<EPI, tc::VAR_ELU | tc::VAR_GENERAL_LOSS>(ta, tb, p, sm_count, st, tb_small)
+                                  : launch_tn_shape<EPI, tc::VAR_GENERAL_LOSS>(ta, tb, p, sm_count, st, tb_small);
   } else if constexpr (HAS_ACT) {
-    if (p.act == CSB_ACT_ELU) return launch_tn_shape<EPI, tc::VAR_ELU>(ta, tb, p, sm_count, st);
+    if (p.act == CSB_ACT_ELU) return launch_tn_shape<EPI, tc::VAR_ELU>(ta, tb, p, sm_count, st, tb_small);
   }
-  return launch_tn_shape<EPI, 0>(ta, tb, p, sm_count, st);
+  return launch_tn_shape<EPI, 0>(ta, tb, p, sm_count, st, tb_small);
 }
 static inline int tn_block_n(int N) { return N > 128 ? 256 : 128; }
 
@@ -297,6 +314,7 @@ struct csb_mlp {
 
   CUtensorMap tm_wt[CSB_MAX_LAYERS];        // Wt16_l as K-major B operand of the forward GEMM
   CUtensorMap tm_w[CSB_MAX_LAYERS];         // W16_l  as K-major B operand of the data-gradient GEMM
+  CUtensorMap tm_wt_s[CSB_MAX_LAYERS], tm_w_s[CSB_MAX_LAYERS];     // the same two with a 128-row box (small-batch tile policy)
   int64_t maps_B = -1;
   ActMaps tm_in[CSB_MAX_LAYERS];            // input of layer l (xn or act[l-1]) with `maps_B` rows
   ActMaps tm_dz[CSB_MAX_LAYERS];            // dZ_l (ping-pong buffer (L-1-l)&1, ld = Np_l) with `maps_B` rows
@@ -397,6 +415,10 @@ static int build_weight_maps(csb_mlp* h) {
     if (rc) return rc;
     // dgrad:    D[B, Kp] = dZ[B, Np] . W16[Kp, Np]^T           B-operand rows = Kp, contraction = Np
     rc = make_tmap_bf16(&h->tm_w[l], h->w16[l], li.Np, li.Kp, li.Np, 64, (uint32_t)tn_b_box_rows(li.Kp));
+    if (rc) return rc;
+    rc = make_tmap_bf16(&h->tm_wt_s[l], h->wt16[l], li.Kp, li.Np, li.Kp, 64, (uint32_t)std::min(li.Np, 128));
+    if (rc) return rc;
+    rc = make_tmap_bf16(&h->tm_w_s[l], h->w16[l], li.Np, li.Kp, li.Np, 64, (uint32_t)std::min(li.Kp, 128));
     if (rc) return rc;
   }
   return CSB_OK;
@@ -554,7 +576,7 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
   CKA(h->d_sub, (size_t)h->in_p * 4); CKA(h->d_div, (size_t)h->in_p * 4);
   CKA(h->d_out_scale, (size_t)h->out_p * 4); CKA(h->d_inv_out_scale, (size_t)h->out_p * 4); CKA(h->d_loss_w, (size_t)h->out_p * 4);
   CKA(h->d_out_mask, (size_t)h->out_p * 4);
-  h->n_loss_partials = (int)std::max<int64_t>(h->cap / 128 * ceil_div(h->out_p, tn_block_n(h->out_p)) * tc::TN_EPI_WARPS, 8 * sm);
+  h->n_loss_partials = (int)std::max<int64_t>(h->cap / 128 * ceil_div(h->out_p, 128) * tc::TN_EPI_WARPS, 8 * sm);   // 128-wide n-blocks: the most partials any tile policy writes
   CKA(h->loss_partials, (size_t)h->n_loss_partials * 4);
   CKA(h->d_loss, 4);
   if (h->bf16) {
@@ -822,7 +844,7 @@ static int run_hidden_forward(csb_mlp* h, int64_t B, cudaStream_t st) {
       p.M = (int)B; p.N = li.Np; p.K = li.Kp; p.act = gemm_act; p.alpha = li.alpha; p.head_relu_from = -1;
       p.bias = h->params + li.b_off; p.out = li.ln ? h->zbuf[l] : h->act[l]; p.ld_out = li.Np;
       p.mask_out = h->amask[l]; p.ld_mask = (int)h->cap;
-      int rc = launch_tn_auto<tc::EPI_BIAS_ACT>(h->tm_in[l].a_k128, h->tm_wt[l], p, h->sm_count, st);
+      int rc = launch_tn_auto<tc::EPI_BIAS_ACT>(h->tm_in[l].a_k128, h->tm_wt[l], p, h->sm_count, st, &h->tm_wt_s[l]);
       if (rc) return rc;
     } else {
       simt::SgemmParams p = {};
@@ -872,9 +894,9 @@ static int run_head(csb_mlp* h, int64_t B, int fused_loss, const float* y, float
       p.y = y; p.ld_y = h->out_dim; p.loss_w = h->d_loss_w; p.grad_scale = grad_scale; p.loss_kind = h->cfg.loss;
       p.loss_partials = h->loss_partials;
       p.pred = nullptr;
-      rc = launch_tn_auto<tc::EPI_HEAD_LOSS>(h->tm_in[l].a_k128, h->tm_wt[l], p, h->sm_count, st);
+      rc = launch_tn_auto<tc::EPI_HEAD_LOSS>(h->tm_in[l].a_k128, h->tm_wt[l], p, h->sm_count, st, &h->tm_wt_s[l]);
     } else {
-      rc = launch_tn_auto<tc::EPI_HEAD_OUT>(h->tm_in[l].a_k128, h->tm_wt[l], p, h->sm_count, st);
+      rc = launch_tn_auto<tc::EPI_HEAD_OUT>(h->tm_in[l].a_k128, h->tm_wt[l], p, h->sm_count, st, &h->tm_wt_s[l]);
     }
     if (rc) return rc;
   } else {
@@ -960,6 +982,14 @@ static int flush_pending(csb_mlp* h, cudaStream_t st) {
   prof_mark(h, K_REDUCE, st);
   h->pending = false;
   return CSB_OK;
+}
+
+// loss partials the output-layer kernel writes for a batch of B rows: one per (m-block, n-block, epilogue warp) of the tile shape
+// the launch policy picks (launch_tn_shape)
+static inline int head_loss_partials(const csb_mlp* h, int64_t B) {
+  const int l = h->L - 1;
+  const int bn = tn_small_tiles((int)B, h->out_p, h->sm_count, &h->tm_wt_s[l]) ? 128 : tn_block_n(h->out_p);
+  return (int)(ceil_div(B, 128) * ceil_div(h->out_p, bn)) * tc::TN_EPI_WARPS;
 }
 
 static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st, int n_loss_partials = 0, float* loss_out = nullptr,
@@ -1060,9 +1090,9 @@ static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st,
         int rc;
         if (h->amask[l - 1] != nullptr) {        // ReLU-family layer: act' from the forward pass's sign bits (no activation re-read)
           p.mask_in = h->amask[l - 1]; p.ld_mask = (int)h->cap;
-          rc = launch_tn_auto<tc::EPI_DGRAD_MASK>(h->tm_dz[l].a_k128, h->tm_w[l], p, h->sm_count, st);
+          rc = launch_tn_auto<tc::EPI_DGRAD_MASK>(h->tm_dz[l].a_k128, h->tm_w[l], p, h->sm_count, st, &h->tm_w_s[l]);
         } else {
-          rc = launch_tn_auto<tc::EPI_DGRAD>(h->tm_dz[l].a_k128, h->tm_w[l], p, h->sm_count, st);
+          rc = launch_tn_auto<tc::EPI_DGRAD>(h->tm_dz[l].a_k128, h->tm_w[l], p, h->sm_count, st, &h->tm_w_s[l]);
         }
         if (rc) return rc;
       } else {
@@ -1084,7 +1114,7 @@ static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st,
       if (h->bf16) {
         tc::GemmParams p = {};
         p.M = (int)B; p.N = li.Kp; p.K = li.Np; p.out = h->dx_tmp; p.ld_out = h->in_p;
-        int rc = launch_tn_auto<tc::EPI_F32>(h->tm_dz[0].a_k128, h->tm_w[0], p, h->sm_count, st);
+        int rc = launch_tn_auto<tc::EPI_F32>(h->tm_dz[0].a_k128, h->tm_w[0], p, h->sm_count, st, &h->tm_w_s[0]);
         if (rc) return rc;
       } else {
         simt::SgemmParams p = {};
@@ -1126,7 +1156,7 @@ static int train_step_body(csb_mlp* h, const float* x, const float* y, int64_t B
   const int l = h->L - 1;
   if (h->bf16) {
     if ((rc = run_head(h, B, 1, y, grad_scale, st))) return rc;
-    n_partials = (int)(ceil_div(B, 128) * ceil_div(h->out_p, tn_block_n(h->out_p))) * tc::TN_EPI_WARPS;
+    n_partials = head_loss_partials(h, B);
   } else {
     if ((rc = run_head(h, B, 0, nullptr, 0.f, st))) return rc;
     const int grid = std::min(h->n_loss_partials, grid_for(B * h->out_p, 256, h->sm_count));
@@ -1188,7 +1218,7 @@ int csb_mlp_train_step(csb_mlp* h, const float* x, const float* y, int64_t B, fl
       h->launches += g.n_launches;
       h->acts_B = -1;
       if ((flags & CSB_TRAIN_FUSED_OPT) != 0 && fused_opt_supported(h)) {      // what run_backward_chain records when it runs eagerly
-        h->pending = true; h->pending_B = B; h->pending_n_loss = (int)(ceil_div(B, 128) * ceil_div(h->out_p, tn_block_n(h->out_p))) * tc::TN_EPI_WARPS;
+        h->pending = true; h->pending_B = B; h->pending_n_loss = head_loss_partials(h, B);
         h->pending_loss_out = lo;
       }
       return CSB_OK;
