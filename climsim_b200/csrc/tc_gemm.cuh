@@ -1,16 +1,20 @@
 // tc_gemm.cuh -- hand-written Blackwell (sm_100a) tensor-core GEMMs for the dense layers of the column emulators.
 //
 // Two kernels, both: TMA (cp.async.bulk.tensor) -> 128B-swizzled shared memory -> tcgen05.mma (kind::f16, bf16
-// operands, fp32 accumulators in TMEM) -> tcgen05.ld -> fused epilogue.  Warp-specialised: warps 0-3 epilogue (one
-// TMEM lane quadrant each), warp 4 = TMA producer, warp 5 = TMEM owner + single-thread MMA issuer.
+// operands, fp32 accumulators in TMEM) -> tcgen05.ld -> fused epilogue; warp-specialised (one TMA producer thread, one
+// MMA-issuing thread, the remaining warps run the epilogue, one TMEM lane quadrant each); optionally on CTA pairs
+// (tcgen05 cta_group::2: a 256-row tile across two SMs, each loading half of the B operand).
 //
 //   gemm_tn_kernel   D[M,N] = A[M,K] . Bt[N,K]^T      both operands K-major.  Forward layers (A = activations,
-//                    Bt = W^T) and data-gradient layers (A = dZ, Bt = W).  Persistent over 128 x BN tiles,
-//                    STAGES-deep smem ring, two TMEM accumulator buffers so the epilogue of tile i overlaps the
-//                    MMAs of tile i+1.  Epilogues: bias+activation->bf16, head+loss (+dZ), act'-masked dgrad, fp32.
+//                    Bt = W^T) and data-gradient layers (A = dZ, Bt = W).  Persistent over 128 x BN tiles (256 x BN per
+//                    pair), STAGES-deep smem ring, two TMEM accumulator buffers so the epilogue of tile i overlaps the
+//                    MMAs of tile i+1; 18 warps (issuer, producer, 16 epilogue).  Epilogues: bias+activation->bf16 (+ sign
+//                    mask), head+loss (+dZ), act'-masked dgrad, residual add, fp32; results go registers -> global, or through a
+//                    per-warp staging tile and coalesced stores for the short-contraction launches (VAR_STAGED).
 //   gemm_nt_kernel   D[M,N] = A[R,M]^T . B[R,N]        both operands MN-major (row index R = batch is the
-//                    contraction).  Weight gradients dW = H^T dZ.  One 128 x BN tile per CTA, split over R
-//                    (blockIdx.y) into fp32 partials that a later kernel reduces deterministically.
+//                    contraction).  Weight gradients dW = H^T dZ, bias gradients as column sums of the dZ tiles in flight.
+//                    One 128 x BN (256 x BN per pair) tile per CTA, split over R (blockIdx.y) into fp32 partials that a
+//                    later kernel reduces deterministically; 6 warps; output through shared memory + bulk-copy stores.
 //
 // Shared-memory operand layouts are the canonical UMMA SWIZZLE_128B layouts (what TMA writes with
 // CU_TENSOR_MAP_SWIZZLE_128B): K-major: rows of 64 bf16 (128 B), 8-row groups 1024 B apart (SBO);
@@ -25,7 +29,7 @@ namespace tc {
 constexpr int BM = 128;          // tile rows == UMMA M == TMEM lanes
 constexpr int BK = 64;           // bf16 elements per 128-byte swizzle row
 constexpr int UMMA_K = 16;       // K per tcgen05.mma for 16-bit operands
-constexpr int NUM_THREADS = 192; // 4 epilogue warps + producer + mma
+constexpr int NUM_THREADS = 192; // gemm_nt_kernel: 4 epilogue warps + producer + mma issuer
 
 enum Epi : int {
   EPI_BIAS_ACT = 0,   // out(bf16) = act(acc + bias)                       forward hidden layer
@@ -546,8 +550,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// gemm_tn_kernel: persistent, K-major x K-major.   18 warps: 0 = TMEM owner + MMA issuer, 1 = TMA producer, 2-17 epilogue (four per TMEM lane quadrant = four per SM
-// sub-partition, each taking a quarter of the tile's columns), 16 = TMA producer, 17 = TMEM owner + MMA issuer.
+// gemm_tn_kernel: persistent, K-major x K-major.   18 warps: 0 = TMEM owner + MMA issuer, 1 = TMA producer, 2-17 epilogue
+// (four per TMEM lane quadrant = four per SM sub-partition, each taking a quarter of the tile's columns).
 // The epilogue warps are independent of each other: each waits for the accumulator, walks its 32-column steps
 // (tcgen05.ld -> registers -> fused math -> 256-bit global stores) and releases the TMEM buffer; no staging tile, no
 // named barriers, so all of the shared memory beyond the bias vector belongs to the operand ring.  Four warps per
@@ -850,8 +854,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
 // ---------------------------------------------------------------------------------------------------------------
 // gemm_nt_kernel: D[M,N] = sum_r A[r, m] * B[r, n]; both operands MN-major; split over r (blockIdx.y).
-// Weight gradient dW = H^T dZ.  The CTAs of the first m-block additionally reduce the dZ tiles that pass through shared
-// memory over their rows (the otherwise idle epilogue warps do it): that is the bias gradient, at no extra HBM traffic.
+// Weight gradient dW = H^T dZ.  The epilogue warps, idle during the mainloop, reduce the dZ tiles that pass through shared
+// memory over their rows (every m-tile takes its share of the row blocks): that is the bias gradient, at no extra HBM traffic.
 // ---------------------------------------------------------------------------------------------------------------
 struct NtParams {
   int M, N, R;             // M, N feature dims (multiples of 64), R rows to contract
