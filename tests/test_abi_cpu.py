@@ -58,3 +58,25 @@ def test_flat_blob_keras_conversion_roundtrip():
     w_head = flat[-(128 * 128 + 128):-128].reshape(128, 128)
     np.testing.assert_array_equal(w_head[:, :120], ws[-4])
     np.testing.assert_array_equal(w_head[:, 120:], ws[-2])
+
+
+def test_header_is_plain_c_and_the_c_example_links(tmp_path):
+    """The boundary is a C ABI: include/climsim_b200.h compiles as C99 with -Wall -Werror, and examples/ffi_demo.c (create, set
+    parameters, forward, train step, optimizer -- from C, no Python, no torch) compiles and links against the shared library."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    cuda_inc = "/usr/local/cuda/include"
+    if gcc is None or not os.path.exists(os.path.join(cuda_inc, "cuda_runtime_api.h")):
+        pytest.skip("needs gcc and the CUDA runtime headers")
+    from climsim_b200 import build
+    build.build()
+    hdr_only = tmp_path / "hdr.c"
+    hdr_only.write_text('#include "climsim_b200.h"\nint main(void) { return csb_version() == CSB_VERSION ? 0 : 1; }\n')
+    inc = ["-I", os.path.join(ROOT, "include"), "-I", cuda_inc]
+    subprocess.run([gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", *inc, "-c", str(hdr_only), "-o", str(tmp_path / "hdr.o")], check=True)
+    obj = tmp_path / "ffi_demo.o"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", *inc, "-c", os.path.join(ROOT, "examples", "ffi_demo.c"), "-o", str(obj)], check=True)
+    lib_dir = os.path.join(ROOT, "climsim_b200")
+    subprocess.run([gcc, str(obj), "-L", lib_dir, "-lclimsim_b200", "-L", "/usr/local/cuda/lib64", "-lcudart", "-o", str(tmp_path / "ffi_demo")],
+                   check=True)
