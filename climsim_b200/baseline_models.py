@@ -131,6 +131,17 @@ class HSRMLP(_EngineModule):
         parts += [sd[f"{prefix}final_linear.weight"].t().reshape(-1), sd[f"{prefix}final_linear.bias"]]
         self.load_flat(torch.cat([p.detach().float().cpu().reshape(-1) for p in parts]).numpy())
 
+    def reference_state_dict(self, prefix: str = "") -> dict:
+        """The parameters under the reference module's keys and layouts (inverse of ``load_reference_state_dict``)."""
+        views, sd, i = self.layer_views(), {}, 0
+        for l in range(self.n_hidden):
+            w, b, g, be = views[i:i + 4]
+            i += 4
+            sd[f"{prefix}linear{l}.0.weight"], sd[f"{prefix}linear{l}.0.bias"] = w.t().contiguous().clone(), b.clone()
+            sd[f"{prefix}linear{l}.1.weight"], sd[f"{prefix}linear{l}.1.bias"] = g.clone(), be.clone()
+        sd[f"{prefix}final_linear.weight"], sd[f"{prefix}final_linear.bias"] = views[i].t().contiguous().clone(), views[i + 1].clone()
+        return sd
+
 
 class HSR(torch.nn.Module):
     """``HeteroskedasticRegression`` (hsr.py:38-81): two LayerNorm MLPs estimating mean and log-precision; ``forward`` returns
@@ -154,6 +165,65 @@ class HSR(torch.nn.Module):
     def load_reference_state_dict(self, sd) -> None:
         self.mean.load_reference_state_dict(sd, "mean.")
         self.logprec.load_reference_state_dict(sd, "logprec.")
+
+    def reference_state_dict(self) -> dict:
+        """``state_dict`` with the reference's keys (``mean.linear0.0.weight`` ... ``logprec.final_linear.bias``): what its
+        ``torch.save(self.state_dict(), save)`` checkpoints hold, loadable by ``hsr.HeteroskedasticRegression.load_state_dict``."""
+        return {**self.mean.reference_state_dict("mean."), **self.logprec.reference_state_dict("logprec.")}
+
+    def trainer(self, data, epochs: int = 20, save: str = "models/vae.cp", plot: bool = True, loss_type: str = "mle",
+                optimizer: str = "adam", lr: float = 0.0001, gamma: float = 0.01, rho: Optional[float] = None,
+                checkpoint_every_s: float = 1200.0):
+        """``HeteroskedasticRegression.trainer`` (hsr.py:83-142), same arguments and behaviour: per-group L2 weight decay
+        alpha = (1-rho)/rho*gamma for the mean network and beta = (1-rho)/rho*(1-gamma) for the log-precision network, Adam or SGD,
+        MSE on the mean for the first third of the epochs and the Gaussian negative log-likelihood afterwards, the loss clipped to
+        +-1e5, a checkpoint (reference keys) every 20 minutes.  ``data`` yields dicts with ``'x'`` and ``'y'``.  The forward and
+        backward passes of both networks run in the engine (``csb_mlp_forward`` / ``csb_mlp_backward`` through autograd); the
+        loss expression and the optimizer are the same torch calls the reference makes.  Returns the per-step losses."""
+        import time
+        rho = rho if rho is not None else 1 - gamma
+        alpha = (1 - rho) / rho * gamma
+        beta = (1 - rho) / rho * (1 - gamma)
+        print("alpha: %.3f, beta: %.3f" % (alpha, beta))
+        pms = [{"params": self.mean.parameters(), "lr": lr, "weight_decay": alpha},
+               {"params": self.logprec.parameters(), "lr": lr, "weight_decay": beta}]
+        if optimizer == "adam":
+            opt = torch.optim.Adam(pms)
+        elif optimizer == "sgd":
+            opt = torch.optim.SGD(pms)
+        else:
+            raise ValueError("Unknown optimizer")
+        device = self.mean.flat.device
+        losses, t_ckpt = [], time.time()
+        for epoch in range(epochs):
+            for batch in data:
+                x, y = batch["x"].to(device), batch["y"].to(device)
+                opt.zero_grad()
+                mu, logprec = self(x)
+                prec = torch.exp(logprec)
+                if loss_type == "mle":
+                    if epoch < epochs / 3:
+                        loss = ((y - mu) ** 2).mean()                        # first only the mean, via MSE
+                    else:
+                        loss = (prec * (y - mu) ** 2 - logprec).mean()       # non-iid Gaussians -> maximum likelihood
+                else:
+                    raise ValueError("Unknown loss")
+                torch.clip(loss, min=-1e5, max=1e5).backward()
+                losses += [loss.item()]
+                opt.step()
+                if time.time() - t_ckpt > checkpoint_every_s:
+                    torch.save(self.reference_state_dict(), save)
+                    t_ckpt = time.time()
+        n = len(data) if hasattr(data, "__len__") else 1
+        print("Last-epoch loss: %.2f" % sum(losses[-n:-1]))
+        print("Finished Training")
+        if plot:
+            try:
+                import matplotlib.pyplot as plt
+                plt.plot(np.array(losses)[:-1])
+            except ImportError:
+                pass
+        return losses
 
 
 class OnlineMLP(_EngineModule):

@@ -132,6 +132,30 @@ def test_hsr_layernorm_model_against_reference_golden(golden_dir, dtype, tol_out
                 assert err <= tol_g, (mode, key, err)
 
 
+def test_hsr_trainer_matches_reference_trainer_end_state(golden_dir, capsys):
+    """HSR.trainer (same arguments as hsr.py:83-142) from the reference's initial weights on the reference's two batches: after
+    3 epochs x 2 batches (MSE phase, then NLL; Adam with the per-group weight decay) the parameters equal the end state of the
+    REFERENCE's own trainer run (tests/golden/hsr_small.npz).  fp32 engine: Adam divides by sqrt(v), so elements whose gradient is
+    cancellation noise may move by O(lr) either way -- the bound is per tensor in relative L2."""
+    from climsim_b200.baseline_models import HSR
+    g = np.load(os.path.join(golden_dir, "hsr_small.npz"))
+    sd = {k[len("init::"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("init::")}
+    net = HSR(124, 128, hidden_dims=32, layers=2, dtype="fp32", max_batch=64)
+    net.load_reference_state_dict(sd)
+    batches = [{"x": torch.from_numpy(g[f"x{i}"]), "y": torch.from_numpy(g[f"y{i}"])} for i in range(2)]
+    losses = net.trainer(batches, epochs=3, save=os.devnull, plot=False, lr=1e-3, gamma=0.022)
+    assert len(losses) == 6 and "alpha:" in capsys.readouterr().out
+    got = net.reference_state_dict()
+    final = {k[len("final::"):]: g[k] for k in g.files if k.startswith("final::")}
+    assert sorted(got) == sorted(final)
+    for k, want in final.items():
+        have = got[k].detach().cpu().numpy()
+        assert have.shape == want.shape, k
+        err = np.linalg.norm(have - want) / max(np.linalg.norm(want), 1e-12)
+        assert err <= 2e-4, (k, err)
+        assert np.abs(have - want).max() <= 3e-3, k                     # nothing moved further than three Adam steps of lr
+
+
 @pytest.mark.parametrize("hidden,layers,B", [(1024, 2, 333), (200, 1, 1000), (512, 3, 129)])
 def test_layernorm_mlp_bf16_wide_rows(hidden, layers, B):
     """bf16 LayerNorm kernels (a row per warp held in registers, fused du -> dz + parameter gradients) at the widths the small golden
