@@ -109,6 +109,10 @@ class data_utils:
         xn[np.isnan(xn)] = 0
         return np.float32(xn)
 
+    def reshape_npy(self, var_arr, var_arr_dim):
+        """:946-952 -- (num_samples, dim) -> (timestep, lat/lon column, dim)."""
+        return var_arr.reshape((int(var_arr.shape[0] / self.num_latlon), self.num_latlon, var_arr_dim))
+
     @staticmethod
     def load_npy_file(load_path=""):
         """:1019-1026"""

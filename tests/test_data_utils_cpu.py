@@ -85,3 +85,9 @@ def test_cnn_reshapes_host(g):
 def test_assert_messages_match_reference(du):
     with pytest.raises(AssertionError, match="Provided data_split is not valid"):
         du.set_pressure_grid("nope")
+
+
+def test_reshape_npy(du):
+    a = np.arange(du.num_latlon * 3 * 60, dtype=np.float32).reshape(du.num_latlon * 3, 60)
+    r = du.reshape_npy(a, 60)
+    assert r.shape == (3, du.num_latlon, 60) and r[1, 2, 5] == a[du.num_latlon + 2, 5]
