@@ -85,6 +85,8 @@ SIGNATURES = {
     "csb_cnn_get_params": (C.c_int, [_VP, _VP]),
     "csb_cnn_get_grads": (C.c_int, [_VP, _VP]),
     "csb_cnn_set_loss_weights": (C.c_int, [_VP, _VP]),
+    "csb_cnn_set_dropout": (C.c_int, [_VP, C.c_float, C.c_uint32]),
+    "csb_cnn_debug_read_hidden": (C.c_int, [_VP, C.c_int, C.c_int, _VP, C.c_int64, _VP]),
     "csb_cnn_forward": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP]),
     "csb_cnn_train_step": (C.c_int, [_VP, _VP, _VP, C.c_int64, C.c_float, _VP, _VP]),
     "csb_cnn_grad_buffer": (C.c_int, [_VP, _P(_VP), _P(C.c_size_t)]),

@@ -313,9 +313,12 @@ class CNN(torch.nn.Module):
     -> (B,60,10)`` for inference; training goes through the fused ``engine.train_step`` / ``engine.apply_opt`` (loss =
     ``mae_adjusted`` or ``mse_adjusted``), the way ``model.fit`` drives it in the reference (hpo_train.py:355-368)."""
 
-    def __init__(self, depth: int = 12, width: int = 406, kernel: int = 3, loss: str = "mae", dtype: str = "bf16", max_batch: int = 4096):
+    def __init__(self, depth: int = 12, width: int = 406, kernel: int = 3, loss: str = "mae", dtype: str = "bf16", max_batch: int = 4096,
+                 dropout: float = 0.175, seed: int = 0):
         super().__init__()
         self.engine = CNNEngine(depth=depth, width=width, kernel=kernel, loss=loss, dtype=dtype, max_batch=max_batch)
+        if dropout > 0 and dtype == "bf16":                   # hp_dropout = 0.175 (hpo_train.py:143); active in train_step only
+            self.engine.set_dropout(dropout, seed)
 
     def load_keras_weights(self, weights: Sequence[np.ndarray]) -> None:
         self.engine.set_params_flat(CNNEngine.keras_to_flat(weights))

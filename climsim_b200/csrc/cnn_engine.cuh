@@ -44,6 +44,9 @@ struct csb_cnn {
   int n_loss_partials = 0;
   int64_t maps_B = -1;
   int64_t step = 0, launches = 0;
+  float dropout = 0.f;                           // Dropout rate behind the two ReLUs of every block (training steps only)
+  uint32_t drop_seed = 0;
+  int64_t train_steps = 0;                       // advances the dropout masks from step to step
 };
 
 static void cnn_free(csb_cnn* h) {
@@ -121,14 +124,14 @@ static inline int cnn_mma_width(int c, int cp) {
 // one convolution-as-GEMM launch.  `dgrad` selects the flipped/transposed weights (output width = Cinp).
 //   kind 0: out = act(conv + bias)   kind 1: out = conv + bias + saved   kind 2: out = conv * act'(saved)
 static int cnn_conv(csb_cnn* h, const ConvLayerInfo& li, bool dgrad, const CnnBuf& in, CnnBuf& out, int kind, const CnnBuf* saved, int act,
-                    const float* bias, int64_t B, cudaStream_t st) {
+                    const float* bias, int64_t B, cudaStream_t st, float dgrad_scale = 0.f) {
   const int M = (int)(B * h->P), N = dgrad ? li.Cinp : li.Coutp, Kt = dgrad ? li.Coutp : li.Cinp;
   int rc = CSB_OK;
   if (h->bf16) {
     tc::GemmParams p = {};
     p.M = M; p.N = cnn_mma_width(dgrad ? li.Cin : li.Cout, N); p.K = li.taps * Kt; p.kb_per_tap = Kt / 64; p.tap_center = (li.taps - 1) / 2;
     p.halo_period = h->P;
-    p.act = act; p.head_relu_from = -1; p.bias = bias;
+    p.act = act; p.head_relu_from = -1; p.bias = bias; p.dgrad_scale = dgrad_scale;
     const CUtensorMap& w = dgrad ? li.tm_wd : li.tm_wt;
     p.out = out.ptr; p.ld_out = out.Cp;
     if (saved) { p.saved = reinterpret_cast<const __nv_bfloat16*>(saved->ptr); p.ld_saved = saved->Cp; }
@@ -209,7 +212,20 @@ static int cnn_wgrad(csb_cnn* h, const ConvLayerInfo& li, const CnnBuf& in, cons
   return CSB_OK;
 }
 
-static int cnn_forward_body(csb_cnn* h, const float* x, int64_t B, cudaStream_t st) {
+// inverted dropout on a hidden activation buffer (training forward); the mask depends on (seed, training step, layer)
+static int cnn_dropout(csb_cnn* h, CnnBuf& a, int layer_id, int64_t B, cudaStream_t st) {
+  const int64_t n8 = B * h->P * a.Cp / 8;
+  const uint32_t seed = h->drop_seed ^ (uint32_t)(h->train_steps * 0x9E3779B97F4A7C15ull >> 32) ^ (uint32_t)(layer_id + 1) * 0x85EBCA77u;
+  const uint32_t thr = (uint32_t)lrintf(h->dropout * 16777216.f);            // keep iff 24 random bits >= rate * 2^24
+  simt::dropout_bf16_kernel<<<grid_for(n8, 256, h->sm_count), 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(a.ptr), n8, seed, thr,
+                                                                           1.f / (1.f - h->dropout));
+  CSB_CUDA_CHECK(cudaGetLastError());
+  h->launches++;
+  return CSB_OK;
+}
+
+static int cnn_forward_body(csb_cnn* h, const float* x, int64_t B, cudaStream_t st, bool training = false) {
+  const bool drop = training && h->dropout > 0.f;
   const int64_t R = B * h->P;
   if (h->bf16) simt::cnn_pack_input_kernel<<<grid_for(R * h->in_p, 256, h->sm_count), 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(h->x0.ptr), B, h->L, h->in_ch, h->in_p);
   else simt::cnn_pack_input_f32_kernel<<<grid_for(R * h->in_p, 256, h->sm_count), 256, 0, st>>>(x, reinterpret_cast<float*>(h->x0.ptr), B, h->L, h->in_ch, h->in_p);
@@ -220,7 +236,9 @@ static int cnn_forward_body(csb_cnn* h, const float* x, int64_t B, cudaStream_t 
   for (int i = 0; i < h->depth; ++i) {
     const ConvLayerInfo &c1 = h->layer[3 * i], &c2 = h->layer[3 * i + 1], &cr = h->layer[3 * i + 2];
     if ((rc = cnn_conv(h, c1, false, *xin, h->h1[i], 0, nullptr, c1.act, h->params + c1.b_off, B, st))) return rc;
+    if (drop && (rc = cnn_dropout(h, h->h1[i], 2 * i, B, st))) return rc;
     if ((rc = cnn_conv(h, c2, false, h->h1[i], h->h2[i], 0, nullptr, c2.act, h->params + c2.b_off, B, st))) return rc;
+    if (drop && (rc = cnn_dropout(h, h->h2[i], 2 * i + 1, B, st))) return rc;
     // out = conv1x1(x_in) + b + relu(conv2)
     if ((rc = cnn_conv(h, cr, false, *xin, h->ob[i], 1, &h->h2[i], CSB_ACT_NONE, h->params + cr.b_off, B, st))) return rc;
     xin = &h->ob[i];
@@ -393,6 +411,29 @@ int csb_cnn_set_loss_weights(csb_cnn* h, const float* w_host) {
   return CSB_OK;
 }
 
+int csb_cnn_set_dropout(csb_cnn* h, float rate, uint32_t seed) {
+  CSB_REQUIRE(h, CSB_EINVAL, "null handle");
+  CSB_REQUIRE(rate >= 0.f && rate < 1.f, CSB_EINVAL, "dropout rate %g outside [0, 1)", (double)rate);
+  CSB_REQUIRE(rate == 0.f || h->bf16, CSB_EUNSUPPORTED, "dropout is implemented for the CSB_BF16 engine (the fp32 engine is the parity mode)");
+  for (int i = 0; i < h->depth && rate > 0.f; ++i)
+    CSB_REQUIRE(h->layer[3 * i].act == CSB_ACT_RELU && h->layer[3 * i + 1].act == CSB_ACT_RELU, CSB_EUNSUPPORTED,
+                "the mask-free dropout backward relies on ReLU (relu'(0) = 0)");
+  h->dropout = rate; h->drop_seed = seed; h->train_steps = 0;
+  return CSB_OK;
+}
+
+int csb_cnn_debug_read_hidden(csb_cnn* h, int which, int block, float* dst, int64_t B, void* stream) {
+  CSB_REQUIRE(h && dst, CSB_EINVAL, "null argument");
+  CSB_REQUIRE(h->bf16, CSB_EUNSUPPORTED, "bf16 engine only");
+  CSB_REQUIRE((which == 1 || which == 2) && block >= 0 && block < h->depth && B >= 1 && B <= h->cfg.max_batch, CSB_EINVAL, "bad selector");
+  const CnnBuf& b = which == 1 ? h->h1[block] : h->h2[block];
+  const int C = h->layer[3 * block].Cout;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  simt::cnn_unpack_hidden_kernel<<<grid_for(B * h->L * C, 256, h->sm_count), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(b.ptr), b.Cp, dst, B, h->L, C);
+  CSB_CUDA_CHECK(cudaGetLastError());
+  return CSB_OK;
+}
+
 int csb_cnn_forward(csb_cnn* h, const float* x, float* y_pred, int64_t B, void* stream) {
   CSB_REQUIRE(h && x && y_pred, CSB_EINVAL, "null argument");
   CSB_REQUIRE(B >= 1 && B <= h->cfg.max_batch, CSB_ESTATE, "batch %lld outside 1..max_batch %lld", (long long)B, (long long)h->cfg.max_batch);
@@ -425,7 +466,9 @@ int csb_cnn_train_step(csb_cnn* h, const float* x, const float* y, int64_t B, fl
   if (grad_scale <= 0.f) grad_scale = 1.f / (float)B;       // the *_adjusted losses average over the batch (weights carry the rest)
   int rc;
   if ((rc = cnn_build_maps(h, B))) return rc;
-  if ((rc = cnn_forward_body(h, x, B, st))) return rc;
+  if ((rc = cnn_forward_body(h, x, B, st, true))) return rc;
+  const float ds = h->dropout > 0.f ? 1.f / (1.f - h->dropout) : 1.f;        // gradient through a kept element of a dropout layer
+  h->train_steps++;
   const int D = h->depth;
   const ConvLayerInfo &co = h->layer[3 * D], &cd = h->layer[3 * D + 1];
   const int64_t R = B * h->P;
@@ -466,7 +509,7 @@ int csb_cnn_train_step(csb_cnn* h, const float* x, const float* y, int64_t B, fl
   };
   auto act_mask = [&](const CnnBuf& g, const CnnBuf& a, CnnBuf& dz, int act) -> int {
     const int64_t n = R * g.Cp;
-    if (h->bf16) simt::act_mask_bf16_kernel<<<grid_for(n / 8, 256, h->sm_count), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g.ptr), reinterpret_cast<const __nv_bfloat16*>(a.ptr), reinterpret_cast<__nv_bfloat16*>(dz.ptr), n / 8, act, 0.f);
+    if (h->bf16) simt::act_mask_bf16_kernel<<<grid_for(n / 8, 256, h->sm_count), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g.ptr), reinterpret_cast<const __nv_bfloat16*>(a.ptr), reinterpret_cast<__nv_bfloat16*>(dz.ptr), n / 8, act, 0.f, ds);
     else simt::act_mask_f32_kernel<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(reinterpret_cast<const float*>(g.ptr), reinterpret_cast<const float*>(a.ptr), reinterpret_cast<float*>(dz.ptr), n, act, 0.f);
     CSB_CUDA_CHECK(cudaGetLastError());
     h->launches++;
@@ -487,7 +530,7 @@ int csb_cnn_train_step(csb_cnn* h, const float* x, const float* y, int64_t B, fl
     if ((rc = act_mask(h->G[g], h->h2[i], h->Z2, c2.act))) return rc;                                       // dz2 = d_out * relu'(h2)
     if ((rc = cnn_wgrad(h, cr, xin, h->G[g], B, tab, max_len, st))) return rc;                               // residual 1x1: dW = xin^T d_out
     if ((rc = cnn_wgrad(h, c2, h->h1[i], h->Z2, B, tab, max_len, st))) return rc;
-    if ((rc = cnn_conv(h, c2, true, h->Z2, h->Z1, 2, &h->h1[i], c1.act, nullptr, B, st))) return rc;       // dz1 = conv^T(dz2; W2) * relu'(h1)
+    if ((rc = cnn_conv(h, c2, true, h->Z2, h->Z1, 2, &h->h1[i], c1.act, nullptr, B, st, h->dropout > 0.f ? ds : 0.f))) return rc;   // dz1 = conv^T(dz2; W2) * relu'(h1) [* 1/(1-p)]
     if ((rc = cnn_wgrad(h, c1, xin, h->Z1, B, tab, max_len, st))) return rc;
     if (i > 0) {
       // d(x_in) = conv^T(dz1; W1) + conv1x1^T(d_out; Wr)

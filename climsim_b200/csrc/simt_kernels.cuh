@@ -993,17 +993,57 @@ cnn_unpack_output_kernel(const float* __restrict__ pred, int ld, float* __restri
   }
 }
 
-// dz = g * act'(a) element-wise (bf16, 8 elements per thread)
+// Inverted dropout in place (Keras Dropout(rate) in training mode, CNN/training/hpo_train.py:170,177): an element is kept with
+// probability 1 - rate and scaled by 1 / (1 - rate), else zeroed.  The keep decisions come from a counter-based generator: one
+// 32-bit mix of (seed, index of the thread's eight elements) starts an LCG whose high 24 bits decide the eight elements, so a
+// (seed, position) pair always gives the same mask (reproducible steps; TensorFlow's own random stream cannot be matched).
+// The backward pass needs no stored mask: a dropped element is zero, and relu'(0) = 0 already blocks its gradient.
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__global__ void __launch_bounds__(256)
+dropout_bf16_kernel(__nv_bfloat16* __restrict__ a, int64_t n8, uint32_t seed, uint32_t keep_threshold, float scale) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 av = reinterpret_cast<const uint4*>(a)[i];
+    const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
+    uint32_t st = mix32(seed ^ mix32((uint32_t)i) ^ (uint32_t)(i >> 32) * 0x9E3779B1u);
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      st = st * 747796405u + 2891336453u;
+      const float lo = (st >> 8) >= keep_threshold ? bf16_lo(aw[j]) * scale : 0.f;
+      st = st * 747796405u + 2891336453u;
+      const float hi = (st >> 8) >= keep_threshold ? bf16_hi(aw[j]) * scale : 0.f;
+      o[j] = pack_bf16x2(lo, hi);
+    }
+    reinterpret_cast<uint4*>(a)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// test hook: hidden activation buffer (bf16, halo layout [B*(L+2), ld]) -> fp32 (B, L, C)
+__global__ void cnn_unpack_hidden_kernel(const __nv_bfloat16* __restrict__ hbuf, int ld, float* __restrict__ y, int64_t B, int L, int C) {
+  const int64_t total = B * L * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int l = (int)((i / C) % L);
+    const int64_t b = i / ((int64_t)C * L);
+    y[i] = __bfloat162float(hbuf[(b * (L + 2) + l + 1) * ld + c]);
+  }
+}
+
+// dz = g * act'(a) * scale element-wise (bf16, 8 elements per thread)
 __global__ void __launch_bounds__(256)
 act_mask_bf16_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ dz,
-                     int64_t n8, int act, float alpha) {
+                     int64_t n8, int act, float alpha, float scale) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
     const uint4 gv = reinterpret_cast<const uint4*>(g)[i], av = reinterpret_cast<const uint4*>(a)[i];
     const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w}, aw[4] = {av.x, av.y, av.z, av.w};
     uint32_t o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      o[j] = pack_bf16x2(bf16_lo(gw[j]) * act_bwd_from_out(act, alpha, bf16_lo(aw[j])), bf16_hi(gw[j]) * act_bwd_from_out(act, alpha, bf16_hi(aw[j])));
+      o[j] = pack_bf16x2(bf16_lo(gw[j]) * act_bwd_from_out(act, alpha, bf16_lo(aw[j])) * scale,
+                         bf16_hi(gw[j]) * act_bwd_from_out(act, alpha, bf16_hi(aw[j])) * scale);
     reinterpret_cast<uint4*>(dz)[i] = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }

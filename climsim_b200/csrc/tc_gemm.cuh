@@ -61,6 +61,7 @@ struct GemmParams {
   int act;                     // CSB_ACT_* for EPI_BIAS_ACT / EPI_DGRAD (activation of the layer whose output is stored / was saved)
   float alpha;
   int head_relu_from;          // EPI_HEAD_*: columns >= this get ReLU (-1: none); otherwise `act` applies
+  float dgrad_scale;           // EPI_DGRAD: extra factor on the result (1 / (1 - p) of a dropout layer behind the activation); 0 = none
   const float* bias;           // [N]
   void* out;                   // bf16 or fp32 [M, ld_out]
   int ld_out;
@@ -433,6 +434,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
     float a[32];
     unpack_bf16x32(sv, a);                          // saved activation (same rows / columns as the output)
     act_bwd32<ELU>(p.act, p.alpha, v, a);
+    if (p.dgrad_scale != 0.f) {                     // kernel-uniform
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= p.dgrad_scale;
+    }
     if (ri.zero_row) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = 0.f;

@@ -372,6 +372,16 @@ class CNNEngine:
         _lib.check(self.lib.csb_cnn_get_grads(self._h, out.ctypes.data), "csb_cnn_get_grads")
         return out
 
+    def set_dropout(self, rate: float, seed: int = 0) -> None:
+        """Dropout behind the two ReLUs of every block in ``train_step`` (the reference: 0.175); ``forward`` never drops."""
+        _lib.check(self.lib.csb_cnn_set_dropout(self._h, float(rate), int(seed) & 0xFFFFFFFF), "csb_cnn_set_dropout")
+
+    def debug_hidden(self, which: int, block: int, B: int) -> torch.Tensor:
+        """Test hook: hidden activation after conv1 / conv2 (``which`` = 1 / 2) of ``block`` from the last step, fp32 (B, levels, width)."""
+        out = torch.empty(B, self.levels, self.width, dtype=torch.float32, device="cuda")
+        _lib.check(self.lib.csb_cnn_debug_read_hidden(self._h, which, block, out.data_ptr(), B, _lib.current_stream_ptr()), "csb_cnn_debug_read_hidden")
+        return out
+
     def set_loss_weights(self, w) -> None:
         w = np.ascontiguousarray(w, dtype=np.float32)
         assert w.size == self.out_ch

@@ -227,6 +227,13 @@ int  csb_cnn_set_params(csb_cnn* h, const float* params_host);
 int  csb_cnn_get_params(csb_cnn* h, float* params_host);
 int  csb_cnn_get_grads(csb_cnn* h, float* grads_host);
 int  csb_cnn_set_loss_weights(csb_cnn* h, const float* w_host);   /* out_ch per-channel weights */
+/* keras.layers.Dropout(rate) behind the two ReLUs of every residual block (hpo_train.py:143,170,177: rate 0.175), active in
+ * csb_cnn_train_step only (csb_cnn_forward is model.predict: no dropout).  Inverted dropout with a counter-based generator keyed by
+ * (seed, training step, layer, position): reproducible, but not TensorFlow's random stream.  CSB_BF16 engines; 0 switches it off. */
+int  csb_cnn_set_dropout(csb_cnn* h, float rate, uint32_t seed);
+/* test hook: the hidden activation after conv1 (which = 1) / conv2 (which = 2) of residual block `block`, as left by the last
+ * csb_cnn_train_step / csb_cnn_forward, unpacked to fp32 (B, levels, width) on the device */
+int  csb_cnn_debug_read_hidden(csb_cnn* h, int which, int block, float* dst, int64_t B, void* stream);
 int  csb_cnn_forward(csb_cnn* h, const float* x, float* y_pred, int64_t B, void* stream);                  /* model.predict */
 int  csb_cnn_train_step(csb_cnn* h, const float* x, const float* y, int64_t B, float grad_scale, float* loss_out, void* stream);
 int  csb_cnn_grad_buffer(csb_cnn* h, float** ptr, size_t* n);

@@ -220,7 +220,9 @@ class CNNRef:
 
     12 x { Conv1D(406,k=3,same) -> ReLU -> Dropout -> Conv1D(406,k=3,same) -> ReLU -> Dropout -> + Conv1D(406,k=1)(block input) }
     -> Conv1D(10, k=1, ELU) -> per-level Dense(2, linear) || Dense(8, relu) -> (B, 60, 10).
-    Dropout is evaluated in inference mode (p = 0): TF's dropout RNG cannot be reproduced.
+    Dropout: inference mode by default; ``forward(x, masks=...)`` applies given multiplicative masks (0 or 1/(1-p)) behind the two
+    ReLUs of every block, which is what keras.layers.Dropout does in training mode with whatever its RNG drew (TF's stream itself
+    cannot be reproduced) -- the GPU test feeds the masks the engine used.
     ``params`` order = Keras ``get_weights()``: per block [Wc1, bc1, Wc2, bc2, Wres, bres], then [Wout, bout,
     Wlin, blin, Wrelu, brelu].
     """
@@ -255,14 +257,19 @@ class CNNRef:
             for b in self.params[1::2]:
                 b.copy_((torch.rand(b.shape, generator=gen, dtype=torch.float64) * 2 - 1).to(self.dtype) * scale)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, masks=None) -> torch.Tensor:
+        """``masks``: optional list (one entry per block) of pairs of (B, 60, width) multipliers for the two Dropout layers."""
         p = self.params
         h = x.to(self.dtype)
         prev = h
         for i in range(self.depth):
             wc1, bc1, wc2, bc2, wr, br = p[6 * i: 6 * i + 6]
             h = torch.relu(conv1d_same_cl(h, wc1, bc1))
+            if masks is not None:
+                h = h * masks[i][0]
             h = torch.relu(conv1d_same_cl(h, wc2, bc2))
+            if masks is not None:
+                h = h * masks[i][1]
             h = h + conv1d_same_cl(prev, wr, br)
             prev = h
         wo, bo, wl, bl, wrl, brl = p[6 * self.depth: 6 * self.depth + 6]

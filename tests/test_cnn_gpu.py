@@ -106,3 +106,50 @@ def test_cnn_fp32_parity(depth, width, B):
     # MAE loss value in fp32
     ref2, eng2, x2, y2 = _setup(depth, width, B, "mae", dtype="fp32")
     assert abs(eng2.train_step(x2.cuda(), y2.cuda()).item() - M.mae_adjusted(y2, ref2(x2)).item()) <= 1e-5 * M.mae_adjusted(y2, ref2(x2)).item()
+
+
+def test_cnn_dropout_training_step_against_oracle_with_the_same_masks():
+    """Dropout(rate) behind both ReLUs of every block in the training step (hpo_train.py:170,177).  TensorFlow's random stream
+    cannot be reproduced, so the check is: read back the hidden activations the engine produced, take the masks from them, and run
+    the oracle with exactly those masks -- loss and every gradient tensor must agree as in the dropout-free test; the drop rate,
+    the 1/(1-p) scaling, step-to-step mask changes, seed reproducibility and the dropout-free inference path are checked too."""
+    depth, width, B, rate = 2, 64, 6, 0.3
+    ref, eng, x, y = _setup(depth, width, B, "mse")
+    eng.set_dropout(rate, seed=123)
+    loss = eng.train_step(x.cuda(), y.cuda()).item()
+    hid = [[eng.debug_hidden(w, i, B).cpu() for w in (1, 2)] for i in range(depth)]
+    g_got = eng.split_flat(eng.get_grads_flat())
+    s = 1.0 / (1.0 - rate)
+    masks = [[(h != 0).float() * s for h in blk] for blk in hid]         # a zero that came from the ReLU has zero gradient anyway
+    want = M.mse_adjusted(y, ref.forward(x, masks=masks))
+    want.backward()
+    assert abs(loss - want.item()) <= 2e-2 * abs(want.item()), (loss, want.item())
+    g_ref = eng.split_flat(_flat([p.grad for p in ref.params]))
+    for i, (a, b) in enumerate(zip(g_got, g_ref)):
+        nb = np.linalg.norm(b)
+        if nb > 0:
+            assert np.linalg.norm(a - b) / nb <= 0.12, (i, a.shape, np.linalg.norm(a - b) / nb)
+    # drop statistics on the first hidden layer, whose pre-dropout value does not depend on any mask
+    with torch.no_grad():
+        h1_ref = torch.relu(M.conv1d_same_cl(x, ref.params[0], ref.params[1]))
+    alive = h1_ref > 1e-2
+    n_alive = alive.float().sum().item()
+    dropped = ((hid[0][0] == 0) & alive).float().sum().item() / n_alive
+    assert abs(dropped - rate) <= 4 * np.sqrt(rate * (1 - rate) / n_alive) + 1e-3, (dropped, n_alive)
+    kept = alive & (hid[0][0] != 0)
+    ratio = (hid[0][0][kept] / h1_ref[kept]).median().item()
+    assert abs(ratio - s) <= 2e-2 * s                                    # inverted dropout: kept activations scaled by 1 / (1 - p)
+    # the next step draws new masks; the same seed replays the same sequence; inference never drops
+    eng.train_step(x.cuda(), y.cuda())
+    assert ((eng.debug_hidden(1, 0, B).cpu() == 0) != (hid[0][0] == 0)).float().mean().item() > 0.1
+    eng.set_dropout(rate, seed=123)                                      # also rewinds the step counter of the mask sequence
+    eng.train_step(x.cuda(), y.cuda())
+    assert torch.equal(eng.debug_hidden(1, 0, B).cpu(), hid[0][0])
+    p_inf = eng.forward(x.cuda()).cpu()
+    with torch.no_grad():
+        p_ref = ref.forward(x)
+    assert (p_inf - p_ref).abs().max().item() <= 3e-2 * p_ref.abs().max().item()
+    # rate 0 is the dropout-free step again
+    eng.set_dropout(0.0)
+    l0 = eng.train_step(x.cuda(), y.cuda()).item()
+    assert abs(l0 - M.mse_adjusted(y, ref(x)).item()) <= 2e-2 * abs(l0)
