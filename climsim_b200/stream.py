@@ -128,6 +128,8 @@ class NpyColumnStream:
         if not order:
             return
         main = torch.cuda.current_stream(self.device)
+        # the window buffers may still be read by gathers of a previous epoch() (or of one abandoned half-way): order after them
+        self._copy_stream.wait_stream(main)
         reader: Optional[threading.Thread] = None
 
         def start_read(k: int) -> threading.Thread:
