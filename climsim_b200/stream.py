@@ -112,6 +112,7 @@ class NpyColumnStream:
         self._copy_stream = torch.cuda.Stream(device=self.device)
         self._copied = [torch.cuda.Event() for _ in range(2)]
         self._consumed = [torch.cuda.Event() for _ in range(2)]
+        self._reader: Optional[threading.Thread] = None
 
     def __len__(self) -> int:
         return self.plan.batches_per_epoch()
@@ -130,12 +131,15 @@ class NpyColumnStream:
         main = torch.cuda.current_stream(self.device)
         # the window buffers may still be read by gathers of a previous epoch() (or of one abandoned half-way): order after them
         self._copy_stream.wait_stream(main)
+        if self._reader is not None:                                        # reader of an abandoned epoch: let it finish with its slot
+            self._reader.join()
         reader: Optional[threading.Thread] = None
 
         def start_read(k: int) -> threading.Thread:
             s, ln = wins[order[k]]
             t = threading.Thread(target=self._read, args=(k & 1, s, ln), daemon=True)
             t.start()
+            self._reader = t
             return t
 
         reader = start_read(0)
