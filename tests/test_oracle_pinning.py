@@ -243,3 +243,40 @@ def test_manual_backward_matches_autograd():
         assert l2.item() == pytest.approx(loss.item(), rel=1e-6)
         for p, gm in zip(ref.params, grads):
             torch.testing.assert_close(gm, p.grad, rtol=1e-4, atol=1e-9)
+
+
+def test_keras_adam_algebra_against_torch_adam_with_eps_zero():
+    """The Keras form (step size lr*sqrt(1-b2^t)/(1-b1^t), epsilon outside the bias correction) and torch.optim.Adam's form
+    ((m/bc1)/(sqrt(v/bc2)+eps)) are the same update when epsilon = 0: an independent implementation (PyTorch's own optimizer) pins
+    the moment updates and the bias-correction algebra of the restatement; only the epsilon placement is Keras-specific."""
+    gen = torch.Generator().manual_seed(0)
+    w0 = torch.randn(257, generator=gen, dtype=torch.float64)
+    pk, m, v = [w0.clone()], [torch.zeros(257, dtype=torch.float64)], [torch.zeros(257, dtype=torch.float64)]
+    pt = torch.nn.Parameter(w0.clone())
+    opt = torch.optim.Adam([pt], lr=3e-3, betas=(0.9, 0.999), eps=0.0)
+    for t in range(1, 8):
+        g = torch.randn(257, generator=gen, dtype=torch.float64)
+        M.keras_adam_step(pk, [g], m, v, t, lr=3e-3, eps=0.0)
+        pt.grad = g.clone()
+        opt.step()
+        torch.testing.assert_close(pk[0], pt.detach(), rtol=1e-12, atol=1e-14)
+    # with the Keras default epsilon the two differ by the epsilon placement only: tiny where |g| >> eps
+    pk2, m2, v2 = [w0.clone()], [torch.zeros(257, dtype=torch.float64)], [torch.zeros(257, dtype=torch.float64)]
+    M.keras_adam_step(pk2, [torch.ones(257, dtype=torch.float64)], m2, v2, 1, lr=3e-3, eps=1e-7)
+    assert (pk2[0] - (w0 - 3e-3)).abs().max().item() < 1e-8
+
+
+def test_conv1d_same_and_activations_against_torch_functional():
+    """conv1d_same_cl (Keras Conv1D(padding='same'), channels-last, kernel (k, Cin, Cout)) == torch.nn.functional.conv1d with
+    padding='same' on the transposed layout; ELU(alpha=1) / LeakyReLU(0.15) as the oracle models use them == torch's."""
+    gen = torch.Generator().manual_seed(2)
+    for k in (1, 3, 5):
+        x, w, b = torch.randn(3, 60, 6, generator=gen), torch.randn(k, 6, 9, generator=gen), torch.randn(9, generator=gen)
+        want = torch.nn.functional.conv1d(x.transpose(1, 2), w.permute(2, 1, 0), b, padding="same").transpose(1, 2)
+        torch.testing.assert_close(M.conv1d_same_cl(x, w, b), want, rtol=1e-5, atol=1e-5)
+    ref = M.MLPRef(units=(32,), act="leakyrelu", seed=0)
+    x = torch.randn(4, 124, generator=gen)
+    h = torch.nn.functional.leaky_relu(x @ ref.params[0] + ref.params[1], 0.15)
+    h = torch.nn.functional.leaky_relu(h @ ref.params[2] + ref.params[3], 0.15)
+    want = torch.cat([h @ ref.params[4] + ref.params[5], torch.relu(h @ ref.params[6] + ref.params[7])], dim=1)
+    torch.testing.assert_close(ref(x), want, rtol=1e-5, atol=1e-6)
