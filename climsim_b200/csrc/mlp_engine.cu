@@ -1009,11 +1009,11 @@ static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st,
       const float* gamma = h->params + li.g_off;
       if (h->bf16 && li.Np <= 256 * simt::LN_MAXP) {
         // one fused kernel: du -> dz and the (dgamma, dbeta) partials of each block
-        S = (int)std::max<int64_t>(1, std::min<int64_t>(2 * h->sm_count, ceil_div(B, 8)));
-        const size_t smem = (size_t)8 * li.Np * 4;
+        S = (int)std::max<int64_t>(1, std::min<int64_t>(2 * h->sm_count, ceil_div(B, 8)));      // two resident blocks per SM
+        const size_t smem = (size_t)(1 + 2 * 8) * 256 * simt::LN_MAXP * 4;        // gamma + (dgamma, dbeta) per warp
         static bool attr_set = false;
         if (!attr_set) {
-          CSB_CUDA_CHECK(cudaFuncSetAttribute(simt::ln_bwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 256 * simt::LN_MAXP * 4));
+          CSB_CUDA_CHECK(cudaFuncSetAttribute(simt::ln_bwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           attr_set = true;
         }
         simt::ln_bwd_bf16_kernel<<<S, 256, smem, st>>>(dz16(h, l), reinterpret_cast<const __nv_bfloat16*>(h->zbuf[l]), li.Np, gamma, h->ln_stats[l],

@@ -479,7 +479,7 @@ __device__ __forceinline__ void ln_load8f(const float* p, float (&v)[8]) {
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 ln_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ z, __nv_bfloat16* __restrict__ a, int ld, const float* __restrict__ gamma,
                    const float* __restrict__ beta, float* __restrict__ stats, int64_t M, int N, int Np, int act, float alpha, float eps) {
   const int lane = threadIdx.x & 31;
@@ -523,22 +523,28 @@ ln_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ z, __nv_bfloat16* __restric
 }
 
 // du -> dz in place (g = du * gamma; dz = rstd * (g - mean(g) - xhat * mean(g * xhat))) fused with the parameter gradients
-// dgamma = sum_rows du * xhat, dbeta = sum_rows du: one partial pair per block at partials + blockIdx.x * 2 * Np
-__global__ void __launch_bounds__(256)
+// dgamma = sum_rows du * xhat, dbeta = sum_rows du: one partial pair per block at partials + blockIdx.x * 2 * Np.
+// The running column sums live in shared memory, one private slice per warp in a lane-major layout (element j of pass p of lane l at
+// (p*8 + j)*32 + l: conflict-free scalar accesses, no atomics), as does gamma: that keeps the kernel at two blocks per SM, which a
+// streaming kernel with one row in flight per warp needs to cover the HBM latency (the first version carried the sums in registers:
+// 200 registers, one block per SM, 2.2 TB/s).
+__global__ void __launch_bounds__(256, 2)
 ln_bwd_bf16_kernel(__nv_bfloat16* __restrict__ du_dz, const __nv_bfloat16* __restrict__ z, int ld, const float* __restrict__ gamma,
                    const float* __restrict__ stats, int64_t M, int N, int Np, float* __restrict__ partials) {
-  extern __shared__ float red[];                     // [8 warps][Np]
+  extern __shared__ float sm[];                      // gamma [LN_MAXP*256] | per warp: dgamma [LN_MAXP*256], dbeta [LN_MAXP*256]
+  constexpr int W = LN_MAXP * 256;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* gm = sm;
+  float* ag = sm + W + warp * 2 * W;
+  float* ab = ag + W;
+  for (int i = threadIdx.x; i < W; i += 256) {       // lane-major copy of gamma: slot (p*8 + j)*32 + l <- column p*256 + l*8 + j
+    const int l = i & 31, pj = i >> 5, c = (pj >> 3) * 256 + l * 8 + (pj & 7);
+    gm[i] = c < N ? gamma[c] : 0.f;
+  }
+  for (int i = lane; i < 2 * W; i += 32) ag[i] = 0.f;
+  __syncthreads();
   const int64_t warps = (int64_t)gridDim.x * 8;
   const float inv_n = 1.f / (float)N;
-  float ag[LN_MAXP][8], ab[LN_MAXP][8], gm[LN_MAXP][8];
-#pragma unroll
-  for (int p = 0; p < LN_MAXP; ++p) {
-    const int c = p * 256 + lane * 8;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { ag[p][j] = 0.f; ab[p][j] = 0.f; gm[p][j] = 0.f; }
-    if (c < Np) ln_load8f(gamma + c, gm[p]);
-  }
   for (int64_t r = blockIdx.x * (int64_t)8 + warp; r < M; r += warps) {
     const float mean = stats[2 * r], rstd = stats[2 * r + 1];
     float du[LN_MAXP][8], xh[LN_MAXP][8];
@@ -552,13 +558,15 @@ ln_bwd_bf16_kernel(__nv_bfloat16* __restrict__ du_dz, const __nv_bfloat16* __res
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const bool ok = c + j < N;
+        const int slot = (p * 8 + j) * 32 + lane;
         xh[p][j] = ok ? (xh[p][j] - mean) * rstd : 0.f;
         du[p][j] = ok ? du[p][j] : 0.f;
-        const float g = du[p][j] * gm[p][j];
+        const float g = du[p][j] * gm[slot];
         s1 += g;
         s2 += g * xh[p][j];
-        ag[p][j] += du[p][j] * xh[p][j];
-        ab[p][j] += du[p][j];
+        ag[slot] += du[p][j] * xh[p][j];
+        ab[slot] += du[p][j];
+        du[p][j] = g;                                // from here on: du holds g = du * gamma
       }
     }
     s1 = warp_sum(s1) * inv_n;
@@ -569,28 +577,20 @@ ln_bwd_bf16_kernel(__nv_bfloat16* __restrict__ du_dz, const __nv_bfloat16* __res
       if (c < Np) {
         float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (c + j < N) ? rstd * (du[p][j] * gm[p][j] - s1 - xh[p][j] * s2) : 0.f;
+        for (int j = 0; j < 8; ++j) o[j] = (c + j < N) ? rstd * (du[p][j] - s1 - xh[p][j] * s2) : 0.f;
         ln_store8(du_dz + r * ld + c, o);
       }
     }
   }
-  // block reduction over the eight warps, warp 0 first (fixed order), once for dgamma and once for dbeta
-#pragma unroll
-  for (int which = 0; which < 2; ++which) {
-    __syncthreads();
-#pragma unroll
-    for (int p = 0; p < LN_MAXP; ++p) {
-      const int c = p * 256 + lane * 8;
-      if (c < Np) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) red[warp * Np + c + j] = which == 0 ? ag[p][j] : ab[p][j];
-      }
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < Np; c += 256) {
+  // block reduction over the eight warps, warp 0 first (fixed order); slot -> column as above
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * W; i += 256) {
+    const int which = i / W, s_ = i - which * W;
+    const int l = s_ & 31, pj = s_ >> 5, c = (pj >> 3) * 256 + l * 8 + (pj & 7);
+    if (c < Np) {
       float t = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) t += red[w * Np + c];
+      for (int w = 0; w < 8; ++w) t += sm[W + w * 2 * W + i];
       partials[(size_t)blockIdx.x * 2 * Np + which * Np + c] = t;
     }
   }

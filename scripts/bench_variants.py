@@ -46,9 +46,15 @@ def run(name, in_dim, layers, rule, layernorm=None, loss="mse", head_relu_from=-
 
 
 if __name__ == "__main__":
-    run("HSR mean net 4x1024 LayerNorm", 124, [(1024, "relu", 0.0)] * 4 + [(128, "none", 0.0)], "adam_torch", layernorm=[True] * 4 + [False])
+    only = sys.argv[2] if len(sys.argv) > 2 else ""          # python scripts/bench_variants.py 131072 hsr   (one variant, e.g. under ncu)
+    if only:
+        STEPS, WARM = 4, 3
+    if only in ("", "hsr"):
+        run("HSR mean net 4x1024 LayerNorm", 124, [(1024, "relu", 0.0)] * 4 + [(128, "none", 0.0)], "adam_torch", layernorm=[True] * 4 + [False])
     d = 463
     w = [d, d, d // 2, d // 4, d // 8, d // 16, 5, d // 16, d // 8, d // 4, d // 2, d, d]
-    run("ED 463-5-463", 124, [(x, "relu", 0.0) for x in w] + [(128, "elu", 0.0)], "adam_keras")
-    run("online MLP 557-[384,1024,640]-368 Huber", 557, [(384, "relu", 0.0), (1024, "relu", 0.0), (640, "relu", 0.0), (368, "none", 0.0)],
+    if only in ("", "ed"):
+        run("ED 463-5-463", 124, [(x, "relu", 0.0) for x in w] + [(128, "elu", 0.0)], "adam_keras")
+    if only in ("", "online"):
+        run("online MLP 557-[384,1024,640]-368 Huber", 557, [(384, "relu", 0.0), (1024, "relu", 0.0), (640, "relu", 0.0), (368, "none", 0.0)],
         "adam_torch", loss="huber", head_relu_from=360)
