@@ -858,13 +858,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// gemm_nt_kernel: D[M,N] = sum_r A[r, m] * B[r, n]; both operands MN-major; split over r (blockIdx.y).
+// gemm_nt_kernel: D[M,N] = sum_r A[r, m] * B[r, n]; both operands MN-major; split over r (blockIdx.y, or NtParams.splits_narrow).
 // Weight gradient dW = H^T dZ.  The epilogue warps, idle during the mainloop, reduce the dZ tiles that pass through shared
 // memory over their rows (every m-tile takes its share of the row blocks): that is the bias gradient, at no extra HBM traffic.
 // ---------------------------------------------------------------------------------------------------------------
 struct NtParams {
   int M, N, R;             // M, N feature dims (multiples of 64), R rows to contract
   int rb_per_split;        // 64-row blocks per split
+  // Uneven split counts (splits_narrow > 0; the grid is then one-dimensional): the tiles of a half-width last n-block do half
+  // the work per row block, so they take `splits_narrow` = ceil(splits / 2) splits of `rb_per_split_narrow` row blocks -- as long
+  // as a full-width tile's split -- and the CTAs saved go into a larger `splits` for everybody.  A narrow tile's CTA also writes
+  // the zeros of the split slots it leaves unused, so that the reduction keeps one slot count per layer.
+  int splits, splits_narrow, rb_per_split_narrow;
   float* out;              // partials: out + split * split_stride + m * ld_out + n
   int ld_out;
   size_t split_stride;
@@ -911,20 +916,38 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_n_blocks = (p.N + BN - 1) / BN;
-  const int tile = (int)(blockIdx.x / CG);                               // both CTAs of a pair share the tile
-  const int m_tile = tile / num_n_blocks;
-  const int m0 = (m_tile * CG + (int)cta_rank) * BM, n0 = (tile % num_n_blocks) * BN;
+  // bias gradient: every m-tile takes the row blocks i with i % num_m_tiles == its index, so no CTA is a straggler;
+  // partial index = split * num_m_tiles + m-tile
+  const int num_m_tiles = ((p.M + BM - 1) / BM + CG - 1) / CG;
+  // (m-tile, n-block, split) of this CTA (both CTAs of a pair share them).  Uniform mode: blockIdx.x = tile, blockIdx.y = split.
+  // Uneven mode: all (split, full-width tile) pairs first, split-major, then the (split, narrow tile) pairs.
+  int m_tile, n_blk, split;
+  bool narrow_tile = false;
+  if (p.splits_narrow > 0) {
+    const int lin = (int)(blockIdx.x / CG), tiles_wide = num_m_tiles * (num_n_blocks - 1), wide_ctas = tiles_wide * p.splits;
+    if (lin < wide_ctas) {
+      split = lin / tiles_wide;
+      const int tw = lin - split * tiles_wide;
+      m_tile = tw / (num_n_blocks - 1); n_blk = tw - m_tile * (num_n_blocks - 1);
+    } else {
+      const int ln = lin - wide_ctas;
+      split = ln / num_m_tiles; m_tile = ln - split * num_m_tiles; n_blk = num_n_blocks - 1;
+      narrow_tile = true;
+    }
+  } else {
+    const int tile = (int)(blockIdx.x / CG);
+    m_tile = tile / num_n_blocks; n_blk = tile - m_tile * num_n_blocks; split = (int)blockIdx.y;
+  }
+  const int m0 = (m_tile * CG + (int)cta_rank) * BM, n0 = n_blk * BN;
   const int n_valid = min(BN, p.N - n0);
   const int nb0 = n0 + (int)cta_rank * (n_valid / CG);                   // first dZ column this CTA loads
   // CG == 2 always loads both 64-wide m chunks (columns past M are zero-filled by TMA) so that the transaction size is uniform
   const int a_chunks = (CG == 2) ? 2 : (min(BM, p.M - m0) + 63) / 64, b_chunks = (n_valid / CG + 63) / 64;
   const int num_rb = (p.R + BK - 1) / BK;
-  const int rb_begin = blockIdx.y * p.rb_per_split;
-  const int rb_end = min(num_rb, rb_begin + p.rb_per_split);
+  const int rps = narrow_tile ? p.rb_per_split_narrow : p.rb_per_split;
+  const int rb_begin = min(num_rb, split * rps);
+  const int rb_end = min(num_rb, rb_begin + rps);
   const int nrb = max(0, rb_end - rb_begin);
-  // bias gradient: every m-tile takes the row blocks i with i % num_m_tiles == its index, so no CTA is a straggler;
-  // partial index = split * num_m_tiles + m-tile
-  const int num_m_tiles = ((p.M + BM - 1) / BM + CG - 1) / CG;
   const bool do_colsum = p.colsum_out != nullptr;                       // kernel-uniform
   const int colsum_warps = do_colsum ? min(4, b_chunks) : 0;            // warp w sums the columns of this CTA's chunk w
 
@@ -1024,14 +1047,21 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         acc8[j] += __shfl_xor_sync(0xffffffffu, acc8[j], 16);
       }
       if (rs == 0) {
-        float* dst = p.colsum_out + ((size_t)blockIdx.y * num_m_tiles + m_tile) * p.colsum_stride + nb0 + 64 * warp + 8 * lp;
+        float* dst = p.colsum_out + ((size_t)split * num_m_tiles + m_tile) * p.colsum_stride + nb0 + 64 * warp + 8 * lp;
         *reinterpret_cast<float4*>(dst) = make_float4(acc8[0], acc8[1], acc8[2], acc8[3]);
         *reinterpret_cast<float4*>(dst + 4) = make_float4(acc8[4], acc8[5], acc8[6], acc8[7]);
+        if (narrow_tile) {                            // the split slots this narrow tile leaves unused hold zeros
+          for (int zs = split + p.splits_narrow; zs < p.splits; zs += p.splits_narrow) {
+            float* z = p.colsum_out + ((size_t)zs * num_m_tiles + m_tile) * p.colsum_stride + nb0 + 64 * warp + 8 * lp;
+            *reinterpret_cast<float4*>(z) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(z + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
       }
     }
     // ---- weight-gradient tile
     const int row = m0 + warp * 32 + lane;
-    float* out = p.out + (size_t)blockIdx.y * p.split_stride + (size_t)row * p.ld_out + n0;
+    float* out = p.out + (size_t)split * p.split_stride + (size_t)row * p.ld_out + n0;
     if (nrb > 0) {
       mbar_wait(tfull_bar, 0);
       tc_fence_after();
@@ -1060,6 +1090,15 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       bulk_wait_read_all();                         // shared memory must stay intact until the copy engine has read it
     } else if (row < p.M) {
       for (int c = 0; c < n_valid; c += 4) *reinterpret_cast<float4*>(out + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (narrow_tile) {                               // zero partials for the unused split slots of this narrow tile, a row per instruction
+      for (int zs = split + p.splits_narrow; zs < p.splits; zs += p.splits_narrow) {
+        float* z = p.out + (size_t)zs * p.split_stride + (size_t)(m0 + warp * 32) * p.ld_out + n0;
+        for (int r = 0; r < 32; ++r) {
+          if (m0 + warp * 32 + r >= p.M) break;
+          for (int c = 4 * lane; c < n_valid; c += 128) *reinterpret_cast<float4*>(z + (size_t)r * p.ld_out + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
     }
   }
 

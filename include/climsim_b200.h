@@ -291,7 +291,9 @@ void csb_test_set_stats(void* dev_u64x8_per_cta);   /* micro-benchmark: per-CTA 
  * contraction over rows; colsum (optional, [splits * ceil(M/128)][N]) receives partial column sums of B (bias gradient). */
 int  csb_test_gemm_nt(const uint16_t* A, const uint16_t* B, float* C, float* colsum, int M, int N, int Kr, int splits, void* stream);
 /* the same with an explicit tile policy: cg = 1 single CTAs, 2 CTA pairs (cta_group::2, needs N % 128 == 0), 0 = the engine's choice;
- * *m_tiles_out = bias-gradient partial rows written per split */
+ * *m_tiles_out = bias-gradient partial rows written per split.  splits < 0: |splits| split slots with the uneven geometry the
+ * engine uses when the last n-block has half width (N = k * 256 + 128): that block takes ceil(|splits| / 2) longer splits and its
+ * CTAs zero the slots it leaves unused. */
 int  csb_test_gemm_nt_cg(const uint16_t* A, const uint16_t* B, float* C, float* colsum, int M, int N, int Kr, int splits, int cg,
                          int* m_tiles_out, void* stream);
 

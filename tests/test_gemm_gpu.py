@@ -140,3 +140,35 @@ def test_linear_fwd_engine_policy(M, N, K, act):
     assert not torch.isnan(out.float()).any()
     err = (out.float() - ref).abs().max().item()
     assert err <= 1e-2 * ref.abs().max().item(), err          # one bf16 rounding of the result
+
+
+@pytest.mark.parametrize("M,N,R,splits,cg", [
+    (768, 640, 5000, 9, 2),     # dW of layer 1 with the engine's geometry: 9 slots, the 128-wide block takes 5 longer splits
+    (640, 640, 4096, 8, 2),     # even slot count, odd m-block count
+    (512, 640, 70000, 14, 2),   # layer 3 at a batch with ragged row blocks
+    (256, 384, 300, 7, 1),      # single CTAs, 256 + 128 columns, more slots than the narrow block has row blocks for
+    (768, 640, 64, 2, 2),       # one row block in total: most CTAs only write zeros
+])
+def test_gemm_nt_uneven_splits(M, N, R, splits, cg):
+    """Uneven split counts for a half-width last n-block (NtParams.splits_narrow): every slot of every column is written (the NaN
+    fill would survive otherwise), the slots sum to the product, the bias-gradient partials to the column sums."""
+    import ctypes
+    lib, L = _lib()
+    A = _bf16_operand(R, M, 9)
+    B = _bf16_operand(R, N, 10)
+    Cout = torch.full((splits, M, N), float("nan"), device="cuda")
+    m_blocks = (M + 127) // 128
+    colsum = torch.full((splits * m_blocks, N), float("nan"), device="cuda")
+    m_tiles = ctypes.c_int(0)
+    L.check(lib.csb_test_gemm_nt_cg(A.data_ptr(), B.data_ptr(), Cout.data_ptr(), colsum.data_ptr(), M, N, R, -splits, cg,
+                                    ctypes.byref(m_tiles), None), "csb_test_gemm_nt_cg")
+    torch.cuda.synchronize()
+    assert not torch.isnan(Cout).any()
+    ref = A.float().t() @ B.float()
+    assert (Cout.sum(dim=0) - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
+    narrow_slots = (splits + 1) // 2
+    assert (Cout[narrow_slots:, :, N - 128:] == 0).all()                      # the slots the narrow block leaves unused hold zeros
+    cs = colsum[: splits * m_tiles.value]
+    assert not torch.isnan(cs).any()
+    cs_ref = B.float().sum(dim=0)
+    assert (cs.sum(dim=0) - cs_ref).abs().max().item() <= 1e-3 * max(cs_ref.abs().max().item(), 1.0)
