@@ -232,7 +232,9 @@ static int launch_nt(const CUtensorMap& ta, const CUtensorMap& tb, const tc::NtP
 static bool g_use_nt_pairs = true;  // CSB_NO_NT_PAIRS=1: single-CTA weight-gradient tiles (debugging aid)
 // CSB_NT_NARROW=1 (opt-in): uneven split counts for a half-width last n-block (NtParams.splits_narrow).  Correct (tests/test_gemm_gpu.py)
 // but measured slower on the MLP_v1 step on one B200 -- 0.913 against 0.890 ms with the 2/3 rule, 0.902 against 0.860 ms with 1/2 --
-// so the default keeps one split count per layer; why the balanced geometry loses is open (round 2).
+// so the default keeps one split count per layer.  Likely cause: with one split count all tiles of a split walk the same row range
+// together, so an activation / dZ row block is fetched from HBM once and hit in L2 by the sibling tiles; narrow tiles with their own
+// (longer) row ranges read their operands at other times and re-fetch them from HBM (+~100 MB on a launch that already moves 130-180 MB).
 static bool g_use_nt_narrow = false;
 static inline int nt_cta_group(int M, int N) { return (g_use_nt_pairs && N % 128 == 0 && N > 128 && M > 128) ? 2 : 1; }   // 128-wide layers: measured no gain
 // Splits of a half-width tile for S splits of the full-width ones: a row block of the narrow tile costs half the MMA cycles but
