@@ -108,3 +108,44 @@ def test_glorot_flat_blob_shape_and_limits():
     assert flat.size == sum(k * n + n for k, n in dims)
     w0 = flat[:124 * 768]
     assert np.abs(w0).max() <= np.sqrt(6.0 / (124 + 768)) and flat[124 * 768:124 * 768 + 768].max() == 0
+
+
+def _stream_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from climsim_b200.stream import StreamPlan
+    from climsim_b200.trainer import Trainer
+    torch.set_num_threads(1)
+    x, y = _batch(96)
+    plan = StreamPlan(96, batch_size=16, window=32, seed=5, rank=rank, world=world)
+    eng = OracleEngine()
+    tr = Trainer(eng, rule="adam_keras", lr=1e-3)
+    losses = [tr.step(x[rows], y[rows]) for rows in plan.epoch_rows(epoch=0)]
+    if rank == 0:
+        np.savez(out, flat=eng.flat(), losses=np.array(losses))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_stream_shares_train_like_one_process_on_the_joined_batches(tmp_path):
+    """StreamPlan's per-rank shares feeding the data-parallel Trainer: rank r steps on the batches of its own share; the result equals
+    one process stepping on the concatenation of the two ranks' k-th batches (the global batch of step k)."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "dp_stream.npz")
+    mp.spawn(_stream_worker, args=(2, port, out), nprocs=2, join=True)
+    got = np.load(out)
+    from climsim_b200.stream import StreamPlan
+    from climsim_b200.trainer import Trainer
+    x, y = _batch(96)
+    plans = [StreamPlan(96, batch_size=16, window=32, seed=5, rank=r, world=2) for r in range(2)]
+    assert plans[0].hi == plans[1].lo == 48 and plans[0].batches_per_epoch() == plans[1].batches_per_epoch() == 3
+    eng = OracleEngine()
+    tr = Trainer(eng, rule="adam_keras", lr=1e-3)
+    losses = []
+    for r0, r1 in zip(plans[0].epoch_rows(0), plans[1].epoch_rows(0)):
+        rows = np.concatenate([r0, r1])
+        losses.append(tr.step(x[rows], y[rows]))
+    np.testing.assert_allclose(got["losses"], losses, rtol=1e-5)
+    np.testing.assert_allclose(got["flat"], eng.flat(), rtol=0, atol=2e-6)
