@@ -111,3 +111,84 @@ class Trainer:
             self.synchronize()
             return float(slot.item())
         return float(self._loss.item()) if return_loss else self._loss
+
+    # ------------------------------------------------------------------------------------------------------------------ model.fit
+    def save_checkpoint(self, path: str) -> None:
+        """Parameters + optimizer state + step counters: the content of Keras' ``ModelCheckpoint(save_weights_only=False)`` file."""
+        m, v, step = self.engine.get_opt_state()
+        with open(path, "wb") as f:                 # a file object: np.savez would append ".npz" to a bare path
+            np.savez(f, params=self.engine.get_params_flat(), m=m, v=v, step=np.int64(step), iteration=np.int64(self.iteration))
+
+    def load_checkpoint(self, path: str) -> None:
+        ck = np.load(path)
+        self.engine.set_params_flat(ck["params"])
+        self.engine.set_opt_state(ck["m"], ck["v"], int(ck["step"]))
+        self.iteration = int(ck["iteration"])
+
+    def evaluate(self, data) -> float:
+        """Mean squared error over ``data`` (an iterable of ``(x, y)``; exact mean over all elements): Keras' ``val_loss`` for
+        ``loss='mse'`` (hpo_baseline_v1.py:127-129).  One D2H read at the end."""
+        se, n = None, 0
+        for x, y in data:
+            d = self.engine.forward(x) - y
+            s = (d * d).sum()
+            se = s if se is None else se + s
+            n += d.numel()
+        return float(se.item()) / max(n, 1) if se is not None else float("nan")
+
+    def fit(self, train, epochs: int, validation_data=None, checkpoint_best: Optional[str] = None, checkpoint_last: Optional[str] = None,
+            csv_log: Optional[str] = None, early_stopping_patience: Optional[int] = None, initial_epoch: int = 0, verbose: int = 2) -> dict:
+        """``model.fit(tds, epochs=.., validation_data=tds_val, callbacks=[checkpoint_best, checkpoint_last, csv_logger, earlystop])`` as
+        the reference's retraining script drives it (baseline_v1/step2_retrain/step2_retrain.py:252-286):
+
+        * ``train`` / ``validation_data``: objects with ``.epoch(e)`` yielding ``(x, y)`` (``NpyColumnStream``: reshuffled every
+          epoch like ``shuffle(reshuffle_each_iteration=True)``) or plain re-iterable collections of ``(x, y)``;
+        * ``loss`` of an epoch = mean of its batch losses (what Keras prints), accumulated on the device: one D2H read per epoch;
+        * ``checkpoint_best``: saved when ``val_loss`` improves (``ModelCheckpoint(monitor='val_loss', save_best_only=True)``);
+          ``checkpoint_last``: saved every epoch; ``csv_log``: ``epoch,loss,val_loss`` rows appended (``CSVLogger(append=True)``);
+          ``early_stopping_patience``: stop after that many epochs without a new best ``val_loss`` (``EarlyStopping('val_loss', patience)``).
+
+        Returns ``{"loss": [...], "val_loss": [...], "stopped_epoch": e or None}`` (Keras' ``History.history`` plus the stop epoch)."""
+        history = {"loss": [], "val_loss": [], "stopped_epoch": None}
+        best, wait = float("inf"), 0
+        if csv_log is not None:
+            import os
+            if not os.path.exists(csv_log) or os.path.getsize(csv_log) == 0:
+                with open(csv_log, "a") as f:
+                    f.write("epoch,loss,val_loss\n")
+        for epoch in range(initial_epoch, epochs):
+            batches = train.epoch(epoch) if hasattr(train, "epoch") else train
+            total, nb = None, 0
+            for x, y in batches:
+                l = self.step(x, y, return_loss=False)
+                l = l if isinstance(l, torch.Tensor) else torch.as_tensor(l)
+                total = l.detach().clone().reshape(()) if total is None else total + l.detach().reshape(())
+                nb += 1
+            if self.world > 1 and total is not None:                 # every rank holds its share of the global-mean loss
+                torch.distributed.all_reduce(total, group=self.pg)
+            loss = float(total.item()) / nb if nb else float("nan")
+            history["loss"].append(loss)
+            val = None
+            if validation_data is not None:
+                vb = validation_data.epoch(epoch) if hasattr(validation_data, "epoch") else validation_data
+                val = self.evaluate(vb)
+                history["val_loss"].append(val)
+            if verbose:
+                print(f"Epoch {epoch + 1}/{epochs} - loss: {loss:.6g}" + (f" - val_loss: {val:.6g}" if val is not None else ""), flush=True)
+            if csv_log is not None:
+                with open(csv_log, "a") as f:
+                    f.write(f"{epoch},{loss!r},{'' if val is None else repr(val)}\n")
+            if checkpoint_last is not None:
+                self.save_checkpoint(checkpoint_last)
+            if val is not None:
+                if val < best:
+                    best, wait = val, 0
+                    if checkpoint_best is not None:
+                        self.save_checkpoint(checkpoint_best)
+                else:
+                    wait += 1
+                    if early_stopping_patience is not None and wait >= early_stopping_patience:
+                        history["stopped_epoch"] = epoch
+                        break
+        return history
+

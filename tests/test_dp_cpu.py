@@ -56,6 +56,31 @@ class OracleEngine:
     def flat(self):
         return torch.cat([p.detach().reshape(-1) for p in self.ref.params]).numpy()
 
+    # -- the rest of the MLPEngine surface Trainer.fit / checkpoints use
+    def forward(self, x):
+        with torch.no_grad():
+            return self.ref(x)
+
+    def get_params_flat(self):
+        return self.flat().copy()
+
+    def set_params_flat(self, flat):
+        off = 0
+        with torch.no_grad():
+            for p in self.ref.params:
+                p.copy_(torch.from_numpy(np.asarray(flat[off:off + p.numel()])).view_as(p)); off += p.numel()
+
+    def get_opt_state(self):
+        cat = lambda ts: torch.cat([t.reshape(-1) for t in ts]).numpy().copy()
+        return cat(self.m), cat(self.v), self.t
+
+    def set_opt_state(self, m, v, step):
+        off = 0
+        for mi, vi in zip(self.m, self.v):
+            n = mi.numel()
+            mi.copy_(torch.from_numpy(np.asarray(m[off:off + n])).view_as(mi)); vi.copy_(torch.from_numpy(np.asarray(v[off:off + n])).view_as(vi)); off += n
+        self.t = int(step)
+
 
 def _batch(B):
     g = torch.Generator().manual_seed(3)
@@ -149,3 +174,38 @@ def test_two_rank_stream_shares_train_like_one_process_on_the_joined_batches(tmp
         losses.append(tr.step(x[rows], y[rows]))
     np.testing.assert_allclose(got["losses"], losses, rtol=1e-5)
     np.testing.assert_allclose(got["flat"], eng.flat(), rtol=0, atol=2e-6)
+
+
+def test_fit_driver_callbacks(tmp_path):
+    """Trainer.fit = model.fit with the reference's callbacks (step2_retrain.py:252-286): per-epoch loss / val_loss history, CSV log
+    appended per epoch, last / best checkpoints that restore parameters + optimizer state + counters, early stopping on val_loss."""
+    from climsim_b200.trainer import Trainer
+    x, y = _batch(96)
+    xv, yv = 0.2 * torch.randn(40, 124, generator=torch.Generator().manual_seed(9)), 0.1 * torch.randn(40, 128, generator=torch.Generator().manual_seed(10))
+    train = [(x[i:i + 32], y[i:i + 32]) for i in range(0, 96, 32)]
+    val = [(xv[:24], yv[:24]), (xv[24:], yv[24:])]                       # unequal batches: val_loss is the exact mean over elements
+    eng = OracleEngine()
+    tr = Trainer(eng, rule="adam_keras", lr=1e-3)
+    best, last, log = str(tmp_path / "best.ckpt"), str(tmp_path / "last.ckpt"), str(tmp_path / "metrics.csv")
+    h = tr.fit(train, epochs=4, validation_data=val, checkpoint_best=best, checkpoint_last=last, csv_log=log, verbose=0)
+    assert len(h["loss"]) == len(h["val_loss"]) == 4 and h["stopped_epoch"] is None
+    assert h["loss"][-1] < h["loss"][0] and tr.iteration == 12
+    want_val = float(((eng.forward(xv) - yv) ** 2).mean())
+    assert h["val_loss"][-1] == pytest.approx(want_val, rel=1e-6)
+    rows = open(log).read().strip().splitlines()
+    assert rows[0] == "epoch,loss,val_loss" and len(rows) == 5 and rows[1].startswith("0,")
+    assert os.path.exists(best) and os.path.exists(last) and not os.path.exists(best + ".npz")
+    # the last checkpoint restores everything: a restored trainer continues exactly like the original
+    eng2 = OracleEngine(seed=5)
+    tr2 = Trainer(eng2, rule="adam_keras", lr=1e-3)
+    tr2.load_checkpoint(last)
+    assert tr2.iteration == 12 and eng2.t == eng.t
+    np.testing.assert_array_equal(eng2.flat(), eng.flat())
+    a, b = tr.step(*train[0]), tr2.step(*train[0])
+    assert a == pytest.approx(b, rel=1e-6)
+    np.testing.assert_allclose(eng2.flat(), eng.flat(), rtol=0, atol=1e-7)
+    # appended log, early stopping: with lr = 0 the validation loss never improves after the first epoch
+    tr3 = Trainer(OracleEngine(), rule="adam_keras", lr=0.0)
+    h3 = tr3.fit(train, epochs=20, validation_data=val, csv_log=log, early_stopping_patience=3, verbose=0)
+    assert h3["stopped_epoch"] == 3 and len(h3["val_loss"]) == 4
+    assert len(open(log).read().strip().splitlines()) == 5 + 4
