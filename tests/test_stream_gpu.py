@@ -70,3 +70,16 @@ def test_end_to_end_stream_train_predict(tmp_path):
     res = mod.run(columns=60_000, batch=2048, epochs=3, workdir=str(tmp_path), verbose=False)
     assert res["epoch_losses"][-1] < res["epoch_losses"][0]
     assert res["val_mse_after"] < 0.5 * res["val_mse_before"], res
+
+
+def test_fit_with_streams(tmp_path):
+    """Trainer.fit (model.fit with the reference's callbacks) fed by NpyColumnStream for both the training and the validation split
+    (scripts/fit_check.py): losses fall, 9 steps per epoch were taken, the CSV log has a header and one row per epoch."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("fit_check", os.path.join(os.path.dirname(__file__), "..", "scripts", "fit_check.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    h = mod.run(str(tmp_path), verbose=0)
+    assert h["loss"][-1] < h["loss"][0] and h["val_loss"][-1] < h["val_loss"][0] and h["stopped_epoch"] is None
+    assert h["iteration"] == 3 * (20000 // 2048) and h["log_rows"] == 4
