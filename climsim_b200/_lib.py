@@ -19,6 +19,7 @@ DTYPE = {"fp32": 0, "f32": 0, "float32": 0, "bf16": 1, "bfloat16": 1}
 LOSS = {"mse": 0, "mae": 1, "huber": 2}
 OPT = {"adam_keras": 0, "adam": 0, "adam_torch": 1, "sgd": 2, "radam": 3, "rmsprop": 4}
 FWD_NORMALIZE_IN, FWD_DENORM_OUT, FWD_KEEP_ACTIVATIONS, TRAIN_FUSED_OPT = 1, 2, 4, 8
+BATCH_METRICS_SCRATCH = 2048
 
 
 class MlpCfg(C.Structure):
@@ -103,6 +104,9 @@ SIGNATURES = {
     "csb_test_set_debug": (None, [C.c_int]),
     "csb_test_set_stats": (None, [_VP]),
     "csb_eval_crps": (C.c_int, [_VP, _VP, C.c_int, C.c_int64, C.c_int, C.c_int, _VP, _VP, _VP]),
+    "csb_batch_metrics": (C.c_int, [_VP, _VP, C.c_int64, C.c_int32, _VP, _VP, _VP]),
+    "csb_hsr_train_step": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int64, C.c_int, C.c_uint32, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+                                     C.c_float, C.c_float, _VP, _VP, _VP]),
     "csb_gather_rows": (C.c_int, [_VP, _VP, _VP, C.c_int64, C.c_int, C.c_int64, _VP]),
     "csb_gather_rows_check": (C.c_int, [_VP]),
     "csb_test_gemm_nt": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP]),

@@ -174,48 +174,51 @@ class HSR(torch.nn.Module):
     def trainer(self, data, epochs: int = 20, save: str = "models/vae.cp", plot: bool = True, loss_type: str = "mle",
                 optimizer: str = "adam", lr: float = 0.0001, gamma: float = 0.01, rho: Optional[float] = None,
                 checkpoint_every_s: float = 1200.0):
-        """``HeteroskedasticRegression.trainer`` (hsr.py:83-142), same arguments and behaviour: per-group L2 weight decay
-        alpha = (1-rho)/rho*gamma for the mean network and beta = (1-rho)/rho*(1-gamma) for the log-precision network, Adam or SGD,
-        MSE on the mean for the first third of the epochs and the Gaussian negative log-likelihood afterwards, the loss clipped to
-        +-1e5, a checkpoint (reference keys) every 20 minutes.  ``data`` yields dicts with ``'x'`` and ``'y'``.  The forward and
-        backward passes of both networks run in the engine (``csb_mlp_forward`` / ``csb_mlp_backward`` through autograd); the
-        loss expression and the optimizer are the same torch calls the reference makes.  Returns the per-step losses."""
+        """``HeteroskedasticRegression.trainer`` (hsr.py:83-142): same arguments, same returned per-step losses, same end state.
+
+        Every batch is ONE engine call (``csb_hsr_train_step``): the forward passes of both networks, the loss -- MSE on the mean
+        for the first third of the epochs, the Gaussian negative log-likelihood afterwards, clipped to +-1e5 -- its gradients, both
+        backward passes and the optimizer (Adam or SGD with the per-group L2 decay alpha = (1-rho)/rho*gamma on the mean network
+        and beta = (1-rho)/rho*(1-gamma) on the log-precision network) run as CUDA kernels of this library.  No torch kernel and
+        no host synchronisation per step: the losses accumulate in a device array that is read once per epoch.  A checkpoint with
+        the reference's ``state_dict`` keys is written every ``checkpoint_every_s`` seconds (20 minutes in the reference)."""
         import time
-        rho = rho if rho is not None else 1 - gamma
-        alpha = (1 - rho) / rho * gamma
-        beta = (1 - rho) / rho * (1 - gamma)
-        print("alpha: %.3f, beta: %.3f" % (alpha, beta))
-        pms = [{"params": self.mean.parameters(), "lr": lr, "weight_decay": alpha},
-               {"params": self.logprec.parameters(), "lr": lr, "weight_decay": beta}]
-        if optimizer == "adam":
-            opt = torch.optim.Adam(pms)
-        elif optimizer == "sgd":
-            opt = torch.optim.SGD(pms)
-        else:
+        from .engine import hsr_train_step
+        from . import _lib
+        if loss_type != "mle":
+            raise ValueError("Unknown loss")
+        if optimizer not in ("adam", "sgd"):
             raise ValueError("Unknown optimizer")
+        rho = rho if rho is not None else 1 - gamma
+        alpha, beta = (1 - rho) / rho * gamma, (1 - rho) / rho * (1 - gamma)
+        print("alpha: %.3f, beta: %.3f" % (alpha, beta))
+        rule = "adam_torch" if optimizer == "adam" else "sgd"
         device = self.mean.flat.device
-        losses, t_ckpt = [], time.time()
+        for m in (self.mean, self.logprec):
+            m._claim_engine()
+            m._sync_params()
+        scratch = torch.zeros(_lib.BATCH_METRICS_SCRATCH, dtype=torch.float64, device=device)
+        losses: List[float] = []
+        t_ckpt = time.time()
+        steps_per_epoch = len(data) if hasattr(data, "__len__") else 0
+        buf = torch.zeros(max(steps_per_epoch, 64), dtype=torch.float32, device=device)
         for epoch in range(epochs):
+            k = 0
             for batch in data:
-                x, y = batch["x"].to(device), batch["y"].to(device)
-                opt.zero_grad()
-                mu, logprec = self(x)
-                prec = torch.exp(logprec)
-                if loss_type == "mle":
-                    if epoch < epochs / 3:
-                        loss = ((y - mu) ** 2).mean()                        # first only the mean, via MSE
-                    else:
-                        loss = (prec * (y - mu) ** 2 - logprec).mean()       # non-iid Gaussians -> maximum likelihood
-                else:
-                    raise ValueError("Unknown loss")
-                torch.clip(loss, min=-1e5, max=1e5).backward()
-                losses += [loss.item()]
-                opt.step()
+                x, y = batch["x"].to(device, non_blocking=True), batch["y"].to(device, non_blocking=True)
+                if k == buf.numel():                                    # an iterable without __len__: grow the per-epoch loss array
+                    buf = torch.cat([buf, torch.zeros_like(buf)])
+                hsr_train_step(self.mean.engine, self.logprec.engine, x, y, mle=not (epoch < epochs / 3), loss_out=buf[k:k + 1],
+                               scratch=scratch, rule=rule, lr=lr, wd_mean=alpha, wd_logprec=beta)
+                k += 1
                 if time.time() - t_ckpt > checkpoint_every_s:
+                    self._pull_params()
                     torch.save(self.reference_state_dict(), save)
                     t_ckpt = time.time()
-        n = len(data) if hasattr(data, "__len__") else 1
-        print("Last-epoch loss: %.2f" % sum(losses[-n:-1]))
+            losses += buf[:k].tolist()                                  # the one D2H read of the epoch
+            steps_per_epoch = k
+        self._pull_params()
+        print("Last-epoch loss: %.2f" % sum(losses[len(losses) - steps_per_epoch:-1]))
         print("Finished Training")
         if plot:
             try:
@@ -224,6 +227,13 @@ class HSR(torch.nn.Module):
             except ImportError:
                 pass
         return losses
+
+    def _pull_params(self) -> None:
+        """Engine-side training updates the parameters inside the engine: mirror them into the modules' ``flat`` parameters."""
+        for m in (self.mean, self.logprec):
+            with torch.no_grad():
+                m.engine.get_params_device(out=m.flat.data)
+            m._uploaded_version = m.flat._version
 
 
 class OnlineMLP(_EngineModule):

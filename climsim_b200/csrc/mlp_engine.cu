@@ -20,6 +20,7 @@
 
 #include "common.cuh"
 #include "simt_kernels.cuh"
+#include "fit_kernels.cuh"
 #include "tc_gemm.cuh"
 
 namespace csb {
@@ -991,9 +992,13 @@ static inline void set_wgrad_geometry(const csb_mlp* h, int l, int64_t B, tc::Nt
 }
 static inline bool fused_opt_supported(const csb_mlp* h) {
   static const bool off = getenv("CSB_NO_FUSED_OPT") != nullptr;     // debugging aid: always take the three-launch path
-  if (!h->bf16 || off) return false;
-  for (int l = 0; l < h->L; ++l) if (h->layer[l].ln) return false;
-  return true;
+  return h->bf16 && !off;          // LayerNorm layers included: their (gamma, beta) partials ride in the same launch
+}
+// number of (dgamma, dbeta) partial pairs the LayerNorm backward of layer l writes at batch B (one per block of the kernel that runs)
+static inline int ln_grad_splits(const csb_mlp* h, int l, int64_t B) {
+  const LayerInfo& li = h->layer[l];
+  if (h->bf16 && li.Np <= 256 * simt::LN_MAXP) return (int)std::max<int64_t>(1, std::min<int64_t>(2 * h->sm_count, ceil_div(B, 8)));
+  return (int)std::max<int64_t>(1, std::min<int64_t>(32, ceil_div(B, 256)));
 }
 
 // reduce the pending split partials into the gradient buffer (and finish the pending loss) with the plain reduction kernel
@@ -1008,6 +1013,10 @@ static int flush_pending(csb_mlp* h, cudaStream_t st) {
     const int splits = wgrad_splits(h, l, h->pending_B, nullptr);
     tab.seg[tab.n++] = {h->ws + li.ws_w_off, (size_t)li.Kp * li.Np, h->grads + li.w_off, (int64_t)li.Kp * li.Np, splits};
     tab.seg[tab.n++] = {h->ws + li.ws_b_off, (size_t)li.Np, h->grads + li.b_off, (int64_t)li.Np, splits * nt_m_tiles(li.Kp, li.nt_cg)};
+    if (li.ln) {
+      const int S = ln_grad_splits(h, l, h->pending_B);
+      tab.seg[tab.n++] = {h->ws + li.ws_g_off, (size_t)2 * li.Np, h->grads + li.g_off, (int64_t)2 * li.Np, S};
+    }
     max_len = std::max<int64_t>(max_len, (int64_t)li.Kp * li.Np);
   }
   dim3 grid((unsigned)std::min<int64_t>(ceil_div(max_len / 4, 256), 2 * h->sm_count), (unsigned)(tab.n + (tab.loss_out ? 1 : 0)));
@@ -1036,13 +1045,13 @@ static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st,
     const LayerInfo& li = h->layer[l];
     if (li.ln) {
       // the buffer holds du_l = dA_l * act'(a_l): LayerNorm parameter gradients, then du -> dz in place
-      int S = (int)std::max<int64_t>(1, std::min<int64_t>(32, ceil_div(B, 256)));
+      const int S = ln_grad_splits(h, l, B);
       dim3 gridp((unsigned)(li.Np / 64), (unsigned)S);
       const int gridb = (int)std::min<int64_t>(ceil_div(B, 8), (int64_t)h->sm_count * 8);
       const float* gamma = h->params + li.g_off;
       if (h->bf16 && li.Np <= 256 * simt::LN_MAXP) {
         // one fused kernel: du -> dz and the (dgamma, dbeta) partials of each block
-        S = (int)std::max<int64_t>(1, std::min<int64_t>(2 * h->sm_count, ceil_div(B, 8)));      // two resident blocks per SM
+        // S = two resident blocks per SM
         const size_t smem = (size_t)(1 + 2 * 8) * 256 * simt::LN_MAXP * 4;        // gamma + (dgamma, dbeta) per warp
         static bool attr_set = false;
         if (!attr_set) {
@@ -1330,8 +1339,9 @@ int csb_mlp_apply_opt(csb_mlp* h, int rule, float lr, float beta1, float beta2, 
       const LayerInfo& li = h->layer[l];
       const int splits = wgrad_splits(h, l, h->pending_B, nullptr);
       tab.l[l] = {li.Kp, li.Np, li.w_off, li.b_off, h->w16[l], h->wt16[l], h->ws + li.ws_w_off, splits,
-                  h->ws + li.ws_b_off, splits * nt_m_tiles(li.Kp, li.nt_cg)};
-      max_items = std::max(max_items, (li.Kp / 32) * (li.Np / 64) + (int)ceil_div(li.Np / 4, 256));
+                  h->ws + li.ws_b_off, splits * nt_m_tiles(li.Kp, li.nt_cg),
+                  li.g_off, h->ws + li.ws_g_off, li.ln ? ln_grad_splits(h, l, h->pending_B) : 0};
+      max_items = std::max(max_items, (li.Kp / 32) * (li.Np / 64) + (int)ceil_div(li.Np / 4, 256) + (li.ln ? (int)ceil_div(li.Np / 2, 256) : 0));
     }
     dim3 grid((unsigned)max_items, (unsigned)(h->L + 1));
     CSB_CUDA_CHECK(launch_pdl(simt::opt_fused_kernel, grid, dim3(256), 0, st, tab, o));
@@ -1349,8 +1359,9 @@ int csb_mlp_apply_opt(csb_mlp* h, int rule, float lr, float beta1, float beta2, 
     int max_items = 1;
     for (int l = 0; l < h->L; ++l) {
       const LayerInfo& li = h->layer[l];
-      tab.l[l] = {li.Kp, li.Np, li.w_off, li.b_off, h->w16[l], h->wt16[l], h->grads + li.w_off, 1, h->grads + li.b_off, 1};
-      max_items = std::max(max_items, (li.Kp / 32) * (li.Np / 64) + (int)ceil_div(li.Np / 4, 256));
+      tab.l[l] = {li.Kp, li.Np, li.w_off, li.b_off, h->w16[l], h->wt16[l], h->grads + li.w_off, 1, h->grads + li.b_off, 1,
+                  li.g_off, h->grads + li.g_off, li.ln ? 1 : 0};
+      max_items = std::max(max_items, (li.Kp / 32) * (li.Np / 64) + (int)ceil_div(li.Np / 4, 256) + (li.ln ? (int)ceil_div(li.Np / 2, 256) : 0));
     }
     dim3 grid((unsigned)max_items, (unsigned)(h->L + 1));
     CSB_CUDA_CHECK(launch_pdl(simt::opt_fused_kernel, grid, dim3(256), 0, st, tab, o));
@@ -1658,6 +1669,85 @@ int csb_test_gemm_nt_cg(const uint16_t* A, const uint16_t* B, float* C, float* c
   }
   if (m_tiles_out) *m_tiles_out = nt_m_tiles(M, cg);
   return launch_nt_auto(ta, tb, p, splits, reinterpret_cast<cudaStream_t>(stream), cg);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Keras metrics of a batch (Trainer.fit / evaluate)
+// ---------------------------------------------------------------------------------------------------------------
+int csb_batch_metrics(const float* pred, const float* y, int64_t B, int32_t F, double* out5, double* scratch, void* stream) {
+  CSB_REQUIRE(pred && y && out5 && scratch, CSB_EINVAL, "null argument");
+  CSB_REQUIRE(B > 0 && F > 0, CSB_EINVAL, "bad shape (B %lld, F %d)", (long long)B, F);
+  static int sm = 0;
+  int rc;
+  if (sm == 0 && (rc = csb_device_info(&sm, nullptr, nullptr, nullptr))) return rc;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(B, 8), std::min(4 * sm, (CSB_BATCH_METRICS_SCRATCH - 1) / 3)));
+  simt::batch_metrics_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pred, y, B, F, out5, scratch);
+  CSB_CUDA_CHECK(cudaGetLastError());
+  return CSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Heteroskedastic regression: one training step of BOTH networks inside the engine (hsr.py:122-140)
+// ---------------------------------------------------------------------------------------------------------------
+static int mlp_forward_keep(csb_mlp* h, const float* x, int64_t B, uint32_t flags, cudaStream_t st) {
+  int rc;
+  if ((rc = build_act_maps(h, B))) return rc;
+  if ((rc = flush_pending(h, st))) return rc;
+  prof_mark(h, K_BEGIN, st);
+  if ((rc = run_normalize(h, x, B, (flags & CSB_FWD_NORMALIZE_IN) ? 1 : 0, st))) return rc;
+  if ((rc = run_hidden_forward(h, B, st))) return rc;
+  if ((rc = run_head(h, B, 0, nullptr, 0.f, st))) return rc;
+  h->acts_B = B;
+  h->acts_normalized = (flags & CSB_FWD_NORMALIZE_IN) != 0;
+  return CSB_OK;
+}
+
+int csb_hsr_train_step(csb_mlp* mean, csb_mlp* logprec, const float* x, const float* y, int64_t B, int mle, uint32_t flags, int rule,
+                       float lr, float beta1, float beta2, float eps, float wd_mean, float wd_logprec, float* loss_out, double* scratch,
+                       void* stream) {
+  CSB_REQUIRE(mean && logprec && x && y && loss_out && scratch, CSB_EINVAL, "null argument");
+  CSB_REQUIRE(mean != logprec, CSB_EINVAL, "the two networks need separate handles");
+  CSB_REQUIRE(mean->in_dim == logprec->in_dim && mean->out_dim == logprec->out_dim && mean->out_p == logprec->out_p && mean->bf16 == logprec->bf16,
+              CSB_EINVAL, "the mean and log-precision networks must agree in input / output width and dtype");
+  for (csb_mlp* h : {mean, logprec}) {
+    CSB_REQUIRE(h->layer[h->L - 1].act == CSB_ACT_NONE && h->cfg.head_relu_from < 0 && !h->has_mask, CSB_EUNSUPPORTED,
+                "csb_hsr_train_step expects linear output layers without a mask (hsr.py:27-35)");
+    int rc = check_batch(h, B);
+    if (rc) return rc;
+  }
+  CSB_REQUIRE(B > 0 && mean->out_dim % 4 == 0, CSB_EINVAL, "empty batch or output width not a multiple of 4");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc;
+  if ((rc = mlp_forward_keep(mean, x, B, flags, st))) return rc;
+  if (mle && (rc = mlp_forward_keep(logprec, x, B, flags, st))) return rc;      // the MSE phase never looks at the log-precision
+  const int F = mean->out_dim, ldp = mean->out_p;
+  const int64_t n = B * F;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n / 4, 256), std::min(4 * mean->sm_count, CSB_BATCH_METRICS_SCRATCH - 1)));
+  simt::hsr_loss_kernel<<<grid, 256, 0, st>>>(mean->pred, logprec->pred, y, B, F, ldp, mle, loss_out, scratch);
+  CSB_CUDA_CHECK(cudaGetLastError());
+  prof_mark(mean, K_LOSS, st);
+  const int lm = mean->L - 1, ll = logprec->L - 1;
+  if (mean->bf16)
+    simt::hsr_grad_kernel<__nv_bfloat16><<<grid_for(B * (ldp / 4), 256, mean->sm_count), 256, 0, st>>>(
+        mean->pred, logprec->pred, y, B, F, ldp, mle, loss_out, dz16(mean, lm), mle ? dz16(logprec, ll) : nullptr);
+  else
+    simt::hsr_grad_kernel<float><<<grid_for(B * (ldp / 4), 256, mean->sm_count), 256, 0, st>>>(
+        mean->pred, logprec->pred, y, B, F, ldp, mle, loss_out, dz32(mean, lm), mle ? dz32(logprec, ll) : nullptr);
+  CSB_CUDA_CHECK(cudaGetLastError());
+  prof_mark(mean, K_LOSS, st);
+  // torch.optim.Adam skips parameters without a gradient: in the MSE phase the log-precision network is not touched at all
+  // (no decay, no moment update, no step count) -- hsr.py:109-112,128-131
+  csb_mlp* nets[2] = {mean, mle ? logprec : nullptr};
+  const float wds[2] = {wd_mean, wd_logprec};
+  for (int i = 0; i < 2; ++i) {
+    csb_mlp* h = nets[i];
+    if (!h) continue;
+    if ((rc = run_backward_chain(h, B, nullptr, st, 0, nullptr, fused_opt_supported(h)))) return rc;
+    h->acts_B = -1;
+    if ((rc = csb_mlp_apply_opt(h, rule, lr, beta1, beta2, eps, wds[i], stream))) return rc;
+  }
+  return CSB_OK;
 }
 
 }  // extern "C"

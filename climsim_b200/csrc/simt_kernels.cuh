@@ -767,6 +767,8 @@ struct FusedOptLayer {
   __nv_bfloat16 *w16, *wt16;
   const float* ws_w; int w_splits;      // partials of dW: ws_w + s * Kp * Np
   const float* ws_b; int b_splits;      // partials of db: ws_b + s * Np
+  // LayerNorm layers: gamma [Np] then beta [Np] at g_off, partials ws_g + s * 2 * Np (g_splits == 0: no LayerNorm)
+  size_t g_off; const float* ws_g; int g_splits;
 };
 struct FusedOptTable {
   int n; FusedOptLayer l[CSB_MAX_LAYERS];
@@ -783,7 +785,8 @@ __global__ void __launch_bounds__(256) opt_fused_kernel(const FusedOptTable tab,
   }
   const FusedOptLayer L = tab.l[blockIdx.y];
   // W_l in tiles of 32 (k) x 64 (n): thread -> 4 consecutive n (one float4) of rows ty and ty + 16
-  const int tiles_n = L.Np / 64, tiles = (L.Kp / 32) * tiles_n, vec_items = (L.Np / 4 + 255) / 256;
+  const int tiles_n = L.Np / 64, tiles = (L.Kp / 32) * tiles_n;
+  const int vec_b = (L.Np / 4 + 255) / 256, vec_items = vec_b + (L.g_splits > 0 ? (2 * L.Np / 4 + 255) / 256 : 0);
   const size_t wsz = (size_t)L.Kp * L.Np;
   __shared__ float t[32][65];
   for (int item = blockIdx.x; item < tiles + vec_items; item += gridDim.x) {
@@ -819,10 +822,13 @@ __global__ void __launch_bounds__(256) opt_fused_kernel(const FusedOptTable tab,
       }
       __syncthreads();
     } else {
-      const int c = ((item - tiles) * 256 + threadIdx.x) * 4;
-      if (c < L.Np) {
-        const size_t e = L.b_off + c;
-        const float4 g4 = sum_partials4(L.ws_b + c, (size_t)L.Np, L.b_splits);
+      // vector segments: the bias [Np] and, behind it, a LayerNorm layer's (gamma, beta) [2 Np]
+      int c = ((item - tiles) * 256 + threadIdx.x) * 4;
+      size_t e; const float* wsp; size_t stride; int splits; bool ok;
+      if (c < L.Np) { e = L.b_off + c; wsp = L.ws_b + c; stride = (size_t)L.Np; splits = L.b_splits; ok = true; }
+      else { c -= vec_b * 1024; e = L.g_off + c; wsp = L.ws_g + c; stride = (size_t)2 * L.Np; splits = L.g_splits; ok = c >= 0 && c < 2 * L.Np && L.g_splits > 0; }
+      if (ok) {
+        const float4 g4 = sum_partials4(wsp, stride, splits);
         const float4 w4 = *reinterpret_cast<const float4*>(tab.params + e), m4 = *reinterpret_cast<const float4*>(tab.m + e),
                      v4 = *reinterpret_cast<const float4*>(tab.v + e);
         float w[4] = {w4.x, w4.y, w4.z, w4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};

@@ -292,6 +292,18 @@ class MLPEngine:
                    "csb_mlp_forward_host")
         return y
 
+    def batch_metrics(self, pred: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        """Device fp64 vector [sum (p-y)^2, sum |p-y|, rows with argmax(p) == argmax(y), elements, rows] of one batch: the
+        sufficient statistics of Keras' ``metrics=['mse','mae','accuracy']`` (``csb_batch_metrics``); no synchronisation."""
+        pred, y = _f32_cuda(pred, "pred"), _f32_cuda(y, "y")
+        assert pred.shape == y.shape and pred.dim() == 2
+        if getattr(self, "_metrics_scratch", None) is None:
+            self._metrics_scratch = torch.zeros(_lib.BATCH_METRICS_SCRATCH, dtype=torch.float64, device=pred.device)
+        out = torch.empty(5, dtype=torch.float64, device=pred.device)
+        _lib.check(self.lib.csb_batch_metrics(pred.data_ptr(), y.data_ptr(), pred.shape[0], pred.shape[1], out.data_ptr(),
+                                              self._metrics_scratch.data_ptr(), _lib.current_stream_ptr()), "csb_batch_metrics")
+        return out
+
     def profile(self, enable: bool = True) -> None:
         _lib.check(self.lib.csb_mlp_profile(self._h, 1 if enable else 0), "csb_mlp_profile")
 
@@ -305,6 +317,21 @@ class MLPEngine:
     @property
     def launch_count(self) -> int:
         return int(self.lib.csb_mlp_launch_count(self._h))
+
+
+def hsr_train_step(mean: MLPEngine, logprec: MLPEngine, x: torch.Tensor, y: torch.Tensor, mle: bool, loss_out: torch.Tensor,
+                   scratch: torch.Tensor, rule: str = "adam_torch", lr: float = 1e-4, beta1: float = 0.9, beta2: float = 0.999,
+                   eps: float = 1e-8, wd_mean: float = 0.0, wd_logprec: float = 0.0, normalize_in: bool = False) -> None:
+    """``csb_hsr_train_step``: one step of both heteroskedastic-regression networks (forward, MSE / Gaussian-NLL loss with the
+    reference's clip, backward, per-group L2 optimizer) entirely inside the engine; the loss lands in ``loss_out`` (a one-element
+    CUDA fp32 tensor, e.g. a slice of a per-epoch loss array) without any host synchronisation."""
+    x, y = _f32_cuda(x, "x"), _f32_cuda(y, "y")
+    assert loss_out.is_cuda and loss_out.dtype == torch.float32 and scratch.is_cuda and scratch.dtype == torch.float64
+    assert scratch.numel() >= _lib.BATCH_METRICS_SCRATCH
+    _lib.check(mean.lib.csb_hsr_train_step(mean._h, logprec._h, x.data_ptr(), y.data_ptr(), x.shape[0], int(bool(mle)),
+                                           _lib.FWD_NORMALIZE_IN if normalize_in else 0, _lib.OPT[rule], lr, beta1, beta2, eps,
+                                           wd_mean, wd_logprec, loss_out.data_ptr(), scratch.data_ptr(), _lib.current_stream_ptr()),
+               "csb_hsr_train_step")
 
 
 class CNNEngine:

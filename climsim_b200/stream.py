@@ -15,8 +15,10 @@ at tens of millions of columns per second that host-side chain is the wall, so h
   (seed, epoch, window), so that the order is reproducible and testable without a GPU); the window order is shuffled per epoch as the
   reference shuffles its file list (step2_retrain.py:198).
 
-Data parallelism: rank r of W takes the r-th contiguous share of the windows' rows (``DistributedSampler`` semantics without
-padding: every row is visited exactly once per epoch across the ranks when ``drop_last`` is off).
+Data parallelism: rank r of W takes the r-th contiguous share of ``ceil(N / W)`` rows.  Every rank gets the SAME number of rows --
+hence the same windows and the same number of batches per epoch, which the per-batch gradient all-reduce needs (a rank with one batch
+more would wait for its peers forever).  When W does not divide N the last shares start a few rows early, i.e. up to W - 1 rows are
+visited twice per epoch: ``DistributedSampler``'s padding with repeated samples (train_mlp_h5loader.py:126-134), in contiguous form.
 
 ``StreamPlan`` is the pure host logic (no CUDA); ``NpyColumnStream`` executes it.
 """
@@ -39,10 +41,12 @@ class StreamPlan:
         self.n_rows, self.batch_size, self.shuffle, self.seed = int(n_rows), int(batch_size), bool(shuffle), int(seed)
         self.rank, self.world, self.drop_last = rank, world, bool(drop_last)
         self.window = max(self.batch_size, (int(window) // self.batch_size) * self.batch_size)
-        # this rank's contiguous share [lo, hi) of the rows (the first n_rows % world ranks get one row more)
-        base, extra = divmod(self.n_rows, world)
-        self.lo = rank * base + min(rank, extra)
-        self.hi = self.lo + base + (1 if rank < extra else 0)
+        # this rank's contiguous share [lo, hi): ceil(n_rows / world) rows on EVERY rank (equal batch counts, see the module docstring);
+        # shares that would run past the end are shifted back, overlapping their predecessor by at most world - 1 rows in total
+        per = -(-self.n_rows // world)
+        assert per * (world - 1) < self.n_rows or world == 1, "more ranks than rows"
+        self.lo = min(rank * per, self.n_rows - per)
+        self.hi = self.lo + per
 
     @property
     def rows(self) -> int:
@@ -113,15 +117,25 @@ class NpyColumnStream:
         self._copied = [torch.cuda.Event() for _ in range(2)]
         self._consumed = [torch.cuda.Event() for _ in range(2)]
         self._reader: Optional[threading.Thread] = None
+        self._reader_error: Optional[BaseException] = None
 
     def __len__(self) -> int:
         return self.plan.batches_per_epoch()
 
     # -- host side: read window `wi` of this epoch into staging slot `slot` -----------------------------------------------------
     def _read(self, slot: int, start: int, length: int) -> None:
-        hx, hy = self._host[slot]
-        np.copyto(hx.numpy()[:length], self.x_all[start:start + length], casting="same_kind")
-        np.copyto(hy.numpy()[:length], self.y_all[start:start + length], casting="same_kind")
+        try:
+            hx, hy = self._host[slot]
+            np.copyto(hx.numpy()[:length], self.x_all[start:start + length], casting="same_kind")
+            np.copyto(hy.numpy()[:length], self.y_all[start:start + length], casting="same_kind")
+        except BaseException as e:                                          # re-raised by the consumer: never train on a stale slot
+            self._reader_error = e
+
+    def _join_reader(self, t: threading.Thread) -> None:
+        t.join()
+        if self._reader_error is not None:
+            e, self._reader_error = self._reader_error, None
+            raise RuntimeError("NpyColumnStream: reading a window from the .npy files failed") from e
 
     def epoch(self, epoch: int = 0):
         torch, plan = self.torch, self.plan
@@ -133,6 +147,7 @@ class NpyColumnStream:
         self._copy_stream.wait_stream(main)
         if self._reader is not None:                                        # reader of an abandoned epoch: let it finish with its slot
             self._reader.join()
+            self._reader_error = None
         reader: Optional[threading.Thread] = None
 
         def start_read(k: int) -> threading.Thread:
@@ -148,7 +163,7 @@ class NpyColumnStream:
         for k, wi in enumerate(order):
             slot = k & 1
             start, length = wins[wi]
-            reader.join()                                                   # staging slot `slot` holds window k
+            self._join_reader(reader)                                       # staging slot `slot` holds window k
             wx, wy, widx = self._win[slot]
             hx, hy = self._host[slot]
             perm = torch.from_numpy(plan.permutation(epoch, wi, length))
@@ -172,6 +187,69 @@ class NpyColumnStream:
                 yield ox[:n], oy[:n]
             self._consumed[slot].record(main)
             used[slot] = True
+        self._lib.check(self.lib.csb_gather_rows_check(self._lib.current_stream_ptr()), "csb_gather_rows_check")
+
+    def __iter__(self):
+        return self.epoch(0)
+
+
+class ResidentColumnStream:
+    """The same iterator with this rank's whole share of the split RESIDENT in HBM.
+
+    The low-resolution training split is about 10 M columns x 1008 B = 10 GB -- a B200 holds it 17 times over -- and the reference
+    walks the same arrays for 18 epochs (step2_retrain.py:280-285), so the share is uploaded ONCE (in chunks through one pinned
+    staging buffer) and every epoch is a fresh permutation of ALL its rows (a full shuffle, where the streaming variant and the
+    reference's 30-day buffer shuffle locally), cut into batches by ``csb_gather_rows``.  Per epoch the host sends 8 bytes per row (the
+    permutation) instead of 1008, which takes the host link out of the training loop.  ``StreamPlan`` with one window spanning the
+    share is the host logic (``epoch_rows`` gives the order without a GPU)."""
+
+    def __init__(self, input_path: str, target_path: str, batch_size: int, shuffle: bool = True, seed: int = 0, rank: int = 0,
+                 world: int = 1, drop_last: bool = False, device: str = "cuda", chunk_rows: int = 1 << 20):
+        import torch
+        from . import _lib
+        self.torch, self._lib, self.lib = torch, _lib, _lib.load()
+        x_all = np.load(input_path, mmap_mode="r")
+        y_all = np.load(target_path, mmap_mode="r")
+        assert x_all.ndim == 2 and y_all.ndim == 2 and x_all.shape[0] == y_all.shape[0], \
+            "input and target arrays must be (N, F_in) and (N, F_out) with the same N"
+        probe = StreamPlan(x_all.shape[0], batch_size, batch_size, shuffle, seed, rank, world, drop_last)
+        one_window = -(-probe.rows // batch_size) * batch_size                 # a single window covering the whole share
+        self.plan = StreamPlan(x_all.shape[0], batch_size, one_window, shuffle, seed, rank, world, drop_last)
+        assert len(self.plan.windows()) == 1
+        self.device = torch.device(device)
+        self.f_in, self.f_out = int(x_all.shape[1]), int(y_all.shape[1])
+        n = self.plan.rows
+        self.x = torch.empty(n, self.f_in, dtype=torch.float32, device=self.device)
+        self.y = torch.empty(n, self.f_out, dtype=torch.float32, device=self.device)
+        chunk = min(chunk_rows, n)
+        hx = torch.empty(chunk, self.f_in, dtype=torch.float32).pin_memory()
+        hy = torch.empty(chunk, self.f_out, dtype=torch.float32).pin_memory()
+        for s in range(0, n, chunk):
+            ln = min(chunk, n - s)
+            np.copyto(hx.numpy()[:ln], x_all[self.plan.lo + s:self.plan.lo + s + ln], casting="same_kind")
+            np.copyto(hy.numpy()[:ln], y_all[self.plan.lo + s:self.plan.lo + s + ln], casting="same_kind")
+            self.x[s:s + ln].copy_(hx[:ln], non_blocking=True)
+            self.y[s:s + ln].copy_(hy[:ln], non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()              # the staging buffer is reused by the next chunk
+        self._idx = torch.empty(n, dtype=torch.int64, device=self.device)
+        self._out = [(torch.empty(batch_size, self.f_in, dtype=torch.float32, device=self.device),
+                      torch.empty(batch_size, self.f_out, dtype=torch.float32, device=self.device)) for _ in range(2)]
+
+    def __len__(self) -> int:
+        return self.plan.batches_per_epoch()
+
+    def epoch(self, epoch: int = 0):
+        torch, plan = self.torch, self.plan
+        n = plan.rows
+        self._idx.copy_(torch.from_numpy(plan.permutation(epoch, 0, n)))      # stream-ordered after the previous epoch's gathers
+        n_out = 0
+        for off, ln in plan.batches_in(n):
+            ox, oy = self._out[n_out & 1]
+            n_out += 1
+            sp = self._lib.current_stream_ptr()
+            self._lib.check(self.lib.csb_gather_rows(self.x.data_ptr(), self._idx[off:].data_ptr(), ox.data_ptr(), ln, self.f_in, n, sp), "csb_gather_rows")
+            self._lib.check(self.lib.csb_gather_rows(self.y.data_ptr(), self._idx[off:].data_ptr(), oy.data_ptr(), ln, self.f_out, n, sp), "csb_gather_rows")
+            yield ox[:ln], oy[:ln]
         self._lib.check(self.lib.csb_gather_rows_check(self._lib.current_stream_ptr()), "csb_gather_rows_check")
 
     def __iter__(self):

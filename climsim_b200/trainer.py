@@ -40,23 +40,45 @@ class Trainer:
 
     Host batches are fed through the engine's two staging slots on its copy stream, so with ``sync=False`` the H2D copy of
     batch i+1 overlaps the compute of batch i (the role of ``tf.data`` prefetch / ``DataLoader(pin_memory=True)`` in the
-    reference's drivers); every step still performs its own H2D copy and the D2H read of its loss."""
+    reference's drivers); every step still performs its own H2D copy and the D2H read of its loss.
+
+    Data parallelism: every rank must start from the same parameters -- rank 0's are broadcast here, as DDP does at construction
+    (train_mlp_h5loader.py:195-207)."""
+
+    _NO_WEIGHT_DECAY = ("adam_keras", "adam", "rmsprop")      # rules whose reference optimizers have no decay term
 
     def __init__(self, engine: MLPEngine, rule: str = "adam_keras", lr: float | Callable[[int], float] = 1e-3,
                  beta1: float = 0.9, beta2: float = 0.999, eps: Optional[float] = None, weight_decay: float = 0.0,
                  process_group=None):
+        if weight_decay != 0.0 and rule in self._NO_WEIGHT_DECAY:
+            raise ValueError(f"optimizer rule {rule!r} has no weight-decay term (Keras Adam / RMSprop); use 'adam_torch', 'sgd' or 'radam'")
         self.engine, self.rule, self.lr = engine, rule, lr
         self.beta1, self.beta2, self.eps, self.weight_decay = beta1, beta2, eps, weight_decay
         self.pg = process_group
-        self.world = 1
+        self.world, self.rank = 1, 0
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(process_group)
+            self.rank = torch.distributed.get_rank(process_group)
         self.iteration = 0
         self.device = getattr(engine, "device", "cuda")
         self._grad = engine.grad_buffer() if self.world > 1 else None
         self._x = self._y = None
         self._loss = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._loss_host = None            # pinned ring of loss slots for the asynchronous host-fed path
+        if self.world > 1:
+            self._broadcast_params()
+
+    def _broadcast_params(self) -> None:
+        eng, dist = self.engine, torch.distributed
+        src = dist.get_global_rank(self.pg, 0) if self.pg is not None else 0
+        if hasattr(eng, "get_params_device") and torch.device(self.device).type == "cuda":
+            flat = eng.get_params_device()
+            dist.broadcast(flat, src=src, group=self.pg)
+            eng.set_params_device(flat)
+        else:
+            flat = torch.from_numpy(np.ascontiguousarray(eng.get_params_flat()))
+            dist.broadcast(flat, src=src, group=self.pg)
+            eng.set_params_flat(flat.numpy())
 
     def _lr(self) -> float:
         return float(self.lr(self.iteration)) if callable(self.lr) else float(self.lr)
@@ -66,9 +88,31 @@ class Trainer:
             self._loss_host = torch.zeros(4, dtype=torch.float32).pin_memory()
         return self._loss_host[self.iteration % 4:self.iteration % 4 + 1]
 
+    def _on_device(self, t: torch.Tensor) -> bool:
+        return t.device.type == torch.device(self.device).type
+
     def synchronize(self) -> None:
         """Wait for every step enqueued so far (the loss slots returned by ``step(..., sync=False)`` are valid afterwards)."""
         torch.cuda.current_stream().synchronize()
+
+    def _step_local(self, x: torch.Tensor, y: torch.Tensor, normalize_in: bool = False) -> torch.Tensor:
+        """One training step; returns the DEVICE scalar holding THIS RANK'S share of the global-mean loss (no loss all-reduce, no
+        host synchronisation).  Host batches go through the staging slots."""
+        eng = self.engine
+        B = x.shape[0]
+        lr = self._lr()
+        staged = not self._on_device(x)
+        if staged:
+            x, y = eng.stage_host_batch(x, y)
+        scale = 1.0 / (B * self.world * eng.out_dim)            # global-mean MSE, as Keras computes on the global batch
+        eng.train_step(x, y, grad_scale=scale, normalize_in=normalize_in, loss_out=self._loss, fused_opt=self.world == 1)
+        if staged:
+            eng.release_staged()
+        if self.world > 1:
+            torch.distributed.all_reduce(self._grad, group=self.pg)
+        eng.apply_opt(self.rule, lr=lr, beta1=self.beta1, beta2=self.beta2, eps=self.eps, weight_decay=self.weight_decay)
+        self.iteration += 1
+        return self._loss
 
     def step(self, x: torch.Tensor, y: torch.Tensor, normalize_in: bool = False, return_loss: bool = True, sync: bool = True):
         """x (B_local, in_dim), y (B_local, out_dim): CUDA tensors, or (pinned, contiguous) host tensors that are copied first.
@@ -79,42 +123,35 @@ class Trainer:
         ``sync=False`` returns the pinned one-element tensor, valid after ``synchronize()`` (or once two further steps have
         been issued) -- x and y must stay untouched for the same span."""
         eng = self.engine
-        B = x.shape[0]
-        lr = self._lr()
-        on_device = x.device.type == torch.device(self.device).type
+        on_device = self._on_device(x)
         slot = None
         if not on_device:
             slot = self._loss_slot()
             if self.world == 1:
-                eng.train_step_host_async(x, y, slot, rule=self.rule, lr=lr, beta1=self.beta1, beta2=self.beta2, eps=self.eps,
+                eng.train_step_host_async(x, y, slot, rule=self.rule, lr=self._lr(), beta1=self.beta1, beta2=self.beta2, eps=self.eps,
                                           weight_decay=self.weight_decay, normalize_in=normalize_in)
                 self.iteration += 1
                 if not sync:
                     return slot
                 self.synchronize()
                 return float(slot.item())
-            x, y = eng.stage_host_batch(x, y)
-        scale = 1.0 / (B * self.world * eng.out_dim)            # global-mean MSE, as Keras computes on the global batch
-        eng.train_step(x, y, grad_scale=scale, normalize_in=normalize_in, loss_out=self._loss, fused_opt=self.world == 1)
+        loss = self._step_local(x, y, normalize_in)
+        if self.world > 1 and (return_loss or slot is not None):
+            torch.distributed.all_reduce(loss, group=self.pg)
         if slot is not None:
-            eng.release_staged()
-        if self.world > 1:
-            torch.distributed.all_reduce(self._grad, group=self.pg)
-            if return_loss or slot is not None:
-                torch.distributed.all_reduce(self._loss, group=self.pg)
-        eng.apply_opt(self.rule, lr=lr, beta1=self.beta1, beta2=self.beta2, eps=self.eps, weight_decay=self.weight_decay)
-        self.iteration += 1
-        if slot is not None:
-            slot.copy_(self._loss, non_blocking=True)
+            slot.copy_(loss, non_blocking=True)
             if not sync:
                 return slot
             self.synchronize()
             return float(slot.item())
-        return float(self._loss.item()) if return_loss else self._loss
+        return float(loss.item()) if return_loss else loss
 
     # ------------------------------------------------------------------------------------------------------------------ model.fit
     def save_checkpoint(self, path: str) -> None:
-        """Parameters + optimizer state + step counters: the content of Keras' ``ModelCheckpoint(save_weights_only=False)`` file."""
+        """Parameters + optimizer state + step counters: the CONTENT of Keras' ``ModelCheckpoint(save_weights_only=False)`` file, as an
+        ``.npz`` of flat fp32 blobs in ``get_weights()`` order.  The format is this library's own -- the reference's artefact is a
+        Keras ``.h5`` (h5py is not available here); ``MLP.keras_weights()`` / ``MLPEngine.flat_to_keras`` give the ``set_weights``
+        list for a model on the Keras side, ``MLP.load_keras_weights`` the way back."""
         m, v, step = self.engine.get_opt_state()
         with open(path, "wb") as f:                 # a file object: np.savez would append ".npz" to a bare path
             np.savez(f, params=self.engine.get_params_flat(), m=m, v=v, step=np.int64(step), iteration=np.int64(self.iteration))
@@ -125,70 +162,129 @@ class Trainer:
         self.engine.set_opt_state(ck["m"], ck["v"], int(ck["step"]))
         self.iteration = int(ck["iteration"])
 
-    def evaluate(self, data) -> float:
-        """Mean squared error over ``data`` (an iterable of ``(x, y)``; exact mean over all elements): Keras' ``val_loss`` for
-        ``loss='mse'`` (hpo_baseline_v1.py:127-129).  One D2H read at the end."""
-        se, n = None, 0
+    METRICS = ("loss", "mse", "mae", "accuracy")
+
+    def _batch_metrics(self, pred: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        """[sum of squared errors, sum of absolute errors, rows whose argmax agrees, elements, rows] of one batch as a device
+        vector (fp64): the sufficient statistics of Keras' ``metrics=['mse', 'mae', 'accuracy']`` (hpo_baseline_v1.py:127-129;
+        with a 128-wide regression output Keras resolves 'accuracy' to categorical accuracy)."""
+        eng = self.engine
+        if hasattr(eng, "batch_metrics"):
+            return eng.batch_metrics(pred, y)
+        d = (pred - y).double()
+        hits = (pred.argmax(dim=1) == y.argmax(dim=1)).double().sum()
+        return torch.stack([(d * d).sum(), d.abs().sum(), hits, torch.tensor(float(d.numel()), dtype=torch.float64, device=d.device),
+                            torch.tensor(float(d.shape[0]), dtype=torch.float64, device=d.device)])
+
+    def evaluate(self, data, return_dict: bool = False):
+        """``model.evaluate``: exact means over all elements of ``data`` (an iterable of ``(x, y)``, CUDA or pinned host tensors) --
+        Keras' ``val_loss`` for ``loss='mse'`` plus ``mse``, ``mae``, ``accuracy`` (hpo_baseline_v1.py:127-129).  Under data
+        parallelism the sufficient statistics are all-reduced, so every rank returns the value of the GLOBAL validation set and
+        takes the same early-stopping / checkpoint decisions.  One D2H read at the end."""
+        eng = self.engine
+        acc = None
         for x, y in data:
-            d = self.engine.forward(x) - y
-            s = (d * d).sum()
-            se = s if se is None else se + s
-            n += d.numel()
-        return float(se.item()) / max(n, 1) if se is not None else float("nan")
+            if not self._on_device(x):
+                x, y = eng.stage_host_batch(x, y)
+                s = self._batch_metrics(eng.forward(x), y)
+                eng.release_staged()
+            else:
+                s = self._batch_metrics(eng.forward(x), y)
+            acc = s.clone() if acc is None else acc + s
+        if acc is None:
+            acc = torch.zeros(5, dtype=torch.float64, device=self.device)
+        if self.world > 1:
+            torch.distributed.all_reduce(acc, group=self.pg)
+        se, ae, hits, n, rows = (float(v) for v in acc.tolist())
+        out = {"loss": se / n if n else float("nan"), "mse": se / n if n else float("nan"), "mae": ae / n if n else float("nan"),
+               "accuracy": hits / rows if rows else float("nan")}
+        return out if return_dict else out["loss"]
 
     def fit(self, train, epochs: int, validation_data=None, checkpoint_best: Optional[str] = None, checkpoint_last: Optional[str] = None,
-            csv_log: Optional[str] = None, early_stopping_patience: Optional[int] = None, initial_epoch: int = 0, verbose: int = 2) -> dict:
+            csv_log: Optional[str] = None, early_stopping_patience: Optional[int] = None, initial_epoch: int = 0, verbose: int = 2,
+            train_metrics: bool = True) -> dict:
         """``model.fit(tds, epochs=.., validation_data=tds_val, callbacks=[checkpoint_best, checkpoint_last, csv_logger, earlystop])`` as
         the reference's retraining script drives it (baseline_v1/step2_retrain/step2_retrain.py:252-286):
 
         * ``train`` / ``validation_data``: objects with ``.epoch(e)`` yielding ``(x, y)`` (``NpyColumnStream``: reshuffled every
           epoch like ``shuffle(reshuffle_each_iteration=True)``) or plain re-iterable collections of ``(x, y)``;
         * ``loss`` of an epoch = mean of its batch losses (what Keras prints), accumulated on the device: one D2H read per epoch;
+          ``mse`` equals it for ``loss='mse'``; ``mae`` / ``accuracy`` of the training batches (``train_metrics``) come from the
+          predictions of a forward pass on each batch BEFORE its update, which is what Keras' running metrics see;
         * ``checkpoint_best``: saved when ``val_loss`` improves (``ModelCheckpoint(monitor='val_loss', save_best_only=True)``);
-          ``checkpoint_last``: saved every epoch; ``csv_log``: ``epoch,loss,val_loss`` rows appended (``CSVLogger(append=True)``);
-          ``early_stopping_patience``: stop after that many epochs without a new best ``val_loss`` (``EarlyStopping('val_loss', patience)``).
+          ``checkpoint_last``: saved every epoch; ``csv_log``: rows ``epoch,accuracy,loss,mae,mse,val_accuracy,val_loss,val_mae,val_mse``
+          appended (``CSVLogger(append=True)`` writes ``epoch`` and then the log keys in sorted order);
+          ``early_stopping_patience``: stop after that many epochs without a new best ``val_loss`` (``EarlyStopping('val_loss', patience)``);
+        * data parallelism: the epoch loss and all validation statistics are all-reduced, so every rank takes the same decisions;
+          files are written by rank 0 only.
 
-        Returns ``{"loss": [...], "val_loss": [...], "stopped_epoch": e or None}`` (Keras' ``History.history`` plus the stop epoch)."""
-        history = {"loss": [], "val_loss": [], "stopped_epoch": None}
+        Returns Keras' ``History.history`` (``loss, mse, mae, accuracy`` and their ``val_`` twins) plus ``stopped_epoch``."""
+        keys = list(self.METRICS) + ["val_" + k for k in self.METRICS]
+        history = {k: [] for k in keys}
+        history["stopped_epoch"] = None
+        csv_keys = sorted(keys)
         best, wait = float("inf"), 0
-        if csv_log is not None:
+        writer = self.rank == 0
+        if csv_log is not None and writer:
             import os
             if not os.path.exists(csv_log) or os.path.getsize(csv_log) == 0:
                 with open(csv_log, "a") as f:
-                    f.write("epoch,loss,val_loss\n")
+                    f.write("epoch," + ",".join(csv_keys) + "\n")
         for epoch in range(initial_epoch, epochs):
             batches = train.epoch(epoch) if hasattr(train, "epoch") else train
-            total, nb = None, 0
+            total, nb, stats = None, 0, None
             for x, y in batches:
-                l = self.step(x, y, return_loss=False)
-                l = l if isinstance(l, torch.Tensor) else torch.as_tensor(l)
+                if train_metrics:
+                    xs, ys, staged = x, y, False
+                    if not self._on_device(x):
+                        # the metrics forward and the step share ONE staged copy of the batch
+                        xs, ys = self.engine.stage_host_batch(x, y)
+                        staged = True
+                    s = self._batch_metrics(self.engine.forward(xs), ys)
+                    stats = s.clone() if stats is None else stats + s
+                    l = self._step_local(xs, ys)
+                    if staged:
+                        self.engine.release_staged()
+                else:
+                    l = self._step_local(x, y)
                 total = l.detach().clone().reshape(()) if total is None else total + l.detach().reshape(())
                 nb += 1
-            if self.world > 1 and total is not None:                 # every rank holds its share of the global-mean loss
+            if total is None:
+                total = torch.zeros((), dtype=torch.float32, device=self.device)
+            if self.world > 1:                                       # every rank holds its share of the global-mean loss
                 torch.distributed.all_reduce(total, group=self.pg)
+                if stats is not None:
+                    torch.distributed.all_reduce(stats, group=self.pg)
             loss = float(total.item()) / nb if nb else float("nan")
-            history["loss"].append(loss)
-            val = None
+            row = {"loss": loss, "mse": loss, "mae": float("nan"), "accuracy": float("nan")}
+            if stats is not None:
+                se, ae, hits, n, rows = (float(v) for v in stats.tolist())
+                row["mae"], row["accuracy"] = ae / n, hits / rows
             if validation_data is not None:
                 vb = validation_data.epoch(epoch) if hasattr(validation_data, "epoch") else validation_data
-                val = self.evaluate(vb)
-                history["val_loss"].append(val)
-            if verbose:
-                print(f"Epoch {epoch + 1}/{epochs} - loss: {loss:.6g}" + (f" - val_loss: {val:.6g}" if val is not None else ""), flush=True)
-            if csv_log is not None:
+                for k, v in self.evaluate(vb, return_dict=True).items():
+                    row["val_" + k] = v
+            for k in keys:
+                if k in row:
+                    history[k].append(row[k])
+            val = row.get("val_loss")
+            if verbose and writer:
+                print(f"Epoch {epoch + 1}/{epochs} - " + " - ".join(f"{k}: {row[k]:.6g}" for k in keys if k in row), flush=True)
+            if csv_log is not None and writer:
                 with open(csv_log, "a") as f:
-                    f.write(f"{epoch},{loss!r},{'' if val is None else repr(val)}\n")
-            if checkpoint_last is not None:
+                    f.write(f"{epoch}," + ",".join(repr(row[k]) if k in row else "" for k in csv_keys) + "\n")
+            if checkpoint_last is not None and writer:
                 self.save_checkpoint(checkpoint_last)
             if val is not None:
                 if val < best:
                     best, wait = val, 0
-                    if checkpoint_best is not None:
+                    if checkpoint_best is not None and writer:
                         self.save_checkpoint(checkpoint_best)
                 else:
                     wait += 1
                     if early_stopping_patience is not None and wait >= early_stopping_patience:
                         history["stopped_epoch"] = epoch
                         break
+        if self.world > 1:
+            torch.distributed.barrier(group=self.pg)                 # rank 0's files are complete when any rank returns
         return history
-

@@ -266,6 +266,26 @@ int  csb_eval_metrics(const float* pred, const float* target, const float* x_nor
 #define CSB_CRPS_BLOCKS 64
 int  csb_eval_crps(const void* samples, const void* target, int is_f64, int64_t n_tc, int L, int S, double* out, double* scratch, void* stream);
 
+/* ---- fit-loop helpers ------------------------------------------------------------------------------------------------------------- */
+/* Sufficient statistics of Keras' `metrics=['mse','mae','accuracy']` (hpo_baseline_v1.py:127-129; step2_retrain.py:262 logs them and
+ * their val_ twins through CSVLogger) for one batch: pred, y device fp32 [B, F] dense.
+ * out5 (device, fp64) = {sum (p-y)^2, sum |p-y|, rows with argmax(p) == argmax(y) [first maximum, as tf.argmax], B*F, B}.
+ * scratch (device) needs CSB_BATCH_METRICS_SCRATCH doubles, zero before the first use (the kernel re-arms it).  Deterministic. */
+#define CSB_BATCH_METRICS_SCRATCH 2048
+int  csb_batch_metrics(const float* pred, const float* y, int64_t B, int32_t F, double* out5, double* scratch, void* stream);
+
+/* One training step of the heteroskedastic-regression model -- BOTH networks, loss, backward, optimizer -- as
+ * HeteroskedasticRegression.trainer runs it per batch (baseline_models/HSR/training/hsr.py:122-140):
+ *   mle == 0: loss = mean((y - mu)^2) (the first third of the epochs; the log-precision network gets no gradient and, like
+ *             torch.optim.Adam with grad None, no update);   mle != 0: loss = mean(exp(lp) (y - mu)^2 - lp);
+ *   torch.clip(loss, -1e5, 1e5).backward(); per-group L2 weight decay (wd_mean = alpha, wd_logprec = beta, hsr.py:100-107) with
+ *   `rule` (CSB_OPT_ADAM_TORCH or CSB_OPT_SGD in the reference).
+ * loss_out (device, fp32): the unclipped mean, what the reference appends to `losses`.  scratch: CSB_BATCH_METRICS_SCRATCH doubles,
+ * zero before the first use.  `flags`: CSB_FWD_NORMALIZE_IN.  Both handles: linear output layer, same widths / dtype. */
+int  csb_hsr_train_step(csb_mlp* mean, csb_mlp* logprec, const float* x, const float* y, int64_t B, int mle, uint32_t flags, int rule,
+                        float lr, float beta1, float beta2, float eps, float wd_mean, float wd_logprec, float* loss_out, double* scratch,
+                        void* stream);
+
 /* ---- input pipeline ------------------------------------------------------------------------------------------------------------- */
 /* dst[i, :] = src[idx[i], :] for i < n_rows (fp32 rows of row_len floats, device pointers, idx int64 on the device): the sample
  * shuffle of the reference's input pipelines -- tf.data `unbatch().shuffle(384*30).batch(B)` (hpo_baseline_v1.py:140-143,

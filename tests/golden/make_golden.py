@@ -179,7 +179,19 @@ def make_hsr():
     out["mu"], out["logprec"] = mu.detach().numpy(), logprec.detach().numpy()
     # the reference's own training loop: 3 epochs x 2 batches (epoch 0 MSE, epochs 1-2 NLL), Adam + weight decay
     net.zero_grad()
-    net.trainer(batches, epochs=3, save="/tmp/_hsr_golden.cp", plot=False, lr=1e-3, gamma=0.022)
+    # the trainer keeps its per-step losses local: record them at the torch.clip(loss, ...) call it makes once per step (hsr.py:138)
+    step_losses, real_clip = [], torch.clip
+
+    def recording_clip(t, *a, **k):
+        step_losses.append(float(t.detach()))
+        return real_clip(t, *a, **k)
+
+    torch.clip = recording_clip
+    try:
+        net.trainer(batches, epochs=3, save="/tmp/_hsr_golden.cp", plot=False, lr=1e-3, gamma=0.022)
+    finally:
+        torch.clip = real_clip
+    out["trainer_losses"] = np.asarray(step_losses, dtype=np.float64)
     for k, v in net.state_dict().items():
         out["final::" + k] = v.detach().clone().numpy()
     np.savez_compressed(os.path.join(HERE, "hsr_small.npz"), **out)

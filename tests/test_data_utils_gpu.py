@@ -132,19 +132,30 @@ def test_hsr_layernorm_model_against_reference_golden(golden_dir, dtype, tol_out
                 assert err <= tol_g, (mode, key, err)
 
 
-def test_hsr_trainer_matches_reference_trainer_end_state(golden_dir, capsys):
+def test_hsr_trainer_matches_reference_trainer_end_state(golden_dir, capsys, monkeypatch):
     """HSR.trainer (same arguments as hsr.py:83-142) from the reference's initial weights on the reference's two batches: after
     3 epochs x 2 batches (MSE phase, then NLL; Adam with the per-group weight decay) the parameters equal the end state of the
-    REFERENCE's own trainer run (tests/golden/hsr_small.npz).  fp32 engine: Adam divides by sqrt(v), so elements whose gradient is
-    cancellation noise may move by O(lr) either way -- the bound is per tensor in relative L2."""
+    REFERENCE's own trainer run (tests/golden/hsr_small.npz) and every per-step loss equals the one the reference computed.
+    fp32 engine: Adam divides by sqrt(v), so elements whose gradient is cancellation noise may move by O(lr) either way -- the bound
+    is per tensor in relative L2.  The whole step (both networks, loss, clip, per-group L2 Adam) is csb_hsr_train_step: torch's
+    optimizers and autograd are made to raise if anything touches them."""
     from climsim_b200.baseline_models import HSR
     g = np.load(os.path.join(golden_dir, "hsr_small.npz"))
     sd = {k[len("init::"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("init::")}
     net = HSR(124, 128, hidden_dims=32, layers=2, dtype="fp32", max_batch=64)
     net.load_reference_state_dict(sd)
     batches = [{"x": torch.from_numpy(g[f"x{i}"]), "y": torch.from_numpy(g[f"y{i}"])} for i in range(2)]
+
+    def forbidden(*a, **k):
+        raise AssertionError("HSR.trainer must not fall back to torch optimizers / autograd")
+
+    monkeypatch.setattr(torch.optim, "Adam", forbidden)
+    monkeypatch.setattr(torch.optim, "SGD", forbidden)
+    monkeypatch.setattr(torch.Tensor, "backward", forbidden)
     losses = net.trainer(batches, epochs=3, save=os.devnull, plot=False, lr=1e-3, gamma=0.022)
+    monkeypatch.undo()
     assert len(losses) == 6 and "alpha:" in capsys.readouterr().out
+    np.testing.assert_allclose(losses, g["trainer_losses"], rtol=2e-4)       # epochs 0: MSE; 1, 2: Gaussian NLL (hsr.py:128-136)
     got = net.reference_state_dict()
     final = {k[len("final::"):]: g[k] for k in g.files if k.startswith("final::")}
     assert sorted(got) == sorted(final)
@@ -342,3 +353,49 @@ def test_gpu_crps_matches_reference_golden(golden_dir):
         np.testing.assert_allclose(got32, want, rtol=2e-6)
     with pytest.raises(NotImplementedError):
         du.calc_CRPS(torch.from_numpy(g["crps_samples"]).cuda(), torch.from_numpy(g["tw_ptend_t"]).cuda(), avg_grid=False)
+
+
+def test_hsr_trainer_bf16_tracks_the_reference_losses(golden_dir):
+    """The same run on the tensor-core engine (bf16 operands, fp32 accumulation / master weights / optimizer, LayerNorm parameters
+    updated by the fused optimizer launch): the loss trajectory follows the reference's within bf16 rounding."""
+    from climsim_b200.baseline_models import HSR
+    g = np.load(os.path.join(golden_dir, "hsr_small.npz"))
+    sd = {k[len("init::"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("init::")}
+    net = HSR(124, 128, hidden_dims=32, layers=2, dtype="bf16", max_batch=64)
+    net.load_reference_state_dict(sd)
+    batches = [{"x": torch.from_numpy(g[f"x{i}"]), "y": torch.from_numpy(g[f"y{i}"])} for i in range(2)]
+    losses = net.trainer(batches, epochs=3, save=os.devnull, plot=False, lr=1e-3, gamma=0.022)
+    np.testing.assert_allclose(losses, g["trainer_losses"], rtol=3e-2)
+    got = net.reference_state_dict()
+    for k in got:
+        want = g["final::" + k]
+        err = np.linalg.norm(got[k].cpu().numpy() - want) / max(np.linalg.norm(want), 1e-12)
+        assert err <= 5e-2, (k, err)                                    # six Adam steps of lr 1e-3 on bf16-rounded gradients
+
+
+def test_hsr_step_loss_clip_blocks_the_gradient():
+    """torch.clip(loss, -1e5, 1e5).backward(): outside the interval the gradient is zero -- parameters then move by the weight decay
+    alone (hsr.py:138).  Targets of 1e4 make the MSE 1e8."""
+    from climsim_b200.baseline_models import HSR
+    net = HSR(124, 128, hidden_dims=64, layers=1, dtype="fp32", max_batch=32)
+    x, y = 0.3 * torch.randn(32, 124), torch.full((32, 128), 1.0e4)
+    before = net.mean.flat.detach().clone()
+    losses = net.trainer([{"x": x, "y": y}], epochs=3, save=os.devnull, plot=False, optimizer="sgd", lr=1e-2, gamma=0.0)   # alpha = 0
+    assert losses[0] > 1e5
+    assert torch.equal(net.mean.flat.detach(), before)                  # SGD without decay and a zero gradient: nothing moves
+
+
+@pytest.mark.parametrize("B,F", [(1, 128), (777, 128), (4096, 368), (33, 10)])
+def test_batch_metrics_kernel_against_torch(B, F):
+    """csb_batch_metrics = the sufficient statistics of Keras' metrics=['mse','mae','accuracy'] (hpo_baseline_v1.py:127-129)."""
+    from climsim_b200 import MLPEngine
+    eng = MLPEngine(8, [(8, "none", 0.0)], dtype="fp32", max_batch=8)
+    g = torch.Generator().manual_seed(B)
+    p, y = torch.randn(B, F, generator=g).cuda(), torch.randn(B, F, generator=g).cuda()
+    p[0, 3] = p[0].max() + 1; p[0, 7] = p[0, 3]                       # a tie: the first maximum wins (tf.argmax)
+    for _ in range(2):                                                  # the scratch ticket re-arms itself
+        got = eng.batch_metrics(p, y).cpu().numpy()
+    d = (p - y).double()
+    want = [float((d * d).sum()), float(d.abs().sum()), float((p.argmax(1) == y.argmax(1)).sum()), B * F, B]
+    np.testing.assert_allclose(got, want, rtol=1e-6)
+    assert int(p[0].argmax()) == 3

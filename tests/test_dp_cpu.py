@@ -192,8 +192,14 @@ def test_fit_driver_callbacks(tmp_path):
     assert h["loss"][-1] < h["loss"][0] and tr.iteration == 12
     want_val = float(((eng.forward(xv) - yv) ** 2).mean())
     assert h["val_loss"][-1] == pytest.approx(want_val, rel=1e-6)
+    # Keras' metrics=['mse','mae','accuracy'] (hpo_baseline_v1.py:127-129): exact means over the validation elements
+    pv = eng.forward(xv)
+    assert h["val_mse"][-1] == h["val_loss"][-1] and h["val_mae"][-1] == pytest.approx(float((pv - yv).abs().mean()), rel=1e-6)
+    assert h["val_accuracy"][-1] == pytest.approx(float((pv.argmax(1) == yv.argmax(1)).float().mean()), abs=1e-9)
+    assert h["mse"] == h["loss"] and all(0.0 < m < 1.0 for m in h["mae"]) and all(0.0 <= a <= 1.0 for a in h["accuracy"])
     rows = open(log).read().strip().splitlines()
-    assert rows[0] == "epoch,loss,val_loss" and len(rows) == 5 and rows[1].startswith("0,")
+    # CSVLogger: 'epoch' first, then the log keys in sorted order (step2_retrain.py:262)
+    assert rows[0] == "epoch,accuracy,loss,mae,mse,val_accuracy,val_loss,val_mae,val_mse" and len(rows) == 5 and rows[1].startswith("0,")
     assert os.path.exists(best) and os.path.exists(last) and not os.path.exists(best + ".npz")
     # the last checkpoint restores everything: a restored trainer continues exactly like the original
     eng2 = OracleEngine(seed=5)
@@ -209,3 +215,69 @@ def test_fit_driver_callbacks(tmp_path):
     h3 = tr3.fit(train, epochs=20, validation_data=val, csv_log=log, early_stopping_patience=3, verbose=0)
     assert h3["stopped_epoch"] == 3 and len(h3["val_loss"]) == 4
     assert len(open(log).read().strip().splitlines()) == 5 + 4
+
+
+def _fit_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from climsim_b200.stream import StreamPlan
+    from climsim_b200.trainer import Trainer
+    torch.set_num_threads(1)
+    x, y = _batch(99)                                                   # 99 rows over 2 ranks: the shares are padded to 50 rows each
+    xv, yv = _batch(41)
+    plan = StreamPlan(99, batch_size=16, window=32, seed=5, rank=rank, world=world)
+    vplan = StreamPlan(41, batch_size=16, window=16, shuffle=False, rank=rank, world=world)
+
+    class Split:
+        def __init__(self, p, a, b):
+            self.p, self.a, self.b = p, a, b
+
+        def epoch(self, e):
+            return ((self.a[r], self.b[r]) for r in self.p.epoch_rows(e))
+
+    eng = OracleEngine(seed=rank)                                       # different initial parameters per rank: Trainer must broadcast rank 0's
+    tr = Trainer(eng, rule="adam_keras", lr=0.0 if os.environ.get("DP_FIT_LR0") else 1e-3)
+    log, ck = out + ".csv", out + ".ckpt"
+    h = tr.fit(Split(plan, x, y), epochs=6, validation_data=Split(vplan, xv, yv), csv_log=log, checkpoint_last=ck,
+               early_stopping_patience=2, verbose=0)
+    np.savez(out + f".{rank}.npz", flat=eng.flat(), val=np.array(h["val_loss"]), loss=np.array(h["loss"]),
+             stopped=-1 if h["stopped_epoch"] is None else h["stopped_epoch"], it=tr.iteration)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("lr0", [False, True])
+def test_two_rank_fit_takes_the_same_decisions_on_every_rank(tmp_path, lr0, monkeypatch):
+    """under data parallelism val_loss must be the GLOBAL value on every rank (else early stopping diverges and the next
+    all-reduce deadlocks), the epoch loss is reduced exactly once, only rank 0 writes files, rank 0's parameters are broadcast, and
+    ranks take equally many steps although 2 does not divide the 99 training rows."""
+    if lr0:
+        monkeypatch.setenv("DP_FIT_LR0", "1")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "fit")
+    mp.spawn(_fit_worker, args=(2, port, out), nprocs=2, join=True)
+    a, b = np.load(out + ".0.npz"), np.load(out + ".1.npz")
+    np.testing.assert_array_equal(a["flat"], b["flat"])
+    np.testing.assert_array_equal(a["val"], b["val"])
+    np.testing.assert_array_equal(a["loss"], b["loss"])
+    assert int(a["stopped"]) == int(b["stopped"]) and int(a["it"]) == int(b["it"])
+    if lr0:
+        assert int(a["stopped"]) == 2 and len(a["val"]) == 3          # never improves after epoch 0: patience 2 stops at epoch 2
+    else:
+        assert int(a["stopped"]) == -1 and a["loss"][-1] < a["loss"][0]
+    rows = open(out + ".csv").read().strip().splitlines()
+    assert len(rows) == 1 + len(a["val"])                               # one header + one row per epoch: a single writer
+    # the global validation loss: 41 rows padded to 21 + 21 (one row seen twice), exact mean over what the ranks evaluated
+    xv, yv = _batch(41)
+    eng = OracleEngine(seed=0)
+    if lr0:
+        rows_seen = np.concatenate([np.arange(0, 21), np.arange(20, 41)])
+        want = float(((eng.forward(xv[rows_seen]) - yv[rows_seen]) ** 2).mean())
+        assert a["val"][0] == pytest.approx(want, rel=1e-6)
+
+
+def test_weight_decay_is_rejected_for_rules_without_it():
+    from climsim_b200.trainer import Trainer
+    with pytest.raises(ValueError):
+        Trainer(OracleEngine(), rule="adam_keras", weight_decay=1e-2)
