@@ -20,6 +20,7 @@ LOSS = {"mse": 0, "mae": 1, "huber": 2}
 OPT = {"adam_keras": 0, "adam": 0, "adam_torch": 1, "sgd": 2, "radam": 3, "rmsprop": 4}
 FWD_NORMALIZE_IN, FWD_DENORM_OUT, FWD_KEEP_ACTIVATIONS, TRAIN_FUSED_OPT = 1, 2, 4, 8
 BATCH_METRICS_SCRATCH = 2048
+HSR_NO_OPT = 16
 
 
 class MlpCfg(C.Structure):

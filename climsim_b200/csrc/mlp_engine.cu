@@ -1743,9 +1743,10 @@ int csb_hsr_train_step(csb_mlp* mean, csb_mlp* logprec, const float* x, const fl
   for (int i = 0; i < 2; ++i) {
     csb_mlp* h = nets[i];
     if (!h) continue;
-    if ((rc = run_backward_chain(h, B, nullptr, st, 0, nullptr, fused_opt_supported(h)))) return rc;
+    const bool no_opt = (flags & CSB_HSR_NO_OPT) != 0;      // data parallelism: the caller all-reduces csb_mlp_grad_buffer, then csb_mlp_apply_opt
+    if ((rc = run_backward_chain(h, B, nullptr, st, 0, nullptr, !no_opt && fused_opt_supported(h)))) return rc;
     h->acts_B = -1;
-    if ((rc = csb_mlp_apply_opt(h, rule, lr, beta1, beta2, eps, wds[i], stream))) return rc;
+    if (!no_opt && (rc = csb_mlp_apply_opt(h, rule, lr, beta1, beta2, eps, wds[i], stream))) return rc;
   }
   return CSB_OK;
 }

@@ -321,15 +321,18 @@ class MLPEngine:
 
 def hsr_train_step(mean: MLPEngine, logprec: MLPEngine, x: torch.Tensor, y: torch.Tensor, mle: bool, loss_out: torch.Tensor,
                    scratch: torch.Tensor, rule: str = "adam_torch", lr: float = 1e-4, beta1: float = 0.9, beta2: float = 0.999,
-                   eps: float = 1e-8, wd_mean: float = 0.0, wd_logprec: float = 0.0, normalize_in: bool = False) -> None:
+                   eps: float = 1e-8, wd_mean: float = 0.0, wd_logprec: float = 0.0, normalize_in: bool = False,
+                   apply_opt: bool = True) -> None:
     """``csb_hsr_train_step``: one step of both heteroskedastic-regression networks (forward, MSE / Gaussian-NLL loss with the
     reference's clip, backward, per-group L2 optimizer) entirely inside the engine; the loss lands in ``loss_out`` (a one-element
-    CUDA fp32 tensor, e.g. a slice of a per-epoch loss array) without any host synchronisation."""
+    CUDA fp32 tensor, e.g. a slice of a per-epoch loss array) without any host synchronisation.  ``apply_opt=False`` stops after the
+    backward passes (data parallelism: all-reduce ``grad_buffer()`` of each engine, then ``apply_opt`` with its own decay)."""
     x, y = _f32_cuda(x, "x"), _f32_cuda(y, "y")
     assert loss_out.is_cuda and loss_out.dtype == torch.float32 and scratch.is_cuda and scratch.dtype == torch.float64
     assert scratch.numel() >= _lib.BATCH_METRICS_SCRATCH
     _lib.check(mean.lib.csb_hsr_train_step(mean._h, logprec._h, x.data_ptr(), y.data_ptr(), x.shape[0], int(bool(mle)),
-                                           _lib.FWD_NORMALIZE_IN if normalize_in else 0, _lib.OPT[rule], lr, beta1, beta2, eps,
+                                           (_lib.FWD_NORMALIZE_IN if normalize_in else 0) | (0 if apply_opt else _lib.HSR_NO_OPT),
+                                           _lib.OPT[rule], lr, beta1, beta2, eps,
                                            wd_mean, wd_logprec, loss_out.data_ptr(), scratch.data_ptr(), _lib.current_stream_ptr()),
                "csb_hsr_train_step")
 

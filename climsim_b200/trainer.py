@@ -35,6 +35,13 @@ def cyclical_lr(step: int, initial_lr: float = 2.5e-4, max_lr: float = 2.5e-3, s
     return initial_lr + (max_lr - initial_lr) * max(0.0, 1 - x) / (2.0 ** (cycle - 1))
 
 
+def ed_step_lr(epoch: int, lr_init: float = 1e-4, drop: float = 5.0, every: int = 7) -> float:
+    """The encoder-decoder's ``LearningRateScheduler`` (ClimSIM_ED_1_3_train.py:98-122): the learning rate is divided by 5 after
+    every 7th epoch -- lr_init for epochs 0-6, /5 for 7-13, /25, /125, /625, /3125 for 35-41 (the reference's function returns None
+    from epoch 42 on, which Keras rejects; the run has 40 epochs)."""
+    return lr_init / (drop ** (epoch // every))
+
+
 class Trainer:
     """``step(x, y)`` = H2D (if host tensors) -> forward + loss + backward -> gradient all-reduce -> optimizer.
 
@@ -202,7 +209,7 @@ class Trainer:
 
     def fit(self, train, epochs: int, validation_data=None, checkpoint_best: Optional[str] = None, checkpoint_last: Optional[str] = None,
             csv_log: Optional[str] = None, early_stopping_patience: Optional[int] = None, initial_epoch: int = 0, verbose: int = 2,
-            train_metrics: bool = True) -> dict:
+            train_metrics: bool = True, lr_schedule: Optional[Callable[[int], float]] = None) -> dict:
         """``model.fit(tds, epochs=.., validation_data=tds_val, callbacks=[checkpoint_best, checkpoint_last, csv_logger, earlystop])`` as
         the reference's retraining script drives it (baseline_v1/step2_retrain/step2_retrain.py:252-286):
 
@@ -215,6 +222,8 @@ class Trainer:
           ``checkpoint_last``: saved every epoch; ``csv_log``: rows ``epoch,accuracy,loss,mae,mse,val_accuracy,val_loss,val_mae,val_mse``
           appended (``CSVLogger(append=True)`` writes ``epoch`` and then the log keys in sorted order);
           ``early_stopping_patience``: stop after that many epochs without a new best ``val_loss`` (``EarlyStopping('val_loss', patience)``);
+        * ``lr_schedule(epoch) -> lr``: Keras' ``LearningRateScheduler`` callback -- the learning rate is set at the start of every
+          epoch (``ed_step_lr`` is the encoder-decoder's schedule, ClimSIM_ED_1_3_train.py:98-122);
         * data parallelism: the epoch loss and all validation statistics are all-reduced, so every rank takes the same decisions;
           files are written by rank 0 only.
 
@@ -231,6 +240,8 @@ class Trainer:
                 with open(csv_log, "a") as f:
                     f.write("epoch," + ",".join(csv_keys) + "\n")
         for epoch in range(initial_epoch, epochs):
+            if lr_schedule is not None:
+                self.lr = float(lr_schedule(epoch))
             batches = train.epoch(epoch) if hasattr(train, "epoch") else train
             total, nb, stats = None, 0, None
             for x, y in batches:

@@ -281,7 +281,10 @@ int  csb_batch_metrics(const float* pred, const float* y, int64_t B, int32_t F, 
  *   torch.clip(loss, -1e5, 1e5).backward(); per-group L2 weight decay (wd_mean = alpha, wd_logprec = beta, hsr.py:100-107) with
  *   `rule` (CSB_OPT_ADAM_TORCH or CSB_OPT_SGD in the reference).
  * loss_out (device, fp32): the unclipped mean, what the reference appends to `losses`.  scratch: CSB_BATCH_METRICS_SCRATCH doubles,
- * zero before the first use.  `flags`: CSB_FWD_NORMALIZE_IN.  Both handles: linear output layer, same widths / dtype. */
+ * zero before the first use.  `flags`: CSB_FWD_NORMALIZE_IN; CSB_HSR_NO_OPT stops after the backward passes with the gradients in the
+ * handles' gradient buffers (data parallelism: all-reduce csb_mlp_grad_buffer of each network, then csb_mlp_apply_opt with its own
+ * decay -- in the MSE phase only for `mean`).  Both handles: linear output layer, same widths / dtype. */
+#define CSB_HSR_NO_OPT 16u
 int  csb_hsr_train_step(csb_mlp* mean, csb_mlp* logprec, const float* x, const float* y, int64_t B, int mle, uint32_t flags, int rule,
                         float lr, float beta1, float beta2, float eps, float wd_mean, float wd_logprec, float* loss_out, double* scratch,
                         void* stream);

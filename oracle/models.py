@@ -47,6 +47,34 @@ def _bf16_round(t: torch.Tensor) -> torch.Tensor:
     return t.to(torch.bfloat16).to(t.dtype)
 
 
+class _RoundNode(torch.autograd.Function):
+    """Marks a tensor the tensor-core engine keeps in bf16: ``fwd`` rounds the value on the way forward (a stored activation),
+    ``bwd`` rounds the gradient flowing back through this point (a stored dZ / dA).  With these nodes at the engine's storage
+    points, ordinary autograd over fp32 ops reproduces the arithmetic contract of the CSB_BF16 mode (bf16 operands, fp32
+    accumulation) for graphs that are awkward to back-propagate by hand (the ResNet-1D, the encoder-decoder)."""
+
+    @staticmethod
+    def forward(ctx, t, fwd, bwd):
+        ctx.bwd = bwd
+        return _bf16_round(t) if fwd else t.view_as(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (_bf16_round(g) if ctx.bwd else g), None, None
+
+
+def _mark(t: torch.Tensor, fwd: bool, bwd: bool, on: bool) -> torch.Tensor:
+    return _RoundNode.apply(t, fwd, bwd) if on else t
+
+
+def _emulated_leaves(params: Sequence[torch.Tensor], on: bool) -> List[torch.Tensor]:
+    """Leaves to differentiate with respect to: the parameters themselves, or -- emulating the engine -- bf16-rounded copies of
+    the kernels (the engine's bf16 weight copies; dW does not depend on W's own rounding) next to the fp32 biases."""
+    if not on:
+        return list(params)
+    return [(_bf16_round(p.detach()) if p.dim() > 1 else p.detach().clone()).requires_grad_(True) for p in params]
+
+
 # --------------------------------------------------------------------------------------------------------------
 # MLP_v1  (Keras functional model)
 # --------------------------------------------------------------------------------------------------------------
@@ -192,15 +220,28 @@ class EDRef:
     def num_parameters(self) -> int:
         return sum(p.numel() for p in self.params)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        h = x.to(self.dtype)
-        n = len(self.params) // 2
+    def forward(self, x: torch.Tensor, emulate_bf16: bool = False, params: Optional[Sequence[torch.Tensor]] = None) -> torch.Tensor:
+        """``emulate_bf16``: the rounding points of the CSB_BF16 engine (input, weights, every stored activation; on the way back
+        every stored dZ) -- see ``_RoundNode``."""
+        p = self.params if params is None else params
+        h = _bf16_round(x.to(self.dtype)) if emulate_bf16 else x.to(self.dtype)
+        n = len(p) // 2
         for i in range(n):
-            z = h @ self.params[2 * i] + self.params[2 * i + 1]
-            h = F.elu(z, alpha=1.0) if i == n - 1 else torch.relu(z)
+            z = h @ p[2 * i] + p[2 * i + 1]
+            if i == n - 1:
+                h = F.elu(_mark(z, False, True, emulate_bf16), alpha=1.0)          # dZ of the output layer is stored in bf16
+            else:
+                h = _mark(torch.relu(z), True, True, emulate_bf16)                # activation stored in bf16; dZ = bf16(dA * relu')
         return h
 
     __call__ = forward
+
+    def emulated_train_step(self, x: torch.Tensor, y: torch.Tensor, emulate_bf16: bool = True):
+        """(loss, grads in ``params`` order) of Keras ``loss='mse'`` with the engine's bf16 rounding points (autograd over
+        ``_RoundNode``-marked fp32 ops); ``emulate_bf16=False`` is plain fp32 autograd."""
+        leaves = _emulated_leaves(self.params, emulate_bf16)
+        loss = mse(y.to(self.dtype), self.forward(x, emulate_bf16, leaves))
+        return loss.detach(), list(torch.autograd.grad(loss, leaves))
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -257,26 +298,44 @@ class CNNRef:
             for b in self.params[1::2]:
                 b.copy_((torch.rand(b.shape, generator=gen, dtype=torch.float64) * 2 - 1).to(self.dtype) * scale)
 
-    def forward(self, x: torch.Tensor, masks=None) -> torch.Tensor:
-        """``masks``: optional list (one entry per block) of pairs of (B, 60, width) multipliers for the two Dropout layers."""
-        p = self.params
-        h = x.to(self.dtype)
+    def forward(self, x: torch.Tensor, masks=None, emulate_bf16: bool = False, params: Optional[Sequence[torch.Tensor]] = None) -> torch.Tensor:
+        """``masks``: optional list (one entry per block) of pairs of (B, 60, width) multipliers for the two Dropout layers.
+        ``emulate_bf16``: the storage points of the CSB_BF16 engine (climsim_b200/csrc/cnn_engine.cuh) are marked with
+        ``_RoundNode``: forward -- the packed input, relu(conv1), relu(conv2) (again after the dropout scaling), the block output
+        ``conv1x1(x_in) + relu(conv2)`` and elu(conv_out) are stored in bf16; backward -- dL/dz of the heads, dze, the block-output
+        gradient G, dz2, dz1 and the conv1-branch gradient T are stored in bf16, while ``conv1x1^T(G) + T`` is summed in fp32 before
+        its one rounding.  Weights enter as bf16 copies (``params`` = ``_emulated_leaves``)."""
+        p = self.params if params is None else params
+        e = emulate_bf16
+        h = _bf16_round(x.to(self.dtype)) if e else x.to(self.dtype)
         prev = h
         for i in range(self.depth):
             wc1, bc1, wc2, bc2, wr, br = p[6 * i: 6 * i + 6]
-            h = torch.relu(conv1d_same_cl(h, wc1, bc1))
+            h = _mark(prev, False, True, e and i > 0)                                 # T = bf16(conv1^T(dz1)); block 0's input needs no gradient
+            h = _mark(torch.relu(conv1d_same_cl(h, wc1, bc1)), True, True, e)         # h1 bf16; dz1 = bf16(conv2^T(dz2) * relu'(h1))
             if masks is not None:
-                h = h * masks[i][0]
-            h = torch.relu(conv1d_same_cl(h, wc2, bc2))
+                h = _mark(h * masks[i][0], True, True, e)
+            h = _mark(torch.relu(conv1d_same_cl(h, wc2, bc2)), True, True, e)         # h2 bf16; dz2 = bf16(G * relu'(h2))
             if masks is not None:
-                h = h * masks[i][1]
-            h = h + conv1d_same_cl(prev, wr, br)
+                h = _mark(h * masks[i][1], True, True, e)
+            h = _mark(h + conv1d_same_cl(prev, wr, br), True, True, e)                # block output bf16; G = bf16(conv1x1^T(G') + T')
             prev = h
         wo, bo, wl, bl, wrl, brl = p[6 * self.depth: 6 * self.depth + 6]
-        h = F.elu(conv1d_same_cl(h, wo, bo), alpha=1.0)
-        return torch.cat([h @ wl + bl, torch.relu(h @ wrl + brl)], dim=-1)
+        u = _mark(conv1d_same_cl(h, wo, bo), False, True, e)                          # dze = bf16((dzh . Wd^T) * elu'(e))
+        h = _mark(F.elu(u, alpha=1.0), True, False, e)                                # e stored in bf16
+        zl = _mark(h @ wl + bl, False, True, e)                                       # dzh (both heads) stored in bf16
+        zr = _mark(h @ wrl + brl, False, True, e)
+        return torch.cat([zl, torch.relu(zr)], dim=-1)
 
     __call__ = forward
+
+    def emulated_train_step(self, x: torch.Tensor, y: torch.Tensor, loss: str = "mae", masks=None, emulate_bf16: bool = True):
+        """(loss, grads in ``params`` order) of ``mae_adjusted`` / ``mse_adjusted`` with the engine's bf16 rounding points;
+        ``emulate_bf16=False`` is plain fp32 autograd."""
+        leaves = _emulated_leaves(self.params, emulate_bf16)
+        fn = mae_adjusted if loss == "mae" else mse_adjusted
+        val = fn(y.to(self.dtype), self.forward(x, masks, emulate_bf16, leaves))
+        return val.detach(), list(torch.autograd.grad(val, leaves))
 
 
 # --------------------------------------------------------------------------------------------------------------

@@ -281,3 +281,22 @@ def test_weight_decay_is_rejected_for_rules_without_it():
     from climsim_b200.trainer import Trainer
     with pytest.raises(ValueError):
         Trainer(OracleEngine(), rule="adam_keras", weight_decay=1e-2)
+
+
+def test_ed_learning_rate_schedule_and_fit_callback():
+    """ClimSIM_ED_1_3_train.py:98-122: lr / 5 after every 7th epoch; Trainer.fit applies it like LearningRateScheduler."""
+    from climsim_b200.trainer import Trainer, ed_step_lr
+    want = {0: 1e-4, 6: 1e-4, 7: 1e-4 / 5, 13: 1e-4 / 5, 14: 1e-4 / 25, 21: 1e-4 / 125, 28: 1e-4 / 625, 35: 1e-4 / 3125, 41: 1e-4 / 3125}
+    for e, lr in want.items():
+        assert ed_step_lr(e) == pytest.approx(lr, rel=1e-12)
+    seen = []
+
+    class Spy(OracleEngine):
+        def apply_opt(self, rule, lr, **kw):
+            seen.append(lr)
+            super().apply_opt(rule, lr, **kw)
+
+    x, y = _batch(32)
+    tr = Trainer(Spy(), rule="adam_keras", lr=123.0)
+    tr.fit([(x, y)], epochs=15, lr_schedule=ed_step_lr, verbose=0, train_metrics=False)
+    assert seen == [pytest.approx(ed_step_lr(e)) for e in range(15)]

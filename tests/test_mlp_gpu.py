@@ -414,3 +414,78 @@ def test_fused_optimizer_launch_is_bitwise_equal_to_the_three_launch_path(rule):
     for a, b in zip(out[False][1:6], out[True][1:6]):
         np.testing.assert_array_equal(a, b)
     assert out[False][6] == out[True][6] == 5
+
+
+def test_train_step_bf16_at_the_benchmark_batch():
+    """bench.py's workload itself -- MLP_v1, B = 65 536 (512 m-blocks, 10.4 waves of pair tiles, 8-49 weight-gradient splits), bf16 --
+    against the bf16-emulating oracle: loss and every gradient tensor, then the benchmark's own call sequence (Trainer.step: the
+    CUDA-graph replay of the step with the fused reduce + Adam + bf16 repack launch) against the plain sequence
+    train_step -> apply_opt: gradients and updated weights must be bit-identical."""
+    from climsim_b200.trainer import Trainer
+    units, B = (768, 640, 512, 640, 640), 65536
+    ref, eng = _oracle(units), _engine(units, "bf16", max_batch=B)
+    _load(eng, ref)
+    x, y = _batch(B)
+    xs, ys = x.cuda(), y.cuda()
+    emu_loss, emu_grads = ref.manual_train_step(x, y, emulate_bf16=True)
+    got_loss = eng.train_step(xs, ys).item()
+    g_plain = eng.get_grads_flat()
+    assert abs(got_loss - emu_loss.item()) <= 1e-3 * abs(emu_loss.item())
+    assert _per_tensor(eng, g_plain, _flat(emu_grads), _rel_l2) <= 1e-2
+    eng.apply_opt("adam_keras", lr=1e-3)
+    w_plain = eng.get_params_flat()
+    # the same step the way bench.py drives it; three calls so that the third one replays the captured CUDA graph
+    eng2 = _engine(units, "bf16", max_batch=B)
+    tr = Trainer(eng2, rule="adam_keras", lr=1e-3)
+    for it in range(3):
+        _load(eng2, ref)
+        eng2.set_opt_state(np.zeros(eng2.n_params, np.float32), np.zeros(eng2.n_params, np.float32), 0)
+        loss = tr.step(xs, ys)
+        assert loss == pytest.approx(got_loss, rel=1e-6)
+        np.testing.assert_array_equal(eng2.get_grads_flat(), g_plain)
+        np.testing.assert_array_equal(eng2.get_params_flat(), w_plain)
+
+
+def _ed_engine(dtype, max_batch):
+    from climsim_b200 import MLPEngine
+    widths = M.ed_widths()
+    layers = [(w, "relu", 0.0) for w in widths[:-1]] + [(widths[-1], "elu", 0.0)]
+    return MLPEngine(124, layers, head_relu_from=-1, dtype=dtype, max_batch=max_batch)
+
+
+@pytest.mark.parametrize("dtype,B", [("fp32", 714), ("bf16", 714), ("bf16", 4096)])
+def test_ed_train_step_parity(dtype, B):
+    """The encoder-decoder (ClimSIM_ED_1_3_train.py:56-92: 14 Dense layers, widths 463/231/115/57/28/5 padded to multiples of 64
+    inside the engine, ReLU, ELU output, 'mse'): loss and every gradient tensor of a training step.  fp32 engine: <= 1e-5 of
+    autograd on the oracle.  bf16 engine: <= 3e-2 relative L2 of the oracle with the engine's rounding points (1.7e-2 measured on
+    the first layer at B = 4096; the width-5 ReLU bottleneck makes the fp32 comparison meaningless -- one flipped unit changes a
+    quarter of the gradient -- and lets single bf16 ulp flips through to every encoder gradient).  Batch 714 is the size the SURVEY
+    quotes for the reference run."""
+    ref = M.EDRef(seed=0)
+    gen = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for b in ref.params[1::2]:
+            b.copy_(0.05 * (2 * torch.rand(b.shape, generator=gen) - 1))
+    eng = _ed_engine(dtype, B)
+    eng.set_params_flat(np.concatenate([p.detach().numpy().reshape(-1) for p in ref.params]))
+    x, y = _batch(B, seed=3)
+    want_loss, want_grads = ref.emulated_train_step(x, y, emulate_bf16=dtype == "bf16")
+    got_loss = eng.train_step(x.cuda(), y.cuda()).item()
+    got = eng.split_flat(eng.get_grads_flat())
+    assert len(got) == len(want_grads) == 28
+    if dtype == "fp32":
+        assert abs(got_loss - want_loss.item()) <= 1e-5 * abs(want_loss.item())
+        for i, (a, b) in enumerate(zip(got, want_grads)):
+            assert _relmax(a, b.numpy()) <= 2e-5, (i, a.shape, _relmax(a, b.numpy()))
+    else:
+        assert abs(got_loss - want_loss.item()) <= 2e-3 * abs(want_loss.item())
+        for i, (a, b) in enumerate(zip(got, want_grads)):
+            assert _rel_l2(a, b.numpy()) <= 1e-2, (i, a.shape, _rel_l2(a, b.numpy()))
+    # Keras Adam(lr=1e-4) on these gradients: the update matches the oracle optimizer fed the engine's own gradients
+    m = [torch.zeros_like(p) for p in ref.params]
+    v = [torch.zeros_like(p) for p in ref.params]
+    with torch.no_grad():
+        M.keras_adam_step(ref.params, [torch.from_numpy(np.array(g)) for g in got], m, v, 1, 1e-4)
+    eng.apply_opt("adam_keras", lr=1e-4)
+    for i, (a, p) in enumerate(zip(eng.split_flat(eng.get_params_flat()), ref.params)):
+        assert np.abs(a - p.detach().numpy()).max() <= 2e-6, i
