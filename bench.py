@@ -482,12 +482,17 @@ def run_mlp_v1(ctx: Ctx) -> dict:
         timed_s = ms_total * 1e-3
         peak, peak_src = choose_peak(ctx.peaks, clocks, timed_s)
         kinds, tot = {}, sum(ms for ms, _ in prof.values())
+        kind_flops = dict(KIND_FLOPS)
+        if prof.get("gemm_tn_dgrad", (0, 0))[1] / prof_steps < 5.5:
+            # fused tail (tail_kernel.cuh): the output layer's data gradient and weight gradient run inside the "head" launch
+            tail = 2 * 128 * 128
+            kind_flops["gemm_tn_head"] += 2 * tail; kind_flops["gemm_tn_dgrad"] -= tail; kind_flops["gemm_nt_wgrad"] -= tail
         for k, (ms, n) in prof.items():
             d = {"ms_per_step_serialised": ms / prof_steps, "launches_per_step": n / prof_steps, "share_of_step": ms / tot,
                  "ms_per_step": ms / tot * ms_step}
-            if k in KIND_FLOPS:
-                d["tflops"] = KIND_FLOPS[k] * B / (d["ms_per_step"] * 1e-3) / 1e12
-                d["tflops_serialised"] = KIND_FLOPS[k] * B / (ms / prof_steps * 1e-3) / 1e12
+            if k in kind_flops:
+                d["tflops"] = kind_flops[k] * B / (d["ms_per_step"] * 1e-3) / 1e12
+                d["tflops_serialised"] = kind_flops[k] * B / (ms / prof_steps * 1e-3) / 1e12
             kinds[k] = d
         dom = max((k for k in kinds if k in KIND_FLOPS), key=lambda k: kinds[k]["ms_per_step"])
         n_dom = kinds[dom]["launches_per_step"]
@@ -507,7 +512,7 @@ def run_mlp_v1(ctx: Ctx) -> dict:
                     "achieved_serialised_pass": kinds[dom]["tflops_serialised"],
                     "traffic": traffic, "traffic_note": f"bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum from profiles/{traffic_src} "
                                                         "(ncu --set full)" if traffic else None,
-                    "flops_per_launch": KIND_FLOPS[dom] * B / max(n_dom, 1), "avg_launch_ms": kinds[dom]["ms_per_step"] / max(n_dom, 1),
+                    "flops_per_launch": kind_flops[dom] * B / max(n_dom, 1), "avg_launch_ms": kinds[dom]["ms_per_step"] / max(n_dom, 1),
                     "step_tflops": step_tf, "step_frac_of_peak": step_tf / peak, "step_frac_of_burst": step_tf / ctx.peaks["tf_burst"],
                     "step_frac_of_sustained": step_tf / ctx.peaks["tf_sustained"]}
         cpu = cpu_baseline("mlp_v1", args.cpu_sample or CPU_SAMPLE["mlp_v1"], 8, 2, os.cpu_count() or 1) if world == 1 else None

@@ -22,6 +22,7 @@
 #include "simt_kernels.cuh"
 #include "fit_kernels.cuh"
 #include "tc_gemm.cuh"
+#include "tail_kernel.cuh"
 
 namespace csb {
 
@@ -72,6 +73,8 @@ static int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t cols, uint
 // ---------------------------------------------------------------------------------------------------------------
 static bool g_use_pairs = true;     // CSB_NO_PAIRS=1 falls back to the single-CTA kernels (debugging aid)
 static bool g_use_pdl = true;       // CSB_NO_PDL=1 launches every kernel fully serialised (debugging aid)
+static bool g_use_tail = true;      // CSB_NO_TAIL_FUSION=1: output layer, its data gradient and its weight gradient as three launches (A/B aid)
+static bool g_use_balanced = false; // CSB_BALANCED=1 (opt-in): balanced contiguous tile ranges instead of round-robin -- measured SLOWER
 
 // launch with (optionally) programmatic stream serialisation: see pdl_wait() in common.cuh
 template <typename... KArgs, typename... Args>
@@ -104,6 +107,7 @@ static int launch_tn(const CUtensorMap& ta, const CUtensorMap& tb, const tc::Gem
   if (p.dbg >> 16) grid = std::min(grid, (p.dbg >> 16) * CG);      // micro-benchmark: run on a few SMs only (no power capping)
   tc::GemmParams q = p;
   q.b_box_rows = std::min(p.N, BN) / CG;     // must equal the box the B tensor map was encoded with
+  q.balanced = (g_use_balanced && EPI != tc::EPI_HEAD_LOSS && EPI != tc::EPI_HEAD_OUT && EPI != tc::EPI_F32) ? 1 : 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(tc::TN_THREADS);
@@ -353,6 +357,7 @@ struct csb_mlp {
   bool side_on = false;
   // CSB_TRAIN_FUSED_OPT: the split partials of the last training step are still unreduced; csb_mlp_apply_opt consumes them
   bool pending = false;
+  bool pending_tail = false;                // the pending partials of the output layer were written by tail_kernel (one per CTA)
   int64_t pending_B = 0;
   int pending_n_loss = 0;
   float* pending_loss_out = nullptr;
@@ -520,6 +525,8 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
   g_use_nt_pairs = getenv("CSB_NO_NT_PAIRS") == nullptr;
   g_use_nt_narrow = getenv("CSB_NT_NARROW") != nullptr;
   g_use_staged = getenv("CSB_NO_STAGED_EPI") == nullptr;
+  g_use_balanced = getenv("CSB_BALANCED") != nullptr;
+  g_use_tail = getenv("CSB_NO_TAIL_FUSION") == nullptr;
   g_use_pdl = getenv("CSB_NO_PDL") == nullptr;
   csb_mlp* h = new (std::nothrow) csb_mlp();
   CSB_REQUIRE(h != nullptr, CSB_ENOMEM, "host allocation failed");
@@ -568,6 +575,7 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
       while (S < 64 && mt * ((nb - 1) * (S + 1) + nt_narrow_splits(S + 1)) <= groups) ++S;
       li.max_w_splits = S;
     }
+    if (h->bf16 && l == h->L - 1 && li.Kp == 128 && li.Np == 128) li.max_w_splits = std::max(li.max_w_splits, sm);   // tail_kernel: one partial per CTA
     li.b_splits = h->bf16 ? li.max_w_splits * nt_m_tiles(li.Kp, li.nt_cg) : 32;
     li.ws_w_off = ws_off; ws_off += (size_t)li.max_w_splits * li.Kp * li.Np;
     li.ws_b_off = ws_off; ws_off += (size_t)li.b_splits * li.Np;
@@ -946,6 +954,38 @@ static int run_head(csb_mlp* h, int64_t B, int fused_loss, const float* y, float
   return CSB_OK;
 }
 
+// The fused tail (tail_kernel.cuh) covers an output layer of exactly 128 x 128 padded columns behind a ReLU / LeakyReLU layer whose
+// sign mask exists, MSE without an output mask on a non-ELU head: MLP_v1.  Everything else keeps the three separate launches.
+static inline bool tail_fusable(const csb_mlp* h) {
+  if (!h->bf16 || !g_use_tail || h->L < 2) return false;
+  const LayerInfo& li = h->layer[h->L - 1];
+  return li.Kp == 128 && li.Np == 128 && !li.ln && h->amask[h->L - 2] != nullptr && h->cfg.loss == CSB_LOSS_MSE && !h->has_mask &&
+         li.act != CSB_ACT_ELU && h->out_dim % 4 == 0;
+}
+static inline int tail_grid(const csb_mlp* h, int64_t B) { return (int)std::min<int64_t>(ceil_div(B, 128), h->sm_count); }
+
+// output layer + loss + its data gradient + its weight / bias gradient partials in one launch (tail_kernel.cuh)
+static int run_tail(csb_mlp* h, int64_t B, const float* y, float grad_scale, cudaStream_t st) {
+  const int l = h->L - 1;
+  const LayerInfo &li = h->layer[l], &lp = h->layer[l - 1];
+  tc::TailParams p = {};
+  p.M = (int)B; p.act = li.act; p.alpha = li.alpha; p.head_relu_from = h->cfg.head_relu_from;
+  p.bias = h->params + li.b_off; p.loss_w = h->d_loss_w; p.y = y; p.ld_y = h->out_dim; p.out_dim = h->out_dim; p.grad_scale = grad_scale;
+  p.loss_partials = h->loss_partials;
+  p.prev_act = lp.act; p.prev_alpha = lp.alpha; p.mask_in = h->amask[l - 1]; p.ld_mask = (int)h->cap;
+  p.dz_prev = dz16(h, l - 1); p.ld_dz = lp.Np;
+  p.dw_out = h->ws + li.ws_w_off; p.db_out = h->ws + li.ws_b_off;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CSB_CUDA_CHECK(cudaFuncSetAttribute(tc::tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TailSmem::TOTAL));
+    attr_set = true;
+  }
+  CSB_CUDA_CHECK(launch_pdl(tc::tail_kernel, dim3((unsigned)tail_grid(h, B)), dim3(tc::TN_THREADS), (size_t)tc::TailSmem::TOTAL, st,
+                            h->tm_in[l].a_k128, h->tm_wt_s[l], h->tm_w_s[l], p));
+  prof_mark(h, K_GEMM_HEAD, st);
+  return CSB_OK;
+}
+
 static int check_batch(csb_mlp* h, int64_t B) {
   CSB_REQUIRE(B >= 0 && B <= h->cfg.max_batch, CSB_ESTATE, "batch %lld exceeds max_batch %lld", (long long)B, (long long)h->cfg.max_batch);
   return CSB_OK;
@@ -976,10 +1016,11 @@ int csb_mlp_forward(csb_mlp* h, const float* x, float* y_pred, int64_t B, uint32
 // backward chain: given dZ_{L-1} in dz(L-1), produce all parameter gradients (and optionally dx)
 // ---------------------------------------------------------------------------------------------------------------
 // split-K geometry of the weight-gradient GEMM of layer l at batch B (CSB_BF16)
-static inline int wgrad_splits(const csb_mlp* h, int l, int64_t B, int* rb_per_split, int* rb_per_split_narrow = nullptr) {
+static inline int wgrad_splits(const csb_mlp* h, int l, int64_t B, int* rb_per_split, int* rb_per_split_narrow = nullptr, bool tail = false) {
   const LayerInfo& li = h->layer[l];
+  if (tail && l == h->L - 1) return tail_grid(h, B);               // one partial per CTA of tail_kernel
   const int num_rb = (int)ceil_div(B, 64);
-  int splits = std::max(1, std::min(li.max_w_splits, num_rb));
+  int splits = std::max(1, std::min(std::min(li.max_w_splits, 64), num_rb));      // (slots beyond 64 exist for tail_kernel only)
   const int rps = (int)ceil_div(num_rb, splits);
   if (rb_per_split) *rb_per_split = rps;
   splits = (int)ceil_div(num_rb, rps);
@@ -1010,7 +1051,7 @@ static int flush_pending(csb_mlp* h, cudaStream_t st) {
   int64_t max_len = 4;
   for (int l = h->L - 1; l >= 0; --l) {
     const LayerInfo& li = h->layer[l];
-    const int splits = wgrad_splits(h, l, h->pending_B, nullptr);
+    const int splits = wgrad_splits(h, l, h->pending_B, nullptr, nullptr, h->pending_tail);
     tab.seg[tab.n++] = {h->ws + li.ws_w_off, (size_t)li.Kp * li.Np, h->grads + li.w_off, (int64_t)li.Kp * li.Np, splits};
     tab.seg[tab.n++] = {h->ws + li.ws_b_off, (size_t)li.Np, h->grads + li.b_off, (int64_t)li.Np, splits * nt_m_tiles(li.Kp, li.nt_cg)};
     if (li.ln) {
@@ -1035,14 +1076,24 @@ static inline int head_loss_partials(const csb_mlp* h, int64_t B) {
 }
 
 static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st, int n_loss_partials = 0, float* loss_out = nullptr,
-                              bool defer_reduce = false) {
+                              bool defer_reduce = false, bool tail_done = false) {
   simt::SegmentTable tab;
   tab.n = 0;
   tab.loss_partials = h->loss_partials; tab.n_loss = n_loss_partials; tab.loss_out = loss_out;
   int64_t max_len = 4;
   const bool conc = h->bf16 && h->side_on && !h->prof_on;      // per-kind profiling wants the launches back to back on one stream
+  h->pending_tail = false;
   for (int l = h->L - 1; l >= 0; --l) {
     const LayerInfo& li = h->layer[l];
+    if (tail_done && l == h->L - 1) {
+      // tail_kernel already produced dZ of the layer below and this layer's gradient partials (one per CTA)
+      const int splits = tail_grid(h, B);
+      tab.seg[tab.n++] = {h->ws + li.ws_w_off, (size_t)li.Kp * li.Np, h->grads + li.w_off, (int64_t)li.Kp * li.Np, splits};
+      tab.seg[tab.n++] = {h->ws + li.ws_b_off, (size_t)li.Np, h->grads + li.b_off, (int64_t)li.Np, splits};
+      max_len = std::max<int64_t>(max_len, (int64_t)li.Kp * li.Np);
+      h->pending_tail = true;
+      continue;
+    }
     if (li.ln) {
       // the buffer holds du_l = dA_l * act'(a_l): LayerNorm parameter gradients, then du -> dz in place
       const int S = ln_grad_splits(h, l, B);
@@ -1197,7 +1248,11 @@ static int train_step_body(csb_mlp* h, const float* x, const float* y, int64_t B
   if ((rc = run_hidden_forward(h, B, st))) return rc;
   int n_partials;
   const int l = h->L - 1;
-  if (h->bf16) {
+  const bool tail = tail_fusable(h);
+  if (tail) {
+    if ((rc = run_tail(h, B, y, grad_scale, st))) return rc;
+    n_partials = (int)ceil_div(B, 128) * tc::TN_EPI_WARPS;
+  } else if (h->bf16) {
     if ((rc = run_head(h, B, 1, y, grad_scale, st))) return rc;
     n_partials = head_loss_partials(h, B);
   } else {
@@ -1212,7 +1267,7 @@ static int train_step_body(csb_mlp* h, const float* x, const float* y, int64_t B
   }
   // the scalar loss is summed inside the gradient-reduction launch at the end of the backward pass
   const bool defer = (flags & CSB_TRAIN_FUSED_OPT) != 0 && fused_opt_supported(h);
-  if ((rc = run_backward_chain(h, B, nullptr, st, n_partials, loss_out, defer))) return rc;
+  if ((rc = run_backward_chain(h, B, nullptr, st, n_partials, loss_out, defer, tail))) return rc;
   h->acts_B = -1;
   return CSB_OK;
 }
@@ -1261,7 +1316,8 @@ int csb_mlp_train_step(csb_mlp* h, const float* x, const float* y, int64_t B, fl
       h->launches += g.n_launches;
       h->acts_B = -1;
       if ((flags & CSB_TRAIN_FUSED_OPT) != 0 && fused_opt_supported(h)) {      // what run_backward_chain records when it runs eagerly
-        h->pending = true; h->pending_B = B; h->pending_n_loss = head_loss_partials(h, B);
+        h->pending = true; h->pending_B = B; h->pending_tail = tail_fusable(h);
+        h->pending_n_loss = h->pending_tail ? (int)ceil_div(B, 128) * tc::TN_EPI_WARPS : head_loss_partials(h, B);
         h->pending_loss_out = lo;
       }
       return CSB_OK;
@@ -1337,11 +1393,11 @@ int csb_mlp_apply_opt(csb_mlp* h, int rule, float lr, float beta1, float beta2, 
     int max_items = 1;
     for (int l = 0; l < h->L; ++l) {
       const LayerInfo& li = h->layer[l];
-      const int splits = wgrad_splits(h, l, h->pending_B, nullptr);
+      const int splits = wgrad_splits(h, l, h->pending_B, nullptr, nullptr, h->pending_tail);
       tab.l[l] = {li.Kp, li.Np, li.w_off, li.b_off, h->w16[l], h->wt16[l], h->ws + li.ws_w_off, splits,
                   h->ws + li.ws_b_off, splits * nt_m_tiles(li.Kp, li.nt_cg),
-                  li.g_off, h->ws + li.ws_g_off, li.ln ? ln_grad_splits(h, l, h->pending_B) : 0};
-      max_items = std::max(max_items, (li.Kp / 32) * (li.Np / 64) + (int)ceil_div(li.Np / 4, 256) + (li.ln ? (int)ceil_div(li.Np / 2, 256) : 0));
+                  li.g_off, h->ws + li.ws_g_off, li.ln ? ln_grad_splits(h, l, h->pending_B) : 0, simt::fused_opt_tk(splits)};
+      max_items = std::max(max_items, (li.Kp / simt::fused_opt_tk(splits)) * (li.Np / 64) + (int)ceil_div(li.Np / 4, 256) + (li.ln ? (int)ceil_div(li.Np / 2, 256) : 0));
     }
     dim3 grid((unsigned)max_items, (unsigned)(h->L + 1));
     CSB_CUDA_CHECK(launch_pdl(simt::opt_fused_kernel, grid, dim3(256), 0, st, tab, o));
@@ -1360,7 +1416,7 @@ int csb_mlp_apply_opt(csb_mlp* h, int rule, float lr, float beta1, float beta2, 
     for (int l = 0; l < h->L; ++l) {
       const LayerInfo& li = h->layer[l];
       tab.l[l] = {li.Kp, li.Np, li.w_off, li.b_off, h->w16[l], h->wt16[l], h->grads + li.w_off, 1, h->grads + li.b_off, 1,
-                  li.g_off, h->grads + li.g_off, li.ln ? 1 : 0};
+                  li.g_off, h->grads + li.g_off, li.ln ? 1 : 0, 32};
       max_items = std::max(max_items, (li.Kp / 32) * (li.Np / 64) + (int)ceil_div(li.Np / 4, 256) + (li.ln ? (int)ceil_div(li.Np / 2, 256) : 0));
     }
     dim3 grid((unsigned)max_items, (unsigned)(h->L + 1));

@@ -634,7 +634,16 @@ struct Segment { const float* ws; size_t stride; float* grad; int64_t len; int s
 __device__ __forceinline__ float4 sum_partials4(const float* __restrict__ p, size_t stride, int splits) {
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
   int s = 0;
-  for (; s + 8 <= splits; s += 8) {               // (the additions stay in split order: only the loads are batched)
+  // (the additions stay in split order: only the loads are batched.  Sixteen in flight first: the output layer of the fused tail has
+  // one partial per CTA -- 148 -- and this walk is a pure latency chain, ~1.2 us per batch whatever its size)
+  for (; s + 16 <= splits; s += 16) {
+    float4 v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = __ldcs(reinterpret_cast<const float4*>(p + (size_t)(s + u) * stride));
+#pragma unroll
+    for (int u = 0; u < 16; ++u) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
+  }
+  for (; s + 8 <= splits; s += 8) {
     float4 v[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) v[u] = __ldcs(reinterpret_cast<const float4*>(p + (size_t)(s + u) * stride));
@@ -769,7 +778,11 @@ struct FusedOptLayer {
   const float* ws_b; int b_splits;      // partials of db: ws_b + s * Np
   // LayerNorm layers: gamma [Np] then beta [Np] at g_off, partials ws_g + s * 2 * Np (g_splits == 0: no LayerNorm)
   size_t g_off; const float* ws_g; int g_splits;
+  // rows of W per work item: 32, or 8 for a layer with many partials (the fused tail writes one per CTA): a block that walks 148
+  // partials of a 32 x 64 tile pulls 1.2 MB through one SM, which alone takes longer than the rest of the launch
+  int tk;
 };
+static inline int fused_opt_tk(int w_splits) { return w_splits > 32 ? 8 : 32; }
 struct FusedOptTable {
   int n; FusedOptLayer l[CSB_MAX_LAYERS];
   float *params, *grads, *m, *v;
@@ -785,17 +798,16 @@ __global__ void __launch_bounds__(256) opt_fused_kernel(const FusedOptTable tab,
   }
   const FusedOptLayer L = tab.l[blockIdx.y];
   // W_l in tiles of 32 (k) x 64 (n): thread -> 4 consecutive n (one float4) of rows ty and ty + 16
-  const int tiles_n = L.Np / 64, tiles = (L.Kp / 32) * tiles_n;
+  const int TK = L.tk;
+  const int tiles_n = L.Np / 64, tiles = (L.Kp / TK) * tiles_n;
   const int vec_b = (L.Np / 4 + 255) / 256, vec_items = vec_b + (L.g_splits > 0 ? (2 * L.Np / 4 + 255) / 256 : 0);
   const size_t wsz = (size_t)L.Kp * L.Np;
   __shared__ float t[32][65];
   for (int item = blockIdx.x; item < tiles + vec_items; item += gridDim.x) {
     if (item < tiles) {
-      const int k0 = (item / tiles_n) * 32, n0 = (item % tiles_n) * 64;
+      const int k0 = (item / tiles_n) * TK, n0 = (item % tiles_n) * 64;
       const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int k = ty + 16 * i;
+      for (int k = ty; k < TK; k += 16) {
         const size_t idx = (size_t)(k0 + k) * L.Np + n0 + 4 * tx, e = L.w_off + idx;
         const float4 g4 = sum_partials4(L.ws_w + idx, wsz, L.w_splits);
         const float4 w4 = *reinterpret_cast<const float4*>(tab.params + e), m4 = *reinterpret_cast<const float4*>(tab.m + e),
@@ -815,10 +827,12 @@ __global__ void __launch_bounds__(256) opt_fused_kernel(const FusedOptTable tab,
       __syncthreads();
       {  // transposed copy: 64 n-rows x 32 k; thread -> 8 consecutive k of one n (one 16-byte store)
         const int n = threadIdx.x >> 2, kq = (threadIdx.x & 3) * 8;
-        uint4 u;
-        u.x = pack_bf16x2(t[kq + 0][n], t[kq + 1][n]); u.y = pack_bf16x2(t[kq + 2][n], t[kq + 3][n]);
-        u.z = pack_bf16x2(t[kq + 4][n], t[kq + 5][n]); u.w = pack_bf16x2(t[kq + 6][n], t[kq + 7][n]);
-        *reinterpret_cast<uint4*>(L.wt16 + (size_t)(n0 + n) * L.Kp + k0 + kq) = u;
+        if (kq < TK) {
+          uint4 u;
+          u.x = pack_bf16x2(t[kq + 0][n], t[kq + 1][n]); u.y = pack_bf16x2(t[kq + 2][n], t[kq + 3][n]);
+          u.z = pack_bf16x2(t[kq + 4][n], t[kq + 5][n]); u.w = pack_bf16x2(t[kq + 6][n], t[kq + 7][n]);
+          *reinterpret_cast<uint4*>(L.wt16 + (size_t)(n0 + n) * L.Kp + k0 + kq) = u;
+        }
       }
       __syncthreads();
     } else {

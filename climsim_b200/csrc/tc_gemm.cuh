@@ -54,6 +54,7 @@ struct GemmParams {
   uint32_t* mask_out;          // EPI_BIAS_ACT: optional sign-bit mask (bit j of word w <-> column 32 w + j, set iff out > 0)
   const uint32_t* mask_in;     // EPI_DGRAD_MASK
   int ld_mask;                 // chunk-major layout [N/32][ld_mask]: word of (row r, columns 32w..32w+31) at w * ld_mask + r
+  int balanced;                // tile schedule: 0 round-robin over the (m, n-block) grid, 1 balanced contiguous unit ranges (TileIter)
   int dbg;                     // micro-benchmark knobs (scripts/microbench_gemm.py): 1 skip bias staging, 2 skip epilogue math + smem
                                // stores, 4 skip TMA store, 8 skip TMEM loads, 16 skip all TMA loads, 32 skip the MMAs, 64 skip the
                                // B loads, 128 skip the A loads.  0 in production.
@@ -594,6 +595,59 @@ struct TnSmem {
 // bit 2 = results staged in shared memory and written with coalesced stores (the launches whose time is the epilogue: K <= 256)
 // bit 3 = in-kernel cycle counters for the micro-benchmark (p.stats); production instantiations carry none of that code
 constexpr int VAR_ELU = 1, VAR_GENERAL_LOSS = 2, VAR_STAGED = 4, VAR_STATS = 8;
+
+// Tile schedule of the persistent kernel; all three warp roles walk the same sequence.
+//   round-robin (the first design): tile t = (m-group t / n_blocks, n-block t % n_blocks), CTA group g takes t = g, g + G, ...
+//     With 768 tiles on 74 CTA pairs (N = 640 or 768 at B = 65 536) that is 10.4 waves -- the last one 38 % full -- and N = 640
+//     leaves every third tile half as wide (256 + 256 + 128), which is bound by operand ingest instead of the tensor pipe.
+//   balanced (GemmParams.balanced): the output is cut into 64-column units, m-group-major; every CTA group owns one CONTIGUOUS range of
+//     total / G units (+-1), and walks it in tiles of up to BN / 64 units that never cross an m-group: what is left of the row inside
+//     the range is split evenly (10 units -> 4 + 3 + 3 rather than 4 + 4 + 2).  All groups finish together (no partial wave), narrow
+//     tiles appear only where a range boundary cuts a row, and consecutive tiles of a group re-read the same activation rows from L2.
+template <int BN>
+struct TileIter {
+  static constexpr int MAXU = BN / 64;
+  bool BALANCED;
+  int num_n_blocks, upm, N;
+  long long u, u_end;          // balanced: current / last unit of this group's range
+  int tile, num_tiles, stride; // round-robin
+  int mg, n0, n_valid, slot;   // current tile: m-group (pairs when CG == 2), first column, width; slot = unique index of the tile in its row
+  __device__ __forceinline__ TileIter(bool balanced, int num_m_groups, int N_, int group, int groups) : BALANCED(balanced), N(N_) {
+    num_n_blocks = (N_ + BN - 1) / BN;
+    upm = (N_ + 63) / 64;
+    if (BALANCED) {
+      const long long total = (long long)num_m_groups * upm;
+      u = total * group / groups;
+      u_end = total * (group + 1) / groups;
+      tile = num_tiles = stride = 0;
+    } else {
+      u = u_end = 0;
+      tile = group; num_tiles = num_m_groups * num_n_blocks; stride = groups;
+    }
+    mg = n0 = n_valid = slot = 0;
+  }
+  __device__ __forceinline__ bool next() {
+    if (BALANCED) {
+      if (u >= u_end) return false;
+      mg = (int)(u / upm);
+      const int c = (int)(u - (long long)mg * upm);
+      const long long row_end = min(u_end, (long long)(mg + 1) * upm);
+      const int r = (int)(row_end - u);
+      const int pieces = (r + MAXU - 1) / MAXU;           // tiles still needed for the rest of this row inside the range
+      const int w = (r + pieces - 1) / pieces;            // ... of even width
+      n0 = c * 64; n_valid = min(w * 64, N - n0); slot = c;
+      u += w;
+      return true;
+    } else {
+      if (tile >= num_tiles) return false;
+      mg = tile / num_n_blocks;
+      slot = tile - mg * num_n_blocks;
+      n0 = slot * BN; n_valid = min(BN, N - n0);
+      tile += stride;
+      return true;
+    }
+  }
+};
 template <int BN, int STAGES, int EPI, int CG, int VAR>
 __global__ void __launch_bounds__(TN_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
@@ -601,6 +655,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   constexpr bool BF16_OUT = (EPI == EPI_BIAS_ACT || EPI == EPI_HEAD_LOSS || EPI == EPI_DGRAD || EPI == EPI_DGRAD_MASK || EPI == EPI_BIAS_ADD);
   constexpr bool STAGED = (VAR & VAR_STAGED) != 0 && BF16_OUT;
   constexpr bool STATS = (VAR & VAR_STATS) != 0;
+  const bool BALANCED = p.balanced != 0 && EPI != EPI_HEAD_LOSS;      // the loss partials are indexed by the round-robin tile grid
   using L = TnSmem<BN, STAGES, CG, STAGED>;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   const bool is_leader = cta_rank == 0;
@@ -625,9 +680,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m_blocks = ((p.M + BM - 1) / BM + CG - 1) / CG;       // in units of CG m-blocks (pairs when CG == 2)
   const int num_n_blocks = (p.N + BN - 1) / BN;
-  const int num_tiles = num_m_blocks * num_n_blocks;
   const int num_kb = p.K / BK;
-  const int first_tile = (int)(blockIdx.x / CG), tile_stride = (int)(gridDim.x / CG);   // both CTAs of a pair walk the same tiles
+  const int my_group = (int)(blockIdx.x / CG), num_groups = (int)(gridDim.x / CG);      // both CTAs of a pair walk the same tiles
+  using Tiles = TileIter<BN>;
 
   if (warp == TN_PRODUCER_WARP && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -664,9 +719,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ===================== TMA producer =====================
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
-      for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
-        const int m0 = ((tile / num_n_blocks) * CG + (int)cta_rank) * BM, n0 = (tile % num_n_blocks) * BN;
-        const int nb0 = n0 + (int)cta_rank * (min(BN, p.N - n0) / CG);       // this CTA's share of the B rows
+      for (Tiles it(BALANCED, num_m_blocks, p.N, my_group, num_groups); it.next();) {
+        const int m0 = (it.mg * CG + (int)cta_rank) * BM, n0 = it.n0;
+        const int nb0 = n0 + (int)cta_rank * (it.n_valid / CG);              // this CTA's share of the B rows (the box may over-fetch)
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t sa = smem_base + s * L::STAGE_BYTES;
@@ -694,9 +749,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (lane == 0 && is_leader) {
       int s = 0; uint32_t ph = 0; int t = 0;
       long long st_tempty = 0, st_full = 0;          // micro-benchmark: cycles the issuer waited for a free accumulator / for operands
-      for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++t) {
-        const int n0 = (tile % num_n_blocks) * BN;
-        const int n_valid = min(BN, p.N - n0);
+      for (Tiles it(BALANCED, num_m_blocks, p.N, my_group, num_groups); it.next(); ++t) {
+        const int n_valid = it.n_valid;
         const uint32_t idesc = make_idesc_bf16(BM * CG, n_valid, 0, 0);
         const int acc = t & 1;
         long long c0 = (STATS && p.stats) ? clock64() : 0;
@@ -736,10 +790,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const uint32_t stage_warp = smem_base + (uint32_t)(L::OUT_OFFSET + ew * L::OUT_WARP_BYTES);     // STAGED only
     int t = 0;
     long long st_epi_wait = 0, st_epi_busy = 0;      // micro-benchmark (epilogue warp 0): cycles waiting for an accumulator / working on it
-    for (int tile = first_tile; tile < num_tiles; tile += tile_stride, ++t) {
-      const int mb = (tile / num_n_blocks) * CG + (int)cta_rank;
-      const int m0 = mb * BM, n0 = (tile % num_n_blocks) * BN;
-      const int n_valid = min(BN, p.N - n0);
+    for (Tiles it(BALANCED, num_m_blocks, p.N, my_group, num_groups); it.next(); ++t) {
+      const int mb = it.mg * CG + (int)cta_rank;
+      const int m0 = mb * BM, n0 = it.n0;
+      const int n_valid = it.n_valid;
       const int acc = t & 1;
       const RowInfo ri = make_row_info(p, m0 + tile_row);
       const int c0 = cq * QCOLS;                              // tile-relative first column of this warp (warp-uniform)
@@ -838,7 +892,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // deterministic: one partial per (m-block, n-block, epilogue warp)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
-        if (lane == 0 && m0 < p.M) p.loss_partials[(mb * num_n_blocks + (tile % num_n_blocks)) * TN_EPI_WARPS + ew] = loss_acc * p.grad_scale;
+        if (lane == 0 && m0 < p.M) p.loss_partials[(mb * num_n_blocks + it.slot) * TN_EPI_WARPS + ew] = loss_acc * p.grad_scale;
       }
     }
     if (STATS && p.stats && ew == 0 && lane == 0) { p.stats[8 * blockIdx.x + 6] = (unsigned long long)st_epi_wait; p.stats[8 * blockIdx.x + 7] = (unsigned long long)st_epi_busy; }
