@@ -21,6 +21,7 @@ OPT = {"adam_keras": 0, "adam": 0, "adam_torch": 1, "sgd": 2, "radam": 3, "rmspr
 FWD_NORMALIZE_IN, FWD_DENORM_OUT, FWD_KEEP_ACTIVATIONS, TRAIN_FUSED_OPT = 1, 2, 4, 8
 BATCH_METRICS_SCRATCH = 2048
 HSR_NO_OPT = 16
+IPC_HANDLE_BYTES = 64
 
 
 class MlpCfg(C.Structure):
@@ -108,6 +109,10 @@ SIGNATURES = {
     "csb_batch_metrics": (C.c_int, [_VP, _VP, C.c_int64, C.c_int32, _VP, _VP, _VP]),
     "csb_hsr_train_step": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int64, C.c_int, C.c_uint32, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
                                      C.c_float, C.c_float, _VP, _VP, _VP]),
+    "csb_mlp_dp_export": (C.c_int, [_VP, _VP]),
+    "csb_mlp_dp_attach": (C.c_int, [_VP, C.c_int, C.c_int, _VP]),
+    "csb_mlp_dp_debug": (C.c_int, [_VP, _VP]),
+    "csb_mlp_dp_step": (C.c_int, [_VP, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _VP, _VP]),
     "csb_gather_rows": (C.c_int, [_VP, _VP, _VP, C.c_int64, C.c_int, C.c_int64, _VP]),
     "csb_gather_rows_check": (C.c_int, [_VP]),
     "csb_test_gemm_nt": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP]),

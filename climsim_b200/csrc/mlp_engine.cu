@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "simt_kernels.cuh"
 #include "fit_kernels.cuh"
+#include "dp_kernels.cuh"
 #include "tc_gemm.cuh"
 #include "tail_kernel.cuh"
 
@@ -361,6 +362,12 @@ struct csb_mlp {
   int64_t pending_B = 0;
   int pending_n_loss = 0;
   float* pending_loss_out = nullptr;
+  // data parallelism over NVLink peer memory (dp_kernels.cuh): `grads` then lives at the head of an IPC-exported slab
+  bool dp_on = false;
+  int dp_rank = 0, dp_world = 1;
+  int64_t dp_n = 0;                         // floats in grads / gsum (P_pad + 4)
+  void* dp_peer_base[simt::DP_MAX_RANKS] = {};
+  unsigned long long dp_epoch = 0;
   int64_t acts_B = -1;                      // batch of the last forward that kept activations
   bool acts_normalized = false;
 };
@@ -402,6 +409,8 @@ static void free_all(csb_mlp* h) {
     if (h->ev_w[l]) cudaEventDestroy(h->ev_w[l]);
   }
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
+  for (int r = 0; r < simt::DP_MAX_RANKS; ++r)
+    if (h->dp_peer_base[r] && r != h->dp_rank) cudaIpcCloseMemHandle(h->dp_peer_base[r]);
 }
 
 #define CSB_ALLOC(ptr, bytes)                                                                          \
@@ -1804,6 +1813,133 @@ int csb_hsr_train_step(csb_mlp* mean, csb_mlp* logprec, const float* x, const fl
     h->acts_B = -1;
     if (!no_opt && (rc = csb_mlp_apply_opt(h, rule, lr, beta1, beta2, eps, wds[i], stream))) return rc;
   }
+  return CSB_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// data parallelism over NVLink peer memory (dp_kernels.cuh)
+// ---------------------------------------------------------------------------------------------------------------
+static inline size_t dp_slab_bytes(int64_t n) { return (size_t)2 * n * 4 + 64 * 8; }
+
+int csb_mlp_dp_export(csb_mlp* h, void* ipc_handle_out) {
+  CSB_REQUIRE(h && ipc_handle_out, CSB_EINVAL, "null argument");
+  CSB_REQUIRE(h->bf16, CSB_EUNSUPPORTED, "the peer-memory exchange is fused with the bf16 engine's optimizer launch");
+  static_assert(sizeof(cudaIpcMemHandle_t) == CSB_IPC_HANDLE_BYTES, "CSB_IPC_HANDLE_BYTES");
+  CSB_CUDA_CHECK(cudaDeviceSynchronize());
+  if (h->dp_n == 0) {
+    const int64_t n = (int64_t)h->P_pad + 4;
+    float* slab = nullptr;
+    CSB_ALLOC(slab, dp_slab_bytes(n));                    // zero-filled: flags and the grid-barrier counter start at 0
+    CSB_CUDA_CHECK(cudaMemcpy(slab, h->grads, h->P_pad * 4, cudaMemcpyDeviceToDevice));
+    cudaFree(h->grads);
+    h->grads = slab;
+    h->dp_n = n;
+    for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);     // cached graphs hold the old gradient pointer
+    h->graphs.clear();
+  }
+  cudaIpcMemHandle_t hd;
+  CSB_CUDA_CHECK(cudaIpcGetMemHandle(&hd, h->grads));
+  memcpy(ipc_handle_out, &hd, sizeof(hd));
+  return CSB_OK;
+}
+
+int csb_mlp_dp_attach(csb_mlp* h, int rank, int world, const void* ipc_handles) {
+  CSB_REQUIRE(h && ipc_handles, CSB_EINVAL, "null argument");
+  CSB_REQUIRE(h->dp_n > 0, CSB_ESTATE, "csb_mlp_dp_export first");
+  CSB_REQUIRE(world >= 2 && world <= simt::DP_MAX_RANKS && rank >= 0 && rank < world, CSB_EINVAL, "rank %d / world %d out of range", rank, world);
+  CSB_REQUIRE(!h->dp_on, CSB_ESTATE, "already attached");
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { h->dp_peer_base[r] = h->grads; continue; }
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, reinterpret_cast<const char*>(ipc_handles) + (size_t)r * sizeof(hd), sizeof(hd));
+    void* base = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      for (int q = 0; q < r; ++q) if (q != rank && h->dp_peer_base[q]) { cudaIpcCloseMemHandle(h->dp_peer_base[q]); h->dp_peer_base[q] = nullptr; }
+      set_last_error("cudaIpcOpenMemHandle of rank %d's slab failed: %s (ranks must be GPUs of one node with peer access)", r, cudaGetErrorString(e));
+      return CSB_EUNSUPPORTED;
+    }
+    h->dp_peer_base[r] = base;
+  }
+  h->dp_rank = rank; h->dp_world = world; h->dp_on = true; h->dp_epoch = 0;
+  return CSB_OK;
+}
+
+int csb_mlp_dp_debug(csb_mlp* h, unsigned long long* stamps6_host) {
+  CSB_REQUIRE(h && stamps6_host && h->dp_n > 0, CSB_EINVAL, "bad argument");
+  CSB_CUDA_CHECK(cudaDeviceSynchronize());
+  CSB_CUDA_CHECK(cudaMemcpy(stamps6_host, reinterpret_cast<unsigned long long*>(h->grads + 2 * h->dp_n) + 40, 6 * 8, cudaMemcpyDeviceToHost));
+  return CSB_OK;
+}
+
+int csb_mlp_dp_step(csb_mlp* h, int rule, float lr, float beta1, float beta2, float eps, float wd, float* loss_out, void* stream) {
+  CSB_REQUIRE(h, CSB_EINVAL, "null handle");
+  CSB_REQUIRE(h->dp_on, CSB_ESTATE, "csb_mlp_dp_attach first");
+  CSB_REQUIRE(rule >= CSB_OPT_ADAM_KERAS && rule <= CSB_OPT_RMSPROP, CSB_EINVAL, "unknown optimizer rule %d", rule);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  prof_mark(h, K_BEGIN, st);
+  h->step++;
+  simt::OptParams o;
+  o.rule = rule; o.lr = lr; o.beta1 = beta1; o.beta2 = beta2; o.eps = eps; o.wd = wd;
+  o.bc1 = (float)(1.0 - pow((double)beta1, (double)h->step));
+  o.bc2 = (float)(1.0 - pow((double)beta2, (double)h->step));
+  o.radam_r = -1.f;
+  if (rule == CSB_OPT_RADAM) {
+    const double t = (double)h->step, b2t = pow((double)beta2, t);
+    const double sma_inf = 2.0 / (1.0 - (double)beta2) - 1.0, sma_t = sma_inf - 2.0 * t * b2t / (1.0 - b2t);
+    if (sma_t >= 5.0) o.radam_r = (float)sqrt((sma_t - 4.0) / (sma_inf - 4.0) * (sma_t - 2.0) / (sma_inf - 2.0) * sma_inf / sma_t);
+  }
+  // phase 0: the split partials a CSB_TRAIN_FUSED_OPT step left behind (none: the gradient buffer is taken as it is)
+  simt::SegmentTable seg;
+  seg.n = 0; seg.loss_partials = h->loss_partials; seg.n_loss = 0; seg.loss_out = nullptr;
+  if (h->pending) {
+    seg.n_loss = h->pending_n_loss; seg.loss_out = h->grads + h->P_pad;      // (the kernel writes the loss share behind the gradient)
+    for (int l = h->L - 1; l >= 0; --l) {
+      const LayerInfo& li = h->layer[l];
+      const int splits = wgrad_splits(h, l, h->pending_B, nullptr, nullptr, h->pending_tail);
+      seg.seg[seg.n++] = {h->ws + li.ws_w_off, (size_t)li.Kp * li.Np, h->grads + li.w_off, (int64_t)li.Kp * li.Np, splits};
+      seg.seg[seg.n++] = {h->ws + li.ws_b_off, (size_t)li.Np, h->grads + li.b_off, (int64_t)li.Np, splits * nt_m_tiles(li.Kp, li.nt_cg)};
+      if (li.ln) seg.seg[seg.n++] = {h->ws + li.ws_g_off, (size_t)2 * li.Np, h->grads + li.g_off, (int64_t)2 * li.Np, ln_grad_splits(h, l, h->pending_B)};
+    }
+    h->pending = false;
+  }
+  simt::DpTable dp;
+  dp.rank = h->dp_rank; dp.world = h->dp_world; dp.epoch = ++h->dp_epoch; dp.n = h->dp_n;
+  dp.slice = (int64_t)ceil_div(ceil_div(h->dp_n, 4), h->dp_world) * 4;
+  for (int r = 0; r < simt::DP_MAX_RANKS; ++r) {
+    float* base = reinterpret_cast<float*>(h->dp_peer_base[r < h->dp_world ? r : h->dp_rank]);
+    dp.grads_peer[r] = base; dp.gsum_peer[r] = base + h->dp_n;
+    dp.flags_peer[r] = reinterpret_cast<unsigned long long*>(base + 2 * h->dp_n);
+  }
+  float* gsum = h->grads + h->dp_n;
+  simt::FusedOptTable tab;
+  tab.n = h->L;
+  tab.params = h->params; tab.grads = h->grads; tab.m = h->m; tab.v = h->v;
+  tab.loss_partials = nullptr; tab.n_loss = 0; tab.loss_out = loss_out ? loss_out : h->d_loss;
+  int64_t items = 0;
+  for (int l = 0; l < h->L; ++l) {
+    const LayerInfo& li = h->layer[l];
+    tab.l[l] = {li.Kp, li.Np, li.w_off, li.b_off, h->w16[l], h->wt16[l], gsum + li.w_off, 1, gsum + li.b_off, 1,
+                li.g_off, gsum + li.g_off, li.ln ? 1 : 0, 32};
+    dp.opt_item_base[l] = (int)items;
+    items += (li.Kp / 32) * (li.Np / 64) + (int)ceil_div(li.Np / 4, 256) + (li.ln ? (int)ceil_div(li.Np / 2, 256) : 0);
+  }
+  dp.opt_item_base[h->L] = (int)items;
+  dp.opt_items_total = items;
+  dp.seg_base[0] = 0;
+  for (int i = 0; i < seg.n; ++i) dp.seg_base[i + 1] = dp.seg_base[i] + seg.seg[i].len / 4;
+  // as many blocks as are co-resident (the kernel spins on flags and on its own grid barrier); the SAME grid every step (the barrier
+  // counter advances by 2 x grid per step); no programmatic overlap with neighbours
+  static int occ = 0;
+  if (occ == 0) {
+    CSB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, simt::dp_reduce_opt_kernel, 256, 0));
+    occ = std::max(1, std::min(occ, 4));
+  }
+  simt::dp_reduce_opt_kernel<<<h->sm_count * occ, 256, 0, st>>>(seg, dp, tab, o);
+  CSB_CUDA_CHECK(cudaGetLastError());
+  prof_mark(h, K_OPT, st);
   return CSB_OK;
 }
 

@@ -789,6 +789,72 @@ struct FusedOptTable {
   const float* loss_partials; int n_loss; float* loss_out;
 };
 
+// work items of one layer in the fused optimizer: tiles of W, then 256-wide pieces of the vector segments
+__device__ __forceinline__ int fused_opt_items(const FusedOptLayer& L) {
+  return (L.Kp / L.tk) * (L.Np / 64) + (L.Np / 4 + 255) / 256 + (L.g_splits > 0 ? (2 * L.Np / 4 + 255) / 256 : 0);
+}
+// one work item (called by all 256 threads of a block; `t` is the block's transpose staging tile)
+__device__ __forceinline__ void fused_opt_item(const FusedOptTable& tab, const OptParams& o, const FusedOptLayer& L, int item, float (*t)[65]) {
+  // W_l in tiles of TK (k) x 64 (n): thread -> 4 consecutive n (one float4) of rows ty, ty + 16
+  const int TK = L.tk;
+  const int tiles_n = L.Np / 64, tiles = (L.Kp / TK) * tiles_n;
+  const int vec_b = (L.Np / 4 + 255) / 256;
+  const size_t wsz = (size_t)L.Kp * L.Np;
+  if (item < tiles) {
+    const int k0 = (item / tiles_n) * TK, n0 = (item % tiles_n) * 64;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    for (int k = ty; k < TK; k += 16) {
+      const size_t idx = (size_t)(k0 + k) * L.Np + n0 + 4 * tx, e = L.w_off + idx;
+      const float4 g4 = sum_partials4(L.ws_w + idx, wsz, L.w_splits);
+      const float4 w4 = *reinterpret_cast<const float4*>(tab.params + e), m4 = *reinterpret_cast<const float4*>(tab.m + e),
+                   v4 = *reinterpret_cast<const float4*>(tab.v + e);
+      float w[4] = {w4.x, w4.y, w4.z, w4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
+      const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { opt_update(o, w[j], g[j], m[j], v[j]); t[k][4 * tx + j] = w[j]; }
+      *reinterpret_cast<float4*>(tab.grads + e) = g4;
+      *reinterpret_cast<float4*>(tab.params + e) = make_float4(w[0], w[1], w[2], w[3]);
+      if (o.rule != CSB_OPT_SGD) {
+        *reinterpret_cast<float4*>(tab.m + e) = make_float4(m[0], m[1], m[2], m[3]);
+        *reinterpret_cast<float4*>(tab.v + e) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+      *reinterpret_cast<uint2*>(L.w16 + idx) = make_uint2(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]));
+    }
+    __syncthreads();
+    {  // transposed copy: 64 n-rows x 32 k; thread -> 8 consecutive k of one n (one 16-byte store)
+      const int n = threadIdx.x >> 2, kq = (threadIdx.x & 3) * 8;
+      if (kq < TK) {
+        uint4 u;
+        u.x = pack_bf16x2(t[kq + 0][n], t[kq + 1][n]); u.y = pack_bf16x2(t[kq + 2][n], t[kq + 3][n]);
+        u.z = pack_bf16x2(t[kq + 4][n], t[kq + 5][n]); u.w = pack_bf16x2(t[kq + 6][n], t[kq + 7][n]);
+        *reinterpret_cast<uint4*>(L.wt16 + (size_t)(n0 + n) * L.Kp + k0 + kq) = u;
+      }
+    }
+    __syncthreads();
+  } else {
+    // vector segments: the bias [Np] and, behind it, a LayerNorm layer's (gamma, beta) [2 Np]
+    int c = ((item - tiles) * 256 + threadIdx.x) * 4;
+    size_t e; const float* wsp; size_t stride; int splits; bool ok;
+    if (c < L.Np) { e = L.b_off + c; wsp = L.ws_b + c; stride = (size_t)L.Np; splits = L.b_splits; ok = true; }
+    else { c -= vec_b * 1024; e = L.g_off + c; wsp = L.ws_g + c; stride = (size_t)2 * L.Np; splits = L.g_splits; ok = c >= 0 && c < 2 * L.Np && L.g_splits > 0; }
+    if (ok) {
+      const float4 g4 = sum_partials4(wsp, stride, splits);
+      const float4 w4 = *reinterpret_cast<const float4*>(tab.params + e), m4 = *reinterpret_cast<const float4*>(tab.m + e),
+                   v4 = *reinterpret_cast<const float4*>(tab.v + e);
+      float w[4] = {w4.x, w4.y, w4.z, w4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
+      const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) opt_update(o, w[j], g[j], m[j], v[j]);
+      *reinterpret_cast<float4*>(tab.grads + e) = g4;
+      *reinterpret_cast<float4*>(tab.params + e) = make_float4(w[0], w[1], w[2], w[3]);
+      if (o.rule != CSB_OPT_SGD) {
+        *reinterpret_cast<float4*>(tab.m + e) = make_float4(m[0], m[1], m[2], m[3]);
+        *reinterpret_cast<float4*>(tab.v + e) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) opt_fused_kernel(const FusedOptTable tab, const OptParams o) {
   pdl_launch_dependents();
   pdl_wait();
@@ -797,67 +863,9 @@ __global__ void __launch_bounds__(256) opt_fused_kernel(const FusedOptTable tab,
     return;
   }
   const FusedOptLayer L = tab.l[blockIdx.y];
-  // W_l in tiles of 32 (k) x 64 (n): thread -> 4 consecutive n (one float4) of rows ty and ty + 16
-  const int TK = L.tk;
-  const int tiles_n = L.Np / 64, tiles = (L.Kp / TK) * tiles_n;
-  const int vec_b = (L.Np / 4 + 255) / 256, vec_items = vec_b + (L.g_splits > 0 ? (2 * L.Np / 4 + 255) / 256 : 0);
-  const size_t wsz = (size_t)L.Kp * L.Np;
   __shared__ float t[32][65];
-  for (int item = blockIdx.x; item < tiles + vec_items; item += gridDim.x) {
-    if (item < tiles) {
-      const int k0 = (item / tiles_n) * TK, n0 = (item % tiles_n) * 64;
-      const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-      for (int k = ty; k < TK; k += 16) {
-        const size_t idx = (size_t)(k0 + k) * L.Np + n0 + 4 * tx, e = L.w_off + idx;
-        const float4 g4 = sum_partials4(L.ws_w + idx, wsz, L.w_splits);
-        const float4 w4 = *reinterpret_cast<const float4*>(tab.params + e), m4 = *reinterpret_cast<const float4*>(tab.m + e),
-                     v4 = *reinterpret_cast<const float4*>(tab.v + e);
-        float w[4] = {w4.x, w4.y, w4.z, w4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
-        const float g[4] = {g4.x, g4.y, g4.z, g4.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { opt_update(o, w[j], g[j], m[j], v[j]); t[k][4 * tx + j] = w[j]; }
-        *reinterpret_cast<float4*>(tab.grads + e) = g4;
-        *reinterpret_cast<float4*>(tab.params + e) = make_float4(w[0], w[1], w[2], w[3]);
-        if (o.rule != CSB_OPT_SGD) {
-          *reinterpret_cast<float4*>(tab.m + e) = make_float4(m[0], m[1], m[2], m[3]);
-          *reinterpret_cast<float4*>(tab.v + e) = make_float4(v[0], v[1], v[2], v[3]);
-        }
-        *reinterpret_cast<uint2*>(L.w16 + idx) = make_uint2(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]));
-      }
-      __syncthreads();
-      {  // transposed copy: 64 n-rows x 32 k; thread -> 8 consecutive k of one n (one 16-byte store)
-        const int n = threadIdx.x >> 2, kq = (threadIdx.x & 3) * 8;
-        if (kq < TK) {
-          uint4 u;
-          u.x = pack_bf16x2(t[kq + 0][n], t[kq + 1][n]); u.y = pack_bf16x2(t[kq + 2][n], t[kq + 3][n]);
-          u.z = pack_bf16x2(t[kq + 4][n], t[kq + 5][n]); u.w = pack_bf16x2(t[kq + 6][n], t[kq + 7][n]);
-          *reinterpret_cast<uint4*>(L.wt16 + (size_t)(n0 + n) * L.Kp + k0 + kq) = u;
-        }
-      }
-      __syncthreads();
-    } else {
-      // vector segments: the bias [Np] and, behind it, a LayerNorm layer's (gamma, beta) [2 Np]
-      int c = ((item - tiles) * 256 + threadIdx.x) * 4;
-      size_t e; const float* wsp; size_t stride; int splits; bool ok;
-      if (c < L.Np) { e = L.b_off + c; wsp = L.ws_b + c; stride = (size_t)L.Np; splits = L.b_splits; ok = true; }
-      else { c -= vec_b * 1024; e = L.g_off + c; wsp = L.ws_g + c; stride = (size_t)2 * L.Np; splits = L.g_splits; ok = c >= 0 && c < 2 * L.Np && L.g_splits > 0; }
-      if (ok) {
-        const float4 g4 = sum_partials4(wsp, stride, splits);
-        const float4 w4 = *reinterpret_cast<const float4*>(tab.params + e), m4 = *reinterpret_cast<const float4*>(tab.m + e),
-                     v4 = *reinterpret_cast<const float4*>(tab.v + e);
-        float w[4] = {w4.x, w4.y, w4.z, w4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
-        const float g[4] = {g4.x, g4.y, g4.z, g4.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) opt_update(o, w[j], g[j], m[j], v[j]);
-        *reinterpret_cast<float4*>(tab.grads + e) = g4;
-        *reinterpret_cast<float4*>(tab.params + e) = make_float4(w[0], w[1], w[2], w[3]);
-        if (o.rule != CSB_OPT_SGD) {
-          *reinterpret_cast<float4*>(tab.m + e) = make_float4(m[0], m[1], m[2], m[3]);
-          *reinterpret_cast<float4*>(tab.v + e) = make_float4(v[0], v[1], v[2], v[3]);
-        }
-      }
-    }
-  }
+  const int items = fused_opt_items(L);
+  for (int item = blockIdx.x; item < items; item += gridDim.x) fused_opt_item(tab, o, L, item, t);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -238,6 +238,27 @@ class MLPEngine:
         _lib.check(self.lib.csb_mlp_grad_buffer(self._h, C.byref(ptr), C.byref(n)), "csb_mlp_grad_buffer")
         return torch.as_tensor(_DevPtr(ptr.value, n.value), device="cuda")
 
+    # -- data parallelism over NVLink peer memory (csb_mlp_dp_*) -------------------------------------------------------
+    def dp_export(self) -> bytes:
+        """Move the gradient buffer into an IPC-exportable slab; returns its handle (gather the handles of all ranks, then ``dp_attach``)."""
+        buf = C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+        _lib.check(self.lib.csb_mlp_dp_export(self._h, buf), "csb_mlp_dp_export")
+        return bytes(buf.raw)
+
+    def dp_attach(self, rank: int, world: int, handles: Sequence[bytes]) -> None:
+        assert len(handles) == world and all(len(hd) == _lib.IPC_HANDLE_BYTES for hd in handles)
+        blob = C.create_string_buffer(b"".join(handles), world * _lib.IPC_HANDLE_BYTES)
+        _lib.check(self.lib.csb_mlp_dp_attach(self._h, rank, world, blob), "csb_mlp_dp_attach")
+
+    def dp_step(self, rule: str = "adam_keras", lr: float = 1e-3, beta1: float = 0.9, beta2: float = 0.999, eps: Optional[float] = None,
+                weight_decay: float = 0.0, loss_out: Optional[torch.Tensor] = None) -> None:
+        """Cross-rank gradient sum + optimizer + bf16 weight copies in one kernel over peer memory; follows
+        ``train_step(..., fused_opt=True)`` on every rank.  ``loss_out`` receives the loss of the global batch."""
+        if eps is None:
+            eps = 1e-8 if rule == "adam_torch" else 1e-7
+        _lib.check(self.lib.csb_mlp_dp_step(self._h, _lib.OPT[rule], lr, beta1, beta2, eps, weight_decay,
+                                            loss_out.data_ptr() if loss_out is not None else None, _lib.current_stream_ptr()), "csb_mlp_dp_step")
+
     def train_step_host(self, x_host: torch.Tensor, y_host: torch.Tensor, rule: str = "adam_keras", lr: float = 1e-3,
                         beta1: float = 0.9, beta2: float = 0.999, eps: Optional[float] = None,
                         weight_decay: float = 0.0, grad_scale: float = 0.0, normalize_in: bool = False) -> float:

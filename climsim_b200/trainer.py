@@ -72,8 +72,38 @@ class Trainer:
         self._x = self._y = None
         self._loss = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._loss_host = None            # pinned ring of loss slots for the asynchronous host-fed path
+        self._peer = False                # gradient exchange fused with the optimizer over NVLink peer memory (csb_mlp_dp_step)
         if self.world > 1:
             self._broadcast_params()
+            self._try_peer_exchange()
+
+    def _try_peer_exchange(self) -> None:
+        """One node, bf16 engine: map the peers' gradient slabs (CUDA IPC) so that the all-reduce rides inside the optimizer kernel.
+        Anything else (fp32 parity engine, no peer access, the CPU test double, CSB_DP_NCCL=1) keeps ncclAllReduce + apply_opt.
+        The decision is collective: every rank takes the peer path or none does."""
+        import os
+        eng, dist = self.engine, torch.distributed
+        ok = (hasattr(eng, "dp_export") and getattr(eng, "dtype", None) == "bf16" and torch.device(self.device).type == "cuda"
+              and os.environ.get("CSB_DP_NCCL") is None and self.world <= 8)
+        handle = None
+        if ok:
+            try:
+                handle = eng.dp_export()
+            except Exception:
+                ok = False
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, handle if ok else None, group=self.pg)
+        if any(g is None for g in gathered):
+            return
+        try:
+            eng.dp_attach(self.rank, self.world, gathered)
+            attached = 1
+        except Exception:
+            attached = 0
+        flag = torch.tensor([attached], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.pg)
+        self._peer = bool(flag.item())
+        self._grad = None if self._peer else eng.grad_buffer()       # (dp_export moved the gradient buffer into the slab)
 
     def _broadcast_params(self) -> None:
         eng, dist = self.engine, torch.distributed
@@ -112,12 +142,15 @@ class Trainer:
         if staged:
             x, y = eng.stage_host_batch(x, y)
         scale = 1.0 / (B * self.world * eng.out_dim)            # global-mean MSE, as Keras computes on the global batch
-        eng.train_step(x, y, grad_scale=scale, normalize_in=normalize_in, loss_out=self._loss, fused_opt=self.world == 1)
+        eng.train_step(x, y, grad_scale=scale, normalize_in=normalize_in, loss_out=self._loss, fused_opt=self.world == 1 or self._peer)
         if staged:
             eng.release_staged()
-        if self.world > 1:
-            torch.distributed.all_reduce(self._grad, group=self.pg)
-        eng.apply_opt(self.rule, lr=lr, beta1=self.beta1, beta2=self.beta2, eps=self.eps, weight_decay=self.weight_decay)
+        if self._peer:                                          # cross-rank sum + optimizer in one kernel; self._loss = GLOBAL loss
+            eng.dp_step(self.rule, lr=lr, beta1=self.beta1, beta2=self.beta2, eps=self.eps, weight_decay=self.weight_decay, loss_out=self._loss)
+        else:
+            if self.world > 1:
+                torch.distributed.all_reduce(self._grad, group=self.pg)
+            eng.apply_opt(self.rule, lr=lr, beta1=self.beta1, beta2=self.beta2, eps=self.eps, weight_decay=self.weight_decay)
         self.iteration += 1
         return self._loss
 
@@ -143,7 +176,7 @@ class Trainer:
                 self.synchronize()
                 return float(slot.item())
         loss = self._step_local(x, y, normalize_in)
-        if self.world > 1 and (return_loss or slot is not None):
+        if self.world > 1 and not self._peer and (return_loss or slot is not None):
             torch.distributed.all_reduce(loss, group=self.pg)
         if slot is not None:
             slot.copy_(loss, non_blocking=True)
@@ -262,8 +295,9 @@ class Trainer:
                 nb += 1
             if total is None:
                 total = torch.zeros((), dtype=torch.float32, device=self.device)
-            if self.world > 1:                                       # every rank holds its share of the global-mean loss
-                torch.distributed.all_reduce(total, group=self.pg)
+            if self.world > 1:
+                if not self._peer:                                   # every rank holds its share of the global-mean loss
+                    torch.distributed.all_reduce(total, group=self.pg)
                 if stats is not None:
                     torch.distributed.all_reduce(stats, group=self.pg)
             loss = float(total.item()) / nb if nb else float("nan")

@@ -289,6 +289,25 @@ int  csb_hsr_train_step(csb_mlp* mean, csb_mlp* logprec, const float* x, const f
                         float lr, float beta1, float beta2, float eps, float wd_mean, float wd_logprec, float* loss_out, double* scratch,
                         void* stream);
 
+/* ---- data parallelism over NVLink peer memory -------------------------------------------------------------------------------------- */
+/* The reference's one collective is DDP's gradient all-reduce (online_testing/baseline_models/MLP_v2rh/training/
+ * train_mlp_h5loader.py:195-207).  Here it is fused with the optimizer into ONE kernel per rank that reads and writes its peers'
+ * gradient slabs directly (reduce-scatter by peer loads, all-gather by peer stores, fixed rank order => bit-identical replicas):
+ *   csb_mlp_dp_export   moves the gradient buffer into an IPC-exportable slab and returns its handle (CSB_IPC_HANDLE_BYTES bytes);
+ *   csb_mlp_dp_attach   maps the peers' slabs: `ipc_handles` = world x CSB_IPC_HANDLE_BYTES bytes in rank order (gathered by the
+ *                       caller, e.g. torch.distributed.all_gather_object); ranks must be GPUs of one node with peer access
+ *                       (CSB_EUNSUPPORTED otherwise: fall back to csb_mlp_grad_buffer + ncclAllReduce + csb_mlp_apply_opt);
+ *   csb_mlp_dp_step     after csb_mlp_train_step(..., CSB_TRAIN_FUSED_OPT) called with grad_scale = 1 / (global batch x out_dim) on
+ *                       EVERY rank: partial reduction, cross-rank sum, optimizer rule and bf16 weight copies in one launch; loss_out
+ *                       (device, optional) receives the loss of the GLOBAL batch.  All ranks must call it the same number of times. */
+#define CSB_IPC_HANDLE_BYTES 64
+int  csb_mlp_dp_export(csb_mlp* h, void* ipc_handle_out);
+int  csb_mlp_dp_attach(csb_mlp* h, int rank, int world, const void* ipc_handles);
+int  csb_mlp_dp_step(csb_mlp* h, int rule, float lr, float beta1, float beta2, float eps, float wd, float* loss_out, void* stream);
+/* measurement hook: globaltimer (ns) of the last csb_mlp_dp_step at {start, gradient summed, all ranks ready, slice exchanged, all
+ * ranks done, end} on this rank; synchronises the device. */
+int  csb_mlp_dp_debug(csb_mlp* h, unsigned long long* stamps6_host);
+
 /* ---- input pipeline ------------------------------------------------------------------------------------------------------------- */
 /* dst[i, :] = src[idx[i], :] for i < n_rows (fp32 rows of row_len floats, device pointers, idx int64 on the device): the sample
  * shuffle of the reference's input pipelines -- tf.data `unbatch().shuffle(384*30).batch(B)` (hpo_baseline_v1.py:140-143,
