@@ -215,7 +215,7 @@ tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         else
           for (int j = 0; j < 32; ++j) if (c0 + j < p.out_dim) yv[j] = __ldg(yptr + j);
       }
-      mbar_wait(acc_full(i & 1), (uint32_t)(i >> 1) & 1u);
+      mbar_wait_long(acc_full(i & 1), (uint32_t)(i >> 1) & 1u);
       tc_fence_after();
       uint32_t raw[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + COL_ACC + (uint32_t)(128 * (i & 1) + c0), raw);
@@ -264,7 +264,7 @@ tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int m0 = ((int)blockIdx.x + j * (int)gridDim.x) * BM, grow = m0 + tile_row;
       const bool in_range = grow < p.M;
       const uint32_t mask_word = in_range ? __ldg(p.mask_in + (size_t)cq * p.ld_mask + grow) : 0u;
-      mbar_wait(dz_full, (uint32_t)j & 1u);
+      mbar_wait_long(dz_full, (uint32_t)j & 1u);
       tc_fence_after();
       uint32_t raw[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + COL_DZ + (uint32_t)c0, raw);
@@ -290,7 +290,7 @@ tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     // ---- the CTA's partial of dW (TMEM -> global, one row of 32 columns per thread) and of db (four lane quadrants folded in order)
     float* dw = p.dw_out + (size_t)blockIdx.x * 128 * 128 + (size_t)tile_row * 128 + c0;
     if (my_blocks > 0) {
-      mbar_wait(dw_full, 0);                     // every MMA has completed: the dZ tiles are free (sdb aliases one of them)
+      mbar_wait_long(dw_full, 0);                     // every MMA has completed: the dZ tiles are free (sdb aliases one of them)
       tc_fence_after();
       uint32_t raw[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + COL_DW + (uint32_t)c0, raw);

@@ -113,12 +113,38 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// Wait with a watchdog: a protocol bug becomes a trap (launch error) after ~2 s instead of a hung GPU.
+// try_wait with a suspend-time hint (ns): the thread may sleep in hardware until the phase completes or the hint expires, instead of
+// coming back after the short default time-out -- far fewer wake-ups (and issued instructions) over a long wait
+__device__ __forceinline__ uint32_t mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok;
+}
+// Wait with a watchdog: a protocol bug becomes a trap (launch error) instead of a hung GPU.  The watchdog counts wake-ups; it does
+// not read a timer (ncu: in the wide forward kernel the try_wait / globaltimer / compare / branch loops of the 18 mostly-waiting
+// warps were 60 % of all issued instructions, competing for issue slots with the one thread that feeds the tensor pipe and with the
+// epilogue warps that do have work).
+//   mbar_wait       latency-critical waits (MMA issuer, TMA producer): plain try_wait retries
+//   mbar_wait_long  waits that are expected to take a while and tolerate ~a hundred cycles of wake-up latency (an epilogue warp
+//                   waiting for its accumulator): hardware sleep of up to 2 us per try
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
+  uint32_t n = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (globaltimer_ns() - t0 > 2000000000ull) __trap();
+    if (++n > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void mbar_wait_long(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t n = 0;
+  while (!mbar_try_wait_hint(bar, parity, 2000u)) {
+    if (++n > (1u << 22)) __trap();
   }
 }
 
@@ -840,7 +866,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       };
       load_targets(c0);
       long long ck0 = (STATS && p.stats) ? clock64() : 0;
-      mbar_wait(tfull_bar(acc), (uint32_t)(t >> 1) & 1u);
+      mbar_wait_long(tfull_bar(acc), (uint32_t)(t >> 1) & 1u);
       long long ck1 = (STATS && p.stats) ? clock64() : 0;
       tc_fence_after();
       float loss_acc = 0.f;
@@ -1117,7 +1143,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int row = m0 + warp * 32 + lane;
     float* out = p.out + (size_t)split * p.split_stride + (size_t)row * p.ld_out + n0;
     if (nrb > 0) {
-      mbar_wait(tfull_bar, 0);
+      mbar_wait_long(tfull_bar, 0);
       tc_fence_after();
       // Every MMA has completed, so the operand ring is free: each thread parks its output row (n_valid fp32) there and hands
       // it to the bulk-copy engine as ONE contiguous shared -> global copy.  (Storing straight from registers makes every
