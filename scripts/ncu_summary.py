@@ -26,6 +26,8 @@ def kind_of(name: str) -> str:
     if "gemm_tn_kernel" in name:
         epi = int(name.split("<")[1].split(">")[0].split(",")[2])
         return {0: "gemm_tn_fwd", 1: "gemm_tn_head", 2: "gemm_tn_dgrad", 6: "gemm_tn_dgrad"}.get(epi, "gemm_tn_other")
+    if "tail_kernel" in name:
+        return "gemm_tn_head"
     return "other"
 
 
