@@ -824,10 +824,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const RowInfo ri = make_row_info(p, m0 + tile_row);
       const int c0 = cq * QCOLS;                              // tile-relative first column of this warp (warp-uniform)
       // everything that does not depend on the accumulator is requested before waiting for it
+      // (arrays an epilogue kind does not use are left uninitialised on purpose: zero-filling them cost 32 register-pair moves per
+      // tile and warp in every kind -- 5 % of the forward epilogue's instructions)
       uint32_t mask_words[NCH];
-#pragma unroll
-      for (int i = 0; i < NCH; ++i) mask_words[i] = 0u;
       if constexpr (EPI == EPI_DGRAD_MASK) {
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) mask_words[i] = 0u;
         if (ri.in_range) {
 #pragma unroll
           for (int i = 0; i < NCH; ++i)
@@ -835,11 +837,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       }
       uint32_t sv[NCH][16];
-#pragma unroll
-      for (int i = 0; i < NCH; ++i)
-#pragma unroll
-        for (int j = 0; j < 16; ++j) sv[i][j] = 0u;
       if constexpr (SAVED_IN) {
+#pragma unroll
+        for (int i = 0; i < NCH; ++i)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sv[i][j] = 0u;
         if (ri.in_range) {
 #pragma unroll
           for (int i = 0; i < NCH; ++i)
@@ -849,9 +851,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // EPI_HEAD_LOSS: the 32 targets of the first step, requested before the accumulator wait (later steps: before their tcgen05.ld)
       float yv[32];
       auto load_targets = [&](int c) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) yv[j] = 0.f;
         if constexpr (EPI == EPI_HEAD_LOSS) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) yv[j] = 0.f;
           if (ri.row_ok && c < n_valid) {
             const int gc = n0 + c;
             const float* yptr = p.y + (size_t)ri.yrow * p.ld_y + gc;
