@@ -92,6 +92,9 @@ SIGNATURES = {
     "csb_cnn_debug_read_hidden": (C.c_int, [_VP, C.c_int, C.c_int, _VP, C.c_int64, _VP]),
     "csb_cnn_forward": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP]),
     "csb_cnn_train_step": (C.c_int, [_VP, _VP, _VP, C.c_int64, C.c_float, _VP, _VP]),
+    "csb_cnn_backward": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP]),
+    "csb_cnn_set_params_device": (C.c_int, [_VP, _VP, _VP]),
+    "csb_cnn_get_grads_device": (C.c_int, [_VP, _VP, _VP]),
     "csb_cnn_grad_buffer": (C.c_int, [_VP, _P(_VP), _P(C.c_size_t)]),
     "csb_cnn_apply_opt": (C.c_int, [_VP, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _VP]),
     "csb_cnn_launch_count": (C.c_int64, [_VP]),

@@ -318,10 +318,30 @@ class OnlineInferenceWrapper(torch.nn.Module):
         return eng.forward(x, normalize_in=True, denorm_out=True)
 
 
+class _CNNFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, flat, module):
+        module._sync_params()
+        y = module.engine.forward(x)
+        ctx.module = module
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        eng = ctx.module.engine
+        eng.backward(y, dy.contiguous())
+        return None, eng.get_grads_device(), None
+
+
 class CNN(torch.nn.Module):
     """ResNet-1D of baseline_models/CNN/training/hpo_train.py:131-200 (a Keras model in the reference): ``forward(x: (B,60,6))
-    -> (B,60,10)`` for inference; training goes through the fused ``engine.train_step`` / ``engine.apply_opt`` (loss =
-    ``mae_adjusted`` or ``mse_adjusted``), the way ``model.fit`` drives it in the reference (hpo_train.py:355-368)."""
+    -> (B,60,10)``.  Two ways to train it: the fused ``train_step`` (loss = ``mae_adjusted`` or ``mse_adjusted``, Dropout 0.175 behind
+    the ReLUs, the optimizer inside the engine -- the way ``model.fit`` drives the reference, hpo_train.py:355-368), or ordinary
+    torch autograd: the parameters are ONE flat ``nn.Parameter`` (Keras ``get_weights()`` order, the two Dense heads concatenated),
+    ``forward`` records an autograd node whose backward is ``csb_cnn_backward``, so any torch loss and optimizer work on top
+    (dropout-free, like ``model(x, training=False)``; no gradient w.r.t. ``x``)."""
 
     def __init__(self, depth: int = 12, width: int = 406, kernel: int = 3, loss: str = "mae", dtype: str = "bf16", max_batch: int = 4096,
                  dropout: float = 0.175, seed: int = 0):
@@ -329,14 +349,42 @@ class CNN(torch.nn.Module):
         self.engine = CNNEngine(depth=depth, width=width, kernel=kernel, loss=loss, dtype=dtype, max_batch=max_batch)
         if dropout > 0 and dtype == "bf16":                   # hp_dropout = 0.175 (hpo_train.py:143); active in train_step only
             self.engine.set_dropout(dropout, seed)
+        rng = np.random.default_rng(seed)
+        parts = []
+        for shp in self.engine.shapes():                      # Keras defaults: glorot_uniform kernels, zero biases
+            if len(shp) == 1:
+                parts.append(np.zeros(shp, np.float32))
+            else:
+                fan_in = int(np.prod(shp[:-1]))
+                fan_out = int(shp[0] * shp[-1]) if len(shp) == 3 else int(shp[-1])
+                lim = float(np.sqrt(6.0 / (fan_in + fan_out)))
+                parts.append(rng.uniform(-lim, lim, size=shp).astype(np.float32))
+        self.flat = torch.nn.Parameter(torch.from_numpy(np.concatenate([p.reshape(-1) for p in parts])).cuda())
+        self._uploaded_version = -1
+
+    def _sync_params(self) -> None:
+        if self.flat._version != self._uploaded_version:
+            self.engine.set_params_device(self.flat.detach())
+            self._uploaded_version = self.flat._version
 
     def load_keras_weights(self, weights: Sequence[np.ndarray]) -> None:
-        self.engine.set_params_flat(CNNEngine.keras_to_flat(weights))
+        with torch.no_grad():
+            self.flat.copy_(torch.from_numpy(CNNEngine.keras_to_flat(weights)))
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if torch.is_grad_enabled() and self.flat.requires_grad:
+            return _CNNFunction.apply(x, self.flat, self)
+        self._sync_params()
         return self.engine.forward(x)
 
     def train_step(self, x: torch.Tensor, y: torch.Tensor, lr: float = 1e-4, rule: str = "adam_keras") -> torch.Tensor:
+        """Fused step inside the engine (the parameters it updates live in the engine; ``pull_params`` mirrors them into ``flat``)."""
+        self._sync_params()
         loss = self.engine.train_step(x, y)
         self.engine.apply_opt(rule, lr=lr)
         return loss
+
+    def pull_params(self) -> None:
+        with torch.no_grad():
+            self.flat.copy_(torch.from_numpy(self.engine.get_params_flat()).to(self.flat.device))
+        self._uploaded_version = self.flat._version

@@ -47,6 +47,7 @@ struct csb_cnn {
   float dropout = 0.f;                           // Dropout rate behind the two ReLUs of every block (training steps only)
   uint32_t drop_seed = 0;
   int64_t train_steps = 0;                       // advances the dropout masks from step to step
+  int64_t fwd_B = -1;                            // batch of the last csb_cnn_forward (its activations are what csb_cnn_backward uses)
 };
 
 static void cnn_free(csb_cnn* h) {
@@ -123,8 +124,14 @@ static inline int cnn_mma_width(int c, int cp) {
 
 // one convolution-as-GEMM launch.  `dgrad` selects the flipped/transposed weights (output width = Cinp).
 //   kind 0: out = act(conv + bias)   kind 1: out = conv + bias + saved   kind 2: out = conv * act'(saved)
+static inline uint32_t cnn_drop_seed(const csb_cnn* h, int layer_id) {
+  return h->drop_seed ^ (uint32_t)(h->train_steps * 0x9E3779B97F4A7C15ull >> 32) ^ (uint32_t)(layer_id + 1) * 0x85EBCA77u;
+}
+static inline uint32_t cnn_drop_threshold(const csb_cnn* h) { return (uint32_t)lrintf(h->dropout * 16777216.f); }   // keep iff 24 random bits >= rate * 2^24
+
+// drop_layer >= 0 (kind 0, bf16): inverted dropout behind the activation inside the epilogue (VAR_DROPOUT), keyed like cnn_dropout
 static int cnn_conv(csb_cnn* h, const ConvLayerInfo& li, bool dgrad, const CnnBuf& in, CnnBuf& out, int kind, const CnnBuf* saved, int act,
-                    const float* bias, int64_t B, cudaStream_t st, float dgrad_scale = 0.f) {
+                    const float* bias, int64_t B, cudaStream_t st, float dgrad_scale = 0.f, int drop_layer = -1) {
   const int M = (int)(B * h->P), N = dgrad ? li.Cinp : li.Coutp, Kt = dgrad ? li.Coutp : li.Cinp;
   int rc = CSB_OK;
   if (h->bf16) {
@@ -135,7 +142,10 @@ static int cnn_conv(csb_cnn* h, const ConvLayerInfo& li, bool dgrad, const CnnBu
     const CUtensorMap& w = dgrad ? li.tm_wd : li.tm_wt;
     p.out = out.ptr; p.ld_out = out.Cp;
     if (saved) { p.saved = reinterpret_cast<const __nv_bfloat16*>(saved->ptr); p.ld_saved = saved->Cp; }
-    if (kind == 0) rc = launch_tn_auto<tc::EPI_BIAS_ACT>(in.maps.k128, w, p, h->sm_count, st);
+    if (kind == 0 && drop_layer >= 0 && act != CSB_ACT_ELU) {
+      p.drop_seed = cnn_drop_seed(h, drop_layer); p.drop_threshold = cnn_drop_threshold(h); p.drop_scale = 1.f / (1.f - h->dropout);
+      rc = launch_tn_shape<tc::EPI_BIAS_ACT, tc::VAR_DROPOUT>(in.maps.k128, w, p, h->sm_count, st);
+    } else if (kind == 0) rc = launch_tn_auto<tc::EPI_BIAS_ACT>(in.maps.k128, w, p, h->sm_count, st);
     else if (kind == 1) rc = launch_tn_auto<tc::EPI_BIAS_ADD>(in.maps.k128, w, p, h->sm_count, st);
     else rc = launch_tn_auto<tc::EPI_DGRAD>(in.maps.k128, w, p, h->sm_count, st);
   } else {
@@ -193,21 +203,26 @@ static int cnn_wgrad(csb_cnn* h, const ConvLayerInfo& li, const CnnBuf& in, cons
   }
   const int num_rb = (int)ceil_div(R, 64);
   int splits = std::max(1, std::min(li.max_splits, num_rb));
+  // CTA pairs (256-row tiles, each CTA loading half of the dZ columns) whenever the layer has at least two 128-row blocks of input
+  // channels and more than 128 output columns: a single CTA needs 96 B/clk of operands, more than an SM takes in
+  static const bool no_pairs = getenv("CSB_CNN_NT_SINGLE") != nullptr;            // A/B aid
+  const int n_mma = cnn_mma_width(li.Cout, li.Coutp);
+  const int cg = (!no_pairs && li.Cinp > 128 && n_mma > 128 && n_mma % 32 == 0) ? 2 : 1;
   for (int t = 0; t < li.taps; ++t) {
     tc::NtParams p = {};
-    p.M = li.Cinp; p.N = cnn_mma_width(li.Cout, li.Coutp); p.R = (int)R;
+    p.M = li.Cinp; p.N = n_mma; p.R = (int)R;
     p.rb_per_split = (int)ceil_div(num_rb, splits);
     const int eff = (int)ceil_div(num_rb, p.rb_per_split);
     p.out = h->ws + li.ws_w_off + (size_t)t * tap_elems; p.ld_out = li.Coutp; p.split_stride = (size_t)li.taps * tap_elems;
     p.a_row_offset = t - (li.taps - 1) / 2;
     if (t == 0) { p.colsum_out = h->ws + li.ws_b_off; p.colsum_stride = (size_t)li.Coutp; }
-    int rc = launch_nt_auto(in.maps.mn64, dz.maps.mn64, p, eff, st);
+    int rc = launch_nt_auto(in.maps.mn64, dz.maps.mn64, p, eff, st, cg);
     if (rc) return rc;
     h->launches++;
     splits = eff;
   }
   tab.seg[tab.n++] = {h->ws + li.ws_w_off, (size_t)li.taps * tap_elems, h->grads + li.w_off, (int64_t)(li.taps * tap_elems), splits};
-  tab.seg[tab.n++] = {h->ws + li.ws_b_off, (size_t)li.Coutp, h->grads + li.b_off, (int64_t)li.Coutp, splits * (int)ceil_div(li.Cinp, 128)};
+  tab.seg[tab.n++] = {h->ws + li.ws_b_off, (size_t)li.Coutp, h->grads + li.b_off, (int64_t)li.Coutp, splits * nt_m_tiles(li.Cinp, cg)};
   max_len = std::max<int64_t>(max_len, (int64_t)(li.taps * tap_elems));
   return CSB_OK;
 }
@@ -215,8 +230,8 @@ static int cnn_wgrad(csb_cnn* h, const ConvLayerInfo& li, const CnnBuf& in, cons
 // inverted dropout on a hidden activation buffer (training forward); the mask depends on (seed, training step, layer)
 static int cnn_dropout(csb_cnn* h, CnnBuf& a, int layer_id, int64_t B, cudaStream_t st) {
   const int64_t n8 = B * h->P * a.Cp / 8;
-  const uint32_t seed = h->drop_seed ^ (uint32_t)(h->train_steps * 0x9E3779B97F4A7C15ull >> 32) ^ (uint32_t)(layer_id + 1) * 0x85EBCA77u;
-  const uint32_t thr = (uint32_t)lrintf(h->dropout * 16777216.f);            // keep iff 24 random bits >= rate * 2^24
+  const uint32_t seed = cnn_drop_seed(h, layer_id);
+  const uint32_t thr = cnn_drop_threshold(h);
   simt::dropout_bf16_kernel<<<grid_for(n8, 256, h->sm_count), 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(a.ptr), n8, seed, thr,
                                                                            1.f / (1.f - h->dropout));
   CSB_CUDA_CHECK(cudaGetLastError());
@@ -226,6 +241,8 @@ static int cnn_dropout(csb_cnn* h, CnnBuf& a, int layer_id, int64_t B, cudaStrea
 
 static int cnn_forward_body(csb_cnn* h, const float* x, int64_t B, cudaStream_t st, bool training = false) {
   const bool drop = training && h->dropout > 0.f;
+  static const bool drop_kernel = getenv("CSB_CNN_DROPOUT_KERNEL") != nullptr;     // A/B aid: the separate element-wise dropout pass
+  const bool fold = drop && h->bf16 && !drop_kernel;                              // dropout inside the conv epilogue
   const int64_t R = B * h->P;
   if (h->bf16) simt::cnn_pack_input_kernel<<<grid_for(R * h->in_p, 256, h->sm_count), 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(h->x0.ptr), B, h->L, h->in_ch, h->in_p);
   else simt::cnn_pack_input_f32_kernel<<<grid_for(R * h->in_p, 256, h->sm_count), 256, 0, st>>>(x, reinterpret_cast<float*>(h->x0.ptr), B, h->L, h->in_ch, h->in_p);
@@ -235,10 +252,10 @@ static int cnn_forward_body(csb_cnn* h, const float* x, int64_t B, cudaStream_t 
   int rc;
   for (int i = 0; i < h->depth; ++i) {
     const ConvLayerInfo &c1 = h->layer[3 * i], &c2 = h->layer[3 * i + 1], &cr = h->layer[3 * i + 2];
-    if ((rc = cnn_conv(h, c1, false, *xin, h->h1[i], 0, nullptr, c1.act, h->params + c1.b_off, B, st))) return rc;
-    if (drop && (rc = cnn_dropout(h, h->h1[i], 2 * i, B, st))) return rc;
-    if ((rc = cnn_conv(h, c2, false, h->h1[i], h->h2[i], 0, nullptr, c2.act, h->params + c2.b_off, B, st))) return rc;
-    if (drop && (rc = cnn_dropout(h, h->h2[i], 2 * i + 1, B, st))) return rc;
+    if ((rc = cnn_conv(h, c1, false, *xin, h->h1[i], 0, nullptr, c1.act, h->params + c1.b_off, B, st, 0.f, fold ? 2 * i : -1))) return rc;
+    if (drop && !fold && (rc = cnn_dropout(h, h->h1[i], 2 * i, B, st))) return rc;
+    if ((rc = cnn_conv(h, c2, false, h->h1[i], h->h2[i], 0, nullptr, c2.act, h->params + c2.b_off, B, st, 0.f, fold ? 2 * i + 1 : -1))) return rc;
+    if (drop && !fold && (rc = cnn_dropout(h, h->h2[i], 2 * i + 1, B, st))) return rc;
     // out = conv1x1(x_in) + b + relu(conv2)
     if ((rc = cnn_conv(h, cr, false, *xin, h->ob[i], 1, &h->h2[i], CSB_ACT_NONE, h->params + cr.b_off, B, st))) return rc;
     xin = &h->ob[i];
@@ -261,6 +278,61 @@ static int cnn_head_f32(csb_cnn* h, int64_t B, cudaStream_t st) {
   CSB_CUDA_CHECK(cudaGetLastError());
   h->launches++;
   return CSB_OK;
+}
+
+// everything behind dL/dz of the Dense heads (already in h->dzh): weight / bias gradients of every layer into h->grads
+static int cnn_backward_chain(csb_cnn* h, int64_t B, cudaStream_t st) {
+  const float ds = h->dropout > 0.f ? 1.f / (1.f - h->dropout) : 1.f;        // gradient through a kept element of a dropout layer
+  const int D = h->depth;
+  const ConvLayerInfo &co = h->layer[3 * D], &cd = h->layer[3 * D + 1];
+  const int64_t R = B * h->P;
+  int rc;
+  simt::SegmentTable tab;
+  tab.n = 0;
+  int64_t max_len = 4;
+  auto flush_reduce = [&]() -> int {
+    if (tab.n == 0) return CSB_OK;
+    dim3 grid((unsigned)std::min<int64_t>(ceil_div(max_len / 4, 256), 2 * h->sm_count), (unsigned)tab.n);
+    simt::reduce_partials_kernel<<<grid, 256, 0, st>>>(tab);
+    CSB_CUDA_CHECK(cudaGetLastError());
+    h->launches++;
+    tab.n = 0; max_len = 4;
+    return CSB_OK;
+  };
+  auto act_mask = [&](const CnnBuf& g, const CnnBuf& a, CnnBuf& dz, int act) -> int {
+    const int64_t n = R * g.Cp;
+    if (h->bf16) simt::act_mask_bf16_kernel<<<grid_for(n / 8, 256, h->sm_count), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g.ptr), reinterpret_cast<const __nv_bfloat16*>(a.ptr), reinterpret_cast<__nv_bfloat16*>(dz.ptr), n / 8, act, 0.f, ds);
+    else simt::act_mask_f32_kernel<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(reinterpret_cast<const float*>(g.ptr), reinterpret_cast<const float*>(a.ptr), reinterpret_cast<float*>(dz.ptr), n, act, 0.f);
+    CSB_CUDA_CHECK(cudaGetLastError());
+    h->launches++;
+    return CSB_OK;
+  };
+  // ---- Dense heads and the 1x1 output convolution
+  if ((rc = cnn_wgrad(h, cd, h->e, h->dzh, B, tab, max_len, st))) return rc;
+  if ((rc = cnn_conv(h, cd, true, h->dzh, h->dze, 2, &h->e, co.act, nullptr, B, st))) return rc;            // dze = (dzh . Wd^T) * elu'(e)
+  const CnnBuf& last_out = D > 0 ? h->ob[D - 1] : h->x0;
+  if ((rc = cnn_wgrad(h, co, last_out, h->dze, B, tab, max_len, st))) return rc;
+  int g = 0;
+  // d(block output): no activation after the residual add
+  if ((rc = cnn_conv(h, co, true, h->dze, h->G[g], 0, nullptr, CSB_ACT_NONE, h->zero_bias, B, st))) return rc;
+  // ---- residual blocks, last to first.  G[g] holds dL/d(block output).
+  for (int i = D - 1; i >= 0; --i) {
+    const ConvLayerInfo &c1 = h->layer[3 * i], &c2 = h->layer[3 * i + 1], &cr = h->layer[3 * i + 2];
+    const CnnBuf& xin = i > 0 ? h->ob[i - 1] : h->x0;
+    if ((rc = act_mask(h->G[g], h->h2[i], h->Z2, c2.act))) return rc;                                       // dz2 = d_out * relu'(h2)
+    if ((rc = cnn_wgrad(h, cr, xin, h->G[g], B, tab, max_len, st))) return rc;                               // residual 1x1: dW = xin^T d_out
+    if ((rc = cnn_wgrad(h, c2, h->h1[i], h->Z2, B, tab, max_len, st))) return rc;
+    if ((rc = cnn_conv(h, c2, true, h->Z2, h->Z1, 2, &h->h1[i], c1.act, nullptr, B, st, h->dropout > 0.f ? ds : 0.f))) return rc;   // dz1 = conv^T(dz2; W2) * relu'(h1) [* 1/(1-p)]
+    if ((rc = cnn_wgrad(h, c1, xin, h->Z1, B, tab, max_len, st))) return rc;
+    if (i > 0) {
+      // d(x_in) = conv^T(dz1; W1) + conv1x1^T(d_out; Wr)
+      if ((rc = cnn_conv(h, c1, true, h->Z1, h->T, 0, nullptr, CSB_ACT_NONE, h->zero_bias, B, st))) return rc;
+      if ((rc = cnn_conv(h, cr, true, h->G[g], h->G[g ^ 1], 1, &h->T, CSB_ACT_NONE, h->zero_bias, B, st))) return rc;
+      g ^= 1;
+    }
+    if (tab.n + 8 > (int)(sizeof(tab.seg) / sizeof(tab.seg[0]))) { if ((rc = flush_reduce())) return rc; }
+  }
+  return flush_reduce();
 }
 
 extern "C" {
@@ -441,6 +513,7 @@ int csb_cnn_forward(csb_cnn* h, const float* x, float* y_pred, int64_t B, void* 
   int rc;
   if ((rc = cnn_build_maps(h, B))) return rc;
   if ((rc = cnn_forward_body(h, x, B, st))) return rc;
+  h->fwd_B = B;
   const ConvLayerInfo& cd = h->layer[3 * h->depth + 1];
   if (!h->bf16) {
     if ((rc = cnn_head_f32(h, B, st))) return rc;
@@ -467,10 +540,9 @@ int csb_cnn_train_step(csb_cnn* h, const float* x, const float* y, int64_t B, fl
   int rc;
   if ((rc = cnn_build_maps(h, B))) return rc;
   if ((rc = cnn_forward_body(h, x, B, st, true))) return rc;
-  const float ds = h->dropout > 0.f ? 1.f / (1.f - h->dropout) : 1.f;        // gradient through a kept element of a dropout layer
   h->train_steps++;
-  const int D = h->depth;
-  const ConvLayerInfo &co = h->layer[3 * D], &cd = h->layer[3 * D + 1];
+  h->fwd_B = -1;
+  const ConvLayerInfo& cd = h->layer[3 * h->depth + 1];
   const int64_t R = B * h->P;
   // ---- head + loss: dzh = dL/dz of the fused Dense heads
   if (h->bf16) {
@@ -495,52 +567,34 @@ int csb_cnn_train_step(csb_cnn* h, const float* x, const float* y, int64_t B, fl
   }
   CSB_CUDA_CHECK(cudaGetLastError());
   h->launches++;
-  simt::SegmentTable tab;
-  tab.n = 0;
-  int64_t max_len = 4;
-  auto flush_reduce = [&]() -> int {
-    if (tab.n == 0) return CSB_OK;
-    dim3 grid((unsigned)std::min<int64_t>(ceil_div(max_len / 4, 256), 2 * h->sm_count), (unsigned)tab.n);
-    simt::reduce_partials_kernel<<<grid, 256, 0, st>>>(tab);
-    CSB_CUDA_CHECK(cudaGetLastError());
-    h->launches++;
-    tab.n = 0; max_len = 4;
-    return CSB_OK;
-  };
-  auto act_mask = [&](const CnnBuf& g, const CnnBuf& a, CnnBuf& dz, int act) -> int {
-    const int64_t n = R * g.Cp;
-    if (h->bf16) simt::act_mask_bf16_kernel<<<grid_for(n / 8, 256, h->sm_count), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(g.ptr), reinterpret_cast<const __nv_bfloat16*>(a.ptr), reinterpret_cast<__nv_bfloat16*>(dz.ptr), n / 8, act, 0.f, ds);
-    else simt::act_mask_f32_kernel<<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(reinterpret_cast<const float*>(g.ptr), reinterpret_cast<const float*>(a.ptr), reinterpret_cast<float*>(dz.ptr), n, act, 0.f);
-    CSB_CUDA_CHECK(cudaGetLastError());
-    h->launches++;
-    return CSB_OK;
-  };
-  // ---- Dense heads and the 1x1 output convolution
-  if ((rc = cnn_wgrad(h, cd, h->e, h->dzh, B, tab, max_len, st))) return rc;
-  if ((rc = cnn_conv(h, cd, true, h->dzh, h->dze, 2, &h->e, co.act, nullptr, B, st))) return rc;            // dze = (dzh . Wd^T) * elu'(e)
-  const CnnBuf& last_out = D > 0 ? h->ob[D - 1] : h->x0;
-  if ((rc = cnn_wgrad(h, co, last_out, h->dze, B, tab, max_len, st))) return rc;
-  int g = 0;
-  // d(block output): no activation after the residual add
-  if ((rc = cnn_conv(h, co, true, h->dze, h->G[g], 0, nullptr, CSB_ACT_NONE, h->zero_bias, B, st))) return rc;
-  // ---- residual blocks, last to first.  G[g] holds dL/d(block output).
-  for (int i = D - 1; i >= 0; --i) {
-    const ConvLayerInfo &c1 = h->layer[3 * i], &c2 = h->layer[3 * i + 1], &cr = h->layer[3 * i + 2];
-    const CnnBuf& xin = i > 0 ? h->ob[i - 1] : h->x0;
-    if ((rc = act_mask(h->G[g], h->h2[i], h->Z2, c2.act))) return rc;                                       // dz2 = d_out * relu'(h2)
-    if ((rc = cnn_wgrad(h, cr, xin, h->G[g], B, tab, max_len, st))) return rc;                               // residual 1x1: dW = xin^T d_out
-    if ((rc = cnn_wgrad(h, c2, h->h1[i], h->Z2, B, tab, max_len, st))) return rc;
-    if ((rc = cnn_conv(h, c2, true, h->Z2, h->Z1, 2, &h->h1[i], c1.act, nullptr, B, st, h->dropout > 0.f ? ds : 0.f))) return rc;   // dz1 = conv^T(dz2; W2) * relu'(h1) [* 1/(1-p)]
-    if ((rc = cnn_wgrad(h, c1, xin, h->Z1, B, tab, max_len, st))) return rc;
-    if (i > 0) {
-      // d(x_in) = conv^T(dz1; W1) + conv1x1^T(d_out; Wr)
-      if ((rc = cnn_conv(h, c1, true, h->Z1, h->T, 0, nullptr, CSB_ACT_NONE, h->zero_bias, B, st))) return rc;
-      if ((rc = cnn_conv(h, cr, true, h->G[g], h->G[g ^ 1], 1, &h->T, CSB_ACT_NONE, h->zero_bias, B, st))) return rc;
-      g ^= 1;
-    }
-    if (tab.n + 8 > (int)(sizeof(tab.seg) / sizeof(tab.seg[0]))) { if ((rc = flush_reduce())) return rc; }
-  }
-  return flush_reduce();
+  return cnn_backward_chain(h, B, st);
+}
+
+int csb_cnn_backward(csb_cnn* h, const float* y_pred, const float* dy, int64_t B, void* stream) {
+  CSB_REQUIRE(h && y_pred && dy, CSB_EINVAL, "null argument");
+  CSB_REQUIRE(B >= 1 && B <= h->cfg.max_batch && h->fwd_B == B, CSB_ESTATE,
+              "csb_cnn_backward follows csb_cnn_forward on the same batch (the activations live in the handle)");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t n = B * h->P * h->out_p;
+  if (h->bf16) simt::cnn_head_grad_kernel<__nv_bfloat16><<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(y_pred, dy, reinterpret_cast<__nv_bfloat16*>(h->dzh.ptr), h->out_p, B, h->L, h->out_ch, h->out_lin);
+  else simt::cnn_head_grad_kernel<float><<<grid_for(n, 256, h->sm_count), 256, 0, st>>>(y_pred, dy, reinterpret_cast<float*>(h->dzh.ptr), h->out_p, B, h->L, h->out_ch, h->out_lin);
+  CSB_CUDA_CHECK(cudaGetLastError());
+  h->launches++;
+  const float keep = h->dropout;
+  h->dropout = 0.f;                          // csb_cnn_forward never drops: no 1 / (1 - p) factors in its backward pass
+  const int rc = cnn_backward_chain(h, B, st);
+  h->dropout = keep;
+  return rc;
+}
+int csb_cnn_set_params_device(csb_cnn* h, const float* params_dev, void* stream) {
+  CSB_REQUIRE(h && params_dev, CSB_EINVAL, "null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = cnn_pad_copy(h, h->params, const_cast<float*>(params_dev), 0, st);
+  return rc ? rc : cnn_repack(h, st);
+}
+int csb_cnn_get_grads_device(csb_cnn* h, float* grads_dev, void* stream) {
+  CSB_REQUIRE(h && grads_dev, CSB_EINVAL, "null argument");
+  return cnn_pad_copy(h, h->grads, grads_dev, 1, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int csb_cnn_apply_opt(csb_cnn* h, int rule, float lr, float beta1, float beta2, float eps, float wd, void* stream) {

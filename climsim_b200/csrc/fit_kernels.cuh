@@ -167,5 +167,28 @@ hsr_grad_kernel(const float* __restrict__ mu, const float* __restrict__ lp, cons
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// CNN autograd entry: upstream gradient dy (B, L, C) w.r.t. the network output -> dL/dz of the fused Dense heads in the halo layout
+// [B*(L+2), ld]: channels < out_lin are linear, the others ReLU (their derivative from the saved prediction: p > 0); halo rows and
+// padding channels are zero.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename TZ>
+__global__ void __launch_bounds__(256)
+cnn_head_grad_kernel(const float* __restrict__ y_pred, const float* __restrict__ dy, TZ* __restrict__ dz, int ld, int64_t B, int L, int C, int out_lin) {
+  const int64_t total = B * (L + 2) * ld;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % ld);
+    const int64_t r = i / ld;
+    const int l = (int)(r % (L + 2)) - 1;
+    const int64_t b = r / (L + 2);
+    float g = 0.f;
+    if (c < C && l >= 0 && l < L) {
+      const int64_t e = (b * L + l) * C + c;
+      g = dy[e] * ((c < out_lin || y_pred[e] > 0.f) ? 1.f : 0.f);
+    }
+    if constexpr (sizeof(TZ) == 2) dz[i] = __float2bfloat16_rn(g); else dz[i] = g;
+  }
+}
+
 }  // namespace simt
 }  // namespace csb

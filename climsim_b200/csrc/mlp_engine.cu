@@ -202,7 +202,9 @@ static int launch_nt(const CUtensorMap& ta, const CUtensorMap& tb, const tc::NtP
     CSB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_set = true;
   }
-  CSB_REQUIRE(CG == 1 || p.N % 128 == 0, CSB_EUNSUPPORTED, "CTA-pair weight-gradient tiles need N %% 128 == 0 (N = %d)", p.N);
+  // pairs: every n-block's width splits into two halves of whole 8-column pieces that are valid cta_group::2 MMA widths (N % 32 == 0);
+  // the halves need not be 64-column-chunk aligned in global memory (the TMA box of the second CTA simply starts mid-chunk)
+  CSB_REQUIRE(CG == 1 || p.N % 32 == 0, CSB_EUNSUPPORTED, "CTA-pair weight-gradient tiles need N %% 32 == 0 (N = %d)", p.N);
   const unsigned m_tiles = (unsigned)ceil_div(ceil_div(p.M, tc::BM), CG), n_blocks = (unsigned)ceil_div(p.N, BN);
   const unsigned tiles = m_tiles * n_blocks;                                                     // CG m-blocks per tile
   cudaLaunchConfig_t cfg = {};

@@ -63,6 +63,11 @@ struct GemmParams {
   float alpha;
   int head_relu_from;          // EPI_HEAD_*: columns >= this get ReLU (-1: none); otherwise `act` applies
   float dgrad_scale;           // EPI_DGRAD: extra factor on the result (1 / (1 - p) of a dropout layer behind the activation); 0 = none
+  // VAR_DROPOUT (EPI_BIAS_ACT): inverted dropout behind the activation, folded into the epilogue -- the same counter-based keep
+  // decisions as simt::dropout_bf16_kernel (one 32-bit mix of (seed, index of the 8-element group in the output buffer) starts an LCG
+  // whose high 24 bits decide the eight elements), so the separate element-wise pass over the activation disappears
+  uint32_t drop_seed, drop_threshold;
+  float drop_scale;
   const float* bias;           // [N]
   void* out;                   // bf16 or fp32 [M, ld_out]
   int ld_out;
@@ -407,7 +412,11 @@ __device__ __forceinline__ RowInfo make_row_info(const GemmParams& p, int grow) 
 // `sv` holds the 32 saved bf16 values of EPI_DGRAD / EPI_BIAS_ADD.
 // STAGED: the 32 bf16 results go to this thread's row of the warp's staging tile in shared memory (`stage_addr`); the warp writes the
 // tile to global memory afterwards with fully coalesced stores (see the kernel).
-template <int EPI, bool ELU, bool GENERAL_LOSS, bool STAGED>
+__device__ __forceinline__ uint32_t drop_mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+template <int EPI, bool ELU, bool GENERAL_LOSS, bool STAGED, bool DROPOUT = false>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float* sbias, const float* sloss_w, const RowInfo& ri, int gcol,
                                                const uint32_t (&raw)[32], const uint32_t (&sv)[16], const float (&yv)[32], float& loss_acc,
                                                uint32_t mask_word, uint32_t stage_addr) {
@@ -441,6 +450,19 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
       if (st_ok) p.mask_out[(size_t)(gcol >> 5) * p.ld_mask + ri.grow] = ~m;
     }
     act_fwd32<ELU>(p.act, p.alpha, v);
+    if constexpr (DROPOUT) {
+      const unsigned long long g0 = ((unsigned long long)ri.grow * (unsigned long long)p.ld_out + (unsigned long long)gcol) >> 3;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const unsigned long long i = g0 + g;
+        uint32_t st = drop_mix32(p.drop_seed ^ drop_mix32((uint32_t)i) ^ (uint32_t)(i >> 32) * 0x9E3779B1u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          st = st * 747796405u + 2891336453u;
+          v[8 * g + j] = (st >> 8) >= p.drop_threshold ? v[8 * g + j] * p.drop_scale : 0.f;
+        }
+      }
+    }
     if (ri.zero_row) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = 0.f;
@@ -620,7 +642,7 @@ struct TnSmem {
 // both keep rarely used code out of the instruction stream (and the register budget) of the common kernels
 // bit 2 = results staged in shared memory and written with coalesced stores (the launches whose time is the epilogue: K <= 256)
 // bit 3 = in-kernel cycle counters for the micro-benchmark (p.stats); production instantiations carry none of that code
-constexpr int VAR_ELU = 1, VAR_GENERAL_LOSS = 2, VAR_STAGED = 4, VAR_STATS = 8;
+constexpr int VAR_ELU = 1, VAR_GENERAL_LOSS = 2, VAR_STAGED = 4, VAR_STATS = 8, VAR_DROPOUT = 16;
 
 // Tile schedule of the persistent kernel; all three warp roles walk the same sequence.
 //   round-robin (the first design): tile t = (m-group t / n_blocks, n-block t % n_blocks), CTA group g takes t = g, g + G, ...
@@ -681,6 +703,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   constexpr bool BF16_OUT = (EPI == EPI_BIAS_ACT || EPI == EPI_HEAD_LOSS || EPI == EPI_DGRAD || EPI == EPI_DGRAD_MASK || EPI == EPI_BIAS_ADD);
   constexpr bool STAGED = (VAR & VAR_STAGED) != 0 && BF16_OUT;
   constexpr bool STATS = (VAR & VAR_STATS) != 0;
+  constexpr bool DROPOUT = (VAR & VAR_DROPOUT) != 0 && EPI == EPI_BIAS_ACT;
   const bool BALANCED = p.balanced != 0 && EPI != EPI_HEAD_LOSS;      // the loss partials are indexed by the round-robin tile grid
   using L = TnSmem<BN, STAGES, CG, STAGED>;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
@@ -887,7 +910,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int j = 0; j < 32; ++j) raw[j] = 0u;
           }
           if (!(p.dbg & 2))
-            epilogue_chunk<EPI, ELU, GENERAL_LOSS, STAGED>(p, sbias, sloss_w, ri, n0 + c, raw, sv[i], yv, loss_acc, mask_words[i],
+            epilogue_chunk<EPI, ELU, GENERAL_LOSS, STAGED, DROPOUT>(p, sbias, sloss_w, ri, n0 + c, raw, sv[i], yv, loss_acc, mask_words[i],
                                                            stage_warp + (uint32_t)(lane * L::OUT_PITCH + 64 * i));
         }
       }
@@ -1128,7 +1151,9 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         acc8[j] += __shfl_xor_sync(0xffffffffu, acc8[j], 8);
         acc8[j] += __shfl_xor_sync(0xffffffffu, acc8[j], 16);
       }
-      if (rs == 0) {
+      // (a CTA's share of the columns need not be a whole number of 64-column chunks -- n_valid = 160 on a pair gives 80 -- so the
+      // last chunk may hold over-fetched columns of the neighbour: only this CTA's own 8-column pieces are written)
+      if (rs == 0 && 64 * warp + 8 * lp < n_valid / CG) {
         float* dst = p.colsum_out + ((size_t)split * num_m_tiles + m_tile) * p.colsum_stride + nb0 + 64 * warp + 8 * lp;
         *reinterpret_cast<float4*>(dst) = make_float4(acc8[0], acc8[1], acc8[2], acc8[3]);
         *reinterpret_cast<float4*>(dst + 4) = make_float4(acc8[4], acc8[5], acc8[6], acc8[7]);

@@ -452,6 +452,21 @@ class CNNEngine:
                                                _lib.current_stream_ptr()), "csb_cnn_train_step")
         return self._loss_buf
 
+    def backward(self, y_pred: torch.Tensor, dy: torch.Tensor) -> None:
+        """Parameter gradients for an upstream gradient ``dy`` w.r.t. the output of the preceding ``forward`` on the same batch."""
+        y_pred, dy = _f32_cuda(y_pred, "y_pred"), _f32_cuda(dy, "dy")
+        _lib.check(self.lib.csb_cnn_backward(self._h, y_pred.data_ptr(), dy.data_ptr(), dy.shape[0], _lib.current_stream_ptr()), "csb_cnn_backward")
+
+    def set_params_device(self, flat: torch.Tensor) -> None:
+        flat = _f32_cuda(flat, "flat")
+        assert flat.numel() == self.n_params
+        _lib.check(self.lib.csb_cnn_set_params_device(self._h, flat.data_ptr(), _lib.current_stream_ptr()), "csb_cnn_set_params_device")
+
+    def get_grads_device(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        out = out if out is not None else torch.empty(self.n_params, dtype=torch.float32, device="cuda")
+        _lib.check(self.lib.csb_cnn_get_grads_device(self._h, out.data_ptr(), _lib.current_stream_ptr()), "csb_cnn_get_grads_device")
+        return out
+
     def apply_opt(self, rule: str = "adam_keras", lr: float = 1e-4, beta1: float = 0.9, beta2: float = 0.999, eps: Optional[float] = None,
                   weight_decay: float = 0.0) -> None:
         if eps is None:

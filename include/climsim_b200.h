@@ -237,6 +237,13 @@ int  csb_cnn_debug_read_hidden(csb_cnn* h, int which, int block, float* dst, int
 int  csb_cnn_forward(csb_cnn* h, const float* x, float* y_pred, int64_t B, void* stream);                  /* model.predict */
 int  csb_cnn_train_step(csb_cnn* h, const float* x, const float* y, int64_t B, float grad_scale, float* loss_out, void* stream);
 int  csb_cnn_grad_buffer(csb_cnn* h, float** ptr, size_t* n);
+/* autograd entry (the reference's CNN is a Keras model driven by model.fit; a torch.nn.Module face needs backward for an arbitrary
+ * upstream gradient): after csb_cnn_forward(h, x, y_pred, B) on the same batch, csb_cnn_backward takes dL/d(y_pred) (B, levels, out_ch)
+ * and leaves every parameter gradient in the gradient buffer (no dropout, as in csb_cnn_forward; dL/dx is not produced).
+ * csb_cnn_set_params_device / csb_cnn_get_grads_device move the flat unpadded blobs without leaving the device. */
+int  csb_cnn_backward(csb_cnn* h, const float* y_pred, const float* dy, int64_t B, void* stream);
+int  csb_cnn_set_params_device(csb_cnn* h, const float* params_dev, void* stream);
+int  csb_cnn_get_grads_device(csb_cnn* h, float* grads_dev, void* stream);
 int  csb_cnn_apply_opt(csb_cnn* h, int rule, float lr, float beta1, float beta2, float eps, float wd, void* stream);
 int64_t csb_cnn_launch_count(const csb_cnn* h);
 

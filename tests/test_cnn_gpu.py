@@ -181,3 +181,38 @@ def test_cnn_train_step_against_the_bf16_emulating_oracle(depth, width, B, loss)
         worst = max(worst, err)
         assert err <= ((2e-2 if depth <= 4 else 4e-2) if loss == "mse" else 1e-1), (i, a.shape, err)
     print(f"cnn depth {depth} width {width} B {B} {loss}: worst gradient rel-L2 vs emulating oracle {worst:.2e}")
+
+
+@pytest.mark.parametrize("dtype,tol", [("fp32", 3e-5), ("bf16", 2e-2)])
+def test_cnn_module_autograd(dtype, tol):
+    """baseline_models.CNN as an ordinary torch module: forward records an autograd node whose backward is csb_cnn_backward, so a
+    loss written in torch (here the reference's mse_adjusted, hpo_train.py:114-116) and torch.optim work on top.  Gradients against
+    autograd on the oracle (fp32 engine: 3e-5 of the largest entry; bf16 engine: relative L2 against the bf16-emulating oracle)."""
+    from climsim_b200.baseline_models import CNN
+    depth, width, B = 2, 64, 7
+    ref = M.CNNRef(depth=depth, width=width, seed=3)
+    ref.randomize_biases(4)
+    net = CNN(depth=depth, width=width, dtype=dtype, max_batch=8, dropout=0.0)
+    net.load_keras_weights([p.detach().numpy() for p in ref.params])
+    g = torch.Generator().manual_seed(5)
+    x, y = 0.5 * torch.randn(B, 60, 6, generator=g), 0.3 * torch.randn(B, 60, 10, generator=g)
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    opt.zero_grad()
+    pred = net(x.cuda())
+    loss = M.mse_adjusted(y.cuda(), pred)
+    loss.backward()
+    want_loss, want_grads = ref.emulated_train_step(x, y, loss="mse", emulate_bf16=dtype == "bf16")
+    assert abs(loss.item() - want_loss.item()) <= (1e-5 if dtype == "fp32" else 2e-3) * abs(want_loss.item())
+    got = net.engine.split_flat(net.flat.grad.cpu().numpy())
+    want = net.engine.split_flat(_flat(want_grads))
+    for i, (a, b) in enumerate(zip(got, want)):
+        if np.abs(b).max() == 0:
+            continue
+        err = np.abs(a - b).max() / np.abs(b).max() if dtype == "fp32" else np.linalg.norm(a - b) / np.linalg.norm(b)
+        assert err <= tol, (i, a.shape, err)
+    before = net(x.cuda()).detach().clone()
+    opt.step()                                                        # torch's optimizer moves the flat parameter; the next forward re-uploads it
+    after = net(x.cuda()).detach()
+    assert (after - before).abs().max().item() > 1e-5
+    with torch.no_grad():                                             # inference path: no autograd node
+        assert not net(x.cuda()).requires_grad
