@@ -981,6 +981,10 @@ struct NtParams {
   float* colsum_out;       // optional: column sums of B (bias gradient) partials: colsum_out + split * colsum_stride + n
   size_t colsum_stride;
   int a_row_offset;        // Conv1D weight gradient of tap t: A rows shifted by (t - center); out-of-range rows read as zero
+  // All taps of a Conv1D in ONE launch: the output rows are stacked tap-major (M = taps * a_tap_m, exactly the layout of the
+  // [taps][Cin][Cout] kernel), and 64-column chunk c of the stacked A^T belongs to tap t = c / (a_tap_m / 64): it is loaded from
+  // columns (c mod a_tap_m / 64) * 64 of the activation matrix with its rows shifted by (t - a_tap_center).  0 = off.
+  int a_tap_m, a_tap_center;
 };
 
 template <int BN, int STAGES, int CG = 1>
@@ -1086,7 +1090,15 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mbar_wait(empty_bar(s), ph ^ 1u);
         mbar_expect_tx(full_bar(s), (uint32_t)((a_chunks + b_chunks) * CHUNK_BYTES));
         const uint32_t sa = smem_base + s * L::STAGE_BYTES;
-        for (int c = 0; c < a_chunks; ++c) tma_load_2d(sa + c * CHUNK_BYTES, &tmap_a, full_bar(s), m0 + 64 * c, rb * BK + p.a_row_offset);
+        for (int c = 0; c < a_chunks; ++c) {
+          int mcol = m0 + 64 * c, roff = p.a_row_offset;
+          if (p.a_tap_m > 0) {                       // stacked taps: chunk -> (tap, column inside the activation matrix)
+            const int t = mcol / p.a_tap_m;
+            roff = t - p.a_tap_center;
+            mcol = (mcol < p.M) ? mcol - t * p.a_tap_m : p.a_tap_m;      // past the last tap: an out-of-range column, zero-filled by TMA
+          }
+          tma_load_2d(sa + c * CHUNK_BYTES, &tmap_a, full_bar(s), mcol, rb * BK + roff);
+        }
         for (int c = 0; c < b_chunks; ++c) tma_load_2d(sa + L::A_BYTES + c * CHUNK_BYTES, &tmap_b, full_bar(s), nb0 + 64 * c, rb * BK);
         if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
