@@ -6,6 +6,6 @@ Device side: hand-written sm_100a CUDA in ``csrc/`` behind the C ABI of ``includ
 """
 from . import _lib  # noqa: F401
 from .engine import CNNEngine, MLPEngine  # noqa: F401
-from .stream import NpyColumnStream, StreamPlan  # noqa: F401
+from .stream import NpyColumnStream, ResidentColumnStream, StreamPlan  # noqa: F401
 
 __version__ = "0.1.0"

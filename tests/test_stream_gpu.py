@@ -39,6 +39,35 @@ def test_stream_matches_plan_and_covers_the_epoch(tmp_path, n, batch, window, wo
     assert (seen == 1).all()
 
 
+@pytest.mark.parametrize("n,batch,world", [(5000, 512, 1), (5003, 512, 2), (777, 1024, 1)])
+def test_resident_stream_full_shuffle_matches_plan(tmp_path, n, batch, world):
+    """ResidentColumnStream: the rank's share uploaded once (in two chunks here), every epoch a fresh permutation of ALL its rows cut
+    by csb_gather_rows; order = StreamPlan with one window spanning the share; ranks get equal batch counts (padded shares)."""
+    from climsim_b200 import ResidentColumnStream
+    x, y = _files(tmp_path, n)
+    seen = np.zeros(n, np.int64)
+    counts = []
+    for rank in range(world):
+        st = ResidentColumnStream(str(tmp_path / "train_input.npy"), str(tmp_path / "train_target.npy"), batch, seed=4, rank=rank, world=world,
+                                  chunk_rows=max(1, -(-n // world) // 2 + 1))
+        assert len(st.plan.windows()) == 1
+        orders = []
+        for epoch in (0, 1):
+            want = list(st.plan.epoch_rows(epoch))
+            got = 0
+            for (bx, by), rows in zip(st.epoch(epoch), want):
+                np.testing.assert_array_equal(bx.cpu().numpy(), x[rows])
+                np.testing.assert_array_equal(by.cpu().numpy(), y[rows])
+                if epoch == 0:
+                    seen[rows] += 1
+                got += 1
+            assert got == len(want) == len(st)
+            orders.append(np.concatenate(want))
+        assert (orders[0] != orders[1]).any()                            # reshuffled every epoch, over the whole share
+        counts.append(len(st))
+    assert len(set(counts)) == 1 and (seen >= 1).all() and int((seen - 1).sum()) == -(-n // world) * world - n
+
+
 def test_gather_rows_reports_bad_indices():
     from climsim_b200 import _lib
     lib = _lib.load()
