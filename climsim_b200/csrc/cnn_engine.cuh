@@ -20,7 +20,13 @@ struct ConvLayerInfo {
   size_t ws_w_off, ws_b_off;
   int max_splits;
   __nv_bfloat16 *wt16 = nullptr, *wd16 = nullptr;
+  // pitch / first column of the copies: the residual 1x1 layer's copies live behind the k = 3 layer they are merged with
+  // (wd16 behind conv1's, wt16 behind conv2's), as one more tap of the same B operand
+  int wt_ld = 0, wt_col0 = 0, wd_ld = 0, wd_col0 = 0;
+  bool wt_alias = false, wd_alias = false;     // the storage belongs to another layer
   CUtensorMap tm_wt, tm_wd;
+  CUtensorMap tm_wtc, tm_wdc;                  // the merged operands (on the k = 3 layers that host a 1x1 layer's copy)
+  bool has_wtc = false, has_wdc = false;
 };
 
 struct BufMaps { CUtensorMap k128, mn64; };
@@ -48,12 +54,19 @@ struct csb_cnn {
   uint32_t drop_seed = 0;
   int64_t train_steps = 0;                       // advances the dropout masks from step to step
   int64_t fwd_B = -1;                            // batch of the last csb_cnn_forward (its activations are what csb_cnn_backward uses)
+  // launch merging (read from the environment when the handle is created; A/B aids):
+  bool merge_bwd = true;                         // CSB_CNN_NO_MERGE=1 off: d(block input) + the previous block's dz2 as one GEMM launch
+  bool merge_fwd = false;                        // CSB_CNN_MERGE_FWD=1 on: conv2 + residual 1x1 as one launch (measured: no gain)
 };
+static bool g_cnn_ktrim = true;                  // CSB_CNN_NO_KTRIM=1 off
 
 static void cnn_free(csb_cnn* h) {
   auto F = [](void* p) { if (p) cudaFree(p); };
   F(h->params); F(h->grads); F(h->m); F(h->v); F(h->ws); F(h->zero_bias);
-  for (int l = 0; l < h->n_layers; ++l) { F(h->layer[l].wt16); F(h->layer[l].wd16); }
+  for (int l = 0; l < h->n_layers; ++l) {
+    if (!h->layer[l].wt_alias) F(h->layer[l].wt16);
+    if (!h->layer[l].wd_alias) F(h->layer[l].wd16);
+  }
   F(h->x0.ptr); F(h->e.ptr); F(h->G[0].ptr); F(h->G[1].ptr); F(h->Z1.ptr); F(h->Z2.ptr); F(h->T.ptr); F(h->dzh.ptr); F(h->dze.ptr);
   for (int i = 0; i < 16; ++i) { F(h->h1[i].ptr); F(h->h2[i].ptr); F(h->ob[i].ptr); }
   F(h->pred); F(h->d_loss_w); F(h->loss_partials); F(h->d_loss);
@@ -66,7 +79,7 @@ static int cnn_repack(csb_cnn* h, cudaStream_t st) {
   int64_t mx = 1;
   for (int l = 0; l < h->n_layers; ++l) {
     ConvLayerInfo& li = h->layer[l];
-    tab.l[l] = {h->params + li.w_off, li.wt16, li.wd16, li.taps, li.Cinp, li.Coutp};
+    tab.l[l] = {h->params + li.w_off, li.wt16, li.wd16, li.taps, li.Cinp, li.Coutp, li.wt_ld, li.wt_col0, li.wd_ld, li.wd_col0};
     mx = std::max<int64_t>(mx, (int64_t)li.taps * li.Cinp * li.Coutp);
   }
   dim3 grid((unsigned)std::min<int64_t>(ceil_div(mx, 256), 4 * h->sm_count), (unsigned)h->n_layers);
@@ -122,6 +135,13 @@ static inline int cnn_mma_width(int c, int cp) {
   return (cp > 256 && w >= 256 && w < cp) ? w : cp;
 }
 
+// MMAs needed for the last 64-channel contraction block of a tensor with `c` real channels stored with pitch `cp`: the channels behind
+// c are zero, so the 16-channel instructions that would only see zeros are skipped (406 -> 2 of 4).  0 = all four.
+static inline int cnn_tail_k(int c, int cp) {
+  const int r = c - (cp - 64);
+  return (!g_cnn_ktrim || r <= 0 || r > 48) ? 0 : (r + 15) / 16;
+}
+
 // one convolution-as-GEMM launch.  `dgrad` selects the flipped/transposed weights (output width = Cinp).
 //   kind 0: out = act(conv + bias)   kind 1: out = conv + bias + saved   kind 2: out = conv * act'(saved)
 static inline uint32_t cnn_drop_seed(const csb_cnn* h, int layer_id) {
@@ -139,12 +159,22 @@ static int cnn_conv(csb_cnn* h, const ConvLayerInfo& li, bool dgrad, const CnnBu
     p.M = M; p.N = cnn_mma_width(dgrad ? li.Cin : li.Cout, N); p.K = li.taps * Kt; p.kb_per_tap = Kt / 64; p.tap_center = (li.taps - 1) / 2;
     p.halo_period = h->P;
     p.act = act; p.head_relu_from = -1; p.bias = bias; p.dgrad_scale = dgrad_scale;
+    p.tap_tail_k = cnn_tail_k(dgrad ? li.Cout : li.Cin, Kt);
     const CUtensorMap& w = dgrad ? li.tm_wd : li.tm_wt;
     p.out = out.ptr; p.ld_out = out.Cp;
     if (saved) { p.saved = reinterpret_cast<const __nv_bfloat16*>(saved->ptr); p.ld_saved = saved->Cp; }
+    // the instantiations that skip the all-zero MMAs of a tap's last block (VAR_KTRIM) exist for the wide pair tiles only
+    const bool trim = p.tap_tail_k > 0 && g_use_pairs && p.N > 128 && act != CSB_ACT_ELU;
+    if (!trim) p.tap_tail_k = 0;
+    constexpr int KT = tc::VAR_KTRIM;
     if (kind == 0 && drop_layer >= 0 && act != CSB_ACT_ELU) {
       p.drop_seed = cnn_drop_seed(h, drop_layer); p.drop_threshold = cnn_drop_threshold(h); p.drop_scale = 1.f / (1.f - h->dropout);
-      rc = launch_tn_shape<tc::EPI_BIAS_ACT, tc::VAR_DROPOUT>(in.maps.k128, w, p, h->sm_count, st);
+      if (trim) rc = launch_tn<256, 6, tc::EPI_BIAS_ACT, 2, tc::VAR_DROPOUT | KT>(in.maps.k128, w, p, h->sm_count, st);
+      else rc = launch_tn_shape<tc::EPI_BIAS_ACT, tc::VAR_DROPOUT>(in.maps.k128, w, p, h->sm_count, st);
+    } else if (trim) {
+      if (kind == 0) rc = launch_tn<256, 6, tc::EPI_BIAS_ACT, 2, KT>(in.maps.k128, w, p, h->sm_count, st);
+      else if (kind == 1) rc = launch_tn<256, 6, tc::EPI_BIAS_ADD, 2, KT>(in.maps.k128, w, p, h->sm_count, st);
+      else rc = launch_tn<256, 6, tc::EPI_DGRAD, 2, KT>(in.maps.k128, w, p, h->sm_count, st);
     } else if (kind == 0) rc = launch_tn_auto<tc::EPI_BIAS_ACT>(in.maps.k128, w, p, h->sm_count, st);
     else if (kind == 1) rc = launch_tn_auto<tc::EPI_BIAS_ADD>(in.maps.k128, w, p, h->sm_count, st);
     else rc = launch_tn_auto<tc::EPI_DGRAD>(in.maps.k128, w, p, h->sm_count, st);
@@ -171,6 +201,64 @@ static int cnn_conv(csb_cnn* h, const ConvLayerInfo& li, bool dgrad, const CnnBu
     }
     if (cudaGetLastError() != cudaSuccess) { set_last_error("sgemm launch failed"); rc = CSB_ECUDA; }
   }
+  if (rc) return rc;
+  h->launches++;
+  return CSB_OK;
+}
+
+// Second half of a residual block in ONE launch (bf16, CTA pairs): the residual 1x1 convolution is a fourth "tap" of conv2's GEMM,
+// read from the block input (VAR_A2) and accumulated separately (VAR_ACC2) because the ReLU [+ dropout] sits on conv2's sum alone:
+//   h2  = dropout(relu(conv2(h1) + b2))                 -> out_h2   (kept for the backward pass)
+//   out = (conv1x1(x_in) + br) + bf16(h2)               -> out_block
+// Replaces conv2 -> h2 and conv1x1(x_in) + h2 -> out (EPI_BIAS_ADD): one launch and one pass over h2 fewer, bit-identical outputs.
+// OPT-IN (CSB_CNN_MERGE_FWD=1): two 256-column accumulators fill the 512 TMEM columns, so the epilogue of a tile no longer overlaps
+// the next tile's MMAs, and that costs what the saved launch gains (28.5 against 28.4 ms per step on the same box).
+static int cnn_conv2_residual(csb_cnn* h, const ConvLayerInfo& c2, const ConvLayerInfo& cr, const CnnBuf& h1, const CnnBuf& xin, CnnBuf& out_h2,
+                              CnnBuf& out_block, int64_t B, cudaStream_t st, int drop_layer) {
+  tc::GemmParams p = {};
+  p.M = (int)(B * h->P); p.N = cnn_mma_width(c2.Cout, c2.Coutp);
+  p.kb_per_tap = c2.Cinp / 64; p.tap_center = (c2.taps - 1) / 2;
+  p.a2_from_kb = c2.taps * p.kb_per_tap;
+  p.K = c2.taps * c2.Cinp + cr.Cinp;
+  p.halo_period = h->P;
+  p.act = c2.act; p.head_relu_from = -1;
+  p.bias = h->params + c2.b_off; p.bias2 = h->params + cr.b_off;
+  p.tap_tail_k = cnn_tail_k(c2.Cin, c2.Cinp); p.a2_tail_k = cnn_tail_k(cr.Cin, cr.Cinp);
+  p.out = out_h2.ptr; p.ld_out = out_h2.Cp;
+  p.out2 = out_block.ptr; p.ld_out2 = out_block.Cp;
+  int rc;
+  if (drop_layer >= 0) {
+    p.drop_seed = cnn_drop_seed(h, drop_layer); p.drop_threshold = cnn_drop_threshold(h); p.drop_scale = 1.f / (1.f - h->dropout);
+    rc = launch_tn<256, 6, tc::EPI_BIAS_ACT, 2, tc::VAR_A2 | tc::VAR_ACC2 | tc::VAR_KTRIM | tc::VAR_DROPOUT>(h1.maps.k128, c2.tm_wtc, p, h->sm_count, st, &xin.maps.k128);
+  } else {
+    rc = launch_tn<256, 6, tc::EPI_BIAS_ACT, 2, tc::VAR_A2 | tc::VAR_ACC2 | tc::VAR_KTRIM>(h1.maps.k128, c2.tm_wtc, p, h->sm_count, st, &xin.maps.k128);
+  }
+  if (rc) return rc;
+  h->launches++;
+  return CSB_OK;
+}
+
+// Data gradient with two outputs in ONE launch (bf16, CTA pairs):
+//   G      = [in taps | in2] . Wd                       (in2 = a second A source behind the taps, VAR_A2; nullptr: none)   -> out_plain
+//   masked = bf16(G) * act'(saved) [* ds]                                                                                  -> out_masked
+// For a residual block: in = dz1, in2 = d(block output), Wd = [W1^T flipped | Wr^T] -> G = d(block input) = d(previous block's output),
+// masked = dz2 of the previous block.  Replaces conv^T(dz1) -> T, conv1x1^T(d_out) + T -> G, act_mask(G, h2) -> dz2.
+static int cnn_dgrad_dual(csb_cnn* h, const ConvLayerInfo& li, const CUtensorMap& w, const CnnBuf& in, const CnnBuf* in2, const CnnBuf& saved,
+                          int act, CnnBuf& out_masked, CnnBuf& out_plain, int64_t B, cudaStream_t st, float ds) {
+  tc::GemmParams p = {};
+  p.M = (int)(B * h->P); p.N = cnn_mma_width(li.Cin, li.Cinp);
+  p.kb_per_tap = li.Coutp / 64; p.tap_center = (li.taps - 1) / 2;
+  p.a2_from_kb = li.taps * p.kb_per_tap;
+  p.K = (li.taps + (in2 ? 1 : 0)) * li.Coutp;
+  p.halo_period = h->P;
+  p.act = act; p.head_relu_from = -1; p.dgrad_scale = ds;
+  p.tap_tail_k = cnn_tail_k(li.Cout, li.Coutp); p.a2_tail_k = p.tap_tail_k;
+  p.out = out_masked.ptr; p.ld_out = out_masked.Cp;
+  p.out2 = out_plain.ptr; p.ld_out2 = out_plain.Cp;
+  p.saved = reinterpret_cast<const __nv_bfloat16*>(saved.ptr); p.ld_saved = saved.Cp;
+  int rc;
+  if (in2) rc = launch_tn<256, 6, tc::EPI_DGRAD, 2, tc::VAR_DUAL | tc::VAR_A2 | tc::VAR_KTRIM>(in.maps.k128, w, p, h->sm_count, st, &in2->maps.k128);
+  else rc = launch_tn<256, 6, tc::EPI_DGRAD, 2, tc::VAR_DUAL | tc::VAR_KTRIM>(in.maps.k128, w, p, h->sm_count, st);
   if (rc) return rc;
   h->launches++;
   return CSB_OK;
@@ -271,10 +359,16 @@ static int cnn_forward_body(csb_cnn* h, const float* x, int64_t B, cudaStream_t 
   h->launches++;
   const CnnBuf* xin = &h->x0;
   int rc;
+  const bool merged = h->bf16 && h->merge_fwd && g_use_pairs && h->width_p > 128 && h->layer[1].act != CSB_ACT_ELU && (!drop || fold);
   for (int i = 0; i < h->depth; ++i) {
     const ConvLayerInfo &c1 = h->layer[3 * i], &c2 = h->layer[3 * i + 1], &cr = h->layer[3 * i + 2];
     if ((rc = cnn_conv(h, c1, false, *xin, h->h1[i], 0, nullptr, c1.act, h->params + c1.b_off, B, st, 0.f, fold ? 2 * i : -1))) return rc;
     if (drop && !fold && (rc = cnn_dropout(h, h->h1[i], 2 * i, B, st))) return rc;
+    if (merged && c2.has_wtc) {
+      if ((rc = cnn_conv2_residual(h, c2, cr, h->h1[i], *xin, h->h2[i], h->ob[i], B, st, fold ? 2 * i + 1 : -1))) return rc;
+      xin = &h->ob[i];
+      continue;
+    }
     if ((rc = cnn_conv(h, c2, false, h->h1[i], h->h2[i], 0, nullptr, c2.act, h->params + c2.b_off, B, st, 0.f, fold ? 2 * i + 1 : -1))) return rc;
     if (drop && !fold && (rc = cnn_dropout(h, h->h2[i], 2 * i + 1, B, st))) return rc;
     // out = conv1x1(x_in) + b + relu(conv2)
@@ -334,18 +428,29 @@ static int cnn_backward_chain(csb_cnn* h, int64_t B, cudaStream_t st) {
   const CnnBuf& last_out = D > 0 ? h->ob[D - 1] : h->x0;
   if ((rc = cnn_wgrad(h, co, last_out, h->dze, B, tab, max_len, st))) return rc;
   int g = 0;
+  // Merged launches (bf16, CTA pairs, ReLU-family blocks): every kernel that produces d(block output) also writes dz2 = d_out * relu'(h2)
+  // of that block (two outputs), and d(block input) = conv^T(dz1; W1) + conv1x1^T(d_out; Wr) is ONE GEMM over [dz1 taps | d_out]:
+  // three launches and four passes over a [R, Cp] tensor fewer per block.  CSB_CNN_NO_MERGE=1: the separate launches (A/B aid).
+  const bool merged = h->bf16 && h->merge_bwd && g_use_pairs && D > 0 && h->width_p > 128 && h->layer[1].act != CSB_ACT_ELU;
   // d(block output): no activation after the residual add
-  if ((rc = cnn_conv(h, co, true, h->dze, h->G[g], 0, nullptr, CSB_ACT_NONE, h->zero_bias, B, st))) return rc;
+  if (merged) {
+    if ((rc = cnn_dgrad_dual(h, co, co.tm_wd, h->dze, nullptr, h->h2[D - 1], h->layer[3 * (D - 1) + 1].act, h->Z2, h->G[g], B, st, h->dropout > 0.f ? ds : 0.f))) return rc;
+  } else if ((rc = cnn_conv(h, co, true, h->dze, h->G[g], 0, nullptr, CSB_ACT_NONE, h->zero_bias, B, st))) return rc;
   // ---- residual blocks, last to first.  G[g] holds dL/d(block output).
   for (int i = D - 1; i >= 0; --i) {
     const ConvLayerInfo &c1 = h->layer[3 * i], &c2 = h->layer[3 * i + 1], &cr = h->layer[3 * i + 2];
     const CnnBuf& xin = i > 0 ? h->ob[i - 1] : h->x0;
-    if ((rc = act_mask(h->G[g], h->h2[i], h->Z2, c2.act))) return rc;                                       // dz2 = d_out * relu'(h2)
+    if (!merged && (rc = act_mask(h->G[g], h->h2[i], h->Z2, c2.act))) return rc;                            // dz2 = d_out * relu'(h2)
     if ((rc = cnn_wgrad(h, cr, xin, h->G[g], B, tab, max_len, st))) return rc;                               // residual 1x1: dW = xin^T d_out
     if ((rc = cnn_wgrad(h, c2, h->h1[i], h->Z2, B, tab, max_len, st))) return rc;
     if ((rc = cnn_conv(h, c2, true, h->Z2, h->Z1, 2, &h->h1[i], c1.act, nullptr, B, st, h->dropout > 0.f ? ds : 0.f))) return rc;   // dz1 = conv^T(dz2; W2) * relu'(h1) [* 1/(1-p)]
     if ((rc = cnn_wgrad(h, c1, xin, h->Z1, B, tab, max_len, st))) return rc;
-    if (i > 0) {
+    if (i > 0 && merged && c1.has_wdc) {
+      // d(x_in) = conv^T(dz1; W1) + conv1x1^T(d_out; Wr), and the previous block's dz2 from it
+      if ((rc = cnn_dgrad_dual(h, c1, c1.tm_wdc, h->Z1, &h->G[g], h->h2[i - 1], h->layer[3 * (i - 1) + 1].act, h->Z2, h->G[g ^ 1], B, st,
+                               h->dropout > 0.f ? ds : 0.f))) return rc;
+      g ^= 1;
+    } else if (i > 0) {
       // d(x_in) = conv^T(dz1; W1) + conv1x1^T(d_out; Wr)
       if ((rc = cnn_conv(h, c1, true, h->Z1, h->T, 0, nullptr, CSB_ACT_NONE, h->zero_bias, B, st))) return rc;
       if ((rc = cnn_conv(h, cr, true, h->G[g], h->G[g ^ 1], 1, &h->T, CSB_ACT_NONE, h->zero_bias, B, st))) return rc;
@@ -372,9 +477,12 @@ int csb_cnn_create(const csb_cnn_cfg* cfg, csb_cnn** out) {
   if (rc) return rc;
   CSB_REQUIRE(maj == 10, CSB_ENODEV, "device has compute capability %d.%d; this library is sm_100a only", maj, mnr);
   g_use_pairs = getenv("CSB_NO_PAIRS") == nullptr;
+  g_cnn_ktrim = getenv("CSB_CNN_NO_KTRIM") == nullptr;
 
   csb_cnn* h = new (std::nothrow) csb_cnn();
   CSB_REQUIRE(h != nullptr, CSB_ENOMEM, "host allocation failed");
+  h->merge_bwd = getenv("CSB_CNN_NO_MERGE") == nullptr;
+  h->merge_fwd = getenv("CSB_CNN_MERGE_FWD") != nullptr;
   h->cfg = *cfg;
   h->depth = cfg->depth; h->L = cfg->levels; h->P = cfg->levels + 2;
   h->in_ch = cfg->in_ch; h->in_p = (int)round_up(cfg->in_ch, 64);
@@ -427,14 +535,36 @@ int csb_cnn_create(const csb_cnn_cfg* cfg, csb_cnn** out) {
   CKA(h->d_loss, 4);
   for (int l = 0; l < h->n_layers && h->bf16; ++l) {
     ConvLayerInfo& li = h->layer[l];
-    const size_t n = (size_t)li.taps * li.Cinp * li.Coutp;
-    CKA(li.wt16, n * 2); CKA(li.wd16, n * 2);
+    li.wt_ld = li.taps * li.Cinp; li.wd_ld = li.taps * li.Coutp;
   }
-#undef CKA
+  // residual blocks: the 1x1 layer's transposed copy behind conv1's (both map d(block output) / dz1 -> d(block input)), its forward
+  // copy behind conv2's (both produce the block output)
+  for (int i = 0; i < h->depth && h->bf16; ++i) {
+    ConvLayerInfo &c1 = h->layer[3 * i], &c2 = h->layer[3 * i + 1], &cr = h->layer[3 * i + 2];
+    if (c1.Cinp == cr.Cinp && c1.Coutp == cr.Coutp) {
+      c1.wd_ld = cr.wd_ld = (c1.taps + 1) * c1.Coutp; cr.wd_col0 = c1.taps * c1.Coutp; cr.wd_alias = true; c1.has_wdc = true;
+    }
+    if (c2.Coutp == cr.Coutp) {
+      c2.wt_ld = cr.wt_ld = c2.taps * c2.Cinp + cr.Cinp; cr.wt_col0 = c2.taps * c2.Cinp; cr.wt_alias = true; c2.has_wtc = true;
+    }
+  }
   for (int l = 0; l < h->n_layers && h->bf16; ++l) {
     ConvLayerInfo& li = h->layer[l];
-    rc = make_tmap_bf16(&li.tm_wt, li.wt16, (uint64_t)li.taps * li.Cinp, li.Coutp, (uint64_t)li.taps * li.Cinp, 64, (uint32_t)tn_b_box_rows(li.Coutp));
-    if (!rc) rc = make_tmap_bf16(&li.tm_wd, li.wd16, (uint64_t)li.taps * li.Coutp, li.Cinp, (uint64_t)li.taps * li.Coutp, 64, (uint32_t)tn_b_box_rows(li.Cinp));
+    if (!li.wt_alias) CKA(li.wt16, (size_t)li.Coutp * li.wt_ld * 2);
+    if (!li.wd_alias) CKA(li.wd16, (size_t)li.Cinp * li.wd_ld * 2);
+  }
+#undef CKA
+  for (int i = 0; i < h->depth && h->bf16; ++i) {
+    ConvLayerInfo &c1 = h->layer[3 * i], &c2 = h->layer[3 * i + 1], &cr = h->layer[3 * i + 2];
+    if (cr.wd_alias) cr.wd16 = c1.wd16;
+    if (cr.wt_alias) cr.wt16 = c2.wt16;
+  }
+  for (int l = 0; l < h->n_layers && h->bf16; ++l) {
+    ConvLayerInfo& li = h->layer[l];
+    rc = make_tmap_bf16(&li.tm_wt, li.wt16 + li.wt_col0, (uint64_t)li.taps * li.Cinp, li.Coutp, (uint64_t)li.wt_ld, 64, (uint32_t)tn_b_box_rows(li.Coutp));
+    if (!rc) rc = make_tmap_bf16(&li.tm_wd, li.wd16 + li.wd_col0, (uint64_t)li.taps * li.Coutp, li.Cinp, (uint64_t)li.wd_ld, 64, (uint32_t)tn_b_box_rows(li.Cinp));
+    if (!rc && li.has_wtc) rc = make_tmap_bf16(&li.tm_wtc, li.wt16, (uint64_t)li.wt_ld, li.Coutp, (uint64_t)li.wt_ld, 64, (uint32_t)tn_b_box_rows(li.Coutp));
+    if (!rc && li.has_wdc) rc = make_tmap_bf16(&li.tm_wdc, li.wd16, (uint64_t)li.wd_ld, li.Cinp, (uint64_t)li.wd_ld, 64, (uint32_t)tn_b_box_rows(li.Cinp));
     if (rc) { cnn_free(h); delete h; return rc; }
   }
   // default loss weights: the reference's *_adjusted losses (hpo_train.py:114-121): per-sample sum over (level, channel) of

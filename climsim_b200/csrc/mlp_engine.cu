@@ -90,12 +90,13 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 }
 
 template <int BN, int STAGES, int EPI, int CG, int VAR = 0>
-static int launch_tn(const CUtensorMap& ta, const CUtensorMap& tb, const tc::GemmParams& p, int sm_count, cudaStream_t st) {
+static int launch_tn(const CUtensorMap& ta, const CUtensorMap& tb, const tc::GemmParams& p, int sm_count, cudaStream_t st,
+                     const CUtensorMap* ta2 = nullptr) {
   constexpr bool BF16_OUT = (EPI == tc::EPI_BIAS_ACT || EPI == tc::EPI_HEAD_LOSS || EPI == tc::EPI_DGRAD || EPI == tc::EPI_DGRAD_MASK ||
                              EPI == tc::EPI_BIAS_ADD);
   using L = tc::TnSmem<BN, STAGES, CG, (VAR & tc::VAR_STAGED) != 0 && BF16_OUT>;
   auto kern = tc::gemm_tn_kernel<BN, STAGES, EPI, CG, VAR>;
-  CSB_REQUIRE((EPI == tc::EPI_HEAD_LOSS ? 2 : 1) * (int)round_up(p.N, BN) <= tc::TN_BIAS_SMEM, CSB_EUNSUPPORTED,
+  CSB_REQUIRE((EPI == tc::EPI_HEAD_LOSS || (VAR & tc::VAR_ACC2) ? 2 : 1) * (int)round_up(p.N, BN) <= tc::TN_BIAS_SMEM, CSB_EUNSUPPORTED,
               "layer width %d too large for the %d-float bias / loss-weight area in shared memory", p.N, tc::TN_BIAS_SMEM);
   static bool attr_set = false;
   if (!attr_set) {
@@ -128,7 +129,7 @@ static int launch_tn(const CUtensorMap& ta, const CUtensorMap& tb, const tc::Gem
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  CSB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, q));
+  CSB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, q, ta2 ? *ta2 : ta));
   return CSB_OK;
 }
 

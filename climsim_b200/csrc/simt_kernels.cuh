@@ -1078,7 +1078,9 @@ act_mask_bf16_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* _
 // conv weight repack from the fp32 master W [taps][Cinp][Coutp]:
 //   wt16 [Coutp][taps*Cinp]            (B operand of the forward GEMM:  k = t*Cinp + ci)
 //   wd16 [Cinp][taps*Coutp], flipped   (B operand of the data-gradient GEMM: k = t'*Coutp + co with t' = taps-1-t)
-struct ConvRepack { const float* w; __nv_bfloat16* wt16; __nv_bfloat16* wd16; int taps, Cinp, Coutp; };
+// The copies may sit inside a wider matrix shared with another layer (row pitch *_ld, first column *_col0): the residual 1x1 kernel
+// rides behind the k = 3 kernel of the same block as a fourth "tap" of one merged GEMM (cnn_engine.cuh).
+struct ConvRepack { const float* w; __nv_bfloat16* wt16; __nv_bfloat16* wd16; int taps, Cinp, Coutp; int wt_ld, wt_col0, wd_ld, wd_col0; };
 struct ConvRepackTable { int n; ConvRepack l[48]; };
 __global__ void __launch_bounds__(256) conv_repack_kernel(const ConvRepackTable tab) {
   const ConvRepack L = tab.l[blockIdx.y];
@@ -1088,8 +1090,8 @@ __global__ void __launch_bounds__(256) conv_repack_kernel(const ConvRepackTable 
     const int ci = (int)((i / L.Coutp) % L.Cinp);
     const int t = (int)(i / ((int64_t)L.Coutp * L.Cinp));
     const __nv_bfloat16 v = __float2bfloat16_rn(L.w[i]);
-    L.wt16[(size_t)co * (L.taps * L.Cinp) + (size_t)t * L.Cinp + ci] = v;
-    L.wd16[(size_t)ci * (L.taps * L.Coutp) + (size_t)(L.taps - 1 - t) * L.Coutp + co] = v;
+    L.wt16[(size_t)co * L.wt_ld + L.wt_col0 + (size_t)t * L.Cinp + ci] = v;
+    L.wd16[(size_t)ci * L.wd_ld + L.wd_col0 + (size_t)(L.taps - 1 - t) * L.Coutp + co] = v;
   }
 }
 // flat user blob <-> padded conv parameters: W [taps][Cin][Cout] <-> [taps][Cinp][Coutp], b [Cout] <-> [Coutp]

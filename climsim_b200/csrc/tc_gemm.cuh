@@ -73,6 +73,21 @@ struct GemmParams {
   int ld_out;
   const __nv_bfloat16* saved;  // EPI_DGRAD: saved activation [M, ld_saved]
   int ld_saved;
+  // VAR_A2: contraction blocks kb >= a2_from_kb read their A tiles from the SECOND tensor map (columns (kb - a2_from_kb) * 64, rows
+  // unshifted): d(x_in) = conv^T(dz1; W1) + conv1x1^T(d_out; Wr) as one GEMM over [dz1 taps | d_out] (cnn_engine.cuh)
+  int a2_from_kb;
+  // VAR_DUAL (EPI_DGRAD): the accumulator itself, rounded to bf16, is a second output (`out2`), and the masked result is computed from
+  // that ROUNDED value -- exactly what a separate act' pass over the stored tensor gives
+  void* out2;
+  int ld_out2;
+  // > 0: the last contraction block of every tap holds only tap_tail_k * 16 non-zero channels (406 = 6 * 64 + 22 -> 2): the issuer
+  // skips the MMAs over the all-zero remainder of that block
+  int tap_tail_k;
+  int a2_tail_k;               // the same for the last contraction block of the second A source (0: all four)
+  // VAR_ACC2 (EPI_BIAS_ACT + VAR_A2, BN = 256): the contraction blocks of the second A source accumulate into a SECOND accumulator
+  // (TMEM columns 256..511; one tile in flight instead of two).  out = act(acc1 + bias) [dropout] as usual, and
+  // out2 = (acc2 + bias2) + bf16(out): a residual block's  relu(conv2(h1)) + conv1x1(x_in)  in one launch (cnn_engine.cuh)
+  const float* bias2;
   // EPI_HEAD_LOSS / EPI_HEAD_OUT
   const float* y;              // targets [M, ld_y]
   int ld_y;
@@ -416,10 +431,10 @@ __device__ __forceinline__ uint32_t drop_mix32(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
   return x;
 }
-template <int EPI, bool ELU, bool GENERAL_LOSS, bool STAGED, bool DROPOUT = false>
+template <int EPI, bool ELU, bool GENERAL_LOSS, bool STAGED, bool DROPOUT = false, bool DUAL = false, bool ACC2 = false>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float* sbias, const float* sloss_w, const RowInfo& ri, int gcol,
                                                const uint32_t (&raw)[32], const uint32_t (&sv)[16], const float (&yv)[32], float& loss_acc,
-                                               uint32_t mask_word, uint32_t stage_addr) {
+                                               uint32_t mask_word, uint32_t stage_addr, uint32_t taddr2 = 0) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
@@ -468,6 +483,25 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
       for (int j = 0; j < 32; ++j) v[j] = 0.f;
     }
     if constexpr (STAGED) stage_bf16x32(stage_addr, v); else if (st_ok) store_bf16x32_global(out16, v);
+    if constexpr (ACC2) {
+      // second accumulator (loaded only now: the first one's registers are free again), its bias behind the first bias vector
+      uint32_t raw2[32];
+      tmem_ld_32x32(taddr2, raw2);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));      // the stored value is what gets added
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(sloss_w + gcol + 4 * q);
+        v[4 * q] += __uint_as_float(raw2[4 * q]) + t.x; v[4 * q + 1] += __uint_as_float(raw2[4 * q + 1]) + t.y;
+        v[4 * q + 2] += __uint_as_float(raw2[4 * q + 2]) + t.z; v[4 * q + 3] += __uint_as_float(raw2[4 * q + 3]) + t.w;
+      }
+      if (ri.zero_row) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      if (st_ok) store_bf16x32_global(reinterpret_cast<__nv_bfloat16*>(p.out2) + (size_t)ri.grow * p.ld_out2 + gcol, v);
+    }
   } else if constexpr (EPI == EPI_DGRAD_MASK) {
     // act'(a) through the sign bit: relu -> {1, 0}, leaky relu -> {1, alpha}
     const float neg = p.act == CSB_ACT_LEAKYRELU ? p.alpha : 0.f;
@@ -480,6 +514,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
     }
     if constexpr (STAGED) stage_bf16x32(stage_addr, v); else if (st_ok) store_bf16x32_global(out16, v);
   } else if constexpr (EPI == EPI_DGRAD) {
+    if constexpr (DUAL) {
+      if (ri.zero_row) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      if (st_ok) store_bf16x32_global(reinterpret_cast<__nv_bfloat16*>(p.out2) + (size_t)ri.grow * p.ld_out2 + gcol, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+    }
     float a[32];
     unpack_bf16x32(sv, a);                          // saved activation (same rows / columns as the output)
     act_bwd32<ELU>(p.act, p.alpha, v, a);
@@ -642,7 +685,7 @@ struct TnSmem {
 // both keep rarely used code out of the instruction stream (and the register budget) of the common kernels
 // bit 2 = results staged in shared memory and written with coalesced stores (the launches whose time is the epilogue: K <= 256)
 // bit 3 = in-kernel cycle counters for the micro-benchmark (p.stats); production instantiations carry none of that code
-constexpr int VAR_ELU = 1, VAR_GENERAL_LOSS = 2, VAR_STAGED = 4, VAR_STATS = 8, VAR_DROPOUT = 16;
+constexpr int VAR_ELU = 1, VAR_GENERAL_LOSS = 2, VAR_STAGED = 4, VAR_STATS = 8, VAR_DROPOUT = 16, VAR_A2 = 32, VAR_DUAL = 64, VAR_ACC2 = 128, VAR_KTRIM = 256;
 
 // Tile schedule of the persistent kernel; all three warp roles walk the same sequence.
 //   round-robin (the first design): tile t = (m-group t / n_blocks, n-block t % n_blocks), CTA group g takes t = g, g + G, ...
@@ -698,12 +741,17 @@ struct TileIter {
 };
 template <int BN, int STAGES, int EPI, int CG, int VAR>
 __global__ void __launch_bounds__(TN_THREADS, 1)
-gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p,
+               const __grid_constant__ CUtensorMap tmap_a2) {
   constexpr bool ELU = (VAR & VAR_ELU) != 0, GENERAL_LOSS = (VAR & VAR_GENERAL_LOSS) != 0;
   constexpr bool BF16_OUT = (EPI == EPI_BIAS_ACT || EPI == EPI_HEAD_LOSS || EPI == EPI_DGRAD || EPI == EPI_DGRAD_MASK || EPI == EPI_BIAS_ADD);
   constexpr bool STAGED = (VAR & VAR_STAGED) != 0 && BF16_OUT;
   constexpr bool STATS = (VAR & VAR_STATS) != 0;
   constexpr bool DROPOUT = (VAR & VAR_DROPOUT) != 0 && EPI == EPI_BIAS_ACT;
+  constexpr bool A2 = (VAR & VAR_A2) != 0, DUAL = (VAR & VAR_DUAL) != 0 && EPI == EPI_DGRAD;
+  constexpr bool ACC2 = (VAR & VAR_ACC2) != 0 && EPI == EPI_BIAS_ACT && A2;
+  constexpr bool KTRIM = (VAR & VAR_KTRIM) != 0;       // GemmParams.tap_tail_k / a2_tail_k honoured (the issuer loop of every other kernel stays as it was)
+  static_assert(!ACC2 || BN == 256, "two accumulators per tile: 2 x 256 TMEM columns");
   const bool BALANCED = p.balanced != 0 && EPI != EPI_HEAD_LOSS;      // the loss partials are indexed by the round-robin tile grid
   using L = TnSmem<BN, STAGES, CG, STAGED>;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
@@ -736,6 +784,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == TN_PRODUCER_WARP && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if constexpr (A2) tma_prefetch_desc(&tmap_a2);
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     // the leader's "accumulator drained" barrier collects the epilogue warps of BOTH CTAs
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TN_EPI_WARPS * CG); }
@@ -752,6 +801,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     for (int i = threadIdx.x; i < num_n_blocks * BN; i += TN_THREADS) {
       sbias[i] = (i < p.N) ? __ldg(p.bias + i) : 0.f;
       if constexpr (EPI == EPI_HEAD_LOSS) sbias[num_n_blocks * BN + i] = (i < p.N) ? __ldg(p.loss_w + i) : 0.f;
+      if constexpr (ACC2) sbias[num_n_blocks * BN + i] = (i < p.N) ? __ldg(p.bias2 + i) : 0.f;
     }
   }
   tc_fence_before();
@@ -775,18 +825,22 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t sa = smem_base + s * L::STAGE_BYTES;
           const int tap = p.kb_per_tap ? kb / p.kb_per_tap : 0;
-          const int ka = (kb - tap * p.kb_per_tap) * BK;          // column block inside the (un-replicated) A matrix
-          const int tap_shift = p.kb_per_tap ? tap - p.tap_center : 0;   // may be -1 at the top: TMA zero-fills out-of-range rows
+          int ka = (kb - tap * p.kb_per_tap) * BK;                // column block inside the (un-replicated) A matrix
+          int tap_shift = p.kb_per_tap ? tap - p.tap_center : 0;  // may be -1 at the top: TMA zero-fills out-of-range rows
+          const CUtensorMap* ta = &tmap_a;
+          if constexpr (A2) {
+            if (kb >= p.a2_from_kb) { ta = &tmap_a2; ka = (kb - p.a2_from_kb) * BK; tap_shift = 0; }
+          }
           const bool ld_a = !(p.dbg & (16 | 128)), ld_b = !(p.dbg & (16 | 64));      // both true in production
           const uint32_t tx = (ld_a ? (uint32_t)L::A_BYTES : 0u) + (ld_b ? (uint32_t)(p.b_box_rows * BK * 2) : 0u);
           if constexpr (CG == 2) {
             // one expect_tx on the leader's barrier covers the four loads of the pair
             if (is_leader) mbar_expect_tx(full_bar(s), 2 * tx);
-            if (ld_a) tma_load_2d_2sm(sa, &tmap_a, full_bar(s), ka, m0 + tap_shift);
+            if (ld_a) tma_load_2d_2sm(sa, ta, full_bar(s), ka, m0 + tap_shift);
             if (ld_b) tma_load_2d_2sm(sa + L::A_BYTES, &tmap_b, full_bar(s), kb * BK, nb0);
           } else {
             mbar_expect_tx(full_bar(s), tx);
-            if (ld_a) tma_load_2d(sa, &tmap_a, full_bar(s), ka, m0 + tap_shift);
+            if (ld_a) tma_load_2d(sa, ta, full_bar(s), ka, m0 + tap_shift);
             if (ld_b) tma_load_2d(sa + L::A_BYTES, &tmap_b, full_bar(s), kb * BK, nb0);
           }
           if (++s == STAGES) { s = 0; ph ^= 1u; }
@@ -801,13 +855,20 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (Tiles it(BALANCED, num_m_blocks, p.N, my_group, num_groups); it.next(); ++t) {
         const int n_valid = it.n_valid;
         const uint32_t idesc = make_idesc_bf16(BM * CG, n_valid, 0, 0);
-        const int acc = t & 1;
+        const int acc = ACC2 ? 0 : (t & 1);          // ACC2: one tile in flight (both accumulators belong to it)
+        const uint32_t acc_par = ACC2 ? ((uint32_t)t & 1u) : ((uint32_t)(t >> 1) & 1u);
         long long c0 = (STATS && p.stats) ? clock64() : 0;
-        mbar_wait(tempty_bar(acc), ((uint32_t)(t >> 1) & 1u) ^ 1u);
+        mbar_wait(tempty_bar(acc), acc_par ^ 1u);
         if (STATS && p.stats) st_tempty += clock64() - c0;
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        [[maybe_unused]] int kin = 0;                // position inside the tap (tap_tail_k)
         for (int kb = 0; kb < num_kb; ++kb) {
+          [[maybe_unused]] int nk = BK / UMMA_K;
+          if constexpr (KTRIM) {
+            if (A2 && kb >= p.a2_from_kb) { if (kb == num_kb - 1 && p.a2_tail_k > 0) nk = p.a2_tail_k; }
+            else if (p.tap_tail_k > 0 && ++kin == p.kb_per_tap) { kin = 0; nk = p.tap_tail_k; }
+          }
           c0 = (STATS && p.stats) ? clock64() : 0;
           mbar_wait(full_bar(s), ph);
           if (STATS && p.stats) st_full += clock64() - c0;
@@ -815,12 +876,26 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint32_t sa = smem_base + s * L::STAGE_BYTES;
           const uint64_t da = make_desc_kmajor_sw128(sa);
           const uint64_t db = make_desc_kmajor_sw128(sa + L::A_BYTES);
+          if constexpr (ACC2 || KTRIM) {
+            uint32_t d_cols = tmem_d;
+            int kfirst = kb;                         // 0 in the block that starts an accumulation
+            if constexpr (ACC2) {
+              if (kb >= p.a2_from_kb) { d_cols = tmem_d + (uint32_t)BN; kfirst = kb - p.a2_from_kb; }
+            }
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              if (k >= nk) break;
+              if constexpr (CG == 2) umma_f16_2sm(d_cols, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kfirst | k) != 0));
+              else umma_f16(d_cols, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kfirst | k) != 0));
+            }
+          } else {
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             if (p.dbg & 32) break;
             // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
             if constexpr (CG == 2) umma_f16_2sm(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
             else umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          }
           }
           // smem slot reusable (in both CTAs of a pair) once these MMAs have read it
           if constexpr (CG == 2) umma_commit_2sm(empty_bar(s)); else umma_commit(empty_bar(s));
@@ -843,7 +918,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int mb = it.mg * CG + (int)cta_rank;
       const int m0 = mb * BM, n0 = it.n0;
       const int n_valid = it.n_valid;
-      const int acc = t & 1;
+      const int acc = ACC2 ? 0 : (t & 1);
+      const uint32_t acc_par = ACC2 ? ((uint32_t)t & 1u) : ((uint32_t)(t >> 1) & 1u);
       const RowInfo ri = make_row_info(p, m0 + tile_row);
       const int c0 = cq * QCOLS;                              // tile-relative first column of this warp (warp-uniform)
       // everything that does not depend on the accumulator is requested before waiting for it
@@ -891,7 +967,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       };
       load_targets(c0);
       long long ck0 = (STATS && p.stats) ? clock64() : 0;
-      mbar_wait_long(tfull_bar(acc), (uint32_t)(t >> 1) & 1u);
+      mbar_wait_long(tfull_bar(acc), acc_par);
       long long ck1 = (STATS && p.stats) ? clock64() : 0;
       tc_fence_after();
       float loss_acc = 0.f;
@@ -910,8 +986,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int j = 0; j < 32; ++j) raw[j] = 0u;
           }
           if (!(p.dbg & 2))
-            epilogue_chunk<EPI, ELU, GENERAL_LOSS, STAGED, DROPOUT>(p, sbias, sloss_w, ri, n0 + c, raw, sv[i], yv, loss_acc, mask_words[i],
-                                                           stage_warp + (uint32_t)(lane * L::OUT_PITCH + 64 * i));
+            epilogue_chunk<EPI, ELU, GENERAL_LOSS, STAGED, DROPOUT, DUAL, ACC2>(p, sbias, sloss_w, ri, n0 + c, raw, sv[i], yv, loss_acc, mask_words[i],
+                                                           stage_warp + (uint32_t)(lane * L::OUT_PITCH + 64 * i),
+                                                           taddr + (uint32_t)(BN + 32 * i));
         }
       }
       tc_fence_before();

@@ -303,15 +303,17 @@ class CNNRef:
         ``emulate_bf16``: the storage points of the CSB_BF16 engine (climsim_b200/csrc/cnn_engine.cuh) are marked with
         ``_RoundNode``: forward -- the packed input, relu(conv1), relu(conv2) (again after the dropout scaling), the block output
         ``conv1x1(x_in) + relu(conv2)`` and elu(conv_out) are stored in bf16; backward -- dL/dz of the heads, dze, the block-output
-        gradient G, dz2, dz1 and the conv1-branch gradient T are stored in bf16, while ``conv1x1^T(G) + T`` is summed in fp32 before
-        its one rounding.  Weights enter as bf16 copies (``params`` = ``_emulated_leaves``)."""
+        gradient G, dz2 and dz1 are stored in bf16; d(block input) = ``conv1^T(dz1) + conv1x1^T(G)`` is ONE fp32 accumulation (the
+        engine's merged GEMM over [dz1 taps | G]) with one rounding, and dz2 derives from the ROUNDED G.  (With CSB_CNN_NO_MERGE=1
+        the engine stores the conv1 branch T in bf16 first: one more rounding, inside the test tolerances.)  Weights enter as bf16
+        copies (``params`` = ``_emulated_leaves``)."""
         p = self.params if params is None else params
         e = emulate_bf16
         h = _bf16_round(x.to(self.dtype)) if e else x.to(self.dtype)
         prev = h
         for i in range(self.depth):
             wc1, bc1, wc2, bc2, wr, br = p[6 * i: 6 * i + 6]
-            h = _mark(prev, False, True, e and i > 0)                                 # T = bf16(conv1^T(dz1)); block 0's input needs no gradient
+            h = prev                                                                  # conv1 branch: its gradient joins G's sum unrounded
             h = _mark(torch.relu(conv1d_same_cl(h, wc1, bc1)), True, True, e)         # h1 bf16; dz1 = bf16(conv2^T(dz2) * relu'(h1))
             if masks is not None:
                 h = _mark(h * masks[i][0], True, True, e)

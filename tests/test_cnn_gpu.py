@@ -183,6 +183,40 @@ def test_cnn_train_step_against_the_bf16_emulating_oracle(depth, width, B, loss)
     print(f"cnn depth {depth} width {width} B {B} {loss}: worst gradient rel-L2 vs emulating oracle {worst:.2e}")
 
 
+def test_cnn_merged_launches_against_the_separate_ones(monkeypatch):
+    """The launch merging of cnn_engine.cuh, A/B inside one process (the switches are read when a handle is created):
+    * the second A source + two-accumulator forward launch (conv2 and the residual 1x1 as one GEMM, CSB_CNN_MERGE_FWD=1, opt-in) and
+      the skipped all-zero MMAs of the last 64-channel block (406 = 6 * 64 + 22; CSB_CNN_NO_KTRIM=1 off) change NO bit of the
+      predictions or the loss;
+    * the merged backward launch (d(block input) over [dz1 taps | d_out] with the previous block's dz2 as second output; default,
+      CSB_CNN_NO_MERGE=1 off) differs from the separate launches only by the rounding of the conv1-branch gradient that it no longer
+      stores: every gradient tensor within 1e-2 relative L2, and three launches fewer per block."""
+    depth, width, B = 3, 406, 40
+    runs = {}
+    for name, env in (("default", {}), ("separate", {"CSB_CNN_NO_MERGE": "1", "CSB_CNN_NO_KTRIM": "1"}), ("fwd", {"CSB_CNN_MERGE_FWD": "1"})):
+        for k in ("CSB_CNN_NO_MERGE", "CSB_CNN_NO_KTRIM", "CSB_CNN_MERGE_FWD"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ref, eng, x, y = _setup(depth, width, B, "mse")
+        pred = eng.forward(x.cuda()).cpu().numpy()
+        n0 = eng.launch_count
+        loss = eng.train_step(x.cuda(), y.cuda()).item()
+        runs[name] = (pred, loss, eng.split_flat(eng.get_grads_flat()), eng.launch_count - n0)
+        eng.close()
+    for name in ("separate", "fwd"):
+        np.testing.assert_array_equal(runs["default"][0], runs[name][0], err_msg=name)
+        assert runs["default"][1] == runs[name][1], name
+    # backward: merged (default, fwd) against separate
+    for i, (a, b) in enumerate(zip(runs["default"][2], runs["separate"][2])):
+        nb = np.linalg.norm(b)
+        assert nb == 0 or np.linalg.norm(a - b) / nb <= 1e-2, (i, np.linalg.norm(a - b) / nb)
+    for a, b in zip(runs["default"][2], runs["fwd"][2]):
+        np.testing.assert_array_equal(a, b)
+    assert runs["default"][3] == runs["separate"][3] - (2 * depth - 1)       # separate: act_mask per block, T + residual add for blocks > 0, the first d(output); merged: one launch per block
+    assert runs["fwd"][3] == runs["default"][3] - depth
+
+
 @pytest.mark.parametrize("dtype,tol", [("fp32", 3e-5), ("bf16", 2e-2)])
 def test_cnn_module_autograd(dtype, tol):
     """baseline_models.CNN as an ordinary torch module: forward records an autograd node whose backward is csb_cnn_backward, so a
