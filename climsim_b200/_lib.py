@@ -21,6 +21,7 @@ OPT = {"adam_keras": 0, "adam": 0, "adam_torch": 1, "sgd": 2, "radam": 3, "rmspr
 FWD_NORMALIZE_IN, FWD_DENORM_OUT, FWD_KEEP_ACTIVATIONS, TRAIN_FUSED_OPT = 1, 2, 4, 8
 BATCH_METRICS_SCRATCH = 2048
 HSR_NO_OPT = 16
+FWD_TRAINING = 32
 IPC_HANDLE_BYTES = 64
 
 
@@ -64,6 +65,8 @@ SIGNATURES = {
     "csb_mlp_set_norm": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
     "csb_mlp_set_input_transform": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
     "csb_mlp_set_output_mask": (C.c_int, [_VP, _VP]),
+    "csb_mlp_set_dropout": (C.c_int, [_VP, C.c_float, C.c_uint32]),
+    "csb_mlp_debug_dropout_mask": (C.c_int, [_VP, C.c_int, _VP, C.c_int64, _VP]),
     "csb_mlp_forward": (C.c_int, [_VP, _VP, _VP, C.c_int64, C.c_uint32, _VP]),
     "csb_mlp_forward_host": (C.c_int, [_VP, _VP, _VP, C.c_int64, C.c_uint32, _VP]),
     "csb_mlp_backward": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP]),

@@ -26,7 +26,7 @@ class _EngineFunction(torch.autograd.Function):
         eng = module.engine
         module._sync_params()
         ctx.module, ctx.need_dx = module, x.requires_grad
-        return eng.forward(x, keep_activations=True)
+        return eng.forward(x, keep_activations=True, training=module.training)      # module.train(): the Dropout layers are active
 
     @staticmethod
     def backward(ctx, dy):
@@ -112,14 +112,18 @@ class ED(_EngineModule):
 
 
 class HSRMLP(_EngineModule):
-    """``MLP`` of baseline_models/HSR/training/hsr.py:14-35: layers x [Linear -> LayerNorm -> Dropout(0) -> ReLU] -> Linear."""
+    """``MLP`` of baseline_models/HSR/training/hsr.py:14-35: layers x [Linear -> LayerNorm -> Dropout(p) -> ReLU] -> Linear.
+    ``dropout`` > 0 is active in training (``module.train()`` forwards that record a graph, and ``HSR.trainer``'s steps) with the
+    engine's own counter-based masks (torch's random stream is not reproduced); the shipped configuration uses p = 0
+    (hpo.py:225-238)."""
 
     def __init__(self, in_dims: int = 124, out_dims: int = 128, hidden_dims: int = 512, layers: int = 1, dropout: float = 0.0,
                  dtype: str = "bf16", max_batch: int = 16384, seed: int = 0):
-        assert dropout == 0, "dropout > 0 needs the reference's torch RNG stream; the shipped configuration uses p = 0 (hpo.py:225-238)"
         spec = [(hidden_dims, "relu", 0.0)] * layers + [(out_dims, "none", 0.0)]
         self.n_hidden = layers
         super().__init__(MLPEngine(in_dims, spec, dtype=dtype, max_batch=max_batch, layernorm=[True] * layers + [False]), seed)
+        if dropout > 0:
+            self.engine.set_dropout(dropout, seed)
 
     def load_reference_state_dict(self, sd, prefix: str = "") -> None:
         """Keys of the reference module: ``linear{i}.0.weight`` (out,in), ``linear{i}.0.bias``, ``linear{i}.1.weight`` (gamma),
@@ -239,11 +243,11 @@ class HSR(torch.nn.Module):
 class OnlineMLP(_EngineModule):
     """The online-testing MLP (online_testing/baseline_models/MLP_v2rh/training/mlp.py:24-68): ``layers`` x [Linear -> ReLU] ->
     Linear, optional ``output_prune`` (zero the top ``strato_lev_out`` levels of the q1, q2, q3 and u tendencies), ReLU on the last
-    eight outputs.  Same constructor arguments as the reference class (``dropout`` must be 0)."""
+    eight outputs.  Same constructor arguments as the reference class (``dropout`` > 0: active in training forwards, with the
+    engine's own counter-based masks)."""
 
     def __init__(self, in_dims: int = 557, out_dims: int = 368, hidden_dims=(384, 1024, 640), layers: int = 3, dropout: float = 0.0,
                  output_prune: bool = False, strato_lev_out: int = 15, dtype: str = "bf16", max_batch: int = 16384, seed: int = 0):
-        assert dropout == 0, "dropout > 0 is not reproducible across frameworks; the online configs use 0"
         if isinstance(hidden_dims, (list, tuple)):
             assert len(hidden_dims) == layers, "Length of hidden_dims should be equal to layers"
             hidden = list(hidden_dims)
@@ -252,6 +256,8 @@ class OnlineMLP(_EngineModule):
         spec = [(h, "relu", 0.0) for h in hidden] + [(out_dims, "none", 0.0)]
         super().__init__(MLPEngine(in_dims, spec, head_relu_from=out_dims - 8, dtype=dtype, max_batch=max_batch), seed)
         self.output_prune, self.strato_lev_out = output_prune, strato_lev_out
+        if dropout > 0:
+            self.engine.set_dropout(dropout, seed)
         self._apply_own_config()
 
     def _own_mask(self) -> Optional[np.ndarray]:

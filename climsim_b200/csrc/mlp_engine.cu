@@ -347,6 +347,13 @@ struct csb_mlp {
   CUtensorMap tm_z[CSB_MAX_LAYERS];         // LayerNorm layers: pre-norm z buffer (TMA-store target of the forward GEMM)
 
   int64_t step = 0, launches = 0;
+  // Dropout behind every hidden layer's activation (hsr.py:20-25, online mlp.py:41-45: Linear -> [LayerNorm] -> Dropout -> ReLU, and
+  // relu(dropout(u)) == dropout(relu(u))): training forwards only, counter-based keep decisions keyed by (seed, training forward, layer,
+  // element) -- no mask is stored, the backward pass recognises a dropped element by its saved output being exactly 0
+  float dropout = 0.f;
+  uint32_t drop_seed = 0;
+  int64_t drop_fwd = 0;                     // training forwards so far (advances the masks)
+  bool drop_live = false;                   // the activations in the handle come from a forward that dropped
   struct GraphEntry { const float* x; const float* y; int64_t B; float gs; uint32_t flags; float* loss_out; int64_t maps_B;
                       cudaGraphExec_t exec; int64_t n_launches; uint64_t use; };
   std::vector<GraphEntry> graphs;           // cached CUDA graphs of the training step (LRU, 8 entries)
@@ -832,6 +839,33 @@ int csb_mlp_set_input_transform(csb_mlp* h, const float* exp_lambda, const float
   return CSB_OK;
 }
 
+static inline uint32_t mlp_drop_seed(const csb_mlp* h, int layer) {
+  return h->drop_seed ^ (uint32_t)((uint64_t)h->drop_fwd * 0x9E3779B97F4A7C15ull >> 32) ^ (uint32_t)(layer + 1) * 0x85EBCA77u;
+}
+static inline uint32_t mlp_drop_threshold(const csb_mlp* h) { return (uint32_t)lrintf(h->dropout * 16777216.f); }   // keep iff 24 random bits >= p * 2^24
+
+int csb_mlp_set_dropout(csb_mlp* h, float rate, uint32_t seed) {
+  CSB_REQUIRE(h, CSB_EINVAL, "null handle");
+  CSB_REQUIRE(rate >= 0.f && rate < 1.f, CSB_EINVAL, "dropout rate %g outside [0, 1)", (double)rate);
+  for (int l = 0; l + 1 < h->L && rate > 0.f; ++l)
+    CSB_REQUIRE(h->layer[l].act == CSB_ACT_RELU || h->layer[l].act == CSB_ACT_LEAKYRELU || h->layer[l].act == CSB_ACT_NONE, CSB_EUNSUPPORTED,
+                "dropout needs hidden activations whose derivative follows from the sign of the stored output (ReLU, LeakyReLU, linear)");
+  h->dropout = rate; h->drop_seed = seed; h->drop_fwd = 0; h->drop_live = false;
+  return CSB_OK;
+}
+
+int csb_mlp_debug_dropout_mask(csb_mlp* h, int layer, float* dst_dev, int64_t B, void* stream) {
+  CSB_REQUIRE(h && dst_dev, CSB_EINVAL, "null argument");
+  CSB_REQUIRE(layer >= 0 && layer + 1 < h->L && B >= 1 && B <= h->cfg.max_batch, CSB_EINVAL, "bad layer / batch");
+  CSB_REQUIRE(h->dropout > 0.f && h->drop_fwd > 0, CSB_ESTATE, "no training forward with dropout has run on this handle");
+  const LayerInfo& li = h->layer[layer];
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  simt::dropout_mask_kernel<<<grid_for(B * li.Np / 8, 256, h->sm_count), 256, 0, st>>>(dst_dev, B, li.N, li.Np, mlp_drop_seed(h, layer), mlp_drop_threshold(h),
+                                                                                     1.f / (1.f - h->dropout));
+  CSB_CUDA_CHECK(cudaGetLastError());
+  return CSB_OK;
+}
+
 int csb_mlp_set_output_mask(csb_mlp* h, const float* mask_host) {
   CSB_REQUIRE(h, CSB_EINVAL, "null handle");
   CSB_CUDA_CHECK(cudaDeviceSynchronize());
@@ -882,7 +916,10 @@ static int run_normalize(csb_mlp* h, const float* x, int64_t B, int apply, cudaS
   return CSB_OK;
 }
 
-static int run_hidden_forward(csb_mlp* h, int64_t B, cudaStream_t st) {
+static int run_hidden_forward(csb_mlp* h, int64_t B, cudaStream_t st, bool training = false) {
+  const bool drop = training && h->dropout > 0.f;
+  if (drop) h->drop_fwd++;
+  h->drop_live = drop;
   for (int l = 0; l + 1 < h->L; ++l) {
     const LayerInfo& li = h->layer[l];
     // LayerNorm layers: the GEMM writes z = hW + b (no activation) to zbuf; ln_fwd_kernel then produces act(LN(z))
@@ -919,6 +956,15 @@ static int run_hidden_forward(csb_mlp* h, int64_t B, cudaStream_t st) {
       else
         simt::ln_fwd_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(h->zbuf[l]), reinterpret_cast<float*>(h->act[l]),
                                                          li.Np, gamma, gamma + li.Np, h->ln_stats[l], B, li.N, li.Np, li.act, li.alpha, 1e-5f);
+      CSB_CUDA_CHECK(cudaGetLastError());
+      prof_mark(h, K_MISC, st);
+    }
+    if (drop) {
+      // inverted dropout in place on the stored activation (padding columns are zero and stay zero)
+      const int64_t n8 = B * li.Np / 8;
+      const float scale = 1.f / (1.f - h->dropout);
+      if (h->bf16) simt::dropout_bf16_kernel<<<grid_for(n8, 256, h->sm_count), 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(h->act[l]), n8, mlp_drop_seed(h, l), mlp_drop_threshold(h), scale);
+      else simt::dropout_f32_kernel<<<grid_for(n8, 256, h->sm_count), 256, 0, st>>>(reinterpret_cast<float*>(h->act[l]), n8, mlp_drop_seed(h, l), mlp_drop_threshold(h), scale);
       CSB_CUDA_CHECK(cudaGetLastError());
       prof_mark(h, K_MISC, st);
     }
@@ -969,7 +1015,7 @@ static int run_head(csb_mlp* h, int64_t B, int fused_loss, const float* y, float
 // The fused tail (tail_kernel.cuh) covers an output layer of exactly 128 x 128 padded columns behind a ReLU / LeakyReLU layer whose
 // sign mask exists, MSE without an output mask on a non-ELU head: MLP_v1.  Everything else keeps the three separate launches.
 static inline bool tail_fusable(const csb_mlp* h) {
-  if (!h->bf16 || !g_use_tail || h->L < 2) return false;
+  if (!h->bf16 || !g_use_tail || h->L < 2 || h->dropout > 0.f) return false;      // (the tail's data gradient reads the sign mask, which knows nothing of dropped elements)
   const LayerInfo& li = h->layer[h->L - 1];
   return li.Kp == 128 && li.Np == 128 && !li.ln && h->amask[h->L - 2] != nullptr && h->cfg.loss == CSB_LOSS_MSE && !h->has_mask &&
          li.act != CSB_ACT_ELU && h->out_dim % 4 == 0;
@@ -1012,7 +1058,7 @@ int csb_mlp_forward(csb_mlp* h, const float* x, float* y_pred, int64_t B, uint32
   if ((rc = build_act_maps(h, B))) return rc;
   prof_mark(h, K_BEGIN, st);
   if ((rc = run_normalize(h, x, B, (flags & CSB_FWD_NORMALIZE_IN) ? 1 : 0, st))) return rc;
-  if ((rc = run_hidden_forward(h, B, st))) return rc;
+  if ((rc = run_hidden_forward(h, B, st, (flags & CSB_FWD_TRAINING) != 0))) return rc;
   if ((rc = run_head(h, B, 0, nullptr, 0.f, st))) return rc;
   const int grid = grid_for(B * h->out_dim, 256, h->sm_count);
   simt::scale_copy_kernel<<<grid, 256, 0, st>>>(h->pred, h->out_p, (flags & CSB_FWD_DENORM_OUT) ? h->d_inv_out_scale : nullptr,
@@ -1193,8 +1239,9 @@ static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st,
         p.M = (int)B; p.N = li.Kp; p.K = li.Np; p.act = lp.act; p.alpha = lp.alpha; p.head_relu_from = -1;
         p.out = dz16(h, l - 1); p.ld_out = lp.Np;
         p.saved = reinterpret_cast<const __nv_bfloat16*>(h->act[l - 1]); p.ld_saved = lp.Np;
+        p.dgrad_scale = h->drop_live ? 1.f / (1.f - h->dropout) : 0.f;
         int rc;
-        if (h->amask[l - 1] != nullptr) {        // ReLU-family layer: act' from the forward pass's sign bits (no activation re-read)
+        if (h->amask[l - 1] != nullptr && !h->drop_live) {        // ReLU-family layer: act' from the forward pass's sign bits (no activation re-read)
           p.mask_in = h->amask[l - 1]; p.ld_mask = (int)h->cap;
           rc = launch_tn_auto<tc::EPI_DGRAD_MASK>(h->tm_dz[l].a_k128, h->tm_w[l], p, h->sm_count, st, &h->tm_w_s[l]);
         } else {
@@ -1209,6 +1256,7 @@ static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st,
         p.C = dz32(h, l - 1); p.ldc = lp.Np;
         p.act = lp.act; p.alpha = lp.alpha; p.head_relu_from = -1;
         p.saved = reinterpret_cast<const float*>(h->act[l - 1]); p.ld_saved = lp.Np;
+        p.dgrad_scale = h->drop_live ? 1.f / (1.f - h->dropout) : 0.f;
         dim3 grid((unsigned)(li.Kp / 64), (unsigned)ceil_div(B, 64));
         simt::sgemm_kernel<false, true, simt::SEPI_DGRAD><<<grid, 256, 0, st>>>(p);
         CSB_CUDA_CHECK(cudaGetLastError());
@@ -1257,7 +1305,7 @@ static int train_step_body(csb_mlp* h, const float* x, const float* y, int64_t B
   int rc;
   prof_mark(h, K_BEGIN, st);
   if ((rc = run_normalize(h, x, B, (flags & CSB_FWD_NORMALIZE_IN) ? 1 : 0, st))) return rc;
-  if ((rc = run_hidden_forward(h, B, st))) return rc;
+  if ((rc = run_hidden_forward(h, B, st, true))) return rc;
   int n_partials;
   const int l = h->L - 1;
   const bool tail = tail_fusable(h);
@@ -1299,7 +1347,8 @@ int csb_mlp_train_step(csb_mlp* h, const float* x, const float* y, int64_t B, fl
   if ((rc = build_act_maps(h, B))) return rc;
   if ((rc = flush_pending(h, st))) return rc;          // a deferred reduction nobody consumed (no csb_mlp_apply_opt in between)
   float* lo = loss_out ? loss_out : h->d_loss;
-  if (!h->graphs_on || h->prof_on) return train_step_body(h, x, y, B, grad_scale, flags, lo, st);
+  // (dropout: the per-step seeds are launch arguments, so those steps are not replayed from a captured graph)
+  if (!h->graphs_on || h->prof_on || h->dropout > 0.f) return train_step_body(h, x, y, B, grad_scale, flags, lo, st);
 
   h->graph_clock++;
   for (auto& g : h->graphs) {
@@ -1764,7 +1813,7 @@ static int mlp_forward_keep(csb_mlp* h, const float* x, int64_t B, uint32_t flag
   if ((rc = flush_pending(h, st))) return rc;
   prof_mark(h, K_BEGIN, st);
   if ((rc = run_normalize(h, x, B, (flags & CSB_FWD_NORMALIZE_IN) ? 1 : 0, st))) return rc;
-  if ((rc = run_hidden_forward(h, B, st))) return rc;
+  if ((rc = run_hidden_forward(h, B, st, true))) return rc;
   if ((rc = run_head(h, B, 0, nullptr, 0.f, st))) return rc;
   h->acts_B = B;
   h->acts_normalized = (flags & CSB_FWD_NORMALIZE_IN) != 0;

@@ -190,6 +190,8 @@ struct SgemmParams {
   const float* bias;          // SEPI_BIAS_ACT
   int act; float alpha; int head_relu_from;
   const float* saved; int ld_saved;   // SEPI_DGRAD (act' of the saved activation) / SEPI_BIAS_ADD (tile to add)
+  float dgrad_scale;                  // SEPI_DGRAD, != 0: a dropout layer sits behind the activation -- zero where the saved output is
+                                      // exactly 0 (dropped), the kept elements' gradient times 1 / (1 - p)
   // Conv1D('same') over the halo-padded channels-last layout (see cnn_engine.cuh):
   int a_tap_k;       // !TA: contraction index k = t*a_tap_k + c reads A row (m + t - tap_center), column c.   0 = plain GEMM
   int tap_center;
@@ -284,6 +286,10 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmParams p) {
       v[1] *= act_bwd_from_out(p.act, p.alpha, a.y);
       v[2] *= act_bwd_from_out(p.act, p.alpha, a.z);
       v[3] *= act_bwd_from_out(p.act, p.alpha, a.w);
+      if (p.dgrad_scale != 0.f) {
+        v[0] = a.x == 0.f ? 0.f : v[0] * p.dgrad_scale; v[1] = a.y == 0.f ? 0.f : v[1] * p.dgrad_scale;
+        v[2] = a.z == 0.f ? 0.f : v[2] * p.dgrad_scale; v[3] = a.w == 0.f ? 0.f : v[3] * p.dgrad_scale;
+      }
     } else if constexpr (EPI == SEPI_BIAS_ADD) {
       const float4 a = *reinterpret_cast<const float4*>(p.saved + (size_t)r * p.ld_saved + c);
       v[0] += p.bias[c] + a.x; v[1] += p.bias[c + 1] + a.y; v[2] += p.bias[c + 2] + a.z; v[3] += p.bias[c + 3] + a.w;
@@ -1046,6 +1052,39 @@ dropout_bf16_kernel(__nv_bfloat16* __restrict__ a, int64_t n8, uint32_t seed, ui
       o[j] = pack_bf16x2(lo, hi);
     }
     reinterpret_cast<uint4*>(a)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// the same keep decisions on an fp32 buffer (element e belongs to group e / 8, LCG step e % 8), so that the CSB_F32 and CSB_BF16 engines
+// drop the same elements for the same (seed, step, layer)
+__global__ void __launch_bounds__(256)
+dropout_f32_kernel(float* __restrict__ a, int64_t n8, uint32_t seed, uint32_t keep_threshold, float scale) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v0 = reinterpret_cast<const float4*>(a)[2 * i], v1 = reinterpret_cast<const float4*>(a)[2 * i + 1];
+    float e[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    uint32_t st = mix32(seed ^ mix32((uint32_t)i) ^ (uint32_t)(i >> 32) * 0x9E3779B1u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      st = st * 747796405u + 2891336453u;
+      e[j] = (st >> 8) >= keep_threshold ? e[j] * scale : 0.f;
+    }
+    reinterpret_cast<float4*>(a)[2 * i] = make_float4(e[0], e[1], e[2], e[3]);
+    reinterpret_cast<float4*>(a)[2 * i + 1] = make_float4(e[4], e[5], e[6], e[7]);
+  }
+}
+// test hook: the multipliers (0 or scale) those decisions amount to, for the first `n` of `ld` columns of every row -> dst [rows, n]
+__global__ void __launch_bounds__(256)
+dropout_mask_kernel(float* __restrict__ dst, int64_t rows, int n, int ld, uint32_t seed, uint32_t keep_threshold, float scale) {
+  const int64_t n8 = rows * ld / 8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t st = mix32(seed ^ mix32((uint32_t)i) ^ (uint32_t)(i >> 32) * 0x9E3779B1u);
+    const int64_t e0 = 8 * i, r = e0 / ld;
+    const int c0 = (int)(e0 - r * ld);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      st = st * 747796405u + 2891336453u;
+      if (c0 + j < n) dst[r * n + c0 + j] = (st >> 8) >= keep_threshold ? scale : 0.f;
+    }
   }
 }
 

@@ -526,9 +526,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
     float a[32];
     unpack_bf16x32(sv, a);                          // saved activation (same rows / columns as the output)
     act_bwd32<ELU>(p.act, p.alpha, v, a);
-    if (p.dgrad_scale != 0.f) {                     // kernel-uniform
+    if (p.dgrad_scale != 0.f) {
+      // kernel-uniform: a dropout layer sits behind the activation -- a dropped element's saved output is exactly 0 (also where
+      // relu'(0) = 0 already did it); the kept ones carry 1 / (1 - p)
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] *= p.dgrad_scale;
+      for (int j = 0; j < 32; ++j) v[j] = a[j] == 0.f ? 0.f : v[j] * p.dgrad_scale;
     }
     if (ri.zero_row) {
 #pragma unroll

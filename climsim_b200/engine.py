@@ -183,21 +183,34 @@ class MLPEngine:
         assert m.size == self.out_dim
         _lib.check(self.lib.csb_mlp_set_output_mask(self._h, m.ctypes.data), "csb_mlp_set_output_mask")
 
+    def set_dropout(self, rate: float, seed: int = 0) -> None:
+        """``torch.nn.Dropout(rate)`` behind every hidden layer (hsr.py:20-25, online mlp.py:41-45), active in training forwards
+        only (``train_step``, ``hsr_train_step``, ``forward(training=True)``); 0 switches it off."""
+        _lib.check(self.lib.csb_mlp_set_dropout(self._h, float(rate), int(seed) & 0xFFFFFFFF), "csb_mlp_set_dropout")
+        self.dropout = float(rate)
+
+    def dropout_mask(self, layer: int, B: int) -> torch.Tensor:
+        """Test hook: the multipliers (0 or 1/(1-p)) the LAST training forward applied behind hidden layer ``layer``, (B, units)."""
+        m = torch.empty(B, self.layer_dims[layer][1], dtype=torch.float32, device="cuda")
+        _lib.check(self.lib.csb_mlp_debug_dropout_mask(self._h, int(layer), m.data_ptr(), B, _lib.current_stream_ptr()),
+                   "csb_mlp_debug_dropout_mask")
+        return m
+
     # -- compute ------------------------------------------------------------------------------------------------
     @staticmethod
-    def _flags(normalize_in: bool, denorm_out: bool, keep: bool) -> int:
+    def _flags(normalize_in: bool, denorm_out: bool, keep: bool, training: bool = False) -> int:
         return (_lib.FWD_NORMALIZE_IN if normalize_in else 0) | (_lib.FWD_DENORM_OUT if denorm_out else 0) | \
-               (_lib.FWD_KEEP_ACTIVATIONS if keep else 0)
+               (_lib.FWD_KEEP_ACTIVATIONS if keep else 0) | (_lib.FWD_TRAINING if training else 0)
 
     def forward(self, x: torch.Tensor, normalize_in: bool = False, denorm_out: bool = False,
-                keep_activations: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                keep_activations: bool = False, out: Optional[torch.Tensor] = None, training: bool = False) -> torch.Tensor:
         x = _f32_cuda(x, "x")
         B = x.shape[0]
         y = out if out is not None else torch.empty(B, self.out_dim, dtype=torch.float32, device=x.device)
         if B == 0:
             return y
         _lib.check(self.lib.csb_mlp_forward(self._h, x.data_ptr(), y.data_ptr(), B,
-                                            self._flags(normalize_in, denorm_out, keep_activations),
+                                            self._flags(normalize_in, denorm_out, keep_activations, training),
                                             _lib.current_stream_ptr()), "csb_mlp_forward")
         return y
 

@@ -76,7 +76,10 @@ enum {
    * refreshes the bf16 weight copies and still fills the gradient buffer.  Results are bit-identical to the unfused path.
    * Not for data-parallel callers (they all-reduce the gradient buffer between the two calls).  If something else reads the
    * gradients first (csb_mlp_get_grads*, another train step) the engine reduces them on demand. */
-  CSB_TRAIN_FUSED_OPT = 8
+  CSB_TRAIN_FUSED_OPT = 8,
+  /* csb_mlp_forward: this is the forward of a training step (module.train() in the reference's PyTorch models): the Dropout layers
+   * set with csb_mlp_set_dropout are active.  Combine with CSB_FWD_KEEP_ACTIVATIONS when csb_mlp_backward follows. */
+  CSB_FWD_TRAINING = 32
 };
 
 /* ---- MLP family ----------------------------------------------------------------------------------------- */
@@ -136,6 +139,16 @@ int  csb_mlp_set_input_transform(csb_mlp* h, const float* exp_lambda, const floa
 /* Per-output-column 0/1 mask applied to the predictions (and therefore to their gradients): the online MLP's `output_prune`
  * zeroing of the stratospheric levels (online_testing/baseline_models/MLP_v2rh/training/mlp.py:56-61).  NULL removes the mask. */
 int  csb_mlp_set_output_mask(csb_mlp* h, const float* mask_host);
+
+/* torch.nn.Dropout(p) behind every hidden layer (baseline_models/HSR/training/hsr.py:20-25: Linear -> LayerNorm -> Dropout -> ReLU;
+ * online_testing/baseline_models/MLP_v2rh/training/mlp.py:41-45: Linear -> Dropout -> ReLU; relu(dropout(u)) == dropout(relu(u))).
+ * Active in training forwards only: csb_mlp_train_step*, csb_hsr_train_step, csb_mlp_forward with CSB_FWD_TRAINING.  Inverted dropout
+ * with counter-based keep decisions keyed by (seed, training forward, layer, element): no mask is stored, and both arithmetic modes drop
+ * the same elements.  PyTorch's random stream is not reproduced (parity is checked with the engine's own masks replayed in the oracle:
+ * csb_mlp_debug_dropout_mask writes the multipliers, 0 or 1/(1-p), of the LAST training forward as fp32 [B, units[layer]] on the device).
+ * Hidden activations must be ReLU / LeakyReLU / none.  rate 0 switches it off.  Training steps with dropout are not graph-replayed. */
+int  csb_mlp_set_dropout(csb_mlp* h, float rate, uint32_t seed);
+int  csb_mlp_debug_dropout_mask(csb_mlp* h, int layer, float* dst_dev, int64_t B, void* stream);
 
 /* model.predict / module.forward: x (B,in_dim) -> y_pred (B,out_dim).  step3_inference.ipynb cell 2; hsr.py:28-35 */
 int  csb_mlp_forward(csb_mlp* h, const float* x, float* y_pred, int64_t B, uint32_t flags, void* stream);

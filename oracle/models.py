@@ -123,9 +123,11 @@ class MLPRef:
                 b.copy_((torch.rand(b.shape, generator=gen, dtype=torch.float64) * 2 - 1).to(self.dtype) * scale)
 
     # -- graph -------------------------------------------------------------------------------------------------
-    def forward(self, x: torch.Tensor, emulate_bf16: bool = False, return_hidden: bool = False):
+    def forward(self, x: torch.Tensor, emulate_bf16: bool = False, return_hidden: bool = False, masks=None):
         """``emulate_bf16`` rounds the GEMM operands (weights, layer inputs) to bf16 but accumulates in fp32 --
-        the numerics of the tensor-core path -- so that the bf16 CUDA mode can be checked tightly."""
+        the numerics of the tensor-core path -- so that the bf16 CUDA mode can be checked tightly.
+        ``masks``: optional list (one (B, units) multiplier per hidden layer) standing for a Dropout layer behind every activation
+        (0 or 1/(1-p): the engine's own keep decisions replayed, csb_mlp_debug_dropout_mask)."""
         rnd = _bf16_round if emulate_bf16 else (lambda t: t)
         p = self.params
         n_hidden = len(self.units) + 1                       # hidden layers + the Dense(128) "upper output" layer
@@ -133,6 +135,8 @@ class MLPRef:
         hidden = []
         for i in range(n_hidden):
             h = rnd(activation(self.act, h @ rnd(p[2 * i]) + p[2 * i + 1], self.alpha))
+            if masks is not None:
+                h = rnd(h * masks[i].to(self.dtype))
             hidden.append(h)
         w_lin, b_lin, w_relu, b_relu = p[2 * n_hidden: 2 * n_hidden + 4]
         out = torch.cat([h @ rnd(w_lin) + b_lin, torch.relu(h @ rnd(w_relu) + b_relu)], dim=1)
@@ -359,9 +363,12 @@ class HSRMLPRef(torch.nn.Module):
                 torch.nn.Dropout(p=dropout)))
         self.final_linear = torch.nn.Linear(hidden_dims, out_dims)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, masks=None) -> torch.Tensor:
+        """``masks``: optional explicit Dropout multipliers (one (B, hidden) tensor per block, 0 or 1/(1-p)) in place of the
+        module's own random ``Dropout`` -- the engine's keep decisions replayed (hsr.py:20-25: Linear -> LayerNorm -> Dropout -> ReLU)."""
         for i in range(self.n_layers):
-            x = torch.relu(getattr(self, "linear%d" % i)(x))
+            seq = getattr(self, "linear%d" % i)
+            x = torch.relu(seq(x) if masks is None else seq[1](seq[0](x)) * masks[i])
         return self.final_linear(x)
 
 

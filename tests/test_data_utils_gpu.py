@@ -399,3 +399,43 @@ def test_batch_metrics_kernel_against_torch(B, F):
     want = [float((d * d).sum()), float(d.abs().sum()), float((p.argmax(1) == y.argmax(1)).sum()), B * F, B]
     np.testing.assert_allclose(got, want, rtol=1e-6)
     assert int(p[0].argmax()) == 3
+
+
+def test_hsr_mlp_dropout_module_training_mode():
+    """hsr.MLP with Dropout(p) (hsr.py:20-25: Linear -> LayerNorm -> Dropout -> ReLU) as a torch module: in ``train()`` mode the
+    autograd forward drops (the engine's masks, replayed in the torch restatement through ``masks=``), ``eval()`` does not; outputs
+    and every gradient tensor of the fp32 engine against torch autograd."""
+    from climsim_b200.baseline_models import HSRMLP
+    from oracle import models as M
+    torch.manual_seed(5)
+    hidden, layers, B, rate = 200, 2, 97, 0.25
+    ref = M.HSRMLPRef(124, 128, hidden, layers)
+    with torch.no_grad():
+        for i in range(layers):
+            ln = getattr(ref, f"linear{i}")[1]
+            ln.weight.uniform_(0.5, 1.5); ln.bias.uniform_(-0.3, 0.3)
+    net = HSRMLP(124, 128, hidden_dims=hidden, layers=layers, dropout=rate, dtype="fp32", max_batch=128)
+    net.load_reference_state_dict(ref.state_dict())
+    g = torch.Generator().manual_seed(6)
+    x, y = 0.5 * torch.randn(B, 124, generator=g), 0.3 * torch.randn(B, 128, generator=g)
+    net.train()
+    got = net(x.cuda())
+    ((got - y.cuda()) ** 2).mean().backward()
+    masks = [net.engine.dropout_mask(l, B).cpu() for l in range(layers)]
+    assert all(abs((m == 0).float().mean().item() - rate) < 0.03 for m in masks)
+    want = ref(x, masks=masks)
+    ((want - y) ** 2).mean().backward()
+    assert (got.detach().cpu() - want.detach()).abs().max().item() <= 2e-5 * want.abs().max().item()
+    want_g = []
+    for i in range(layers):
+        seq = getattr(ref, f"linear{i}")
+        want_g += [seq[0].weight.grad.t().reshape(-1), seq[0].bias.grad, seq[1].weight.grad, seq[1].bias.grad]
+    want_g += [ref.final_linear.weight.grad.t().reshape(-1), ref.final_linear.bias.grad]
+    off, got_g = 0, net.flat.grad.cpu()
+    for i, w in enumerate(want_g):
+        part = got_g[off:off + w.numel()]
+        off += w.numel()
+        assert (part - w).abs().max().item() <= 5e-5 * max(w.abs().max().item(), 1e-12), (i, (part - w).abs().max().item())
+    net.eval()
+    with torch.no_grad():
+        assert (net(x.cuda()).cpu() - ref(x)).abs().max().item() <= 2e-5 * want.abs().max().item()

@@ -524,3 +524,58 @@ def test_fused_tail_kernel_against_the_three_launches(units, B, act, monkeypatch
         np.testing.assert_array_equal(a, b, err_msg=f"tensor {i}")
     for a, b in zip(ga[-2:], gb[-2:]):
         assert np.abs(a - b).max() <= 1e-5 * np.abs(b).max()
+
+
+@pytest.mark.parametrize("act", ["leakyrelu", "relu"])
+def test_mlp_dropout_train_step_against_oracle_with_the_same_masks(act):
+    """Dropout behind every hidden activation (csb_mlp_set_dropout; the reference's torch models: hsr.py:20-25, online mlp.py:41-45).
+    PyTorch's random stream cannot be reproduced, so the engine's own keep decisions are read back (csb_mlp_debug_dropout_mask) and
+    replayed in the oracle: fp32 engine loss / every gradient tensor <= 1e-5 (2e-5 of the largest entry for the gradients), bf16
+    engine within the bf16 bounds, both arithmetic modes dropping the SAME elements; drop rate, inverted scaling, fresh masks per
+    step, inference forward dropout-free, rate 0 = the plain step.  LeakyReLU is the case the mask-free backward must get right:
+    a dropped element's saved output is 0, where act' from the sign alone would let alpha * dA through."""
+    from climsim_b200 import MLPEngine
+    units, B, rate = (256, 192, 64), 300, 0.3
+    ref = M.MLPRef(units=units, act=act, seed=31)
+    ref.randomize_biases(32)
+    x, y = _batch(B, 33)
+    n_hidden = len(units) + 1
+    masks_by_dtype = {}
+    for dtype in ("fp32", "bf16"):
+        eng = MLPEngine.mlp_v1(units=units, act=act, dtype=dtype, max_batch=512)
+        _load(eng, ref)
+        eng.set_dropout(rate, seed=7)
+        loss = eng.train_step(x.cuda(), y.cuda()).item()
+        masks = [eng.dropout_mask(l, B).cpu() for l in range(n_hidden)]
+        masks_by_dtype[dtype] = masks
+        for m in masks:
+            assert all(min(abs(v), abs(v - 1.0 / (1.0 - rate))) < 1e-6 for v in torch.unique(m).tolist())
+            assert abs((m == 0).float().mean().item() - rate) < 0.02                       # drop rate
+        pred = ref.forward(x, masks=masks)
+        want_loss = M.mse(y, pred)
+        want_g = torch.autograd.grad(want_loss, ref.params)
+        g_got, g_ref = eng.split_flat(eng.get_grads_flat()), eng.split_flat(_flat(want_g))
+        if dtype == "fp32":
+            assert abs(loss - want_loss.item()) <= 1e-5 * abs(want_loss.item())
+            for i, (a, b) in enumerate(zip(g_got, g_ref)):
+                assert np.abs(a - b).max() <= 2e-5 * max(np.abs(b).max(), 1e-12), (i, np.abs(a - b).max(), np.abs(b).max())
+        else:
+            assert abs(loss - want_loss.item()) <= 2e-2 * abs(want_loss.item())
+            for i, (a, b) in enumerate(zip(g_got, g_ref)):
+                # against the fp32 oracle (no rounding emulation): 5.1e-2 measured on the first layer's kernel
+                assert np.linalg.norm(a - b) <= 1e-1 * max(np.linalg.norm(b), 1e-12), (i, np.linalg.norm(a - b) / np.linalg.norm(b))
+        # a second step draws fresh masks
+        eng.train_step(x.cuda(), y.cuda())
+        assert not torch.equal(eng.dropout_mask(0, B).cpu(), masks[0])
+        # inference is dropout-free
+        p_inf = eng.forward(x.cuda()).cpu()
+        with torch.no_grad():
+            p_ref = ref.forward(x)
+        assert (p_inf - p_ref).abs().max().item() <= (1e-5 if dtype == "fp32" else 3e-2) * p_ref.abs().max().item()
+        # rate 0: the plain step again
+        eng.set_dropout(0.0)
+        l0 = eng.train_step(x.cuda(), y.cuda()).item()
+        assert abs(l0 - M.mse(y, p_ref).item()) <= (1e-5 if dtype == "fp32" else 2e-2) * abs(l0)
+        eng.close()
+    for a, b in zip(masks_by_dtype["fp32"], masks_by_dtype["bf16"]):
+        assert torch.equal(a, b)
