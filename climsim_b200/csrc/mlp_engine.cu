@@ -69,6 +69,22 @@ static int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t cols, uint
   return CSB_OK;
 }
 
+// fp32 matrix as a kind::tf32 operand: the 128-byte swizzle row holds 32 elements
+static int make_tmap_f32(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  CSB_REQUIRE(fn != nullptr, CSB_ECUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 4};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CSB_REQUIRE(r == CUDA_SUCCESS, CSB_ECUDA, "cuTensorMapEncodeTiled (fp32) failed with CUresult %d (cols %llu rows %llu ld %llu box 32x%u)",
+              (int)r, (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)ld, box_rows);
+  return CSB_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // tensor-core launch helpers
 // ---------------------------------------------------------------------------------------------------------------
@@ -193,6 +209,15 @@ static int launch_tn_auto(const CUtensorMap& ta, const CUtensorMap& tb, const tc
   return launch_tn_shape<EPI, 0>(ta, tb, p, sm_count, st, tb_small);
 }
 static inline int tn_block_n(int N) { return N > 128 ? 256 : 128; }
+
+// kind::tf32 launches (CSB_TF32): 256-wide pair tiles for layers wider than 128 columns, else 128-wide single-CTA tiles; the B tensor
+// map must have been encoded with tf32_b_box(N) rows
+template <int EPI, int VARX = 0>
+static int launch_tn_tf32(const CUtensorMap& ta, const CUtensorMap& tb, const tc::GemmParams& p, int sm_count, cudaStream_t st) {
+  constexpr int V = tc::VAR_TF32 | VARX;
+  if (g_use_pairs && p.N > 128) return launch_tn<256, 6, EPI, 2, V>(ta, tb, p, sm_count, st);
+  return launch_tn<128, 6, EPI, 1, V>(ta, tb, p, sm_count, st);
+}
 
 template <int BN, int STAGES, int CG>
 static int launch_nt(const CUtensorMap& ta, const CUtensorMap& tb, const tc::NtParams& p, int splits, cudaStream_t st) {
@@ -342,6 +367,16 @@ struct csb_mlp {
   CUtensorMap tm_w[CSB_MAX_LAYERS];         // W16_l  as K-major B operand of the data-gradient GEMM
   CUtensorMap tm_wt_s[CSB_MAX_LAYERS], tm_w_s[CSB_MAX_LAYERS];     // the same two with a 128-row box (small-batch tile policy)
   int64_t maps_B = -1;
+  // CSB_TF32: fp32 buffers as kind::tf32 operands.  wt32_l = W_l^T [Np, Kp] (B operand of the forward GEMM; W_l itself, [Kp, Np], is the
+  // K-major B operand of the data gradient); tr_a / tr_b = transposed copies of a layer's input and dZ ([features, batch]: the weight
+  // gradient contracts over the batch)
+  bool tf32 = false;
+  float* wt32[CSB_MAX_LAYERS] = {};
+  float* w32r[CSB_MAX_LAYERS] = {};        // W_l rounded to the TF32 grid, [Kp, Np] (the fp32 master weights stay exact)
+  float *tr_a = nullptr, *tr_b = nullptr;
+  int64_t tr_ld = 0;
+  CUtensorMap tm32_wt[CSB_MAX_LAYERS], tm32_w[CSB_MAX_LAYERS];
+  CUtensorMap tm32_in[CSB_MAX_LAYERS], tm32_dz[CSB_MAX_LAYERS], tm32_tra[CSB_MAX_LAYERS], tm32_trb[CSB_MAX_LAYERS];
   ActMaps tm_in[CSB_MAX_LAYERS];            // input of layer l (xn or act[l-1]) with `maps_B` rows
   ActMaps tm_dz[CSB_MAX_LAYERS];            // dZ_l (ping-pong buffer (L-1-l)&1, ld = Np_l) with `maps_B` rows
   CUtensorMap tm_z[CSB_MAX_LAYERS];         // LayerNorm layers: pre-norm z buffer (TMA-store target of the forward GEMM)
@@ -404,7 +439,8 @@ static inline size_t esize(const csb_mlp* h) { return h->bf16 ? 2 : 4; }
 static void free_all(csb_mlp* h) {
   auto F = [](void* p) { if (p) cudaFree(p); };
   F(h->params); F(h->grads); F(h->m); F(h->v); F(h->ws);
-  for (int l = 0; l < CSB_MAX_LAYERS; ++l) { F(h->w16[l]); F(h->wt16[l]); F(h->act[l]); F(h->zbuf[l]); F(h->ln_stats[l]); F(h->amask[l]); }
+  for (int l = 0; l < CSB_MAX_LAYERS; ++l) { F(h->w16[l]); F(h->wt16[l]); F(h->wt32[l]); F(h->w32r[l]); F(h->act[l]); F(h->zbuf[l]); F(h->ln_stats[l]); F(h->amask[l]); }
+  F(h->tr_a); F(h->tr_b);
   F(h->xn); F(h->dz[0]); F(h->dz[1]); F(h->pred); F(h->dx_tmp);
   F(h->d_sub); F(h->d_div); F(h->d_out_scale); F(h->d_inv_out_scale); F(h->d_loss_w); F(h->d_out_mask);
   F(h->loss_partials); F(h->d_loss); F(h->d_xform);
@@ -433,7 +469,20 @@ static void free_all(csb_mlp* h) {
     if (cudaMemset((ptr), 0, (bytes)) != cudaSuccess) { set_last_error("cudaMemset failed"); return CSB_ECUDA; } \
   } while (0)
 
+static inline int transpose_grid(const csb_mlp* h, int64_t rows, int cols) {
+  return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(rows, 32) * ceil_div(cols, 32), (int64_t)h->sm_count * 16));
+}
 static int repack_weights(csb_mlp* h, cudaStream_t st) {
+  if (h->tf32) {                       // W_l [Kp, Np] -> wt32_l [Np, Kp] and w32r_l [Kp, Np], both rounded to the TF32 grid
+    for (int l = 0; l < h->L; ++l) {
+      const LayerInfo& li = h->layer[l];
+      simt::transpose_f32_kernel<<<transpose_grid(h, li.Kp, li.Np), 256, 0, st>>>(h->params + li.w_off, li.Np, li.Kp, li.Np, h->wt32[l], li.Kp, 1);
+      simt::transpose_f32_kernel<<<transpose_grid(h, li.Kp, li.Np), 256, 0, st>>>(h->params + li.w_off, li.Np, li.Kp, li.Np, h->w32r[l], 0, 1);
+      CSB_CUDA_CHECK(cudaGetLastError());
+    }
+    prof_mark(h, K_REPACK, st);
+    return CSB_OK;
+  }
   if (!h->bf16) return CSB_OK;
   simt::RepackTable tab;
   tab.n = h->L;
@@ -469,7 +518,24 @@ static int build_weight_maps(csb_mlp* h) {
 static inline __nv_bfloat16* dz16(csb_mlp* h, int l) { return reinterpret_cast<__nv_bfloat16*>(h->dz[(h->L - 1 - l) & 1]); }
 static inline float* dz32(csb_mlp* h, int l) { return reinterpret_cast<float*>(h->dz[(h->L - 1 - l) & 1]); }
 
+// B-operand box rows of the kind::tf32 launches: 256-wide pair tiles when the layer is wider than 128 columns, else 128-wide single-CTA tiles
+static inline bool tf32_pairs(int N) { return g_use_pairs && N > 128; }
+static inline uint32_t tf32_b_box(int N) { return (uint32_t)(tf32_pairs(N) ? std::min(N, 256) / 2 : std::min(N, 128)); }
+
 static int build_act_maps(csb_mlp* h, int64_t B) {
+  if (h->tf32 && h->maps_B != B) {
+    for (int l = 0; l < h->L; ++l) {
+      const LayerInfo& li = h->layer[l];
+      int rc = make_tmap_f32(&h->tm32_in[l], layer_in(h, l), li.Kp, B, li.Kp, 128);
+      if (!rc) rc = make_tmap_f32(&h->tm32_dz[l], dz32(h, l), li.Np, B, li.Np, 128);
+      // transposed copies [features, batch]: A operand rows = Kp (box 128), B operand rows = Np
+      if (!rc) rc = make_tmap_f32(&h->tm32_tra[l], h->tr_a, B, li.Kp, h->tr_ld, 128);
+      if (!rc) rc = make_tmap_f32(&h->tm32_trb[l], h->tr_b, B, li.Np, h->tr_ld, tf32_b_box(li.Np));
+      if (rc) return rc;
+    }
+    h->maps_B = B;
+    return CSB_OK;
+  }
   if (!h->bf16 || h->maps_B == B) return CSB_OK;
   for (int l = 0; l < h->L; ++l) {
     const LayerInfo& li = h->layer[l];
@@ -528,7 +594,7 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
   *out = nullptr;
   CSB_REQUIRE(cfg->n_layers >= 1 && cfg->n_layers <= CSB_MAX_LAYERS, CSB_EINVAL, "n_layers %d out of range", cfg->n_layers);
   CSB_REQUIRE(cfg->in_dim >= 1 && cfg->max_batch >= 1, CSB_EINVAL, "in_dim / max_batch must be positive");
-  CSB_REQUIRE(cfg->dtype == CSB_F32 || cfg->dtype == CSB_BF16, CSB_EINVAL, "unknown dtype %d", cfg->dtype);
+  CSB_REQUIRE(cfg->dtype == CSB_F32 || cfg->dtype == CSB_BF16 || cfg->dtype == CSB_TF32, CSB_EINVAL, "unknown dtype %d", cfg->dtype);
   CSB_REQUIRE(cfg->loss >= CSB_LOSS_MSE && cfg->loss <= CSB_LOSS_HUBER, CSB_EINVAL, "unknown loss %d", cfg->loss);
   int sm = 0, maj = 0, min = 0;
   int rc = csb_device_info(&sm, &maj, &min, nullptr);
@@ -554,6 +620,7 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
   h->L = cfg->n_layers;
   h->sm_count = sm;
   h->bf16 = cfg->dtype == CSB_BF16;
+  h->tf32 = cfg->dtype == CSB_TF32;            // fp32 storage (every `!bf16` path below), GEMMs on the tensor cores
   // opt-in (CSB_CONCURRENT_WGRAD=1): measured 0.896 against 0.875-0.89 ms/step for the plain in-order chain on one B200 -- the
   // cross-stream dependencies cost the programmatic-launch overlap that the single stream has, and both kernels want every SM
   if (h->bf16 && getenv("CSB_CONCURRENT_WGRAD") != nullptr) {         // side stream for the weight-gradient GEMMs (see csb_mlp)
@@ -585,6 +652,11 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
     const int tiles = nt_m_tiles(li.Kp, li.nt_cg) * (int)ceil_div(li.Np, li.nt_block_n);
     // one wave of CTAs, but at most 64 partials: the reduction walks a tile's partials serially
     li.max_w_splits = h->bf16 ? std::max(1, std::min(64, (sm / li.nt_cg) / tiles)) : 1;
+    if (h->tf32) {                    // split contraction of the TF32 weight gradient: one wave of 256 x 256 pair tiles (or 128 x 128 tiles)
+      const bool pr = tf32_pairs(li.Np);
+      const int t32 = pr ? (int)(ceil_div(ceil_div(li.Kp, 128), 2) * ceil_div(li.Np, 256)) : (int)(ceil_div(li.Kp, 128) * ceil_div(li.Np, 128));
+      li.max_w_splits = std::max(1, std::min(64, (pr ? sm / 2 : sm) / t32));
+    }
     // a last n-block of exactly half width (640 = 256 + 256 + 128) takes fewer, longer splits (NtParams.splits_narrow): nt_narrow_splits(S)
     // of them; the largest S with  m_tiles * ((n_blocks - 1) * S + nt_narrow_splits(S))  CTA groups in one wave
     li.nt_narrow = h->bf16 && g_use_nt_narrow && li.Np > li.nt_block_n && li.Np % li.nt_block_n == li.nt_block_n / 2;
@@ -640,6 +712,21 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
       CKA(h->wt16[l], (size_t)h->layer[l].Kp * h->layer[l].Np * 2);
     }
     CK(build_weight_maps(h));
+  }
+  if (h->tf32) {
+    int max_dim = h->in_p;
+    for (int l = 0; l < h->L; ++l) {
+      const LayerInfo& li = h->layer[l];
+      if (l + 1 < h->L && li.act == CSB_ACT_ELU) { free_all(h); delete h; set_last_error("CSB_TF32: ELU hidden layers are not instantiated"); return CSB_EUNSUPPORTED; }
+      max_dim = std::max(max_dim, std::max(li.Kp, li.Np));
+      CKA(h->wt32[l], (size_t)li.Kp * li.Np * 4);
+      CKA(h->w32r[l], (size_t)li.Kp * li.Np * 4);
+      CK(make_tmap_f32(&h->tm32_wt[l], h->wt32[l], li.Kp, li.Np, li.Kp, tf32_b_box(li.Np)));
+      CK(make_tmap_f32(&h->tm32_w[l], h->w32r[l], li.Np, li.Kp, li.Np, tf32_b_box(li.Kp)));
+    }
+    h->tr_ld = h->cap;                  // a multiple of 128 floats
+    CKA(h->tr_a, (size_t)max_dim * h->tr_ld * 4);
+    CKA(h->tr_b, (size_t)max_dim * h->tr_ld * 4);
   }
   CK(csb_mlp_set_norm(h, nullptr, nullptr, nullptr, nullptr));
 #undef CK
@@ -890,7 +977,7 @@ int csb_mlp_grad_buffer(csb_mlp* h, float** ptr, size_t* n) {
 // ---------------------------------------------------------------------------------------------------------------
 // forward pieces
 // ---------------------------------------------------------------------------------------------------------------
-static int run_normalize(csb_mlp* h, const float* x, int64_t B, int apply, cudaStream_t st) {
+static int run_normalize_raw(csb_mlp* h, const float* x, int64_t B, int apply, cudaStream_t st) {
   if (apply && h->d_xform != nullptr) {       // generalised prologue (exp transforms, pruned columns, clipping) of the online models
     dim3 grid((unsigned)std::min<int64_t>(ceil_div(B, 2), (int64_t)h->sm_count * 8), (unsigned)ceil_div(h->in_p, 128));
     simt::prepare_input_kernel<<<grid, 256, 0, st>>>(x, h->in_dim, h->d_sub, h->d_div, h->d_xform,
@@ -916,6 +1003,16 @@ static int run_normalize(csb_mlp* h, const float* x, int64_t B, int apply, cudaS
   return CSB_OK;
 }
 
+static int run_normalize(csb_mlp* h, const float* x, int64_t B, int apply, cudaStream_t st) {
+  int rc = run_normalize_raw(h, x, B, apply, st);
+  if (rc || !h->tf32) return rc;
+  // CSB_TF32: the first GEMM's A operand rounded (to nearest) onto the TF32 grid, like every other stored tensor of this mode
+  simt::transpose_f32_kernel<<<transpose_grid(h, B, h->in_p), 256, 0, st>>>(reinterpret_cast<const float*>(h->xn), h->in_p, B, h->in_p,
+                                                                          reinterpret_cast<float*>(h->xn), 0, 1);
+  CSB_CUDA_CHECK(cudaGetLastError());
+  return CSB_OK;
+}
+
 static int run_hidden_forward(csb_mlp* h, int64_t B, cudaStream_t st, bool training = false) {
   const bool drop = training && h->dropout > 0.f;
   if (drop) h->drop_fwd++;
@@ -930,6 +1027,12 @@ static int run_hidden_forward(csb_mlp* h, int64_t B, cudaStream_t st, bool train
       p.bias = h->params + li.b_off; p.out = li.ln ? h->zbuf[l] : h->act[l]; p.ld_out = li.Np;
       p.mask_out = h->amask[l]; p.ld_mask = (int)h->cap;
       int rc = launch_tn_auto<tc::EPI_BIAS_ACT>(h->tm_in[l].a_k128, h->tm_wt[l], p, h->sm_count, st, &h->tm_wt_s[l]);
+      if (rc) return rc;
+    } else if (h->tf32) {
+      tc::GemmParams p = {};
+      p.M = (int)B; p.N = li.Np; p.K = li.Kp; p.act = gemm_act; p.alpha = li.alpha; p.head_relu_from = -1;
+      p.bias = h->params + li.b_off; p.out = li.ln ? h->zbuf[l] : h->act[l]; p.ld_out = li.Np;
+      int rc = launch_tn_tf32<tc::EPI_BIAS_ACT>(h->tm32_in[l], h->tm32_wt[l], p, h->sm_count, st);
       if (rc) return rc;
     } else {
       simt::SgemmParams p = {};
@@ -992,6 +1095,16 @@ static int run_head(csb_mlp* h, int64_t B, int fused_loss, const float* y, float
     } else {
       rc = launch_tn_auto<tc::EPI_HEAD_OUT>(h->tm_in[l].a_k128, h->tm_wt[l], p, h->sm_count, st, &h->tm_wt_s[l]);
     }
+    if (rc) return rc;
+  } else if (h->tf32) {
+    // predictions (fp32) straight from the head epilogue; loss and dL/dz follow in head_grad_kernel as in the fp32 mode
+    tc::GemmParams p = {};
+    p.M = (int)B; p.N = li.Np; p.K = li.Kp; p.act = li.act; p.alpha = li.alpha; p.head_relu_from = h->cfg.head_relu_from;
+    p.bias = h->params + li.b_off; p.out_dim = h->out_dim;
+    p.pred = h->pred; p.ld_pred = h->out_p;
+    p.out_mask = h->has_mask ? h->d_out_mask : nullptr;
+    int rc = li.act == CSB_ACT_ELU ? launch_tn_tf32<tc::EPI_HEAD_OUT, tc::VAR_ELU>(h->tm32_in[l], h->tm32_wt[l], p, h->sm_count, st)
+                                   : launch_tn_tf32<tc::EPI_HEAD_OUT>(h->tm32_in[l], h->tm32_wt[l], p, h->sm_count, st);
     if (rc) return rc;
   } else {
     simt::SgemmParams p = {};
@@ -1141,6 +1254,13 @@ static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st,
   int64_t max_len = 4;
   const bool conc = h->bf16 && h->side_on && !h->prof_on;      // per-kind profiling wants the launches back to back on one stream
   h->pending_tail = false;
+  if (h->tf32) {
+    // the output layer's dL/dz (written in full fp32 by the loss kernels) onto the TF32 grid, like every dZ this mode stores: all of its
+    // consumers (bias column sums, weight gradient, data gradient) then see one and the same value
+    const LayerInfo& lo = h->layer[h->L - 1];
+    simt::transpose_f32_kernel<<<transpose_grid(h, B, lo.Np), 256, 0, st>>>(dz32(h, h->L - 1), lo.Np, B, lo.Np, dz32(h, h->L - 1), 0, 1);
+    CSB_CUDA_CHECK(cudaGetLastError());
+  }
   for (int l = h->L - 1; l >= 0; --l) {
     const LayerInfo& li = h->layer[l];
     if (tail_done && l == h->L - 1) {
@@ -1197,6 +1317,22 @@ static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st,
         p.colsum_out = h->ws + li.ws_b_off; p.colsum_stride = (size_t)li.Np;      // bias gradient fused into this kernel
         int rc = launch_nt_auto(h->tm_in[l].mn64, h->tm_dz[l].mn64, p, splits, ws, li.nt_cg);
         if (rc) return rc;
+      } else if (h->tf32) {
+        // dW_l = in_l^T . dZ_l contracts over the batch: both operands transposed to [features, batch] (K-major for tcgen05), the
+        // contraction cut into `splits` ranges whose fp32 partial products are summed in a fixed order with every other gradient
+        simt::transpose_f32_kernel<<<transpose_grid(h, B, li.Kp), 256, 0, ws>>>(reinterpret_cast<const float*>(layer_in(h, l)), li.Kp, B, li.Kp, h->tr_a, h->tr_ld, 1);
+        simt::transpose_f32_kernel<<<transpose_grid(h, B, li.Np), 256, 0, ws>>>(dz32(h, l), li.Np, B, li.Np, h->tr_b, h->tr_ld, 1);
+        CSB_CUDA_CHECK(cudaGetLastError());
+        tc::GemmParams p = {};
+        p.M = li.Kp; p.N = li.Np; p.K = (int)round_up(B, 32);                 // columns past B are zero-filled by TMA
+        const int num_kb = p.K / 32;
+        const int want = std::max(1, std::min(li.max_w_splits, num_kb));
+        const int kps = (int)ceil_div(num_kb, want);
+        splits = (int)ceil_div(num_kb, kps);                                  // every range holds at least one k-block
+        p.k_splits = splits; p.split_stride = (size_t)li.Kp * li.Np;
+        p.out = h->ws + li.ws_w_off; p.ld_out = li.Np;
+        int rc = launch_tn_tf32<tc::EPI_F32, tc::VAR_KSPLIT>(h->tm32_tra[l], h->tm32_trb[l], p, h->sm_count, ws);
+        if (rc) return rc;
       } else {
         simt::SgemmParams p = {};
         p.M = li.Kp; p.N = li.Np; p.K = (int)B;
@@ -1247,6 +1383,14 @@ static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st,
         } else {
           rc = launch_tn_auto<tc::EPI_DGRAD>(h->tm_dz[l].a_k128, h->tm_w[l], p, h->sm_count, st, &h->tm_w_s[l]);
         }
+        if (rc) return rc;
+      } else if (h->tf32) {
+        tc::GemmParams p = {};
+        p.M = (int)B; p.N = li.Kp; p.K = li.Np; p.act = lp.act; p.alpha = lp.alpha; p.head_relu_from = -1;
+        p.out = dz32(h, l - 1); p.ld_out = lp.Np;
+        p.saved = reinterpret_cast<const __nv_bfloat16*>(h->act[l - 1]); p.ld_saved = lp.Np;      // fp32 in this mode (VAR_TF32 epilogue)
+        p.dgrad_scale = h->drop_live ? 1.f / (1.f - h->dropout) : 0.f;
+        int rc = launch_tn_tf32<tc::EPI_DGRAD>(h->tm32_dz[l], h->tm32_w[l], p, h->sm_count, st);
         if (rc) return rc;
       } else {
         simt::SgemmParams p = {};
@@ -1655,6 +1799,25 @@ int csb_test_gemm_tn(const uint16_t* A, const uint16_t* Bt, float* C, int M, int
   if (pairs) return launch_tn<256, 6, tc::EPI_F32, 2>(ta, tb, p, sm, st);
   if (block_n == 256) return launch_tn<256, 4, tc::EPI_F32, 1>(ta, tb, p, sm, st);
   return launch_tn<128, 6, tc::EPI_F32, 1>(ta, tb, p, sm, st);
+}
+
+// C[M,N] (fp32) = A[M,K] . Bt[N,K]^T with fp32 operands through tcgen05 kind::tf32 (block_n as above)
+int csb_test_gemm_tn_tf32(const float* A, const float* Bt, float* C, int M, int N, int K, int block_n, void* stream) {
+  CSB_REQUIRE(A && Bt && C, CSB_EINVAL, "null argument");
+  CSB_REQUIRE(N % 64 == 0 && K % 32 == 0 && M > 0, CSB_EINVAL, "N must be a multiple of 64 and K of 32");
+  CSB_REQUIRE(block_n == 128 || block_n == 512, CSB_EINVAL, "block_n must be 128 (single CTA) or 512 (= 256 on CTA pairs)");
+  const bool pairs = block_n == 512;
+  int sm = 0;
+  int rc = csb_device_info(&sm, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  CUtensorMap ta, tb;
+  if ((rc = make_tmap_f32(&ta, A, K, M, K, 128))) return rc;
+  if ((rc = make_tmap_f32(&tb, Bt, K, N, K, (uint32_t)(pairs ? std::min(N, 256) / 2 : std::min(N, 128))))) return rc;
+  tc::GemmParams p = {};
+  p.M = M; p.N = N; p.K = K; p.out = C; p.ld_out = N;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (pairs) return launch_tn<256, 6, tc::EPI_F32, 2, tc::VAR_TF32>(ta, tb, p, sm, st);
+  return launch_tn<128, 6, tc::EPI_F32, 1, tc::VAR_TF32>(ta, tb, p, sm, st);
 }
 
 static int g_test_dbg = 0;

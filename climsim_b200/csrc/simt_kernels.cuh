@@ -1055,6 +1055,42 @@ dropout_bf16_kernel(__nv_bfloat16* __restrict__ a, int64_t n8, uint32_t seed, ui
   }
 }
 
+// dst[c][r] = src[r][c] for r < rows, c < cols (fp32; 32 x 32 tiles through shared memory, both sides coalesced): the TF32 mode's weight
+// gradient contracts over the batch, which the K-major tcgen05 operands want contiguous
+// round_tf32 != 0: values rounded to nearest onto the TF32 grid on the way (tc::round_tf32); ld_dst == 0: no transposition (a rounded copy).
+__global__ void __launch_bounds__(256) transpose_f32_kernel(const float* __restrict__ src, int64_t ld_src, int64_t rows, int cols,
+                                                            float* __restrict__ dst, int64_t ld_dst, int round_tf32) {
+  __shared__ float t[32][33];
+  const int64_t tiles_c = (cols + 31) / 32, tiles_r = (rows + 31) / 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;            // 32 x 8
+  for (int64_t tile = blockIdx.x; tile < tiles_c * tiles_r; tile += gridDim.x) {
+    const int64_t r0 = (tile / tiles_c) * 32;
+    const int c0 = (int)(tile % tiles_c) * 32;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t r = r0 + ty + 8 * j;
+      float v = (r < rows && c0 + tx < cols) ? src[r * ld_src + c0 + tx] : 0.f;
+      if (round_tf32) v = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+      t[ty + 8 * j][tx] = v;
+    }
+    __syncthreads();
+    if (ld_dst == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t r = r0 + ty + 8 * j;
+        if (r < rows && c0 + tx < cols) dst[r * ld_src + c0 + tx] = t[ty + 8 * j][tx];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = c0 + ty + 8 * j;
+        if (c < cols && r0 + tx < rows) dst[(int64_t)c * ld_dst + r0 + tx] = t[tx][ty + 8 * j];
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // the same keep decisions on an fp32 buffer (element e belongs to group e / 8, LCG step e % 8), so that the CSB_F32 and CSB_BF16 engines
 // drop the same elements for the same (seed, step, layer)
 __global__ void __launch_bounds__(256)

@@ -88,6 +88,11 @@ struct GemmParams {
   // (TMEM columns 256..511; one tile in flight instead of two).  out = act(acc1 + bias) [dropout] as usual, and
   // out2 = (acc2 + bias2) + bf16(out): a residual block's  relu(conv2(h1)) + conv1x1(x_in)  in one launch (cnn_engine.cuh)
   const float* bias2;
+  // VAR_KSPLIT (EPI_F32): the contraction is cut into k_splits ranges of whole k-blocks, range s writes its partial product to
+  // out + s * split_stride (floats); the caller sums the partials in a fixed order (the weight gradient of the TF32 mode, whose
+  // contraction runs over the batch)
+  int k_splits;
+  size_t split_stride;
   // EPI_HEAD_LOSS / EPI_HEAD_OUT
   const float* y;              // targets [M, ld_y]
   int ld_y;
@@ -208,6 +213,16 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::tf32: the operands are fp32 words in shared memory, of which the tensor core uses sign, exponent and the top 10 mantissa bits
+// (what TF32 on the reference's A100 runs does); 8 elements = 32 B of contraction per instruction, fp32 accumulation
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // mbarrier arrives once all previously issued tcgen05.mma of this thread have completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -255,6 +270,14 @@ __device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, u
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // commit: arrive on the mbarrier at this offset in BOTH CTAs of the pair once the issued MMAs have completed
 __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -294,6 +317,12 @@ __device__ __forceinline__ uint64_t make_desc_mnmajor_sw128(uint32_t saddr, uint
 // N>>3 at bits 17-22, M>>4 at bits 24-28.
 __device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// kind::tf32 instruction descriptor: the same fields with A, B format 2 (TF32)
+__device__ __forceinline__ uint32_t make_idesc_tf32(int m, int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
@@ -431,15 +460,21 @@ __device__ __forceinline__ uint32_t drop_mix32(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
   return x;
 }
-template <int EPI, bool ELU, bool GENERAL_LOSS, bool STAGED, bool DROPOUT = false, bool DUAL = false, bool ACC2 = false>
+// round-to-nearest onto the TF32 grid (10 mantissa bits): kind::tf32 itself TRUNCATES the low 13 bits of what it reads, which biases
+// every product downwards by ~2^-11 and adds up over a chain of layers; tensors that will be tensor-core operands again are therefore
+// stored already rounded (the truncation is then exact)
+__device__ __forceinline__ float round_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+// F32IO (VAR_TF32): the stored tensors (outputs, saved activations) are fp32 instead of bf16.
+template <int EPI, bool ELU, bool GENERAL_LOSS, bool STAGED, bool DROPOUT = false, bool DUAL = false, bool ACC2 = false, bool F32IO = false>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float* sbias, const float* sloss_w, const RowInfo& ri, int gcol,
                                                const uint32_t (&raw)[32], const uint32_t (&sv)[16], const float (&yv)[32], float& loss_acc,
-                                               uint32_t mask_word, uint32_t stage_addr, uint32_t taddr2 = 0) {
+                                               uint32_t mask_word, uint32_t stage_addr, uint32_t taddr2 = 0, size_t out_off = 0) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
   const bool st_ok = ri.in_range && !(p.dbg & 4);
   __nv_bfloat16* out16 = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)ri.grow * p.ld_out + gcol;
+  [[maybe_unused]] float* out32 = reinterpret_cast<float*>(p.out) + (size_t)ri.grow * p.ld_out + gcol;      // F32IO
   constexpr bool USE_BIAS = (EPI == EPI_BIAS_ACT || EPI == EPI_BIAS_ADD || EPI == EPI_HEAD_LOSS || EPI == EPI_HEAD_OUT);
   if constexpr (USE_BIAS) {
     if (!(p.dbg & 1)) {
@@ -452,7 +487,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
   }
 
   if constexpr (EPI == EPI_F32) {
-    if (ri.row_ok) store_f32x32(reinterpret_cast<float*>(p.out) + (size_t)ri.grow * p.ld_out + gcol, v);
+    if (ri.row_ok) store_f32x32(reinterpret_cast<float*>(p.out) + out_off + (size_t)ri.grow * p.ld_out + gcol, v);
   } else if constexpr (EPI == EPI_BIAS_ACT) {
     if (p.mask_out != nullptr) {
       // sign bits of the pre-activation (the activations here preserve the sign; act' of ReLU / LeakyReLU needs nothing else):
@@ -482,7 +517,12 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = 0.f;
     }
-    if constexpr (STAGED) stage_bf16x32(stage_addr, v); else if (st_ok) store_bf16x32_global(out16, v);
+    if constexpr (F32IO) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+      if (st_ok) store_f32x32(out32, v);
+    }
+    else if constexpr (STAGED) stage_bf16x32(stage_addr, v); else if (st_ok) store_bf16x32_global(out16, v);
     if constexpr (ACC2) {
       // second accumulator (loaded only now: the first one's registers are free again), its bias behind the first bias vector
       uint32_t raw2[32];
@@ -524,7 +564,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
       for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
     }
     float a[32];
-    unpack_bf16x32(sv, a);                          // saved activation (same rows / columns as the output)
+    if constexpr (F32IO) {
+      if (ri.in_range) load_f32x32(reinterpret_cast<const float*>(p.saved) + (size_t)ri.grow * p.ld_saved + gcol, a);
+      else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a[j] = 0.f;
+      }
+    } else {
+      unpack_bf16x32(sv, a);                        // saved activation (same rows / columns as the output)
+    }
     act_bwd32<ELU>(p.act, p.alpha, v, a);
     if (p.dgrad_scale != 0.f) {
       // kernel-uniform: a dropout layer sits behind the activation -- a dropped element's saved output is exactly 0 (also where
@@ -536,7 +584,12 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = 0.f;
     }
-    if constexpr (STAGED) stage_bf16x32(stage_addr, v); else if (st_ok) store_bf16x32_global(out16, v);
+    if constexpr (F32IO) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+      if (st_ok) store_f32x32(out32, v);
+    }
+    else if constexpr (STAGED) stage_bf16x32(stage_addr, v); else if (st_ok) store_bf16x32_global(out16, v);
   } else if constexpr (EPI == EPI_BIAS_ADD) {
     float a[32];
     unpack_bf16x32(sv, a);                          // tile to add (residual branch / partial gradient)
@@ -687,7 +740,7 @@ struct TnSmem {
 // both keep rarely used code out of the instruction stream (and the register budget) of the common kernels
 // bit 2 = results staged in shared memory and written with coalesced stores (the launches whose time is the epilogue: K <= 256)
 // bit 3 = in-kernel cycle counters for the micro-benchmark (p.stats); production instantiations carry none of that code
-constexpr int VAR_ELU = 1, VAR_GENERAL_LOSS = 2, VAR_STAGED = 4, VAR_STATS = 8, VAR_DROPOUT = 16, VAR_A2 = 32, VAR_DUAL = 64, VAR_ACC2 = 128, VAR_KTRIM = 256;
+constexpr int VAR_ELU = 1, VAR_GENERAL_LOSS = 2, VAR_STAGED = 4, VAR_STATS = 8, VAR_DROPOUT = 16, VAR_A2 = 32, VAR_DUAL = 64, VAR_ACC2 = 128, VAR_KTRIM = 256, VAR_TF32 = 512, VAR_KSPLIT = 1024;
 
 // Tile schedule of the persistent kernel; all three warp roles walk the same sequence.
 //   round-robin (the first design): tile t = (m-group t / n_blocks, n-block t % n_blocks), CTA group g takes t = g, g + G, ...
@@ -746,7 +799,11 @@ __global__ void __launch_bounds__(TN_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p,
                const __grid_constant__ CUtensorMap tmap_a2) {
   constexpr bool ELU = (VAR & VAR_ELU) != 0, GENERAL_LOSS = (VAR & VAR_GENERAL_LOSS) != 0;
-  constexpr bool BF16_OUT = (EPI == EPI_BIAS_ACT || EPI == EPI_HEAD_LOSS || EPI == EPI_DGRAD || EPI == EPI_DGRAD_MASK || EPI == EPI_BIAS_ADD);
+  // VAR_TF32: fp32 operands through kind::tf32 (a 128-byte k-block holds 32 elements, an instruction contracts 8), fp32 stored tensors
+  constexpr bool TF32 = (VAR & VAR_TF32) != 0;
+  static_assert(!TF32 || EPI == EPI_BIAS_ACT || EPI == EPI_DGRAD || EPI == EPI_HEAD_OUT || EPI == EPI_F32, "no fp32-storage variant of this epilogue");
+  constexpr int BKE = TF32 ? 32 : BK;                  // elements per k-block (TMA coordinates are in elements)
+  constexpr bool BF16_OUT = !TF32 && (EPI == EPI_BIAS_ACT || EPI == EPI_HEAD_LOSS || EPI == EPI_DGRAD || EPI == EPI_DGRAD_MASK || EPI == EPI_BIAS_ADD);
   constexpr bool STAGED = (VAR & VAR_STAGED) != 0 && BF16_OUT;
   constexpr bool STATS = (VAR & VAR_STATS) != 0;
   constexpr bool DROPOUT = (VAR & VAR_DROPOUT) != 0 && EPI == EPI_BIAS_ACT;
@@ -754,13 +811,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   constexpr bool ACC2 = (VAR & VAR_ACC2) != 0 && EPI == EPI_BIAS_ACT && A2;
   constexpr bool KTRIM = (VAR & VAR_KTRIM) != 0;       // GemmParams.tap_tail_k / a2_tail_k honoured (the issuer loop of every other kernel stays as it was)
   static_assert(!ACC2 || BN == 256, "two accumulators per tile: 2 x 256 TMEM columns");
+  static_assert(!TF32 || (VAR & (VAR_ACC2 | VAR_KTRIM | VAR_A2 | VAR_DUAL | VAR_DROPOUT | VAR_STAGED)) == 0, "kind::tf32 exists for the plain variants");
+  constexpr bool KSPLIT = (VAR & VAR_KSPLIT) != 0;
+  static_assert(!KSPLIT || (EPI == EPI_F32 && (VAR & (VAR_ACC2 | VAR_KTRIM | VAR_A2)) == 0), "split contraction: fp32 partial products only");
   const bool BALANCED = p.balanced != 0 && EPI != EPI_HEAD_LOSS;      // the loss partials are indexed by the round-robin tile grid
   using L = TnSmem<BN, STAGES, CG, STAGED>;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   const bool is_leader = cta_rank == 0;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static_assert(2 * BN <= 512, "two accumulator buffers must fit the 512 TMEM columns");
-  constexpr bool SAVED_IN = (EPI == EPI_DGRAD || EPI == EPI_BIAS_ADD);
+  constexpr bool SAVED_IN = (EPI == EPI_DGRAD || EPI == EPI_BIAS_ADD) && !TF32;      // (fp32 storage: loaded inside the epilogue step)
   constexpr bool USE_BIAS = (EPI == EPI_BIAS_ACT || EPI == EPI_HEAD_LOSS || EPI == EPI_HEAD_OUT || EPI == EPI_BIAS_ADD);
   constexpr int QCOLS = BN / 4, NCH = QCOLS / 32;      // columns / 32-column steps per epilogue warp
   static_assert(NCH >= 1, "BN must be at least 128");
@@ -779,7 +839,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m_blocks = ((p.M + BM - 1) / BM + CG - 1) / CG;       // in units of CG m-blocks (pairs when CG == 2)
   const int num_n_blocks = (p.N + BN - 1) / BN;
-  const int num_kb = p.K / BK;
+  const int num_kb = p.K / BKE;
+  // KSPLIT: the tile grid is (split, m-group, n-block); split s covers the k-blocks [s * kps, (s + 1) * kps)
+  const int m_groups_real = num_m_blocks;
+  const int kps = KSPLIT ? (num_kb + p.k_splits - 1) / p.k_splits : num_kb;
+  const int tile_m_groups = KSPLIT ? num_m_blocks * p.k_splits : num_m_blocks;
   const int my_group = (int)(blockIdx.x / CG), num_groups = (int)(gridDim.x / CG);      // both CTAs of a pair walk the same tiles
   using Tiles = TileIter<BN>;
 
@@ -820,30 +884,33 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ===================== TMA producer =====================
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
-      for (Tiles it(BALANCED, num_m_blocks, p.N, my_group, num_groups); it.next();) {
-        const int m0 = (it.mg * CG + (int)cta_rank) * BM, n0 = it.n0;
+      for (Tiles it(BALANCED, tile_m_groups, p.N, my_group, num_groups); it.next();) {
+        const int split = KSPLIT ? it.mg / m_groups_real : 0;
+        const int mg = KSPLIT ? it.mg - split * m_groups_real : it.mg;
+        const int kb0 = KSPLIT ? split * kps : 0, kb1 = KSPLIT ? min(num_kb, kb0 + kps) : num_kb;
+        const int m0 = (mg * CG + (int)cta_rank) * BM, n0 = it.n0;
         const int nb0 = n0 + (int)cta_rank * (it.n_valid / CG);              // this CTA's share of the B rows (the box may over-fetch)
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t sa = smem_base + s * L::STAGE_BYTES;
           const int tap = p.kb_per_tap ? kb / p.kb_per_tap : 0;
-          int ka = (kb - tap * p.kb_per_tap) * BK;                // column block inside the (un-replicated) A matrix
+          int ka = (kb - tap * p.kb_per_tap) * BKE;               // column block inside the (un-replicated) A matrix
           int tap_shift = p.kb_per_tap ? tap - p.tap_center : 0;  // may be -1 at the top: TMA zero-fills out-of-range rows
           const CUtensorMap* ta = &tmap_a;
           if constexpr (A2) {
-            if (kb >= p.a2_from_kb) { ta = &tmap_a2; ka = (kb - p.a2_from_kb) * BK; tap_shift = 0; }
+            if (kb >= p.a2_from_kb) { ta = &tmap_a2; ka = (kb - p.a2_from_kb) * BKE; tap_shift = 0; }
           }
           const bool ld_a = !(p.dbg & (16 | 128)), ld_b = !(p.dbg & (16 | 64));      // both true in production
-          const uint32_t tx = (ld_a ? (uint32_t)L::A_BYTES : 0u) + (ld_b ? (uint32_t)(p.b_box_rows * BK * 2) : 0u);
+          const uint32_t tx = (ld_a ? (uint32_t)L::A_BYTES : 0u) + (ld_b ? (uint32_t)(p.b_box_rows * 128) : 0u);
           if constexpr (CG == 2) {
             // one expect_tx on the leader's barrier covers the four loads of the pair
             if (is_leader) mbar_expect_tx(full_bar(s), 2 * tx);
             if (ld_a) tma_load_2d_2sm(sa, ta, full_bar(s), ka, m0 + tap_shift);
-            if (ld_b) tma_load_2d_2sm(sa + L::A_BYTES, &tmap_b, full_bar(s), kb * BK, nb0);
+            if (ld_b) tma_load_2d_2sm(sa + L::A_BYTES, &tmap_b, full_bar(s), kb * BKE, nb0);
           } else {
             mbar_expect_tx(full_bar(s), tx);
             if (ld_a) tma_load_2d(sa, ta, full_bar(s), ka, m0 + tap_shift);
-            if (ld_b) tma_load_2d(sa + L::A_BYTES, &tmap_b, full_bar(s), kb * BK, nb0);
+            if (ld_b) tma_load_2d(sa + L::A_BYTES, &tmap_b, full_bar(s), kb * BKE, nb0);
           }
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
@@ -854,9 +921,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (lane == 0 && is_leader) {
       int s = 0; uint32_t ph = 0; int t = 0;
       long long st_tempty = 0, st_full = 0;          // micro-benchmark: cycles the issuer waited for a free accumulator / for operands
-      for (Tiles it(BALANCED, num_m_blocks, p.N, my_group, num_groups); it.next(); ++t) {
+      for (Tiles it(BALANCED, tile_m_groups, p.N, my_group, num_groups); it.next(); ++t) {
         const int n_valid = it.n_valid;
-        const uint32_t idesc = make_idesc_bf16(BM * CG, n_valid, 0, 0);
+        const int kb0 = KSPLIT ? (it.mg / m_groups_real) * kps : 0, kb1 = KSPLIT ? min(num_kb, kb0 + kps) : num_kb;
+        const uint32_t idesc = TF32 ? make_idesc_tf32(BM * CG, n_valid, 0, 0) : make_idesc_bf16(BM * CG, n_valid, 0, 0);
         const int acc = ACC2 ? 0 : (t & 1);          // ACC2: one tile in flight (both accumulators belong to it)
         const uint32_t acc_par = ACC2 ? ((uint32_t)t & 1u) : ((uint32_t)(t >> 1) & 1u);
         long long c0 = (STATS && p.stats) ? clock64() : 0;
@@ -865,7 +933,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
         [[maybe_unused]] int kin = 0;                // position inside the tap (tap_tail_k)
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           [[maybe_unused]] int nk = BK / UMMA_K;
           if constexpr (KTRIM) {
             if (A2 && kb >= p.a2_from_kb) { if (kb == num_kb - 1 && p.a2_tail_k > 0) nk = p.a2_tail_k; }
@@ -894,9 +962,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             if (p.dbg & 32) break;
-            // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
-            if constexpr (CG == 2) umma_f16_2sm(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
-            else umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+            // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in the (addr >> 4) field  (tf32: 8 elements = 32 B)
+            if constexpr (TF32) {
+              if constexpr (CG == 2) umma_tf32_2sm(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)(((kb - kb0) | k) != 0));
+              else umma_tf32(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)(((kb - kb0) | k) != 0));
+            } else {
+            if constexpr (CG == 2) umma_f16_2sm(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)(((kb - kb0) | k) != 0));
+            else umma_f16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)(((kb - kb0) | k) != 0));
+            }
           }
           }
           // smem slot reusable (in both CTAs of a pair) once these MMAs have read it
@@ -916,8 +989,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const uint32_t stage_warp = smem_base + (uint32_t)(L::OUT_OFFSET + ew * L::OUT_WARP_BYTES);     // STAGED only
     int t = 0;
     long long st_epi_wait = 0, st_epi_busy = 0;      // micro-benchmark (epilogue warp 0): cycles waiting for an accumulator / working on it
-    for (Tiles it(BALANCED, num_m_blocks, p.N, my_group, num_groups); it.next(); ++t) {
-      const int mb = it.mg * CG + (int)cta_rank;
+    for (Tiles it(BALANCED, tile_m_groups, p.N, my_group, num_groups); it.next(); ++t) {
+      const int split = KSPLIT ? it.mg / m_groups_real : 0;
+      const int mb = (KSPLIT ? it.mg - split * m_groups_real : it.mg) * CG + (int)cta_rank;
       const int m0 = mb * BM, n0 = it.n0;
       const int n_valid = it.n_valid;
       const int acc = ACC2 ? 0 : (t & 1);
@@ -988,9 +1062,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int j = 0; j < 32; ++j) raw[j] = 0u;
           }
           if (!(p.dbg & 2))
-            epilogue_chunk<EPI, ELU, GENERAL_LOSS, STAGED, DROPOUT, DUAL, ACC2>(p, sbias, sloss_w, ri, n0 + c, raw, sv[i], yv, loss_acc, mask_words[i],
+            epilogue_chunk<EPI, ELU, GENERAL_LOSS, STAGED, DROPOUT, DUAL, ACC2, TF32>(p, sbias, sloss_w, ri, n0 + c, raw, sv[i], yv, loss_acc, mask_words[i],
                                                            stage_warp + (uint32_t)(lane * L::OUT_PITCH + 64 * i),
-                                                           taddr + (uint32_t)(BN + 32 * i));
+                                                           taddr + (uint32_t)(BN + 32 * i), KSPLIT ? (size_t)split * p.split_stride : (size_t)0);
         }
       }
       tc_fence_before();

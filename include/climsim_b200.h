@@ -48,8 +48,12 @@ enum { CSB_ACT_NONE = 0, CSB_ACT_RELU = 1, CSB_ACT_ELU = 2 /* alpha = 1 */, CSB_
 
 /* Arithmetic mode.  CSB_F32: fp32 FFMA everywhere (parity mode, <= 1e-5 relative to the fp32 CPU reference).
  * CSB_BF16: bf16 operands on the tcgen05 tensor cores with fp32 accumulation in TMEM, fp32 master weights,
- * fp32 loss / optimizer (throughput mode; tolerance stated in tests/test_mlp_gpu.py). */
-enum { CSB_F32 = 0, CSB_BF16 = 1 };
+ * fp32 loss / optimizer (throughput mode; tolerance stated in tests/test_mlp_gpu.py).
+ * CSB_TF32 (MLP family): fp32 storage everywhere, every GEMM of the step on the SAME tcgen05 kernels with kind::tf32 products (the
+ * tensor core reads sign, exponent and 10 mantissa bits of each fp32 operand, accumulates in fp32) -- the arithmetic the reference's
+ * own A100 runs used (TF32 is TensorFlow's default there; step3_prediction/step3_inference.ipynb cell 2).  Agreement with the fp32
+ * oracle ~1e-3; with operands representable in TF32 the products are exact up to summation order (tests/test_gemm_gpu.py). */
+enum { CSB_F32 = 0, CSB_BF16 = 1, CSB_TF32 = 2 };
 
 /* Loss.  MSE: mean_ij w_j (p_ij - y_ij)^2  (w = 1 is Keras 'mse', hpo_baseline_v1.py:127-129).
  * MAE: mean_ij w_j |p_ij - y_ij|           (CNN mae_adjusted through w, CNN/training/hpo_train.py:114-121). */
@@ -340,6 +344,8 @@ int  csb_gather_rows_check(void* stream);
 /* ---- kernel self-test hooks (used by tests/test_gemm_gpu.py; device pointers) ----------------------------- */
 /* C[M,N] (fp32) = A[M,K] * Bt[N,K]^T on the tcgen05 path (both operands K-major bf16, raw uint16 payloads). */
 int  csb_test_gemm_tn(const uint16_t* A, const uint16_t* Bt, float* C, int M, int N, int K, int block_n, void* stream);
+/* the same kernel on fp32 operands through tcgen05 kind::tf32 (block_n 128 or 512; K a multiple of 32) */
+int  csb_test_gemm_tn_tf32(const float* A, const float* Bt, float* C, int M, int N, int K, int block_n, void* stream);
 /* out[M,N] (bf16) = act(A[M,K] * Wt[N,K]^T + bias): one forward layer as the engine runs it.  pairs = 0: single-CTA tiles,
  * 1: cta_group::2 pairs (layers wider than 128), 2: the engine's own launch policy (pairs + the staged coalesced-store epilogue
  * for K <= 256).  For kernel micro-benchmarks (scripts/microbench_gemm.py) and tests/test_gemm_gpu.py. */

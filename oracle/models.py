@@ -63,6 +63,13 @@ class _RoundNode(torch.autograd.Function):
         return (_bf16_round(g) if ctx.bwd else g), None, None
 
 
+def _tf32_round(t: torch.Tensor) -> torch.Tensor:
+    """Round to nearest onto the TF32 grid (sign, 8 exponent bits, 10 mantissa bits): the storage rounding of the CSB_TF32 engine
+    (climsim_b200/csrc/tc_gemm.cuh::round_tf32: add half an ulp of the 13 dropped bits, then clear them)."""
+    t = t.to(torch.float32).contiguous()
+    return ((t.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
 def _mark(t: torch.Tensor, fwd: bool, bwd: bool, on: bool) -> torch.Tensor:
     return _RoundNode.apply(t, fwd, bwd) if on else t
 
@@ -153,7 +160,9 @@ class MLPRef:
         the arithmetic contract of the CSB_BF16 mode (climsim_b200/csrc/mlp_engine.cu), so that its gradients can
         be checked tightly instead of against a loose fp32 tolerance.  Without it this is plain fp32 backprop and
         must agree with autograd (tests/test_oracle_pinning.py)."""
-        rnd = _bf16_round if emulate_bf16 else (lambda t: t)
+        # ``emulate_bf16="tf32"``: the same storage points rounded onto the TF32 grid instead (the CSB_TF32 engine: fp32 storage whose
+        # tensor-core operands carry 10 mantissa bits, products exact, fp32 accumulation)
+        rnd = _tf32_round if emulate_bf16 == "tf32" else (_bf16_round if emulate_bf16 else (lambda t: t))
         with torch.no_grad():
             p = [t.detach() for t in self.params]
             n_hidden = len(self.units) + 1

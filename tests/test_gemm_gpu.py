@@ -172,3 +172,43 @@ def test_gemm_nt_uneven_splits(M, N, R, splits, cg):
     assert not torch.isnan(cs).any()
     cs_ref = B.float().sum(dim=0)
     assert (cs.sum(dim=0) - cs_ref).abs().max().item() <= 1e-3 * max(cs_ref.abs().max().item(), 1.0)
+
+
+def _tf32_trunc(t):
+    """Keep sign, exponent and the top 10 mantissa bits: what kind::tf32 reads of an fp32 word."""
+    return (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+@pytest.mark.parametrize("M,N,K,bn", [
+    (128, 128, 32, 128),        # one tile, one k-block of 32 fp32 elements
+    (1000, 640, 768, 128),
+    (333, 64, 96, 128),         # N = 64, K = three k-blocks
+    (70000, 128, 128, 128),     # both accumulator buffers, phase flips
+    (256, 256, 64, 512),        # CTA pairs
+    (1000, 640, 768, 512),      # pairs, ragged last n-block, odd m-block count
+    (65536, 768, 128, 512),     # layer-0 shape at the benchmark batch
+])
+def test_gemm_tn_tf32(M, N, K, bn):
+    """The same tcgen05 kernel on fp32 operands (kind::tf32): with operands that are exactly representable in TF32 the result is the
+    fp32 product up to the summation order; with arbitrary fp32 operands it is the product of the TRUNCATED operands (the tensor core
+    drops the low 13 mantissa bits), i.e. within 2^-10 relative of the fp32 product per term."""
+    lib, L = _lib()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    Bt = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    Cout = torch.full((M, N), float("nan"), device="cuda")
+    L.check(lib.csb_test_gemm_tn_tf32(A.data_ptr(), Bt.data_ptr(), Cout.data_ptr(), M, N, K, bn, None), "csb_test_gemm_tn_tf32")
+    torch.cuda.synchronize()
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ref_trunc = (_tf32_trunc(A).double() @ _tf32_trunc(Bt).double().t()).float()
+        ref_full = (A.double() @ Bt.double().t()).float()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    scale = ref_full.abs().max().item()
+    err_t = (Cout - ref_trunc).abs().max().item()
+    err_f = (Cout - ref_full).abs().max().item()
+    print(f"tf32 gemm {M}x{N}x{K} bn {bn}: vs truncated operands {err_t / scale:.2e}, vs fp32 product {err_f / scale:.2e}")
+    assert err_t <= 2e-6 * scale * max(1.0, (K / 128) ** 0.5), (err_t, scale)
+    assert err_f <= 2e-3 * scale, (err_f, scale)

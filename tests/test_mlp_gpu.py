@@ -579,3 +579,50 @@ def test_mlp_dropout_train_step_against_oracle_with_the_same_masks(act):
         eng.close()
     for a, b in zip(masks_by_dtype["fp32"], masks_by_dtype["bf16"]):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("units,B", [(SMALL_UNITS, 1000), ((768, 640, 512, 640, 640), 4096), (SMALL_UNITS, 77)])
+def test_train_step_tf32_mode(units, B):
+    """CSB_TF32: fp32 storage, every GEMM of the step (forward, output layer, data gradients, weight gradients with their contraction
+    over the batch split into fixed-order partials) on the tcgen05 kernels with kind::tf32 products -- the arithmetic of the
+    reference's A100 runs.  Against the fp32 oracle: predictions 2e-3 of the largest (6e-4 measured), loss 1e-3 (1e-5 measured);
+    gradients are checked tightly against the oracle with the engine's TF32 rounding points and loosely (6e-2) against plain fp32;
+    deterministic; optimizer steps refresh the rounded weight copies."""
+    from climsim_b200 import MLPEngine
+    ref, eng = _oracle(units), _engine(units, "tf32", max_batch=4096)
+    _load(eng, ref)
+    x, y = _batch(B)
+    got = eng.forward(x.cuda()).cpu().numpy()
+    want = ref(x).detach().numpy()
+    e_pred = _relmax(got, want)
+    loss = M.mse(y, ref(x))
+    loss.backward()
+    got_loss = eng.train_step(x.cuda(), y.cuda()).item()
+    e_loss = abs(got_loss - loss.item()) / abs(loss.item())
+    g_ref, g_got = _flat([p.grad for p in ref.params]), eng.get_grads_flat()
+    worst = _per_tensor(eng, g_got, g_ref, _rel_l2)
+    # the oracle with the engine's rounding points (every stored activation / dZ / weight copy on the TF32 grid): tight, because both
+    # sides then take the same side of every LeakyReLU kink -- against plain fp32 a pre-activation within 5e-4 of zero may flip, about
+    # one unit per row, which alone moves a gradient tensor by ~sqrt(4e-4) = 2e-2 relative L2
+    emu_loss, emu_grads = ref.manual_train_step(x, y, emulate_bf16="tf32")
+    e_emu_loss = abs(got_loss - emu_loss.item()) / abs(emu_loss.item())
+    worst_emu = _per_tensor(eng, g_got, _flat(emu_grads), _rel_l2)
+    print(f"tf32 mode units {units} B {B}: predictions {e_pred:.2e}, loss {e_loss:.2e}, worst gradient rel-L2 {worst:.2e} vs the fp32 oracle; "
+          f"loss {e_emu_loss:.2e}, gradients {worst_emu:.2e} vs the TF32-emulating oracle")
+    assert e_pred <= 2e-3 and e_loss <= 1e-3 and worst <= 6e-2
+    # measured: loss 1e-7 .. 8e-7; gradients 1.7e-4 / 2.4e-4 on the small network, 7.4e-3 on the full-width one at B = 4096 (a value that
+    # lands on the other side of a TF32 rounding boundary because of the fp32 summation order moves by a whole TF32 ulp, and every
+    # further layer rounds again: the bf16 engine's bound against ITS emulating oracle is 1e-2 for the same reason)
+    assert e_emu_loss <= 1e-5 and worst_emu <= (1e-3 if len(units) <= 3 else 1e-2)
+    eng.train_step(x.cuda(), y.cuda())
+    np.testing.assert_array_equal(eng.get_grads_flat(), g_got)                   # fixed-order reduction of the split partials
+    # optimizer steps refresh the transposed fp32 weight copies the forward GEMMs read
+    l_prev = got_loss
+    for _ in range(3):
+        eng.train_step(x.cuda(), y.cuda())
+        eng.apply_opt("adam_keras", lr=1e-3)
+    l_new = eng.train_step(x.cuda(), y.cuda()).item()
+    assert l_new < l_prev
+    p_after = eng.forward(x.cuda()).cpu()
+    assert abs(M.mse(y, p_after).item() - l_new) <= 2e-3 * l_new                 # forward (wt32 copies) and train step (same copies) agree
+    eng.close()
