@@ -534,6 +534,32 @@ def run_mlp_v1(ctx: Ctx) -> dict:
 
 
 # ------------------------------------------------------------------------------------------------------------------ ED
+def run_modes(ctx: Ctx) -> dict:
+    """The MLP_v1 training step of the other two arithmetic modes at the benchmark batch, beside the bf16 headline (rank 0 of a
+    single-GPU run): CSB_TF32 = the same tcgen05 kernels on fp32 storage with kind::tf32 products (the reference's A100 arithmetic),
+    CSB_F32 = the FFMA parity engine.  Device-resident, CUDA events, a few steps each."""
+    from climsim_b200 import MLPEngine
+    from climsim_b200.synthetic import synthetic_batch
+    from climsim_b200.trainer import Trainer, glorot_uniform_flat
+    B = ctx.args.batch or 65536
+    batches = [synthetic_batch(B, seed=100 + i, device="cuda") for i in range(2)]
+    out = {}
+    for dtype, steps in (("tf32", 10), ("fp32", 3)):
+        eng = MLPEngine.mlp_v1(units=UNITS, dtype=dtype, max_batch=B)
+        eng.set_params_flat(glorot_uniform_flat(eng.layer_dims, seed=0))
+        tr = Trainer(eng, rule="adam_keras", lr=1e-3)
+        for it in range(3):
+            tr.step(*batches[it % 2], return_loss=False)
+        ms, _, _ = ctx.timed(lambda it: tr.step(*batches[it % 2], return_loss=False), steps)
+        loss = float(tr.step(*batches[0]))
+        out[dtype] = {"ms_per_step": ms / steps, "columns_per_s": B * steps / (ms * 1e-3), "steps": steps, "last_loss": loss,
+                      "step_tflops": FLOP_TRAIN * B / (ms / steps * 1e-3) / 1e12}
+        eng.close()
+    out["note"] = ("tf32: fp32 storage, every GEMM on the tcgen05 kernels with kind::tf32 (weight gradient = split contraction over "
+                   "transposed operands); fp32: 64x64x16 FFMA tiles (the <= 1e-5 parity engine)")
+    return out
+
+
 def run_ed(ctx: Ctx, steps: int, warmup: int) -> dict:
     from climsim_b200 import MLPEngine
     from climsim_b200.synthetic import synthetic_batch
@@ -875,6 +901,11 @@ def main():
                     raise
         if ctx.rank == 0 and subs:
             line["workloads"] = subs
+        if ctx.world == 1 and args.extras and args.dtype == "bf16":
+            try:
+                line["arithmetic_modes"] = run_modes(ctx)
+            except Exception as e:
+                line["arithmetic_modes"] = {"error": f"{type(e).__name__}: {e}"}
     else:
         fn = {"cnn": run_cnn, "hsr": run_hsr, "ed": run_ed}[args.workload]
         sub = fn(ctx, args.steps, args.warmup)

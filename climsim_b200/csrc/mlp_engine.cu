@@ -119,7 +119,8 @@ static int launch_tn(const CUtensorMap& ta, const CUtensorMap& tb, const tc::Gem
     CSB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_set = true;
   }
-  const int tiles = (int)(ceil_div(ceil_div(p.M, tc::BM), CG) * ceil_div(p.N, BN));   // CG m-blocks per tile
+  int tiles = (int)(ceil_div(ceil_div(p.M, tc::BM), CG) * ceil_div(p.N, BN));   // CG m-blocks per tile
+  if ((VAR & tc::VAR_KSPLIT) != 0) tiles *= std::max(1, p.k_splits);              // (split, m-group, n-block) grid
   if (tiles == 0) return CSB_OK;
   int grid = std::min(tiles, sm_count / CG) * CG;
   if (p.dbg >> 16) grid = std::min(grid, (p.dbg >> 16) * CG);      // micro-benchmark: run on a few SMs only (no power capping)

@@ -439,3 +439,38 @@ def test_hsr_mlp_dropout_module_training_mode():
     net.eval()
     with torch.no_grad():
         assert (net(x.cuda()).cpu() - ref(x)).abs().max().item() <= 2e-5 * want.abs().max().item()
+
+
+def test_layernorm_mlp_tf32_mode():
+    """The HSR network (Linear -> LayerNorm -> ReLU) in the CSB_TF32 mode: GEMMs on the tensor cores with kind::tf32, the fp32 LayerNorm
+    kernels in between.  Outputs 2e-3 of the largest, gradients 6e-2 relative L2 against fp32 torch (ReLU kinks: see
+    tests/test_mlp_gpu.py::test_train_step_tf32_mode)."""
+    from climsim_b200.baseline_models import HSRMLP
+    from oracle import models as M
+    torch.manual_seed(3)
+    hidden, layers, B = 512, 2, 333
+    ref = M.HSRMLPRef(124, 128, hidden, layers)
+    with torch.no_grad():
+        for i in range(layers):
+            ln = getattr(ref, f"linear{i}")[1]
+            ln.weight.uniform_(0.5, 1.5); ln.bias.uniform_(-0.3, 0.3)
+    net = HSRMLP(124, 128, hidden_dims=hidden, layers=layers, dtype="tf32", max_batch=512)
+    net.load_reference_state_dict(ref.state_dict())
+    g = torch.Generator().manual_seed(4)
+    x, y = 0.5 * torch.randn(B, 124, generator=g), 0.3 * torch.randn(B, 128, generator=g)
+    want = ref(x)
+    ((want - y) ** 2).mean().backward()
+    got = net(x.cuda())
+    ((got - y.cuda()) ** 2).mean().backward()
+    assert (got.detach().cpu() - want.detach()).abs().max().item() <= 2e-3 * want.abs().max().item()
+    want_g = []
+    for i in range(layers):
+        seq = getattr(ref, f"linear{i}")
+        want_g += [seq[0].weight.grad.t().reshape(-1), seq[0].bias.grad, seq[1].weight.grad, seq[1].bias.grad]
+    want_g += [ref.final_linear.weight.grad.t().reshape(-1), ref.final_linear.bias.grad]
+    off, got_g = 0, net.flat.grad.cpu()
+    for i, w in enumerate(want_g):
+        part = got_g[off:off + w.numel()]
+        off += w.numel()
+        err = (part - w).norm().item() / max(w.norm().item(), 1e-12)
+        assert err <= 6e-2, (i, err)
