@@ -544,7 +544,7 @@ def run_modes(ctx: Ctx) -> dict:
     B = ctx.args.batch or 65536
     batches = [synthetic_batch(B, seed=100 + i, device="cuda") for i in range(2)]
     out = {}
-    for dtype, steps in (("tf32", 10), ("fp32", 3)):
+    for dtype, steps in (("tf32", 10), ("tf32x3", 5), ("fp32", 3)):
         eng = MLPEngine.mlp_v1(units=UNITS, dtype=dtype, max_batch=B)
         eng.set_params_flat(glorot_uniform_flat(eng.layer_dims, seed=0))
         tr = Trainer(eng, rule="adam_keras", lr=1e-3)
@@ -556,7 +556,8 @@ def run_modes(ctx: Ctx) -> dict:
                       "step_tflops": FLOP_TRAIN * B / (ms / steps * 1e-3) / 1e12}
         eng.close()
     out["note"] = ("tf32: fp32 storage, every GEMM on the tcgen05 kernels with kind::tf32 (weight gradient = split contraction over "
-                   "transposed operands); fp32: 64x64x16 FFMA tiles (the <= 1e-5 parity engine)")
+                   "transposed operands); tf32x3: the same kernels over hi/lo-split operands, three products per fp32 product "
+                   "(<= 3e-5 of the fp32 oracle); fp32: 64x64x16 FFMA tiles (the <= 1e-5 parity engine)")
     return out
 
 

@@ -15,7 +15,7 @@ MAX_LAYERS = 24
 
 OK, EINVAL, ENODEV, ENOMEM, ECUDA, ESTATE, EUNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 ACT = {"none": 0, "linear": 0, "relu": 1, "elu": 2, "leakyrelu": 3}
-DTYPE = {"fp32": 0, "f32": 0, "float32": 0, "bf16": 1, "bfloat16": 1, "tf32": 2}
+DTYPE = {"fp32": 0, "f32": 0, "float32": 0, "bf16": 1, "bfloat16": 1, "tf32": 2, "tf32x3": 3}
 LOSS = {"mse": 0, "mae": 1, "huber": 2}
 OPT = {"adam_keras": 0, "adam": 0, "adam_torch": 1, "sgd": 2, "radam": 3, "rmsprop": 4}
 FWD_NORMALIZE_IN, FWD_DENORM_OUT, FWD_KEEP_ACTIVATIONS, TRAIN_FUSED_OPT = 1, 2, 4, 8

@@ -372,6 +372,11 @@ struct csb_mlp {
   // K-major B operand of the data gradient); tr_a / tr_b = transposed copies of a layer's input and dZ ([features, batch]: the weight
   // gradient contracts over the batch)
   bool tf32 = false;
+  // CSB_TF32X3 (x3): nothing is rounded; every GEMM contracts over the tripled operands [hi | lo | hi] x [hi | hi | lo] written by
+  // split3_f32_kernel (sp_a: the A-side copy of the current layer input / dZ; the weight copies and the transposed weight-gradient
+  // operands carry their three blocks side by side), i.e. three kind::tf32 products per fp32 product: fp32-class results
+  bool x3 = false;
+  float* sp_a = nullptr;
   float* wt32[CSB_MAX_LAYERS] = {};
   float* w32r[CSB_MAX_LAYERS] = {};        // W_l rounded to the TF32 grid, [Kp, Np] (the fp32 master weights stay exact)
   float *tr_a = nullptr, *tr_b = nullptr;
@@ -441,7 +446,7 @@ static void free_all(csb_mlp* h) {
   auto F = [](void* p) { if (p) cudaFree(p); };
   F(h->params); F(h->grads); F(h->m); F(h->v); F(h->ws);
   for (int l = 0; l < CSB_MAX_LAYERS; ++l) { F(h->w16[l]); F(h->wt16[l]); F(h->wt32[l]); F(h->w32r[l]); F(h->act[l]); F(h->zbuf[l]); F(h->ln_stats[l]); F(h->amask[l]); }
-  F(h->tr_a); F(h->tr_b);
+  F(h->tr_a); F(h->tr_b); F(h->sp_a);
   F(h->xn); F(h->dz[0]); F(h->dz[1]); F(h->pred); F(h->dx_tmp);
   F(h->d_sub); F(h->d_div); F(h->d_out_scale); F(h->d_inv_out_scale); F(h->d_loss_w); F(h->d_out_mask);
   F(h->loss_partials); F(h->d_loss); F(h->d_xform);
@@ -475,7 +480,13 @@ static inline int transpose_grid(const csb_mlp* h, int64_t rows, int cols) {
 }
 static int repack_weights(csb_mlp* h, cudaStream_t st) {
   if (h->tf32) {                       // W_l [Kp, Np] -> wt32_l [Np, Kp] and w32r_l [Kp, Np], both rounded to the TF32 grid
-    for (int l = 0; l < h->L; ++l) {
+    for (int l = 0; l < h->L && h->x3; ++l) {      // [hi | hi | lo] copies: wt32_l [Np, 3 Kp] (transposed), w32r_l [Kp, 3 Np]
+      const LayerInfo& li = h->layer[l];
+      simt::split3_f32_kernel<<<transpose_grid(h, li.Kp, li.Np), 256, 0, st>>>(h->params + li.w_off, li.Np, li.Kp, li.Np, h->wt32[l], 3 * (int64_t)li.Kp, li.Kp, 1, 1, li.Kp);
+      simt::split3_f32_kernel<<<transpose_grid(h, li.Kp, li.Np), 256, 0, st>>>(h->params + li.w_off, li.Np, li.Kp, li.Np, h->w32r[l], 3 * (int64_t)li.Np, li.Np, 0, 1, li.Kp);
+      CSB_CUDA_CHECK(cudaGetLastError());
+    }
+    for (int l = 0; l < h->L && !h->x3; ++l) {
       const LayerInfo& li = h->layer[l];
       simt::transpose_f32_kernel<<<transpose_grid(h, li.Kp, li.Np), 256, 0, st>>>(h->params + li.w_off, li.Np, li.Kp, li.Np, h->wt32[l], li.Kp, 1);
       simt::transpose_f32_kernel<<<transpose_grid(h, li.Kp, li.Np), 256, 0, st>>>(h->params + li.w_off, li.Np, li.Kp, li.Np, h->w32r[l], 0, 1);
@@ -525,13 +536,22 @@ static inline uint32_t tf32_b_box(int N) { return (uint32_t)(tf32_pairs(N) ? std
 
 static int build_act_maps(csb_mlp* h, int64_t B) {
   if (h->tf32 && h->maps_B != B) {
+    const int64_t bb = round_up(B, 32);               // x3: the three [features, batch] blocks are bb columns apart
     for (int l = 0; l < h->L; ++l) {
       const LayerInfo& li = h->layer[l];
-      int rc = make_tmap_f32(&h->tm32_in[l], layer_in(h, l), li.Kp, B, li.Kp, 128);
-      if (!rc) rc = make_tmap_f32(&h->tm32_dz[l], dz32(h, l), li.Np, B, li.Np, 128);
-      // transposed copies [features, batch]: A operand rows = Kp (box 128), B operand rows = Np
-      if (!rc) rc = make_tmap_f32(&h->tm32_tra[l], h->tr_a, B, li.Kp, h->tr_ld, 128);
-      if (!rc) rc = make_tmap_f32(&h->tm32_trb[l], h->tr_b, B, li.Np, h->tr_ld, tf32_b_box(li.Np));
+      int rc;
+      if (h->x3) {
+        rc = make_tmap_f32(&h->tm32_in[l], h->sp_a, 3 * (uint64_t)li.Kp, B, 3 * (uint64_t)li.Kp, 128);
+        if (!rc) rc = make_tmap_f32(&h->tm32_dz[l], h->sp_a, 3 * (uint64_t)li.Np, B, 3 * (uint64_t)li.Np, 128);
+        if (!rc) rc = make_tmap_f32(&h->tm32_tra[l], h->tr_a, 3 * (uint64_t)bb, li.Kp, 3 * (uint64_t)bb, 128);
+        if (!rc) rc = make_tmap_f32(&h->tm32_trb[l], h->tr_b, 3 * (uint64_t)bb, li.Np, 3 * (uint64_t)bb, tf32_b_box(li.Np));
+      } else {
+        rc = make_tmap_f32(&h->tm32_in[l], layer_in(h, l), li.Kp, B, li.Kp, 128);
+        if (!rc) rc = make_tmap_f32(&h->tm32_dz[l], dz32(h, l), li.Np, B, li.Np, 128);
+        // transposed copies [features, batch]: A operand rows = Kp (box 128), B operand rows = Np
+        if (!rc) rc = make_tmap_f32(&h->tm32_tra[l], h->tr_a, B, li.Kp, h->tr_ld, 128);
+        if (!rc) rc = make_tmap_f32(&h->tm32_trb[l], h->tr_b, B, li.Np, h->tr_ld, tf32_b_box(li.Np));
+      }
       if (rc) return rc;
     }
     h->maps_B = B;
@@ -595,7 +615,8 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
   *out = nullptr;
   CSB_REQUIRE(cfg->n_layers >= 1 && cfg->n_layers <= CSB_MAX_LAYERS, CSB_EINVAL, "n_layers %d out of range", cfg->n_layers);
   CSB_REQUIRE(cfg->in_dim >= 1 && cfg->max_batch >= 1, CSB_EINVAL, "in_dim / max_batch must be positive");
-  CSB_REQUIRE(cfg->dtype == CSB_F32 || cfg->dtype == CSB_BF16 || cfg->dtype == CSB_TF32, CSB_EINVAL, "unknown dtype %d", cfg->dtype);
+  CSB_REQUIRE(cfg->dtype == CSB_F32 || cfg->dtype == CSB_BF16 || cfg->dtype == CSB_TF32 || cfg->dtype == CSB_TF32X3, CSB_EINVAL, "unknown dtype %d",
+              cfg->dtype);
   CSB_REQUIRE(cfg->loss >= CSB_LOSS_MSE && cfg->loss <= CSB_LOSS_HUBER, CSB_EINVAL, "unknown loss %d", cfg->loss);
   int sm = 0, maj = 0, min = 0;
   int rc = csb_device_info(&sm, &maj, &min, nullptr);
@@ -621,7 +642,8 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
   h->L = cfg->n_layers;
   h->sm_count = sm;
   h->bf16 = cfg->dtype == CSB_BF16;
-  h->tf32 = cfg->dtype == CSB_TF32;            // fp32 storage (every `!bf16` path below), GEMMs on the tensor cores
+  h->tf32 = cfg->dtype == CSB_TF32 || cfg->dtype == CSB_TF32X3;      // fp32 storage (every `!bf16` path below), GEMMs on the tensor cores
+  h->x3 = cfg->dtype == CSB_TF32X3;
   // opt-in (CSB_CONCURRENT_WGRAD=1): measured 0.896 against 0.875-0.89 ms/step for the plain in-order chain on one B200 -- the
   // cross-stream dependencies cost the programmatic-launch overlap that the single stream has, and both kernels want every SM
   if (h->bf16 && getenv("CSB_CONCURRENT_WGRAD") != nullptr) {         // side stream for the weight-gradient GEMMs (see csb_mlp)
@@ -720,14 +742,16 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
       const LayerInfo& li = h->layer[l];
       if (l + 1 < h->L && li.act == CSB_ACT_ELU) { free_all(h); delete h; set_last_error("CSB_TF32: ELU hidden layers are not instantiated"); return CSB_EUNSUPPORTED; }
       max_dim = std::max(max_dim, std::max(li.Kp, li.Np));
-      CKA(h->wt32[l], (size_t)li.Kp * li.Np * 4);
-      CKA(h->w32r[l], (size_t)li.Kp * li.Np * 4);
-      CK(make_tmap_f32(&h->tm32_wt[l], h->wt32[l], li.Kp, li.Np, li.Kp, tf32_b_box(li.Np)));
-      CK(make_tmap_f32(&h->tm32_w[l], h->w32r[l], li.Np, li.Kp, li.Np, tf32_b_box(li.Kp)));
+      const size_t kx = h->x3 ? 3 : 1;
+      CKA(h->wt32[l], kx * li.Kp * li.Np * 4);
+      CKA(h->w32r[l], kx * li.Kp * li.Np * 4);
+      CK(make_tmap_f32(&h->tm32_wt[l], h->wt32[l], kx * li.Kp, li.Np, kx * li.Kp, tf32_b_box(li.Np)));
+      CK(make_tmap_f32(&h->tm32_w[l], h->w32r[l], kx * li.Np, li.Kp, kx * li.Np, tf32_b_box(li.Kp)));
     }
     h->tr_ld = h->cap;                  // a multiple of 128 floats
-    CKA(h->tr_a, (size_t)max_dim * h->tr_ld * 4);
-    CKA(h->tr_b, (size_t)max_dim * h->tr_ld * 4);
+    CKA(h->tr_a, (size_t)(h->x3 ? 3 : 1) * max_dim * h->tr_ld * 4);
+    CKA(h->tr_b, (size_t)(h->x3 ? 3 : 1) * max_dim * h->tr_ld * 4);
+    if (h->x3) CKA(h->sp_a, (size_t)3 * max_dim * h->cap * 4);
   }
   CK(csb_mlp_set_norm(h, nullptr, nullptr, nullptr, nullptr));
 #undef CK
@@ -1006,7 +1030,7 @@ static int run_normalize_raw(csb_mlp* h, const float* x, int64_t B, int apply, c
 
 static int run_normalize(csb_mlp* h, const float* x, int64_t B, int apply, cudaStream_t st) {
   int rc = run_normalize_raw(h, x, B, apply, st);
-  if (rc || !h->tf32) return rc;
+  if (rc || !h->tf32 || h->x3) return rc;
   // CSB_TF32: the first GEMM's A operand rounded (to nearest) onto the TF32 grid, like every other stored tensor of this mode
   simt::transpose_f32_kernel<<<transpose_grid(h, B, h->in_p), 256, 0, st>>>(reinterpret_cast<const float*>(h->xn), h->in_p, B, h->in_p,
                                                                           reinterpret_cast<float*>(h->xn), 0, 1);
@@ -1032,6 +1056,11 @@ static int run_hidden_forward(csb_mlp* h, int64_t B, cudaStream_t st, bool train
     } else if (h->tf32) {
       tc::GemmParams p = {};
       p.M = (int)B; p.N = li.Np; p.K = li.Kp; p.act = gemm_act; p.alpha = li.alpha; p.head_relu_from = -1;
+      if (h->x3) {
+        simt::split3_f32_kernel<<<transpose_grid(h, B, li.Kp), 256, 0, st>>>(reinterpret_cast<const float*>(layer_in(h, l)), li.Kp, B, li.Kp, h->sp_a, 3 * (int64_t)li.Kp, li.Kp, 0, 0, B);
+        CSB_CUDA_CHECK(cudaGetLastError());
+        p.K = 3 * li.Kp; p.tf32_exact_store = 1;
+      }
       p.bias = h->params + li.b_off; p.out = li.ln ? h->zbuf[l] : h->act[l]; p.ld_out = li.Np;
       int rc = launch_tn_tf32<tc::EPI_BIAS_ACT>(h->tm32_in[l], h->tm32_wt[l], p, h->sm_count, st);
       if (rc) return rc;
@@ -1101,6 +1130,11 @@ static int run_head(csb_mlp* h, int64_t B, int fused_loss, const float* y, float
     // predictions (fp32) straight from the head epilogue; loss and dL/dz follow in head_grad_kernel as in the fp32 mode
     tc::GemmParams p = {};
     p.M = (int)B; p.N = li.Np; p.K = li.Kp; p.act = li.act; p.alpha = li.alpha; p.head_relu_from = h->cfg.head_relu_from;
+    if (h->x3) {
+      simt::split3_f32_kernel<<<transpose_grid(h, B, li.Kp), 256, 0, st>>>(reinterpret_cast<const float*>(layer_in(h, l)), li.Kp, B, li.Kp, h->sp_a, 3 * (int64_t)li.Kp, li.Kp, 0, 0, B);
+      CSB_CUDA_CHECK(cudaGetLastError());
+      p.K = 3 * li.Kp;
+    }
     p.bias = h->params + li.b_off; p.out_dim = h->out_dim;
     p.pred = h->pred; p.ld_pred = h->out_p;
     p.out_mask = h->has_mask ? h->d_out_mask : nullptr;
@@ -1255,7 +1289,7 @@ static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st,
   int64_t max_len = 4;
   const bool conc = h->bf16 && h->side_on && !h->prof_on;      // per-kind profiling wants the launches back to back on one stream
   h->pending_tail = false;
-  if (h->tf32) {
+  if (h->tf32 && !h->x3) {
     // the output layer's dL/dz (written in full fp32 by the loss kernels) onto the TF32 grid, like every dZ this mode stores: all of its
     // consumers (bias column sums, weight gradient, data gradient) then see one and the same value
     const LayerInfo& lo = h->layer[h->L - 1];
@@ -1321,11 +1355,17 @@ static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st,
       } else if (h->tf32) {
         // dW_l = in_l^T . dZ_l contracts over the batch: both operands transposed to [features, batch] (K-major for tcgen05), the
         // contraction cut into `splits` ranges whose fp32 partial products are summed in a fixed order with every other gradient
-        simt::transpose_f32_kernel<<<transpose_grid(h, B, li.Kp), 256, 0, ws>>>(reinterpret_cast<const float*>(layer_in(h, l)), li.Kp, B, li.Kp, h->tr_a, h->tr_ld, 1);
-        simt::transpose_f32_kernel<<<transpose_grid(h, B, li.Np), 256, 0, ws>>>(dz32(h, l), li.Np, B, li.Np, h->tr_b, h->tr_ld, 1);
+        const int64_t bb = round_up(B, 32);
+        if (h->x3) {
+          simt::split3_f32_kernel<<<transpose_grid(h, bb, li.Kp), 256, 0, ws>>>(reinterpret_cast<const float*>(layer_in(h, l)), li.Kp, B, li.Kp, h->tr_a, 3 * bb, bb, 1, 0, bb);
+          simt::split3_f32_kernel<<<transpose_grid(h, bb, li.Np), 256, 0, ws>>>(dz32(h, l), li.Np, B, li.Np, h->tr_b, 3 * bb, bb, 1, 1, bb);
+        } else {
+          simt::transpose_f32_kernel<<<transpose_grid(h, B, li.Kp), 256, 0, ws>>>(reinterpret_cast<const float*>(layer_in(h, l)), li.Kp, B, li.Kp, h->tr_a, h->tr_ld, 1);
+          simt::transpose_f32_kernel<<<transpose_grid(h, B, li.Np), 256, 0, ws>>>(dz32(h, l), li.Np, B, li.Np, h->tr_b, h->tr_ld, 1);
+        }
         CSB_CUDA_CHECK(cudaGetLastError());
         tc::GemmParams p = {};
-        p.M = li.Kp; p.N = li.Np; p.K = (int)round_up(B, 32);                 // columns past B are zero-filled by TMA
+        p.M = li.Kp; p.N = li.Np; p.K = (int)((h->x3 ? 3 : 1) * bb);          // columns past B are zero (TMA fill / split3's padding)
         const int num_kb = p.K / 32;
         const int want = std::max(1, std::min(li.max_w_splits, num_kb));
         const int kps = (int)ceil_div(num_kb, want);
@@ -1391,6 +1431,11 @@ static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st,
         p.out = dz32(h, l - 1); p.ld_out = lp.Np;
         p.saved = reinterpret_cast<const __nv_bfloat16*>(h->act[l - 1]); p.ld_saved = lp.Np;      // fp32 in this mode (VAR_TF32 epilogue)
         p.dgrad_scale = h->drop_live ? 1.f / (1.f - h->dropout) : 0.f;
+        if (h->x3) {
+          simt::split3_f32_kernel<<<transpose_grid(h, B, li.Np), 256, 0, st>>>(dz32(h, l), li.Np, B, li.Np, h->sp_a, 3 * (int64_t)li.Np, li.Np, 0, 0, B);
+          CSB_CUDA_CHECK(cudaGetLastError());
+          p.K = 3 * li.Np; p.tf32_exact_store = 1;
+        }
         int rc = launch_tn_tf32<tc::EPI_DGRAD>(h->tm32_dz[l], h->tm32_w[l], p, h->sm_count, st);
         if (rc) return rc;
       } else {

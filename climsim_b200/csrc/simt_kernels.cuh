@@ -1091,6 +1091,57 @@ __global__ void __launch_bounds__(256) transpose_f32_kernel(const float* __restr
   }
 }
 
+// CSB_TF32X3 operands: dst holds THREE copies of src (transposed if `transpose`), `blk` elements apart along dst's column (contraction)
+// axis:  A-side [hi | lo | hi],  B-side (mode_b) [hi | hi | lo],  hi = x rounded to the TF32 grid, lo = (x - hi) rounded to it again.
+// One GEMM over the tripled contraction then sums  hi.hi + lo.hi + hi.lo  -- the fp32 product up to the dropped lo.lo term and the
+// rounding of lo, ~2^-22 relative each and unbiased.  transpose: dst columns rows..rows_pad-1 of every
+// copy are written as zeros (the contraction is cut into 32-element blocks).
+__global__ void __launch_bounds__(256) split3_f32_kernel(const float* __restrict__ src, int64_t ld_src, int64_t rows, int cols,
+                                                         float* __restrict__ dst, int64_t ld_dst, int64_t blk, int transpose, int mode_b,
+                                                         int64_t rows_pad) {
+  __shared__ float t[32][33];
+  const int64_t rows_all = transpose ? rows_pad : rows;
+  const int64_t tiles_c = (cols + 31) / 32, tiles_r = (rows_all + 31) / 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int64_t tile = blockIdx.x; tile < tiles_c * tiles_r; tile += gridDim.x) {
+    const int64_t r0 = (tile / tiles_c) * 32;
+    const int c0 = (int)(tile % tiles_c) * 32;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t r = r0 + ty + 8 * j;
+      t[ty + 8 * j][tx] = (r < rows && c0 + tx < cols) ? src[r * ld_src + c0 + tx] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float x;
+      int64_t o;
+      bool ok;
+      if (transpose) {
+        const int c = c0 + ty + 8 * j;
+        x = t[tx][ty + 8 * j];
+        ok = c < cols && r0 + tx < rows_all;
+        o = (int64_t)c * ld_dst + r0 + tx;
+      } else {
+        const int64_t r = r0 + ty + 8 * j;
+        x = t[ty + 8 * j][tx];
+        ok = r < rows && c0 + tx < cols;
+        o = r * ld_dst + c0 + tx;
+      }
+      if (ok) {
+        // both parts ROUNDED to nearest onto the TF32 grid (the tensor core then reads them exactly): truncating instead leaves a
+        // one-sided 2^-20 error per product that seven chained layers add up to 1e-5
+        const float hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+        const float lo = __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xFFFFE000u);
+        dst[o] = hi;
+        dst[o + blk] = mode_b ? hi : lo;
+        dst[o + 2 * blk] = mode_b ? lo : hi;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // the same keep decisions on an fp32 buffer (element e belongs to group e / 8, LCG step e % 8), so that the CSB_F32 and CSB_BF16 engines
 // drop the same elements for the same (seed, step, layer)
 __global__ void __launch_bounds__(256)

@@ -93,6 +93,8 @@ struct GemmParams {
   // contraction runs over the batch)
   int k_splits;
   size_t split_stride;
+  int tf32_exact_store;        // VAR_TF32: 1 = store the fp32 results as they are (CSB_TF32X3: operands are split into hi / lo copies
+                               // elsewhere); 0 = round them onto the TF32 grid (CSB_TF32)
   // EPI_HEAD_LOSS / EPI_HEAD_OUT
   const float* y;              // targets [M, ld_y]
   int ld_y;
@@ -518,8 +520,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
       for (int j = 0; j < 32; ++j) v[j] = 0.f;
     }
     if constexpr (F32IO) {
+      if (!p.tf32_exact_store) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+        for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+      }
       if (st_ok) store_f32x32(out32, v);
     }
     else if constexpr (STAGED) stage_bf16x32(stage_addr, v); else if (st_ok) store_bf16x32_global(out16, v);
@@ -585,8 +589,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
       for (int j = 0; j < 32; ++j) v[j] = 0.f;
     }
     if constexpr (F32IO) {
+      if (!p.tf32_exact_store) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+        for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+      }
       if (st_ok) store_f32x32(out32, v);
     }
     else if constexpr (STAGED) stage_bf16x32(stage_addr, v); else if (st_ok) store_bf16x32_global(out16, v);
