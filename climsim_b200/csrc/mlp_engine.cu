@@ -309,6 +309,7 @@ struct LayerInfo {
   // split-K workspace
   size_t ws_w_off, ws_b_off;
   int max_w_splits, b_splits;
+  int split_cap = 64;      // most weight-gradient splits a step uses (the fused optimizer walks a tile's partials serially)
   int nt_block_n;
   int nt_cg;                   // CTAs per weight-gradient tile (2: cta_group::2 pairs)
   bool nt_narrow;              // half-width last n-block: uneven split counts (NtParams.rb_per_split_narrow)
@@ -675,6 +676,10 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
     const int tiles = nt_m_tiles(li.Kp, li.nt_cg) * (int)ceil_div(li.Np, li.nt_block_n);
     // one wave of CTAs, but at most 64 partials: the reduction walks a tile's partials serially
     li.max_w_splits = h->bf16 ? std::max(1, std::min(64, (sm / li.nt_cg) / tiles)) : 1;
+    // a layer that is ONE 128 x 128 tile (ED's 115 -> 57 -> 28 -> 5 -> ... chain) gets a split per SM: its launch is bound by how many SMs
+    // pull the two [B, <= 128] operands out of HBM, not by the partials (64 KB each; the fused optimizer walks them in 8-row items)
+    li.split_cap = (h->bf16 && tiles == 1 && li.Kp <= 128 && li.Np <= 128 && getenv("CSB_NO_WIDE_SPLITS") == nullptr) ? sm : 64;
+    if (li.split_cap > 64) li.max_w_splits = sm;
     if (h->tf32) {                    // split contraction of the TF32 weight gradient: one wave of 256 x 256 pair tiles (or 128 x 128 tiles)
       const bool pr = tf32_pairs(li.Np);
       const int t32 = pr ? (int)(ceil_div(ceil_div(li.Kp, 128), 2) * ceil_div(li.Np, 256)) : (int)(ceil_div(li.Kp, 128) * ceil_div(li.Np, 128));
@@ -1226,7 +1231,7 @@ static inline int wgrad_splits(const csb_mlp* h, int l, int64_t B, int* rb_per_s
   const LayerInfo& li = h->layer[l];
   if (tail && l == h->L - 1) return tail_grid(h, B);               // one partial per CTA of tail_kernel
   const int num_rb = (int)ceil_div(B, 64);
-  int splits = std::max(1, std::min(std::min(li.max_w_splits, 64), num_rb));      // (slots beyond 64 exist for tail_kernel only)
+  int splits = std::max(1, std::min(std::min(li.max_w_splits, li.split_cap), num_rb));      // (slots beyond the cap exist for tail_kernel only)
   const int rps = (int)ceil_div(num_rb, splits);
   if (rb_per_split) *rb_per_split = rps;
   splits = (int)ceil_div(num_rb, rps);
