@@ -280,3 +280,39 @@ def test_conv1d_same_and_activations_against_torch_functional():
     h = torch.nn.functional.leaky_relu(h @ ref.params[2] + ref.params[3], 0.15)
     want = torch.cat([h @ ref.params[4] + ref.params[5], torch.relu(h @ ref.params[6] + ref.params[7])], dim=1)
     torch.testing.assert_close(ref(x), want, rtol=1e-5, atol=1e-6)
+
+
+def test_tf32_rounding_of_the_emulating_oracle():
+    """``_tf32_round`` (the storage rounding of the CSB_TF32 engine restated): results have at most 10 explicit mantissa bits, the error
+    is at most half a TF32 ulp (2^-11 relative), the map is idempotent and odd, exactly representable values are fixed points."""
+    g = torch.Generator().manual_seed(0)
+    x = torch.cat([torch.randn(4096, generator=g) * 10.0 ** torch.randint(-6, 6, (4096,), generator=g).float(),
+                   torch.tensor([0.0, 1.0, -1.0, 1.0 + 2.0 ** -10, 1.0 + 2.0 ** -11, 3.0, 0.15])])
+    r = M._tf32_round(x)
+    assert ((r.view(torch.int32) & 0x1FFF) == 0).all()                         # low 13 mantissa bits cleared
+    nz = x != 0
+    assert ((r[nz] - x[nz]).abs() / x[nz].abs()).max().item() <= 2.0 ** -11 + 1e-9
+    assert torch.equal(M._tf32_round(r), r)
+    assert torch.equal(M._tf32_round(-x), -r)
+    assert r[-7:-4].tolist() == [0.0, 1.0, -1.0] and r[-4].item() == 1.0 + 2.0 ** -10 and r[-3].item() == 1.0 + 2.0 ** -10   # tie rounds up
+
+
+def test_dropout_masks_of_ones_change_nothing_and_scale_like_torch_dropout():
+    """The explicit ``masks=`` path of the oracles (the engine's keep decisions replayed): multipliers of 1 reproduce the dropout-free
+    forward; a 0 / (1/(1-p)) mask is ``torch.nn.functional.dropout``'s own arithmetic (inverted dropout) for the same keep pattern,
+    placed where the reference puts it -- behind LayerNorm and before the ReLU in hsr.MLP (hsr.py:20-25)."""
+    torch.manual_seed(1)
+    ref = M.MLPRef(units=(32, 16), seed=2)
+    x = torch.randn(7, 124)
+    ones = [torch.ones(7, n) for n in (32, 16, 128)]
+    assert torch.equal(ref.forward(x, masks=ones), ref.forward(x))
+    h = M.HSRMLPRef(124, 128, 24, 2)
+    assert torch.allclose(h(x, masks=[torch.ones(7, 24)] * 2), h(x), atol=0, rtol=0)
+    keep = (torch.rand(7, 24) > 0.3).float()
+    lin, ln = h.linear0[0], h.linear0[1]
+    u = ln(lin(x))
+    want = torch.relu(u * keep / 0.7)                                          # Dropout(p=0.3) with this keep pattern, then ReLU
+    got = torch.relu(h.linear0[1](h.linear0[0](x)) * (keep / 0.7))
+    assert torch.allclose(got, want)
+    full = h(x, masks=[keep / 0.7, torch.ones(7, 24)])
+    assert torch.allclose(full, h.final_linear(torch.relu(h.linear1(want))), atol=1e-6)
