@@ -378,6 +378,14 @@ struct csb_mlp {
   // operands carry their three blocks side by side), i.e. three kind::tf32 products per fp32 product: fp32-class results
   bool x3 = false;
   float* sp_a = nullptr;
+  // CSB_TF32 (not x3): persistent [features, batch] copies written by the GEMM epilogues themselves (GemmParams.out_t): xn^T, act_l^T,
+  // dZ^T (ping-pong like dz).  A copy the epilogue could not write (LayerNorm layers: the activation comes from ln_fwd and dZ from
+  // ln_bwd; dropout: the activation changes after the GEMM; the output layer's dZ) is produced by transpose_f32_kernel into the SAME buffer.
+  float* xn_t = nullptr;
+  float* act_t[CSB_MAX_LAYERS] = {};
+  float* dz_t[2] = {nullptr, nullptr};
+  bool act_t_valid[CSB_MAX_LAYERS] = {};
+  bool dz_t_valid = false;                  // the transposed copy of the dZ the backward chain currently holds is valid
   float* wt32[CSB_MAX_LAYERS] = {};
   float* w32r[CSB_MAX_LAYERS] = {};        // W_l rounded to the TF32 grid, [Kp, Np] (the fp32 master weights stay exact)
   float *tr_a = nullptr, *tr_b = nullptr;
@@ -447,7 +455,8 @@ static void free_all(csb_mlp* h) {
   auto F = [](void* p) { if (p) cudaFree(p); };
   F(h->params); F(h->grads); F(h->m); F(h->v); F(h->ws);
   for (int l = 0; l < CSB_MAX_LAYERS; ++l) { F(h->w16[l]); F(h->wt16[l]); F(h->wt32[l]); F(h->w32r[l]); F(h->act[l]); F(h->zbuf[l]); F(h->ln_stats[l]); F(h->amask[l]); }
-  F(h->tr_a); F(h->tr_b); F(h->sp_a);
+  F(h->tr_a); F(h->tr_b); F(h->sp_a); F(h->xn_t); F(h->dz_t[0]); F(h->dz_t[1]);
+  for (int l = 0; l < CSB_MAX_LAYERS; ++l) F(h->act_t[l]);
   F(h->xn); F(h->dz[0]); F(h->dz[1]); F(h->pred); F(h->dx_tmp);
   F(h->d_sub); F(h->d_div); F(h->d_out_scale); F(h->d_inv_out_scale); F(h->d_loss_w); F(h->d_out_mask);
   F(h->loss_partials); F(h->d_loss); F(h->d_xform);
@@ -550,8 +559,8 @@ static int build_act_maps(csb_mlp* h, int64_t B) {
         rc = make_tmap_f32(&h->tm32_in[l], layer_in(h, l), li.Kp, B, li.Kp, 128);
         if (!rc) rc = make_tmap_f32(&h->tm32_dz[l], dz32(h, l), li.Np, B, li.Np, 128);
         // transposed copies [features, batch]: A operand rows = Kp (box 128), B operand rows = Np
-        if (!rc) rc = make_tmap_f32(&h->tm32_tra[l], h->tr_a, B, li.Kp, h->tr_ld, 128);
-        if (!rc) rc = make_tmap_f32(&h->tm32_trb[l], h->tr_b, B, li.Np, h->tr_ld, tf32_b_box(li.Np));
+        if (!rc) rc = make_tmap_f32(&h->tm32_tra[l], l == 0 ? h->xn_t : h->act_t[l - 1], B, li.Kp, h->tr_ld, 128);
+        if (!rc) rc = make_tmap_f32(&h->tm32_trb[l], h->dz_t[(h->L - 1 - l) & 1], B, li.Np, h->tr_ld, tf32_b_box(li.Np));
       }
       if (rc) return rc;
     }
@@ -695,7 +704,7 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
       li.max_w_splits = S;
     }
     if (h->bf16 && l == h->L - 1 && li.Kp == 128 && li.Np == 128) li.max_w_splits = std::max(li.max_w_splits, sm);   // tail_kernel: one partial per CTA
-    li.b_splits = h->bf16 ? li.max_w_splits * nt_m_tiles(li.Kp, li.nt_cg) : 32;
+    li.b_splits = h->bf16 ? li.max_w_splits * nt_m_tiles(li.Kp, li.nt_cg) : (h->tf32 ? 128 : 32);
     li.ws_w_off = ws_off; ws_off += (size_t)li.max_w_splits * li.Kp * li.Np;
     li.ws_b_off = ws_off; ws_off += (size_t)li.b_splits * li.Np;
     li.ws_g_off = ws_off; if (li.ln) ws_off += (size_t)std::max(32, 2 * sm) * 2 * li.Np;      // one partial pair per block of ln_bwd_bf16_kernel
@@ -717,7 +726,7 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
   CKA(h->xn, (size_t)h->cap * h->in_p * es);
   for (int l = 0; l + 1 < h->L; ++l) {
     CKA(h->act[l], (size_t)h->cap * h->layer[l].Np * es);
-    if (h->bf16 && !h->layer[l].ln && (h->layer[l].act == CSB_ACT_RELU || h->layer[l].act == CSB_ACT_LEAKYRELU) &&
+    if ((h->bf16 || (h->tf32 && !h->x3)) && !h->layer[l].ln && (h->layer[l].act == CSB_ACT_RELU || h->layer[l].act == CSB_ACT_LEAKYRELU) &&
         getenv("CSB_NO_MASK") == nullptr)
       CKA(h->amask[l], (size_t)h->cap * (h->layer[l].Np / 32) * 4);
     if (h->layer[l].ln) {
@@ -754,9 +763,16 @@ int csb_mlp_create(const csb_mlp_cfg* cfg, csb_mlp** out) {
       CK(make_tmap_f32(&h->tm32_w[l], h->w32r[l], kx * li.Np, li.Kp, kx * li.Np, tf32_b_box(li.Kp)));
     }
     h->tr_ld = h->cap;                  // a multiple of 128 floats
-    CKA(h->tr_a, (size_t)(h->x3 ? 3 : 1) * max_dim * h->tr_ld * 4);
-    CKA(h->tr_b, (size_t)(h->x3 ? 3 : 1) * max_dim * h->tr_ld * 4);
-    if (h->x3) CKA(h->sp_a, (size_t)3 * max_dim * h->cap * 4);
+    if (h->x3) {
+      CKA(h->tr_a, (size_t)3 * max_dim * h->tr_ld * 4);
+      CKA(h->tr_b, (size_t)3 * max_dim * h->tr_ld * 4);
+      CKA(h->sp_a, (size_t)3 * max_dim * h->cap * 4);
+    } else {
+      CKA(h->xn_t, (size_t)h->in_p * h->tr_ld * 4);
+      for (int l = 0; l + 1 < h->L; ++l) CKA(h->act_t[l], (size_t)h->layer[l].Np * h->tr_ld * 4);
+      CKA(h->dz_t[0], (size_t)h->max_np * h->tr_ld * 4);
+      CKA(h->dz_t[1], (size_t)h->max_np * h->tr_ld * 4);
+    }
   }
   CK(csb_mlp_set_norm(h, nullptr, nullptr, nullptr, nullptr));
 #undef CK
@@ -1039,6 +1055,7 @@ static int run_normalize(csb_mlp* h, const float* x, int64_t B, int apply, cudaS
   // CSB_TF32: the first GEMM's A operand rounded (to nearest) onto the TF32 grid, like every other stored tensor of this mode
   simt::transpose_f32_kernel<<<transpose_grid(h, B, h->in_p), 256, 0, st>>>(reinterpret_cast<const float*>(h->xn), h->in_p, B, h->in_p,
                                                                           reinterpret_cast<float*>(h->xn), 0, 1);
+  simt::transpose_f32_kernel<<<transpose_grid(h, B, h->in_p), 256, 0, st>>>(reinterpret_cast<const float*>(h->xn), h->in_p, B, h->in_p, h->xn_t, h->tr_ld, 1);
   CSB_CUDA_CHECK(cudaGetLastError());
   return CSB_OK;
 }
@@ -1067,6 +1084,11 @@ static int run_hidden_forward(csb_mlp* h, int64_t B, cudaStream_t st, bool train
         p.K = 3 * li.Kp; p.tf32_exact_store = 1;
       }
       p.bias = h->params + li.b_off; p.out = li.ln ? h->zbuf[l] : h->act[l]; p.ld_out = li.Np;
+      h->act_t_valid[l] = false;
+      if (!h->x3) {
+        p.mask_out = h->amask[l]; p.ld_mask = (int)h->cap;
+        if (!li.ln && !drop) { p.out_t = h->act_t[l]; p.ld_out_t = h->tr_ld; h->act_t_valid[l] = true; }
+      }
       int rc = launch_tn_tf32<tc::EPI_BIAS_ACT>(h->tm32_in[l], h->tm32_wt[l], p, h->sm_count, st);
       if (rc) return rc;
     } else {
@@ -1300,6 +1322,7 @@ static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st,
     const LayerInfo& lo = h->layer[h->L - 1];
     simt::transpose_f32_kernel<<<transpose_grid(h, B, lo.Np), 256, 0, st>>>(dz32(h, h->L - 1), lo.Np, B, lo.Np, dz32(h, h->L - 1), 0, 1);
     CSB_CUDA_CHECK(cudaGetLastError());
+    h->dz_t_valid = false;
   }
   for (int l = h->L - 1; l >= 0; --l) {
     const LayerInfo& li = h->layer[l];
@@ -1365,8 +1388,11 @@ static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st,
           simt::split3_f32_kernel<<<transpose_grid(h, bb, li.Kp), 256, 0, ws>>>(reinterpret_cast<const float*>(layer_in(h, l)), li.Kp, B, li.Kp, h->tr_a, 3 * bb, bb, 1, 0, bb);
           simt::split3_f32_kernel<<<transpose_grid(h, bb, li.Np), 256, 0, ws>>>(dz32(h, l), li.Np, B, li.Np, h->tr_b, 3 * bb, bb, 1, 1, bb);
         } else {
-          simt::transpose_f32_kernel<<<transpose_grid(h, B, li.Kp), 256, 0, ws>>>(reinterpret_cast<const float*>(layer_in(h, l)), li.Kp, B, li.Kp, h->tr_a, h->tr_ld, 1);
-          simt::transpose_f32_kernel<<<transpose_grid(h, B, li.Np), 256, 0, ws>>>(dz32(h, l), li.Np, B, li.Np, h->tr_b, h->tr_ld, 1);
+          // the [features, batch] copies the epilogues did not write themselves
+          if (l > 0 && !h->act_t_valid[l - 1])
+            simt::transpose_f32_kernel<<<transpose_grid(h, B, li.Kp), 256, 0, ws>>>(reinterpret_cast<const float*>(layer_in(h, l)), li.Kp, B, li.Kp, h->act_t[l - 1], h->tr_ld, 1);
+          if (!h->dz_t_valid)
+            simt::transpose_f32_kernel<<<transpose_grid(h, B, li.Np), 256, 0, ws>>>(dz32(h, l), li.Np, B, li.Np, h->dz_t[(h->L - 1 - l) & 1], h->tr_ld, 1);
         }
         CSB_CUDA_CHECK(cudaGetLastError());
         tc::GemmParams p = {};
@@ -1441,7 +1467,16 @@ static int run_backward_chain(csb_mlp* h, int64_t B, float* dx, cudaStream_t st,
           CSB_CUDA_CHECK(cudaGetLastError());
           p.K = 3 * li.Np; p.tf32_exact_store = 1;
         }
-        int rc = launch_tn_tf32<tc::EPI_DGRAD>(h->tm32_dz[l], h->tm32_w[l], p, h->sm_count, st);
+        // dZ_{l-1} also lands transposed, ready for its weight gradient -- unless a LayerNorm backward still has to turn du into dz
+        h->dz_t_valid = !h->x3 && !lp.ln;
+        if (h->dz_t_valid) { p.out_t = h->dz_t[(h->L - l) & 1]; p.ld_out_t = h->tr_ld; }
+        int rc;
+        if (!h->x3 && h->amask[l - 1] != nullptr && !h->drop_live) {      // act' from the sign bits: no fp32 activation re-read
+          p.mask_in = h->amask[l - 1]; p.ld_mask = (int)h->cap;
+          rc = launch_tn_tf32<tc::EPI_DGRAD_MASK>(h->tm32_dz[l], h->tm32_w[l], p, h->sm_count, st);
+        } else {
+          rc = launch_tn_tf32<tc::EPI_DGRAD>(h->tm32_dz[l], h->tm32_w[l], p, h->sm_count, st);
+        }
         if (rc) return rc;
       } else {
         simt::SgemmParams p = {};

@@ -93,6 +93,10 @@ struct GemmParams {
   // contraction runs over the batch)
   int k_splits;
   size_t split_stride;
+  // VAR_TF32: optional second, TRANSPOSED copy of the stored tile, out_t[col * ld_out_t + row] (the weight gradient of this mode
+  // contracts over the batch and wants [features, batch] operands; a warp's 32 rows make every such store one 128-byte line)
+  float* out_t;
+  int64_t ld_out_t;
   int tf32_exact_store;        // VAR_TF32: 1 = store the fp32 results as they are (CSB_TF32X3: operands are split into hi / lo copies
                                // elsewhere); 0 = round them onto the TF32 grid (CSB_TF32)
   // EPI_HEAD_LOSS / EPI_HEAD_OUT
@@ -466,6 +470,20 @@ __device__ __forceinline__ uint32_t drop_mix32(uint32_t x) {
 // every product downwards by ~2^-11 and adds up over a chain of layers; tensors that will be tensor-core operands again are therefore
 // stored already rounded (the truncation is then exact)
 __device__ __forceinline__ float round_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+// F32IO store of one 32-column step: rounded onto the TF32 grid unless the caller keeps exact values, plus the optional transposed copy
+__device__ __forceinline__ void store_tf32_step(const GemmParams& p, const RowInfo& ri, int gcol, float (&v)[32], bool st_ok) {
+  if (!p.tf32_exact_store) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+  }
+  if (!st_ok) return;
+  store_f32x32(reinterpret_cast<float*>(p.out) + (size_t)ri.grow * p.ld_out + gcol, v);
+  if (p.out_t != nullptr) {
+    float* t = p.out_t + (size_t)gcol * (size_t)p.ld_out_t + ri.grow;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t[(size_t)j * (size_t)p.ld_out_t] = v[j];
+  }
+}
 // F32IO (VAR_TF32): the stored tensors (outputs, saved activations) are fp32 instead of bf16.
 template <int EPI, bool ELU, bool GENERAL_LOSS, bool STAGED, bool DROPOUT = false, bool DUAL = false, bool ACC2 = false, bool F32IO = false>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float* sbias, const float* sloss_w, const RowInfo& ri, int gcol,
@@ -519,13 +537,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = 0.f;
     }
-    if constexpr (F32IO) {
-      if (!p.tf32_exact_store) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
-      }
-      if (st_ok) store_f32x32(out32, v);
-    }
+    if constexpr (F32IO) store_tf32_step(p, ri, gcol, v, st_ok);
     else if constexpr (STAGED) stage_bf16x32(stage_addr, v); else if (st_ok) store_bf16x32_global(out16, v);
     if constexpr (ACC2) {
       // second accumulator (loaded only now: the first one's registers are free again), its bias behind the first bias vector
@@ -556,7 +568,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = 0.f;
     }
-    if constexpr (STAGED) stage_bf16x32(stage_addr, v); else if (st_ok) store_bf16x32_global(out16, v);
+    if constexpr (F32IO) store_tf32_step(p, ri, gcol, v, st_ok);
+    else if constexpr (STAGED) stage_bf16x32(stage_addr, v); else if (st_ok) store_bf16x32_global(out16, v);
   } else if constexpr (EPI == EPI_DGRAD) {
     if constexpr (DUAL) {
       if (ri.zero_row) {
@@ -588,13 +601,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = 0.f;
     }
-    if constexpr (F32IO) {
-      if (!p.tf32_exact_store) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
-      }
-      if (st_ok) store_f32x32(out32, v);
-    }
+    if constexpr (F32IO) store_tf32_step(p, ri, gcol, v, st_ok);
     else if constexpr (STAGED) stage_bf16x32(stage_addr, v); else if (st_ok) store_bf16x32_global(out16, v);
   } else if constexpr (EPI == EPI_BIAS_ADD) {
     float a[32];
@@ -807,7 +814,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   constexpr bool ELU = (VAR & VAR_ELU) != 0, GENERAL_LOSS = (VAR & VAR_GENERAL_LOSS) != 0;
   // VAR_TF32: fp32 operands through kind::tf32 (a 128-byte k-block holds 32 elements, an instruction contracts 8), fp32 stored tensors
   constexpr bool TF32 = (VAR & VAR_TF32) != 0;
-  static_assert(!TF32 || EPI == EPI_BIAS_ACT || EPI == EPI_DGRAD || EPI == EPI_HEAD_OUT || EPI == EPI_F32, "no fp32-storage variant of this epilogue");
+  static_assert(!TF32 || EPI == EPI_BIAS_ACT || EPI == EPI_DGRAD || EPI == EPI_DGRAD_MASK || EPI == EPI_HEAD_OUT || EPI == EPI_F32,
+                "no fp32-storage variant of this epilogue");
   constexpr int BKE = TF32 ? 32 : BK;                  // elements per k-block (TMA coordinates are in elements)
   constexpr bool BF16_OUT = !TF32 && (EPI == EPI_BIAS_ACT || EPI == EPI_HEAD_LOSS || EPI == EPI_DGRAD || EPI == EPI_DGRAD_MASK || EPI == EPI_BIAS_ADD);
   constexpr bool STAGED = (VAR & VAR_STAGED) != 0 && BF16_OUT;
