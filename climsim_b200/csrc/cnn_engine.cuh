@@ -11,6 +11,9 @@
 //
 // Backward: data gradients are convolutions with the tap-flipped, transposed kernels (wd16 copies); weight gradients
 // are one gemm_nt launch per tap with the activation rows shifted by (tap - 1); bias gradients ride in the tap-0 launch.
+// Per residual block, d(block input) = conv1^T(dz1) + conv1x1^T(d_out) is ONE launch over [dz1 taps | d_out] (second A tensor
+// map) whose second output is the previous block's dz2 (cnn_dgrad_dual); the dropout of the forward pass sits in the conv
+// epilogues, and the MMAs over the all-zero tail of a 406 -> 448 channel block are skipped (cnn_tail_k).
 // CSB_F32 parity mode: the same flow on fp32 buffers with sgemm_kernel (tap-aware loaders), no split-K workspace.
 #pragma once
 
