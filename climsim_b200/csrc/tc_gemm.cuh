@@ -11,6 +11,7 @@
 //                    MMAs of tile i+1; 18 warps (issuer, producer, 16 epilogue).  Epilogues: bias+activation->bf16 (+ sign
 //                    mask), head+loss (+dZ), act'-masked dgrad, residual add, fp32; results go registers -> global, or through a
 //                    per-warp staging tile and coalesced stores for the short-contraction launches (VAR_STAGED).
+//                    The same kernel with fp32 operands and tcgen05 kind::tf32 (VAR_TF32) is the CSB_TF32 / CSB_TF32X3 mode.
 //   gemm_nt_kernel   D[M,N] = A[R,M]^T . B[R,N]        both operands MN-major (row index R = batch is the
 //                    contraction).  Weight gradients dW = H^T dZ, bias gradients as column sums of the dZ tiles in flight.
 //                    One 128 x BN (256 x BN per pair) tile per CTA, split over R (blockIdx.y) into fp32 partials that a
@@ -753,6 +754,13 @@ struct TnSmem {
 // both keep rarely used code out of the instruction stream (and the register budget) of the common kernels
 // bit 2 = results staged in shared memory and written with coalesced stores (the launches whose time is the epilogue: K <= 256)
 // bit 3 = in-kernel cycle counters for the micro-benchmark (p.stats); production instantiations carry none of that code
+// bit 4 = inverted dropout behind the activation inside the epilogue (CNN blocks)
+// bit 5 = the last contraction blocks come from a SECOND A tensor map (GemmParams.a2_from_kb): two GEMMs with one accumulator
+// bit 6 = EPI_DGRAD with two outputs: the rounded accumulator itself and its act'-masked version (CNN: d(block input) + dz2)
+// bit 7 = the second A source accumulates into a second TMEM accumulator (conv2 + residual 1x1 forward; opt-in, no gain)
+// bit 8 = skip the MMAs over the all-zero channel tail of a tap's last block (GemmParams.tap_tail_k)
+// bit 9 = fp32 operands through tcgen05 kind::tf32, fp32 stored tensors (CSB_TF32 / CSB_TF32X3), optional transposed second store
+// bit 10 = split contraction: the tile grid is (split, m-group, n-block), fp32 partial products (the TF32 weight gradient)
 constexpr int VAR_ELU = 1, VAR_GENERAL_LOSS = 2, VAR_STAGED = 4, VAR_STATS = 8, VAR_DROPOUT = 16, VAR_A2 = 32, VAR_DUAL = 64, VAR_ACC2 = 128, VAR_KTRIM = 256, VAR_TF32 = 512, VAR_KSPLIT = 1024;
 
 // Tile schedule of the persistent kernel; all three warp roles walk the same sequence.
