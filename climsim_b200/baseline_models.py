@@ -78,6 +78,18 @@ class _EngineModule(torch.nn.Module):
         with torch.no_grad():
             self.flat.copy_(torch.from_numpy(np.ascontiguousarray(flat, dtype=np.float32)))
 
+    def load_keras_h5(self, path: str) -> dict:
+        """Load a Keras ``.h5`` checkpoint of the reference (``ModelCheckpoint`` / ``model.save``: step2_retrain.py:252-262; the shipped
+        ``baseline_models/MLP/model/*.best.h5`` and ``baseline_models/ED/model/ED_ClimSIM_1_3_model.h5``) -- no h5py / TensorFlow
+        needed (``climsim_b200.keras_h5``).  Returns what the file holds (weights, optimizer slots, configs)."""
+        from .keras_h5 import read_keras_h5
+        ck = read_keras_h5(path)
+        fused = getattr(self, "out_lin", None) is not None                  # MLP_v1: the two output Dense layers are one fused layer here
+        flat = MLPEngine.keras_to_flat(ck["weights"], fused_head=fused)
+        assert flat.size == self.flat.numel(), f"{path}: {flat.size} parameters, this module has {self.flat.numel()}"
+        self.load_flat(flat)
+        return ck
+
 
 class MLP(_EngineModule):
     """MLP_v1: ``x -> [Dense(u) -> act]* -> Dense(128) -> act -> concat(Dense(120), relu(Dense(8)))``.

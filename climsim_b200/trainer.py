@@ -187,6 +187,20 @@ class Trainer:
         return float(loss.item()) if return_loss else loss
 
     # ------------------------------------------------------------------------------------------------------------------ model.fit
+    def load_keras_h5(self, path: str, load_optimizer: bool = True, fused_head: bool = True) -> dict:
+        """Continue from one of the reference's Keras ``.h5`` checkpoints (step2_retrain.py:252-262 ``ModelCheckpoint``; the `sw_continue`
+        workflow): parameters, and -- when the file has them and ``load_optimizer`` -- the optimizer's (m, v) slots and iteration
+        count, so that the next ``step`` is the next step of that run.  ``fused_head``: MLP_v1's two output layers are one layer here."""
+        from .keras_h5 import read_keras_h5
+        ck = read_keras_h5(path)
+        to_flat = type(self.engine).keras_to_flat
+        self.engine.set_params_flat(to_flat(ck["weights"], fused_head=fused_head))
+        opt = ck.get("optimizer")
+        if load_optimizer and opt and opt["m"]:
+            self.engine.set_opt_state(to_flat(opt["m"], fused_head=fused_head), to_flat(opt["v"], fused_head=fused_head), opt["iterations"])
+            self.iteration = opt["iterations"]
+        return ck
+
     def save_checkpoint(self, path: str) -> None:
         """Parameters + optimizer state + step counters: the CONTENT of Keras' ``ModelCheckpoint(save_weights_only=False)`` file, as an
         ``.npz`` of flat fp32 blobs in ``get_weights()`` order.  The format is this library's own -- the reference's artefact is a

@@ -273,7 +273,81 @@ def make_online():
     print("wrote online_mlp.npz with", len(out), "arrays; state_dict keys:", list(net.state_dict().keys()))
 
 
+def _json_objects_in(path, min_len=100):
+    """The JSON documents a Keras ``.h5`` carries as HDF5 string attributes (``model_config``, ``training_config``), found by scanning
+    the file for decodable objects -- h5py is not installed here, and the attributes are stored contiguously."""
+    import json
+    blob, out, i, dec = open(path, "rb").read(), [], 0, json.JSONDecoder()
+    while True:
+        i = blob.find(b'{"', i)
+        if i < 0:
+            return out
+        try:
+            obj, end = dec.raw_decode(blob[i:i + 400000].decode("utf-8", errors="ignore"))
+            if isinstance(obj, dict) and end > min_len:
+                out.append(obj)
+                i += end
+                continue
+        except ValueError:
+            pass
+        i += 2
+
+
+def make_keras_configs():
+    """``keras_configs.json``: what the reference's OWN saved Keras models say about the graphs and training set-ups the oracle restates
+    (TensorFlow cannot run here, but the shipped artefacts carry their ``model_config`` / ``training_config``):
+    baseline_models/MLP/model/backup_phase-7_retrained_models_step2_lot-147_trial_0027.best.h5 (MLP_v1, the best HPO trial) and
+    baseline_models/ED/model/ED_ClimSIM_1_3_model.h5 (encoder-decoder)."""
+    import json
+
+    def layers_of(cfg):
+        out = []
+        for layer in cfg["config"]["layers"]:
+            if layer["class_name"] in ("Functional", "Sequential", "Model"):
+                out += layers_of(layer)
+            else:
+                c = layer["config"]
+                out.append({"class": layer["class_name"], "name": c.get("name"), "units": c.get("units"), "activation": c.get("activation"),
+                            "alpha": c.get("alpha"), "use_bias": c.get("use_bias"),
+                            "kernel_initializer": (c.get("kernel_initializer") or {}).get("class_name"),
+                            "bias_initializer": (c.get("bias_initializer") or {}).get("class_name"),
+                            "input_shape": c.get("batch_input_shape"),
+                            "inbound": [n[0] for n in layer["inbound_nodes"][0]] if layer.get("inbound_nodes") else []})
+        return out
+
+    res = {}
+    for key, rel in (("mlp_v1", "baseline_models/MLP/model/backup_phase-7_retrained_models_step2_lot-147_trial_0027.best.h5"),
+                     ("ed", "baseline_models/ED/model/ED_ClimSIM_1_3_model.h5")):
+        objs = _json_objects_in(os.path.join(REF, rel))
+        model = [o for o in objs if "config" in o and "layers" in o.get("config", {})][0]
+        train = [o for o in objs if "optimizer_config" in o][0]
+        res[key] = {"source": rel, "model_name": model["config"]["name"], "layers": layers_of(model),
+                    "loss": train["loss"], "metrics": [m["config"]["fn"] for m in train["metrics"][0]],
+                    "optimizer": train["optimizer_config"]}
+    with open(os.path.join(HERE, "keras_configs.json"), "w") as f:
+        json.dump(res, f, indent=1, sort_keys=True)
+    print("wrote keras_configs.json:", {k: len(v["layers"]) for k, v in res.items()})
+
+
+def make_keras_weights():
+    """``mlp_v1_shipped_f16.npz``: the reference's shipped MLP_v1 (baseline_models/MLP/model/backup_phase-7_retrained_models_step2_lot-147_
+    trial_0027.best.h5, read with climsim_b200.keras_h5) with every array rounded to float16 -- 3.3 MB instead of 7 MB -- so that the
+    GPU box, which has no reference checkout, can run the engines on a REAL trained model (non-zero biases, dead units, the trained
+    weight spectrum) instead of Glorot noise.  Plus per-array fingerprints of the exact fp32 values (sum, abs-sum) that tie the fixture
+    to the file."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from climsim_b200.keras_h5 import read_keras_h5
+    ck = read_keras_h5(os.path.join(REF, "baseline_models/MLP/model/backup_phase-7_retrained_models_step2_lot-147_trial_0027.best.h5"))
+    out = {f"w{i:02d}": w.astype(np.float16) for i, w in enumerate(ck["weights"])}
+    out["fingerprint"] = np.array([[float(w.astype(np.float64).sum()), float(np.abs(w.astype(np.float64)).sum())] for w in ck["weights"]])
+    out["iterations"] = np.array(ck["optimizer"]["iterations"])
+    np.savez_compressed(os.path.join(HERE, "mlp_v1_shipped_f16.npz"), **out)
+    print("wrote mlp_v1_shipped_f16.npz:", sum(w.size for w in ck["weights"]), "parameters")
+
+
 if __name__ == "__main__":
     make_data_utils()
     make_hsr()
     make_online()
+    make_keras_configs()
+    make_keras_weights()

@@ -1,0 +1,83 @@
+"""climsim_b200.keras_h5: the reference's Keras .h5 checkpoints read without h5py / TensorFlow.  The reader is exercised on the
+reference's own shipped files (this container has them under /root/reference; elsewhere these tests skip), and the committed
+fixture derived from one of them is tied back to the file."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import models as M
+
+REF = os.environ.get("CLIMSIM_REFERENCE", "/root/reference")
+MLP_H5 = os.path.join(REF, "baseline_models/MLP/model/backup_phase-7_retrained_models_step2_lot-147_trial_0027.best.h5")
+ED_H5 = os.path.join(REF, "baseline_models/ED/model/ED_ClimSIM_1_3_model.h5")
+needs_ref = pytest.mark.skipif(not (os.path.exists(MLP_H5) and os.path.exists(ED_H5)), reason="reference checkout with the shipped Keras models not present")
+
+
+@needs_ref
+def test_shipped_mlp_v1_checkpoint(golden_dir):
+    from climsim_b200.keras_h5 import read_keras_h5
+    ck = read_keras_h5(MLP_H5)
+    ref = M.MLPRef()
+    # get_weights() order and layouts: kernel (in, out), bias; exactly the oracle's parameter list -- and step1_results.csv's count
+    assert [tuple(w.shape) for w in ck["weights"]] == [tuple(p.shape) for p in ref.params]
+    assert sum(w.size for w in ck["weights"]) == 1753472
+    assert all(w.dtype == np.float32 and np.isfinite(w).all() for w in ck["weights"])
+    # the configs the committed fixture was generated from are the ones in the file
+    cfg = json.load(open(os.path.join(golden_dir, "keras_configs.json")))["mlp_v1"]
+    assert [l["config"]["name"] for l in ck["model_config"]["config"]["layers"]] == [l["name"] for l in cfg["layers"]]
+    assert ck["training_config"]["optimizer_config"] == cfg["optimizer"]
+    # optimizer: RectifiedAdam slots for every weight, in the same order, second moments non-negative
+    opt = ck["optimizer"]
+    assert opt["name"] == "RectifiedAdam" and opt["iterations"] == 6570 and len(opt["m"]) == len(opt["v"]) == 16
+    assert all(m.shape == w.shape == v.shape and (v >= 0).all() for m, v, w in zip(opt["m"], opt["v"], ck["weights"]))
+    # the oracle runs the reference's trained model: a trained emulator of normalised targets predicts O(1) numbers, and ReLU on its 8 scalars
+    with torch.no_grad():
+        for p, w in zip(ref.params, ck["weights"]):
+            p.copy_(torch.from_numpy(w))
+        g = torch.Generator().manual_seed(0)
+        out = ref(torch.rand(64, 124, generator=g))
+    assert torch.isfinite(out).all() and out.abs().max() < 1e3 and (out[:, 120:] >= 0).all()
+    # the GPU fixture is this file rounded to float16
+    fx = np.load(os.path.join(golden_dir, "mlp_v1_shipped_f16.npz"))
+    for i, w in enumerate(ck["weights"]):
+        np.testing.assert_array_equal(fx[f"w{i:02d}"], w.astype(np.float16))
+        np.testing.assert_allclose(fx["fingerprint"][i], [w.astype(np.float64).sum(), np.abs(w.astype(np.float64)).sum()], rtol=1e-12)
+    assert int(fx["iterations"]) == opt["iterations"]
+
+
+@needs_ref
+def test_shipped_ed_checkpoint():
+    from climsim_b200.keras_h5 import read_keras_h5
+    ck = read_keras_h5(ED_H5)
+    ref = M.EDRef()
+    assert [tuple(w.shape) for w in ck["weights"]] == [tuple(p.shape) for p in ref.params]      # nested encoder / decoder flattened in model order
+    assert sum(w.size for w in ck["weights"]) == ref.num_parameters() == 831879
+    assert ck["optimizer"]["name"] == "Adam" and len(ck["optimizer"]["m"]) == 28 and ck["optimizer"]["iterations"] > 0
+    with torch.no_grad():
+        for p, w in zip(ref.params, ck["weights"]):
+            p.copy_(torch.from_numpy(w))
+        out = ref(torch.rand(32, 124, generator=torch.Generator().manual_seed(1)))
+    assert torch.isfinite(out).all() and (out > -1.0).all()                                     # ELU output layer
+
+
+def test_reader_rejects_what_it_does_not_understand(tmp_path):
+    from climsim_b200.keras_h5 import read_keras_h5
+    p = tmp_path / "not_hdf5.h5"
+    p.write_bytes(b"PK\x03\x04 a zip, not HDF5")
+    with pytest.raises(ValueError, match="not an HDF5 file"):
+        read_keras_h5(str(p))
+    q = tmp_path / "v2.h5"
+    q.write_bytes(b"\x89HDF\r\n\x1a\n" + bytes([2]) + bytes(64))
+    with pytest.raises(ValueError, match="version-0 superblocks"):
+        read_keras_h5(str(q))
+
+
+def test_fixture_is_self_consistent(golden_dir):
+    """Runs everywhere: the committed float16 copy of the shipped MLP_v1 has the oracle's shapes and 1 753 472 parameters."""
+    fx = np.load(os.path.join(golden_dir, "mlp_v1_shipped_f16.npz"))
+    ws = [fx[f"w{i:02d}"] for i in range(16)]
+    assert [tuple(w.shape) for w in ws] == [tuple(p.shape) for p in M.MLPRef().params] and sum(w.size for w in ws) == 1753472
+    assert all(w.dtype == np.float16 for w in ws) and all(np.abs(b).max() > 0 for b in ws[1::2])      # trained biases are not Keras' zeros

@@ -7,6 +7,8 @@ Tolerances (north_star: "<= 1e-5 relative fp32"):
     the same bf16 operand rounding (``emulate_bf16``), within 3e-2 * max|ref| of the fp32 oracle; gradients within
     3e-2 relative L2 of the fp32 oracle.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -666,3 +668,49 @@ def test_tf32x3_mode_is_fp32_class(units, B):
     p2 = eng.forward(x.cuda()).cpu()
     assert abs(M.mse(y, p2).item() - eng.train_step(x.cuda(), y.cuda()).item()) <= 1e-5 * got_loss
     eng.close()
+
+
+def test_engines_on_the_reference_shipped_mlp_v1_model():
+    """The reference's own trained MLP_v1 (baseline_models/MLP/model/backup_phase-7_retrained_models_step2_lot-147_trial_0027.best.h5,
+    read without h5py by climsim_b200.keras_h5; the fixture is that file rounded to float16, tests/test_keras_h5_cpu.py ties the two)
+    instead of Glorot noise: trained weight spectrum, non-zero biases, saturated and dead units.  Forward and training step of every
+    arithmetic mode against the oracle running the same model; through the MLP module's Keras-weights entry."""
+    from climsim_b200 import MLPEngine
+    from climsim_b200.baseline_models import MLP
+    fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mlp_v1_shipped_f16.npz"))
+    weights = [fx[f"w{i:02d}"].astype(np.float32) for i in range(16)]
+    ref = M.MLPRef()
+    with torch.no_grad():
+        for p, w in zip(ref.params, weights):
+            p.copy_(torch.from_numpy(w))
+    B = 2048
+    x, y = _batch(B, 41)
+    xk, yk = _drop_kink_rows(ref, x, y)
+    want = ref(xk).detach().numpy()
+    loss = M.mse(yk, ref(xk))
+    loss.backward()
+    g_ref = _flat([p.grad for p in ref.params])
+    emu_loss, emu_grads = ref.manual_train_step(xk, yk, emulate_bf16=True)
+    flat = MLPEngine.keras_to_flat(weights)
+    for dtype in ("fp32", "tf32x3", "tf32", "bf16"):
+        eng = MLPEngine.mlp_v1(dtype=dtype, max_batch=B)
+        eng.set_params_flat(flat)
+        e_pred = _relmax(eng.forward(xk.cuda()).cpu().numpy(), want)
+        got_loss = eng.train_step(xk.cuda(), yk.cuda()).item()
+        e_loss = abs(got_loss - loss.item()) / abs(loss.item())
+        g_got = eng.get_grads_flat()
+        e_g = _per_tensor(eng, g_got, g_ref, _rel_l2)
+        print(f"shipped MLP_v1 [{dtype}]: predictions {e_pred:.2e}, loss {e_loss:.2e}, worst gradient rel-L2 {e_g:.2e} vs the fp32 oracle")
+        # measured on a B200 (predictions / loss / worst gradient tensor): fp32 5.6e-7 / 0 / 2.7e-5, tf32x3 2.2e-5 / 4.5e-5 / 6.7e-4,
+        # tf32 7.9e-4 / 1.1e-5 / 6.3e-3, bf16 4.2e-3 / 2.0e-3 / 2.3e-2 -- the arithmetic is deterministic, the bounds are ~3x those
+        tol_pred, tol_loss, tol_g = {"fp32": (1e-5, 1e-5, 1e-4), "tf32x3": (1e-4, 2e-4, 3e-3), "tf32": (3e-3, 1e-4, 2e-2), "bf16": (2e-2, 1e-2, 8e-2)}[dtype]
+        assert e_pred <= tol_pred and e_loss <= tol_loss and e_g <= tol_g
+        if dtype == "bf16":      # and tightly against the oracle with the engine's rounding points
+            e_emu = _per_tensor(eng, g_got, _flat(emu_grads), _rel_l2)
+            print(f"shipped MLP_v1 [bf16] vs the bf16-emulating oracle: loss {abs(got_loss - emu_loss.item()) / abs(emu_loss.item()):.2e}, gradients {e_emu:.2e}")
+            assert abs(got_loss - emu_loss.item()) <= 1e-4 * abs(emu_loss.item()) and e_emu <= 5e-3      # measured 8.3e-6 / 9.0e-4
+        eng.close()
+    net = MLP(dtype="fp32", max_batch=B)
+    net.load_keras_weights(weights)
+    with torch.no_grad():
+        assert _relmax(net(xk.cuda()).cpu().numpy(), want) <= 1e-5

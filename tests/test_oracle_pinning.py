@@ -316,3 +316,63 @@ def test_dropout_masks_of_ones_change_nothing_and_scale_like_torch_dropout():
     assert torch.allclose(got, want)
     full = h(x, masks=[keep / 0.7, torch.ones(7, 24)])
     assert torch.allclose(full, h.final_linear(torch.relu(h.linear1(want))), atol=1e-6)
+
+
+def test_graphs_and_training_setups_match_the_reference_saved_keras_models(golden_dir):
+    """TensorFlow cannot run here, but the reference SHIPS its trained Keras models, and their ``.h5`` files carry ``model_config`` and
+    ``training_config`` (tests/golden/make_golden.py::make_keras_configs reads the JSON out of the files -> keras_configs.json):
+    baseline_models/MLP/model/backup_phase-7_retrained_models_step2_lot-147_trial_0027.best.h5 and
+    baseline_models/ED/model/ED_ClimSIM_1_3_model.h5.  The oracle's graphs, the engine presets and the optimizer / metric / schedule
+    defaults are held to what those artefacts say -- the structure of the 'parity unpinned' Keras models is pinned by the
+    reference's own files, not only by reading its scripts."""
+    import inspect
+    import json
+    from climsim_b200 import trainer as T
+    cfg = json.load(open(os.path.join(golden_dir, "keras_configs.json")))
+
+    # ---- MLP_v1: Dense(768) LeakyReLU(0.15) ... Dense(128) LeakyReLU -> Dense(120, linear) || Dense(8, relu) -> Concatenate
+    mlp = cfg["mlp_v1"]
+    layers = mlp["layers"]
+    assert layers[0]["class"] == "InputLayer" and layers[0]["input_shape"] == [None, 124]
+    dense = [l for l in layers if l["class"] == "Dense"]
+    leaky = [l for l in layers if l["class"] == "LeakyReLU"]
+    ref = M.MLPRef()                                                             # the oracle's defaults = the shipped best trial
+    assert [d["units"] for d in dense[:-2]] == list(ref.units) + [ref.out_lin + ref.out_relu] == [768, 640, 512, 640, 640, 128]
+    assert all(d["activation"] == "linear" and d["use_bias"] for d in dense[:-2]) and len(leaky) == len(dense) - 2
+    assert ref.act == "leakyrelu" and all(abs(l["alpha"] - ref.alpha) < 1e-7 for l in leaky)       # 0.15 stored as float32
+    # every hidden Dense feeds its own LeakyReLU, which feeds the next Dense: a plain chain
+    for i, d in enumerate(dense[1:-2], start=1):
+        assert d["inbound"] == [leaky[i - 1]["name"]] and leaky[i]["inbound"] == [d["name"]]
+    lin, rel, cat = dense[-2], dense[-1], layers[-1]
+    assert (lin["units"], lin["activation"], rel["units"], rel["activation"]) == (ref.out_lin, "linear", ref.out_relu, "relu") == (120, "linear", 8, "relu")
+    assert lin["inbound"] == rel["inbound"] == [leaky[-1]["name"]]              # both heads read the last hidden activation
+    assert cat["class"] == "Concatenate" and cat["inbound"] == [lin["name"], rel["name"]]          # [120 linear | 8 relu], in this order
+    assert all(d["kernel_initializer"] == "GlorotUniform" and d["bias_initializer"] == "Zeros" for d in dense)   # trainer.glorot_uniform_flat
+    assert ref.num_parameters() == 1753472
+    # training set-up: loss 'mse', metrics mse / mae / accuracy (= categorical accuracy: argmax agreement, csb_batch_metrics)
+    assert mlp["loss"] == "mse" and mlp["metrics"] == ["mean_squared_error", "mean_absolute_error", "categorical_accuracy"]
+    opt = mlp["optimizer"]
+    assert opt["class_name"] == "Addons>RectifiedAdam"                           # the best trial's optimizer: the engine's CSB_OPT_RADAM rule
+    oc = opt["config"]
+    sig = inspect.signature(M.radam_step).parameters
+    assert abs(oc["beta_1"] - sig["beta1"].default) < 1e-7 and abs(oc["beta_2"] - sig["beta2"].default) < 1e-7
+    assert oc["epsilon"] == sig["eps"].default == 1e-7 and oc["sma_threshold"] == sig["sma_threshold"].default == 5.0
+    assert oc["total_steps"] == 0 and oc["weight_decay"] == 0.0 and not oc["amsgrad"]          # no warm-up schedule inside the optimizer
+    clr = oc["learning_rate"]
+    assert clr["class_name"] == "Addons>CyclicalLearningRate" and clr["config"]["scale_mode"] == "cycle"
+    d = inspect.signature(T.cyclical_lr).parameters
+    assert (clr["config"]["initial_learning_rate"], clr["config"]["maximal_learning_rate"]) == (d["initial_lr"].default, d["max_lr"].default) == (2.5e-4, 2.5e-3)
+    assert inspect.signature(M.keras_adam_step).parameters["eps"].default == 1e-7
+
+    # ---- ED: 124 -> 463 -> 463 -> 231 -> 115 -> 57 -> 28 -> 5 | 28 -> 57 -> 115 -> 231 -> 463 -> 463 -> 128 (ReLU, ELU output)
+    ed = cfg["ed"]
+    dense = [l for l in ed["layers"] if l["class"] == "Dense"]
+    assert [d["units"] for d in dense] == M.ed_widths() == [463, 463, 231, 115, 57, 28, 5, 28, 57, 115, 231, 463, 463, 128]
+    assert [d["activation"] for d in dense] == ["relu"] * 13 + ["elu"]
+    assert M.EDRef().num_parameters() == sum(k * n + n for k, n in zip([124] + M.ed_widths()[:-1], M.ed_widths()))
+    assert ed["loss"] == "mean_squared_error" and ed["metrics"] == mlp["metrics"]
+    eo = ed["optimizer"]
+    assert eo["class_name"] == "Adam" and eo["config"]["epsilon"] == 1e-7 and not eo["config"]["amsgrad"]
+    # the saved learning rate is where the divide-by-5-every-7-epochs schedule stands at the end of the 40-epoch run: 1e-4 / 5^5
+    assert abs(eo["config"]["learning_rate"] - T.ed_step_lr(39)) <= 1e-6 * T.ed_step_lr(39)
+    assert abs(T.ed_step_lr(39) - 1e-4 / 3125) < 1e-15 and T.ed_step_lr(0) == 1e-4 and abs(T.ed_step_lr(7) - 2e-5) < 1e-12
