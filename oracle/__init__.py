@@ -18,7 +18,12 @@ Parity pinning status (see DESIGN.md "Oracle"):
   builds these with tensorflow 2.11.1 / keras 2.11.0 / tensorflow-addons 0.19.0 (MLP: baseline_models/MLP/env/
   environment.yml:119,287,337) and tensorflow 2.10.0 / tfa 0.18.0 (CNN, ED), none of which is installable here, and
   the reference ships no golden outputs.  They are restated from the published Keras semantics and anchored on the
-  reference's call sites; the only reference-held known answers they are pinned to are the parameter count
-  1 753 472 (step1_results.csv, lot-147 trial_0027), the FLOP count 3 503 488 (FLOP_calculation.ipynb cells 5-6)
-  and the CNN/ED/HSR parameter counts derivable from the reference's layer lists.
+  reference's call sites; the reference-held known answers they are pinned to are the parameter count
+  1 753 472 (step1_results.csv, lot-147 trial_0027), the FLOP count 3 503 488 (FLOP_calculation.ipynb cells 5-6),
+  the CNN/ED/HSR parameter counts derivable from the reference's layer lists, and -- STRUCTURE PINNED -- the
+  ``model_config`` / ``training_config`` / weight shapes of the reference's own shipped Keras models
+  (baseline_models/MLP/model/*.best.h5, baseline_models/ED/model/ED_ClimSIM_1_3_model.h5, read without h5py) and the
+  layer inventory of baseline_models/CNN/model/saved_model.pb: ``tests/golden/keras_configs.json``,
+  ``tests/test_oracle_pinning.py::test_graphs_and_training_setups_match_the_reference_saved_keras_models``,
+  ``tests/test_keras_h5_cpu.py``.  What a TensorFlow run would OUTPUT stays unpinned.
 """

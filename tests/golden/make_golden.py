@@ -324,6 +324,18 @@ def make_keras_configs():
         res[key] = {"source": rel, "model_name": model["config"]["name"], "layers": layers_of(model),
                     "loss": train["loss"], "metrics": [m["config"]["fn"] for m in train["metrics"][0]],
                     "optimizer": train["optimizer_config"]}
+    # the CNN ships as a TensorFlow SavedModel graph without its variables (baseline_models/CNN/model/saved_model.pb): the layer
+    # inventory is still in the node names (conv1d .. conv1d_36/..., dropout_23/..., add_11/...)
+    import re
+    pb = open(os.path.join(REF, "baseline_models/CNN/model/saved_model.pb"), "rb").read()
+
+    def layer_indices(base):
+        return sorted({int(m.group(1)) if m.group(1) else 0 for m in re.finditer(rb"(?<![a-z_])" + base.encode() + rb"(?:_(\d{1,3}))?/", pb)})
+
+    res["cnn"] = {"source": "baseline_models/CNN/model/saved_model.pb",
+                  "layers": {k: len(layer_indices(k)) for k in ("conv1d", "dense", "dropout", "activation", "add", "concatenate")},
+                  "padding": sorted({m.decode() for m in re.findall(rb"SAME|VALID", pb)}),
+                  "padding_same_count": len(re.findall(rb"SAME", pb)), "has_elu": b"Elu" in pb, "has_relu": b"Relu" in pb}
     with open(os.path.join(HERE, "keras_configs.json"), "w") as f:
         json.dump(res, f, indent=1, sort_keys=True)
     print("wrote keras_configs.json:", {k: len(v["layers"]) for k, v in res.items()})

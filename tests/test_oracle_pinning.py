@@ -376,3 +376,13 @@ def test_graphs_and_training_setups_match_the_reference_saved_keras_models(golde
     # the saved learning rate is where the divide-by-5-every-7-epochs schedule stands at the end of the 40-epoch run: 1e-4 / 5^5
     assert abs(eo["config"]["learning_rate"] - T.ed_step_lr(39)) <= 1e-6 * T.ed_step_lr(39)
     assert abs(T.ed_step_lr(39) - 1e-4 / 3125) < 1e-15 and T.ed_step_lr(0) == 1e-4 and abs(T.ed_step_lr(7) - 2e-5) < 1e-12
+
+    # ---- CNN: the shipped SavedModel graph (no variables) still lists its layers: 12 residual blocks of
+    # [Conv1D, Activation, Dropout, Conv1D, Activation, Dropout, Conv1D(1x1 on the block input), Add] + the output Conv1D + two Dense heads
+    cnn = cfg["cnn"]
+    ref = M.CNNRef()
+    depth = ref.depth
+    assert depth == 12
+    assert cnn["layers"] == {"conv1d": 3 * depth + 1, "dense": 2, "dropout": 2 * depth, "activation": 2 * depth, "add": depth, "concatenate": 1}
+    assert len(ref.params) == 2 * (cnn["layers"]["conv1d"] + cnn["layers"]["dense"])          # (kernel, bias) per Conv1D / Dense
+    assert cnn["has_relu"] and cnn["has_elu"] and "SAME" in cnn["padding"] and cnn["padding_same_count"] >= cnn["layers"]["conv1d"]
