@@ -81,3 +81,41 @@ def test_fixture_is_self_consistent(golden_dir):
     ws = [fx[f"w{i:02d}"] for i in range(16)]
     assert [tuple(w.shape) for w in ws] == [tuple(p.shape) for p in M.MLPRef().params] and sum(w.size for w in ws) == 1753472
     assert all(w.dtype == np.float16 for w in ws) and all(np.abs(b).max() > 0 for b in ws[1::2])      # trained biases are not Keras' zeros
+
+
+@needs_ref
+def test_trainer_load_keras_h5_hands_the_engine_parameters_and_optimizer_state():
+    """Trainer.load_keras_h5 on a recording stand-in for the engine: the flat blobs it passes are the file's arrays in the engine's
+    layout (the two output Dense layers fused column-wise, for the slots as for the weights), and the iteration count carries over."""
+    from climsim_b200 import MLPEngine
+    from climsim_b200.keras_h5 import read_keras_h5
+    from climsim_b200.trainer import Trainer
+
+    class Recorder:
+        keras_to_flat = staticmethod(MLPEngine.keras_to_flat)
+        dtype = "fp32"
+
+        def __init__(self):
+            self.calls = {}
+
+        def set_params_flat(self, flat):
+            self.calls["params"] = flat
+
+        def set_opt_state(self, m, v, step):
+            self.calls["opt"] = (m, v, step)
+
+    tr = Trainer.__new__(Trainer)                      # no device, no process group: only the method under test
+    tr.engine, tr.iteration = Recorder(), 0
+    ck = tr.load_keras_h5(MLP_H5)
+    want = read_keras_h5(MLP_H5)
+    flat = tr.engine.calls["params"]
+    assert flat.size == 1753472
+    head_w = np.concatenate([want["weights"][-4], want["weights"][-2]], axis=1)              # [W_lin | W_relu], (128, 128)
+    n_head = head_w.size + 128
+    np.testing.assert_array_equal(flat[-n_head:-128].reshape(128, 128), head_w)
+    np.testing.assert_array_equal(flat[-128:], np.concatenate([want["weights"][-3], want["weights"][-1]]))
+    np.testing.assert_array_equal(flat[:124 * 768].reshape(124, 768), want["weights"][0])
+    m, v, step = tr.engine.calls["opt"]
+    assert step == tr.iteration == 6570 and m.size == v.size == flat.size and (v >= 0).all()
+    np.testing.assert_array_equal(m[:124 * 768].reshape(124, 768), want["optimizer"]["m"][0])
+    assert ck["optimizer"]["name"] == "RectifiedAdam"
