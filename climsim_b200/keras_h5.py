@@ -11,6 +11,7 @@ the part of HDF5 such a file uses -- version-0 superblock, version-1 object head
 take, plus the optimizer's slot variables in the same order -- so the reference's shipped model (and a run's ``checkpoint_best.h5``)
 loads into the engine, optimizer state included."""
 import json
+import mmap
 import struct
 from typing import Dict, Iterator, List, Optional, Tuple
 
@@ -21,8 +22,12 @@ _SIG = b"\x89HDF\r\n\x1a\n"
 
 class _H5:
     def __init__(self, path: str):
-        with open(path, "rb") as f:
-            self.b = f.read()
+        self.path = path
+        with open(path, "rb") as f:                                 # mapped, not read: the column files are tens of GB
+            try:
+                self.b = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+            except ValueError:                                      # empty file
+                self.b = b""
         if self.b[:8] != _SIG:
             raise ValueError(f"{path}: not an HDF5 file")
         if self.b[8] != 0 or self.b[13] != 8 or self.b[14] != 8:
@@ -54,7 +59,7 @@ class _H5:
         if self.b[heap:heap + 4] != b"HEAP":
             raise ValueError("bad local heap")
         start = struct.unpack_from("<Q", self.b, heap + 24)[0] + offset
-        return self.b[start:self.b.index(b"\x00", start)].decode()
+        return self.b[start:self.b.find(b"\x00", start)].decode()
 
     def _children(self, btree: int, heap: int) -> List[Tuple[str, int]]:
         b, out = self.b, []
@@ -78,14 +83,20 @@ class _H5:
         return out
 
     def datasets(self, hdr: Optional[int] = None, prefix: str = "") -> Iterator[Tuple[str, np.ndarray]]:
-        """(path, array) of every fp32 / int64 dataset below the object at ``hdr`` (default: the root group)."""
+        """(path, array copy) of every contiguous numeric dataset below the object at ``hdr`` (default: the root group)."""
+        for name, shape, np_dtype, addr in self.dataset_infos(hdr, prefix):
+            n = int(np.prod(shape)) if shape else 1
+            yield name, np.frombuffer(self.b, dtype=np_dtype, count=n, offset=addr).reshape(shape).copy()
+
+    def dataset_infos(self, hdr: Optional[int] = None, prefix: str = "") -> Iterator[Tuple[str, tuple, str, int]]:
+        """(path, shape, numpy dtype string, byte offset of the contiguous data) of every such dataset."""
         hdr = self.root if hdr is None else hdr
         msgs = self._messages(hdr)
         sym = [m for m in msgs if m[0] == 0x11]
         if sym:
             btree, heap = struct.unpack_from("<QQ", self.b, sym[0][1])
             for name, child in self._children(btree, heap):
-                yield from self.datasets(child, prefix + "/" + name)
+                yield from self.dataset_infos(child, prefix + "/" + name)
             return
         shape = dtype = addr = None
         for mtype, body, _ in msgs:
@@ -101,8 +112,7 @@ class _H5:
         np_dtype = {(1, 4): "<f4", (0, 8): "<i8", (1, 8): "<f8", (0, 4): "<i4"}.get(dtype)
         if np_dtype is None:
             return
-        n = int(np.prod(shape)) if shape else 1
-        yield prefix, np.frombuffer(self.b, dtype=np_dtype, count=n, offset=addr).reshape(shape).copy()
+        yield prefix, tuple(int(d) for d in shape), np_dtype, int(addr)
 
     def json_attributes(self, min_len: int = 100) -> List[dict]:
         """The JSON documents stored as string attributes (Keras: ``model_config``, ``training_config``)."""
@@ -169,3 +179,15 @@ def read_keras_h5(path: str) -> Dict[str, object]:
             m, v = [], []                                          # an optimizer without (m, v) slots
         res["optimizer"] = {"name": name, "iterations": int(it[0]) if it else 0, "m": m, "v": v}
     return res
+
+
+def open_h5_dataset(path: str, name: str = "data") -> np.memmap:
+    """A read-only ``np.memmap`` over one contiguous dataset of an HDF5 file -- the reference writes its column arrays this way
+    (climsim_utils/data_utils.py:912-913, 924-925: ``h5py.File(..., 'w').create_dataset('data', data=npy_input)``) and reads them row by
+    row through h5py (online_testing/baseline_models/MLP_v2rh/training/climsim_datapip_h5.py:104-126).  The mapping behaves like
+    ``np.load(..., mmap_mode='r')`` of the ``.npy`` twin, so the column streams take either file."""
+    want = "/" + name.strip("/")
+    for ds, shape, np_dtype, addr in _H5(path).dataset_infos():
+        if ds == want:
+            return np.memmap(path, dtype=np_dtype, mode="r", offset=addr, shape=shape)
+    raise KeyError(f"{path}: no contiguous numeric dataset named {name!r}")

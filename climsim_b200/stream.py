@@ -88,6 +88,15 @@ class StreamPlan:
                 yield start + perm[off:off + n]
 
 
+def open_column_array(path: str, dataset: str = "data"):
+    """``<split>_input.npy`` / ``_target.npy`` (data_utils.py:884-921) or their ``.h5`` twins (data_utils.py:908-925: one dataset
+    ``'data'``) as a read-only memory map of shape (N, F)."""
+    if str(path).lower().endswith((".h5", ".hdf5")):
+        from .keras_h5 import open_h5_dataset
+        return open_h5_dataset(path, dataset)
+    return np.load(path, mmap_mode="r")
+
+
 class NpyColumnStream:
     """Iterate ``(x, y)`` CUDA tensors of ``batch_size`` columns over ``<split>_input.npy`` / ``<split>_target.npy``.
 
@@ -100,8 +109,8 @@ class NpyColumnStream:
         import torch
         from . import _lib
         self.torch, self._lib, self.lib = torch, _lib, _lib.load()           # no CPU fallback: raises without the CUDA library
-        self.x_all = np.load(input_path, mmap_mode="r")
-        self.y_all = np.load(target_path, mmap_mode="r")
+        self.x_all = open_column_array(input_path)
+        self.y_all = open_column_array(target_path)
         assert self.x_all.ndim == 2 and self.y_all.ndim == 2 and self.x_all.shape[0] == self.y_all.shape[0], \
             "input and target arrays must be (N, F_in) and (N, F_out) with the same N"
         self.plan = StreamPlan(self.x_all.shape[0], batch_size, window, shuffle, seed, rank, world, drop_last)
@@ -208,8 +217,8 @@ class ResidentColumnStream:
         import torch
         from . import _lib
         self.torch, self._lib, self.lib = torch, _lib, _lib.load()
-        x_all = np.load(input_path, mmap_mode="r")
-        y_all = np.load(target_path, mmap_mode="r")
+        x_all = open_column_array(input_path)
+        y_all = open_column_array(target_path)
         assert x_all.ndim == 2 and y_all.ndim == 2 and x_all.shape[0] == y_all.shape[0], \
             "input and target arrays must be (N, F_in) and (N, F_out) with the same N"
         probe = StreamPlan(x_all.shape[0], batch_size, batch_size, shuffle, seed, rank, world, drop_last)

@@ -119,3 +119,29 @@ def test_trainer_load_keras_h5_hands_the_engine_parameters_and_optimizer_state()
     assert step == tr.iteration == 6570 and m.size == v.size == flat.size and (v >= 0).all()
     np.testing.assert_array_equal(m[:124 * 768].reshape(124, 768), want["optimizer"]["m"][0])
     assert ck["optimizer"]["name"] == "RectifiedAdam"
+
+
+@needs_ref
+def test_h5_datasets_open_as_memory_maps_like_their_npy_twins(tmp_path):
+    """The reference also writes its column arrays as HDF5 (climsim_utils/data_utils.py:908-925: one contiguous dataset 'data' per
+    file) and reads them row by row with h5py (climsim_datapip_h5.py:104-126).  ``open_h5_dataset`` maps such a dataset read-only at
+    its file offset -- exercised here on datasets h5py itself wrote (the shipped Keras file: 2-D fp32 arrays inside a group, the
+    same object-header / dataspace / contiguous-layout structure as a root-level 'data'), row slices and fancy indexing included --
+    and ``open_column_array`` is the one place the column streams open their files: ``.npy`` and ``.h5`` give the same array."""
+    from climsim_b200.keras_h5 import open_h5_dataset, read_keras_h5
+    from climsim_b200.stream import open_column_array
+    want = read_keras_h5(MLP_H5)["weights"]
+    k1 = open_h5_dataset(MLP_H5, "model_weights/dense_1/dense_1/kernel:0")
+    assert isinstance(k1, np.memmap) and k1.shape == (768, 640) and k1.dtype == np.float32 and not k1.flags.writeable
+    np.testing.assert_array_equal(k1, want[2])
+    np.testing.assert_array_equal(k1[100:164], want[2][100:164])                       # a window of rows, as the stream reads
+    np.testing.assert_array_equal(k1[[5, 700, 33]], want[2][[5, 700, 33]])
+    with pytest.raises(KeyError):
+        open_h5_dataset(MLP_H5, "data")
+    # the dispatch: the same columns through a .npy file and through the .h5 dataset
+    npy = tmp_path / "cols_input.npy"
+    np.save(npy, want[2])
+    a = open_column_array(str(npy))
+    b = open_column_array(MLP_H5, dataset="model_weights/dense_1/dense_1/kernel:0")
+    assert a.shape == b.shape and a.dtype == b.dtype
+    np.testing.assert_array_equal(np.asarray(a), np.asarray(b))
