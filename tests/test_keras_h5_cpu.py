@@ -145,3 +145,29 @@ def test_h5_datasets_open_as_memory_maps_like_their_npy_twins(tmp_path):
     b = open_column_array(MLP_H5, dataset="model_weights/dense_1/dense_1/kernel:0")
     assert a.shape == b.shape and a.dtype == b.dtype
     np.testing.assert_array_equal(np.asarray(a), np.asarray(b))
+
+
+@needs_ref
+def test_module_load_keras_h5_layouts_for_mlp_v1_and_ed():
+    """``MLP.load_keras_h5`` / ``ED.load_keras_h5`` (one method of their common base) on stand-ins that only record the flat blob:
+    MLP_v1 fuses the two output Dense layers column-wise, the encoder-decoder keeps Keras' layer list as it is."""
+    import types
+    from climsim_b200.baseline_models import _EngineModule
+    from climsim_b200.keras_h5 import read_keras_h5
+
+    def stand_in(n, **extra):
+        box = types.SimpleNamespace(flat=torch.zeros(n), got=None, **extra)
+        box.load_flat = lambda flat: setattr(box, "got", np.asarray(flat))
+        return box
+
+    mlp = stand_in(1753472, out_lin=120)
+    ck = _EngineModule.load_keras_h5(mlp, MLP_H5)
+    w = read_keras_h5(MLP_H5)["weights"]
+    assert mlp.got.size == 1753472 and ck["optimizer"]["iterations"] == 6570
+    np.testing.assert_array_equal(mlp.got[-128:], np.concatenate([w[-3], w[-1]]))              # fused bias [b_lin | b_relu]
+    ed = stand_in(831879)
+    _EngineModule.load_keras_h5(ed, ED_H5)
+    we = read_keras_h5(ED_H5)["weights"]
+    np.testing.assert_array_equal(ed.got, np.concatenate([a.reshape(-1) for a in we]))
+    with pytest.raises(AssertionError, match="parameters"):
+        _EngineModule.load_keras_h5(stand_in(10), ED_H5)
